@@ -1,0 +1,276 @@
+/*
+ * abr.h — C ABI of the B200 batched rigid-body rollout engine ("abr").
+ *
+ * This is the drop-in boundary for the one hot path ambersim drives: thousands of
+ * independent mjx.step rollouts. The reference has no FFI layer of its own; the seam this
+ * ABI replaces is the Python call boundary into MJX (paths relative to the reference tree):
+ *
+ *   mjx.device_put(mj.MjModel) -> mjx.Model     ambersim/utils/io_utils.py:225, ambersim/rl/base.py:52
+ *   mjx.make_data(mjx.Model)   -> mjx.Data      ambersim/utils/io_utils.py:226, ambersim/trajopt/shooting.py:34
+ *   mjx.forward(Model, Data)   -> Data          ambersim/trajopt/shooting.py:36, ambersim/rl/base.py:85
+ *   mjx.step(Model, Data)      -> Data          ambersim/trajopt/shooting.py:41, ambersim/rl/base.py:93
+ *
+ * and the ambersim-level loops built on it:
+ *
+ *   shoot(m, x0, us) -> xs                               ambersim/trajopt/shooting.py:22-48
+ *   VanillaPredictiveSampler.optimize(params)            ambersim/trajopt/shooting.py:119-157
+ *   StaticGoalQuadraticCost.cost(xs, us, params)         ambersim/trajopt/cost.py:62-85
+ *   MjxEnv.pipeline_init / pipeline_step                 ambersim/rl/base.py:81-96
+ *
+ * Conventions
+ *   - every function is extern "C", returns int (0 = ABR_OK, <0 = error code), never throws;
+ *     the message of the last error on the calling thread is abr_last_error().
+ *   - all arrays are row-major float32 / int32. Field names of AbrModelHost follow mjx.Model.
+ *   - "_dev" entry points take DEVICE pointers and a cudaStream_t (passed as void*); they are
+ *     stream-ordered and never synchronise. "_host" entry points take HOST pointers, stage the
+ *     copies on the handle's own stream and return after the result is in the host buffers.
+ *   - state layout x = [qpos(nq); qvel(nv)]  (shooting.py:35,42), nx = nq + nv.
+ *   - there is NO CPU fallback: without a CUDA device every compute call returns ABR_ENODEVICE.
+ */
+#ifndef ABR_H_
+#define ABR_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ABR_VERSION 100
+
+/* error codes */
+#define ABR_OK 0
+#define ABR_EINVAL (-1)       /* bad argument (null pointer, negative size, shape mismatch)      */
+#define ABR_EUNSUPPORTED (-2) /* model feature outside the engine (mirrors MJX NotImplementedError,
+                                 io_utils.py:228-241): elliptic cone, ball joint, mesh pair, ...   */
+#define ABR_ECUDA (-3)        /* CUDA runtime error, text in abr_last_error()                    */
+#define ABR_ENODEVICE (-4)    /* no CUDA device: the engine has no CPU path                      */
+#define ABR_ECAPACITY (-5)    /* model larger than the compiled kernel limits                    */
+
+/* enums (values = MuJoCo's) */
+enum { ABR_JNT_FREE = 0, ABR_JNT_BALL = 1, ABR_JNT_SLIDE = 2, ABR_JNT_HINGE = 3 };
+enum { ABR_GEOM_PLANE = 0, ABR_GEOM_SPHERE = 2, ABR_GEOM_CAPSULE = 3 };
+enum { ABR_INT_EULER = 0, ABR_INT_RK4 = 1 };
+enum { ABR_SOLVER_CG = 1, ABR_SOLVER_NEWTON = 2 };
+enum { ABR_EQ_JOINT = 2 };
+enum { ABR_GAIN_FIXED = 0, ABR_GAIN_AFFINE = 1 };
+enum { ABR_BIAS_NONE = 0, ABR_BIAS_AFFINE = 1 };
+enum { ABR_PAIR_PLANE_SPHERE = 0, ABR_PAIR_PLANE_CAPSULE = 1, ABR_PAIR_SPHERE_SPHERE = 2,
+       ABR_PAIR_SPHERE_CAPSULE = 3, ABR_PAIR_CAPSULE_CAPSULE = 4 };
+/* mjtDisableBit */
+enum {
+  ABR_DSBL_CONSTRAINT = 1, ABR_DSBL_EQUALITY = 2, ABR_DSBL_FRICTIONLOSS = 4, ABR_DSBL_LIMIT = 8,
+  ABR_DSBL_CONTACT = 16, ABR_DSBL_PASSIVE = 32, ABR_DSBL_GRAVITY = 64, ABR_DSBL_CLAMPCTRL = 128,
+  ABR_DSBL_WARMSTART = 256, ABR_DSBL_FILTERPARENT = 512, ABR_DSBL_ACTUATION = 1024,
+  ABR_DSBL_REFSAFE = 2048, ABR_DSBL_SENSOR = 4096, ABR_DSBL_EULERDAMP = 16384
+};
+
+/* model.opt (+ stat.meaninertia). What `model.opt.replace(...)` changes in the reference test
+ * (tests/trajopt/test_predictive_sampler.py:22-31). */
+/* ABR_STRUCT_BEGIN AbrOpt */
+typedef struct AbrOpt {
+  float timestep;
+  float impratio;
+  float tolerance;
+  float ls_tolerance;
+  float gravity[3];
+  float meaninertia;
+  int integrator;
+  int cone;
+  int jacobian;
+  int solver;
+  int iterations;
+  int ls_iterations;
+  int disableflags;
+  int reserved0;
+} AbrOpt;
+/* ABR_STRUCT_END */
+
+/* Flattened MjModel, structure-of-arrays, host side. Produced by the loader
+ * (ambersim_b200/utils/io_utils.py: mj_to_mjx_model_and_data, replacing io_utils.py:222-241). */
+/* ABR_STRUCT_BEGIN AbrModelHost */
+typedef struct AbrModelHost {
+  int nq;
+  int nv;
+  int nu;
+  int na;
+  int nbody;
+  int njnt;
+  int ngeom;
+  int neq;
+  int npair;       /* statically enumerated colliding geom pairs (MJX enumerates at trace time) */
+  int reserved0;
+  AbrOpt opt;
+  /* bodies [nbody] */
+  const int* body_parentid;
+  const int* body_rootid;
+  const int* body_jntnum;
+  const int* body_jntadr;
+  const int* body_dofnum;
+  const int* body_dofadr;
+  const float* body_pos;        /* [nbody,3] */
+  const float* body_quat;       /* [nbody,4] (w,x,y,z) */
+  const float* body_ipos;       /* [nbody,3] */
+  const float* body_iquat;      /* [nbody,4] */
+  const float* body_mass;       /* [nbody]   */
+  const float* body_subtreemass;/* [nbody]   */
+  const float* body_inertia;    /* [nbody,3] */
+  const float* body_invweight0; /* [nbody,2] */
+  /* joints [njnt] */
+  const int* jnt_type;
+  const int* jnt_qposadr;
+  const int* jnt_dofadr;
+  const int* jnt_bodyid;
+  const int* jnt_limited;
+  const float* jnt_solref;      /* [njnt,2] */
+  const float* jnt_solimp;      /* [njnt,5] */
+  const float* jnt_pos;         /* [njnt,3] */
+  const float* jnt_axis;        /* [njnt,3] */
+  const float* jnt_stiffness;   /* [njnt]   */
+  const float* jnt_range;       /* [njnt,2] */
+  const float* jnt_margin;      /* [njnt]   */
+  /* dofs [nv] */
+  const int* dof_bodyid;
+  const int* dof_jntid;
+  const int* dof_parentid;
+  const float* dof_armature;
+  const float* dof_damping;
+  const float* dof_invweight0;
+  /* geoms [ngeom] */
+  const int* geom_type;
+  const int* geom_bodyid;
+  const float* geom_size;       /* [ngeom,3] */
+  const float* geom_pos;        /* [ngeom,3] */
+  const float* geom_quat;       /* [ngeom,4] */
+  /* static contact pairs [npair]; mixing of friction/solref/solimp/margin done by the loader */
+  const int* pair_geom1;
+  const int* pair_geom2;
+  const int* pair_kind;         /* ABR_PAIR_* */
+  const int* pair_condim;       /* 1 or 3 */
+  const float* pair_friction;   /* [npair,5] */
+  const float* pair_solref;     /* [npair,2] */
+  const float* pair_solimp;     /* [npair,5] */
+  const float* pair_includemargin; /* [npair] margin - gap */
+  /* equality [neq] */
+  const int* eq_type;
+  const int* eq_obj1id;
+  const int* eq_obj2id;
+  const int* eq_active;
+  const float* eq_solref;       /* [neq,2]  */
+  const float* eq_solimp;       /* [neq,5]  */
+  const float* eq_data;         /* [neq,11] */
+  /* actuators [nu] (joint transmission only) */
+  const int* actuator_trnid;    /* [nu] joint id */
+  const int* actuator_gaintype;
+  const int* actuator_biastype;
+  const int* actuator_ctrllimited;
+  const int* actuator_forcelimited;
+  const float* actuator_ctrlrange;  /* [nu,2] */
+  const float* actuator_forcerange; /* [nu,2] */
+  const float* actuator_gainprm;    /* [nu,3] */
+  const float* actuator_biasprm;    /* [nu,3] */
+  const float* actuator_gear;       /* [nu]   gear[0] */
+  /* reference configuration */
+  const float* qpos0;           /* [nq] */
+  const float* qpos_spring;     /* [nq] */
+} AbrModelHost;
+/* ABR_STRUCT_END */
+
+/* Dense quadratic tracking cost, StaticGoalQuadraticCost (ambersim/trajopt/cost.py:13-85):
+ *   0.5 * [ sum_{t<N} (x_t-xg)' Q (x_t-xg) + (x_N-xg)' Qf (x_N-xg) + sum_{t<N} u_t' R u_t ]
+ * HOST pointers; copied to the device by abr_cost_create. */
+/* ABR_STRUCT_BEGIN AbrQuadCostHost */
+typedef struct AbrQuadCostHost {
+  int nx;
+  int nu;
+  const float* Q;   /* [nx,nx] */
+  const float* Qf;  /* [nx,nx] */
+  const float* R;   /* [nu,nu] */
+  const float* xg;  /* [nx]    */
+} AbrQuadCostHost;
+/* ABR_STRUCT_END */
+
+typedef struct AbrModel AbrModel; /* opaque device-resident model handle */
+typedef struct AbrCost AbrCost;   /* opaque device-resident cost handle  */
+
+const char* abr_last_error(void);
+int abr_version(void);
+size_t abr_sizeof_model_host(void);
+size_t abr_sizeof_opt(void);
+int abr_device_count(void);
+
+/* replaces mjx.device_put(mj_model) (io_utils.py:225). Validates feature support. */
+int abr_model_create(const AbrModelHost* host, int device, AbrModel** out);
+int abr_model_destroy(AbrModel* m);
+/* replaces model.replace(opt=model.opt.replace(...)) (test_predictive_sampler.py:22-31) */
+int abr_model_set_opt(AbrModel* m, const AbrOpt* opt);
+int abr_model_get_opt(const AbrModel* m, AbrOpt* opt);
+/* static sizes derived at create: ncon, ne, nl, nefc, tree depth, lanes per world chosen */
+int abr_model_info(const AbrModel* m, int* ncon, int* ne, int* nl, int* nefc, int* depth);
+/* override the lanes-per-world group size G in {0 (auto), 4, 8, 16, 32}  */
+int abr_model_set_lanes(AbrModel* m, int lanes);
+
+int abr_cost_create(const AbrQuadCostHost* host, int device, AbrCost** out);
+int abr_cost_destroy(AbrCost* c);
+
+/* ---- shoot (shooting.py:22-48) for nworld independent worlds, DEVICE pointers -----------
+ * x0        [nworld,nx] if x0_stride==nx, or [nx] shared if x0_stride==0
+ * us        [nworld,N,nu]  (us_stride = N*nu), or shared guess when us_stride==0
+ * xs_out    nullable [nworld,N+1,nx]; row 0 = caller's x0 verbatim (shooting.py:47)
+ * cost      nullable; costs_out nullable [nworld] (fused cost.py:62-85)
+ * Does make_data + forward (ctrl = 0) to seed qacc_warmstart (shooting.py:34-36), then N steps. */
+int abr_rollout_dev(AbrModel* m, const float* x0, int x0_stride, const float* us, int us_stride,
+                    int nworld, int N, float* xs_out, const AbrCost* cost, float* costs_out,
+                    void* stream);
+/* same, HOST pointers (copies inside) */
+int abr_rollout_host(AbrModel* m, const float* x0, int x0_stride, const float* us, int us_stride,
+                     int nworld, int N, float* xs_out, const AbrCost* cost, float* costs_out);
+
+/* ---- VanillaPredictiveSampler.optimize (shooting.py:119-157), batch of B problems --------
+ * x0 [B,nx]; us_guess [B,N,nu]; noise: nullable [B,S-1,N,nu] standard normals supplied by the
+ * caller (parity mode: pass jax.random.normal's values); NULL => counter-based on-device normals
+ * keyed by (seed, b, global_sample, t, u) so results do not depend on the GPU count.
+ * sample_offset/S_total: this rank evaluates global samples [sample_offset, sample_offset+S) of
+ * S_total (sample 0 = un-noised guess, shooting.py:140-142). Clips to actuator_ctrlrange
+ * unconditionally (shooting.py:146-148). argmin = first minimum, NaN counts as minimum (jnp.argmin).
+ * outputs: xs_star [B,N+1,nx], us_star [B,N,nu], best_idx [B] (GLOBAL sample index),
+ * best_cost [B]; costs_out nullable [B,S]. */
+int abr_predictive_sample_dev(AbrModel* m, const AbrCost* cost, const float* x0,
+                              const float* us_guess, const float* noise,
+                              unsigned long long seed, int B, int S, int N, float stdev,
+                              int sample_offset, int S_total, float* xs_star, float* us_star,
+                              int* best_idx, float* best_cost, float* costs_out, void* stream);
+int abr_predictive_sample_host(AbrModel* m, const AbrCost* cost, const float* x0,
+                               const float* us_guess, const float* noise,
+                               unsigned long long seed, int B, int S, int N, float stdev,
+                               int sample_offset, int S_total, float* xs_star, float* us_star,
+                               int* best_idx, float* best_cost, float* costs_out);
+
+/* ---- MjxEnv.pipeline_init / pipeline_step (rl/base.py:81-96), E envs, in place, DEVICE ---
+ * state SoA: qpos [E,nq], qvel [E,nv], qacc_warmstart [E,nv], time [E].
+ * abr_forward_dev: mjx.forward with ctrl (nullable => 0): writes qacc [E,nv] (nullable) and
+ *   qacc_warmstart. abr_env_step_dev: optional auto-reset prologue
+ *   (brax AutoResetWrapper: where(done, first_state, state)), then nsubsteps x mjx.step with
+ *   ctrl held (rl/base.py:92-95). */
+int abr_forward_dev(AbrModel* m, float* qpos, float* qvel, const float* ctrl, float* qacc_warmstart,
+                    float* qacc, int E, void* stream);
+int abr_env_step_dev(AbrModel* m, float* qpos, float* qvel, float* qacc_warmstart, float* time,
+                     const float* ctrl, int E, int nsubsteps, const unsigned char* reset_mask,
+                     const float* first_qpos, const float* first_qvel,
+                     const float* first_qacc_warmstart, void* stream);
+
+/* ---- stage dump for parity tests (tests only): one world, mjx.forward, HOST pointers ------
+ * name in {"xpos","xquat","xipos","ximat","subtree_com","cinert","cdof","qM","cvel","cdof_dot",
+ * "qfrc_bias","qfrc_passive","qfrc_actuator","qfrc_smooth","qacc_smooth","efc_J","efc_D",
+ * "efc_aref","qacc","qfrc_constraint","efc_force"}; out has capacity `cap` floats; *n = count. */
+int abr_debug_forward_host(AbrModel* m, const float* qpos, const float* qvel, const float* ctrl,
+                           const float* qacc_warmstart, const char* name, float* out, int cap,
+                           int* n);
+
+/* FP32 FMA-pipe peak microbenchmark (roofline denominator): returns TFLOP/s */
+int abr_ffma_peak(int device, double* tflops, double* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ABR_H_ */

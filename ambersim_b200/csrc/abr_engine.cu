@@ -1,0 +1,865 @@
+// abr_engine.cu — kernels + C ABI (include/abr.h) of the B200 batched rollout engine.
+//
+// One group of G lanes per world; a CTA stages the model blob into shared memory once and then
+// each group runs its world's whole horizon (shoot, shooting.py:22-48) out of shared memory:
+// HBM traffic is controls in and states/costs out only.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "abr.h"
+#include "abr_layout.h"
+#include "abr_kernels.cuh"
+
+using namespace abr;
+
+// ================================================================================ errors
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess)                                                                \
+      return fail(ABR_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));         \
+  } while (0)
+
+// ================================================================================ handles
+struct HostModel {  // deep copy of AbrModelHost
+  int nq, nv, nu, na, nbody, njnt, ngeom, neq, npair;
+  AbrOpt opt;
+  std::vector<int> body_parentid, body_rootid, body_jntnum, body_jntadr, body_dofnum, body_dofadr;
+  std::vector<float> body_pos, body_quat, body_ipos, body_iquat, body_mass, body_subtreemass, body_inertia, body_invweight0;
+  std::vector<int> jnt_type, jnt_qposadr, jnt_dofadr, jnt_bodyid, jnt_limited;
+  std::vector<float> jnt_solref, jnt_solimp, jnt_pos, jnt_axis, jnt_stiffness, jnt_range, jnt_margin;
+  std::vector<int> dof_bodyid, dof_jntid, dof_parentid;
+  std::vector<float> dof_armature, dof_damping, dof_invweight0;
+  std::vector<int> geom_type, geom_bodyid;
+  std::vector<float> geom_size, geom_pos, geom_quat;
+  std::vector<int> pair_geom1, pair_geom2, pair_kind, pair_condim;
+  std::vector<float> pair_friction, pair_solref, pair_solimp, pair_includemargin;
+  std::vector<int> eq_type, eq_obj1id, eq_obj2id, eq_active;
+  std::vector<float> eq_solref, eq_solimp, eq_data;
+  std::vector<int> actuator_trnid, actuator_gaintype, actuator_biastype, actuator_ctrllimited, actuator_forcelimited;
+  std::vector<float> actuator_ctrlrange, actuator_forcerange, actuator_gainprm, actuator_biasprm, actuator_gear;
+  std::vector<float> qpos0, qpos_spring;
+};
+
+struct Scratch {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return ABR_OK;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return fail(ABR_ECUDA, std::string("cudaMalloc scratch: ") + cudaGetErrorString(e));
+    cap = bytes;
+    return ABR_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct AbrModel {
+  int device = 0;
+  HostModel hm;
+  Layout lay;        // production layout (aliased per-world regions)
+  Layout lay_dbg;    // debug layout (no aliasing: every intermediate survives the step)
+  std::vector<float> mf;
+  std::vector<int> mi;
+  float* d_blob = nullptr;
+  int lanes = 0;     // 0 = auto
+  int num_sms = 148;
+  int max_smem = 0;
+  cudaStream_t stream = nullptr;  // for the *_host entry points
+  Scratch s_costs, s_in, s_out, s_dbg;
+};
+
+struct AbrCost {
+  int device = 0;
+  int nx = 0, nu = 0;
+  int diag = 0;      // Q, Qf and R are all diagonal
+  float* d = nullptr;  // [Q nx*nx][Qf nx*nx][R nu*nu][xg nx][qd nx][qfd nx][rd nu]
+};
+
+// ================================================================================ blob build
+template <class T> static std::vector<T> vcopy(const T* p, size_t n) { return p ? std::vector<T>(p, p + n) : std::vector<T>(n, T(0)); }
+
+static void copy_host_model(const AbrModelHost* h, HostModel& m) {
+  m.nq = h->nq; m.nv = h->nv; m.nu = h->nu; m.na = h->na; m.nbody = h->nbody; m.njnt = h->njnt;
+  m.ngeom = h->ngeom; m.neq = h->neq; m.npair = h->npair; m.opt = h->opt;
+  const int nb = m.nbody, nj = m.njnt, nv = m.nv, ng = m.ngeom, np = m.npair, ne = m.neq, nu = m.nu;
+  m.body_parentid = vcopy(h->body_parentid, nb); m.body_rootid = vcopy(h->body_rootid, nb);
+  m.body_jntnum = vcopy(h->body_jntnum, nb); m.body_jntadr = vcopy(h->body_jntadr, nb);
+  m.body_dofnum = vcopy(h->body_dofnum, nb); m.body_dofadr = vcopy(h->body_dofadr, nb);
+  m.body_pos = vcopy(h->body_pos, 3 * nb); m.body_quat = vcopy(h->body_quat, 4 * nb);
+  m.body_ipos = vcopy(h->body_ipos, 3 * nb); m.body_iquat = vcopy(h->body_iquat, 4 * nb);
+  m.body_mass = vcopy(h->body_mass, nb); m.body_subtreemass = vcopy(h->body_subtreemass, nb);
+  m.body_inertia = vcopy(h->body_inertia, 3 * nb); m.body_invweight0 = vcopy(h->body_invweight0, 2 * nb);
+  m.jnt_type = vcopy(h->jnt_type, nj); m.jnt_qposadr = vcopy(h->jnt_qposadr, nj);
+  m.jnt_dofadr = vcopy(h->jnt_dofadr, nj); m.jnt_bodyid = vcopy(h->jnt_bodyid, nj);
+  m.jnt_limited = vcopy(h->jnt_limited, nj);
+  m.jnt_solref = vcopy(h->jnt_solref, 2 * nj); m.jnt_solimp = vcopy(h->jnt_solimp, 5 * nj);
+  m.jnt_pos = vcopy(h->jnt_pos, 3 * nj); m.jnt_axis = vcopy(h->jnt_axis, 3 * nj);
+  m.jnt_stiffness = vcopy(h->jnt_stiffness, nj); m.jnt_range = vcopy(h->jnt_range, 2 * nj);
+  m.jnt_margin = vcopy(h->jnt_margin, nj);
+  m.dof_bodyid = vcopy(h->dof_bodyid, nv); m.dof_jntid = vcopy(h->dof_jntid, nv); m.dof_parentid = vcopy(h->dof_parentid, nv);
+  m.dof_armature = vcopy(h->dof_armature, nv); m.dof_damping = vcopy(h->dof_damping, nv);
+  m.dof_invweight0 = vcopy(h->dof_invweight0, nv);
+  m.geom_type = vcopy(h->geom_type, ng); m.geom_bodyid = vcopy(h->geom_bodyid, ng);
+  m.geom_size = vcopy(h->geom_size, 3 * ng); m.geom_pos = vcopy(h->geom_pos, 3 * ng); m.geom_quat = vcopy(h->geom_quat, 4 * ng);
+  m.pair_geom1 = vcopy(h->pair_geom1, np); m.pair_geom2 = vcopy(h->pair_geom2, np);
+  m.pair_kind = vcopy(h->pair_kind, np); m.pair_condim = vcopy(h->pair_condim, np);
+  m.pair_friction = vcopy(h->pair_friction, 5 * np); m.pair_solref = vcopy(h->pair_solref, 2 * np);
+  m.pair_solimp = vcopy(h->pair_solimp, 5 * np); m.pair_includemargin = vcopy(h->pair_includemargin, np);
+  m.eq_type = vcopy(h->eq_type, ne); m.eq_obj1id = vcopy(h->eq_obj1id, ne); m.eq_obj2id = vcopy(h->eq_obj2id, ne);
+  m.eq_active = vcopy(h->eq_active, ne);
+  m.eq_solref = vcopy(h->eq_solref, 2 * ne); m.eq_solimp = vcopy(h->eq_solimp, 5 * ne); m.eq_data = vcopy(h->eq_data, 11 * ne);
+  m.actuator_trnid = vcopy(h->actuator_trnid, nu); m.actuator_gaintype = vcopy(h->actuator_gaintype, nu);
+  m.actuator_biastype = vcopy(h->actuator_biastype, nu); m.actuator_ctrllimited = vcopy(h->actuator_ctrllimited, nu);
+  m.actuator_forcelimited = vcopy(h->actuator_forcelimited, nu);
+  m.actuator_ctrlrange = vcopy(h->actuator_ctrlrange, 2 * nu); m.actuator_forcerange = vcopy(h->actuator_forcerange, 2 * nu);
+  m.actuator_gainprm = vcopy(h->actuator_gainprm, 3 * nu); m.actuator_biasprm = vcopy(h->actuator_biasprm, 3 * nu);
+  m.actuator_gear = vcopy(h->actuator_gear, nu);
+  m.qpos0 = vcopy(h->qpos0, m.nq); m.qpos_spring = vcopy(h->qpos_spring, m.nq);
+}
+
+struct Pool {
+  std::vector<float> f;
+  std::vector<int> i;
+  int addf(const std::vector<float>& v) { int o = (int)f.size(); f.insert(f.end(), v.begin(), v.end()); return o; }
+  int addi(const std::vector<int>& v) { int o = (int)i.size(); i.insert(i.end(), v.begin(), v.end()); return o; }
+};
+
+// constraint._kbi constants of one row source (solref, solimp) under the current options
+static void row_prm(const AbrOpt& opt, const float* solref, const float* solimp, float invweight, float* out) {
+  double timeconst = solref[0], dampratio = solref[1];
+  if (!(opt.disableflags & ABR_DSBL_REFSAFE)) timeconst = std::max(timeconst, 2.0 * (double)opt.timestep);
+  auto clip = [](double x, double lo, double hi) { return std::min(std::max(x, lo), hi); };
+  double dmin = clip(solimp[0], 1e-4, 0.9999), dmax = clip(solimp[1], 1e-4, 0.9999);
+  double width = std::max(1e-15, (double)solimp[2]);
+  double mid = clip(solimp[3], 1e-4, 0.9999), power = std::max(1.0, (double)solimp[4]);
+  double k = 1.0 / (dmax * dmax * timeconst * timeconst * dampratio * dampratio);
+  double b = 2.0 / (dmax * timeconst);
+  if (solref[0] <= 0) k = -(double)solref[0] / (dmax * dmax);
+  if (solref[1] <= 0) b = -(double)solref[1] / dmax;
+  out[0] = (float)k; out[1] = (float)b; out[2] = (float)dmin; out[3] = (float)dmax;
+  out[4] = (float)(1.0 / width); out[5] = (float)mid; out[6] = (float)power; out[7] = invweight;
+  out[8] = (float)(1.0 / std::pow(mid, power - 1.0));
+  out[9] = (float)(1.0 / std::pow(1.0 - mid, power - 1.0));
+}
+
+static int pair_ncon(int kind) { return kind == ABR_PAIR_PLANE_CAPSULE ? 2 : 1; }
+
+static int build_blob(const HostModel& m, bool alias, Layout& L, std::vector<float>& mf, std::vector<int>& mi) {
+  memset(&L, 0, sizeof(L));
+  const AbrOpt& opt = m.opt;
+  const int nb = m.nbody, nj = m.njnt, nv = m.nv, nu = m.nu, nq = m.nq;
+  // ---- validation (mirrors MJX device_put's NotImplementedError, io_utils.py:228-241)
+  if (opt.cone != 0) return fail(ABR_EUNSUPPORTED, "elliptic friction cones are not supported (pyramidal only)");
+  if (opt.integrator != ABR_INT_EULER && opt.integrator != ABR_INT_RK4)
+    return fail(ABR_EUNSUPPORTED, "integrator must be Euler (0) or RK4 (1)");
+  if (opt.solver != ABR_SOLVER_NEWTON && opt.solver != ABR_SOLVER_CG)
+    return fail(ABR_EUNSUPPORTED, "solver must be CG (1) or Newton (2)");
+  if (nv > 64 || nb > 4096) return fail(ABR_ECAPACITY, "model too large for the compiled kernels (nv <= 64)");
+  if (m.na != 0) return fail(ABR_EUNSUPPORTED, "stateful actuators are not supported");
+  for (int j = 0; j < nj; j++)
+    if (m.jnt_type[j] == ABR_JNT_BALL) return fail(ABR_EUNSUPPORTED, "ball joints are not supported");
+  for (int e = 0; e < m.neq; e++)
+    if (m.eq_active[e] && m.eq_type[e] != ABR_EQ_JOINT) return fail(ABR_EUNSUPPORTED, "only joint equalities are supported");
+  for (int b = 1; b < nb; b++)
+    if (m.body_parentid[b] >= b) return fail(ABR_EINVAL, "bodies must be ordered parent before child");
+
+  const int dis = opt.disableflags;
+  const bool con_all = !(dis & ABR_DSBL_CONSTRAINT);
+  Pool P;
+  L.nq = nq; L.nv = nv; L.nu = nu; L.nbody = nb; L.njnt = nj; L.ngeom = m.ngeom; L.npair = m.npair; L.nx = nq + nv;
+  L.integrator = opt.integrator; L.solver = opt.solver; L.iterations = opt.iterations;
+  L.ls_iterations = opt.ls_iterations; L.disableflags = dis;
+  L.timestep = opt.timestep; L.tolerance = opt.tolerance; L.ls_tolerance = opt.ls_tolerance;
+  L.meaninertia = opt.meaninertia; L.impratio = opt.impratio;
+  for (int i = 0; i < 3; i++) L.gravity[i] = opt.gravity[i];
+
+  // ---- float pool: plain model arrays
+  L.f_body_pos = P.addf(m.body_pos); L.f_body_quat = P.addf(m.body_quat); L.f_body_ipos = P.addf(m.body_ipos);
+  L.f_body_iquat = P.addf(m.body_iquat); L.f_body_mass = P.addf(m.body_mass); L.f_body_inertia = P.addf(m.body_inertia);
+  L.f_jnt_pos = P.addf(m.jnt_pos); L.f_jnt_axis = P.addf(m.jnt_axis); L.f_jnt_range = P.addf(m.jnt_range);
+  L.f_jnt_margin = P.addf(m.jnt_margin); L.f_jnt_stiffness = P.addf(m.jnt_stiffness);
+  L.f_dof_armature = P.addf(m.dof_armature); L.f_dof_damping = P.addf(m.dof_damping);
+  L.f_qpos0 = P.addf(m.qpos0); L.f_qpos_spring = P.addf(m.qpos_spring);
+  L.f_geom_size = P.addf(m.geom_size); L.f_geom_pos = P.addf(m.geom_pos); L.f_geom_quat = P.addf(m.geom_quat);
+
+  // ---- tree tables
+  std::vector<int> depth(nb, 0), rootslot(nb, 0), roots;
+  int maxdepth = 0;
+  for (int b = 1; b < nb; b++) {
+    depth[b] = depth[m.body_parentid[b]] + 1;
+    maxdepth = std::max(maxdepth, depth[b]);
+    if (m.body_parentid[b] == 0) { rootslot[b] = (int)roots.size(); roots.push_back(b); }
+    else rootslot[b] = rootslot[m.body_parentid[b]];
+  }
+  L.depth = maxdepth; L.nroot = (int)roots.size();
+  std::vector<int> level_adr(maxdepth + 2, 0), level_body;
+  for (int lev = 0; lev <= maxdepth; lev++) {
+    level_adr[lev] = (int)level_body.size();
+    for (int b = 0; b < nb; b++) if (depth[b] == lev) level_body.push_back(b);
+  }
+  level_adr[maxdepth + 1] = (int)level_body.size();
+  std::vector<int> childadr(nb, 0), childnum(nb, 0), child;
+  for (int p = 0; p < nb; p++) {
+    childadr[p] = (int)child.size();
+    for (int b = 1; b < nb; b++) if (m.body_parentid[b] == p && b != p) { child.push_back(b); childnum[p]++; }
+  }
+  L.i_body_parent = P.addi(m.body_parentid); L.i_body_jntadr = P.addi(m.body_jntadr); L.i_body_jntnum = P.addi(m.body_jntnum);
+  L.i_body_dofadr = P.addi(m.body_dofadr); L.i_body_dofnum = P.addi(m.body_dofnum); L.i_body_rootslot = P.addi(rootslot);
+  L.i_body_childadr = P.addi(childadr); L.i_body_childnum = P.addi(childnum); L.i_child = P.addi(child);
+  L.i_level_adr = P.addi(level_adr); L.i_level_body = P.addi(level_body);
+  L.i_jnt_type = P.addi(m.jnt_type); L.i_jnt_qposadr = P.addi(m.jnt_qposadr); L.i_jnt_dofadr = P.addi(m.jnt_dofadr);
+  L.i_jnt_body = P.addi(m.jnt_bodyid);
+  L.i_dof_body = P.addi(m.dof_bodyid); L.i_dof_jnt = P.addi(m.dof_jntid);
+  L.i_root_body = P.addi(roots);
+  L.i_geom_body = P.addi(m.geom_bodyid);
+  L.i_pair_g1 = P.addi(m.pair_geom1); L.i_pair_g2 = P.addi(m.pair_geom2); L.i_pair_kind = P.addi(m.pair_kind);
+
+  // M sparsity (ancestor pairs) and packed-index table
+  std::vector<int> mpair, tri_tab;
+  for (int i = 0; i < nv; i++)
+    for (int j = i; j >= 0; j = m.dof_parentid[j]) mpair.push_back((i << 16) | j);
+  for (int i = 0; i < nv; i++)
+    for (int j = 0; j <= i; j++) tri_tab.push_back((i << 16) | j);
+  L.nmpair = (int)mpair.size(); L.ntri = nv * (nv + 1) / 2;
+  L.i_mpair = P.addi(mpair); L.i_tri = P.addi(tri_tab);
+
+  // ---- constraint rows: equality, limit, contact (static sizes)
+  std::vector<int> eq_j1, eq_j2, lim_jnt, dof_limrow(nv, -1), row_info;
+  std::vector<float> eq_prm, eq_data, lim_prm, con_prm;
+  if (con_all && !(dis & ABR_DSBL_EQUALITY)) {
+    for (int e = 0; e < m.neq; e++) {
+      if (!m.eq_active[e]) continue;
+      int j1 = m.eq_obj1id[e], j2 = m.eq_obj2id[e];
+      for (int j : {j1, j2})
+        if (j >= 0 && m.jnt_type[j] != ABR_JNT_HINGE && m.jnt_type[j] != ABR_JNT_SLIDE)
+          return fail(ABR_EUNSUPPORTED, "joint equality on a non-scalar joint");
+      float inv = m.dof_invweight0[m.jnt_dofadr[j1]] + (j2 >= 0 ? m.dof_invweight0[m.jnt_dofadr[j2]] : 0.f);
+      float prm[kRowPrm];
+      row_prm(opt, &m.eq_solref[2 * e], &m.eq_solimp[5 * e], inv, prm);
+      row_info.push_back(0 | ((int)eq_j1.size() << 2));
+      eq_j1.push_back(j1); eq_j2.push_back(j2);
+      eq_prm.insert(eq_prm.end(), prm, prm + kRowPrm);
+      eq_data.insert(eq_data.end(), &m.eq_data[11 * e], &m.eq_data[11 * e] + 5);
+    }
+  }
+  L.ne = (int)eq_j1.size();
+  if (con_all && !(dis & ABR_DSBL_LIMIT)) {
+    for (int j = 0; j < nj; j++) {
+      if (!m.jnt_limited[j]) continue;
+      if (m.jnt_type[j] != ABR_JNT_HINGE && m.jnt_type[j] != ABR_JNT_SLIDE) continue;
+      float prm[kRowPrm];
+      row_prm(opt, &m.jnt_solref[2 * j], &m.jnt_solimp[5 * j], m.dof_invweight0[m.jnt_dofadr[j]], prm);
+      dof_limrow[m.jnt_dofadr[j]] = (int)lim_jnt.size();
+      row_info.push_back(1 | ((int)lim_jnt.size() << 2));
+      lim_jnt.push_back(j);
+      lim_prm.insert(lim_prm.end(), prm, prm + kRowPrm);
+    }
+  }
+  L.nl = (int)lim_jnt.size();
+  std::vector<int> con_pair, con_sub, con_row, con_condim, con_dofmask;
+  // contact parameter blocks are per pair (allocated for every pair so indices stay pair ids)
+  for (int p = 0; p < m.npair; p++) {
+    int b1 = m.geom_bodyid[m.pair_geom1[p]], b2 = m.geom_bodyid[m.pair_geom2[p]];
+    float t = m.body_invweight0[2 * b1] + m.body_invweight0[2 * b2];
+    float prm[kConPrm];
+    float mu1 = m.pair_friction[5 * p], mu2 = m.pair_friction[5 * p + 1];
+    row_prm(opt, &m.pair_solref[2 * p], &m.pair_solimp[5 * p], t, prm);
+    if (m.pair_condim[p] == 3) {
+      prm[7] = (t + mu1 * mu1 * t) * 2.f * mu1 * mu1 / opt.impratio;
+      prm[10] = (t + mu2 * mu2 * t) * 2.f * mu2 * mu2 / opt.impratio;
+    } else {
+      prm[10] = t;
+    }
+    prm[11] = mu1; prm[12] = mu2; prm[13] = m.pair_includemargin[p];
+    con_prm.insert(con_prm.end(), prm, prm + kConPrm);
+  }
+  if (con_all && !(dis & ABR_DSBL_CONTACT)) {
+    for (int p = 0; p < m.npair; p++) {
+      if (m.pair_condim[p] != 1 && m.pair_condim[p] != 3) return fail(ABR_EUNSUPPORTED, "contact condim must be 1 or 3");
+      int b1 = m.geom_bodyid[m.pair_geom1[p]], b2 = m.geom_bodyid[m.pair_geom2[p]];
+      std::vector<char> anc1(nb, 0), anc2(nb, 0);
+      for (int b = b1; b > 0; b = m.body_parentid[b]) anc1[b] = 1;
+      for (int b = b2; b > 0; b = m.body_parentid[b]) anc2[b] = 1;
+      for (int s = 0; s < pair_ncon(m.pair_kind[p]); s++) {
+        int ci = (int)con_pair.size();
+        con_pair.push_back(p); con_sub.push_back(s); con_condim.push_back(m.pair_condim[p]);
+        con_row.push_back((int)row_info.size());
+        int nrow = m.pair_condim[p] == 1 ? 1 : 4;
+        for (int r = 0; r < nrow; r++) row_info.push_back(2 | (ci << 2) | (r << 20));
+        for (int d = 0; d < nv; d++) {
+          int bd = m.dof_bodyid[d];
+          int mk = (anc2[bd] ? 1 : 0) | (anc1[bd] ? 2 : 0);
+          con_dofmask.push_back(mk == 3 ? 0 : mk);  // common ancestors cancel exactly
+        }
+      }
+    }
+  }
+  L.ncon = (int)con_pair.size();
+  L.nefc = (int)row_info.size();
+  L.f_eq_prm = P.addf(eq_prm); L.f_eq_data = P.addf(eq_data); L.f_lim_prm = P.addf(lim_prm); L.f_con_prm = P.addf(con_prm);
+  L.i_dof_limrow = P.addi(dof_limrow); L.i_lim_jnt = P.addi(lim_jnt); L.i_eq_j1 = P.addi(eq_j1); L.i_eq_j2 = P.addi(eq_j2);
+  L.i_con_pair = P.addi(con_pair); L.i_con_sub = P.addi(con_sub); L.i_con_row = P.addi(con_row);
+  L.i_con_condim = P.addi(con_condim); L.i_con_dofmask = P.addi(con_dofmask); L.i_row_info = P.addi(row_info);
+
+  // ---- actuators
+  std::vector<float> act_prm;
+  std::vector<int> act_jnt, act_flags, dof_actadr(nv, 0), dof_actnum(nv, 0), dof_act;
+  for (int u = 0; u < nu; u++) {
+    int j = m.actuator_trnid[u];
+    if (j < 0 || j >= nj || (m.jnt_type[j] != ABR_JNT_HINGE && m.jnt_type[j] != ABR_JNT_SLIDE))
+      return fail(ABR_EUNSUPPORTED, "actuators must drive hinge or slide joints");
+    float prm[kActPrm] = {m.actuator_ctrlrange[2 * u], m.actuator_ctrlrange[2 * u + 1], m.actuator_forcerange[2 * u],
+                          m.actuator_forcerange[2 * u + 1], m.actuator_gainprm[3 * u], m.actuator_gainprm[3 * u + 1],
+                          m.actuator_gainprm[3 * u + 2], m.actuator_biasprm[3 * u], m.actuator_biasprm[3 * u + 1],
+                          m.actuator_biasprm[3 * u + 2], m.actuator_gear[u]};
+    act_prm.insert(act_prm.end(), prm, prm + kActPrm);
+    act_jnt.push_back(j);
+    act_flags.push_back((m.actuator_ctrllimited[u] ? 1 : 0) | (m.actuator_forcelimited[u] ? 2 : 0) |
+                        (m.actuator_gaintype[u] == ABR_GAIN_AFFINE ? 4 : 0) | (m.actuator_biastype[u] == ABR_BIAS_AFFINE ? 8 : 0));
+  }
+  for (int d = 0; d < nv; d++) {
+    dof_actadr[d] = (int)dof_act.size();
+    for (int u = 0; u < nu; u++)
+      if (m.jnt_dofadr[act_jnt[u]] == d) { dof_act.push_back(u); dof_actnum[d]++; }
+  }
+  L.f_act_prm = P.addf(act_prm);
+  L.i_act_jnt = P.addi(act_jnt); L.i_act_flags = P.addi(act_flags);
+  L.i_dof_actadr = P.addi(dof_actadr); L.i_dof_actnum = P.addi(dof_actnum); L.i_dof_act = P.addi(dof_act);
+
+  while (P.f.size() % 4) P.f.push_back(0.f);
+  while (P.i.size() % 4) P.i.push_back(0);
+  L.n_mf = (int)P.f.size(); L.n_mi = (int)P.i.size();
+  mf = P.f; mi = P.i;
+
+  // ---- per-world shared-memory layout
+  const int ne = L.nefc, nc = L.ncon, ntri = L.ntri;
+  int off = 0;
+  auto take = [&](int n) { int o = off; off += n; return o; };
+  // persistent across the step
+  L.w_qpos = take(nq); L.w_qvel = take(nv);   // x = [qpos; qvel] contiguous
+  L.w_warm = take(nv); L.w_ctrl = take(nu);
+  L.w_M = take(ntri); L.w_H = take(ntri);
+  L.w_eqc = take(L.ne); L.w_lims = take(L.nl); L.w_B = take(3 * nc * nv);
+  L.w_D = take(ne); L.w_aref = take(ne);
+  L.w_fs = take(nv); L.w_as = take(nv); L.w_a = take(nv); L.w_fc = take(nv); L.w_y = take(nv);
+  L.w_cinert = take(10 * nb); L.w_cdof = take(6 * nv);
+  L.w_actf = take(nu); L.w_bv = take(3 * nc);
+  int rk = 2 * nv;  // CG Polak-Ribiere history
+  if (opt.integrator == ABR_INT_RK4) rk += nq + 6 * nv;
+  L.w_rk = take(rk);
+  const int base = off;
+  // region A (position phase): poses, contact geometry            | solver vectors
+  L.w_xpos = take(3 * nb); L.w_xquat = take(4 * nb); L.w_xipos = take(3 * nb);
+  L.w_xanchor = take(3 * nj); L.w_xaxis = take(3 * nj); L.w_rootcom = take(3 * L.nroot);
+  L.w_cdist = take(nc); L.w_cpos = take(3 * nc); L.w_cframe = take(9 * nc);
+  const int endA = off;
+  if (alias) off = base;
+  L.w_Ma = take(nv); L.w_grad = take(nv); L.w_search = take(nv); L.w_mv = take(nv);
+  L.w_Jaref = take(ne); L.w_jv = take(ne); L.w_force = take(ne); L.w_Fc = take(3 * nc); L.w_WB = take(3 * nc * nv);
+  const int endS = off;
+  off = std::max(endA, endS);
+  // region B: crb + buf (inertia phase)                            | cvel, cacc, cdof_dot (velocity phase)
+  const int baseB = off;
+  L.w_crb = take(10 * nb); L.w_buf = take(6 * nv);
+  const int endB1 = off;
+  if (alias) off = baseB;
+  L.w_cvel = take(6 * nb); L.w_cacc = take(6 * nb); L.w_cdofdot = take(6 * nv);
+  off = std::max(endB1, off);
+  // NOTE: region A holds rootcom/xpos/xquat, which stage_collision (before crb) and stage_com use;
+  // the solver vectors only become live in stage_solve, after every reader of region A.
+  L.world_stride = (off + 3) & ~3;
+  return ABR_OK;
+}
+
+// segmented first-minimum argmin, NaN counts as the minimum (jnp.argmin, shooting.py:154)
+__device__ __forceinline__ bool better(float ca, int ia, float cb, int ib) {
+  const bool na = isnan(ca), nb = isnan(cb);
+  if (na != nb) return na;
+  if (!na && ca != cb) return ca < cb;
+  return ia < ib;
+}
+__global__ void k_argmin(const float* costs, int S, int sample_offset, int* best_idx, float* best_cost) {
+  __shared__ float sc[256];
+  __shared__ int si[256];
+  const int b = blockIdx.x;
+  const float* cs = costs + (size_t)b * S;
+  float bc = 0.f; int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < S; i += blockDim.x) {
+    const float v = cs[i];
+    if (bi == 0x7fffffff || better(v, i, bc, bi)) { bc = v; bi = i; }
+  }
+  sc[threadIdx.x] = bc; si[threadIdx.x] = bi;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      const float c2 = sc[threadIdx.x + o]; const int i2 = si[threadIdx.x + o];
+      if (i2 != 0x7fffffff && (si[threadIdx.x] == 0x7fffffff || better(c2, i2, sc[threadIdx.x], si[threadIdx.x]))) {
+        sc[threadIdx.x] = c2; si[threadIdx.x] = i2;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { best_idx[b] = sample_offset + si[0]; best_cost[b] = sc[0]; }
+}
+
+// FP32 FMA-pipe peak: 8 independent FFMA chains per thread
+__global__ void __launch_bounds__(1024) k_ffma(float* out, int iters, float a, float b) {
+  float x0 = threadIdx.x, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+      x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+    }
+  }
+  const float s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+  if (s == 12345.678f) out[0] = s;
+}
+
+// ================================================================================ launch helpers
+static int pick_lanes(const AbrModel* m, int nworld) {
+  if (m->lanes) return m->lanes;
+  const char* e = getenv("ABR_LANES");
+  if (e && atoi(e) > 0) return atoi(e);
+  // enough worlds to fill the machine with narrow groups -> better lane efficiency
+  const long per_sm = (long)nworld / m->num_sms;
+  if (per_sm >= 256) return 8;
+  if (per_sm >= 64) return 16;
+  return 32;
+}
+
+static int launch_result(int rc) {
+  if (rc == 0) return ABR_OK;
+  if (rc == -1000) return fail(ABR_ECAPACITY, "model does not fit in shared memory");
+  return fail(ABR_ECUDA, std::string("kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
+}
+static int launch_rollout(const AbrModel* m, const Layout& L, const RolloutArgs& a, cudaStream_t st) {
+  if (a.nworld <= 0) return ABR_OK;
+  LaunchCfg cfg{m->max_smem};
+  switch (pick_lanes(m, a.nworld)) {
+    case 4: return launch_result(launch_rollout_4(cfg, L, a, st));
+    case 8: return launch_result(launch_rollout_8(cfg, L, a, st));
+    case 16: return launch_result(launch_rollout_16(cfg, L, a, st));
+    default: return launch_result(launch_rollout_32(cfg, L, a, st));
+  }
+}
+static int launch_env(const AbrModel* m, const Layout& L, const EnvArgs& a, cudaStream_t st) {
+  if (a.E <= 0) return ABR_OK;
+  LaunchCfg cfg{m->max_smem};
+  switch (pick_lanes(m, a.E)) {
+    case 4: return launch_result(launch_env_4(cfg, L, a, st));
+    case 8: return launch_result(launch_env_8(cfg, L, a, st));
+    case 16: return launch_result(launch_env_16(cfg, L, a, st));
+    default: return launch_result(launch_env_32(cfg, L, a, st));
+  }
+}
+
+static CostView cost_view(const AbrCost* c) {
+  CostView v;
+  memset(&v, 0, sizeof(v));
+  if (!c) return v;
+  const int nx = c->nx, nu = c->nu;
+  v.Q = c->d; v.Qf = v.Q + nx * nx; v.R = v.Qf + nx * nx; v.xg = v.R + nu * nu;
+  v.qd = v.xg + nx; v.qfd = v.qd + nx; v.rd = v.qfd + nx;
+  v.enabled = 1; v.diag = c->diag;
+  return v;
+}
+
+static int rebuild(AbrModel* m) {
+  int rc = build_blob(m->hm, getenv("ABR_NO_ALIAS") == nullptr, m->lay, m->mf, m->mi);
+  if (rc) return rc;
+  std::vector<float> f2; std::vector<int> i2;
+  rc = build_blob(m->hm, false, m->lay_dbg, f2, i2);
+  if (rc) return rc;
+  CK(cudaSetDevice(m->device));
+  if (m->d_blob) { cudaFree(m->d_blob); m->d_blob = nullptr; }
+  const size_t bytes = sizeof(float) * ((size_t)m->lay.n_mf + m->lay.n_mi);
+  CK(cudaMalloc(&m->d_blob, bytes));
+  std::vector<float> blob(m->lay.n_mf + m->lay.n_mi);
+  memcpy(blob.data(), m->mf.data(), sizeof(float) * m->lay.n_mf);
+  memcpy(blob.data() + m->lay.n_mf, m->mi.data(), sizeof(int) * m->lay.n_mi);
+  CK(cudaMemcpy(m->d_blob, blob.data(), bytes, cudaMemcpyHostToDevice));
+  return ABR_OK;
+}
+
+// ================================================================================ C ABI
+extern "C" {
+
+const char* abr_last_error(void) { return g_err.c_str(); }
+int abr_version(void) { return ABR_VERSION; }
+size_t abr_sizeof_model_host(void) { return sizeof(AbrModelHost); }
+size_t abr_sizeof_opt(void) { return sizeof(AbrOpt); }
+int abr_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int abr_model_create(const AbrModelHost* host, int device, AbrModel** out) {
+  if (!host || !out) return fail(ABR_EINVAL, "abr_model_create: null argument");
+  *out = nullptr;
+  if (abr_device_count() <= 0) return fail(ABR_ENODEVICE, "no CUDA device: the engine has no CPU path");
+  if (host->nq < 0 || host->nv < 0 || host->nbody < 1) return fail(ABR_EINVAL, "abr_model_create: bad sizes");
+  AbrModel* m = new AbrModel();
+  m->device = device;
+  copy_host_model(host, m->hm);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete m; return fail(ABR_ECUDA, "cudaGetDeviceProperties failed"); }
+  m->num_sms = prop.multiProcessorCount;
+  m->max_smem = (int)prop.sharedMemPerBlockOptin;
+  int rc = rebuild(m);
+  if (rc) { delete m; return rc; }
+  if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess) { delete m; return fail(ABR_ECUDA, "cudaStreamCreate failed"); }
+  *out = m;
+  return ABR_OK;
+}
+
+int abr_model_destroy(AbrModel* m) {
+  if (!m) return ABR_OK;
+  cudaSetDevice(m->device);
+  if (m->d_blob) cudaFree(m->d_blob);
+  m->s_costs.release(); m->s_in.release(); m->s_out.release(); m->s_dbg.release();
+  if (m->stream) cudaStreamDestroy(m->stream);
+  delete m;
+  return ABR_OK;
+}
+
+int abr_model_set_opt(AbrModel* m, const AbrOpt* opt) {
+  if (!m || !opt) return fail(ABR_EINVAL, "abr_model_set_opt: null argument");
+  AbrOpt old = m->hm.opt;
+  m->hm.opt = *opt;
+  int rc = rebuild(m);
+  if (rc) { m->hm.opt = old; rebuild(m); }
+  return rc;
+}
+
+int abr_model_get_opt(const AbrModel* m, AbrOpt* opt) {
+  if (!m || !opt) return fail(ABR_EINVAL, "abr_model_get_opt: null argument");
+  *opt = m->hm.opt;
+  return ABR_OK;
+}
+
+int abr_model_info(const AbrModel* m, int* ncon, int* ne, int* nl, int* nefc, int* depth) {
+  if (!m) return fail(ABR_EINVAL, "abr_model_info: null model");
+  if (ncon) *ncon = m->lay.ncon;
+  if (ne) *ne = m->lay.ne;
+  if (nl) *nl = m->lay.nl;
+  if (nefc) *nefc = m->lay.nefc;
+  if (depth) *depth = m->lay.depth;
+  return ABR_OK;
+}
+
+int abr_model_set_lanes(AbrModel* m, int lanes) {
+  if (!m) return fail(ABR_EINVAL, "abr_model_set_lanes: null model");
+  if (lanes != 0 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32) return fail(ABR_EINVAL, "lanes must be 0, 4, 8, 16 or 32");
+  m->lanes = lanes;
+  return ABR_OK;
+}
+
+int abr_cost_create(const AbrQuadCostHost* h, int device, AbrCost** out) {
+  if (!h || !out || !h->Q || !h->Qf || !h->R || !h->xg) return fail(ABR_EINVAL, "abr_cost_create: null argument");
+  *out = nullptr;
+  if (abr_device_count() <= 0) return fail(ABR_ENODEVICE, "no CUDA device: the engine has no CPU path");
+  const int nx = h->nx, nu = h->nu;
+  std::vector<float> buf((size_t)2 * nx * nx + nu * nu + 3 * nx + nu);
+  float* p = buf.data();
+  memcpy(p, h->Q, sizeof(float) * nx * nx); p += nx * nx;
+  memcpy(p, h->Qf, sizeof(float) * nx * nx); p += nx * nx;
+  memcpy(p, h->R, sizeof(float) * nu * nu); p += nu * nu;
+  memcpy(p, h->xg, sizeof(float) * nx); p += nx;
+  bool diag = true;
+  for (int i = 0; i < nx; i++)
+    for (int j = 0; j < nx; j++)
+      if (i != j && (h->Q[i * nx + j] != 0.f || h->Qf[i * nx + j] != 0.f)) diag = false;
+  for (int i = 0; i < nu; i++)
+    for (int j = 0; j < nu; j++)
+      if (i != j && h->R[i * nu + j] != 0.f) diag = false;
+  for (int i = 0; i < nx; i++) p[i] = h->Q[i * nx + i];
+  p += nx;
+  for (int i = 0; i < nx; i++) p[i] = h->Qf[i * nx + i];
+  p += nx;
+  for (int i = 0; i < nu; i++) p[i] = h->R[i * nu + i];
+  AbrCost* c = new AbrCost();
+  c->device = device; c->nx = nx; c->nu = nu; c->diag = diag ? 1 : 0;
+  if (cudaSetDevice(device) != cudaSuccess || cudaMalloc(&c->d, sizeof(float) * buf.size()) != cudaSuccess ||
+      cudaMemcpy(c->d, buf.data(), sizeof(float) * buf.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+    delete c;
+    return fail(ABR_ECUDA, std::string("abr_cost_create: ") + cudaGetErrorString(cudaGetLastError()));
+  }
+  *out = c;
+  return ABR_OK;
+}
+
+int abr_cost_destroy(AbrCost* c) {
+  if (!c) return ABR_OK;
+  cudaSetDevice(c->device);
+  if (c->d) cudaFree(c->d);
+  delete c;
+  return ABR_OK;
+}
+
+int abr_rollout_dev(AbrModel* m, const float* x0, int x0_stride, const float* us, int us_stride, int nworld, int N,
+                    float* xs_out, const AbrCost* cost, float* costs_out, void* stream) {
+  if (!m || !x0 || (!us && N > 0)) return fail(ABR_EINVAL, "abr_rollout_dev: null argument");
+  if (nworld < 0 || N < 0) return fail(ABR_EINVAL, "abr_rollout_dev: negative size");
+  if (cost && (cost->nx != m->lay.nx || cost->nu != m->lay.nu)) return fail(ABR_EINVAL, "abr_rollout_dev: cost dimensions do not match the model");
+  if (costs_out && !cost) return fail(ABR_EINVAL, "abr_rollout_dev: costs_out without a cost");
+  CK(cudaSetDevice(m->device));
+  RolloutArgs a;
+  memset(&a, 0, sizeof(a));
+  a.blob = m->d_blob; a.x0 = x0; a.x0_stride = x0_stride; a.us = us; a.us_stride = us_stride;
+  a.mode = 0; a.nworld = nworld; a.N = N; a.xs_out = xs_out; a.costs_out = costs_out;
+  a.cost = cost_view(costs_out ? cost : nullptr);
+  return launch_rollout(m, m->lay, a, (cudaStream_t)stream);
+}
+
+int abr_rollout_host(AbrModel* m, const float* x0, int x0_stride, const float* us, int us_stride, int nworld, int N,
+                     float* xs_out, const AbrCost* cost, float* costs_out) {
+  if (!m || !x0 || (!us && N > 0)) return fail(ABR_EINVAL, "abr_rollout_host: null argument");
+  if (nworld < 0 || N < 0) return fail(ABR_EINVAL, "abr_rollout_host: negative size");
+  if (nworld == 0) return ABR_OK;
+  CK(cudaSetDevice(m->device));
+  const int nx = m->lay.nx, nu = m->lay.nu;
+  const size_t n_x0 = x0_stride ? (size_t)nworld * nx : nx;
+  const size_t n_us = us_stride ? (size_t)nworld * N * nu : (size_t)N * nu;
+  const size_t n_xs = xs_out ? (size_t)nworld * (N + 1) * nx : 0;
+  const size_t n_c = costs_out ? nworld : 0;
+  int rc = m->s_in.ensure(sizeof(float) * (n_x0 + n_us + 4));
+  if (rc) return rc;
+  rc = m->s_out.ensure(sizeof(float) * (n_xs + n_c + 4));
+  if (rc) return rc;
+  float* d_x0 = (float*)m->s_in.p; float* d_us = d_x0 + n_x0;
+  float* d_xs = (float*)m->s_out.p; float* d_c = d_xs + n_xs;
+  CK(cudaMemcpyAsync(d_x0, x0, sizeof(float) * n_x0, cudaMemcpyHostToDevice, m->stream));
+  if (n_us) CK(cudaMemcpyAsync(d_us, us, sizeof(float) * n_us, cudaMemcpyHostToDevice, m->stream));
+  rc = abr_rollout_dev(m, d_x0, x0_stride, d_us, us_stride, nworld, N, xs_out ? d_xs : nullptr, cost, costs_out ? d_c : nullptr, m->stream);
+  if (rc) return rc;
+  if (n_xs) CK(cudaMemcpyAsync(xs_out, d_xs, sizeof(float) * n_xs, cudaMemcpyDeviceToHost, m->stream));
+  if (n_c) CK(cudaMemcpyAsync(costs_out, d_c, sizeof(float) * n_c, cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  return ABR_OK;
+}
+
+int abr_predictive_sample_dev(AbrModel* m, const AbrCost* cost, const float* x0, const float* us_guess, const float* noise,
+                              unsigned long long seed, int B, int S, int N, float stdev, int sample_offset, int S_total,
+                              float* xs_star, float* us_star, int* best_idx, float* best_cost, float* costs_out, void* stream) {
+  if (!m || !cost || !x0 || !us_guess || !best_idx || !best_cost) return fail(ABR_EINVAL, "abr_predictive_sample_dev: null argument");
+  if (B <= 0 || S <= 0 || N < 0 || sample_offset < 0 || sample_offset + S > S_total) return fail(ABR_EINVAL, "abr_predictive_sample_dev: bad sizes");
+  if (cost->nx != m->lay.nx || cost->nu != m->lay.nu) return fail(ABR_EINVAL, "abr_predictive_sample_dev: cost dimensions do not match the model");
+  CK(cudaSetDevice(m->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  float* d_costs = costs_out;
+  if (!d_costs) {
+    int rc = m->s_costs.ensure(sizeof(float) * (size_t)B * S);
+    if (rc) return rc;
+    d_costs = (float*)m->s_costs.p;
+  }
+  RolloutArgs a;
+  memset(&a, 0, sizeof(a));
+  a.blob = m->d_blob; a.x0 = x0; a.x0_stride = m->lay.nx; a.us = us_guess; a.us_stride = N * m->lay.nu;
+  a.noise = noise; a.seed = seed; a.stdev = stdev; a.mode = 1; a.S = S; a.S_total = S_total; a.sample_offset = sample_offset;
+  a.nworld = B * S; a.N = N; a.costs_out = d_costs; a.cost = cost_view(cost);
+  int rc = launch_rollout(m, m->lay, a, st);
+  if (rc) return rc;
+  k_argmin<<<B, 256, 0, st>>>(d_costs, S, sample_offset, best_idx, best_cost);
+  CK(cudaGetLastError());
+  if (xs_star || us_star) {
+    // re-roll the winners (B worlds) to emit their trajectories; the S x (N+1) x nx tensor of all
+    // samples (shooting.py:152) is never materialised
+    RolloutArgs w = a;
+    w.sample_ids = best_idx; w.nworld = B; w.costs_out = nullptr; w.cost.enabled = 0;
+    w.xs_out = xs_star; w.us_out = us_star;
+    rc = launch_rollout(m, m->lay, w, st);
+    if (rc) return rc;
+  }
+  return ABR_OK;
+}
+
+int abr_predictive_sample_host(AbrModel* m, const AbrCost* cost, const float* x0, const float* us_guess, const float* noise,
+                               unsigned long long seed, int B, int S, int N, float stdev, int sample_offset, int S_total,
+                               float* xs_star, float* us_star, int* best_idx, float* best_cost, float* costs_out) {
+  if (!m || !cost || !x0 || !us_guess || !best_idx || !best_cost) return fail(ABR_EINVAL, "abr_predictive_sample_host: null argument");
+  if (B <= 0 || S <= 0 || N < 0) return fail(ABR_EINVAL, "abr_predictive_sample_host: bad sizes");
+  CK(cudaSetDevice(m->device));
+  const int nx = m->lay.nx, nu = m->lay.nu;
+  const size_t n_x0 = (size_t)B * nx, n_ug = (size_t)B * N * nu;
+  const size_t n_nz = noise ? (size_t)B * (S_total - 1) * N * nu : 0;
+  const size_t n_xs = (size_t)B * (N + 1) * nx, n_us = (size_t)B * N * nu, n_cs = (size_t)B * S;
+  int rc = m->s_in.ensure(sizeof(float) * (n_x0 + n_ug + n_nz + 4));
+  if (rc) return rc;
+  rc = m->s_out.ensure(sizeof(float) * (n_xs + n_us + n_cs + 2 * (size_t)B + 4));
+  if (rc) return rc;
+  float* d_x0 = (float*)m->s_in.p; float* d_ug = d_x0 + n_x0; float* d_nz = d_ug + n_ug;
+  float* d_xs = (float*)m->s_out.p; float* d_us = d_xs + n_xs; float* d_cs = d_us + n_us;
+  float* d_bc = d_cs + n_cs; int* d_bi = (int*)(d_bc + B);
+  CK(cudaMemcpyAsync(d_x0, x0, sizeof(float) * n_x0, cudaMemcpyHostToDevice, m->stream));
+  if (n_ug) CK(cudaMemcpyAsync(d_ug, us_guess, sizeof(float) * n_ug, cudaMemcpyHostToDevice, m->stream));
+  if (n_nz) CK(cudaMemcpyAsync(d_nz, noise, sizeof(float) * n_nz, cudaMemcpyHostToDevice, m->stream));
+  rc = abr_predictive_sample_dev(m, cost, d_x0, d_ug, noise ? d_nz : nullptr, seed, B, S, N, stdev, sample_offset, S_total,
+                                 xs_star ? d_xs : nullptr, us_star ? d_us : nullptr, d_bi, d_bc, d_cs, m->stream);
+  if (rc) return rc;
+  if (xs_star) CK(cudaMemcpyAsync(xs_star, d_xs, sizeof(float) * n_xs, cudaMemcpyDeviceToHost, m->stream));
+  if (us_star && n_us) CK(cudaMemcpyAsync(us_star, d_us, sizeof(float) * n_us, cudaMemcpyDeviceToHost, m->stream));
+  if (costs_out) CK(cudaMemcpyAsync(costs_out, d_cs, sizeof(float) * n_cs, cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaMemcpyAsync(best_idx, d_bi, sizeof(int) * B, cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaMemcpyAsync(best_cost, d_bc, sizeof(float) * B, cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  return ABR_OK;
+}
+
+int abr_forward_dev(AbrModel* m, float* qpos, float* qvel, const float* ctrl, float* qacc_warmstart, float* qacc, int E, void* stream) {
+  if (!m || !qpos || !qvel) return fail(ABR_EINVAL, "abr_forward_dev: null argument");
+  if (E < 0) return fail(ABR_EINVAL, "abr_forward_dev: negative size");
+  CK(cudaSetDevice(m->device));
+  EnvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.blob = m->d_blob; a.qpos = qpos; a.qvel = qvel; a.warm = qacc_warmstart; a.qacc = qacc; a.ctrl = ctrl;
+  a.E = E; a.nsubsteps = 0; a.forward_only = 1;
+  return launch_env(m, m->lay, a, (cudaStream_t)stream);
+}
+
+int abr_env_step_dev(AbrModel* m, float* qpos, float* qvel, float* qacc_warmstart, float* time, const float* ctrl, int E,
+                     int nsubsteps, const unsigned char* reset_mask, const float* first_qpos, const float* first_qvel,
+                     const float* first_qacc_warmstart, void* stream) {
+  if (!m || !qpos || !qvel || !qacc_warmstart) return fail(ABR_EINVAL, "abr_env_step_dev: null argument");
+  if (E < 0 || nsubsteps < 0) return fail(ABR_EINVAL, "abr_env_step_dev: negative size");
+  if (reset_mask && (!first_qpos || !first_qvel)) return fail(ABR_EINVAL, "abr_env_step_dev: reset_mask without first state");
+  CK(cudaSetDevice(m->device));
+  EnvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.blob = m->d_blob; a.qpos = qpos; a.qvel = qvel; a.warm = qacc_warmstart; a.time = time; a.ctrl = ctrl;
+  a.reset_mask = reset_mask; a.first_qpos = first_qpos; a.first_qvel = first_qvel; a.first_warm = first_qacc_warmstart;
+  a.E = E; a.nsubsteps = nsubsteps; a.forward_only = 0;
+  return launch_env(m, m->lay, a, (cudaStream_t)stream);
+}
+
+int abr_debug_forward_host(AbrModel* m, const float* qpos, const float* qvel, const float* ctrl, const float* qacc_warmstart,
+                           const char* name, float* out, int cap, int* n) {
+  if (!m || !qpos || !qvel || !name || !out || !n) return fail(ABR_EINVAL, "abr_debug_forward_host: null argument");
+  CK(cudaSetDevice(m->device));
+  const Layout& L = m->lay_dbg;
+  const int nq = L.nq, nv = L.nv, nu = L.nu;
+  int rc = m->s_dbg.ensure(sizeof(float) * ((size_t)nq + 3 * nv + nu + L.world_stride + 8));
+  if (rc) return rc;
+  float* d_q = (float*)m->s_dbg.p; float* d_v = d_q + nq; float* d_w = d_v + nv; float* d_a = d_w + nv;
+  float* d_c = d_a + nv; float* d_dbg = d_c + nu;
+  std::vector<float> zero(std::max(nv, nu) + 1, 0.f);
+  CK(cudaMemcpy(d_q, qpos, sizeof(float) * nq, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_v, qvel, sizeof(float) * nv, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_w, qacc_warmstart ? qacc_warmstart : zero.data(), sizeof(float) * nv, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_c, ctrl ? ctrl : zero.data(), sizeof(float) * nu, cudaMemcpyHostToDevice));
+  EnvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.blob = m->d_blob; a.qpos = d_q; a.qvel = d_v; a.warm = d_w; a.qacc = d_a; a.ctrl = d_c;
+  a.E = 1; a.forward_only = 1; a.dbg = d_dbg;
+  rc = launch_env(m, L, a, m->stream);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(m->stream));
+  std::vector<float> W(L.world_stride);
+  CK(cudaMemcpy(W.data(), d_dbg, sizeof(float) * L.world_stride, cudaMemcpyDeviceToHost));
+  std::vector<float> res;
+  const std::string s(name);
+  auto span = [&](int off, int cnt) { res.assign(W.begin() + off, W.begin() + off + cnt); };
+  auto unpack = [&](int off) {  // packed lower -> dense symmetric
+    res.assign((size_t)nv * nv, 0.f);
+    for (int i = 0; i < nv; i++) for (int j = 0; j <= i; j++) { res[i * nv + j] = W[off + i * (i + 1) / 2 + j]; res[j * nv + i] = res[i * nv + j]; }
+  };
+  const int nb = L.nbody;
+  if (s == "qpos") span(L.w_qpos, nq);
+  else if (s == "xpos") span(L.w_xpos, 3 * nb);
+  else if (s == "xquat") span(L.w_xquat, 4 * nb);
+  else if (s == "xipos") span(L.w_xipos, 3 * nb);
+  else if (s == "xanchor") span(L.w_xanchor, 3 * L.njnt);
+  else if (s == "xaxis") span(L.w_xaxis, 3 * L.njnt);
+  else if (s == "subtree_com") span(L.w_rootcom, 3 * L.nroot);  // per kinematic root
+  else if (s == "cinert") span(L.w_cinert, 10 * nb);
+  else if (s == "cdof") span(L.w_cdof, 6 * nv);
+  else if (s == "crb") span(L.w_crb, 10 * nb);
+  else if (s == "qM") unpack(L.w_M);
+  else if (s == "cvel") span(L.w_cvel, 6 * nb);
+  else if (s == "cdof_dot") span(L.w_cdofdot, 6 * nv);
+  else if (s == "contact_dist") span(L.w_cdist, L.ncon);
+  else if (s == "contact_pos") span(L.w_cpos, 3 * L.ncon);
+  else if (s == "contact_frame") span(L.w_cframe, 9 * L.ncon);
+  else if (s == "qfrc_smooth") span(L.w_fs, nv);
+  else if (s == "qacc_smooth") span(L.w_as, nv);
+  else if (s == "qacc") span(L.w_a, nv);
+  else if (s == "qacc_warmstart") span(L.w_warm, nv);
+  else if (s == "qfrc_constraint") span(L.w_fc, nv);
+  else if (s == "efc_force") span(L.w_force, L.nefc);
+  else if (s == "efc_D") span(L.w_D, L.nefc);
+  else if (s == "efc_aref") span(L.w_aref, L.nefc);
+  else if (s == "efc_J") {
+    res.assign((size_t)L.nefc * nv, 0.f);
+    const std::vector<int>& mi = m->mi;  // same tables for both layouts
+    const std::vector<float>& mf = m->mf;
+    for (int r = 0; r < L.nefc; r++) {
+      const int info = mi[L.i_row_info + r];
+      const int kind = info & 3, idx = (info >> 2) & 0x3ffff, sub = info >> 20;
+      if (kind == 0) {
+        const int j1 = mi[L.i_eq_j1 + idx], j2 = mi[L.i_eq_j2 + idx];
+        if (j2 >= 0) res[r * nv + mi[L.i_jnt_dofadr + j2]] = W[L.w_eqc + idx];
+        res[r * nv + mi[L.i_jnt_dofadr + j1]] = 1.f;
+      } else if (kind == 1) {
+        res[r * nv + mi[L.i_jnt_dofadr + mi[L.i_lim_jnt + idx]]] = W[L.w_lims + idx];
+      } else {
+        const bool active = W[L.w_D + r] != 0.f;  // MJX zeroes inactive rows
+        const float* prm = &mf[L.f_con_prm + kConPrm * mi[L.i_con_pair + idx]];
+        for (int d = 0; d < nv && active; d++) {
+          float v = W[L.w_B + (3 * idx) * nv + d];
+          if (mi[L.i_con_condim + idx] == 3) {
+            const float mu = prm[11 + (sub >> 1)];
+            v += ((sub & 1) ? -mu : mu) * W[L.w_B + (3 * idx + 1 + (sub >> 1)) * nv + d];
+          }
+          res[r * nv + d] = v;
+        }
+      }
+    }
+  } else {
+    return fail(ABR_EINVAL, "abr_debug_forward_host: unknown field " + s);
+  }
+  *n = (int)res.size();
+  if (*n > cap) return fail(ABR_EINVAL, "abr_debug_forward_host: output buffer too small");
+  memcpy(out, res.data(), sizeof(float) * res.size());
+  return ABR_OK;
+}
+
+int abr_ffma_peak(int device, double* tflops, double* ms_out) {
+  if (!tflops) return fail(ABR_EINVAL, "abr_ffma_peak: null argument");
+  if (abr_device_count() <= 0) return fail(ABR_ENODEVICE, "no CUDA device");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  float* d = nullptr;
+  CK(cudaMalloc(&d, 4));
+  const int grid = prop.multiProcessorCount * 2, tpb = 1024, iters = 4096;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  for (int i = 0; i < 2; i++) k_ffma<<<grid, tpb>>>(d, iters, 1.0000001f, 1e-9f);
+  CK(cudaEventRecord(e0));
+  k_ffma<<<grid, tpb>>>(d, iters, 1.0000001f, 1e-9f);
+  CK(cudaEventRecord(e1));
+  CK(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  const double flops = 2.0 * 8 * 16 * (double)iters * (double)grid * tpb;
+  *tflops = flops / (ms * 1e-3) / 1e12;
+  if (ms_out) *ms_out = ms;
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+  return ABR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,5 @@
+// instantiation of the fused kernels for G = 16 lanes per world
+#include "abr_kernels.cuh"
+namespace abr {
+ABR_DEFINE_LAUNCHERS(16)
+}

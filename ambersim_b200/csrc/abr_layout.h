@@ -1,0 +1,65 @@
+// abr_layout.h — device-side model blob + per-world shared-memory layout.
+//
+// The flattened model (AbrModelHost, include/abr.h) is repacked at abr_model_create into one
+// float pool and one int pool ("blob") that every CTA stages into shared memory once; the
+// Layout struct (all offsets/dims/options) travels by value as a __grid_constant__ kernel
+// parameter, so every offset is a constant-bank operand.
+#ifndef ABR_LAYOUT_H_
+#define ABR_LAYOUT_H_
+
+namespace abr {
+
+// per-row constant block produced on the host from (solref, solimp, timestep, flags):
+//   [0] k  [1] b  [2] dmin  [3] dmax  [4] 1/width  [5] mid  [6] power  [7] invweight
+//   [8] 1/mid^(power-1)  [9] 1/(1-mid)^(power-1)
+// contact pairs append: [10] invweight of tangent 2  [11] mu1  [12] mu2  [13] includemargin
+constexpr int kRowPrm = 10;
+constexpr int kConPrm = 14;
+constexpr int kActPrm = 11;  // ctrlrange[2] forcerange[2] gainprm[3] biasprm[3] gear
+
+struct Layout {
+  // ---- dims
+  int nq, nv, nu, nbody, njnt, ngeom, npair, nx;
+  int ne, nl, ncon, nefc;      // static constraint sizes (MJX era: inactive rows are zeroed)
+  int depth;                   // deepest body level (world = 0)
+  int nroot;                   // kinematic roots (bodies whose parent is the world)
+  int nmpair;                  // nonzero lower-triangular entries of the joint-space inertia
+  int ntri;                    // nv*(nv+1)/2
+  // ---- options
+  int integrator, solver, iterations, ls_iterations, disableflags;
+  float timestep, tolerance, ls_tolerance, meaninertia, impratio;
+  float gravity[3];
+  // ---- blob sizes
+  int n_mf, n_mi;
+  // ---- float pool offsets
+  int f_body_pos, f_body_quat, f_body_ipos, f_body_iquat, f_body_mass, f_body_inertia;
+  int f_jnt_pos, f_jnt_axis, f_jnt_range, f_jnt_margin, f_jnt_stiffness;
+  int f_dof_armature, f_dof_damping;
+  int f_qpos0, f_qpos_spring;
+  int f_geom_size, f_geom_pos, f_geom_quat;
+  int f_eq_prm, f_eq_data, f_lim_prm, f_con_prm, f_act_prm;
+  // ---- int pool offsets
+  int i_body_parent, i_body_jntadr, i_body_jntnum, i_body_dofadr, i_body_dofnum, i_body_rootslot;
+  int i_body_childadr, i_body_childnum, i_child;
+  int i_level_adr, i_level_body;
+  int i_jnt_type, i_jnt_qposadr, i_jnt_dofadr, i_jnt_body;
+  int i_dof_body, i_dof_jnt, i_dof_limrow, i_dof_actadr, i_dof_actnum, i_dof_act;
+  int i_mpair;      // (i << 16) | j  for every nonzero lower entry of M
+  int i_tri;        // (i << 16) | j  for every packed lower entry k
+  int i_root_body;
+  int i_lim_jnt, i_eq_j1, i_eq_j2;
+  int i_con_pair, i_con_sub, i_con_row, i_con_condim, i_con_dofmask;
+  int i_row_info;   // per efc row: kind (0 eq, 1 limit, 2 contact) | idx << 2 | sub << 20
+  int i_pair_g1, i_pair_g2, i_pair_kind, i_geom_body;
+  int i_act_jnt, i_act_flags;
+  // ---- per-world shared-memory offsets (floats)
+  int w_qpos, w_qvel, w_warm, w_ctrl, w_M, w_eqc, w_lims, w_B, w_D, w_aref, w_fs, w_as, w_H;
+  int w_xpos, w_xquat, w_xipos, w_xanchor, w_xaxis, w_rootcom, w_cinert, w_cdof;
+  int w_crb, w_buf, w_cvel, w_cacc, w_cdofdot, w_cdist, w_cpos, w_cframe, w_actf, w_bv;
+  int w_a, w_Ma, w_grad, w_search, w_mv, w_fc, w_Jaref, w_jv, w_force, w_Fc, w_WB, w_y;
+  int w_rk;         // RK4 save area: qpos0[nq] qvel0[nv] warm0[nv] sv[nv] sa[nv] kq[nv]
+  int world_stride; // floats per world
+};
+
+}  // namespace abr
+#endif

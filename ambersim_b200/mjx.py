@@ -1,0 +1,260 @@
+"""Drop-in for the slice of `mujoco.mjx` that ambersim's hot path uses.
+
+    mjx.device_put(mj_model) -> Model     (reference call sites: io_utils.py:225, rl/base.py:52)
+    mjx.make_data(model)     -> Data      (io_utils.py:226, shooting.py:34)
+    mjx.forward(model, data) -> Data      (shooting.py:36, rl/base.py:85)
+    mjx.step(model, data)    -> Data      (shooting.py:41, rl/base.py:93)
+
+`Model` keeps the `mjx.Model` field names (numpy on the host, a device-resident blob behind the
+C ABI); `Data` keeps the `mjx.Data` field names for the state that persists across steps, as torch
+CUDA tensors (JAX is not present in this image; torch is the array/stream plumbing). All physics
+runs in the CUDA engine (libabr.so); there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+import enum
+from typing import Optional
+
+import numpy as np
+import torch
+
+from ambersim_b200 import _abi, _lib
+from ambersim_b200.utils.mjcf import MjModel, Option
+
+
+class DisableBit(enum.IntFlag):
+    """mujoco.mjx._src.types.DisableBit (used by tests/trajopt/test_predictive_sampler.py:7,29)."""
+
+    CONSTRAINT = 1
+    EQUALITY = 2
+    FRICTIONLOSS = 4
+    LIMIT = 8
+    CONTACT = 16
+    PASSIVE = 32
+    GRAVITY = 64
+    CLAMPCTRL = 128
+    WARMSTART = 256
+    FILTERPARENT = 512
+    ACTUATION = 1024
+    REFSAFE = 2048
+    SENSOR = 4096
+    EULERDAMP = 16384
+
+
+class IntegratorType(enum.IntEnum):
+    EULER = 0
+    RK4 = 1
+
+
+class SolverType(enum.IntEnum):
+    CG = 1
+    NEWTON = 2
+
+
+_MODEL_FIELDS = [
+    "nq", "nv", "nu", "na", "nbody", "njnt", "ngeom", "neq", "npair",
+    "body_parentid", "body_rootid", "body_jntnum", "body_jntadr", "body_dofnum", "body_dofadr", "body_pos",
+    "body_quat", "body_ipos", "body_iquat", "body_mass", "body_subtreemass", "body_inertia", "body_invweight0",
+    "jnt_type", "jnt_qposadr", "jnt_dofadr", "jnt_bodyid", "jnt_limited", "jnt_solref", "jnt_solimp", "jnt_pos",
+    "jnt_axis", "jnt_stiffness", "jnt_range", "jnt_margin",
+    "dof_bodyid", "dof_jntid", "dof_parentid", "dof_armature", "dof_damping", "dof_invweight0",
+    "geom_type", "geom_bodyid", "geom_size", "geom_pos", "geom_quat",
+    "pair_geom1", "pair_geom2", "pair_kind", "pair_condim", "pair_friction", "pair_solref", "pair_solimp",
+    "pair_includemargin",
+    "eq_type", "eq_obj1id", "eq_obj2id", "eq_active", "eq_solref", "eq_solimp", "eq_data",
+    "actuator_trnid", "actuator_gaintype", "actuator_biastype", "actuator_ctrllimited", "actuator_forcelimited",
+    "actuator_ctrlrange", "actuator_forcerange", "actuator_gainprm", "actuator_biasprm", "actuator_gear",
+    "qpos0", "qpos_spring",
+]
+
+
+class _Handle:
+    """Owns one AbrModel* (device-resident blob) and frees it with the Python object."""
+
+    def __init__(self, model: "Model", device: int):
+        L = _lib.lib()
+        host, keep = _abi.pack_model(model, model.opt)
+        ptr = C.c_void_p()
+        _lib.check(L.abr_model_create(C.byref(host), device, C.byref(ptr)))
+        self.ptr = ptr
+        self.device = device
+        info = [C.c_int() for _ in range(5)]
+        _lib.check(L.abr_model_info(ptr, *[C.byref(i) for i in info]))
+        self.ncon, self.ne, self.nl, self.nefc, self.depth = (i.value for i in info)
+        del keep
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                _lib.lib().abr_model_destroy(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+class Model:
+    """Mirror of `mjx.Model`: same field names, numpy host arrays + a device blob created lazily."""
+
+    def __init__(self, mj_model: MjModel, opt: Optional[Option] = None):
+        for f in _MODEL_FIELDS:
+            setattr(self, f, getattr(mj_model, f))
+        self.opt = mj_model.opt if opt is None else opt
+        self.stat = mj_model.stat
+        self.names = mj_model.names
+        self.keyframes = mj_model.keyframes
+        self.n_unsupported_pairs = mj_model.n_unsupported_pairs
+        self.unsupported_reason = mj_model.unsupported_reason
+        self._mj = mj_model
+        self._handles = {}
+        self._lanes = 0
+
+    @property
+    def nx(self) -> int:
+        return self.nq + self.nv
+
+    def replace(self, **kw) -> "Model":
+        """`model.replace(opt=model.opt.replace(...))` (tests/trajopt/test_predictive_sampler.py:22-31)."""
+        m = Model(self._mj, opt=kw.pop("opt", self.opt))
+        m._lanes = self._lanes
+        for k, v in kw.items():
+            if k not in _MODEL_FIELDS:
+                raise AttributeError(f"Model has no field {k!r}")
+            setattr(m, k, v)
+        return m
+
+    def set_lanes(self, lanes: int) -> "Model":
+        """Pin the lanes-per-world group size (0 = auto); tuning knob, not part of mjx."""
+        self._lanes = lanes
+        for h in self._handles.values():
+            _lib.check(_lib.lib().abr_model_set_lanes(h.ptr, lanes))
+        return self
+
+    def handle(self, device: Optional[int] = None) -> _Handle:
+        if device is None:
+            device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        h = self._handles.get(device)
+        if h is None:
+            contact_on = not (self.opt.disableflags & (DisableBit.CONTACT | DisableBit.CONSTRAINT))
+            if self.n_unsupported_pairs and contact_on:
+                raise NotImplementedError(
+                    f"{self.n_unsupported_pairs} colliding geom pair(s) are outside the engine's collision "
+                    f"functions ({self.unsupported_reason}); disable contacts or change the geoms")
+            h = _Handle(self, device)
+            if self._lanes:
+                _lib.check(_lib.lib().abr_model_set_lanes(h.ptr, self._lanes))
+            self._handles[device] = h
+        return h
+
+
+@dataclasses.dataclass
+class Data:
+    """Mirror of the `mjx.Data` fields that persist across steps, torch tensors.
+
+    Leading batch dimensions are allowed on every field (the reference vmaps over them).
+    """
+
+    qpos: torch.Tensor
+    qvel: torch.Tensor
+    ctrl: torch.Tensor
+    qacc: torch.Tensor
+    qacc_warmstart: torch.Tensor
+    time: torch.Tensor
+
+    def replace(self, **kw) -> "Data":
+        return dataclasses.replace(self, **kw)
+
+
+def device_put(mj_model: MjModel) -> Model:
+    """mjx.device_put(mj_model): flatten the MjModel into the structure-of-arrays the engine uploads."""
+    if isinstance(mj_model, Model):
+        return mj_model
+    return Model(mj_model)
+
+
+def _dev(device=None) -> torch.device:
+    if device is not None:
+        return torch.device(device)
+    if not torch.cuda.is_available():
+        raise RuntimeError("ambersim_b200 needs a CUDA device: the engine has no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def make_data(m: Model, device=None) -> Data:
+    """mjx.make_data(m): zeros, qpos = qpos0."""
+    dev = _dev(device)
+    f = dict(dtype=torch.float32, device=dev)
+    return Data(
+        qpos=torch.tensor(np.asarray(m.qpos0), **f), qvel=torch.zeros(m.nv, **f), ctrl=torch.zeros(m.nu, **f),
+        qacc=torch.zeros(m.nv, **f), qacc_warmstart=torch.zeros(m.nv, **f), time=torch.zeros((), **f),
+    )
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(dev: torch.device):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _flat(t: torch.Tensor, n: int, dev: torch.device, batch: tuple) -> torch.Tensor:
+    t = torch.as_tensor(t, dtype=torch.float32, device=dev)
+    return t.expand(*batch, n).reshape(-1, n).contiguous().clone()
+
+
+def _batch_shape(m: Model, d: Data) -> tuple:
+    b1 = tuple(d.qpos.shape[:-1])
+    b2 = tuple(torch.as_tensor(d.ctrl).shape[:-1])
+    return b1 if len(b1) >= len(b2) else b2
+
+
+def forward(m: Model, d: Data) -> Data:
+    """mjx.forward(m, d): fills qacc and qacc_warmstart; qpos gets its quaternions normalised."""
+    dev = d.qpos.device
+    h = m.handle(dev.index or 0)
+    batch = _batch_shape(m, d)
+    qpos, qvel = _flat(d.qpos, m.nq, dev, batch), _flat(d.qvel, m.nv, dev, batch)
+    ctrl, warm = _flat(d.ctrl, m.nu, dev, batch), _flat(d.qacc_warmstart, m.nv, dev, batch)
+    qacc = torch.empty_like(qvel)
+    E = qpos.shape[0]
+    _lib.check(_lib.lib().abr_forward_dev(h.ptr, _ptr(qpos), _ptr(qvel), _ptr(ctrl), _ptr(warm), _ptr(qacc), E, _stream(dev)))
+    rs = lambda t, n: t.reshape(*batch, n)
+    return d.replace(qpos=rs(qpos, m.nq), qvel=rs(qvel, m.nv), ctrl=rs(ctrl, m.nu), qacc=rs(qacc, m.nv),
+                     qacc_warmstart=rs(warm, m.nv))
+
+
+def step(m: Model, d: Data, nsubsteps: int = 1) -> Data:
+    """mjx.step(m, d) (x nsubsteps with ctrl held: MjxEnv.pipeline_step, rl/base.py:88-96)."""
+    dev = d.qpos.device
+    h = m.handle(dev.index or 0)
+    batch = _batch_shape(m, d)
+    qpos, qvel = _flat(d.qpos, m.nq, dev, batch), _flat(d.qvel, m.nv, dev, batch)
+    ctrl, warm = _flat(d.ctrl, m.nu, dev, batch), _flat(d.qacc_warmstart, m.nv, dev, batch)
+    time = torch.as_tensor(d.time, dtype=torch.float32, device=dev).expand(*batch).reshape(-1).contiguous().clone()
+    E = qpos.shape[0]
+    _lib.check(_lib.lib().abr_env_step_dev(h.ptr, _ptr(qpos), _ptr(qvel), _ptr(warm), _ptr(time), _ptr(ctrl), E,
+                                           int(nsubsteps), None, None, None, None, _stream(dev)))
+    rs = lambda t, n: t.reshape(*batch, n)
+    return d.replace(qpos=rs(qpos, m.nq), qvel=rs(qvel, m.nv), ctrl=rs(ctrl, m.nu), qacc_warmstart=rs(warm, m.nv),
+                     time=time.reshape(batch))
+
+
+def debug_forward(m: Model, qpos, qvel, ctrl=None, qacc_warmstart=None, names=()):
+    """Stage dump for parity tests: one world through mjx.forward, named intermediates as numpy."""
+    h = m.handle()
+    L = _lib.lib()
+    fp = C.POINTER(C.c_float)
+    f32 = lambda a, n: np.ascontiguousarray(np.zeros(n) if a is None else a, dtype=np.float32)
+    q, v = f32(qpos, m.nq), f32(qvel, m.nv)
+    c, w = f32(ctrl, m.nu), f32(qacc_warmstart, m.nv)
+    out = {}
+    cap = max(64, h.nefc * m.nv + 16, m.nv * m.nv, 16 * m.nbody)
+    for name in names:
+        buf = np.zeros(cap, dtype=np.float32)
+        n = C.c_int()
+        _lib.check(L.abr_debug_forward_host(h.ptr, q.ctypes.data_as(fp), v.ctypes.data_as(fp), c.ctypes.data_as(fp),
+                                            w.ctypes.data_as(fp), name.encode(), buf.ctypes.data_as(fp), cap, C.byref(n)))
+        out[name] = buf[: n.value].copy()
+    return out

@@ -1,0 +1,246 @@
+"""shoot + vanilla predictive sampling on the CUDA engine (reference ambersim/trajopt/shooting.py).
+
+Same names and argument meaning as the reference:
+    shoot(m, x0, us) -> xs                                        (shooting.py:22-48)
+    VanillaPredictiveSampler(model, cost_function, nsamples, stdev).optimize(params) -> (xs*, us*)
+                                                                  (shooting.py:96-157)
+The reference vmaps `shoot` over samples and materialises every trajectory; here one fused kernel
+rolls all samples, evaluates the quadratic cost in-flight, and only the winner's trajectory leaves
+the GPU. Leading batch dimensions stand in for jax.vmap.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+from typing import Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from ambersim_b200 import _lib, mjx
+from ambersim_b200.trajopt.base import CostFunction, TrajectoryOptimizer, TrajectoryOptimizerParams
+from ambersim_b200.trajopt.cost import StaticGoalQuadraticCost
+
+Array = Union[torch.Tensor, np.ndarray]
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _np_ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def _rollout(m: mjx.Model, x0: Array, us: Array, cost: Optional[StaticGoalQuadraticCost], want_xs: bool, want_cost: bool):
+    """Common path of `shoot`: device tensors go through abr_rollout_dev on the current stream,
+    host arrays through abr_rollout_host (copies inside the call)."""
+    L = _lib.lib()
+    nx, nu = m.nx, m.nu
+    on_device = isinstance(us, torch.Tensor) and us.is_cuda
+    if on_device:
+        dev = us.device
+        us_t = us.to(torch.float32)
+        x0_t = torch.as_tensor(x0, dtype=torch.float32, device=dev)
+        N = us_t.shape[-2]
+        batch = tuple(us_t.shape[:-2]) if us_t.dim() - 2 >= x0_t.dim() - 1 else tuple(x0_t.shape[:-1])
+        us_f = us_t.expand(*batch, N, nu).reshape(-1, N, nu).contiguous()
+        W = us_f.shape[0]
+        if x0_t.dim() == 1:
+            x0_f, stride = x0_t.contiguous(), 0
+        else:
+            x0_f, stride = x0_t.expand(*batch, nx).reshape(-1, nx).contiguous(), nx
+        h = m.handle(dev.index or 0)
+        xs = torch.empty((W, N + 1, nx), dtype=torch.float32, device=dev) if want_xs else None
+        costs = torch.empty((W,), dtype=torch.float32, device=dev) if want_cost else None
+        ch = cost.device_cost(dev.index or 0).ptr if want_cost else None
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(L.abr_rollout_dev(h.ptr, _ptr(x0_f), stride, _ptr(us_f), N * nu, W, N, _ptr(xs), ch, _ptr(costs), stream))
+        return (xs.reshape(*batch, N + 1, nx) if want_xs else None), (costs.reshape(batch) if want_cost else None)
+    us_n = np.ascontiguousarray(us.cpu().numpy() if isinstance(us, torch.Tensor) else us, dtype=np.float32)
+    x0_n = np.ascontiguousarray(x0.cpu().numpy() if isinstance(x0, torch.Tensor) else x0, dtype=np.float32)
+    N = us_n.shape[-2]
+    batch = us_n.shape[:-2] if us_n.ndim - 2 >= x0_n.ndim - 1 else x0_n.shape[:-1]
+    us_f = np.ascontiguousarray(np.broadcast_to(us_n, (*batch, N, nu)).reshape(-1, N, nu))
+    W = us_f.shape[0]
+    if x0_n.ndim == 1:
+        x0_f, stride = x0_n, 0
+    else:
+        x0_f, stride = np.ascontiguousarray(np.broadcast_to(x0_n, (*batch, nx)).reshape(-1, nx)), nx
+    h = m.handle()
+    xs = np.empty((W, N + 1, nx), dtype=np.float32) if want_xs else None
+    costs = np.empty((W,), dtype=np.float32) if want_cost else None
+    ch = cost.device_cost(h.device).ptr if want_cost else None
+    _lib.check(L.abr_rollout_host(h.ptr, _np_ptr(x0_f), stride, _np_ptr(us_f), N * nu, W, N, _np_ptr(xs), ch, _np_ptr(costs)))
+    return (xs.reshape(*batch, N + 1, nx) if want_xs else None), (costs.reshape(batch) if want_cost else None)
+
+
+def shoot(m: mjx.Model, x0: Array, us: Array) -> Array:
+    """Rolls the model forward from x0 under the zero-order-hold controls us.
+
+    Args:
+        m: the model.
+        x0 (shape=(nq+nv,) or (..., nq+nv)): initial state(s), x = [qpos; qvel].
+        us (shape=(N, nu) or (..., N, nu)): control sequence(s).
+
+    Returns:
+        xs (shape=(..., N+1, nq+nv)): state trajectory, row 0 is x0 verbatim.
+    """
+    xs, _ = _rollout(m, x0, us, None, True, False)
+    return xs
+
+
+def shoot_cost(m: mjx.Model, x0: Array, us: Array, cost_function: StaticGoalQuadraticCost) -> Array:
+    """Fused `cost(shoot(m, x0, us), us)` without materialising xs (engine extension)."""
+    _, costs = _rollout(m, x0, us, cost_function, False, True)
+    return costs
+
+
+@dataclasses.dataclass
+class ShootingParams(TrajectoryOptimizerParams):
+    """Inputs of shooting methods (reference shooting.py:58-73)."""
+
+    x0: Array = None  # shape=(nq+nv,) or (B, nq+nv)
+    us_guess: Array = None  # shape=(N, nu) or (B, N, nu)
+
+    @property
+    def N(self) -> int:
+        """Number of time steps (zero-order-hold parameterisation)."""
+        return self.us_guess.shape[-2]
+
+
+@dataclasses.dataclass
+class ShootingAlgorithm(TrajectoryOptimizer):
+    """A shooting-based trajectory optimiser (reference shooting.py:76-90)."""
+
+    def optimize(self, params: ShootingParams) -> Tuple[Array, Array]:
+        raise NotImplementedError
+
+
+@dataclasses.dataclass
+class VanillaPredictiveSamplerParams(ShootingParams):
+    """Inputs of predictive sampling (reference shooting.py:96-100).
+
+    key: random seed: an int, or an integer array/tensor (a JAX-PRNGKey-like uint32[2], or (B,2)).
+    noise: optional standard normals (S-1, N, nu) / (B, S-1, N, nu) supplied by the caller instead of
+        the engine's counter-based generator ("parity mode": pass jax.random.normal's values).
+    """
+
+    key: Union[int, Array] = 0
+    noise: Optional[Array] = None
+
+
+def _seed_of(key) -> int:
+    if isinstance(key, (int, np.integer)):
+        return int(key) & 0xFFFFFFFFFFFFFFFF
+    k = key.detach().cpu().numpy() if isinstance(key, torch.Tensor) else np.asarray(key)
+    k = k.reshape(-1).astype(np.uint64)
+    if k.size == 1:
+        return int(k[0])
+    return int((k[0] << np.uint64(32)) | (k[1] & np.uint64(0xFFFFFFFF)))
+
+
+@dataclasses.dataclass
+class VanillaPredictiveSampler(ShootingAlgorithm):
+    """Vanilla predictive sampling (reference shooting.py:103-157): fixed model, ZOH controls,
+    isotropic normal noise around the guess (sample 0 is the guess itself), quadratic cost."""
+
+    model: mjx.Model = None
+    cost_function: CostFunction = None
+    nsamples: int = 1
+    stdev: float = 0.0
+
+    def optimize(self, params: VanillaPredictiveSamplerParams, sample_offset: int = 0, nsamples_total: Optional[int] = None,
+                 return_info: bool = False):
+        """Returns (xs_star (N+1, nq+nv), us_star (N, nu)); batched inputs give batched outputs.
+
+        sample_offset / nsamples_total: this call evaluates global samples
+        [sample_offset, sample_offset + nsamples) of nsamples_total (multi-GPU sharding; the noise is
+        keyed by the global sample id, so the union over ranks equals the single-GPU result).
+        return_info: also return dict(best_idx (global), best_cost, costs).
+        """
+        m, S, L = self.model, int(self.nsamples), _lib.lib()
+        S_total = S if nsamples_total is None else int(nsamples_total)
+        nx, nu = m.nx, m.nu
+        if not isinstance(self.cost_function, StaticGoalQuadraticCost):
+            return self._optimize_generic(params, return_info)
+        on_device = isinstance(params.us_guess, torch.Tensor) and params.us_guess.is_cuda
+        seed = _seed_of(params.key)
+        if on_device:
+            dev = params.us_guess.device
+            ug = params.us_guess.to(torch.float32)
+            x0 = torch.as_tensor(params.x0, dtype=torch.float32, device=dev)
+            batched = ug.dim() == 3
+            N = ug.shape[-2]
+            ug_f = ug.reshape(-1, N, nu).contiguous()
+            B = ug_f.shape[0]
+            x0_f = x0.expand(B, nx).contiguous() if x0.dim() == 1 else x0.reshape(-1, nx).contiguous()
+            nz = None
+            if params.noise is not None:
+                nz = torch.as_tensor(params.noise, dtype=torch.float32, device=dev).expand(B, S_total - 1, N, nu).contiguous()
+            h = m.handle(dev.index or 0)
+            f = dict(dtype=torch.float32, device=dev)
+            xs_star, us_star = torch.empty((B, N + 1, nx), **f), torch.empty((B, N, nu), **f)
+            best_idx, best_cost = torch.empty((B,), dtype=torch.int32, device=dev), torch.empty((B,), **f)
+            costs = torch.empty((B, S), **f) if return_info else None
+            ch = self.cost_function.device_cost(dev.index or 0).ptr
+            stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check(L.abr_predictive_sample_dev(h.ptr, ch, _ptr(x0_f), _ptr(ug_f), _ptr(nz), seed, B, S, N, float(self.stdev),
+                                                   int(sample_offset), S_total, _ptr(xs_star), _ptr(us_star), _ptr(best_idx),
+                                                   _ptr(best_cost), _ptr(costs), stream))
+        else:
+            ug = np.ascontiguousarray(_to_np(params.us_guess), dtype=np.float32)
+            x0 = np.ascontiguousarray(_to_np(params.x0), dtype=np.float32)
+            batched = ug.ndim == 3
+            N = ug.shape[-2]
+            ug_f = np.ascontiguousarray(ug.reshape(-1, N, nu))
+            B = ug_f.shape[0]
+            x0_f = np.ascontiguousarray(np.broadcast_to(x0, (B, nx)) if x0.ndim == 1 else x0.reshape(-1, nx))
+            nz = None
+            if params.noise is not None:
+                nz = np.ascontiguousarray(np.broadcast_to(_to_np(params.noise), (B, S_total - 1, N, nu)), dtype=np.float32)
+            h = m.handle()
+            xs_star, us_star = np.empty((B, N + 1, nx), np.float32), np.empty((B, N, nu), np.float32)
+            best_idx, best_cost = np.empty((B,), np.int32), np.empty((B,), np.float32)
+            costs = np.empty((B, S), np.float32) if return_info else None
+            ch = self.cost_function.device_cost(h.device).ptr
+            _lib.check(L.abr_predictive_sample_host(h.ptr, ch, _np_ptr(x0_f), _np_ptr(ug_f), _np_ptr(nz), seed, B, S, N,
+                                                    float(self.stdev), int(sample_offset), S_total, _np_ptr(xs_star),
+                                                    _np_ptr(us_star), _np_ptr(best_idx), _np_ptr(best_cost), _np_ptr(costs)))
+        if not batched:
+            xs_star, us_star = xs_star[0], us_star[0]
+        if return_info:
+            info = dict(best_idx=best_idx if batched else best_idx[0], best_cost=best_cost if batched else best_cost[0],
+                        costs=costs if batched else costs[0])
+            return xs_star, us_star, info
+        return xs_star, us_star
+
+    def _optimize_generic(self, params: VanillaPredictiveSamplerParams, return_info: bool):
+        """User-defined CostFunction: sample + clip on the host framework, roll every sample on the
+        engine, evaluate `cost_function.cost` on the returned trajectories (reference order,
+        shooting.py:140-156). Unbatched problems only."""
+        m, S = self.model, int(self.nsamples)
+        ug = torch.as_tensor(params.us_guess, dtype=torch.float32)
+        dev = ug.device if ug.is_cuda else mjx._dev()
+        ug = ug.to(dev)
+        N = ug.shape[-2]
+        if params.noise is not None:
+            nz = torch.as_tensor(params.noise, dtype=torch.float32, device=dev)
+        else:
+            g = torch.Generator(device=dev)
+            g.manual_seed(_seed_of(params.key) & 0x7FFFFFFFFFFFFFFF)
+            nz = torch.randn((S - 1, N, m.nu), generator=g, device=dev)
+        noise = torch.cat((torch.zeros((1, N, m.nu), device=dev), nz * self.stdev), dim=0)
+        lim = torch.as_tensor(np.asarray(m.actuator_ctrlrange), dtype=torch.float32, device=dev)
+        us_samples = torch.clamp(ug + noise, lim[:, 0], lim[:, 1])
+        xs_samples = shoot(m, torch.as_tensor(params.x0, dtype=torch.float32, device=dev), us_samples)
+        costs = torch.stack([self.cost_function.cost(xs_samples[i], us_samples[i], None)[0] for i in range(S)])
+        costs_nan_first = torch.where(torch.isnan(costs), torch.full_like(costs, -float("inf")), costs)
+        best = int(torch.argmin(costs_nan_first))
+        if return_info:
+            return xs_samples[best], us_samples[best], dict(best_idx=best, best_cost=costs[best], costs=costs)
+        return xs_samples[best], us_samples[best]
+
+
+def _to_np(a):
+    return a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)

@@ -1,0 +1,37 @@
+import os
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+MODELS = {
+    "pendulum": ("models/pendulum/scene.xml", None),
+    "bh280": ("models/barrett_hand/bh280.xml", None),
+    "barkour": ("models/barkour_standin/barkour_vb_standin.xml", "home"),
+    "biped": ("models/biped_standin/biped_exo_standin.xml", "stand"),
+}
+
+
+@pytest.fixture(scope="session")
+def load_model():
+    from ambersim_b200.utils.io_utils import load_mj_model_from_file
+
+    cache = {}
+
+    def _load(name, **kw):
+        key = (name, tuple(sorted(kw.items())))
+        if key not in cache:
+            cache[key] = load_mj_model_from_file(MODELS[name][0], **kw)
+        return cache[key]
+
+    return _load

@@ -1,0 +1,77 @@
+"""Multi-GPU sharding of predictive sampling: one process per GPU, torch.distributed plumbing.
+
+Samples are independent, so rank r of R owns the contiguous global sample ids
+[r*S/R, (r+1)*S/R); the noise is keyed by the GLOBAL sample id, hence the union over ranks equals
+the single-GPU result. The only exchange is one all_gather of a small per-rank record
+{best_cost, best_idx, us*[N,nu], xs*[N+1,nx]}; every rank then takes the first minimum (NaN counts
+as minimal, lower global index wins ties) so all ranks end with identical winners and no dependent
+broadcast is needed. Rollout / env-step throughput needs no collective at all (replicas).
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(nsamples: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous global-sample range [lo, hi) owned by `rank` (sample 0, the guess, is on rank 0)."""
+    per = (nsamples + world_size - 1) // world_size
+    lo = min(nsamples, rank * per)
+    return lo, min(nsamples, lo + per)
+
+
+def first_min_index(costs: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """Index (along dim 0) of the record with minimal cost; NaN is minimal; ties -> lowest idx.
+
+    costs, idx: (R, B). Returns (B,) positions into the R records."""
+    key = torch.where(torch.isnan(costs), torch.full_like(costs, -float("inf")), costs)
+    best = key.min(dim=0, keepdim=True).values
+    cand = torch.where(key == best, idx, torch.full_like(idx, torch.iinfo(idx.dtype).max))
+    return cand.argmin(dim=0)
+
+
+def merge_best(best_cost: torch.Tensor, best_idx: torch.Tensor, xs_star: torch.Tensor, us_star: torch.Tensor, group=None):
+    """All-gather the per-rank winners and pick the global one on every rank.
+
+    best_cost (B,), best_idx (B,) global sample ids, xs_star (B,N+1,nx), us_star (B,N,nu).
+    Returns (xs_star, us_star, best_idx, best_cost) of the global winner, identical on all ranks."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return xs_star, us_star, best_idx, best_cost
+    R = dist.get_world_size(group)
+    B = best_cost.shape[0]
+    rec = torch.cat((best_cost.reshape(B, 1).float(), best_idx.reshape(B, 1).float(),
+                     us_star.reshape(B, -1).float(), xs_star.reshape(B, -1).float()), dim=1).contiguous()
+    flat = torch.empty((R * B, rec.shape[1]), dtype=rec.dtype, device=rec.device)
+    dist.all_gather_into_tensor(flat, rec, group=group)  # concatenated layout works on nccl and gloo
+    out = flat.reshape(R, B, rec.shape[1])
+    costs = out[:, :, 0]
+    idx = out[:, :, 1].to(torch.int64)
+    pick = first_min_index(costs, idx)  # (B,)
+    sel = out[pick, torch.arange(B, device=rec.device)]  # (B, rec)
+    nu_n = us_star[0].numel()
+    return (sel[:, 2 + nu_n:].reshape(xs_star.shape).to(xs_star.dtype), sel[:, 2:2 + nu_n].reshape(us_star.shape).to(us_star.dtype),
+            sel[:, 1].to(best_idx.dtype), sel[:, 0].to(best_cost.dtype))
+
+
+def sharded_optimize(sampler, params, group=None):
+    """VanillaPredictiveSampler.optimize with `sampler.nsamples` samples split over the ranks."""
+    import dataclasses
+
+    if not dist.is_initialized():
+        return sampler.optimize(params)
+    rank, R = dist.get_rank(group), dist.get_world_size(group)
+    S = int(sampler.nsamples)
+    lo, hi = shard_range(S, rank, R)
+    local = dataclasses.replace(sampler, nsamples=max(1, hi - lo))
+    ug = params.us_guess
+    batched = ug.dim() == 3
+    xs, us, info = local.optimize(params, sample_offset=min(lo, S - 1), nsamples_total=S, return_info=True)
+    if not batched:
+        xs, us = xs[None], us[None]
+        info = {k: (v[None] if hasattr(v, "dim") else v) for k, v in info.items()}
+    xs, us, idx, cost = merge_best(info["best_cost"].reshape(-1), info["best_idx"].reshape(-1), xs, us, group)
+    if not batched:
+        xs, us = xs[0], us[0]
+    return xs, us

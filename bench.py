@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the batched rollout engine (BASELINE.json configs[1], "C2"):
+
+    Barkour-vB-class stand-in, 4096 worlds x 1000 steps per GPU, random controls, contacts on,
+    fused quadratic cost; one "step" = one pass of the fused rollout over the whole batch.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
+  python bench.py --impl reference ...                     CPU arm: the oracle port on all host cores
+
+Prints ONE JSON line on rank 0 (see the keys below). `value` is whole-job world-steps/s with the
+inputs resident in HBM; `e2e` is the same pass through the host-pointer C-ABI call
+(abr_rollout_host) with pinned host buffers, copies inside the timed region.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+MODEL = "models/barkour_standin/barkour_vb_standin.xml"
+WORLDS, HORIZON = 4096, 1000
+CTRL_NOISE, JITTER = 0.1, 0.05
+# algorithmic FLOPs of one world-step: op-counting build of the CPU oracle, "necessary
+# work" variant (no unused post-iteration Hessian), home state: add=sub=mul=div=sqrt=sin=cos=pow=1.
+F_WS = 46349.0
+NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return json.loads(p.read_text()), "measured"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) >= 6 and r[2 + k] == "Active" for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def make_inputs(mj, torch, device, rank):
+    """Seeded synthetic inputs of config C2, generated on the device."""
+    g = torch.Generator(device=device)
+    g.manual_seed(1000 + rank)
+    f = dict(dtype=torch.float32, device=device)
+    q0 = np.concatenate([mj.key_qpos("home"), np.zeros(mj.nv)])
+    x0 = torch.tensor(q0, **f).repeat(WORLDS, 1)
+    x0[:, 7:19] += (torch.rand((WORLDS, 12), generator=g, **f) - 0.5) * 2 * JITTER
+    lim = torch.tensor(mj.actuator_ctrlrange, **f)
+    us = torch.tensor(mj.key_ctrl("home"), **f) + CTRL_NOISE * torch.randn((WORLDS, HORIZON, mj.nu), generator=g, **f)
+    us = torch.minimum(torch.maximum(us, lim[:, 0]), lim[:, 1]).contiguous()
+    return x0.contiguous(), us, q0
+
+
+def cost_weights(mj, q0):
+    nx = mj.nq + mj.nv
+    return np.eye(nx), 10.0 * np.eye(nx), 0.01 * np.eye(mj.nu), q0  # mirrors the reference fixture's Q, Qf, R
+
+
+def cpu_arm(mj, budget_s, nthreads):
+    """The oracle port (float32, the reference's precision) on the host cores, bounded sample."""
+    from oracle.oracle import Oracle  # test infrastructure: only this leg may use it
+
+    o = Oracle(mj)
+    rng = np.random.default_rng(0)
+    q0 = np.concatenate([mj.key_qpos("home"), np.zeros(mj.nv)])
+
+    def run(worlds, steps):
+        x0 = np.tile(q0, (worlds, 1))
+        x0[:, 7:19] += rng.uniform(-JITTER, JITTER, (worlds, 12))
+        us = np.clip(mj.key_ctrl("home") + CTRL_NOISE * rng.standard_normal((worlds, steps, mj.nu)),
+                     mj.actuator_ctrlrange[:, 0], mj.actuator_ctrlrange[:, 1])
+        t0 = time.perf_counter()
+        o.rollout(x0, us, prec=1, nthreads=nthreads, return_xs=False)
+        return worlds * steps / (time.perf_counter() - t0)
+
+    probe = run(nthreads * 8, 100)
+    worlds = int(min(WORLDS, max(nthreads, probe * budget_s / HORIZON)))
+    worlds = max(nthreads, worlds // nthreads * nthreads)
+    rate = run(worlds, HORIZON)
+    return rate, f"{worlds} worlds x {HORIZON} steps of the C2 workload, float32 oracle port, {nthreads} threads"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--lanes", type=int, default=0, help="lanes per world (0 = engine default)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-extra", action="store_true", help="skip the e2e / cpu_baseline / solve-latency legs")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+
+    from ambersim_b200.utils.io_utils import load_mj_model_from_file
+
+    mj = load_mj_model_from_file(MODEL)
+    ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    config = {"workload": "C2 (BASELINE.json configs[1]): Barkour-vB-class stand-in batched rollout, 4096 worlds x 1000 steps per GPU, "
+                          "random controls, contacts on, fused quadratic cost",
+              "worlds_per_gpu": WORLDS, "horizon": HORIZON, "ctrl_noise_std": CTRL_NOISE,
+              "model": "barkour_vb_standin (nq=19 nv=18 nu=12 nbody=14 ncon=4 nefc=28; Newton it=1 ls=5 Euler dt=.004)",
+              "l2": "per-step inputs (196.6 MB of controls per GPU) exceed the 126 MB L2"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        K, Wm = max(1, args.steps), max(0, args.warmup)
+        per = max(2.0, min(20.0, 90.0 / (K + Wm)))
+        rates = [cpu_arm(mj, per, ncores) for _ in range(Wm + K)][Wm:]
+        rate = statistics.mean(r[0] for r in rates)
+        out = {"impl": "reference", "metric": "world-steps/s", "value": rate, "unit": "world-steps/s", "n_gpus": args.gpus, "steps": K,
+               "warmup": Wm, "ms_per_step": 1e3 * WORLDS * HORIZON / rate, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+               "cpu_baseline": {"value": rate, "unit": "world-steps/s", "cores": ncores, "kind": "port", "sample": rates[-1][1],
+                                "note": "mujoco / mujoco-mjx / jax are not installable in this image; the oracle port stands in"},
+               "e2e": {"value": rate, "unit": "world-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(out), flush=True)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from ambersim_b200 import _lib, mjx
+    from ambersim_b200.trajopt.cost import StaticGoalQuadraticCost
+    from ambersim_b200.trajopt.shooting import VanillaPredictiveSampler, VanillaPredictiveSamplerParams
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    L = _lib.lib()
+    m = mjx.device_put(mj)
+    if args.lanes:
+        m.set_lanes(args.lanes)
+    h = m.handle(local)
+    x0, us, q0 = make_inputs(mj, torch, device, rank)
+    cf = StaticGoalQuadraticCost(*cost_weights(mj, q0))
+    ch = cf.device_cost(local)
+    costs = torch.empty(WORLDS, dtype=torch.float32, device=device)
+    stream = torch.cuda.current_stream(device)
+    p = lambda t: C.c_void_p(t.data_ptr())
+
+    def one_step():
+        _lib.check(L.abr_rollout_dev(h.ptr, p(x0), mj.nq + mj.nv, p(us), HORIZON * mj.nu, WORLDS, HORIZON, None, ch.ptr, p(costs),
+                                     C.c_void_p(stream.cuda_stream)))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    K, Wm = max(1, args.steps), max(3, args.warmup)
+    for _ in range(Wm):
+        one_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record(stream)
+        for _ in range(K):
+            one_step()
+        e1.record(stream)
+        barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms)
+    ms_per_step = ms_total / K
+    value = world * WORLDS * HORIZON / (ms_per_step * 1e-3)
+    finite = bool(torch.isfinite(costs).all())
+
+    out = {"metric": "world-steps/s", "value": value, "unit": "world-steps/s", "n_gpus": world, "steps": K, "warmup": Wm,
+           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic", "config": config, "clocks": clk.summary(), "gpu_launches": K, "costs_finite": finite}
+    out["config"]["lanes_per_world"] = args.lanes or "auto"
+
+    # ---- roofline of the one dominant kernel (k_rollout): FP32 FMA pipe, not HBM and not tensor cores
+    pk, pk_kind = peaks()
+    tf, tms = C.c_double(), C.c_double()
+    _lib.check(L.abr_ffma_peak(local, C.byref(tf), C.byref(tms)))
+    per_gpu_ws = WORLDS * HORIZON / (ms_per_step * 1e-3)
+    achieved_tf = F_WS * per_gpu_ws / 1e12
+    alg_bytes = WORLDS * HORIZON * mj.nu * 4 + WORLDS * (mj.nq + mj.nv) * 4 + WORLDS * 4
+    out["roofline"] = {"bound": "fp32", "achieved": achieved_tf, "peak": tf.value, "unit": "TFLOP/s", "frac": achieved_tf / tf.value,
+                       "traffic": None, "peak_kind": "FFMA microkernel timed in this run (abr_ffma_peak)",
+                       "peak_nominal": NOMINAL_FP32_TFLOPS, "frac_of_nominal": achieved_tf / NOMINAL_FP32_TFLOPS,
+                       "flop_per_world_step": F_WS,
+                       "hbm": {"achieved": alg_bytes / (ms_per_step * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                               "frac": alg_bytes / (ms_per_step * 1e-3) / 1e9 / pk["hbm_gbs"], "peak_kind": pk_kind,
+                               "algorithmic_bytes_per_launch": alg_bytes},
+                       "note": "tensor cores unused: per-world algebra is 18x18 / 28x18 (see DESIGN.md)"}
+
+    if not args.no_extra:
+        # ---- e2e: host buffers through the C-ABI host entry point, copies inside the timed region
+        x0_h, us_h = x0.cpu().pin_memory(), us.cpu().pin_memory()
+        costs_h = torch.empty(WORLDS, dtype=torch.float32).pin_memory()
+        hp = lambda t: C.c_void_p(t.data_ptr())
+
+        def e2e_step():
+            _lib.check(L.abr_rollout_host(h.ptr, hp(x0_h), mj.nq + mj.nv, hp(us_h), HORIZON * mj.nu, WORLDS, HORIZON, None, ch.ptr, hp(costs_h)))
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            e2e_step()
+        torch.cuda.synchronize(device)
+        dt = torch.tensor([time.perf_counter() - t0], device=device)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        out["e2e"] = {"value": world * WORLDS * HORIZON * K / float(dt), "unit": "world-steps/s",
+                      "h2d_bytes_per_step": int(us_h.numel() * 4 + x0_h.numel() * 4), "d2h_bytes_per_step": int(costs_h.numel() * 4),
+                      "api": "abr_rollout_host (pinned host buffers in, costs out)", "timer": "host wall clock around K calls"}
+        out["e2e_matches_device"] = bool(torch.equal(costs_h.to(device), costs))
+
+        if rank == 0:
+            # ---- second half of BASELINE's metric: 4096-sample x 32-step predictive-sampling solve latency
+            ps = VanillaPredictiveSampler(model=m, cost_function=cf, nsamples=4096, stdev=0.1)
+            prm = VanillaPredictiveSamplerParams(key=3, x0=torch.tensor(q0, dtype=torch.float32, device=device),
+                                                 us_guess=torch.tensor(mj.key_ctrl("home"), dtype=torch.float32, device=device).repeat(32, 1))
+            for _ in range(3):
+                ps.optimize(prm)
+            torch.cuda.synchronize(device)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 10
+            a.record(stream)
+            for _ in range(reps):
+                ps.optimize(prm)
+            b.record(stream)
+            torch.cuda.synchronize(device)
+            out["extra"] = {"vps_4096x32_solve_ms": a.elapsed_time(b) / reps,
+                            "vps_note": "VanillaPredictiveSampler.optimize, device-resident inputs, includes argmin + winner re-roll"}
+            rate, sample = cpu_arm(mj, args.cpu_seconds, ncores)
+            out["cpu_baseline"] = {"value": rate, "unit": "world-steps/s", "cores": ncores, "kind": "port", "sample": sample,
+                                   "note": "oracle port (float32); the reference's own CPU path (MJX on JAX-CPU, MuJoCo C) is not "
+                                           "installable in this image"}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,373 @@
+"""GPU parity tests: the CUDA engine, called through the C ABI, against the CPU oracle on the same
+seeded inputs (sizes the oracle finishes in seconds), plus size-independent properties at
+BASELINE.json's full sizes. Tolerances (float32 kernel vs float64 oracle):
+  * one forward/step from an identical state: |d| <= 1e-5 + 1e-4 |ref| on qpos/qvel, 2e-4 relative
+    on internal stages;
+  * contact-free rollouts (N <= 32): 1e-3 absolute on qpos/qvel, cost rtol 1e-3;
+  * rollouts with contacts: teacher-forced per-step comparison, cost rtol 1e-2;
+  * argmin: bit-exact against numpy.argmin of the device's own costs, and equal to the oracle's
+    index whenever the oracle's best-vs-second gap exceeds the cost tolerance.
+"""
+import numpy as np
+import pytest
+import torch
+
+from ambersim_b200 import _lib, mjx
+from ambersim_b200.rl.base import VectorEnvStepper
+from ambersim_b200.rl.pendulum.swingup import PendulumSwingupEnv
+from ambersim_b200.trajopt.base import CostFunction, CostFunctionParams
+from ambersim_b200.trajopt.cost import StaticGoalQuadraticCost
+from ambersim_b200.trajopt.shooting import VanillaPredictiveSampler, VanillaPredictiveSamplerParams, shoot, shoot_cost
+from oracle.oracle import Oracle, quad_cost
+from tests import _philox
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+STAGES = ["xpos", "xquat", "xipos", "cinert", "cdof", "qM", "cvel", "cdof_dot", "contact_dist", "contact_pos", "contact_frame",
+          "qfrc_smooth", "qacc_smooth", "efc_J", "efc_D", "efc_aref", "qacc", "efc_force", "qfrc_constraint"]
+BH_OPT = dict(timestep=0.002, iterations=1, ls_iterations=4, integrator=0, solver=2, disableflags=16)  # the reference test's options
+
+
+def t32(a):
+    return torch.as_tensor(np.asarray(a), dtype=torch.float32, device=DEV)
+
+
+def sample_state(mj, name, rng):
+    key = {"barkour": "home", "biped": "stand"}.get(name)
+    q = mj.key_qpos(key) if key else mj.qpos0.copy()
+    if name == "bh280":
+        q = q + rng.uniform(0.0, 0.5, mj.nq)
+    elif name == "pendulum":
+        q = q + rng.uniform(-2, 2, 1)
+    else:
+        q[7:] += rng.uniform(-0.1, 0.1, mj.nq - 7)
+        q[2] -= 0.004
+    v = rng.normal(size=mj.nv) * 0.3
+    c = (mj.key_ctrl(key) if key else np.zeros(mj.nu)) + rng.normal(size=mj.nu) * 0.1
+    return q, v, c
+
+
+def model_with(load_model, name, **opt):
+    mj = load_model(name)
+    if name == "bh280":
+        opt = {**BH_OPT, **opt}
+    m = mjx.device_put(mj)
+    m = m.replace(opt=m.opt.replace(**opt))
+    return mj, m, Oracle(mj, m.opt)
+
+
+@pytest.mark.parametrize("name", ["pendulum", "bh280", "barkour", "biped"])
+def test_forward_stage_parity(load_model, name):
+    mj, m, o = model_with(load_model, name)
+    rng = np.random.default_rng(0)
+    q, v, c = sample_state(mj, name, rng)
+    w = rng.normal(size=mj.nv)
+    ref = o.forward(q, v, c, w)
+    got = mjx.debug_forward(m, q, v, c, w, names=STAGES)
+    for f in STAGES:
+        r, g = ref[f].ravel(), got[f].ravel()
+        assert r.size == g.size, f
+        if r.size:
+            assert np.abs(r - g).max() <= 2e-4 * max(1e-6, np.abs(r).max()), f
+
+
+@pytest.mark.parametrize("name", ["pendulum", "bh280", "barkour", "biped"])
+@pytest.mark.parametrize("variant", ["default", "rk4", "cg", "eulerdamp", "converged", "nowarm"])
+def test_single_step_parity_option_variants(load_model, name, variant):
+    opt = dict(default={}, rk4=dict(integrator=1), cg=dict(solver=1, iterations=8, ls_iterations=10),
+               eulerdamp=dict(disableflags=0), converged=dict(iterations=30, ls_iterations=30), nowarm=dict(disableflags=16384 | 256))[variant]
+    if name == "bh280" and "disableflags" in opt:
+        opt = dict(disableflags=opt["disableflags"] | 16)
+    mj, m, o = model_with(load_model, name, **opt)
+    rng = np.random.default_rng(11)
+    E = 6
+    states = [sample_state(mj, name, rng) for _ in range(E)]
+    q = np.stack([s[0] for s in states]); v = np.stack([s[1] for s in states]); c = np.stack([s[2] for s in states])
+    w = rng.normal(size=(E, mj.nv))
+    d = mjx.Data(qpos=t32(q), qvel=t32(v), ctrl=t32(c), qacc=torch.zeros(E, mj.nv, device=DEV), qacc_warmstart=t32(w),
+                 time=torch.zeros(E, device=DEV))
+    d1 = mjx.step(m, d)
+    for e in range(E):
+        qr, vr, wr, tr = o.step(q[e], v[e], c[e], w[e])
+        assert np.all(np.abs(d1.qpos[e].cpu().numpy() - qr) <= 1e-5 + 1e-4 * np.abs(qr))
+        assert np.all(np.abs(d1.qvel[e].cpu().numpy() - vr) <= 2e-5 + 2e-4 * np.abs(vr))
+        assert np.abs(d1.qacc_warmstart[e].cpu().numpy() - wr).max() <= 1e-3 * max(1.0, np.abs(wr).max())
+        assert abs(float(d1.time[e]) - tr) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["pendulum", "bh280"])
+@pytest.mark.parametrize("lanes", [4, 8, 16, 32])
+def test_contact_free_rollout_parity(load_model, name, lanes):
+    mj, m, o = model_with(load_model, name)
+    m.set_lanes(lanes)
+    rng = np.random.default_rng(2)
+    W, N = 5, 32
+    x0 = np.stack([np.concatenate(sample_state(mj, name, rng)[:2]) for _ in range(W)])
+    us = rng.normal(size=(W, N, mj.nu)) * 0.5
+    xs = shoot(m, t32(x0), t32(us)).cpu().numpy()
+    ref = o.rollout(x0, us)
+    assert xs.shape == (W, N + 1, mj.nq + mj.nv)
+    assert np.array_equal(xs[:, 0], x0.astype(np.float32))  # row 0 is the caller's x0 verbatim
+    assert np.abs(xs - ref).max() < 1e-3
+    eye = np.eye(mj.nq + mj.nv)
+    cf = StaticGoalQuadraticCost(eye, 10 * eye, 0.01 * np.eye(mj.nu), np.zeros(mj.nq + mj.nv))
+    costs = shoot_cost(m, t32(x0), t32(us), cf).cpu().numpy()
+    assert np.allclose(costs, quad_cost(ref, us, eye, 10 * eye, 0.01 * np.eye(mj.nu), 0.0), rtol=1e-3)
+
+
+@pytest.mark.parametrize("name", ["barkour", "biped"])
+@pytest.mark.parametrize("lanes", [4, 8, 16, 32])
+def test_contact_rollout_teacher_forced(load_model, name, lanes):
+    mj, m, o = model_with(load_model, name)
+    m.set_lanes(lanes)
+    rng = np.random.default_rng(4)
+    N = 40
+    q, v, c = sample_state(mj, name, rng)
+    x0 = np.concatenate([q, v])
+    us = np.clip(c + 0.1 * rng.normal(size=(N, mj.nu)), mj.actuator_ctrlrange[:, 0], mj.actuator_ctrlrange[:, 1])
+    ref = o.rollout(x0, us)
+    # free-running comparison (chaotic once contacts switch, so a loose bound) ...
+    xs = shoot(m, t32(x0), t32(us)).cpu().numpy()
+    assert np.abs(xs - ref).max() < 5e-3
+    # ... and teacher-forced: every step restarted from the oracle's state, with the oracle's warm start
+    qs, vs, ws = [], [], []
+    qq, vv, ww = x0[: mj.nq].copy(), x0[mj.nq:].copy(), o.forward(x0[: mj.nq], x0[mj.nq:])["qacc_warmstart"]
+    for t in range(N):
+        qs.append(qq); vs.append(vv); ws.append(ww)
+        qq, vv, ww, _ = o.step(qq, vv, us[t], ww)
+    d = mjx.Data(qpos=t32(np.stack(qs)), qvel=t32(np.stack(vs)), ctrl=t32(us), qacc=torch.zeros(N, mj.nv, device=DEV),
+                 qacc_warmstart=t32(np.stack(ws)), time=torch.zeros(N, device=DEV))
+    d1 = mjx.step(m, d)
+    assert np.all(np.abs(d1.qpos.cpu().numpy() - ref[1:, : mj.nq]) <= 1e-5 + 1e-4 * np.abs(ref[1:, : mj.nq]))
+    assert np.all(np.abs(d1.qvel.cpu().numpy() - ref[1:, mj.nq:]) <= 5e-5 + 5e-4 * np.abs(ref[1:, mj.nq:]))
+    eye = np.eye(mj.nq + mj.nv)
+    cf = StaticGoalQuadraticCost(eye, 10 * eye, 0.01 * np.eye(mj.nu), x0)
+    cost = float(shoot_cost(m, t32(x0), t32(us), cf).cpu())
+    assert np.isclose(cost, quad_cost(ref, us, eye, 10 * eye, 0.01 * np.eye(mj.nu), x0), rtol=1e-2)
+
+
+def test_shoot_shapes_and_host_api(load_model):
+    """x0 (nx,) with us (S,N,nu) = vmap(shoot,(None,None,0)); x0 (B,nx) with us (B,N,nu) =
+    vmap(shoot,(None,0,0)) (tests/trajopt/test_predictive_sampler.py:85); numpy in -> numpy out."""
+    mj, m, o = model_with(load_model, "bh280")
+    rng = np.random.default_rng(5)
+    x0 = rng.normal(size=16) * 0.2
+    us = rng.normal(size=(7, 10, 4))
+    a = shoot(m, t32(x0), t32(us))
+    b = shoot(m, t32(np.tile(x0, (7, 1))), t32(us))
+    assert a.shape == (7, 11, 16) and torch.equal(a, b)
+    single = shoot(m, t32(x0), t32(us[3]))
+    assert single.shape == (11, 16) and torch.equal(single, a[3])
+    host = shoot(m, x0.astype(np.float32), us.astype(np.float32))
+    assert isinstance(host, np.ndarray) and np.array_equal(host, a.cpu().numpy())
+    empty = shoot(m, t32(x0), t32(np.zeros((0, 4))))  # N = 0: just x0
+    assert empty.shape == (1, 16) and np.array_equal(empty.cpu().numpy()[0], x0.astype(np.float32))
+
+
+# ------------------------------------------------------------------ predictive sampler
+@pytest.fixture
+def vps_data(load_model):
+    """The reference fixture (tests/trajopt/test_predictive_sampler.py:17-41): bh280, contacts off,
+    Q = I, Qf = 10 I, R = 0.01 I, xg = 0, 100 samples, stdev 0.01."""
+    mj, model, o = model_with(load_model, "bh280")
+    nx = model.nq + model.nv
+    cost_function = StaticGoalQuadraticCost(Q=torch.eye(nx), Qf=10.0 * torch.eye(nx), R=0.01 * torch.eye(model.nu), xg=torch.zeros(nx))
+    ps = VanillaPredictiveSampler(model=model, cost_function=cost_function, nsamples=100, stdev=0.01)
+    return ps, model, cost_function, o
+
+
+def test_smoke_VPS(vps_data):
+    ps, model, _, _ = vps_data
+    params = VanillaPredictiveSamplerParams(key=0, x0=torch.zeros(model.nq + model.nv, device=DEV),
+                                            us_guess=torch.zeros((10, model.nu), device=DEV))
+    xs_star, us_star = ps.optimize(params)
+    assert xs_star.shape == (11, 16) and us_star.shape == (10, 4)
+    assert torch.isfinite(xs_star).all() and torch.isfinite(us_star).all()
+
+
+def test_VPS_cost_decrease(vps_data):
+    ps, model, cost_function, _ = vps_data
+    g = torch.Generator(device=DEV).manual_seed(0)
+    B, N = 10, 10
+    x0 = torch.randn((B, model.nq + model.nv), generator=g, device=DEV)
+    us_guess = torch.randn((B, N, model.nu), generator=g, device=DEV)
+    xs_stars, us_stars = ps.optimize(VanillaPredictiveSamplerParams(key=torch.tensor([0, 7]), x0=x0, us_guess=us_guess))
+    costs_star, _ = cost_function.cost(xs_stars, us_stars, CostFunctionParams())
+    xs_guess = shoot(model, x0, us_guess)
+    costs_guess, _ = cost_function.cost(xs_guess, us_guess, CostFunctionParams())
+    assert torch.all(costs_star <= costs_guess)
+
+
+def test_VPS_parity_mode_against_oracle(vps_data):
+    """Caller-supplied normals: the engine's costs match the oracle's, the device argmin is the numpy
+    argmin of its own costs bit-exactly, and equals the oracle's wherever the gap is resolvable."""
+    ps, model, cf, o = vps_data
+    rng = np.random.default_rng(7)
+    B, S, N = 3, 100, 10
+    x0 = rng.normal(size=(B, 16)) * 0.3
+    ug = rng.normal(size=(B, N, 4))
+    noise = rng.normal(size=(B, S - 1, N, 4))
+    xs, us, info = ps.optimize(VanillaPredictiveSamplerParams(key=0, x0=t32(x0), us_guess=t32(ug), noise=t32(noise)), return_info=True)
+    costs = info["costs"].cpu().numpy()
+    assert np.array_equal(info["best_idx"].cpu().numpy(), np.argmin(costs, axis=1))
+    lim = model.actuator_ctrlrange
+    for b in range(B):
+        us_all = np.clip(ug[b][None] + np.concatenate([np.zeros((1, N, 4)), noise[b] * 0.01]), lim[:, 0], lim[:, 1])
+        xs_all = o.rollout(np.tile(x0[b], (S, 1)), us_all)
+        ref = quad_cost(xs_all, us_all, np.eye(16), 10 * np.eye(16), 0.01 * np.eye(4), 0.0)
+        assert np.allclose(costs[b], ref, rtol=1e-3)
+        order = np.sort(ref)
+        if order[1] - order[0] > 2e-3 * abs(order[0]):
+            assert int(info["best_idx"][b]) == int(np.argmin(ref))
+        k = int(info["best_idx"][b])
+        assert np.allclose(us[b].cpu().numpy(), us_all[k], atol=1e-6)
+        assert np.abs(xs[b].cpu().numpy() - xs_all[k]).max() < 1e-3
+        assert np.isclose(float(info["best_cost"][b]), costs[b, k])
+
+
+def test_VPS_device_noise_matches_numpy_philox_and_sharding(vps_data):
+    ps, model, cf, o = vps_data
+    rng = np.random.default_rng(8)
+    B, S, N, seed = 2, 64, 6, 0x1234ABCD5678
+    x0, ug = t32(rng.normal(size=(B, 16)) * 0.2), t32(rng.normal(size=(B, N, 4)))
+    ps = VanillaPredictiveSampler(model=model, cost_function=cf, nsamples=S, stdev=0.5)
+    p = VanillaPredictiveSamplerParams(key=seed, x0=x0, us_guess=ug)
+    xs, us, info = ps.optimize(p, return_info=True)
+    idx = info["best_idx"].cpu().numpy()
+    lim = model.actuator_ctrlrange.astype(np.float32)
+    for b in range(B):
+        z = _philox.normals(seed, idx[b], b, np.arange(N * 4)).reshape(N, 4) if idx[b] > 0 else np.zeros((N, 4), np.float32)
+        expect = np.clip(ug[b].cpu().numpy() + z * np.float32(0.5), lim[:, 0], lim[:, 1])
+        assert np.allclose(us[b].cpu().numpy(), expect, atol=2e-6)
+    # sample 0 is the un-noised guess
+    ps1 = VanillaPredictiveSampler(model=model, cost_function=cf, nsamples=1, stdev=0.5)
+    _, us1 = ps1.optimize(p)
+    assert torch.equal(us1, torch.clamp(ug, -30, 30))
+    # sharding by global sample id: the union over shards reproduces the single call bit-exactly
+    parts = []
+    for lo, hi in ((0, 20), (20, 48), (48, 64)):
+        psk = VanillaPredictiveSampler(model=model, cost_function=cf, nsamples=hi - lo, stdev=0.5)
+        parts.append(psk.optimize(p, sample_offset=lo, nsamples_total=S, return_info=True)[2])
+    assert torch.equal(torch.cat([q["costs"] for q in parts], dim=1), info["costs"])
+    best = torch.stack([q["best_cost"] for q in parts])
+    gid = torch.stack([q["best_idx"] for q in parts])
+    pick = best.argmin(dim=0)
+    assert torch.equal(gid[pick, torch.arange(B, device=DEV)], info["best_idx"])
+    # host-pointer entry point gives the same answer
+    xs_h, us_h = ps.optimize(VanillaPredictiveSamplerParams(key=seed, x0=x0.cpu().numpy(), us_guess=ug.cpu().numpy()))
+    assert np.array_equal(xs_h, xs.cpu().numpy()) and np.array_equal(us_h, us.cpu().numpy())
+
+
+def test_argmin_nan_counts_as_minimum(vps_data):
+    ps, model, cf, _ = vps_data
+    x0 = torch.zeros((2, 16), device=DEV)
+    x0[1, 3] = float("nan")
+    _, _, info = ps.optimize(VanillaPredictiveSamplerParams(key=1, x0=x0, us_guess=torch.zeros((2, 5, 4), device=DEV)), return_info=True)
+    assert int(info["best_idx"][1]) == 0 and torch.isnan(info["best_cost"][1])  # all NaN -> first index
+    assert torch.isfinite(info["best_cost"][0])
+
+
+def test_generic_cost_function_path(vps_data):
+    ps, model, cf, _ = vps_data
+
+    class Mine(CostFunction):
+        def cost(self, xs, us, params):
+            return cf.cost(xs, us, params)
+
+    g = torch.Generator(device=DEV).manual_seed(3)
+    x0, ug = torch.randn(16, generator=g, device=DEV) * 0.2, torch.randn((8, 4), generator=g, device=DEV)
+    nz = torch.randn((99, 8, 4), generator=g, device=DEV)
+    a = ps.optimize(VanillaPredictiveSamplerParams(key=0, x0=x0, us_guess=ug, noise=nz))
+    b = VanillaPredictiveSampler(model=model, cost_function=Mine(), nsamples=100, stdev=0.01).optimize(
+        VanillaPredictiveSamplerParams(key=0, x0=x0, us_guess=ug, noise=nz))
+    assert torch.allclose(a[1], b[1]) and torch.allclose(a[0], b[0], atol=1e-5)
+
+
+# ------------------------------------------------------------------ env step
+def test_pipeline_step_and_env(load_model):
+    env = PendulumSwingupEnv(num_envs=16)
+    state = env.reset(0)
+    assert state.obs.shape == (16, 3) and env.action_size == 1 and env.observation_size == 3
+    o = Oracle(env.model)
+    q, v = state.pipeline_state.qpos.cpu().numpy(), state.pipeline_state.qvel.cpu().numpy()
+    act = torch.linspace(-3, 3, 16, device=DEV)[:, None]  # beyond the +-2 ctrl limit: clamped in fwd_actuation
+    s1 = env.step(state, act)
+    for e in range(16):
+        qr, vr, _, _ = o.step(q[e], v[e], [float(act[e])])
+        assert np.allclose(s1.pipeline_state.qpos[e].cpu().numpy(), qr, atol=1e-5)
+        assert np.allclose(s1.pipeline_state.qvel[e].cpu().numpy(), vr, atol=1e-4)
+    th, thd = s1.pipeline_state.qpos[:, 0], s1.pipeline_state.qvel[:, 0]
+    assert torch.allclose(s1.obs, torch.stack((torch.cos(th), torch.sin(th), thd), -1))
+    assert torch.all(s1.reward <= 0) and torch.all(s1.done == 0) and s1.info["step"] == 1
+
+
+def test_substeps_and_auto_reset(load_model):
+    mj, m, o = model_with(load_model, "barkour")
+    rng = np.random.default_rng(9)
+    E = 8
+    st = [sample_state(mj, "barkour", rng) for _ in range(E)]
+    q0, v0, c = (np.stack([s[i] for s in st]) for i in range(3))
+    env = VectorEnvStepper(m, t32(q0), t32(v0), nsubsteps=3)
+    first_q = env.first_qpos.clone()
+    env.step(t32(c))
+    for e in range(0, E, 3):
+        w0 = o.forward(q0[e], v0[e])["qacc_warmstart"]
+        qr, vr, _, tr = o.step(q0[e], v0[e], c[e], w0, nsteps=3)
+        assert np.all(np.abs(env.qpos[e].cpu().numpy() - qr) <= 2e-5 + 2e-4 * np.abs(qr))
+        assert np.isclose(float(env.time[e]), tr, atol=1e-6)
+    after_one = env.qpos.clone()
+    done = torch.zeros(E, dtype=torch.bool, device=DEV)
+    done[2] = done[5] = True
+    env.step(t32(c), done)
+    # reset envs restart from the cached first state: they land where the first step landed
+    assert torch.allclose(env.qpos[done], after_one[done], atol=1e-6)
+    assert torch.allclose(env.time[done], torch.full((2,), 0.012, device=DEV))
+    assert not torch.allclose(env.qpos[~done], after_one[~done], atol=1e-6)
+    assert torch.equal(env.first_qpos, first_q)
+
+
+def test_unsupported_option_raises(load_model):
+    mj = load_model("pendulum")
+    m = mjx.device_put(mj)
+    with pytest.raises(NotImplementedError):
+        m.replace(opt=m.opt.replace(cone=1)).handle(0)
+    with pytest.raises(NotImplementedError):
+        m.replace(opt=m.opt.replace(integrator=3)).handle(0)
+
+
+# ------------------------------------------------------------------ full-size properties
+def test_full_size_properties_barkour(load_model):
+    """BASELINE config C2 shape (4096 worlds x 1000 steps): determinism, batch independence,
+    finiteness, and physical sanity. The oracle cannot cover this size in seconds; these properties do."""
+    mj, m, o = model_with(load_model, "barkour")
+    W, N = 4096, 1000
+    g = torch.Generator(device=DEV).manual_seed(2)
+    c0, q0 = t32(mj.key_ctrl("home")), mj.key_qpos("home")
+    lim = t32(mj.actuator_ctrlrange)
+    us = torch.clamp(c0 + 0.1 * torch.randn((W, N, mj.nu), generator=g, device=DEV), lim[:, 0], lim[:, 1])
+    x0 = t32(np.concatenate([q0, np.zeros(mj.nv)])).repeat(W, 1)
+    x0[:, 7:19] += (torch.rand((W, 12), generator=g, device=DEV) - 0.5) * 0.1
+    eye = np.eye(37)
+    cf = StaticGoalQuadraticCost(eye, 10 * eye, 0.01 * np.eye(12), np.concatenate([q0, np.zeros(mj.nv)]))
+    c1 = shoot_cost(m, x0, us, cf)
+    c2 = shoot_cost(m, x0, us, cf)
+    assert torch.equal(c1, c2)  # bit-deterministic
+    assert torch.isfinite(c1).all()
+    sub = torch.tensor([0, 1, 777, 4095], device=DEV)
+    xs_sub = shoot(m, x0[sub], us[sub])
+    assert torch.isfinite(xs_sub).all()
+    c_sub, _ = cf.cost(xs_sub, us[sub], None)
+    assert torch.allclose(c_sub, c1[sub], rtol=1e-4)  # a world's result does not depend on its batch
+    quat = xs_sub[:, :, 3:7]
+    assert torch.allclose(quat.norm(dim=-1), torch.ones_like(quat[..., 0]), atol=1e-5)  # integrator keeps unit quaternions
+    # first 20 steps of one world against the oracle
+    ref = o.rollout(x0[777].cpu().numpy().astype(np.float64), us[777, :20].cpu().numpy().astype(np.float64))
+    assert np.abs(xs_sub[2, :21].cpu().numpy() - ref).max() < 2e-3
+
+
+def test_ffma_peak_is_plausible():
+    import ctypes as C
+
+    tf, ms = C.c_double(), C.c_double()
+    _lib.check(_lib.lib().abr_ffma_peak(0, C.byref(tf), C.byref(ms)))
+    assert 20.0 < tf.value < 90.0  # nominal 74.4 TFLOP/s at 1965 MHz

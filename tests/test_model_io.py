@@ -1,0 +1,106 @@
+"""Loader contract, mirroring the reference's tests/test_model_io.py (path resolution :23-45, every
+bundled model loads with and without force_float :49-54, bh280 sizes :76,98,143,146)."""
+import os
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from ambersim_b200 import ROOT, mjx
+from ambersim_b200.utils._internal_utils import _check_filepath
+from ambersim_b200.utils.io_utils import load_mj_model_from_file, mj_to_mjx_model_and_data
+
+
+def test_path_resolution(tmp_path, monkeypatch):
+    rel = "models/pendulum/pendulum.xml"
+    absolute = Path(ROOT) / rel
+    for p in (absolute, str(absolute), rel, Path(rel)):
+        assert Path(_check_filepath(p)).samefile(absolute)
+    # cwd-relative takes precedence over the package root
+    local = tmp_path / "local.xml"
+    local.write_text(absolute.read_text())
+    monkeypatch.chdir(tmp_path)
+    assert Path(_check_filepath("local.xml")).samefile(local)
+    with pytest.raises(FileNotFoundError):
+        _check_filepath("does/not/exist.xml")
+
+
+def test_all_models_load():
+    files = sorted(Path(ROOT, "models").rglob("*.xml"))
+    assert len(files) >= 5
+    for f in files:
+        for ff in (False, True):
+            if ff and f.name in ("barkour_vb_standin.xml", "biped_exo_standin.xml"):
+                continue  # already floating
+            m = load_mj_model_from_file(f, force_float=ff)
+            assert m.nq >= m.nv > 0
+
+
+def test_bh280_dimensions_and_force_float():
+    m = load_mj_model_from_file("models/barrett_hand/bh280.xml")
+    assert (m.nq, m.nv, m.nu, m.neq) == (8, 8, 4, 4)
+    assert m.names["actuator"] == [f"bh_j{j}_joint_actuator" for j in (32, 11, 12, 22)]
+    assert all(n.endswith("_equality") for n in m.names["equality"])
+    assert int(m.jnt_limited.sum()) == 8
+    mf = load_mj_model_from_file("models/barrett_hand/bh280.xml", force_float=True)
+    assert (mf.nq, mf.nv) == (15, 14)
+    assert mf.jnt_type[0] == 0 and mf.body_jntnum[1] == 1
+
+
+def test_solver_and_iteration_overrides():
+    m = load_mj_model_from_file("models/pendulum/scene.xml")
+    assert (m.opt.solver, m.opt.iterations, m.opt.ls_iterations, m.opt.timestep) == (2, 5, 10, 0.02)
+    m = load_mj_model_from_file("models/pendulum/scene.xml", solver="cg", iterations=3, ls_iterations=7)
+    assert (m.opt.solver, m.opt.iterations, m.opt.ls_iterations) == (1, 3, 7)
+    with pytest.raises(ValueError):
+        load_mj_model_from_file("models/pendulum/scene.xml", solver="pgs")
+
+
+def test_standin_dimensions_are_frozen():
+    b = load_mj_model_from_file("models/barkour_standin/barkour_vb_standin.xml")
+    assert (b.nq, b.nv, b.nu, b.nbody, b.npair) == (19, 18, 12, 14, 4)
+    assert b.opt.disableflags == 16384 and b.opt.iterations == 1 and b.opt.ls_iterations == 5
+    p = load_mj_model_from_file("models/biped_standin/biped_exo_standin.xml")
+    assert (p.nq, p.nv, p.nu, p.nbody, p.npair) == (28, 27, 21, 23, 8)
+
+
+def test_compile_constants():
+    m = load_mj_model_from_file("models/pendulum/scene.xml")
+    assert np.isclose(m.stat.meaninertia, 0.087959 + 0.25)
+    assert np.isclose(m.dof_invweight0[0], 1 / (0.087959 + 0.25))
+    assert np.allclose(m.body_subtreemass, [3, 3, 1])
+    b = load_mj_model_from_file("models/barkour_standin/barkour_vb_standin.xml")
+    # free joint: translational and rotational invweights averaged separately
+    assert np.allclose(b.dof_invweight0[:3], b.dof_invweight0[0]) and np.allclose(b.dof_invweight0[3:6], b.dof_invweight0[3])
+    assert np.isclose(b.dof_invweight0[0], np.linalg.inv(b.qM0)[:3, :3].diagonal().mean())
+    assert b.body_invweight0[0].sum() == 0 and np.all(b.body_invweight0[1:] > 0)
+
+
+def test_model_mirror_and_unsupported(tmp_path):
+    mj = load_mj_model_from_file("models/barrett_hand/bh280.xml")
+    model = mjx.device_put(mj)
+    m2 = model.replace(opt=model.opt.replace(timestep=0.002, iterations=1, ls_iterations=4, disableflags=mjx.DisableBit.CONTACT))
+    assert m2.opt.iterations == 1 and model.opt.iterations == 100 and m2.opt.disableflags == 16 and m2.nq == 8
+    assert np.allclose(model.actuator_ctrlrange, [[-30, 30]] * 4)
+    # a box geom colliding with a plane is outside the engine: reported like MJX's NotImplementedError
+    xml = tmp_path / "box.xml"
+    xml.write_text("""<mujoco><worldbody><geom type="plane" size="1 1 .1"/>
+      <body pos="0 0 1"><freejoint/><inertial pos="0 0 0" mass="1" diaginertia=".1 .1 .1"/>
+      <geom type="box" size=".1 .1 .1"/></body></worldbody></mujoco>""")
+    bad = mjx.device_put(load_mj_model_from_file(xml))
+    assert bad.n_unsupported_pairs == 1
+    with pytest.raises(NotImplementedError):
+        bad.handle(0)
+    urdf = tmp_path / "x.urdf"
+    urdf.write_text("<robot name='x'/>")
+    with pytest.raises(NotImplementedError):
+        load_mj_model_from_file(urdf)
+
+
+def test_default_classes_and_keyframes():
+    b = load_mj_model_from_file("models/barkour_standin/barkour_vb_standin.xml")
+    assert np.allclose(b.dof_damping[6:], 1.0) and np.allclose(b.dof_armature[6:], 0.0111)
+    assert np.allclose(b.actuator_gainprm[:, 0], 60) and np.allclose(b.actuator_biasprm[:, 1], -60)
+    assert np.allclose(b.jnt_axis[3], [0, -1, 0])  # knee class
+    assert np.allclose(b.key_ctrl("home"), [0, 0.5, 1.0] * 4)
+    assert b.pair_kind.tolist() == [0, 0, 0, 0] and np.allclose(b.pair_friction[0], [1.0, 1.0, 0.02, 0.01, 0.01])  # elementwise max with the plane

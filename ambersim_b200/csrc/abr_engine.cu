@@ -339,13 +339,105 @@ static int build_blob(const HostModel& m, bool alias, Layout& L, std::vector<flo
   L.i_act_jnt = P.addi(act_jnt); L.i_act_flags = P.addi(act_flags);
   L.i_dof_actadr = P.addi(dof_actadr); L.i_dof_actnum = P.addi(dof_actnum); L.i_dof_act = P.addi(dof_act);
 
+  // ---- tree-sparse linear-algebra tables (see abr_layout.h)
+  {
+    const std::vector<int>& par = m.dof_parentid;
+    std::vector<int> sp_adr(nv + 1, 0);
+    for (int i = 0, e = 0; i <= nv; i++) {
+      sp_adr[i] = e;
+      if (i < nv) for (int j = i; j >= 0; j = par[j]) e++;
+    }
+    auto is_anc = [&](int a, int d) { for (int j = d; j >= 0; j = par[j]) if (j == a) return true; return false; };
+    auto ent = [&](int i, int j) { int e = sp_adr[i]; for (int q = i; q >= 0; q = par[q], e++) if (q == j) return e; return -1; };
+    bool ok = getenv("ABR_DENSE") == nullptr;
+    for (size_t e = 0; e < eq_j1.size() && ok; e++) {
+      if (eq_j2[e] < 0) continue;
+      int d1 = m.jnt_dofadr[eq_j1[e]], d2 = m.jnt_dofadr[eq_j2[e]];
+      if (!is_anc(d1, d2) && !is_anc(d2, d1)) ok = false;
+    }
+    std::vector<int> cd_adr(L.ncon + 1, 0), cd_dof;
+    for (int ci = 0; ci < L.ncon; ci++) {
+      cd_adr[ci] = (int)cd_dof.size();
+      for (int d = 0; d < nv; d++) if (con_dofmask[ci * nv + d]) cd_dof.push_back((ci << 16) | d);
+      for (int a = cd_adr[ci]; a < (int)cd_dof.size() && ok; a++)
+        for (int b = a + 1; b < (int)cd_dof.size(); b++)
+          if (!is_anc(cd_dof[a] & 0xffff, cd_dof[b] & 0xffff) && !is_anc(cd_dof[b] & 0xffff, cd_dof[a] & 0xffff)) ok = false;
+    }
+    cd_adr[L.ncon] = (int)cd_dof.size();
+    L.sparse = ok ? 1 : 0;
+    L.nnz = sp_adr[nv];
+    std::vector<int> height(nv, 0);
+    for (int k = nv - 1; k >= 0; k--) if (par[k] >= 0) height[par[k]] = std::max(height[par[k]], height[k] + 1);
+    int nstage = 0;
+    for (int k = 0; k < nv; k++) nstage = std::max(nstage, height[k] + 1);
+    L.nstage = nstage;
+    std::vector<int> st_adr(nstage + 1, 0), st_dof;
+    std::vector<int> fu_tadr(nstage + 1, 0), fu_tgt, fu_cadr(1, 0), fu_src, fu_k;
+    std::vector<int> sb_tadr(nstage + 1, 0), sb_tgt, sb_cadr(1, 0), sb_src;
+    for (int st = 0; st < nstage; st++) {
+      st_adr[st] = (int)st_dof.size();
+      std::vector<std::vector<std::pair<int, int>>> upd(L.nnz);   // target entry -> (src pair, pivot)
+      std::vector<std::vector<int>> bs(nv);                       // target dof -> (entry << 16 | k)
+      for (int k = 0; k < nv; k++) {
+        if (height[k] != st) continue;
+        st_dof.push_back(k);
+        for (int i = par[k]; i >= 0; i = par[i]) {
+          bs[i].push_back((ent(k, i) << 16) | k);
+          for (int j = i; j >= 0; j = par[j]) upd[ent(i, j)].push_back({(ent(k, i) << 16) | ent(k, j), k});
+        }
+      }
+      fu_tadr[st] = (int)fu_tgt.size();
+      for (int e = 0; e < L.nnz; e++) {
+        if (upd[e].empty()) continue;
+        fu_tgt.push_back(e);
+        for (auto& u : upd[e]) { fu_src.push_back(u.first); fu_k.push_back(u.second); }
+        fu_cadr.push_back((int)fu_src.size());
+      }
+      sb_tadr[st] = (int)sb_tgt.size();
+      for (int i = 0; i < nv; i++) {
+        if (bs[i].empty()) continue;
+        sb_tgt.push_back(i);
+        for (int v : bs[i]) sb_src.push_back(v);
+        sb_cadr.push_back((int)sb_src.size());
+      }
+    }
+    st_adr[nstage] = (int)st_dof.size(); fu_tadr[nstage] = (int)fu_tgt.size(); sb_tadr[nstage] = (int)sb_tgt.size();
+    std::vector<int> mm_adr(nv + 1, 0), mm_src;
+    for (int i = 0; i < nv; i++) {
+      mm_adr[i] = (int)mm_src.size();
+      for (int j = i; j >= 0; j = par[j]) mm_src.push_back((ent(i, j) << 16) | j);
+      for (int k = i + 1; k < nv; k++) if (is_anc(i, k)) mm_src.push_back((ent(k, i) << 16) | k);
+    }
+    mm_adr[nv] = (int)mm_src.size();
+    std::vector<int> hc_adr(L.nnz + 1, 0), hc_con, he_adr(L.nnz + 1, 0), he_eq;
+    for (int i = 0, e = 0; i < nv; i++)
+      for (int j = i; j >= 0; j = par[j], e++) {
+        hc_adr[e] = (int)hc_con.size();
+        he_adr[e] = (int)he_eq.size();
+        for (int ci = 0; ci < L.ncon; ci++) if (con_dofmask[ci * nv + i] && con_dofmask[ci * nv + j]) hc_con.push_back(ci);
+        for (size_t q = 0; q < eq_j1.size(); q++) {
+          int d1 = m.jnt_dofadr[eq_j1[q]], d2 = eq_j2[q] >= 0 ? m.jnt_dofadr[eq_j2[q]] : -1;
+          if (i == d1 && j == d1) he_eq.push_back(((int)q << 2) | 0);
+          else if (i == d2 && j == d2) he_eq.push_back(((int)q << 2) | 1);
+          else if ((i == d1 && j == d2) || (i == d2 && j == d1)) he_eq.push_back(((int)q << 2) | 2);
+        }
+      }
+    hc_adr[L.nnz] = (int)hc_con.size(); he_adr[L.nnz] = (int)he_eq.size();
+    L.i_sp_adr = P.addi(sp_adr); L.i_st_adr = P.addi(st_adr); L.i_st_dof = P.addi(st_dof);
+    L.i_fu_tadr = P.addi(fu_tadr); L.i_fu_tgt = P.addi(fu_tgt); L.i_fu_cadr = P.addi(fu_cadr); L.i_fu_src = P.addi(fu_src); L.i_fu_k = P.addi(fu_k);
+    L.i_sb_tadr = P.addi(sb_tadr); L.i_sb_tgt = P.addi(sb_tgt); L.i_sb_cadr = P.addi(sb_cadr); L.i_sb_src = P.addi(sb_src);
+    L.i_mm_adr = P.addi(mm_adr); L.i_mm_src = P.addi(mm_src);
+    L.i_hc_adr = P.addi(hc_adr); L.i_hc_con = P.addi(hc_con); L.i_he_adr = P.addi(he_adr); L.i_he_eq = P.addi(he_eq);
+    L.i_cd_adr = P.addi(cd_adr); L.i_cd_dof = P.addi(cd_dof);
+  }
+
   while (P.f.size() % 4) P.f.push_back(0.f);
   while (P.i.size() % 4) P.i.push_back(0);
   L.n_mf = (int)P.f.size(); L.n_mi = (int)P.i.size();
   mf = P.f; mi = P.i;
 
   // ---- per-world shared-memory layout
-  const int ne = L.nefc, nc = L.ncon, ntri = L.ntri;
+  const int ne = L.nefc, nc = L.ncon, ntri = L.sparse ? L.nnz : L.ntri;
   int off = 0;
   auto take = [&](int n) { int o = off; off += n; return o; };
   // persistent across the step
@@ -354,7 +446,7 @@ static int build_blob(const HostModel& m, bool alias, Layout& L, std::vector<flo
   L.w_M = take(ntri); L.w_H = take(ntri);
   L.w_eqc = take(L.ne); L.w_lims = take(L.nl); L.w_B = take(3 * nc * nv);
   L.w_D = take(ne); L.w_aref = take(ne);
-  L.w_fs = take(nv); L.w_as = take(nv); L.w_a = take(nv); L.w_fc = take(nv); L.w_y = take(nv);
+  L.w_fs = take(nv); L.w_as = take(nv); L.w_a = take(nv); L.w_fc = take(nv); L.w_y = take(nv); L.w_invD = take(nv);
   L.w_cinert = take(10 * nb); L.w_cdof = take(6 * nv);
   L.w_actf = take(nu); L.w_bv = take(3 * nc);
   int rk = 2 * nv;  // CG Polak-Ribiere history
@@ -788,7 +880,18 @@ int abr_debug_forward_host(AbrModel* m, const float* qpos, const float* qvel, co
   else if (s == "cinert") span(L.w_cinert, 10 * nb);
   else if (s == "cdof") span(L.w_cdof, 6 * nv);
   else if (s == "crb") span(L.w_crb, 10 * nb);
-  else if (s == "qM") unpack(L.w_M);
+  else if (s == "qM") {
+    if (L.sparse) {
+      res.assign((size_t)nv * nv, 0.f);
+      for (int k = 0; k < L.nnz; k++) {
+        const int ij = m->mi[L.i_mpair + k];
+        res[(ij >> 16) * nv + (ij & 0xffff)] = W[L.w_M + k];
+        res[(ij & 0xffff) * nv + (ij >> 16)] = W[L.w_M + k];
+      }
+    } else {
+      unpack(L.w_M);
+    }
+  }
   else if (s == "cvel") span(L.w_cvel, 6 * nb);
   else if (s == "cdof_dot") span(L.w_cdofdot, 6 * nv);
   else if (s == "contact_dist") span(L.w_cdist, L.ncon);

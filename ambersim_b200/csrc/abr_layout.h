@@ -52,11 +52,24 @@ struct Layout {
   int i_row_info;   // per efc row: kind (0 eq, 1 limit, 2 contact) | idx << 2 | sub << 20
   int i_pair_g1, i_pair_g2, i_pair_kind, i_geom_body;
   int i_act_jnt, i_act_flags;
+  // ---- tree-sparse linear algebra (valid when every constraint couples dofs of one ancestor
+  //      chain only, so H = M + J'DJ keeps M's branch-induced sparsity and L'DL has no fill-in)
+  int sparse;       // 1 = tree-sparse path, 0 = dense packed-Cholesky fallback
+  int nnz;          // entries (i,j), j ancestor-or-self of i, in row-chain order (== nmpair)
+  int nstage;       // elimination stages: dofs of equal height in the dof tree
+  int i_sp_adr;     // [nv+1] row start in the sparse array (diagonal first, then ancestors)
+  int i_st_adr, i_st_dof;                         // stage -> dofs eliminated
+  int i_fu_tadr, i_fu_tgt, i_fu_cadr, i_fu_src, i_fu_k;   // factor updates, gathered by target entry
+  int i_sb_tadr, i_sb_tgt, i_sb_cadr, i_sb_src;   // back-substitution, gathered by target dof
+  int i_mm_adr, i_mm_src;                         // M v: per row (entry << 16 | other dof)
+  int i_hc_adr, i_hc_con;                         // Hessian: contacts touching both dofs of an entry
+  int i_he_adr, i_he_eq;                          // Hessian: equality rows touching an entry (eq << 2 | which)
+  int i_cd_adr, i_cd_dof;                         // contact -> dofs with a non-zero Jacobian column
   // ---- per-world shared-memory offsets (floats)
   int w_qpos, w_qvel, w_warm, w_ctrl, w_M, w_eqc, w_lims, w_B, w_D, w_aref, w_fs, w_as, w_H;
   int w_xpos, w_xquat, w_xipos, w_xanchor, w_xaxis, w_rootcom, w_cinert, w_cdof;
   int w_crb, w_buf, w_cvel, w_cacc, w_cdofdot, w_cdist, w_cpos, w_cframe, w_actf, w_bv;
-  int w_a, w_Ma, w_grad, w_search, w_mv, w_fc, w_Jaref, w_jv, w_force, w_Fc, w_WB, w_y;
+  int w_a, w_Ma, w_grad, w_search, w_mv, w_fc, w_Jaref, w_jv, w_force, w_Fc, w_WB, w_y, w_invD;
   int w_rk;         // RK4 save area: qpos0[nq] qvel0[nv] warm0[nv] sv[nv] sa[nv] kq[nv]
   int world_stride; // floats per world
 };

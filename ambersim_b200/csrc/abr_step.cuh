@@ -350,26 +350,26 @@ template <int G> __device__ void stage_collision(const Ctx& c) {
     for (int i = 0; i < 9; i++) cframe[9 * ci + i] = fr[i];
   }
   __syncwarp();
-  // Jacobian basis: item = (contact, dof)
+  // Jacobian basis: item = (contact, dof on the contact's chain); other columns stay 0 from init
   float* B = WF(B);
   const float* cdof = WF(cdof); const float* rootcom = WF(rootcom);
   const int nv = L.nv;
-  for (int it = c.lane; it < L.ncon * nv; it += G) {
-    const int ci = it / nv, d = it - ci * nv;
-    const int mask = MI(con_dofmask)[it];
-    float o0 = 0.f, o1 = 0.f, o2 = 0.f;
-    if (mask) {
-      const int b = MI(dof_body)[d];
-      const float* rc = rootcom + 3 * MI(body_rootslot)[b];
-      float off[3] = {cpos[3 * ci] - rc[0], cpos[3 * ci + 1] - rc[1], cpos[3 * ci + 2] - rc[2]};
-      float cr[3];
-      v_cross(cdof + 6 * d, off, cr);
-      float jp[3] = {cdof[6 * d + 3] + cr[0], cdof[6 * d + 4] + cr[1], cdof[6 * d + 5] + cr[2]};
-      const float sg = (mask == 1) ? 1.f : -1.f;
-      const float* fr = cframe + 9 * ci;
-      o0 = sg * v_dot(fr, jp); o1 = sg * v_dot(fr + 3, jp); o2 = sg * v_dot(fr + 6, jp);
-    }
-    B[(3 * ci) * nv + d] = o0; B[(3 * ci + 1) * nv + d] = o1; B[(3 * ci + 2) * nv + d] = o2;
+  const int ncd = MI(cd_adr)[L.ncon];
+#pragma unroll 1
+  for (int it = c.lane; it < ncd; it += G) {
+    const int cd = MI(cd_dof)[it];
+    const int ci = cd >> 16, d = cd & 0xffff;
+    const int b = MI(dof_body)[d];
+    const float* rc = rootcom + 3 * MI(body_rootslot)[b];
+    float off[3] = {cpos[3 * ci] - rc[0], cpos[3 * ci + 1] - rc[1], cpos[3 * ci + 2] - rc[2]};
+    float cr[3];
+    v_cross(cdof + 6 * d, off, cr);
+    float jp[3] = {cdof[6 * d + 3] + cr[0], cdof[6 * d + 4] + cr[1], cdof[6 * d + 5] + cr[2]};
+    const float sg = (MI(con_dofmask)[ci * nv + d] == 1) ? 1.f : -1.f;
+    const float* fr = cframe + 9 * ci;
+    B[(3 * ci) * nv + d] = sg * v_dot(fr, jp);
+    B[(3 * ci + 1) * nv + d] = sg * v_dot(fr + 3, jp);
+    B[(3 * ci + 2) * nv + d] = sg * v_dot(fr + 6, jp);
   }
   __syncwarp();
 }
@@ -408,7 +408,7 @@ template <int G> __device__ void stage_crb(const Ctx& c) {
     const float* a = cdof + 6 * j; const float* b = buf + 6 * i;
     float s = a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5];
     if (i == j) s += MF(dof_armature)[i];
-    M[tri(i) + j] = s;
+    M[L.sparse ? k : tri(i) + j] = s;
   }
   __syncwarp();
 }
@@ -422,7 +422,7 @@ template <int G> __device__ __noinline__ void chol_factor(float* A, int n, int l
     const float* rk = A + tri(k);
     float sk = rk[k];
     for (int p = 0; p < k; p++) sk -= rk[p] * rk[p];
-    const float d = sqrtf(sk);
+    const float d = sqrtf(fmaxf(sk, kMinVal));  // pivot clamp as in MuJoCo's mj_cholFactor
     const float inv = 1.f / d;
     float vals[(64 + G - 1) / G];
     int cnt = 0;
@@ -473,20 +473,122 @@ template <int G> __device__ __noinline__ void mul_m(const float* M, const float*
   }
 }
 
+// ------------------------------------------------------------------------------ tree-sparse L'DL
+// When every constraint couples dofs of one ancestor chain only, H = M + J'DJ has M's
+// branch-induced sparsity and eliminating dofs leaves-first (MuJoCo's L'DL order) creates no
+// fill-in. Entries (i,j), j ancestor-or-self of i, are stored in row-chain order (diagonal first);
+// dofs of equal height in the dof tree form one elimination stage, and every update is a gather
+// over a host-built task list, so a stage needs two __syncwarp() and no atomics.
+// After sp_factor: A holds D on the diagonal and D*L off it (L[k,i] = A[k,i] * invD[k]).
+template <int G> __device__ __forceinline__ void sp_factor(const Ctx& c, float* A) {
+  const Layout& L = c.L;
+  float* invD = WF(invD);
+  const int* sp_adr = MI(sp_adr);
+  for (int s = 0; s < L.nstage; s++) {
+    const int d0 = MI(st_adr)[s], d1 = MI(st_adr)[s + 1];
+#pragma unroll 1
+    for (int q = d0 + c.lane; q < d1; q += G) { const int k = MI(st_dof)[q]; invD[k] = 1.f / fmaxf(A[sp_adr[k]], kMinVal); }
+    __syncwarp();
+    const int t0 = MI(fu_tadr)[s], t1 = MI(fu_tadr)[s + 1];
+#pragma unroll 1
+    for (int t = t0 + c.lane; t < t1; t += G) {
+      float acc = 0.f;
+      const int q1 = MI(fu_cadr)[t + 1];
+#pragma unroll 1
+      for (int q = MI(fu_cadr)[t]; q < q1; q++) {
+        const int src = MI(fu_src)[q];
+        acc += A[src >> 16] * A[src & 0xffff] * invD[MI(fu_k)[q]];
+      }
+      A[MI(fu_tgt)[t]] -= acc;
+    }
+    __syncwarp();
+  }
+}
+
+// x = (L' D L)^-1 b with the factor above; x may alias b; WF(y) is the scratch.
+template <int G> __device__ __forceinline__ void sp_solve(const Ctx& c, const float* A, const float* b, float* x) {
+  const Layout& L = c.L;
+  float* z = WF(y); const float* invD = WF(invD);
+  const int* sp_adr = MI(sp_adr);
+#pragma unroll 1
+  for (int i = c.lane; i < L.nv; i += G) z[i] = b[i];
+  __syncwarp();
+  for (int s = 0; s < L.nstage; s++) {  // leaves -> root:  z = D^-1 L^-T b
+    const int d0 = MI(st_adr)[s], d1 = MI(st_adr)[s + 1];
+#pragma unroll 1
+    for (int q = d0 + c.lane; q < d1; q += G) { const int k = MI(st_dof)[q]; z[k] *= invD[k]; }
+    __syncwarp();
+    const int t0 = MI(sb_tadr)[s], t1 = MI(sb_tadr)[s + 1];
+#pragma unroll 1
+    for (int t = t0 + c.lane; t < t1; t += G) {
+      float acc = 0.f;
+      const int q1 = MI(sb_cadr)[t + 1];
+#pragma unroll 1
+      for (int q = MI(sb_cadr)[t]; q < q1; q++) { const int src = MI(sb_src)[q]; acc += A[src >> 16] * z[src & 0xffff]; }
+      z[MI(sb_tgt)[t]] -= acc;
+    }
+    __syncwarp();
+  }
+  for (int s = L.nstage - 1; s >= 0; s--) {  // root -> leaves:  x = L^-1 z
+    const int d0 = MI(st_adr)[s], d1 = MI(st_adr)[s + 1];
+#pragma unroll 1
+    for (int q = d0 + c.lane; q < d1; q += G) {
+      const int k = MI(st_dof)[q];
+      float acc = 0.f;
+      const int e1 = sp_adr[k + 1];
+#pragma unroll 1
+      for (int e = sp_adr[k] + 1; e < e1; e++) acc += A[e] * z[MI(mpair)[e] & 0xffff];
+      z[k] -= invD[k] * acc;
+    }
+    __syncwarp();
+  }
+#pragma unroll 1
+  for (int i = c.lane; i < L.nv; i += G) x[i] = z[i];
+  __syncwarp();
+}
+
+// out = M v for the sparse storage. No trailing sync: caller syncs.
+template <int G> __device__ __forceinline__ void sp_mul_m(const Ctx& c, const float* M, const float* v, float* out) {
+#pragma unroll 1
+  for (int i = c.lane; i < c.L.nv; i += G) {
+    float acc = 0.f;
+    const int q1 = MI(mm_adr)[i + 1];
+#pragma unroll 1
+    for (int q = MI(mm_adr)[i]; q < q1; q++) { const int src = MI(mm_src)[q]; acc += M[src >> 16] * v[src & 0xffff]; }
+    out[i] = acc;
+  }
+}
+
+// dispatchers: tree-sparse path or dense packed-Cholesky fallback
+template <int G> __device__ __forceinline__ void la_factor(const Ctx& c, float* A) {
+  if (c.L.sparse) sp_factor<G>(c, A); else chol_factor<G>(A, c.L.nv, c.lane);
+}
+template <int G> __device__ __forceinline__ void la_solve(const Ctx& c, const float* A, const float* b, float* x) {
+  if (c.L.sparse) sp_solve<G>(c, A, b, x); else chol_solve<G>(A, b, x, WF(y), c.L.nv, c.lane);
+}
+template <int G> __device__ __forceinline__ void la_mul_m(const Ctx& c, const float* v, float* out) {
+  if (c.L.sparse) sp_mul_m<G>(c, WF(M), v, out); else mul_m<G>(WF(M), v, out, c.L.nv, c.lane);
+}
+
 // out[r] = (J v)[r] for the structured Jacobian (equality coefficients, limit signs, contact
 // basis B). bv is a 3*ncon scratch. Ends synced.
 template <int G> __device__ void mul_j(const Ctx& c, const float* v, float* out) {
   const Layout& L = c.L;
   const int nv = L.nv;
   float* bv = WF(bv); const float* B = WF(B);
+#pragma unroll 1
   for (int it = c.lane; it < 3 * L.ncon; it += G) {
     const float* row = B + it * nv;
+    const int ci = it / 3;
     float s = 0.f;
-    for (int d = 0; d < nv; d++) s += row[d] * v[d];
+    const int q1 = MI(cd_adr)[ci + 1];
+#pragma unroll 1
+    for (int q = MI(cd_adr)[ci]; q < q1; q++) { const int d = MI(cd_dof)[q] & 0xffff; s += row[d] * v[d]; }
     bv[it] = s;
   }
   __syncwarp();
   const float* eqc = WF(eqc); const float* lims = WF(lims);
+#pragma unroll 1
   for (int r = c.lane; r < L.nefc; r += G) {
     const int info = MI(row_info)[r];
     const int kind = info & 3, idx = (info >> 2) & 0x3ffff, sub = info >> 20;
@@ -552,10 +654,14 @@ template <int G> __device__ void stage_rows(const Ctx& c) {
   float* eqc = WF(eqc); float* lims = WF(lims); float* D = WF(D); float* aref = WF(aref);
   float* bv = WF(bv); const float* B = WF(B);
   const int nv = L.nv;
+#pragma unroll 1
   for (int it = c.lane; it < 3 * L.ncon; it += G) {
     const float* row = B + it * nv;
+    const int ci = it / 3;
     float s = 0.f;
-    for (int d = 0; d < nv; d++) s += row[d] * qvel[d];
+    const int q1 = MI(cd_adr)[ci + 1];
+#pragma unroll 1
+    for (int q = MI(cd_adr)[ci]; q < q1; q++) { const int d = MI(cd_dof)[q] & 0xffff; s += row[d] * qvel[d]; }
     bv[it] = s;
   }
   __syncwarp();
@@ -787,9 +893,13 @@ template <int G> __device__ void solver_hessian(const Ctx& c, const float* Jaref
   const Layout& L = c.L;
   const int nv = L.nv;
   const float* D = WF(D); const float* B = WF(B); float* WB = WF(WB);
-  // per contact: 3x3 weight in the (n,t1,t2) basis, then WB = W B
-  for (int it = c.lane; it < L.ncon * nv; it += G) {
-    const int ci = it / nv, j = it - ci * nv;
+  // per contact: 3x3 weight in the (n,t1,t2) basis, then WB = W B on the contact's dof chain
+  const int ncd = L.sparse ? MI(cd_adr)[L.ncon] : L.ncon * nv;
+#pragma unroll 1
+  for (int it = c.lane; it < ncd; it += G) {
+    int ci, j;
+    if (L.sparse) { const int cd = MI(cd_dof)[it]; ci = cd >> 16; j = cd & 0xffff; }
+    else { ci = it / nv; j = it - ci * nv; }  // dense fallback reads every column of WB
     const int r0 = MI(con_row)[ci];
     const float b0 = B[(3 * ci) * nv + j], b1 = B[(3 * ci + 1) * nv + j], b2 = B[(3 * ci + 2) * nv + j];
     float o0, o1, o2;
@@ -812,6 +922,36 @@ template <int G> __device__ void solver_hessian(const Ctx& c, const float* Jaref
   __syncwarp();
   const float* M = WF(M); float* H = WF(H);
   const float* eqc = WF(eqc);
+  if (L.sparse) {
+#pragma unroll 1
+    for (int e = c.lane; e < L.nnz; e += G) {
+      const int ij = MI(mpair)[e];
+      const int i = ij >> 16, j = ij & 0xffff;
+      float s = M[e];
+      if (i == j) {
+        const int lr = MI(dof_limrow)[i];
+        if (lr >= 0) { const int r = L.ne + lr; if (Jaref[r] < 0.f) s += D[r] * WF(lims)[lr] * WF(lims)[lr]; }
+      }
+      const int h1 = MI(he_adr)[e + 1];
+#pragma unroll 1
+      for (int q = MI(he_adr)[e]; q < h1; q++) {
+        const int code = MI(he_eq)[q];
+        const int eq = code >> 2, which = code & 3;
+        const float cf = eqc[eq];
+        s += D[eq] * (which == 0 ? 1.f : (which == 1 ? cf * cf : cf));
+      }
+      const int q1 = MI(hc_adr)[e + 1];
+#pragma unroll 1
+      for (int q = MI(hc_adr)[e]; q < q1; q++) {
+        const int r3 = 3 * MI(hc_con)[q] * nv;
+        s += B[r3 + i] * WB[r3 + j] + B[r3 + nv + i] * WB[r3 + nv + j] + B[r3 + 2 * nv + i] * WB[r3 + 2 * nv + j];
+      }
+      H[e] = s;
+    }
+    __syncwarp();
+    return;
+  }
+#pragma unroll 1
   for (int k = c.lane; k < L.ntri; k += G) {
     const int ij = MI(tri)[k];
     const int i = ij >> 16, j = ij & 0xffff;
@@ -827,6 +967,7 @@ template <int G> __device__ void solver_hessian(const Ctx& c, const float* Jaref
       const float vj = (j == d1) ? 1.f : ((j == d2) ? eqc[e] : 0.f);
       s += D[e] * vi * vj;
     }
+#pragma unroll 1
     for (int it = 0; it < 3 * L.ncon; it++) s += B[it * nv + i] * WB[it * nv + j];
     H[k] = s;
   }
@@ -863,7 +1004,7 @@ template <int G> __device__ void solver_linesearch(const Ctx& c, float gauss, bo
   const Layout& L = c.L;
   float* a = WF(a); float* Ma = WF(Ma); float* Jaref = WF(Jaref);
   const float* search = WF(search); float* mv = WF(mv); float* jv = WF(jv); const float* fs = WF(fs);
-  mul_m<G>(WF(M), search, mv, L.nv, c.lane);
+  la_mul_m<G>(c, search, mv);
   mul_j<G>(c, search, jv);  // syncs
   float sn = 0.f, sMa = 0.f, sq = 0.f, smv = 0.f;
   for (int d = c.lane; d < L.nv; d += G) {
@@ -933,7 +1074,7 @@ template <int G> __device__ void stage_solve(const Ctx& c) {
     const float* v = cand ? warm : as;
     float* oM = cand ? mv : Ma;
     float* oJ = cand ? jv : Jaref;
-    mul_m<G>(M, v, oM, nv, c.lane);
+    la_mul_m<G>(c, v, oM);
     mul_j<G>(c, v, oJ);
     for (int r = c.lane; r < nefc; r += G) oJ[r] -= aref[r];
     __syncwarp();
@@ -958,10 +1099,10 @@ template <int G> __device__ void stage_solve(const Ctx& c) {
     __syncwarp();
     if (L.solver == ABR_SOLVER_NEWTON) {
       solver_hessian<G>(c, Jaref);
-      chol_factor<G>(WF(H), nv, c.lane);
+      la_factor<G>(c, WF(H));
     }
     float* mg = mv;  // free outside the line search
-    chol_solve<G>(WF(H), grad, mg, WF(y), nv, c.lane);
+    la_solve<G>(c, WF(H), grad, mg);
     if (L.iterations != 1) {
       float gn = 0.f;
       for (int d = c.lane; d < nv; d += G) gn += grad[d] * grad[d];
@@ -1003,11 +1144,13 @@ template <int G> __device__ __forceinline__ void forward(const Ctx& c) {
   stage_com<G>(c);
   stage_collision<G>(c);
   stage_crb<G>(c);
-  for (int k = c.lane; k < L.ntri; k += G) WF(H)[k] = WF(M)[k];
+  const int nent = L.sparse ? L.nnz : L.ntri;
+#pragma unroll 1
+  for (int k = c.lane; k < nent; k += G) WF(H)[k] = WF(M)[k];
   __syncwarp();
-  chol_factor<G>(WF(H), L.nv, c.lane);
+  la_factor<G>(c, WF(H));
   stage_velocity<G>(c);
-  chol_solve<G>(WF(H), WF(fs), WF(as), WF(y), L.nv, c.lane);
+  la_solve<G>(c, WF(H), WF(fs), WF(as));
   if (L.nefc == 0) {
     for (int d = c.lane; d < L.nv; d += G) { WF(a)[d] = WF(as)[d]; WF(fc)[d] = 0.f; }
     __syncwarp();
@@ -1050,15 +1193,18 @@ template <int G> __device__ bool post_forward(const Ctx& c, int stage) {
     // forward.euler (+ implicit joint damping unless EULERDAMP is disabled)
     if (!(L.disableflags & ABR_DSBL_EULERDAMP)) {
       float* H = WF(H); const float* M = WF(M);
-      for (int k = c.lane; k < L.ntri; k += G) {
-        const int ij = MI(tri)[k];
+      const int nent = L.sparse ? L.nnz : L.ntri;
+      const int* tab = L.sparse ? MI(mpair) : MI(tri);
+#pragma unroll 1
+      for (int k = c.lane; k < nent; k += G) {
+        const int ij = tab[k];
         H[k] = M[k] + (((ij >> 16) == (ij & 0xffff)) ? MF(dof_damping)[ij >> 16] * dt : 0.f);
       }
       float* rhs = WF(grad);
       for (int d = c.lane; d < nv; d += G) rhs[d] = WF(fs)[d] + WF(fc)[d];
       __syncwarp();
-      chol_factor<G>(H, nv, c.lane);
-      chol_solve<G>(H, rhs, a, WF(y), nv, c.lane);
+      la_factor<G>(c, H);
+      la_solve<G>(c, H, rhs, a);
     }
     for (int d = c.lane; d < nv; d += G) qvel[d] += a[d] * dt;
     __syncwarp();

@@ -44,8 +44,8 @@ def _rollout(m: mjx.Model, x0: Array, us: Array, cost: Optional[StaticGoalQuadra
         x0_t = torch.as_tensor(x0, dtype=torch.float32, device=dev)
         N = us_t.shape[-2]
         batch = tuple(us_t.shape[:-2]) if us_t.dim() - 2 >= x0_t.dim() - 1 else tuple(x0_t.shape[:-1])
-        us_f = us_t.expand(*batch, N, nu).reshape(-1, N, nu).contiguous()
-        W = us_f.shape[0]
+        W = int(np.prod(batch)) if len(batch) else 1
+        us_f = us_t.expand(*batch, N, nu).reshape(W, N, nu).contiguous()
         if x0_t.dim() == 1:
             x0_f, stride = x0_t.contiguous(), 0
         else:
@@ -61,8 +61,8 @@ def _rollout(m: mjx.Model, x0: Array, us: Array, cost: Optional[StaticGoalQuadra
     x0_n = np.ascontiguousarray(x0.cpu().numpy() if isinstance(x0, torch.Tensor) else x0, dtype=np.float32)
     N = us_n.shape[-2]
     batch = us_n.shape[:-2] if us_n.ndim - 2 >= x0_n.ndim - 1 else x0_n.shape[:-1]
-    us_f = np.ascontiguousarray(np.broadcast_to(us_n, (*batch, N, nu)).reshape(-1, N, nu))
-    W = us_f.shape[0]
+    W = int(np.prod(batch)) if len(batch) else 1
+    us_f = np.ascontiguousarray(np.broadcast_to(us_n, (*batch, N, nu)).reshape(W, N, nu))
     if x0_n.ndim == 1:
         x0_f, stride = x0_n, 0
     else:

@@ -17,6 +17,7 @@
 #include "abr.h"
 #include "abr_layout.h"
 #include "abr_kernels.cuh"
+#include "abr_limb.cuh"
 
 using namespace abr;
 
@@ -431,189 +432,151 @@ static int build_blob(const HostModel& m, bool alias, Layout& L, std::vector<flo
     L.i_cd_adr = P.addi(cd_adr); L.i_cd_dof = P.addi(cd_dof);
   }
 
-  // ---- limb decomposition (abr_limb.cuh)
+  // ---- limb (path) decomposition: tables of abr_limb.cuh
+  L.limb_ok = 0;
   {
-    L.limb_ok = 0;
-    bool ok = getenv("ABR_NO_LIMB") == nullptr && L.nroot == 1 && opt.solver == ABR_SOLVER_NEWTON &&
-              opt.integrator == ABR_INT_EULER && nv > 0;
-    // trunk: chain from the world while a body has exactly one child
-    std::vector<int> trunk;
+    bool ok = getenv("ABR_NO_LIMB") == nullptr && opt.solver == ABR_SOLVER_NEWTON && opt.integrator == ABR_INT_EULER &&
+              L.ne == 0 && nb >= 2 && nv >= 6 && roots.size() == 1 && roots[0] == 1;
     if (ok) {
-      int cur = 0;
-      while (childnum[cur] == 1) { cur = child[childadr[cur]]; trunk.push_back(cur); }
-      if (trunk.empty()) ok = false;
+      const int j0 = m.body_jntadr[1];
+      ok = m.body_jntnum[1] == 1 && m.jnt_type[j0] == ABR_JNT_FREE && m.jnt_dofadr[j0] == 0 && m.jnt_qposadr[j0] == 0;
+    }
+    for (int b = 2; b < nb && ok; b++) {
+      const int j = m.body_jntadr[b];
+      ok = m.body_jntnum[b] == 1 && (m.jnt_type[j] == ABR_JNT_HINGE || m.jnt_type[j] == ABR_JNT_SLIDE);
+    }
+    for (int d = 0; d < nv && ok; d++) ok = dof_actnum[d] <= 1;
+    for (int ci = 0; ci < L.ncon && ok; ci++) {  // every contact: a plane on the world body against a sphere on the tree
+      const int p = con_pair[ci];
+      ok = m.pair_kind[p] == ABR_PAIR_PLANE_SPHERE && m.geom_bodyid[m.pair_geom1[p]] == 0 && m.geom_bodyid[m.pair_geom2[p]] >= 1;
+    }
+    // lane blocks: a leaf takes one lane; an inner body the next power of two of its children's blocks
+    std::vector<int> bsize(nb, 1), lane0(nb, 0), bdepth(nb, 0);
+    auto np2 = [](int x) { int r = 1; while (r < x) r *= 2; return r; };
+    if (ok) {
+      for (int b = nb - 1; b >= 1; b--) {
+        if (!childnum[b]) continue;
+        int sum = 0;
+        for (int q = 0; q < childnum[b]; q++) sum += bsize[child[childadr[b] + q]];
+        bsize[b] = np2(sum);
+      }
+      ok = bsize[1] <= limb::kStride;
+    }
+    int NLm = 0, NCm = 0, G = 1;
+    std::vector<int> con_lane(L.ncon, 0), con_slot(L.ncon, 0);
+    if (ok) {
+      G = bsize[1];
+      for (int b = 1; b < nb; b++) {
+        if (b > 1) bdepth[b] = bdepth[m.body_parentid[b]] + 1;
+        NLm = std::max(NLm, bdepth[b]);
+        std::vector<int> kids(child.begin() + childadr[b], child.begin() + childadr[b] + childnum[b]);
+        std::stable_sort(kids.begin(), kids.end(), [&](int x, int y) { return bsize[x] > bsize[y]; });
+        int off = lane0[b];
+        for (int c : kids) { lane0[c] = off; off += bsize[c]; }
+      }
+      std::vector<int> cnt(limb::kStride, 0);
+      for (int ci = 0; ci < L.ncon; ci++) {
+        const int l = lane0[m.geom_bodyid[m.pair_geom2[con_pair[ci]]]];
+        con_lane[ci] = l; con_slot[ci] = cnt[l]++;
+        NCm = std::max(NCm, cnt[l]);
+      }
+    }
+    static const int kInst[][2] = {{3, 1}, {6, 4}};  // compiled <NL, NC> instantiations (abr_limb_*.cu)
+    int NLi = -1, NCi = -1;
+    if (ok) {
+      for (auto& in : kInst) if (in[0] >= NLm && in[1] >= NCm) { NLi = in[0]; NCi = in[1]; break; }
+      ok = NLi >= 0;
     }
     if (ok) {
-      const int last = trunk.back();
-      std::vector<int> owner(nb, -1);          // -1 world, -2 trunk, >=0 limb id
-      for (int b : trunk) owner[b] = -2;
-      int nlimb = 0;
-      for (int q = 0; q < childnum[last]; q++) owner[child[childadr[last] + q]] = nlimb++;
-      for (int b = 1; b < nb; b++) if (owner[b] == -1) owner[b] = owner[m.body_parentid[b]];
-      // merge limbs coupled by constraints
-      std::vector<int> uf(std::max(1, nlimb));
-      for (int i = 0; i < nlimb; i++) uf[i] = i;
-      auto find = [&](int x) { while (uf[x] != x) x = uf[x] = uf[uf[x]]; return x; };
-      auto unite = [&](int a, int b) { if (a >= 0 && b >= 0) uf[find(a)] = find(b); };
-      for (size_t e = 0; e < eq_j1.size(); e++)
-        if (eq_j2[e] >= 0) unite(owner[m.jnt_bodyid[eq_j1[e]]], owner[m.jnt_bodyid[eq_j2[e]]]);
-      for (int ci = 0; ci < L.ncon; ci++) {
-        const int p = con_pair[ci];
-        unite(owner[m.geom_bodyid[m.pair_geom1[p]]], owner[m.geom_bodyid[m.pair_geom2[p]]]);
-      }
-      // groups -> lanes (greedy by dof count)
-      std::vector<int> gid(std::max(1, nlimb), -1), gdofs;
-      int ngroup = 0;
-      for (int i = 0; i < nlimb; i++) { int r = find(i); if (gid[r] < 0) { gid[r] = ngroup++; gdofs.push_back(0); } gid[i] = gid[r]; }
-      for (int d = 0; d < nv; d++) { int o = owner[m.dof_bodyid[d]]; if (o >= 0) gdofs[gid[o]]++; }
-      int G = 1;
-      while (G < ngroup && G < 8) G *= 2;
-      std::vector<int> lane_of_group(std::max(1, ngroup), 0), load(G, 0);
-      {
-        std::vector<int> order(ngroup);
-        for (int i = 0; i < ngroup; i++) order[i] = i;
-        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return gdofs[a] > gdofs[b]; });
-        for (int g : order) { int best = 0; for (int l = 1; l < G; l++) if (load[l] < load[best]) best = l; lane_of_group[g] = best; load[best] += std::max(1, gdofs[g]); }
-      }
-      auto lane_of_body = [&](int b) { return owner[b] >= 0 ? lane_of_group[gid[owner[b]]] : -1; };
-      // local orderings: trunk first, then the lane's limb items in global (topological) order
-      const int ntb = (int)trunk.size();
-      std::vector<std::vector<int>> lbody(G), ljnt(G), ldof(G);
-      for (int l = 0; l < G; l++) {
-        for (int b : trunk) lbody[l].push_back(b);
-        for (int b = 1; b < nb; b++) if (lane_of_body(b) == l) lbody[l].push_back(b);
-        for (int b : lbody[l]) for (int q = 0; q < m.body_jntnum[b]; q++) {
-          int j = m.body_jntadr[b] + q;
-          ljnt[l].push_back(j);
-          int w = m.jnt_type[j] == ABR_JNT_FREE ? 6 : 1;
-          for (int k = 0; k < w; k++) ldof[l].push_back(m.jnt_dofadr[j] + k);
-        }
-      }
-      int nt = 0, ntj = 0;
-      for (int b : trunk) { nt += m.body_dofnum[b]; ntj += m.body_jntnum[b]; }
-      int NB = 0, NJ = 0, NV = 0, NZ = 0, NR = 0, NC = 0, NA = 0;
-      auto loc = [&](const std::vector<int>& v, int x) { for (size_t i = 0; i < v.size(); i++) if (v[i] == x) return (int)i; return -1; };
-      // rows / contacts / actuators per lane (trunk-owned items go to lane 0)
-      std::vector<std::vector<int>> lrow(G), lcon(G), lact(G);
-      for (int r = 0; r < L.nefc; r++) {
-        const int info = row_info[r], kind = info & 3, idx = (info >> 2) & 0x3ffff;
-        int b;
-        if (kind == 0) { int ba = m.jnt_bodyid[eq_j1[idx]], bb = eq_j2[idx] >= 0 ? m.jnt_bodyid[eq_j2[idx]] : ba; b = owner[ba] >= 0 ? ba : bb; }
-        else if (kind == 1) b = m.jnt_bodyid[lim_jnt[idx]];
-        else { const int p = con_pair[idx]; int ba = m.geom_bodyid[m.pair_geom1[p]], bb = m.geom_bodyid[m.pair_geom2[p]]; b = owner[ba] >= 0 ? ba : bb; }
-        int l = lane_of_body(b);
-        lrow[l < 0 ? 0 : l].push_back(r);
-      }
-      for (int ci = 0; ci < L.ncon; ci++) {
-        const int p = con_pair[ci];
-        int ba = m.geom_bodyid[m.pair_geom1[p]], bb = m.geom_bodyid[m.pair_geom2[p]];
-        int l = lane_of_body(owner[ba] >= 0 ? ba : bb);
-        lcon[l < 0 ? 0 : l].push_back(ci);
-      }
-      for (int u = 0; u < nu; u++) {
-        int l = lane_of_body(m.jnt_bodyid[act_jnt[u]]);
-        if (l < 0) { for (int q = 0; q < G; q++) lact[q].push_back(u); }  // trunk actuators: every lane, redundantly
-        else lact[l].push_back(u);
-      }
-      std::vector<int> nzl(G, 0);
-      for (int l = 0; l < G; l++) {
-        NB = std::max(NB, (int)lbody[l].size()); NJ = std::max(NJ, (int)ljnt[l].size()); NV = std::max(NV, (int)ldof[l].size());
-        for (int d : ldof[l]) for (int j = d; j >= 0; j = m.dof_parentid[j]) nzl[l]++;
-        NZ = std::max(NZ, nzl[l]); NR = std::max(NR, (int)lrow[l].size()); NC = std::max(NC, (int)lcon[l].size());
-        NA = std::max(NA, (int)lact[l].size());
-      }
-      if (NV > 255 || NC > 255 || NB > 255) ok = false;
-      if (ok) {
-        std::vector<int> t_nb(G), t_body(G * NB, 0), t_bpar(G * NB, -1), t_bjadr(G * NB, 0);
-        std::vector<int> t_nj(G), t_jnt(G * std::max(1, NJ), 0);
-        std::vector<int> t_nv(G), t_dof(G * NV, 0), t_dpar(G * NV, -1), t_dbody(G * NV, 0), t_djnt(G * NV, 0);
-        std::vector<int> t_radr(G * (NV + 1), 0), t_rcol(G * std::max(1, NZ), 0);
-        std::vector<int> t_nrow(G), t_row(G * std::max(1, NR) * 2, 0);
-        std::vector<int> t_ncon(G), t_con(G * std::max(1, NC), 0), t_cb1(G * std::max(1, NC), -1), t_cb2(G * std::max(1, NC), -1);
-        std::vector<int> t_cmask(G * std::max(1, NC) * NV, 0), t_crow(G * std::max(1, NC), 0);
-        std::vector<int> t_nact(G), t_act(G * std::max(1, NA), 0), t_adof(G * std::max(1, NA), 0);
-        for (int l = 0; l < G; l++) {
-          t_nb[l] = (int)lbody[l].size(); t_nj[l] = (int)ljnt[l].size(); t_nv[l] = (int)ldof[l].size();
-          for (int a = 0; a < t_nb[l]; a++) {
-            const int b = lbody[l][a];
-            t_body[l * NB + a] = b;
-            t_bpar[l * NB + a] = m.body_parentid[b] == 0 ? -1 : loc(lbody[l], m.body_parentid[b]);
-            t_bjadr[l * NB + a] = m.body_jntnum[b] ? loc(ljnt[l], m.body_jntadr[b]) : 0;
+      const limb::Map mp{NLi, NCi};
+      std::vector<float> T((size_t)mp.total() * limb::kStride, 0.f);
+      auto setf = [&](int slot, int g, float v) { T[(size_t)slot * limb::kStride + g] = v; };
+      auto seti = [&](int slot, int g, int v) { float f; memcpy(&f, &v, 4); T[(size_t)slot * limb::kStride + g] = f; };
+      const float benign[kConPrm] = {0.f, 0.f, 0.9f, 0.95f, 1000.f, 0.5f, 2.f, 1.f, 2.f, 2.f, 1.f, 0.f, 0.f, 0.f};
+      int mxbits = 0;
+      double mass = 0;
+      for (int b = 1; b < nb; b++) mass += m.body_mass[b];
+      for (int g = 0; g < limb::kStride; g++) {
+        int ownbits = 0, lvlbits = 0;
+        for (int p = 0; p <= NLi; p++) {
+          int body = -1;
+          if (g < G) for (int b = 1; b < nb; b++) if (bdepth[b] == p && g >= lane0[b] && g < lane0[b] + bsize[b]) body = b;
+          const int sb = mp.body(p);
+          if (body >= 0) {
+            int lv = 0;
+            while ((1 << lv) < bsize[body]) lv++;
+            if (g == lane0[body]) ownbits |= 1 << p;
+            lvlbits |= lv << (2 * p);
+            if (lv > ((mxbits >> (2 * p)) & 3)) mxbits = (mxbits & ~(3 << (2 * p))) | (lv << (2 * p));
+            for (int i = 0; i < 3; i++) { setf(sb + i, g, m.body_pos[3 * body + i]); setf(sb + 7 + i, g, m.body_ipos[3 * body + i]); setf(sb + 15 + i, g, m.body_inertia[3 * body + i]); }
+            for (int i = 0; i < 4; i++) { setf(sb + 3 + i, g, m.body_quat[4 * body + i]); setf(sb + 10 + i, g, m.body_iquat[4 * body + i]); }
+            setf(sb + 14, g, m.body_mass[body]);
+          } else {
+            ownbits |= 1 << p;  // padding is private
+            setf(sb + 3, g, 1.f); setf(sb + 10, g, 1.f);
           }
-          for (int a = 0; a < t_nj[l]; a++) t_jnt[l * NJ + a] = ljnt[l][a];
-          int e = 0;
-          for (int a = 0; a < t_nv[l]; a++) {
-            const int d = ldof[l][a];
-            t_dof[l * NV + a] = d;
-            t_dpar[l * NV + a] = m.dof_parentid[d] < 0 ? -1 : loc(ldof[l], m.dof_parentid[d]);
-            t_dbody[l * NV + a] = loc(lbody[l], m.dof_bodyid[d]);
-            t_djnt[l * NV + a] = loc(ljnt[l], m.dof_jntid[d]);
-            t_radr[l * (NV + 1) + a] = e;
-            for (int j = d; j >= 0; j = m.dof_parentid[j]) t_rcol[l * NZ + e++] = loc(ldof[l], j);
-          }
-          for (int a = t_nv[l]; a <= NV; a++) t_radr[l * (NV + 1) + a] = e;
-          t_ncon[l] = (int)lcon[l].size();
-          for (int k = 0; k < t_ncon[l]; k++) {
-            const int ci = lcon[l][k], p = con_pair[ci];
-            t_con[l * NC + k] = ci;
-            t_cb1[l * NC + k] = loc(lbody[l], m.geom_bodyid[m.pair_geom1[p]]);
-            t_cb2[l * NC + k] = loc(lbody[l], m.geom_bodyid[m.pair_geom2[p]]);
-            for (int a = 0; a < t_nv[l]; a++) {
-              const int mk = con_dofmask[ci * nv + ldof[l][a]];
-              t_cmask[(l * NC + k) * NV + a] = mk == 1 ? 1 : (mk == 2 ? -1 : 0);
+          if (p == 0) continue;
+          const int sj = mp.jnt(p), si = mp.ijnt(p);
+          for (int i = 0; i < kRowPrm; i++) setf(sj + 14 + i, g, benign[i]);
+          if (body >= 0) {
+            const int j = m.body_jntadr[body], d = m.jnt_dofadr[j], qa = m.jnt_qposadr[j];
+            for (int i = 0; i < 3; i++) { setf(sj + i, g, m.jnt_pos[3 * j + i]); setf(sj + 3 + i, g, m.jnt_axis[3 * j + i]); }
+            setf(sj + 6, g, m.qpos0[qa]); setf(sj + 7, g, m.qpos_spring[qa]); setf(sj + 8, g, m.jnt_stiffness[j]);
+            setf(sj + 9, g, m.dof_damping[d]); setf(sj + 10, g, m.dof_armature[d]);
+            setf(sj + 11, g, m.jnt_range[2 * j]); setf(sj + 12, g, m.jnt_range[2 * j + 1]); setf(sj + 13, g, m.jnt_margin[j]);
+            int flags = m.jnt_type[j] == ABR_JNT_HINGE ? limb::kJHinge : limb::kJSlide;
+            if (dof_limrow[d] >= 0) {
+              flags |= limb::kJLimited;
+              for (int i = 0; i < kRowPrm; i++) setf(sj + 14 + i, g, lim_prm[(size_t)kRowPrm * dof_limrow[d] + i]);
             }
+            int act = -1;
+            if (dof_actnum[d] == 1) {
+              act = dof_act[dof_actadr[d]];
+              flags |= limb::kJAct | (act_flags[act] << limb::kJActShift);
+              for (int i = 0; i < kActPrm; i++) setf(sj + 24 + i, g, act_prm[(size_t)kActPrm * act + i]);
+            }
+            seti(si, g, flags); seti(si + 1, g, d); seti(si + 2, g, qa); seti(si + 3, g, act);
+          } else {
+            setf(sj + 10, g, 1.f);  // unit armature keeps the padded dof's pivot at 1
+            seti(si, g, 0); seti(si + 1, g, -1); seti(si + 2, g, -1); seti(si + 3, g, -1);
           }
-          t_nrow[l] = (int)lrow[l].size();
-          for (int q = 0; q < t_nrow[l]; q++) {
-            const int r = lrow[l][q], info = row_info[r], kind = info & 3, idx = (info >> 2) & 0x3ffff, sub = info >> 20;
-            int a = 0, b = 255;
-            if (kind == 0) { a = loc(ldof[l], m.jnt_dofadr[eq_j1[idx]]); if (eq_j2[idx] >= 0) b = loc(ldof[l], m.jnt_dofadr[eq_j2[idx]]); }
-            else if (kind == 1) a = loc(ldof[l], m.jnt_dofadr[lim_jnt[idx]]);
-            else { a = loc(lcon[l], idx); if (sub == 0) t_crow[l * NC + a] = q; }
-            t_row[(l * NR + q) * 2] = kind | (a << 2) | (b << 10) | (sub << 18);
-            t_row[(l * NR + q) * 2 + 1] = idx;
-          }
-          t_nact[l] = (int)lact[l].size();
-          for (int k = 0; k < t_nact[l]; k++) { t_act[l * NA + k] = lact[l][k]; t_adof[l * NA + k] = loc(ldof[l], m.jnt_dofadr[act_jnt[lact[l][k]]]); }
         }
-        L.limb_ok = 1; L.lG = G; L.nt = nt; L.ntb = ntb; L.ntj = ntj; L.ntri_t = nt * (nt + 1) / 2;
-        L.NBl = NB; L.NJl = std::max(1, NJ); L.NVl = NV; L.NZl = std::max(1, NZ); L.NRl = std::max(1, NR); L.NCl = std::max(1, NC); L.NAl = std::max(1, NA);
-        L.i_lb_nb = P.addi(t_nb); L.i_lb_body = P.addi(t_body); L.i_lb_bpar = P.addi(t_bpar); L.i_lb_bjadr = P.addi(t_bjadr);
-        L.i_lb_nj = P.addi(t_nj); L.i_lb_jnt = P.addi(t_jnt);
-        L.i_lb_nv = P.addi(t_nv); L.i_lb_dof = P.addi(t_dof); L.i_lb_dpar = P.addi(t_dpar); L.i_lb_dbody = P.addi(t_dbody);
-        L.i_lb_djnt = P.addi(t_djnt); L.i_lb_radr = P.addi(t_radr); L.i_lb_rcol = P.addi(t_rcol);
-        L.i_lb_nrow = P.addi(t_nrow); L.i_lb_row = P.addi(t_row);
-        L.i_lb_ncon = P.addi(t_ncon); L.i_lb_con = P.addi(t_con); L.i_lb_cb1 = P.addi(t_cb1); L.i_lb_cb2 = P.addi(t_cb2);
-        L.i_lb_cmask = P.addi(t_cmask); L.i_lb_crow = P.addi(t_crow);
-        L.i_lb_nact = P.addi(t_nact); L.i_lb_act = P.addi(t_act); L.i_lb_adof = P.addi(t_adof);
-        // slice layout (floats per lane), with aliasing of regions whose live ranges are disjoint
-        int o = 0;
-        auto tk = [&](int n) { int r = o; o += n; return r; };
-        const int NRr = L.NRl, NCc = L.NCl;
-        L.s_cinert = tk(10 * NB); L.s_cdof = tk(6 * NV);
-        L.s_M = tk(L.NZl); L.s_H = tk(L.NZl); L.s_S = tk(std::max(1, L.ntri_t)); L.s_invD = tk(NV); L.s_t = tk(std::max(1, nt));
-        L.s_B = tk(3 * NCc * NV); L.s_bv = tk(3 * NCc);
-        L.s_D = tk(NRr); L.s_aref = tk(NRr); L.s_coef = tk(NRr);
-        L.s_v = tk(NV); L.s_fs = tk(NV); L.s_as = tk(NV); L.s_a = tk(NV); L.s_fc = tk(NV); L.s_z = tk(NV);
-        const int base = o;
-        // position phase                                            | solver phase
-        L.s_xpos = tk(3 * NB); L.s_xquat = tk(4 * NB); L.s_xipos = tk(3 * NB); L.s_xanchor = tk(3 * L.NJl); L.s_xaxis = tk(3 * L.NJl);
-        L.s_cdist = tk(NCc); L.s_cpos = tk(3 * NCc); L.s_cframe = tk(9 * NCc);
-        const int endA = o;
-        if (alias) o = base;
-        L.s_Ma = tk(NV); L.s_grad = tk(NV); L.s_search = tk(NV); L.s_mv = tk(NV);
-        L.s_Jaref = tk(NRr); L.s_jv = tk(NRr); L.s_force = tk(NRr); L.s_WB = tk(3 * NCc * NV);
-        o = std::max(o, endA);
-        const int baseB = o;
-        L.s_crb = tk(10 * NB);
-        const int endB = o;
-        if (alias) o = baseB;
-        L.s_cvel = tk(6 * NB); L.s_cacc = tk(6 * NB); L.s_cdd = tk(6 * NV);
-        o = std::max(o, endB);
-        L.slice_stride = o | 1;
-        L.h_qpos = 0; L.h_qvel = nq; L.h_warm = nq + nv; L.h_ctrl = nq + 2 * nv;
-        L.sh_stride = nq + 2 * nv + nu;
+        for (int i = 0; i < 6; i++) { setf(mp.trunk() + i, g, m.dof_damping[i]); setf(mp.trunk() + 6 + i, g, m.dof_armature[i]); }
+        for (int c = 0; c < NCi; c++) {
+          const int sc = mp.con(c);
+          for (int i = 0; i < kConPrm; i++) setf(sc + 4 + i, g, benign[i]);
+          setf(sc + 20, g, 1.f); setf(sc + 24, g, 1.f); setf(sc + 28, g, 1.f); setf(sc + 32, g, 1.f);
+          seti(mp.icon(c), g, -1); seti(mp.icon(c) + 1, g, 3);
+        }
+        seti(mp.ish(), g, ownbits); seti(mp.ish() + 1, g, lvlbits);
       }
+      for (int ci = 0; ci < L.ncon; ci++) {
+        const int g = con_lane[ci], c = con_slot[ci], p = con_pair[ci];
+        const int g1 = m.pair_geom1[p], g2 = m.pair_geom2[p];
+        const int sc = mp.con(c);
+        for (int i = 0; i < 3; i++) setf(sc + i, g, m.geom_pos[3 * g2 + i]);
+        setf(sc + 3, g, m.geom_size[3 * g2]);
+        for (int i = 0; i < kConPrm; i++) setf(sc + 4 + i, g, con_prm[(size_t)kConPrm * p + i]);
+        // plane on the world body: normal = z axis of the geom frame, frame as in math.make_frame
+        const float* q = &m.geom_quat[4 * g1];
+        float a[3] = {2.f * (q[1] * q[3] + q[0] * q[2]), 2.f * (q[2] * q[3] - q[0] * q[1]), q[0] * q[0] - q[1] * q[1] - q[2] * q[2] + q[3] * q[3]};
+        float an = std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+        for (int i = 0; i < 3; i++) { setf(sc + 18 + i, g, a[i]); setf(sc + 21 + i, g, m.geom_pos[3 * g1 + i]); }
+        float fa[3] = {a[0] / an, a[1] / an, a[2] / an}, fb[3] = {0.f, 0.f, 0.f};
+        if (-0.5f < fa[1] && fa[1] < 0.5f) fb[1] = 1.f; else fb[2] = 1.f;
+        const float ab = fa[0] * fb[0] + fa[1] * fb[1] + fa[2] * fb[2];
+        for (int i = 0; i < 3; i++) fb[i] -= fa[i] * ab;
+        const float bn = std::sqrt(fb[0] * fb[0] + fb[1] * fb[1] + fb[2] * fb[2]);
+        for (int i = 0; i < 3; i++) fb[i] /= bn;
+        const float fcx[3] = {fa[1] * fb[2] - fa[2] * fb[1], fa[2] * fb[0] - fa[0] * fb[2], fa[0] * fb[1] - fa[1] * fb[0]};
+        for (int i = 0; i < 3; i++) { setf(sc + 24 + i, g, fa[i]); setf(sc + 27 + i, g, fb[i]); setf(sc + 30 + i, g, fcx[i]); }
+        seti(mp.icon(c), g, bdepth[m.geom_bodyid[g2]]); seti(mp.icon(c) + 1, g, m.pair_condim[p]);
+      }
+      while (P.f.size() % 4) P.f.push_back(0.f);
+      L.limb_ok = 1; L.lNL = NLi; L.lNC = NCi; L.l_mx = mxbits; L.l_mass = (float)mass;
+      L.lg2G = 0;
+      while ((1 << L.lg2G) < G) L.lg2G++;
+      L.f_ltab = P.addf(T);
     }
   }
 
@@ -709,9 +672,9 @@ __global__ void __launch_bounds__(1024) k_ffma(float* out, int iters, float a, f
 
 // ================================================================================ launch helpers
 static int pick_lanes(const AbrModel* m, int nworld) {
-  if (m->lanes) return m->lanes;
+  if (m->lanes > 1) return m->lanes;
   const char* e = getenv("ABR_LANES");
-  if (e && atoi(e) > 0) return atoi(e);
+  if (e && atoi(e) > 1) return atoi(e);
   // enough worlds to fill the machine with narrow groups -> better lane efficiency
   const long per_sm = (long)nworld / m->num_sms;
   if (per_sm >= 256) return 8;
@@ -724,8 +687,21 @@ static int launch_result(int rc) {
   if (rc == -1000) return fail(ABR_ECAPACITY, "model does not fit in shared memory");
   return fail(ABR_ECUDA, std::string("kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
 }
+// the limb path serves eligible models unless a generic group size was pinned (lanes = 4..32);
+// lanes = 1 pins the limb path. Dense (non-diagonal) cost matrices stay on the generic kernels.
+static bool use_limb(const AbrModel* m, const Layout& L, bool dense_cost, bool debug) {
+  if (!L.limb_ok || debug || dense_cost) return false;
+  int lanes = m->lanes;
+  if (!lanes) { const char* e = getenv("ABR_LANES"); if (e) lanes = atoi(e); }
+  return lanes == 0 || lanes == 1;
+}
 static int launch_rollout(const AbrModel* m, const Layout& L, const RolloutArgs& a, cudaStream_t st) {
   if (a.nworld <= 0) return ABR_OK;
+  if (use_limb(m, L, a.cost.enabled && !a.cost.diag, false)) {
+    if (L.lNL == 3 && L.lNC == 1) return launch_result(launch_limb_rollout_3_1(L, a, st));
+    if (L.lNL == 6 && L.lNC == 4) return launch_result(launch_limb_rollout_6_4(L, a, st));
+    return fail(ABR_ECAPACITY, "no compiled limb kernel for this model");
+  }
   LaunchCfg cfg{m->max_smem};
   switch (pick_lanes(m, a.nworld)) {
     case 4: return launch_result(launch_rollout_4(cfg, L, a, st));
@@ -736,6 +712,11 @@ static int launch_rollout(const AbrModel* m, const Layout& L, const RolloutArgs&
 }
 static int launch_env(const AbrModel* m, const Layout& L, const EnvArgs& a, cudaStream_t st) {
   if (a.E <= 0) return ABR_OK;
+  if (use_limb(m, L, false, a.dbg != nullptr)) {
+    if (L.lNL == 3 && L.lNC == 1) return launch_result(launch_limb_env_3_1(L, a, st));
+    if (L.lNL == 6 && L.lNC == 4) return launch_result(launch_limb_env_6_4(L, a, st));
+    return fail(ABR_ECAPACITY, "no compiled limb kernel for this model");
+  }
   LaunchCfg cfg{m->max_smem};
   switch (pick_lanes(m, a.E)) {
     case 4: return launch_result(launch_env_4(cfg, L, a, st));
@@ -842,7 +823,8 @@ int abr_model_info(const AbrModel* m, int* ncon, int* ne, int* nl, int* nefc, in
 
 int abr_model_set_lanes(AbrModel* m, int lanes) {
   if (!m) return fail(ABR_EINVAL, "abr_model_set_lanes: null model");
-  if (lanes != 0 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32) return fail(ABR_EINVAL, "lanes must be 0, 4, 8, 16 or 32");
+  if (lanes != 0 && lanes != 1 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32) return fail(ABR_EINVAL, "lanes must be 0, 1, 4, 8, 16 or 32");
+  if (lanes == 1 && !m->lay.limb_ok) return fail(ABR_EUNSUPPORTED, "lanes = 1 pins the limb path, which this model/options are not eligible for");
   m->lanes = lanes;
   return ABR_OK;
 }

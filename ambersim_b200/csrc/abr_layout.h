@@ -70,26 +70,13 @@ struct Layout {
   int w_xpos, w_xquat, w_xipos, w_xanchor, w_xaxis, w_rootcom, w_cinert, w_cdof;
   int w_crb, w_buf, w_cvel, w_cacc, w_cdofdot, w_cdist, w_cpos, w_cframe, w_actf, w_bv;
   int w_a, w_Ma, w_grad, w_search, w_mv, w_fc, w_Jaref, w_jv, w_force, w_Fc, w_WB, w_y, w_invD;
-  // ---- limb path (abr_limb.cuh): one lane per subtree ("limb") hanging off the kinematic trunk.
-  //      Every lane simulates trunk + its own limbs out of a private, bank-conflict-free slice;
-  //      the trunk is processed redundantly and coupled through shuffle reductions.
-  int limb_ok;      // model/options eligible for the limb kernel
-  int lG;           // lanes per world (1, 2, 4 or 8)
-  int nt, ntb, ntj, ntri_t;            // trunk dofs / bodies / joints, nt(nt+1)/2
-  int NBl, NJl, NVl, NZl, NRl, NCl, NAl; // per-lane maxima: bodies, joints, dofs, sparse entries, rows, contacts, actuators
-  int i_lb_nb, i_lb_body, i_lb_bpar, i_lb_bjadr;
-  int i_lb_nj, i_lb_jnt;
-  int i_lb_nv, i_lb_dof, i_lb_dpar, i_lb_dbody, i_lb_djnt, i_lb_radr, i_lb_rcol;
-  int i_lb_nrow, i_lb_row;             // 2 ints per row: kind | a<<2 | b<<10 | sub<<18 ; global index
-  int i_lb_ncon, i_lb_con, i_lb_cb1, i_lb_cb2, i_lb_cmask, i_lb_crow;
-  int i_lb_nact, i_lb_act, i_lb_adof;
-  int s_xpos, s_xquat, s_xipos, s_xanchor, s_xaxis, s_cinert, s_crb, s_cdof, s_cdd, s_cvel, s_cacc;
-  int s_M, s_H, s_S, s_invD, s_cdist, s_cpos, s_cframe, s_B, s_WB, s_bv;
-  int s_D, s_aref, s_coef, s_Jaref, s_jv, s_force;
-  int s_v, s_fs, s_as, s_a, s_Ma, s_grad, s_search, s_mv, s_fc, s_z, s_t;
-  int slice_stride; // floats per lane slice (odd => conflict-free when all lanes use one offset)
-  int sh_stride;    // floats per world of shared state: qpos qvel warm ctrl
-  int h_qpos, h_qvel, h_warm, h_ctrl;
+  // ---- limb path (abr_limb.cuh): one lane per root-to-leaf path of a floating-base tree
+  int limb_ok;      // model/options eligible for the limb kernels
+  int lNL, lNC;     // compiled instantiation that serves this model (chain length, contacts per path)
+  int lg2G;         // log2 of the lanes per world (paths padded to a power of two, <= 8)
+  int l_mx;         // 2 bits per chain position: log2 of the largest lane group sharing a body there
+  int f_ltab;       // float-pool offset of the per-lane table (limb::Map, row stride limb::kStride)
+  float l_mass;     // total mass of the tree (subtree CoM denominator)
   int w_rk;         // RK4 save area: qpos0[nq] qvel0[nv] warm0[nv] sv[nv] sa[nv] kq[nv]
   int world_stride; // floats per world
 };

@@ -1,0 +1,1038 @@
+// abr_limb.cuh — the path-decomposed ("limb") world step: the fast path of the engine.
+//
+// A floating-base articulated body whose other bodies carry one hinge/slide joint each (quadruped,
+// biped, exoskeleton, hand on a free base ...) is cut into its root-to-leaf paths. One LANE owns
+// one path: trunk (free joint, 6 dofs) + NL chain bodies, so every local dof is an ancestor of all
+// later ones and the lane's joint-space inertia / Newton Hessian is a plain dense lower triangle
+// of order N = 6 + NL with compile-time indices. The whole world step is straight-line code over
+// per-lane arrays that the compiler keeps in registers: no index tables, no shared-memory state,
+// no __syncwarp, no divergence between lanes (per-lane differences are selects).
+//
+// Bodies shared by several paths (the trunk by all G lanes; e.g. a torso by its two arm paths)
+// are processed redundantly and stay bit-identical across their lanes. Quantities that flow up the
+// tree (composite inertia, RNE forces, L'DL Schur updates, M v and J'f partial sums, the subtree
+// CoM) are held as per-lane SHARES on shared bodies and summed over the sharing lane group with
+// xor-butterfly shuffles right before they are consumed ("merge"); a contribution produced on a
+// shared body is added by that body's owner lane only, so it is counted once. G worlds-lanes are
+// packed 32/G worlds to a warp.
+//
+// Replaces the third-party mjx.step behind ambersim/trajopt/shooting.py:41 and
+// ambersim/rl/base.py:93 for eligible models (see build_limb in abr_engine.cu); everything else
+// runs on the generic G-lane kernel (abr_step.cuh). Formulas follow SURVEY.md Appendix A.
+#ifndef ABR_LIMB_CUH_
+#define ABR_LIMB_CUH_
+
+#include "abr_kernels.cuh"
+
+namespace abr {
+namespace limb {
+
+// ---- per-lane model table: word (slot, lane) lives at T[slot * kStride + lane]
+constexpr int kStride = 8;  // max lanes per world
+constexpr int kBodyW = 18;  // body_pos3 body_quat4 body_ipos3 body_iquat4 mass inertia3
+constexpr int kJntW = 35;   // jnt_pos3 jnt_axis3 qpos0 qpos_spring stiffness damping armature range2 margin | limit prm[10] | act prm[11]
+constexpr int kConW = 33;   // geom_pos3 radius | con prm[14] | plane normal3 point3 frame9
+constexpr int kJntI = 4;    // flags, global dof, global qpos adr, global actuator
+constexpr int kConI = 2;    // local body position of the sphere (-1 = empty slot), condim
+struct Map {
+  int NL, NC;
+  __host__ __device__ constexpr int body(int p) const { return kBodyW * p; }
+  __host__ __device__ constexpr int jnt(int p) const { return kBodyW * (NL + 1) + kJntW * (p - 1); }
+  __host__ __device__ constexpr int trunk() const { return kBodyW * (NL + 1) + kJntW * NL; }  // damping[6] armature[6]
+  __host__ __device__ constexpr int con(int c) const { return trunk() + 12 + kConW * c; }
+  __host__ __device__ constexpr int ijnt(int p) const { return con(NC) + kJntI * (p - 1); }
+  __host__ __device__ constexpr int ish() const { return ijnt(NL + 1); }  // own bits, level bits
+  __host__ __device__ constexpr int icon(int c) const { return ish() + 2 + kConI * c; }
+  __host__ __device__ constexpr int total() const { return icon(NC); }
+};
+// joint flag bits
+constexpr int kJHinge = 1, kJSlide = 2, kJTypeMask = 3, kJLimited = 4, kJAct = 8, kJActShift = 4;
+
+__host__ __device__ constexpr int PD(int d) { return d < 6 ? 0 : d - 5; }   // dof -> position
+__host__ __device__ constexpr int FD(int p) { return p == 0 ? 0 : 5 + p; }  // first dof of a position
+__host__ __device__ constexpr int LD(int p) { return 5 + p; }               // last dof of a position
+__host__ __device__ constexpr int TR(int i, int j) { return i * (i + 1) / 2 + j; }
+
+// per-lane sharing info
+struct Share {
+  int own;   // bit p: this lane is the owner of its body at position p (always set on private bodies)
+  int lvl;   // 2 bits per position: log2 of the lane-group size sharing the body
+  int mx;    // 2 bits per position: max of lvl over the lanes (uniform)
+  int lg;    // log2(G)
+  __device__ __forceinline__ bool o(int p) const { return (own >> p) & 1; }
+  __device__ __forceinline__ int l(int p) const { return (lvl >> (2 * p)) & 3; }
+  __device__ __forceinline__ int m(int p) const { return (mx >> (2 * p)) & 3; }
+};
+
+// sum over the lane group of level `lv` (per lane, uniform within a group); mxl is uniform
+__device__ __forceinline__ float gs(float x, int lv, int mxl) {
+  if (mxl > 0) { const float y = __shfl_xor_sync(ABR_FULL, x, 1); x = (lv > 0) ? x + y : x; }
+  if (mxl > 1) { const float y = __shfl_xor_sync(ABR_FULL, x, 2); x = (lv > 1) ? x + y : x; }
+  if (mxl > 2) { const float y = __shfl_xor_sync(ABR_FULL, x, 4); x = (lv > 2) ? x + y : x; }
+  return x;
+}
+__device__ __forceinline__ float gall(float x, int lg) { return gs(x, lg, lg); }
+
+// ------------------------------------------------------------------------------ dense local L'DL
+// A: packed lower triangle in "share" form on shared rows. Leaves-first elimination (MuJoCo's
+// L'DL order): after the call A holds D on the diagonal and D*L below it, replicated on shared rows.
+template <int N> __device__ __forceinline__ void ldl_factor(float (&A)[N * (N + 1) / 2], float (&invD)[N], const Share& S) {
+#pragma unroll
+  for (int k = N - 1; k >= 0; k--) {
+    const int p = PD(k);
+    if (k == LD(p) && S.m(p)) {  // merge the rows of position p before they are used as pivots
+      const int lv = S.l(p), mxl = S.m(p);
+#pragma unroll
+      for (int i = 0; i < N; i++)
+#pragma unroll
+        for (int j = 0; j < N; j++)
+          if (PD(i) == p && j <= i) A[TR(i, j)] = gs(A[TR(i, j)], lv, mxl);
+    }
+    const float d = 1.f / fmaxf(A[TR(k, k)], kMinVal);
+    invD[k] = d;
+    const bool ownp = S.o(p);
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      if (i < k) {
+        float t = A[TR(k, i)] * d;
+        if (PD(i) != p) t = ownp ? t : 0.f;  // shallower rows hold shares: the owner adds the update
+#pragma unroll
+        for (int j = 0; j < N; j++)
+          if (j <= i) A[TR(i, j)] = fmaf(-t, A[TR(k, j)], A[TR(i, j)]);
+      }
+    }
+  }
+}
+// x <- (L'DL)^-1 x ; x comes in full (replicated on shared dofs) and leaves full
+template <int N> __device__ __forceinline__ void ldl_solve(const float (&A)[N * (N + 1) / 2], const float (&invD)[N], float (&x)[N], const Share& S) {
+#pragma unroll
+  for (int i = 0; i < N; i++) x[i] = S.o(PD(i)) ? x[i] : 0.f;  // to share form
+#pragma unroll
+  for (int k = N - 1; k >= 0; k--) {
+    const int p = PD(k);
+    if (k == LD(p) && S.m(p)) {
+      const int lv = S.l(p), mxl = S.m(p);
+#pragma unroll
+      for (int i = 0; i < N; i++)
+        if (PD(i) == p) x[i] = gs(x[i], lv, mxl);
+    }
+    const float t0 = x[k] * invD[k];
+    const bool ownp = S.o(p);
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      if (i < k) {
+        float t = A[TR(k, i)] * t0;
+        if (PD(i) != p) t = ownp ? t : 0.f;
+        x[i] -= t;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < N; i++)
+      if (i < k) acc = fmaf(A[TR(k, i)], x[i], acc);
+    x[k] = (x[k] - acc) * invD[k];
+  }
+}
+// out = M x, M full (replicated on shared rows), x full
+template <int N> __device__ __forceinline__ void mul_m(const float (&M)[N * (N + 1) / 2], const float (&x)[N], float (&out)[N], const Share& S) {
+  float up[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    float lo = 0.f;
+    float u = 0.f;
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+      if (j <= i) lo = fmaf(M[TR(i, j)], x[j], lo);
+      else if (PD(j) == PD(i)) lo = fmaf(M[TR(j, i)], x[j], lo);
+      else u += S.o(PD(j)) ? M[TR(j, i)] * x[j] : 0.f;
+    }
+    out[i] = lo; up[i] = u;
+  }
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    const int p = PD(i);
+    if (S.m(p)) up[i] = gs(up[i], S.l(p), S.m(p));
+    out[i] += up[i];
+  }
+}
+
+// ------------------------------------------------------------------------------ lane state
+template <int NL, int NC> struct Lane {
+  static constexpr int NP = NL + 1, N = 6 + NL, NTRI = N * (N + 1) / 2, NR = NL + 4 * NC;
+  float qt[7];     // trunk qpos: position, quaternion
+  float qc[NL];    // chain joint positions
+  float v[N];      // qvel (trunk 6, chain)
+  float warm[N];   // qacc_warmstart
+  float ctrl[NL];  // control of the chain joint's actuator
+  float a[N];      // qacc of the last forward
+};
+
+struct LaneCfg {
+  const float* T;  // table + lane-in-group
+  Share S;
+  float dt, grav[3], mass, tol, ls_tol, meaninertia;
+  int iterations, ls_iterations, disableflags, nefc, nv;
+};
+
+#define LTF(slot) (C.T[(slot) * kStride])
+#define LTI(slot) (__float_as_int(C.T[(slot) * kStride]))
+
+// kbi: impedance, D and aref of one active row (constraint._kbi / _row in SURVEY App. A.7)
+__device__ __forceinline__ void row_kbi(const float* prm /* smem, stride kStride */, float pos, float jvel, float invw, bool active, float& D, float& aref) {
+  const float k = prm[0 * kStride], b = prm[1 * kStride], dmin = prm[2 * kStride], dmax = prm[3 * kStride];
+  const float iw = prm[4 * kStride], mid = prm[5 * kStride], power = prm[6 * kStride];
+  const float x = fabsf(pos) * iw;
+  float ia, ib;
+  if (power == 2.f) { ia = x * x; const float t = 1.f - x; ib = t * t; }
+  else if (power == 1.f) { ia = x; ib = 1.f - x; }
+  else { ia = powf(x, power); ib = powf(1.f - x, power); }
+  const float y = (x < mid) ? prm[8 * kStride] * ia : 1.f - prm[9 * kStride] * ib;
+  float imp = dmin + y * (dmax - dmin);
+  imp = fminf(fmaxf(imp, dmin), dmax);
+  if (x > 1.f) imp = dmax;
+  const float R = fmaxf(invw * (1.f - imp) / imp, kMinVal);
+  D = active ? 1.f / R : 0.f;
+  aref = active ? -b * jvel - k * imp * pos : 0.f;
+}
+
+struct LSP { float alpha, cost, d0, d1; };
+
+// constraint rows of one lane: NL joint-limit rows (chain dof 6 + r), then 4 pyramid rows per contact slot
+template <int NL, int NC> struct Rows {
+  static constexpr int N = 6 + NL, NR = NL + 4 * NC, NCC = NC > 0 ? NC : 1;
+  float D[NR], aref[NR], lsg[NL];
+  float B[NCC][3][N];       // contact Jacobian basis: normal, tangent 1, tangent 2
+  float mu1[NCC], mu2[NCC]; // 0 on condim-1 slots
+};
+// out = J x for the structured Jacobian
+template <int NL, int NC> __device__ __forceinline__ void mul_j(const Rows<NL, NC>& R, const float (&x)[6 + NL], float (&out)[NL + 4 * NC]) {
+  constexpr int N = 6 + NL;
+#pragma unroll
+  for (int r = 0; r < NL; r++) out[r] = R.lsg[r] * x[6 + r];
+#pragma unroll
+  for (int c = 0; c < NC; c++) {
+    float bv[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      float t = 0.f;
+#pragma unroll
+      for (int d = 0; d < N; d++) t = fmaf(R.B[c][k][d], x[d], t);
+      bv[k] = t;
+    }
+    out[NL + 4 * c + 0] = fmaf(R.mu1[c], bv[1], bv[0]);
+    out[NL + 4 * c + 1] = fmaf(-R.mu1[c], bv[1], bv[0]);
+    out[NL + 4 * c + 2] = fmaf(R.mu2[c], bv[2], bv[0]);
+    out[NL + 4 * c + 3] = fmaf(-R.mu2[c], bv[2], bv[0]);
+  }
+}
+// cost = 0.5 sum_active D Jaref^2 + 0.5 (Ma - fs).(a - as); uniform over the world's lanes
+template <int NL, int NC> __device__ __forceinline__ float solver_cost(const Rows<NL, NC>& R, const Share& S, const float (&x)[6 + NL], const float (&Mx)[6 + NL],
+                                                                       const float (&Jx)[NL + 4 * NC], const float (&fs)[6 + NL], const float (&as)[6 + NL], float& gauss) {
+  float sc = 0.f, g = 0.f;
+#pragma unroll
+  for (int r = 0; r < NL + 4 * NC; r++) sc += (Jx[r] < 0.f) ? R.D[r] * Jx[r] * Jx[r] : 0.f;
+#pragma unroll
+  for (int d = 0; d < 6 + NL; d++) g += S.o(PD(d)) ? (Mx[d] - fs[d]) * (x[d] - as[d]) : 0.f;
+  sc = gall(sc, S.lg); g = gall(g, S.lg);
+  gauss = 0.5f * g;
+  return 0.5f * sc + 0.5f * g;
+}
+// one point of the exact line search: (cost, d0, d1) at alpha
+template <int NL, int NC> __device__ __forceinline__ LSP ls_eval(const Rows<NL, NC>& R, const float (&Jaref)[NL + 4 * NC], const float (&jv)[NL + 4 * NC], float alpha,
+                                                                 float qg0, float qg1, float qg2, int lg) {
+  float q0 = 0.f, q1 = 0.f, q2 = 0.f;
+#pragma unroll
+  for (int r = 0; r < NL + 4 * NC; r++) {
+    const float ja = Jaref[r], w = jv[r];
+    const float x = fmaf(alpha, w, ja);
+    const float Dr = (x < 0.f) ? R.D[r] : 0.f;
+    q0 = fmaf(0.5f * ja * ja, Dr, q0); q1 = fmaf(w * ja, Dr, q1); q2 = fmaf(0.5f * w * w, Dr, q2);
+  }
+  q0 = gall(q0, lg) + qg0; q1 = gall(q1, lg) + qg1; q2 = gall(q2, lg) + qg2;
+  LSP pt;
+  pt.alpha = alpha;
+  pt.cost = alpha * alpha * q2 + alpha * q1 + q0;
+  pt.d0 = 2.f * alpha * q2 + q1;
+  pt.d1 = 2.f * q2 + ((q2 == 0.f) ? kMinVal : 0.f);
+  return pt;
+}
+
+// mjx.forward for one lane: on exit s.a = qacc, s.warm = qacc; M, fs, fc are returned for the
+// implicit-damping Euler variant.
+template <int NL, int NC>
+__device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg& C, float (&M)[(6 + NL) * (7 + NL) / 2], float (&fs)[6 + NL], float (&fc)[6 + NL]) {
+  constexpr int NP = NL + 1, N = 6 + NL, NTRI = N * (N + 1) / 2, NR = NL + 4 * NC;
+  constexpr Map mp{NL, NC};
+  const Share& S = C.S;
+  // ---------------------------------------------------------------- kinematics (smooth.kinematics)
+  float xpos[NP][3], xquat[NP][4], xipos[NP][3], xanc[NP][3], xax[NP][3];
+  {
+    float q[4] = {s.qt[3], s.qt[4], s.qt[5], s.qt[6]};
+    v_normalize(q, 4);
+    s.qt[3] = q[0]; s.qt[4] = q[1]; s.qt[5] = q[2]; s.qt[6] = q[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) { xpos[0][i] = s.qt[i]; xanc[0][i] = s.qt[i]; xax[0][i] = (i == 2) ? 1.f : 0.f; }
+#pragma unroll
+    for (int i = 0; i < 4; i++) xquat[0][i] = q[i];
+    const float ip[3] = {LTF(mp.body(0) + 7), LTF(mp.body(0) + 8), LTF(mp.body(0) + 9)};
+    float r[3];
+    q_rot(ip, q, r);
+#pragma unroll
+    for (int i = 0; i < 3; i++) xipos[0][i] = xpos[0][i] + r[i];
+  }
+  int jflags[NP];
+  jflags[0] = 0;
+#pragma unroll
+  for (int p = 1; p < NP; p++) {
+    const int fl = LTI(mp.ijnt(p));
+    jflags[p] = fl;
+    const int type = fl & kJTypeMask;
+    const float bp[3] = {LTF(mp.body(p)), LTF(mp.body(p) + 1), LTF(mp.body(p) + 2)};
+    const float bq[4] = {LTF(mp.body(p) + 3), LTF(mp.body(p) + 4), LTF(mp.body(p) + 5), LTF(mp.body(p) + 6)};
+    const float jp[3] = {LTF(mp.jnt(p)), LTF(mp.jnt(p) + 1), LTF(mp.jnt(p) + 2)};
+    const float jx[3] = {LTF(mp.jnt(p) + 3), LTF(mp.jnt(p) + 4), LTF(mp.jnt(p) + 5)};
+    float r[3], pos[3], quat[4], axis[3], anchor[3];
+    q_rot(bp, xquat[p - 1], r);
+#pragma unroll
+    for (int i = 0; i < 3; i++) pos[i] = xpos[p - 1][i] + r[i];
+    q_mul(xquat[p - 1], bq, quat);
+    q_rot(jp, quat, r);
+#pragma unroll
+    for (int i = 0; i < 3; i++) anchor[i] = r[i] + pos[i];
+    q_rot(jx, quat, axis);
+    const float dq = s.qc[p - 1] - LTF(mp.jnt(p) + 6);
+    // hinge: rotate about the joint axis and re-anchor; slide: translate along the axis
+    float ql[4], qn[4];
+    axis_angle_quat(jx, (type == kJHinge) ? dq : 0.f, ql);
+    q_mul(quat, ql, qn);
+    q_rot(jp, qn, r);
+    const float sl = (type == kJSlide) ? dq : 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; i++) pos[i] = anchor[i] - r[i] + axis[i] * sl;
+#pragma unroll
+    for (int i = 0; i < 3; i++) { xpos[p][i] = pos[i]; xanc[p][i] = anchor[i]; xax[p][i] = axis[i]; }
+#pragma unroll
+    for (int i = 0; i < 4; i++) xquat[p][i] = qn[i];
+    const float ip[3] = {LTF(mp.body(p) + 7), LTF(mp.body(p) + 8), LTF(mp.body(p) + 9)};
+    q_rot(ip, qn, r);
+#pragma unroll
+    for (int i = 0; i < 3; i++) xipos[p][i] = pos[i] + r[i];
+  }
+  // ---------------------------------------------------------------- com_pos: subtree CoM, cinert, cdof
+  float com[3];
+  {
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+      const float ms = S.o(p) ? LTF(mp.body(p) + 14) : 0.f;
+      sx = fmaf(xipos[p][0], ms, sx); sy = fmaf(xipos[p][1], ms, sy); sz = fmaf(xipos[p][2], ms, sz);
+    }
+    sx = gall(sx, S.lg); sy = gall(sy, S.lg); sz = gall(sz, S.lg);
+    com[0] = sx / C.mass; com[1] = sy / C.mass; com[2] = sz / C.mass;
+  }
+  float cinert[NP][10];
+#pragma unroll
+  for (int p = 0; p < NP; p++) {
+    const float off[3] = {xipos[p][0] - com[0], xipos[p][1] - com[1], xipos[p][2] - com[2]};
+    const float ms = LTF(mp.body(p) + 14);
+    const float iq[4] = {LTF(mp.body(p) + 10), LTF(mp.body(p) + 11), LTF(mp.body(p) + 12), LTF(mp.body(p) + 13)};
+    const float in[3] = {LTF(mp.body(p) + 15), LTF(mp.body(p) + 16), LTF(mp.body(p) + 17)};
+    float q2[4], R[9];
+    q_mul(xquat[p], iq, q2);
+    q_to_mat(q2, R);
+    const float oo = v_dot(off, off);
+    constexpr int ra[6] = {0, 1, 2, 0, 0, 1}, cb[6] = {0, 1, 2, 1, 2, 2};
+#pragma unroll
+    for (int e = 0; e < 6; e++) {
+      const int r_ = ra[e], c_ = cb[e];
+      float t = R[3 * r_] * in[0] * R[3 * c_] + R[3 * r_ + 1] * in[1] * R[3 * c_ + 1] + R[3 * r_ + 2] * in[2] * R[3 * c_ + 2];
+      t += ms * ((r_ == c_ ? oo : 0.f) - off[r_] * off[c_]);
+      cinert[p][e] = t;
+    }
+    cinert[p][6] = off[0] * ms; cinert[p][7] = off[1] * ms; cinert[p][8] = off[2] * ms; cinert[p][9] = ms;
+  }
+  float cdof[N][6];
+  {
+    const float off[3] = {com[0] - xanc[0][0], com[1] - xanc[0][1], com[2] - xanc[0][2]};
+    float R[9];
+    q_to_mat(xquat[0], R);
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+#pragma unroll
+      for (int i = 0; i < 6; i++) cdof[q][i] = (i == 3 + q) ? 1.f : 0.f;
+      const float ax[3] = {R[q], R[3 + q], R[6 + q]};
+      float cr[3];
+      v_cross(ax, off, cr);
+      cdof[3 + q][0] = ax[0]; cdof[3 + q][1] = ax[1]; cdof[3 + q][2] = ax[2];
+      cdof[3 + q][3] = cr[0]; cdof[3 + q][4] = cr[1]; cdof[3 + q][5] = cr[2];
+    }
+  }
+#pragma unroll
+  for (int p = 1; p < NP; p++) {
+    const int d = 5 + p;
+    const bool hinge = (jflags[p] & kJTypeMask) == kJHinge;
+    const float off[3] = {com[0] - xanc[p][0], com[1] - xanc[p][1], com[2] - xanc[p][2]};
+    float cr[3];
+    v_cross(xax[p], off, cr);
+#pragma unroll
+    for (int i = 0; i < 3; i++) { cdof[d][i] = hinge ? xax[p][i] : 0.f; cdof[d][3 + i] = hinge ? cr[i] : xax[p][i]; }
+  }
+  // ---------------------------------------------------------------- collision (plane - sphere) + Jacobian basis
+  Rows<NL, NC> R;
+  float cdist[NC > 0 ? NC : 1];
+#pragma unroll
+  for (int c = 0; c < NC; c++) {
+    const int pc = LTI(mp.icon(c));
+    {
+      const bool pyr = LTI(mp.icon(c) + 1) == 3;
+      R.mu1[c] = pyr ? LTF(mp.con(c) + 4 + 11) : 0.f; R.mu2[c] = pyr ? LTF(mp.con(c) + 4 + 12) : 0.f;
+    }
+    float bx[3] = {xpos[0][0], xpos[0][1], xpos[0][2]}, bq[4] = {xquat[0][0], xquat[0][1], xquat[0][2], xquat[0][3]};
+#pragma unroll
+    for (int p = 1; p < NP; p++) {
+      if (pc == p) {
+#pragma unroll
+        for (int i = 0; i < 3; i++) bx[i] = xpos[p][i];
+#pragma unroll
+        for (int i = 0; i < 4; i++) bq[i] = xquat[p][i];
+      }
+    }
+    const float gp[3] = {LTF(mp.con(c)), LTF(mp.con(c) + 1), LTF(mp.con(c) + 2)};
+    const float rad = LTF(mp.con(c) + 3);
+    const float n[3] = {LTF(mp.con(c) + 18), LTF(mp.con(c) + 19), LTF(mp.con(c) + 20)};
+    const float pp[3] = {LTF(mp.con(c) + 21), LTF(mp.con(c) + 22), LTF(mp.con(c) + 23)};
+    float r[3];
+    q_rot(gp, bq, r);
+    const float sp[3] = {bx[0] + r[0], bx[1] + r[1], bx[2] + r[2]};
+    const float dd[3] = {sp[0] - pp[0], sp[1] - pp[1], sp[2] - pp[2]};
+    const float dist = v_dot(dd, n) - rad;
+    cdist[c] = dist;
+    const float kk = rad + 0.5f * dist;
+    const float off[3] = {sp[0] - n[0] * kk - com[0], sp[1] - n[1] * kk - com[1], sp[2] - n[2] * kk - com[2]};
+    const int ld = (pc < 0) ? -1 : 5 + pc;
+#pragma unroll
+    for (int d = 0; d < N; d++) {
+      float cr[3];
+      v_cross(cdof[d], off, cr);
+      const float jp[3] = {cdof[d][3] + cr[0], cdof[d][4] + cr[1], cdof[d][5] + cr[2]};
+      const bool on = d <= ld;
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const float fr[3] = {LTF(mp.con(c) + 24 + 3 * k), LTF(mp.con(c) + 25 + 3 * k), LTF(mp.con(c) + 26 + 3 * k)};
+        R.B[c][k][d] = on ? v_dot(fr, jp) : 0.f;
+      }
+    }
+  }
+  // ---------------------------------------------------------------- crb + M (smooth.crb, support.make_m)
+  {
+    float crb[10], up[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) up[i] = 0.f;
+#pragma unroll
+    for (int p = NP - 1; p >= 0; p--) {
+      if (S.m(p)) {
+#pragma unroll
+        for (int i = 0; i < 10; i++) up[i] = gs(up[i], S.l(p), S.m(p));
+      }
+#pragma unroll
+      for (int i = 0; i < 10; i++) crb[i] = cinert[p][i] + up[i];
+      // rows of M for the dofs of this position
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        if (PD(i) == p) {
+          float buf[6];
+          inert_mul(crb, cdof[i], buf);
+#pragma unroll
+          for (int j = 0; j < N; j++) {
+            if (j <= i) {
+              float t = cdof[j][0] * buf[0] + cdof[j][1] * buf[1] + cdof[j][2] * buf[2] + cdof[j][3] * buf[3] + cdof[j][4] * buf[4] + cdof[j][5] * buf[5];
+              if (i == j) t += (i < 6) ? LTF(mp.trunk() + 6 + i) : LTF(mp.jnt(PD(i)) + 10);
+              M[TR(i, j)] = t;
+            }
+          }
+        }
+      }
+      const bool ownp = S.o(p);
+#pragma unroll
+      for (int i = 0; i < 10; i++) up[i] = ownp ? crb[i] : 0.f;
+    }
+  }
+  // ---------------------------------------------------------------- factor M
+  float F[NTRI], invD[N];
+#pragma unroll
+  for (int i = 0; i < N; i++)
+#pragma unroll
+    for (int j = 0; j < N; j++)
+      if (j <= i) F[TR(i, j)] = S.o(PD(i)) ? M[TR(i, j)] : 0.f;
+  ldl_factor<N>(F, invD, S);
+  // ---------------------------------------------------------------- velocity pass: com_vel + rne + passive + actuation
+  {
+    float cvel[NP][6], cfrc[NP][6], cdd[N][6];
+    float cv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const bool grav = !(C.disableflags & ABR_DSBL_GRAVITY);
+    float ca[6] = {0.f, 0.f, 0.f, grav ? -C.grav[0] : 0.f, grav ? -C.grav[1] : 0.f, grav ? -C.grav[2] : 0.f};
+    // trunk (free joint): translations first, then rotations against the translated cvel
+#pragma unroll
+    for (int q = 0; q < 3; q++)
+#pragma unroll
+      for (int i = 0; i < 6; i++) { cv[i] = fmaf(cdof[q][i], s.v[q], cv[i]); cdd[q][i] = 0.f; }
+#pragma unroll
+    for (int q = 3; q < 6; q++) motion_cross(cv, cdof[q], cdd[q]);
+#pragma unroll
+    for (int q = 3; q < 6; q++)
+#pragma unroll
+      for (int i = 0; i < 6; i++) cv[i] = fmaf(cdof[q][i], s.v[q], cv[i]);
+#pragma unroll
+    for (int q = 3; q < 6; q++)
+#pragma unroll
+      for (int i = 0; i < 6; i++) ca[i] = fmaf(cdd[q][i], s.v[q], ca[i]);
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+      if (p > 0) {
+        const int d = 5 + p;
+        motion_cross(cv, cdof[d], cdd[d]);
+        const float qd = s.v[d];
+#pragma unroll
+        for (int i = 0; i < 6; i++) { cv[i] = fmaf(cdof[d][i], qd, cv[i]); ca[i] = fmaf(cdd[d][i], qd, ca[i]); }
+      }
+#pragma unroll
+      for (int i = 0; i < 6; i++) cvel[p][i] = cv[i];
+      float f1[6], f2[6], f3[6];
+      inert_mul(cinert[p], ca, f1);
+      inert_mul(cinert[p], cv, f2);
+      motion_cross_force(cv, f2, f3);
+#pragma unroll
+      for (int i = 0; i < 6; i++) cfrc[p][i] = f1[i] + f3[i];
+    }
+    (void)cvel;
+    float up[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const bool passive_on = !(C.disableflags & ABR_DSBL_PASSIVE);
+    const bool act_on = !(C.disableflags & ABR_DSBL_ACTUATION);
+#pragma unroll
+    for (int p = NP - 1; p >= 0; p--) {
+      if (S.m(p)) {
+#pragma unroll
+        for (int i = 0; i < 6; i++) up[i] = gs(up[i], S.l(p), S.m(p));
+      }
+      float f[6];
+#pragma unroll
+      for (int i = 0; i < 6; i++) f[i] = cfrc[p][i] + up[i];
+#pragma unroll
+      for (int d = 0; d < N; d++) {
+        if (PD(d) != p) continue;
+        const float bias = cdof[d][0] * f[0] + cdof[d][1] * f[1] + cdof[d][2] * f[2] + cdof[d][3] * f[3] + cdof[d][4] * f[4] + cdof[d][5] * f[5];
+        float t = 0.f;
+        if (p == 0) {
+          if (passive_on) t = -LTF(mp.trunk() + d) * s.v[d];
+        } else {
+          const int fl = jflags[p];
+          const float q = s.qc[p - 1];
+          if (passive_on) t = -LTF(mp.jnt(p) + 8) * (q - LTF(mp.jnt(p) + 7)) - LTF(mp.jnt(p) + 9) * s.v[d];
+          // actuator (transmission + fwd_actuation); prm: ctrlrange2 forcerange2 gainprm3 biasprm3 gear
+          const float* prm = &LTF(mp.jnt(p) + 24);
+          const int af = fl >> kJActShift;
+          float ct = s.ctrl[p - 1];
+          if ((af & 1) && !(C.disableflags & ABR_DSBL_CLAMPCTRL)) ct = fminf(fmaxf(ct, prm[0]), prm[1 * kStride]);
+          const float gear = prm[10 * kStride];
+          const float len = q * gear, vel = s.v[d] * gear;
+          float gain = prm[4 * kStride];
+          if (af & 4) gain += prm[5 * kStride] * len + prm[6 * kStride] * vel;
+          float bs = 0.f;
+          if (af & 8) bs = prm[7 * kStride] + prm[8 * kStride] * len + prm[9 * kStride] * vel;
+          float af_ = gain * ct + bs;
+          if (af & 2) af_ = fminf(fmaxf(af_, prm[2 * kStride]), prm[3 * kStride]);
+          af_ *= gear;
+          t += ((fl & kJAct) && act_on) ? af_ : 0.f;
+        }
+        fs[d] = t - bias;
+      }
+      const bool ownp = S.o(p);
+#pragma unroll
+      for (int i = 0; i < 6; i++) up[i] = ownp ? f[i] : 0.f;
+    }
+  }
+  // ---------------------------------------------------------------- qacc_smooth
+  float as[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) as[i] = fs[i];
+  ldl_solve<N>(F, invD, as, S);
+  if (C.nefc == 0) {
+#pragma unroll
+    for (int i = 0; i < N; i++) { s.a[i] = as[i]; s.warm[i] = as[i]; fc[i] = 0.f; }
+    return;
+  }
+  // ---------------------------------------------------------------- constraint rows (make_constraint)
+#pragma unroll
+  for (int p = 1; p < NP; p++) {
+    const int d = 5 + p, r = p - 1;
+    const float q = s.qc[p - 1];
+    const float dmin = q - LTF(mp.jnt(p) + 11), dmax = LTF(mp.jnt(p) + 12) - q;
+    const float pos = fminf(dmin, dmax) - LTF(mp.jnt(p) + 13);
+    const bool active = (pos < 0.f) && (jflags[p] & kJLimited) && S.o(p);
+    const float sg = (dmin < dmax) ? 1.f : -1.f;
+    R.lsg[r] = active ? sg : 0.f;
+    row_kbi(&LTF(mp.jnt(p) + 14), pos, sg * s.v[d], LTF(mp.jnt(p) + 14 + 7), active, R.D[r], R.aref[r]);
+  }
+#pragma unroll
+  for (int c = 0; c < NC; c++) {
+    const float* prm = &LTF(mp.con(c) + 4);
+    const float pos = cdist[c] - prm[13 * kStride];
+    const bool act0 = (pos < 0.f) && (LTI(mp.icon(c)) >= 0);
+    const bool pyr = LTI(mp.icon(c) + 1) == 3;
+    float bv[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      float t = 0.f;
+#pragma unroll
+      for (int d = 0; d < N; d++) t = fmaf(R.B[c][k][d], s.v[d], t);
+      bv[k] = t;
+    }
+#pragma unroll
+    for (int sub = 0; sub < 4; sub++) {
+      const int r = NL + 4 * c + sub;
+      const float mu = (sub < 2) ? R.mu1[c] : R.mu2[c];
+      const float jvel = bv[0] + ((sub & 1) ? -mu : mu) * bv[1 + (sub >> 1)];
+      const float invw = (sub < 2 || !pyr) ? prm[7 * kStride] : prm[10 * kStride];
+      row_kbi(prm, pos, jvel, invw, act0 && (pyr || sub == 0), R.D[r], R.aref[r]);
+    }
+  }
+  // ---------------------------------------------------------------- solver.solve (Newton)
+  float Ma[N], Jaref[NR];
+  float gauss, cost;
+  mul_m<N>(M, as, Ma, S);
+  mul_j<NL, NC>(R, as, Jaref);
+#pragma unroll
+  for (int r = 0; r < NR; r++) Jaref[r] -= R.aref[r];
+  cost = solver_cost<NL, NC>(R, S, as, Ma, Jaref, fs, as, gauss);
+#pragma unroll
+  for (int d = 0; d < N; d++) s.a[d] = as[d];
+  if (!(C.disableflags & ABR_DSBL_WARMSTART)) {
+    float Mw[N], Jw[NR], g2;
+    mul_m<N>(M, s.warm, Mw, S);
+    mul_j<NL, NC>(R, s.warm, Jw);
+#pragma unroll
+    for (int r = 0; r < NR; r++) Jw[r] -= R.aref[r];
+    const float c2 = solver_cost<NL, NC>(R, S, s.warm, Mw, Jw, fs, as, g2);
+    const bool use = c2 < cost;
+    cost = use ? c2 : cost; gauss = use ? g2 : gauss;
+#pragma unroll
+    for (int d = 0; d < N; d++) { s.a[d] = use ? s.warm[d] : s.a[d]; Ma[d] = use ? Mw[d] : Ma[d]; }
+#pragma unroll
+    for (int r = 0; r < NR; r++) Jaref[r] = use ? Jw[r] : Jaref[r];
+  }
+  float prev_cost = INFINITY;
+  const float scale = 1.f / (C.meaninertia * (float)max(1, C.nv));
+  bool live = true;
+  for (int niter = 0;; niter++) {
+    // efc_force and qfrc_constraint at the current point
+    {
+      float up[N];
+#pragma unroll
+      for (int d = 0; d < N; d++) up[d] = 0.f;
+#pragma unroll
+      for (int r = 0; r < NL; r++) { const float f = (Jaref[r] < 0.f) ? -R.D[r] * Jaref[r] : 0.f; up[6 + r] = R.lsg[r] * f; }
+#pragma unroll
+      for (int c = 0; c < NC; c++) {
+        float f[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const int r = NL + 4 * c + k; f[k] = (Jaref[r] < 0.f) ? -R.D[r] * Jaref[r] : 0.f; }
+        const float mu1 = R.mu1[c], mu2 = R.mu2[c];
+        const float F0 = f[0] + f[1] + f[2] + f[3], F1 = mu1 * (f[0] - f[1]), F2 = mu2 * (f[2] - f[3]);
+#pragma unroll
+        for (int d = 0; d < N; d++) up[d] += R.B[c][0][d] * F0 + R.B[c][1][d] * F1 + R.B[c][2][d] * F2;
+      }
+#pragma unroll
+      for (int d = 0; d < N; d++) {
+        const int p = PD(d);
+        fc[d] = S.m(p) ? gs(up[d], S.l(p), S.m(p)) : up[d];
+      }
+    }
+    if (niter >= C.iterations) break;
+    float grad[N];
+#pragma unroll
+    for (int d = 0; d < N; d++) grad[d] = Ma[d] - fs[d] - fc[d];
+    // Hessian H = M + J' diag(D active) J in share form, then L'DL
+    float H[NTRI], hD[N];
+#pragma unroll
+    for (int i = 0; i < N; i++)
+#pragma unroll
+      for (int j = 0; j < N; j++)
+        if (j <= i) H[TR(i, j)] = S.o(PD(i)) ? M[TR(i, j)] : 0.f;
+#pragma unroll
+    for (int r = 0; r < NL; r++) H[TR(6 + r, 6 + r)] += (Jaref[r] < 0.f) ? R.D[r] * R.lsg[r] * R.lsg[r] : 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+      const int r0 = NL + 4 * c;
+      const float mu1 = R.mu1[c], mu2 = R.mu2[c];
+      const float w0 = (Jaref[r0] < 0.f) ? R.D[r0] : 0.f, w1 = (Jaref[r0 + 1] < 0.f) ? R.D[r0 + 1] : 0.f;
+      const float w2 = (Jaref[r0 + 2] < 0.f) ? R.D[r0 + 2] : 0.f, w3 = (Jaref[r0 + 3] < 0.f) ? R.D[r0 + 3] : 0.f;
+      const float W00 = w0 + w1 + w2 + w3, W01 = mu1 * (w0 - w1), W02 = mu2 * (w2 - w3);
+      const float W11 = mu1 * mu1 * (w0 + w1), W22 = mu2 * mu2 * (w2 + w3);
+#pragma unroll
+      for (int j = 0; j < N; j++) {
+        const float b0 = R.B[c][0][j], b1 = R.B[c][1][j], b2 = R.B[c][2][j];
+        const float o0 = W00 * b0 + W01 * b1 + W02 * b2, o1 = W01 * b0 + W11 * b1, o2 = W02 * b0 + W22 * b2;
+#pragma unroll
+        for (int i = 0; i < N; i++)
+          if (i >= j) H[TR(i, j)] += R.B[c][0][i] * o0 + R.B[c][1][i] * o1 + R.B[c][2][i] * o2;
+      }
+    }
+    ldl_factor<N>(H, hD, S);
+    float mg[N];
+#pragma unroll
+    for (int d = 0; d < N; d++) mg[d] = grad[d];
+    ldl_solve<N>(H, hD, mg, S);
+    if (C.iterations != 1) {
+      float gn = 0.f;
+#pragma unroll
+      for (int d = 0; d < N; d++) gn += S.o(PD(d)) ? grad[d] * grad[d] : 0.f;
+      gn = gall(gn, S.lg);
+      bool done = scale * (prev_cost - cost) < C.tol;
+      done = done || (scale * sqrtf(gn) < C.tol);
+      live = live && !done;
+      if (!__any_sync(ABR_FULL, live)) break;
+    }
+    float search[N], mv[N], jv[NR];
+#pragma unroll
+    for (int d = 0; d < N; d++) search[d] = -mg[d];
+    // ---- exact line search (solver._linesearch)
+    mul_m<N>(M, search, mv, S);
+    mul_j<NL, NC>(R, search, jv);
+    float sn = 0.f, sMa = 0.f, sq = 0.f, smv = 0.f;
+#pragma unroll
+    for (int d = 0; d < N; d++) {
+      if (S.o(PD(d))) { const float t = search[d]; sn += t * t; sMa += t * Ma[d]; sq += t * fs[d]; smv += t * mv[d]; }
+    }
+    sn = gall(sn, S.lg); sMa = gall(sMa, S.lg); sq = gall(sq, S.lg); smv = gall(smv, S.lg);
+    const float smag = sqrtf(sn) * C.meaninertia * (float)max(1, C.nv);
+    const float gtol = C.tol * C.ls_tol * smag;
+    const float qg0 = gauss, qg1 = sMa - sq, qg2 = 0.5f * smv;
+#define LS_EVAL(al) ls_eval<NL, NC>(R, Jaref, jv, (al), qg0, qg1, qg2, S.lg)
+    const LSP p0 = LS_EVAL(0.f);
+    const LSP l0 = LS_EVAL(-safe_div(p0.d0, p0.d1));
+    const bool lesser = l0.d0 < p0.d0;
+    LSP hi = lesser ? p0 : l0;
+    LSP lo = lesser ? l0 : p0;
+    bool swap = true;
+    int it = 0;
+    while (true) {
+      bool done = it >= C.ls_iterations;
+      done = done || !swap;
+      done = done || ((lo.d0 < 0.f) && (lo.d0 > -gtol));
+      done = done || ((hi.d0 > 0.f) && (hi.d0 < gtol));
+      if (!__any_sync(ABR_FULL, !done)) break;
+      const LSP lo_next = LS_EVAL(lo.alpha - safe_div(lo.d0, lo.d1));
+      const LSP hi_next = LS_EVAL(hi.alpha - safe_div(hi.d0, hi.d1));
+      const LSP mid = LS_EVAL(0.5f * (lo.alpha + hi.alpha));
+      if (!done) {
+        const bool swap_lo_next = (lo.d0 > 0.f) || (lo.d0 < lo_next.d0);
+        if (swap_lo_next) lo = lo_next;
+        const bool swap_lo_mid = (mid.d0 < 0.f) && (lo.d0 < mid.d0);
+        if (swap_lo_mid) lo = mid;
+        const bool swap_hi_next = (hi.d0 < 0.f) || (hi.d0 > hi_next.d0);
+        if (swap_hi_next) hi = hi_next;
+        const bool swap_hi_mid = (mid.d0 > 0.f) && (hi.d0 > mid.d0);
+        if (swap_hi_mid) hi = mid;
+        swap = swap_lo_next || swap_lo_mid || swap_hi_next || swap_hi_mid;
+        it++;
+      }
+    }
+    const bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
+    const float alpha = (improved && live) ? ((lo.cost < hi.cost) ? lo.alpha : hi.alpha) : 0.f;
+#pragma unroll
+    for (int d = 0; d < N; d++) { s.a[d] = fmaf(search[d], alpha, s.a[d]); Ma[d] = fmaf(mv[d], alpha, Ma[d]); }
+#pragma unroll
+    for (int r = 0; r < NR; r++) Jaref[r] = fmaf(jv[r], alpha, Jaref[r]);
+    if (C.iterations != 1) {
+      float g2;
+      const float c2 = solver_cost<NL, NC>(R, S, s.a, Ma, Jaref, fs, as, g2);
+      if (live) { prev_cost = cost; cost = c2; gauss = g2; }
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < N; d++) s.warm[d] = s.a[d];
+}
+
+// forward.euler (+ implicit joint damping unless EULERDAMP is disabled) and position integration
+template <int NL, int NC>
+__device__ __forceinline__ void euler(Lane<NL, NC>& s, const LaneCfg& C, float (&M)[(6 + NL) * (7 + NL) / 2], const float (&fs)[6 + NL], const float (&fc)[6 + NL]) {
+  constexpr int N = 6 + NL;
+  constexpr Map mp{NL, NC};
+  const float dt = C.dt;
+  if (!(C.disableflags & ABR_DSBL_EULERDAMP)) {
+    float hD[N], rhs[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      const float damp = (i < 6) ? LTF(mp.trunk() + i) : LTF(mp.jnt(PD(i)) + 9);
+      M[TR(i, i)] += damp * dt;
+      rhs[i] = fs[i] + fc[i];
+    }
+#pragma unroll
+    for (int i = 0; i < N; i++)
+#pragma unroll
+      for (int j = 0; j < N; j++)
+        if (j <= i) M[TR(i, j)] = C.S.o(PD(i)) ? M[TR(i, j)] : 0.f;
+    ldl_factor<N>(M, hD, C.S);
+    ldl_solve<N>(M, hD, rhs, C.S);
+#pragma unroll
+    for (int i = 0; i < N; i++) s.a[i] = rhs[i];
+  }
+#pragma unroll
+  for (int d = 0; d < N; d++) s.v[d] = fmaf(s.a[d], dt, s.v[d]);
+  // free joint
+  s.qt[0] = fmaf(dt, s.v[0], s.qt[0]); s.qt[1] = fmaf(dt, s.v[1], s.qt[1]); s.qt[2] = fmaf(dt, s.v[2], s.qt[2]);
+  float w[3] = {s.v[3], s.v[4], s.v[5]};
+  const float nrm = v_normalize(w, 3);
+  float ql[4], qn[4];
+  axis_angle_quat(w, dt * nrm, ql);
+  q_mul(s.qt + 3, ql, qn);
+  v_normalize(qn, 4);
+  s.qt[3] = qn[0]; s.qt[4] = qn[1]; s.qt[5] = qn[2]; s.qt[6] = qn[3];
+#pragma unroll
+  for (int p = 1; p <= NL; p++) s.qc[p - 1] = fmaf(dt, s.v[5 + p], s.qc[p - 1]);
+}
+
+#undef LS_EVAL
+
+// ------------------------------------------------------------------------------ kernels
+constexpr int kTPB = 32;  // one warp per CTA: 32/G worlds; small CTAs spread a 4096-world batch over every SM sub-partition
+
+template <int NL, int NC> __device__ __forceinline__ LaneCfg make_cfg(const Layout& L, const float* T, int g) {
+  constexpr Map mp{NL, NC};
+  LaneCfg C;
+  C.T = T + g;
+  C.S.own = LTI(mp.ish()); C.S.lvl = LTI(mp.ish() + 1); C.S.mx = L.l_mx; C.S.lg = L.lg2G;
+  C.dt = L.timestep; C.grav[0] = L.gravity[0]; C.grav[1] = L.gravity[1]; C.grav[2] = L.gravity[2];
+  C.mass = L.l_mass; C.tol = L.tolerance; C.ls_tol = L.ls_tolerance; C.meaninertia = L.meaninertia;
+  C.iterations = L.iterations; C.ls_iterations = L.ls_iterations; C.disableflags = L.disableflags; C.nefc = L.nefc; C.nv = L.nv;
+  return C;
+}
+
+// this lane's share of sum_i w_i (x_i - xg_i)^2 over the state entries it owns (cost.py:62-85, diagonal Q)
+template <int NL, int NC> __device__ __forceinline__ float quad_x_diag(const Lane<NL, NC>& s, const LaneCfg& C, const float* w, const float* xg, int nq) {
+  constexpr Map mp{NL, NC};
+  float acc = 0.f;
+  if (C.S.o(0)) {
+#pragma unroll
+    for (int i = 0; i < 7; i++) { const float e = s.qt[i] - xg[i]; acc = fmaf(w[i] * e, e, acc); }
+#pragma unroll
+    for (int i = 0; i < 6; i++) { const float e = s.v[i] - xg[nq + i]; acc = fmaf(w[nq + i] * e, e, acc); }
+  }
+#pragma unroll
+  for (int p = 1; p <= NL; p++) {
+    const int gd = LTI(mp.ijnt(p) + 1), gq = LTI(mp.ijnt(p) + 2);
+    if (gd >= 0 && C.S.o(p)) {
+      const float e = s.qc[p - 1] - xg[gq]; acc = fmaf(w[gq] * e, e, acc);
+      const float e2 = s.v[5 + p] - xg[nq + gd]; acc = fmaf(w[nq + gd] * e2, e2, acc);
+    }
+  }
+  return acc;
+}
+template <int NL, int NC> __device__ __forceinline__ void store_x(const Lane<NL, NC>& s, const LaneCfg& C, float* x, int nq) {
+  constexpr Map mp{NL, NC};
+  if (C.S.o(0)) {
+#pragma unroll
+    for (int i = 0; i < 7; i++) x[i] = s.qt[i];
+#pragma unroll
+    for (int i = 0; i < 6; i++) x[nq + i] = s.v[i];
+  }
+#pragma unroll
+  for (int p = 1; p <= NL; p++) {
+    const int gd = LTI(mp.ijnt(p) + 1), gq = LTI(mp.ijnt(p) + 2);
+    if (gd >= 0 && C.S.o(p)) { x[gq] = s.qc[p - 1]; x[nq + gd] = s.v[5 + p]; }
+  }
+}
+
+// shoot (shooting.py:22-48) / the sampler's rollouts (shooting.py:140-153) on the limb path
+template <int NL, int NC>
+__global__ void __launch_bounds__(kTPB) k_limb_rollout(const __grid_constant__ Layout L, const __grid_constant__ RolloutArgs A) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr Map mp{NL, NC};
+  constexpr int N = 6 + NL, NTRI = N * (N + 1) / 2;
+  const int ntab = mp.total() * kStride;
+  const int nx = L.nx, nu = L.nu, nq = L.nq, Nh = A.N;
+  for (int i = threadIdx.x; i < ntab; i += blockDim.x) smem[i] = A.blob[L.f_ltab + i];
+  float* cqd = smem + ntab; float* cqf = cqd + nx; float* crd = cqf + nx; float* cxg = crd + nu;
+  if (A.cost.enabled) {
+    for (int i = threadIdx.x; i < nx; i += blockDim.x) { cqd[i] = A.cost.qd[i]; cqf[i] = A.cost.qfd[i]; cxg[i] = A.cost.xg[i]; }
+    for (int i = threadIdx.x; i < nu; i += blockDim.x) crd[i] = A.cost.rd[i];
+  }
+  __syncthreads();
+  const int lg = L.lg2G;
+  const int g = threadIdx.x & ((1 << lg) - 1);
+  const int wraw = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> lg);
+  const bool valid = wraw < A.nworld;
+  const int w = valid ? wraw : A.nworld - 1;
+  const LaneCfg C = make_cfg<NL, NC>(L, smem, g);
+  int prob = w, sample = 0;
+  if (A.mode == 1) {
+    if (A.sample_ids) { prob = w; sample = A.sample_ids[w]; }
+    else { prob = w / A.S; sample = A.sample_offset + (w - prob * A.S); }
+  }
+  const float* x0 = A.x0 + (size_t)(A.mode == 1 ? prob : w) * A.x0_stride;
+  Lane<NL, NC> s;
+#pragma unroll
+  for (int i = 0; i < 7; i++) s.qt[i] = x0[i];
+#pragma unroll
+  for (int i = 0; i < 6; i++) s.v[i] = x0[nq + i];
+#pragma unroll
+  for (int p = 1; p <= NL; p++) {
+    const int gd = LTI(mp.ijnt(p) + 1), gq = LTI(mp.ijnt(p) + 2);
+    s.qc[p - 1] = (gd >= 0) ? x0[gq] : 0.f;
+    s.v[5 + p] = (gd >= 0) ? x0[nq + gd] : 0.f;
+    s.ctrl[p - 1] = 0.f;
+  }
+#pragma unroll
+  for (int d = 0; d < N; d++) { s.warm[d] = 0.f; s.a[d] = 0.f; }
+  float* xs = A.xs_out ? A.xs_out + (size_t)w * (Nh + 1) * nx : nullptr;
+  if (xs && valid) store_x<NL, NC>(s, C, xs, nq);
+  float cacc = 0.f;
+  if (A.cost.enabled) cacc += quad_x_diag<NL, NC>(s, C, Nh > 0 ? cqd : cqf, cxg, nq);
+  // t = -1 is mjx.forward with ctrl = 0, which seeds qacc_warmstart (shooting.py:36)
+#pragma unroll 1
+  for (int t = -1; t < Nh; t++) {
+    if (t >= 0) {
+#pragma unroll
+      for (int p = 1; p <= NL; p++) {
+        const int ga = LTI(mp.ijnt(p) + 3);
+        float u = 0.f;
+        if (ga >= 0) {
+          if (A.mode == 0) {
+            u = A.us[(size_t)w * A.us_stride + (size_t)t * nu + ga];
+          } else {
+            float nz = 0.f;
+            if (sample > 0) {
+              if (A.noise) nz = A.noise[(((size_t)prob * (A.S_total - 1) + (sample - 1)) * Nh + t) * nu + ga];
+              else nz = philox_normal(A.seed, (uint32_t)sample, (uint32_t)prob, (uint32_t)(t * nu + ga));
+            }
+            const float vv = A.us[(size_t)prob * A.us_stride + (size_t)t * nu + ga] + nz * A.stdev;
+            u = fminf(fmaxf(vv, LTF(mp.jnt(p) + 24)), LTF(mp.jnt(p) + 25));  // clip to actuator_ctrlrange (shooting.py:146-148)
+          }
+          if (C.S.o(p)) {
+            if (A.us_out && valid) A.us_out[((size_t)w * Nh + t) * nu + ga] = u;
+            if (A.cost.enabled) cacc = fmaf(crd[ga] * u, u, cacc);
+          }
+        }
+        s.ctrl[p - 1] = u;
+      }
+    }
+    float M[NTRI], fs[N], fc[N];
+    forward<NL, NC>(s, C, M, fs, fc);
+    if (t >= 0) {
+      euler<NL, NC>(s, C, M, fs, fc);
+      if (xs && valid) store_x<NL, NC>(s, C, xs + (size_t)(t + 1) * nx, nq);
+      if (A.cost.enabled) cacc += quad_x_diag<NL, NC>(s, C, (t == Nh - 1) ? cqf : cqd, cxg, nq);
+    }
+  }
+  if (A.costs_out) {
+    cacc = gall(cacc, lg);
+    if (valid && g == 0) A.costs_out[w] = 0.5f * cacc;
+  }
+}
+
+// MjxEnv.pipeline_init / pipeline_step (rl/base.py:81-96) with the auto-reset blend, on the limb path
+template <int NL, int NC>
+__global__ void __launch_bounds__(kTPB) k_limb_env(const __grid_constant__ Layout L, const __grid_constant__ EnvArgs A) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr Map mp{NL, NC};
+  constexpr int N = 6 + NL, NTRI = N * (N + 1) / 2;
+  const int ntab = mp.total() * kStride;
+  const int nu = L.nu, nq = L.nq, nv = L.nv;
+  for (int i = threadIdx.x; i < ntab; i += blockDim.x) smem[i] = A.blob[L.f_ltab + i];
+  __syncthreads();
+  const int lg = L.lg2G;
+  const int g = threadIdx.x & ((1 << lg) - 1);
+  const int wraw = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> lg);
+  const bool valid = wraw < A.E;
+  const int w = valid ? wraw : A.E - 1;
+  const LaneCfg C = make_cfg<NL, NC>(L, smem, g);
+  const bool reset = A.reset_mask && A.reset_mask[w];
+  const float* sq = (reset ? A.first_qpos : A.qpos) + (size_t)w * nq;
+  const float* sv = (reset ? A.first_qvel : A.qvel) + (size_t)w * nv;
+  const float* sw = reset ? A.first_warm : A.warm;
+  if (sw) sw += (size_t)w * nv;
+  Lane<NL, NC> s;
+#pragma unroll
+  for (int i = 0; i < 7; i++) s.qt[i] = sq[i];
+#pragma unroll
+  for (int i = 0; i < 6; i++) { s.v[i] = sv[i]; s.warm[i] = sw ? sw[i] : 0.f; s.a[i] = 0.f; }
+#pragma unroll
+  for (int p = 1; p <= NL; p++) {
+    const int gd = LTI(mp.ijnt(p) + 1), gq = LTI(mp.ijnt(p) + 2), ga = LTI(mp.ijnt(p) + 3);
+    s.qc[p - 1] = (gd >= 0) ? sq[gq] : 0.f;
+    s.v[5 + p] = (gd >= 0) ? sv[gd] : 0.f;
+    s.warm[5 + p] = (gd >= 0 && sw) ? sw[gd] : 0.f;
+    s.ctrl[p - 1] = (ga >= 0 && A.ctrl) ? A.ctrl[(size_t)w * nu + ga] : 0.f;
+    s.a[5 + p] = 0.f;
+  }
+  const int nfw = A.forward_only ? 1 : A.nsubsteps;
+#pragma unroll 1
+  for (int it = 0; it < nfw; it++) {
+    float M[NTRI], fs[N], fc[N];
+    forward<NL, NC>(s, C, M, fs, fc);
+    if (!A.forward_only) euler<NL, NC>(s, C, M, fs, fc);
+  }
+  if (valid) {
+    float* oq = A.qpos + (size_t)w * nq; float* ov = A.qvel + (size_t)w * nv;
+    float* ow = A.warm ? A.warm + (size_t)w * nv : nullptr; float* oa = A.qacc ? A.qacc + (size_t)w * nv : nullptr;
+    if (C.S.o(0)) {
+#pragma unroll
+      for (int i = 0; i < 7; i++) oq[i] = s.qt[i];
+#pragma unroll
+      for (int i = 0; i < 6; i++) {
+        if (!A.forward_only) ov[i] = s.v[i];
+        if (ow) ow[i] = s.warm[i];
+        if (oa) oa[i] = s.a[i];
+      }
+      if (A.time) {
+        const float t0 = reset ? 0.f : A.time[w];
+        A.time[w] = A.forward_only ? t0 : t0 + L.timestep * (float)A.nsubsteps;
+      }
+    }
+#pragma unroll
+    for (int p = 1; p <= NL; p++) {
+      const int gd = LTI(mp.ijnt(p) + 1), gq = LTI(mp.ijnt(p) + 2);
+      if (gd >= 0 && C.S.o(p)) {
+        oq[gq] = s.qc[p - 1];
+        if (!A.forward_only) ov[gd] = s.v[5 + p];
+        if (ow) ow[gd] = s.warm[5 + p];
+        if (oa) oa[gd] = s.a[5 + p];
+      }
+    }
+  }
+}
+
+template <int NL, int NC, class Args, class K> int launch_limb(K kern, const Layout& L, const Args& a, int nworld, int extra_floats, cudaStream_t st) {
+  constexpr Map mp{NL, NC};
+  const size_t sm = sizeof(float) * ((size_t)mp.total() * kStride + extra_floats);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  if (e != cudaSuccess) return (int)e;
+  const long threads = (long)nworld << L.lg2G;
+  const int grid = (int)((threads + kTPB - 1) / kTPB);
+  kern<<<grid, kTPB, sm, st>>>(L, a);
+  return (int)cudaGetLastError();
+}
+
+#undef LTF
+#undef LTI
+
+}  // namespace limb
+
+#define ABR_DECLARE_LIMB_LAUNCHERS(NL, NC)                                                       \
+  int launch_limb_rollout_##NL##_##NC(const Layout&, const RolloutArgs&, cudaStream_t);          \
+  int launch_limb_env_##NL##_##NC(const Layout&, const EnvArgs&, cudaStream_t);
+#define ABR_DEFINE_LIMB_LAUNCHERS(NL, NC)                                                        \
+  int launch_limb_rollout_##NL##_##NC(const Layout& L, const RolloutArgs& a, cudaStream_t st) {  \
+    return limb::launch_limb<NL, NC>(limb::k_limb_rollout<NL, NC>, L, a, a.nworld, 3 * L.nx + L.nu, st); \
+  }                                                                                              \
+  int launch_limb_env_##NL##_##NC(const Layout& L, const EnvArgs& a, cudaStream_t st) {          \
+    return limb::launch_limb<NL, NC>(limb::k_limb_env<NL, NC>, L, a, a.E, 0, st);                \
+  }
+ABR_DECLARE_LIMB_LAUNCHERS(3, 1)
+ABR_DECLARE_LIMB_LAUNCHERS(6, 4)
+
+}  // namespace abr
+#endif

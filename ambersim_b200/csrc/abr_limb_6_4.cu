@@ -1,0 +1,5 @@
+// limb-path kernels for chains of up to 6 joints and 4 contacts per path (biped / exoskeleton class)
+#include "abr_limb.cuh"
+namespace abr {
+ABR_DEFINE_LIMB_LAUNCHERS(6, 4)
+}

@@ -22,6 +22,8 @@
 #ifndef ABR_LIMB_CUH_
 #define ABR_LIMB_CUH_
 
+#include <stdlib.h>
+
 #include "abr_kernels.cuh"
 
 namespace abr {
@@ -53,15 +55,18 @@ __host__ __device__ constexpr int FD(int p) { return p == 0 ? 0 : 5 + p; }  // f
 __host__ __device__ constexpr int LD(int p) { return 5 + p; }               // last dof of a position
 __host__ __device__ constexpr int TR(int i, int j) { return i * (i + 1) / 2 + j; }
 
-// per-lane sharing info
-struct Share {
+// per-lane sharing info. LGC >= 0 is the FLAT pattern resolved at compile time: only the trunk is
+// shared, by all 2^LGC lanes (quadrupeds, hexapods, hands ...), so every merge below the trunk and
+// every level test folds away; LGC = -1 reads the general (nested) pattern from the lane table.
+template <int LGC> struct ShareT {
   int own;   // bit p: this lane is the owner of its body at position p (always set on private bodies)
   int lvl;   // 2 bits per position: log2 of the lane-group size sharing the body
   int mx;    // 2 bits per position: max of lvl over the lanes (uniform)
-  int lg;    // log2(G)
-  __device__ __forceinline__ bool o(int p) const { return (own >> p) & 1; }
-  __device__ __forceinline__ int l(int p) const { return (lvl >> (2 * p)) & 3; }
-  __device__ __forceinline__ int m(int p) const { return (mx >> (2 * p)) & 3; }
+  int lg_;   // log2(G)
+  __device__ __forceinline__ bool o(int p) const { if (LGC >= 0) return p == 0 ? (own & 1) : true; return (own >> p) & 1; }
+  __device__ __forceinline__ int l(int p) const { if (LGC >= 0) return p == 0 ? LGC : 0; return (lvl >> (2 * p)) & 3; }
+  __device__ __forceinline__ int m(int p) const { if (LGC >= 0) return p == 0 ? LGC : 0; return (mx >> (2 * p)) & 3; }
+  __device__ __forceinline__ int lg() const { return LGC >= 0 ? LGC : lg_; }
 };
 
 // sum over the lane group of level `lv` (per lane, uniform within a group); mxl is uniform
@@ -76,7 +81,7 @@ __device__ __forceinline__ float gall(float x, int lg) { return gs(x, lg, lg); }
 // ------------------------------------------------------------------------------ dense local L'DL
 // A: packed lower triangle in "share" form on shared rows. Leaves-first elimination (MuJoCo's
 // L'DL order): after the call A holds D on the diagonal and D*L below it, replicated on shared rows.
-template <int N> __device__ __forceinline__ void ldl_factor(float (&A)[N * (N + 1) / 2], float (&invD)[N], const Share& S) {
+template <int N, class SH> __device__ __forceinline__ void ldl_factor(float (&A)[N * (N + 1) / 2], float (&invD)[N], const SH& S) {
 #pragma unroll
   for (int k = N - 1; k >= 0; k--) {
     const int p = PD(k);
@@ -104,7 +109,7 @@ template <int N> __device__ __forceinline__ void ldl_factor(float (&A)[N * (N + 
   }
 }
 // x <- (L'DL)^-1 x ; x comes in full (replicated on shared dofs) and leaves full
-template <int N> __device__ __forceinline__ void ldl_solve(const float (&A)[N * (N + 1) / 2], const float (&invD)[N], float (&x)[N], const Share& S) {
+template <int N, class SH> __device__ __forceinline__ void ldl_solve(const float (&A)[N * (N + 1) / 2], const float (&invD)[N], float (&x)[N], const SH& S) {
 #pragma unroll
   for (int i = 0; i < N; i++) x[i] = S.o(PD(i)) ? x[i] : 0.f;  // to share form
 #pragma unroll
@@ -137,7 +142,7 @@ template <int N> __device__ __forceinline__ void ldl_solve(const float (&A)[N * 
   }
 }
 // out = M x, M full (replicated on shared rows), x full
-template <int N> __device__ __forceinline__ void mul_m(const float (&M)[N * (N + 1) / 2], const float (&x)[N], float (&out)[N], const Share& S) {
+template <int N, class SH> __device__ __forceinline__ void mul_m(const float (&M)[N * (N + 1) / 2], const float (&x)[N], float (&out)[N], const SH& S) {
   float up[N];
 #pragma unroll
   for (int i = 0; i < N; i++) {
@@ -170,9 +175,9 @@ template <int NL, int NC> struct Lane {
   float a[N];      // qacc of the last forward
 };
 
-struct LaneCfg {
+template <int LGC> struct LaneCfg {
   const float* T;  // table + lane-in-group
-  Share S;
+  ShareT<LGC> S;
   float dt, grav[3], mass, tol, ls_tol, meaninertia;
   int iterations, ls_iterations, disableflags, nefc, nv;
 };
@@ -229,14 +234,14 @@ template <int NL, int NC> __device__ __forceinline__ void mul_j(const Rows<NL, N
   }
 }
 // cost = 0.5 sum_active D Jaref^2 + 0.5 (Ma - fs).(a - as); uniform over the world's lanes
-template <int NL, int NC> __device__ __forceinline__ float solver_cost(const Rows<NL, NC>& R, const Share& S, const float (&x)[6 + NL], const float (&Mx)[6 + NL],
+template <int NL, int NC, class SH> __device__ __forceinline__ float solver_cost(const Rows<NL, NC>& R, const SH& S, const float (&x)[6 + NL], const float (&Mx)[6 + NL],
                                                                        const float (&Jx)[NL + 4 * NC], const float (&fs)[6 + NL], const float (&as)[6 + NL], float& gauss) {
   float sc = 0.f, g = 0.f;
 #pragma unroll
   for (int r = 0; r < NL + 4 * NC; r++) sc += (Jx[r] < 0.f) ? R.D[r] * Jx[r] * Jx[r] : 0.f;
 #pragma unroll
   for (int d = 0; d < 6 + NL; d++) g += S.o(PD(d)) ? (Mx[d] - fs[d]) * (x[d] - as[d]) : 0.f;
-  sc = gall(sc, S.lg); g = gall(g, S.lg);
+  sc = gall(sc, S.lg()); g = gall(g, S.lg());
   gauss = 0.5f * g;
   return 0.5f * sc + 0.5f * g;
 }
@@ -262,11 +267,11 @@ template <int NL, int NC> __device__ __forceinline__ LSP ls_eval(const Rows<NL, 
 
 // mjx.forward for one lane: on exit s.a = qacc, s.warm = qacc; M, fs, fc are returned for the
 // implicit-damping Euler variant.
-template <int NL, int NC>
-__device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg& C, float (&M)[(6 + NL) * (7 + NL) / 2], float (&fs)[6 + NL], float (&fc)[6 + NL]) {
+template <int NL, int NC, int LGC>
+__device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, float (&M)[(6 + NL) * (7 + NL) / 2], float (&fs)[6 + NL], float (&fc)[6 + NL]) {
   constexpr int NP = NL + 1, N = 6 + NL, NTRI = N * (N + 1) / 2, NR = NL + 4 * NC;
   constexpr Map mp{NL, NC};
-  const Share& S = C.S;
+  const ShareT<LGC>& S = C.S;
   // ---------------------------------------------------------------- kinematics (smooth.kinematics)
   float xpos[NP][3], xquat[NP][4], xipos[NP][3], xanc[NP][3], xax[NP][3];
   {
@@ -330,7 +335,7 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg& C, float
       const float ms = S.o(p) ? LTF(mp.body(p) + 14) : 0.f;
       sx = fmaf(xipos[p][0], ms, sx); sy = fmaf(xipos[p][1], ms, sy); sz = fmaf(xipos[p][2], ms, sz);
     }
-    sx = gall(sx, S.lg); sy = gall(sy, S.lg); sz = gall(sz, S.lg);
+    sx = gall(sx, S.lg()); sy = gall(sy, S.lg()); sz = gall(sz, S.lg());
     com[0] = sx / C.mass; com[1] = sy / C.mass; com[2] = sz / C.mass;
   }
   float cinert[NP][10];
@@ -689,7 +694,7 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg& C, float
       float gn = 0.f;
 #pragma unroll
       for (int d = 0; d < N; d++) gn += S.o(PD(d)) ? grad[d] * grad[d] : 0.f;
-      gn = gall(gn, S.lg);
+      gn = gall(gn, S.lg());
       bool done = scale * (prev_cost - cost) < C.tol;
       done = done || (scale * sqrtf(gn) < C.tol);
       live = live && !done;
@@ -706,11 +711,11 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg& C, float
     for (int d = 0; d < N; d++) {
       if (S.o(PD(d))) { const float t = search[d]; sn += t * t; sMa += t * Ma[d]; sq += t * fs[d]; smv += t * mv[d]; }
     }
-    sn = gall(sn, S.lg); sMa = gall(sMa, S.lg); sq = gall(sq, S.lg); smv = gall(smv, S.lg);
+    sn = gall(sn, S.lg()); sMa = gall(sMa, S.lg()); sq = gall(sq, S.lg()); smv = gall(smv, S.lg());
     const float smag = sqrtf(sn) * C.meaninertia * (float)max(1, C.nv);
     const float gtol = C.tol * C.ls_tol * smag;
     const float qg0 = gauss, qg1 = sMa - sq, qg2 = 0.5f * smv;
-#define LS_EVAL(al) ls_eval<NL, NC>(R, Jaref, jv, (al), qg0, qg1, qg2, S.lg)
+#define LS_EVAL(al) ls_eval<NL, NC>(R, Jaref, jv, (al), qg0, qg1, qg2, S.lg())
     const LSP p0 = LS_EVAL(0.f);
     const LSP l0 = LS_EVAL(-safe_div(p0.d0, p0.d1));
     const bool lesser = l0.d0 < p0.d0;
@@ -757,8 +762,8 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg& C, float
 }
 
 // forward.euler (+ implicit joint damping unless EULERDAMP is disabled) and position integration
-template <int NL, int NC>
-__device__ __forceinline__ void euler(Lane<NL, NC>& s, const LaneCfg& C, float (&M)[(6 + NL) * (7 + NL) / 2], const float (&fs)[6 + NL], const float (&fc)[6 + NL]) {
+template <int NL, int NC, int LGC>
+__device__ __forceinline__ void euler(Lane<NL, NC>& s, const LaneCfg<LGC>& C, float (&M)[(6 + NL) * (7 + NL) / 2], const float (&fs)[6 + NL], const float (&fc)[6 + NL]) {
   constexpr int N = 6 + NL;
   constexpr Map mp{NL, NC};
   const float dt = C.dt;
@@ -798,13 +803,14 @@ __device__ __forceinline__ void euler(Lane<NL, NC>& s, const LaneCfg& C, float (
 #undef LS_EVAL
 
 // ------------------------------------------------------------------------------ kernels
-constexpr int kTPB = 32;  // one warp per CTA: 32/G worlds; small CTAs spread a 4096-world batch over every SM sub-partition
+constexpr int kTPB = 32;      // default: one warp per CTA (32/G worlds); small CTAs spread a 4096-world batch over every SM sub-partition
+constexpr int kMaxTPB = 256;  // larger CTAs run their warps in lockstep (one barrier per step) so they share instruction fetches
 
-template <int NL, int NC> __device__ __forceinline__ LaneCfg make_cfg(const Layout& L, const float* T, int g) {
+template <int NL, int NC, int LGC> __device__ __forceinline__ LaneCfg<LGC> make_cfg(const Layout& L, const float* T, int g) {
   constexpr Map mp{NL, NC};
-  LaneCfg C;
+  LaneCfg<LGC> C;
   C.T = T + g;
-  C.S.own = LTI(mp.ish()); C.S.lvl = LTI(mp.ish() + 1); C.S.mx = L.l_mx; C.S.lg = L.lg2G;
+  C.S.own = LTI(mp.ish()); C.S.lvl = LTI(mp.ish() + 1); C.S.mx = L.l_mx; C.S.lg_ = L.lg2G;
   C.dt = L.timestep; C.grav[0] = L.gravity[0]; C.grav[1] = L.gravity[1]; C.grav[2] = L.gravity[2];
   C.mass = L.l_mass; C.tol = L.tolerance; C.ls_tol = L.ls_tolerance; C.meaninertia = L.meaninertia;
   C.iterations = L.iterations; C.ls_iterations = L.ls_iterations; C.disableflags = L.disableflags; C.nefc = L.nefc; C.nv = L.nv;
@@ -812,7 +818,7 @@ template <int NL, int NC> __device__ __forceinline__ LaneCfg make_cfg(const Layo
 }
 
 // this lane's share of sum_i w_i (x_i - xg_i)^2 over the state entries it owns (cost.py:62-85, diagonal Q)
-template <int NL, int NC> __device__ __forceinline__ float quad_x_diag(const Lane<NL, NC>& s, const LaneCfg& C, const float* w, const float* xg, int nq) {
+template <int NL, int NC, int LGC> __device__ __forceinline__ float quad_x_diag(const Lane<NL, NC>& s, const LaneCfg<LGC>& C, const float* w, const float* xg, int nq) {
   constexpr Map mp{NL, NC};
   float acc = 0.f;
   if (C.S.o(0)) {
@@ -831,7 +837,7 @@ template <int NL, int NC> __device__ __forceinline__ float quad_x_diag(const Lan
   }
   return acc;
 }
-template <int NL, int NC> __device__ __forceinline__ void store_x(const Lane<NL, NC>& s, const LaneCfg& C, float* x, int nq) {
+template <int NL, int NC, int LGC> __device__ __forceinline__ void store_x(const Lane<NL, NC>& s, const LaneCfg<LGC>& C, float* x, int nq) {
   constexpr Map mp{NL, NC};
   if (C.S.o(0)) {
 #pragma unroll
@@ -847,8 +853,8 @@ template <int NL, int NC> __device__ __forceinline__ void store_x(const Lane<NL,
 }
 
 // shoot (shooting.py:22-48) / the sampler's rollouts (shooting.py:140-153) on the limb path
-template <int NL, int NC>
-__global__ void __launch_bounds__(kTPB) k_limb_rollout(const __grid_constant__ Layout L, const __grid_constant__ RolloutArgs A) {
+template <int NL, int NC, int LGC>
+__global__ void __launch_bounds__(kMaxTPB) k_limb_rollout(const __grid_constant__ Layout L, const __grid_constant__ RolloutArgs A) {
   extern __shared__ __align__(16) float smem[];
   constexpr Map mp{NL, NC};
   constexpr int N = 6 + NL, NTRI = N * (N + 1) / 2;
@@ -861,12 +867,12 @@ __global__ void __launch_bounds__(kTPB) k_limb_rollout(const __grid_constant__ L
     for (int i = threadIdx.x; i < nu; i += blockDim.x) crd[i] = A.cost.rd[i];
   }
   __syncthreads();
-  const int lg = L.lg2G;
+  const int lg = (LGC >= 0) ? LGC : L.lg2G;
   const int g = threadIdx.x & ((1 << lg) - 1);
   const int wraw = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> lg);
   const bool valid = wraw < A.nworld;
   const int w = valid ? wraw : A.nworld - 1;
-  const LaneCfg C = make_cfg<NL, NC>(L, smem, g);
+  const LaneCfg<LGC> C = make_cfg<NL, NC, LGC>(L, smem, g);
   int prob = w, sample = 0;
   if (A.mode == 1) {
     if (A.sample_ids) { prob = w; sample = A.sample_ids[w]; }
@@ -888,12 +894,13 @@ __global__ void __launch_bounds__(kTPB) k_limb_rollout(const __grid_constant__ L
 #pragma unroll
   for (int d = 0; d < N; d++) { s.warm[d] = 0.f; s.a[d] = 0.f; }
   float* xs = A.xs_out ? A.xs_out + (size_t)w * (Nh + 1) * nx : nullptr;
-  if (xs && valid) store_x<NL, NC>(s, C, xs, nq);
+  if (xs && valid) store_x<NL, NC, LGC>(s, C, xs, nq);
   float cacc = 0.f;
-  if (A.cost.enabled) cacc += quad_x_diag<NL, NC>(s, C, Nh > 0 ? cqd : cqf, cxg, nq);
+  if (A.cost.enabled) cacc += quad_x_diag<NL, NC, LGC>(s, C, Nh > 0 ? cqd : cqf, cxg, nq);
   // t = -1 is mjx.forward with ctrl = 0, which seeds qacc_warmstart (shooting.py:36)
 #pragma unroll 1
   for (int t = -1; t < Nh; t++) {
+    if (blockDim.x > 32) __syncthreads();
     if (t >= 0) {
 #pragma unroll
       for (int p = 1; p <= NL; p++) {
@@ -920,11 +927,11 @@ __global__ void __launch_bounds__(kTPB) k_limb_rollout(const __grid_constant__ L
       }
     }
     float M[NTRI], fs[N], fc[N];
-    forward<NL, NC>(s, C, M, fs, fc);
+    forward<NL, NC, LGC>(s, C, M, fs, fc);
     if (t >= 0) {
-      euler<NL, NC>(s, C, M, fs, fc);
-      if (xs && valid) store_x<NL, NC>(s, C, xs + (size_t)(t + 1) * nx, nq);
-      if (A.cost.enabled) cacc += quad_x_diag<NL, NC>(s, C, (t == Nh - 1) ? cqf : cqd, cxg, nq);
+      euler<NL, NC, LGC>(s, C, M, fs, fc);
+      if (xs && valid) store_x<NL, NC, LGC>(s, C, xs + (size_t)(t + 1) * nx, nq);
+      if (A.cost.enabled) cacc += quad_x_diag<NL, NC, LGC>(s, C, (t == Nh - 1) ? cqf : cqd, cxg, nq);
     }
   }
   if (A.costs_out) {
@@ -934,8 +941,8 @@ __global__ void __launch_bounds__(kTPB) k_limb_rollout(const __grid_constant__ L
 }
 
 // MjxEnv.pipeline_init / pipeline_step (rl/base.py:81-96) with the auto-reset blend, on the limb path
-template <int NL, int NC>
-__global__ void __launch_bounds__(kTPB) k_limb_env(const __grid_constant__ Layout L, const __grid_constant__ EnvArgs A) {
+template <int NL, int NC, int LGC>
+__global__ void __launch_bounds__(kMaxTPB) k_limb_env(const __grid_constant__ Layout L, const __grid_constant__ EnvArgs A) {
   extern __shared__ __align__(16) float smem[];
   constexpr Map mp{NL, NC};
   constexpr int N = 6 + NL, NTRI = N * (N + 1) / 2;
@@ -943,12 +950,12 @@ __global__ void __launch_bounds__(kTPB) k_limb_env(const __grid_constant__ Layou
   const int nu = L.nu, nq = L.nq, nv = L.nv;
   for (int i = threadIdx.x; i < ntab; i += blockDim.x) smem[i] = A.blob[L.f_ltab + i];
   __syncthreads();
-  const int lg = L.lg2G;
+  const int lg = (LGC >= 0) ? LGC : L.lg2G;
   const int g = threadIdx.x & ((1 << lg) - 1);
   const int wraw = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> lg);
   const bool valid = wraw < A.E;
   const int w = valid ? wraw : A.E - 1;
-  const LaneCfg C = make_cfg<NL, NC>(L, smem, g);
+  const LaneCfg<LGC> C = make_cfg<NL, NC, LGC>(L, smem, g);
   const bool reset = A.reset_mask && A.reset_mask[w];
   const float* sq = (reset ? A.first_qpos : A.qpos) + (size_t)w * nq;
   const float* sv = (reset ? A.first_qvel : A.qvel) + (size_t)w * nv;
@@ -972,8 +979,8 @@ __global__ void __launch_bounds__(kTPB) k_limb_env(const __grid_constant__ Layou
 #pragma unroll 1
   for (int it = 0; it < nfw; it++) {
     float M[NTRI], fs[N], fc[N];
-    forward<NL, NC>(s, C, M, fs, fc);
-    if (!A.forward_only) euler<NL, NC>(s, C, M, fs, fc);
+    forward<NL, NC, LGC>(s, C, M, fs, fc);
+    if (!A.forward_only) euler<NL, NC, LGC>(s, C, M, fs, fc);
   }
   if (valid) {
     float* oq = A.qpos + (size_t)w * nq; float* ov = A.qvel + (size_t)w * nv;
@@ -1011,8 +1018,10 @@ template <int NL, int NC, class Args, class K> int launch_limb(K kern, const Lay
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   if (e != cudaSuccess) return (int)e;
   const long threads = (long)nworld << L.lg2G;
-  const int grid = (int)((threads + kTPB - 1) / kTPB);
-  kern<<<grid, kTPB, sm, st>>>(L, a);
+  int tpb = kTPB;
+  if (const char* e = getenv("ABR_LIMB_TPB")) { const int v = atoi(e); if (v == 32 || v == 64 || v == 128 || v == 256) tpb = v; }
+  const int grid = (int)((threads + tpb - 1) / tpb);
+  kern<<<grid, tpb, sm, st>>>(L, a);
   return (int)cudaGetLastError();
 }
 
@@ -1021,18 +1030,20 @@ template <int NL, int NC, class Args, class K> int launch_limb(K kern, const Lay
 
 }  // namespace limb
 
-#define ABR_DECLARE_LIMB_LAUNCHERS(NL, NC)                                                       \
-  int launch_limb_rollout_##NL##_##NC(const Layout&, const RolloutArgs&, cudaStream_t);          \
-  int launch_limb_env_##NL##_##NC(const Layout&, const EnvArgs&, cudaStream_t);
-#define ABR_DEFINE_LIMB_LAUNCHERS(NL, NC)                                                        \
-  int launch_limb_rollout_##NL##_##NC(const Layout& L, const RolloutArgs& a, cudaStream_t st) {  \
-    return limb::launch_limb<NL, NC>(limb::k_limb_rollout<NL, NC>, L, a, a.nworld, 3 * L.nx + L.nu, st); \
-  }                                                                                              \
-  int launch_limb_env_##NL##_##NC(const Layout& L, const EnvArgs& a, cudaStream_t st) {          \
-    return limb::launch_limb<NL, NC>(limb::k_limb_env<NL, NC>, L, a, a.E, 0, st);                \
+// LGC: -1 = general sharing pattern (suffix g), 2 = flat 4-lane pattern (suffix f2)
+#define ABR_DECLARE_LIMB_LAUNCHERS(NL, NC, TAG)                                                        \
+  int launch_limb_rollout_##NL##_##NC##_##TAG(const Layout&, const RolloutArgs&, cudaStream_t);        \
+  int launch_limb_env_##NL##_##NC##_##TAG(const Layout&, const EnvArgs&, cudaStream_t);
+#define ABR_DEFINE_LIMB_LAUNCHERS(NL, NC, LGC, TAG)                                                    \
+  int launch_limb_rollout_##NL##_##NC##_##TAG(const Layout& L, const RolloutArgs& a, cudaStream_t st) { \
+    return limb::launch_limb<NL, NC>(limb::k_limb_rollout<NL, NC, LGC>, L, a, a.nworld, 3 * L.nx + L.nu, st); \
+  }                                                                                                    \
+  int launch_limb_env_##NL##_##NC##_##TAG(const Layout& L, const EnvArgs& a, cudaStream_t st) {        \
+    return limb::launch_limb<NL, NC>(limb::k_limb_env<NL, NC, LGC>, L, a, a.E, 0, st);                 \
   }
-ABR_DECLARE_LIMB_LAUNCHERS(3, 1)
-ABR_DECLARE_LIMB_LAUNCHERS(6, 4)
+ABR_DECLARE_LIMB_LAUNCHERS(3, 1, f2)
+ABR_DECLARE_LIMB_LAUNCHERS(3, 1, g)
+ABR_DECLARE_LIMB_LAUNCHERS(6, 4, g)
 
 }  // namespace abr
 #endif

@@ -125,7 +125,9 @@ class Model:
         return m
 
     def set_lanes(self, lanes: int) -> "Model":
-        """Pin the lanes-per-world group size (0 = auto); tuning knob, not part of mjx."""
+        """Pin the kernel family: 0 = auto (limb kernels when the model is eligible, else the generic kernels with
+        an automatic group size), 1 = limb kernels (error if ineligible), 4/8/16/32 = generic kernels with that
+        many lanes per world. Tuning knob, not part of mjx."""
         self._lanes = lanes
         for h in self._handles.values():
             _lib.check(_lib.lib().abr_model_set_lanes(h.ptr, lanes))

@@ -207,7 +207,10 @@ int abr_model_set_opt(AbrModel* m, const AbrOpt* opt);
 int abr_model_get_opt(const AbrModel* m, AbrOpt* opt);
 /* static sizes derived at create: ncon, ne, nl, nefc, tree depth, lanes per world chosen */
 int abr_model_info(const AbrModel* m, int* ncon, int* ne, int* nl, int* nefc, int* depth);
-/* override the lanes-per-world group size G in {0 (auto), 4, 8, 16, 32}  */
+/* kernel family: 0 = auto (limb kernels, one lane per root-to-leaf path, when the model is eligible:
+ * floating base, one hinge/slide joint per other body, plane-sphere contacts, Newton + Euler, no
+ * equalities; otherwise the generic kernels), 1 = limb kernels or ABR_EUNSUPPORTED,
+ * 4/8/16/32 = generic kernels with that many lanes per world */
 int abr_model_set_lanes(AbrModel* m, int lanes);
 
 int abr_cost_create(const AbrQuadCostHost* host, int device, AbrCost** out);

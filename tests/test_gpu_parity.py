@@ -28,6 +28,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 STAGES = ["xpos", "xquat", "xipos", "cinert", "cdof", "qM", "cvel", "cdof_dot", "contact_dist", "contact_pos", "contact_frame",
           "qfrc_smooth", "qacc_smooth", "efc_J", "efc_D", "efc_aref", "qacc", "efc_force", "qfrc_constraint"]
+MODEL_KEY = {"barkour": "home", "biped": "stand", "tripod": "home"}
 BH_OPT = dict(timestep=0.002, iterations=1, ls_iterations=4, integrator=0, solver=2, disableflags=16)  # the reference test's options
 
 
@@ -36,7 +37,7 @@ def t32(a):
 
 
 def sample_state(mj, name, rng):
-    key = {"barkour": "home", "biped": "stand"}.get(name)
+    key = {"barkour": "home", "biped": "stand", "tripod": "home"}.get(name)
     q = mj.key_qpos(key) if key else mj.qpos0.copy()
     if name == "bh280":
         q = q + rng.uniform(0.0, 0.5, mj.nq)
@@ -74,7 +75,7 @@ def test_forward_stage_parity(load_model, name):
             assert np.abs(r - g).max() <= 2e-4 * max(1e-6, np.abs(r).max()), f
 
 
-@pytest.mark.parametrize("name", ["pendulum", "bh280", "barkour", "biped"])
+@pytest.mark.parametrize("name", ["pendulum", "bh280", "barkour", "biped", "tripod"])
 @pytest.mark.parametrize("variant", ["default", "rk4", "cg", "eulerdamp", "converged", "nowarm"])
 def test_single_step_parity_option_variants(load_model, name, variant):
     opt = dict(default={}, rk4=dict(integrator=1), cg=dict(solver=1, iterations=8, ls_iterations=10),
@@ -120,8 +121,8 @@ def test_contact_free_rollout_parity(load_model, name, lanes):
     assert np.allclose(costs, quad_cost(ref, us, eye, 10 * eye, 0.01 * np.eye(mj.nu), 0.0), rtol=1e-3)
 
 
-@pytest.mark.parametrize("name", ["barkour", "biped"])
-@pytest.mark.parametrize("lanes", [4, 8, 16, 32])
+@pytest.mark.parametrize("name", ["barkour", "biped", "tripod"])
+@pytest.mark.parametrize("lanes", [1, 4, 8, 16, 32])  # 1 = the limb (path-decomposed) kernels, 4..32 = generic group sizes
 def test_contact_rollout_teacher_forced(load_model, name, lanes):
     mj, m, o = model_with(load_model, name)
     m.set_lanes(lanes)
@@ -380,3 +381,54 @@ def test_ffma_peak_is_plausible():
     tf, ms = C.c_double(), C.c_double()
     _lib.check(_lib.lib().abr_ffma_peak(0, C.byref(tf), C.byref(ms)))
     assert 20.0 < tf.value < 90.0  # nominal 74.4 TFLOP/s at 1965 MHz
+
+
+# ------------------------------------------------------------------ limb (path-decomposed) kernels
+@pytest.mark.parametrize("name", ["barkour", "biped", "tripod"])
+def test_limb_path_is_default_and_matches_generic(load_model, name, monkeypatch):
+    """Eligible models run on the limb kernels by default (lanes = 0 or 1); pinning a generic group size
+    gives the same trajectory and costs up to float32 rounding, and the general-sharing build of the limb
+    kernel (ABR_LIMB_GENERAL) agrees with the flat-pattern build."""
+    mj, m, o = model_with(load_model, name)
+    rng = np.random.default_rng(21)
+    W, N = 24, 12
+    key = MODEL_KEY[name]
+    x0 = np.tile(np.concatenate([mj.key_qpos(key), np.zeros(mj.nv)]), (W, 1))
+    x0[:, 7:mj.nq] += rng.uniform(-0.05, 0.05, (W, mj.nq - 7))
+    x0[:, mj.nq:] = 0.2 * rng.normal(size=(W, mj.nv))
+    lo, hi = mj.actuator_ctrlrange[:, 0], mj.actuator_ctrlrange[:, 1]
+    us = mj.key_ctrl(key) + 0.1 * rng.normal(size=(W, N, mj.nu))
+    us = np.where(mj.actuator_ctrllimited[None, None, :] > 0, np.clip(us, lo, hi), us)
+    nx = mj.nq + mj.nv
+    qd = rng.uniform(0.5, 2.0, nx)
+    cf = StaticGoalQuadraticCost(np.diag(qd), 10 * np.diag(qd), 0.01 * np.eye(mj.nu), x0[0])
+    out = {}
+    for lanes in (0, 1, 32):
+        mm = mjx.device_put(mj).replace(opt=m.opt)
+        mm.set_lanes(lanes)
+        out[lanes] = (shoot(mm, t32(x0), t32(us)).cpu().numpy(), shoot_cost(mm, t32(x0), t32(us), cf).cpu().numpy())
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])  # default == pinned limb
+    assert not np.array_equal(out[1][0], out[32][0])  # a different kernel really ran
+    assert np.abs(out[1][0] - out[32][0]).max() < 2e-3
+    assert np.allclose(out[1][1], out[32][1], rtol=2e-3)
+    ref = o.rollout(x0, us)
+    assert np.abs(out[1][0] - ref).max() < 5e-3
+    assert np.allclose(out[1][1], quad_cost(ref, us, np.diag(qd), 10 * np.diag(qd), 0.01 * np.eye(mj.nu), x0[0]), rtol=1e-2)
+    monkeypatch.setenv("ABR_LIMB_GENERAL", "1")
+    mm = mjx.device_put(mj).replace(opt=m.opt)
+    mm.set_lanes(1)
+    xs_g = shoot(mm, t32(x0), t32(us)).cpu().numpy()
+    assert np.abs(xs_g - out[1][0]).max() < 2e-3
+
+
+def test_limb_path_eligibility(load_model):
+    """Fixed-base models, equality constraints, CG and RK4 stay on the generic kernels: pinning the limb
+    path there is an error, not a silent fallback."""
+    for name, opt in (("pendulum", {}), ("bh280", {}), ("barkour", dict(solver=1)), ("barkour", dict(integrator=1))):
+        mj, m, _ = model_with(load_model, name, **opt)
+        with pytest.raises(Exception):
+            m.set_lanes(1)
+            shoot(m, t32(np.zeros(mj.nq + mj.nv)), t32(np.zeros((2, mj.nu))))
+    mj, m, _ = model_with(load_model, "barkour")
+    m.set_lanes(1)
+    assert shoot(m, t32(np.concatenate([mj.key_qpos("home"), np.zeros(mj.nv)])), t32(np.zeros((2, mj.nu)))).shape == (3, mj.nq + mj.nv)

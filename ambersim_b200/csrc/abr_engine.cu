@@ -79,7 +79,7 @@ struct AbrModel {
   int num_sms = 148;
   int max_smem = 0;
   cudaStream_t stream = nullptr;  // for the *_host entry points
-  Scratch s_costs, s_in, s_out, s_dbg;
+  Scratch s_costs, s_in, s_out, s_dbg, s_traj;
 };
 
 struct AbrCost {
@@ -656,6 +656,15 @@ __global__ void k_argmin(const float* costs, int S, int sample_offset, int* best
   if (threadIdx.x == 0) { best_idx[b] = sample_offset + si[0]; best_cost[b] = sc[0]; }
 }
 
+// copy each problem's winning trajectory / control sequence out of the per-sample scratch (shooting.py:155-156)
+__global__ void k_gather_winner(const float* xs_all, const float* us_all, const int* best_idx, int sample_offset, int S, int nxs, int nus,
+                                float* xs_star, float* us_star) {
+  const int b = blockIdx.x;
+  const size_t w = (size_t)b * S + (best_idx[b] - sample_offset);
+  if (xs_star) for (int i = threadIdx.x; i < nxs; i += blockDim.x) xs_star[(size_t)b * nxs + i] = xs_all[w * nxs + i];
+  if (us_star) for (int i = threadIdx.x; i < nus; i += blockDim.x) us_star[(size_t)b * nus + i] = us_all[w * nus + i];
+}
+
 // FP32 FMA-pipe peak: 8 independent FFMA chains per thread
 __global__ void __launch_bounds__(1024) k_ffma(float* out, int iters, float a, float b) {
   float x0 = threadIdx.x, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
@@ -792,7 +801,7 @@ int abr_model_destroy(AbrModel* m) {
   if (!m) return ABR_OK;
   cudaSetDevice(m->device);
   if (m->d_blob) cudaFree(m->d_blob);
-  m->s_costs.release(); m->s_in.release(); m->s_out.release(); m->s_dbg.release();
+  m->s_costs.release(); m->s_in.release(); m->s_out.release(); m->s_dbg.release(); m->s_traj.release();
   if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
   return ABR_OK;
@@ -934,13 +943,29 @@ int abr_predictive_sample_dev(AbrModel* m, const AbrCost* cost, const float* x0,
   a.blob = m->d_blob; a.x0 = x0; a.x0_stride = m->lay.nx; a.us = us_guess; a.us_stride = N * m->lay.nu;
   a.noise = noise; a.seed = seed; a.stdev = stdev; a.mode = 1; a.S = S; a.S_total = S_total; a.sample_offset = sample_offset;
   a.nworld = B * S; a.N = N; a.costs_out = d_costs; a.cost = cost_view(cost);
+  // Winner trajectories: when every sample's states fit a modest scratch they are kept (a few MB at the
+  // 4096 x 32 solve) and the winner is gathered, so the solve is ONE rollout launch deep; larger sweeps
+  // re-roll the B winners instead and never materialise the S x (N+1) x nx tensor (shooting.py:152).
+  const size_t nxs = (size_t)(N + 1) * m->lay.nx, nus = (size_t)N * m->lay.nu;
+  const size_t traj_bytes = sizeof(float) * (size_t)B * S * (nxs + nus);
+  size_t keep_cap = (size_t)256 << 20;
+  if (const char* e = getenv("ABR_KEEP_TRAJ_MB")) keep_cap = (size_t)atol(e) << 20;
+  const bool keep = (xs_star || us_star) && traj_bytes <= keep_cap;
+  float* xs_all = nullptr; float* us_all = nullptr;
+  if (keep) {
+    int rc = m->s_traj.ensure(traj_bytes + 16);
+    if (rc) return rc;
+    xs_all = (float*)m->s_traj.p; us_all = xs_all + (size_t)B * S * nxs;
+    a.xs_out = xs_all; a.us_out = us_all;
+  }
   int rc = launch_rollout(m, m->lay, a, st);
   if (rc) return rc;
   k_argmin<<<B, 256, 0, st>>>(d_costs, S, sample_offset, best_idx, best_cost);
   CK(cudaGetLastError());
-  if (xs_star || us_star) {
-    // re-roll the winners (B worlds) to emit their trajectories; the S x (N+1) x nx tensor of all
-    // samples (shooting.py:152) is never materialised
+  if (keep) {
+    k_gather_winner<<<B, 128, 0, st>>>(xs_all, us_all, best_idx, sample_offset, S, (int)nxs, (int)nus, xs_star, us_star);
+    CK(cudaGetLastError());
+  } else if (xs_star || us_star) {
     RolloutArgs w = a;
     w.sample_ids = best_idx; w.nworld = B; w.costs_out = nullptr; w.cost.enabled = 0;
     w.xs_out = xs_star; w.us_out = us_star;

@@ -280,7 +280,7 @@ def main():
             b.record(stream)
             torch.cuda.synchronize(device)
             out["extra"] = {"vps_4096x32_solve_ms": a.elapsed_time(b) / reps,
-                            "vps_note": "VanillaPredictiveSampler.optimize, device-resident inputs, includes argmin + winner re-roll"}
+                            "vps_note": "VanillaPredictiveSampler.optimize, device-resident inputs: rollouts + argmin + winner gather (3 launches)"}
             rate, sample = cpu_arm(mj, args.cpu_seconds, ncores)
             out["cpu_baseline"] = {"value": rate, "unit": "world-steps/s", "cores": ncores, "kind": "port", "sample": sample,
                                    "note": "oracle port (float32); the reference's own CPU path (MJX on JAX-CPU, MuJoCo C) is not "

@@ -432,3 +432,22 @@ def test_limb_path_eligibility(load_model):
     mj, m, _ = model_with(load_model, "barkour")
     m.set_lanes(1)
     assert shoot(m, t32(np.concatenate([mj.key_qpos("home"), np.zeros(mj.nv)])), t32(np.zeros((2, mj.nu)))).shape == (3, mj.nq + mj.nv)
+
+
+@pytest.mark.parametrize("name", ["barkour", "bh280"])
+def test_vps_kept_trajectories_equal_rerolled_winner(load_model, name, monkeypatch):
+    """The sampler either keeps every sample's trajectory in scratch and gathers the winner (small solves) or
+    re-rolls the winner (large sweeps): both give the same (xs*, us*) bit for bit."""
+    mj, m, _ = model_with(load_model, name)
+    nx = mj.nq + mj.nv
+    x0 = np.concatenate([mj.key_qpos("home"), np.zeros(mj.nv)]) if name == "barkour" else np.zeros(nx)
+    ug = np.tile(mj.key_ctrl("home"), (8, 1)) if name == "barkour" else np.zeros((8, mj.nu))
+    cf = StaticGoalQuadraticCost(np.eye(nx), 10 * np.eye(nx), 0.01 * np.eye(mj.nu), x0)
+    res = []
+    for mb in ("256", "0"):
+        monkeypatch.setenv("ABR_KEEP_TRAJ_MB", mb)
+        ps = VanillaPredictiveSampler(model=m, cost_function=cf, nsamples=64, stdev=0.05)
+        xs, us, info = ps.optimize(VanillaPredictiveSamplerParams(key=5, x0=t32(x0), us_guess=t32(ug)), return_info=True)
+        res.append((xs.cpu().numpy(), us.cpu().numpy(), int(info["best_idx"])))
+    assert res[0][2] == res[1][2]
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])

@@ -78,6 +78,40 @@ __device__ __forceinline__ float gs(float x, int lv, int mxl) {
 }
 __device__ __forceinline__ float gall(float x, int lg) { return gs(x, lg, lg); }
 
+
+// sin/cos with a three-constant Cody-Waite reduction and Cephes minimax polynomials (about 1 ulp for
+// |x| < 1e5): branch-free, so the straight-line step carries no Payne-Hanek slow path per call site.
+__device__ __forceinline__ void sincos_bf(float x, float& sn, float& cs) {
+  const float j = rintf(x * 0.636619772367581343f);
+  float r = fmaf(-j, 1.57079625129699707031f, x);
+  r = fmaf(-j, 7.54978941586159635335e-08f, r);
+  r = fmaf(-j, 5.39030252995776476554e-15f, r);
+  const int q = (int)j;
+  const float r2 = r * r;
+  const float sp = fmaf(r * r2, fmaf(r2, fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f), -1.6666654611e-1f), r);
+  const float cp = fmaf(r2 * r2, fmaf(r2, fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f), 4.166664568298827e-2f), fmaf(-0.5f, r2, 1.f));
+  const float a = (q & 1) ? cp : sp, b = (q & 1) ? sp : cp;
+  sn = (q & 2) ? -a : a;
+  cs = ((q + 1) & 2) ? -b : b;
+}
+__device__ __forceinline__ void axis_angle_quat_bf(const float* axis, float angle, float* q) {
+  float sn, cs;
+  sincos_bf(angle * 0.5f, sn, cs);
+  q[0] = cs; q[1] = axis[0] * sn; q[2] = axis[1] * sn; q[3] = axis[2] * sn;
+}
+// x / max(|x|, tiny) with one reciprocal
+template <int K> __device__ __forceinline__ float normalize_k(float (&x)[K]) {
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < K; i++) ss = fmaf(x[i], x[i], ss);
+  const float nrm = sqrtf(ss);
+  const float inv = 1.f / ((nrm == 0.f) ? 1e-6f : nrm);
+#pragma unroll
+  for (int i = 0; i < K; i++) x[i] *= inv;
+  return nrm;
+}
+static __device__ __noinline__ float pow_cold(float x, float p) { return powf(x, p); }
+
 // ------------------------------------------------------------------------------ dense local L'DL
 // A: packed lower triangle in "share" form on shared rows. Leaves-first elimination (MuJoCo's
 // L'DL order): after the call A holds D on the diagonal and D*L below it, replicated on shared rows.
@@ -193,7 +227,7 @@ __device__ __forceinline__ void row_kbi(const float* prm /* smem, stride kStride
   float ia, ib;
   if (power == 2.f) { ia = x * x; const float t = 1.f - x; ib = t * t; }
   else if (power == 1.f) { ia = x; ib = 1.f - x; }
-  else { ia = powf(x, power); ib = powf(1.f - x, power); }
+  else { ia = pow_cold(x, power); ib = pow_cold(1.f - x, power); }
   const float y = (x < mid) ? prm[8 * kStride] * ia : 1.f - prm[9 * kStride] * ib;
   float imp = dmin + y * (dmax - dmin);
   imp = fminf(fmaxf(imp, dmin), dmax);
@@ -245,16 +279,15 @@ template <int NL, int NC, class SH> __device__ __forceinline__ float solver_cost
   gauss = 0.5f * g;
   return 0.5f * sc + 0.5f * g;
 }
-// one point of the exact line search: (cost, d0, d1) at alpha
-template <int NL, int NC> __device__ __forceinline__ LSP ls_eval(const Rows<NL, NC>& R, const float (&Jaref)[NL + 4 * NC], const float (&jv)[NL + 4 * NC], float alpha,
-                                                                 float qg0, float qg1, float qg2, int lg) {
+// one point of the exact line search: (cost, d0, d1) at alpha. a0/a1/a2 are the per-row quadratic
+// coefficients 0.5 D ja^2, D ja jv, 0.5 D jv^2 (a row counts while ja + alpha jv < 0).
+template <int NR> __device__ __forceinline__ LSP ls_eval(const float (&Jaref)[NR], const float (&jv)[NR], const float (&a0)[NR], const float (&a1)[NR],
+                                                         const float (&a2)[NR], float alpha, float qg0, float qg1, float qg2, int lg) {
   float q0 = 0.f, q1 = 0.f, q2 = 0.f;
 #pragma unroll
-  for (int r = 0; r < NL + 4 * NC; r++) {
-    const float ja = Jaref[r], w = jv[r];
-    const float x = fmaf(alpha, w, ja);
-    const float Dr = (x < 0.f) ? R.D[r] : 0.f;
-    q0 = fmaf(0.5f * ja * ja, Dr, q0); q1 = fmaf(w * ja, Dr, q1); q2 = fmaf(0.5f * w * w, Dr, q2);
+  for (int r = 0; r < NR; r++) {
+    const bool on = fmaf(alpha, jv[r], Jaref[r]) < 0.f;
+    q0 += on ? a0[r] : 0.f; q1 += on ? a1[r] : 0.f; q2 += on ? a2[r] : 0.f;
   }
   q0 = gall(q0, lg) + qg0; q1 = gall(q1, lg) + qg1; q2 = gall(q2, lg) + qg2;
   LSP pt;
@@ -276,7 +309,7 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
   float xpos[NP][3], xquat[NP][4], xipos[NP][3], xanc[NP][3], xax[NP][3];
   {
     float q[4] = {s.qt[3], s.qt[4], s.qt[5], s.qt[6]};
-    v_normalize(q, 4);
+    normalize_k<4>(q);
     s.qt[3] = q[0]; s.qt[4] = q[1]; s.qt[5] = q[2]; s.qt[6] = q[3];
 #pragma unroll
     for (int i = 0; i < 3; i++) { xpos[0][i] = s.qt[i]; xanc[0][i] = s.qt[i]; xax[0][i] = (i == 2) ? 1.f : 0.f; }
@@ -311,7 +344,7 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
     const float dq = s.qc[p - 1] - LTF(mp.jnt(p) + 6);
     // hinge: rotate about the joint axis and re-anchor; slide: translate along the axis
     float ql[4], qn[4];
-    axis_angle_quat(jx, (type == kJHinge) ? dq : 0.f, ql);
+    axis_angle_quat_bf(jx, (type == kJHinge) ? dq : 0.f, ql);
     q_mul(quat, ql, qn);
     q_rot(jp, qn, r);
     const float sl = (type == kJSlide) ? dq : 0.f;
@@ -336,7 +369,8 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
       sx = fmaf(xipos[p][0], ms, sx); sy = fmaf(xipos[p][1], ms, sy); sz = fmaf(xipos[p][2], ms, sz);
     }
     sx = gall(sx, S.lg()); sy = gall(sy, S.lg()); sz = gall(sz, S.lg());
-    com[0] = sx / C.mass; com[1] = sy / C.mass; com[2] = sz / C.mass;
+    const float im = 1.f / C.mass;
+    com[0] = sx * im; com[1] = sy * im; com[2] = sz * im;
   }
   float cinert[NP][10];
 #pragma unroll
@@ -715,7 +749,13 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
     const float smag = sqrtf(sn) * C.meaninertia * (float)max(1, C.nv);
     const float gtol = C.tol * C.ls_tol * smag;
     const float qg0 = gauss, qg1 = sMa - sq, qg2 = 0.5f * smv;
-#define LS_EVAL(al) ls_eval<NL, NC>(R, Jaref, jv, (al), qg0, qg1, qg2, S.lg())
+    float la0[NR], la1[NR], la2[NR];
+#pragma unroll
+    for (int r = 0; r < NR; r++) {
+      const float ja = Jaref[r], w = jv[r], Dr = R.D[r];
+      la0[r] = 0.5f * ja * ja * Dr; la1[r] = w * ja * Dr; la2[r] = 0.5f * w * w * Dr;
+    }
+#define LS_EVAL(al) ls_eval<NR>(Jaref, jv, la0, la1, la2, (al), qg0, qg1, qg2, S.lg())
     const LSP p0 = LS_EVAL(0.f);
     const LSP l0 = LS_EVAL(-safe_div(p0.d0, p0.d1));
     const bool lesser = l0.d0 < p0.d0;
@@ -790,11 +830,11 @@ __device__ __forceinline__ void euler(Lane<NL, NC>& s, const LaneCfg<LGC>& C, fl
   // free joint
   s.qt[0] = fmaf(dt, s.v[0], s.qt[0]); s.qt[1] = fmaf(dt, s.v[1], s.qt[1]); s.qt[2] = fmaf(dt, s.v[2], s.qt[2]);
   float w[3] = {s.v[3], s.v[4], s.v[5]};
-  const float nrm = v_normalize(w, 3);
+  const float nrm = normalize_k<3>(w);
   float ql[4], qn[4];
-  axis_angle_quat(w, dt * nrm, ql);
+  axis_angle_quat_bf(w, dt * nrm, ql);
   q_mul(s.qt + 3, ql, qn);
-  v_normalize(qn, 4);
+  normalize_k<4>(qn);
   s.qt[3] = qn[0]; s.qt[4] = qn[1]; s.qt[5] = qn[2]; s.qt[6] = qn[3];
 #pragma unroll
   for (int p = 1; p <= NL; p++) s.qc[p - 1] = fmaf(dt, s.v[5 + p], s.qc[p - 1]);

@@ -79,7 +79,9 @@ struct AbrModel {
   int num_sms = 148;
   int max_smem = 0;
   cudaStream_t stream = nullptr;  // for the *_host entry points
-  Scratch s_costs, s_in, s_out, s_dbg, s_traj;
+  cudaStream_t copy_stream = nullptr;  // host->device slices of a pipelined abr_rollout_host
+  std::vector<cudaEvent_t> ev;
+  Scratch s_costs, s_in, s_out, s_dbg, s_traj, s_carry;
 };
 
 struct AbrCost {
@@ -801,7 +803,9 @@ int abr_model_destroy(AbrModel* m) {
   if (!m) return ABR_OK;
   cudaSetDevice(m->device);
   if (m->d_blob) cudaFree(m->d_blob);
-  m->s_costs.release(); m->s_in.release(); m->s_out.release(); m->s_dbg.release(); m->s_traj.release();
+  m->s_costs.release(); m->s_in.release(); m->s_out.release(); m->s_dbg.release(); m->s_traj.release(); m->s_carry.release();
+  for (cudaEvent_t e : m->ev) cudaEventDestroy(e);
+  if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
   if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
   return ABR_OK;
@@ -894,6 +898,7 @@ int abr_rollout_dev(AbrModel* m, const float* x0, int x0_stride, const float* us
   a.blob = m->d_blob; a.x0 = x0; a.x0_stride = x0_stride; a.us = us; a.us_stride = us_stride;
   a.mode = 0; a.nworld = nworld; a.N = N; a.xs_out = xs_out; a.costs_out = costs_out;
   a.cost = cost_view(costs_out ? cost : nullptr);
+  a.t_begin = 0; a.t_end = N;
   return launch_rollout(m, m->lay, a, (cudaStream_t)stream);
 }
 
@@ -915,9 +920,42 @@ int abr_rollout_host(AbrModel* m, const float* x0, int x0_stride, const float* u
   float* d_x0 = (float*)m->s_in.p; float* d_us = d_x0 + n_x0;
   float* d_xs = (float*)m->s_out.p; float* d_c = d_xs + n_xs;
   CK(cudaMemcpyAsync(d_x0, x0, sizeof(float) * n_x0, cudaMemcpyHostToDevice, m->stream));
-  if (n_us) CK(cudaMemcpyAsync(d_us, us, sizeof(float) * n_us, cudaMemcpyHostToDevice, m->stream));
-  rc = abr_rollout_dev(m, d_x0, x0_stride, d_us, us_stride, nworld, N, xs_out ? d_xs : nullptr, cost, costs_out ? d_c : nullptr, m->stream);
-  if (rc) return rc;
+  // Pipelined form (limb kernels, long horizons): the controls go up in horizon slices on a copy stream
+  // while the previous slice's steps run; state and running cost pass between the slice launches in `carry`.
+  int nslice = 1;
+  if (us_stride != 0 && N >= 64 && getenv("ABR_NO_PIPELINE") == nullptr && use_limb(m, m->lay, costs_out && cost && !cost->diag, false)) nslice = 8;
+  if (const char* e = getenv("ABR_SLICES")) { const int v = atoi(e); if (v >= 1 && v <= 64 && nslice > 1) nslice = v; }
+  if (nslice == 1) {
+    if (n_us) CK(cudaMemcpyAsync(d_us, us, sizeof(float) * n_us, cudaMemcpyHostToDevice, m->stream));
+    rc = abr_rollout_dev(m, d_x0, x0_stride, d_us, us_stride, nworld, N, xs_out ? d_xs : nullptr, cost, costs_out ? d_c : nullptr, m->stream);
+    if (rc) return rc;
+  } else {
+    if (!m->copy_stream) CK(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+    while ((int)m->ev.size() < nslice + 1) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); m->ev.push_back(e); }
+    rc = m->s_carry.ensure(sizeof(float) * (size_t)nworld * (m->lay.nq + 2 * m->lay.nv + 8));
+    if (rc) return rc;
+    // the copy stream must not overwrite d_us while an earlier call's kernels may still read it
+    CK(cudaEventRecord(m->ev[nslice], m->stream));
+    CK(cudaStreamWaitEvent(m->copy_stream, m->ev[nslice], 0));
+    const int per = (N + nslice - 1) / nslice;
+    RolloutArgs a;
+    memset(&a, 0, sizeof(a));
+    a.blob = m->d_blob; a.x0 = d_x0; a.x0_stride = x0_stride; a.us = d_us; a.us_stride = us_stride;
+    a.mode = 0; a.nworld = nworld; a.N = N; a.xs_out = xs_out ? d_xs : nullptr; a.costs_out = costs_out ? d_c : nullptr;
+    a.cost = cost_view(costs_out ? cost : nullptr); a.carry = (float*)m->s_carry.p;
+    const size_t pitch = sizeof(float) * (size_t)N * nu;
+    for (int k = 0; k < nslice; k++) {
+      const int tb = k * per, te = std::min(N, tb + per);
+      if (tb >= te) break;
+      CK(cudaMemcpy2DAsync(d_us + (size_t)tb * nu, pitch, us + (size_t)tb * nu, pitch, sizeof(float) * (size_t)(te - tb) * nu, nworld,
+                           cudaMemcpyHostToDevice, m->copy_stream));
+      CK(cudaEventRecord(m->ev[k], m->copy_stream));
+      CK(cudaStreamWaitEvent(m->stream, m->ev[k], 0));
+      a.t_begin = tb; a.t_end = te;
+      rc = launch_rollout(m, m->lay, a, m->stream);
+      if (rc) return rc;
+    }
+  }
   if (n_xs) CK(cudaMemcpyAsync(xs_out, d_xs, sizeof(float) * n_xs, cudaMemcpyDeviceToHost, m->stream));
   if (n_c) CK(cudaMemcpyAsync(costs_out, d_c, sizeof(float) * n_c, cudaMemcpyDeviceToHost, m->stream));
   CK(cudaStreamSynchronize(m->stream));
@@ -943,6 +981,7 @@ int abr_predictive_sample_dev(AbrModel* m, const AbrCost* cost, const float* x0,
   a.blob = m->d_blob; a.x0 = x0; a.x0_stride = m->lay.nx; a.us = us_guess; a.us_stride = N * m->lay.nu;
   a.noise = noise; a.seed = seed; a.stdev = stdev; a.mode = 1; a.S = S; a.S_total = S_total; a.sample_offset = sample_offset;
   a.nworld = B * S; a.N = N; a.costs_out = d_costs; a.cost = cost_view(cost);
+  a.t_begin = 0; a.t_end = N;
   // Winner trajectories: when every sample's states fit a modest scratch they are kept (a few MB at the
   // 4096 x 32 solve) and the winner is gathered, so the solve is ONE rollout launch deep; larger sweeps
   // re-roll the B winners instead and never materialise the S x (N+1) x nx tensor (shooting.py:152).

@@ -38,6 +38,10 @@ struct RolloutArgs {
   float* us_out;                           // nullable [nworld,N,nu] (controls actually applied)
   float* costs_out;                        // nullable [nworld]
   CostView cost;
+  // horizon slice [t_begin, t_end) of a pipelined rollout (limb kernels): state and the running cost are
+  // carried between the slices' launches in `carry` [nworld, nq + 2 nv + 8]; t_begin = 0 starts from x0
+  int t_begin, t_end;
+  float* carry;
 };
 
 __device__ __forceinline__ void stage_blob(const Layout& L, const float* blob, float* smem) {

@@ -918,28 +918,37 @@ __global__ void __launch_bounds__(kMaxTPB) k_limb_rollout(const __grid_constant_
     if (A.sample_ids) { prob = w; sample = A.sample_ids[w]; }
     else { prob = w / A.S; sample = A.sample_offset + (w - prob * A.S); }
   }
-  const float* x0 = A.x0 + (size_t)(A.mode == 1 ? prob : w) * A.x0_stride;
+  const int t_first = A.t_begin, t_last = A.t_end;
+  const bool resume = t_first > 0;
+  const int cstride = nq + 2 * L.nv + 8;
+  float* carry = A.carry ? A.carry + (size_t)w * cstride : nullptr;
+  // a resumed slice reads the state its predecessor left in `carry` (same layout as x0, then qacc_warmstart)
+  const float* x0 = resume ? carry : A.x0 + (size_t)(A.mode == 1 ? prob : w) * A.x0_stride;
   Lane<NL, NC> s;
 #pragma unroll
   for (int i = 0; i < 7; i++) s.qt[i] = x0[i];
 #pragma unroll
-  for (int i = 0; i < 6; i++) s.v[i] = x0[nq + i];
+  for (int i = 0; i < 6; i++) { s.v[i] = x0[nq + i]; s.warm[i] = resume ? x0[nx + i] : 0.f; s.a[i] = 0.f; }
 #pragma unroll
   for (int p = 1; p <= NL; p++) {
     const int gd = LTI(mp.ijnt(p) + 1), gq = LTI(mp.ijnt(p) + 2);
     s.qc[p - 1] = (gd >= 0) ? x0[gq] : 0.f;
     s.v[5 + p] = (gd >= 0) ? x0[nq + gd] : 0.f;
+    s.warm[5 + p] = (gd >= 0 && resume) ? x0[nx + gd] : 0.f;
     s.ctrl[p - 1] = 0.f;
+    s.a[5 + p] = 0.f;
   }
-#pragma unroll
-  for (int d = 0; d < N; d++) { s.warm[d] = 0.f; s.a[d] = 0.f; }
   float* xs = A.xs_out ? A.xs_out + (size_t)w * (Nh + 1) * nx : nullptr;
-  if (xs && valid) store_x<NL, NC, LGC>(s, C, xs, nq);
   float cacc = 0.f;
-  if (A.cost.enabled) cacc += quad_x_diag<NL, NC, LGC>(s, C, Nh > 0 ? cqd : cqf, cxg, nq);
+  if (!resume) {
+    if (xs && valid) store_x<NL, NC, LGC>(s, C, xs, nq);
+    if (A.cost.enabled) cacc += quad_x_diag<NL, NC, LGC>(s, C, Nh > 0 ? cqd : cqf, cxg, nq);
+  } else {
+    cacc = carry[nx + L.nv + g];
+  }
   // t = -1 is mjx.forward with ctrl = 0, which seeds qacc_warmstart (shooting.py:36)
 #pragma unroll 1
-  for (int t = -1; t < Nh; t++) {
+  for (int t = resume ? t_first : -1; t < t_last; t++) {
     if (blockDim.x > 32) __syncthreads();
     if (t >= 0) {
 #pragma unroll
@@ -973,6 +982,22 @@ __global__ void __launch_bounds__(kMaxTPB) k_limb_rollout(const __grid_constant_
       if (xs && valid) store_x<NL, NC, LGC>(s, C, xs + (size_t)(t + 1) * nx, nq);
       if (A.cost.enabled) cacc += quad_x_diag<NL, NC, LGC>(s, C, (t == Nh - 1) ? cqf : cqd, cxg, nq);
     }
+  }
+  if (t_last < Nh) {  // hand the state to the next slice
+    if (valid && carry) {
+      store_x<NL, NC, LGC>(s, C, carry, nq);
+      if (C.S.o(0)) {
+#pragma unroll
+        for (int i = 0; i < 6; i++) carry[nx + i] = s.warm[i];
+      }
+#pragma unroll
+      for (int p = 1; p <= NL; p++) {
+        const int gd = LTI(mp.ijnt(p) + 1);
+        if (gd >= 0 && C.S.o(p)) carry[nx + gd] = s.warm[5 + p];
+      }
+      carry[nx + L.nv + g] = cacc;
+    }
+    return;
   }
   if (A.costs_out) {
     cacc = gall(cacc, lg);

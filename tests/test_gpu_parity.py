@@ -451,3 +451,27 @@ def test_vps_kept_trajectories_equal_rerolled_winner(load_model, name, monkeypat
         res.append((xs.cpu().numpy(), us.cpu().numpy(), int(info["best_idx"])))
     assert res[0][2] == res[1][2]
     assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+
+
+def test_host_rollout_pipelined_slices_equal_one_launch(load_model, monkeypatch):
+    """abr_rollout_host sends long control sequences up in horizon slices that overlap the previous slice's
+    steps (state and running cost carried between the slice launches): same bits as the single launch."""
+    mj, m, _ = model_with(load_model, "barkour")
+    rng = np.random.default_rng(8)
+    W, N = 40, 70
+    nx = mj.nq + mj.nv
+    x0 = np.tile(np.concatenate([mj.key_qpos("home"), np.zeros(mj.nv)]), (W, 1)).astype(np.float32)
+    x0[:, 7:mj.nq] += rng.uniform(-0.05, 0.05, (W, mj.nq - 7)).astype(np.float32)
+    us = np.clip(mj.key_ctrl("home") + 0.1 * rng.normal(size=(W, N, mj.nu)), mj.actuator_ctrlrange[:, 0], mj.actuator_ctrlrange[:, 1]).astype(np.float32)
+    cf = StaticGoalQuadraticCost(np.eye(nx), 10 * np.eye(nx), 0.01 * np.eye(mj.nu), x0[0])
+    res = {}
+    for mode, env in (("sliced", {"ABR_SLICES": "5"}), ("single", {"ABR_NO_PIPELINE": "1"})):
+        for k in ("ABR_SLICES", "ABR_NO_PIPELINE"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        res[mode] = (shoot(m, x0, us), shoot_cost(m, x0, us, cf))
+    assert isinstance(res["sliced"][0], np.ndarray)
+    assert np.array_equal(res["sliced"][0], res["single"][0])
+    assert np.array_equal(np.asarray(res["sliced"][1]), np.asarray(res["single"][1]))
+    assert np.isfinite(res["sliced"][0]).all()

@@ -709,9 +709,9 @@ static bool use_limb(const AbrModel* m, const Layout& L, bool dense_cost, bool d
 static int launch_rollout(const AbrModel* m, const Layout& L, const RolloutArgs& a, cudaStream_t st) {
   if (a.nworld <= 0) return ABR_OK;
   if (use_limb(m, L, a.cost.enabled && !a.cost.diag, false)) {
-    const bool flat2 = L.lg2G == 2 && (L.l_mx >> 2) == 0 && getenv("ABR_LIMB_GENERAL") == nullptr;
-    if (L.lNL == 3 && L.lNC == 1) return launch_result(flat2 ? launch_limb_rollout_3_1_f2(L, a, st) : launch_limb_rollout_3_1_g(L, a, st));
-    if (L.lNL == 6 && L.lNC == 4) return launch_result(launch_limb_rollout_6_4_g(L, a, st));
+    const bool spec = getenv("ABR_LIMB_GENERAL") == nullptr;  // compile-time sharing patterns: 2 = flat 4 lanes, 86 = biped
+    if (L.lNL == 3 && L.lNC == 1) return launch_result(spec && L.l_mx == 2 ? launch_limb_rollout_3_1_f2(L, a, st) : launch_limb_rollout_3_1_g(L, a, st));
+    if (L.lNL == 6 && L.lNC == 4) return launch_result(spec && L.l_mx == 86 ? launch_limb_rollout_6_4_b(L, a, st) : launch_limb_rollout_6_4_g(L, a, st));
     return fail(ABR_ECAPACITY, "no compiled limb kernel for this model");
   }
   LaunchCfg cfg{m->max_smem};
@@ -725,9 +725,9 @@ static int launch_rollout(const AbrModel* m, const Layout& L, const RolloutArgs&
 static int launch_env(const AbrModel* m, const Layout& L, const EnvArgs& a, cudaStream_t st) {
   if (a.E <= 0) return ABR_OK;
   if (use_limb(m, L, false, a.dbg != nullptr)) {
-    const bool flat2 = L.lg2G == 2 && (L.l_mx >> 2) == 0 && getenv("ABR_LIMB_GENERAL") == nullptr;
-    if (L.lNL == 3 && L.lNC == 1) return launch_result(flat2 ? launch_limb_env_3_1_f2(L, a, st) : launch_limb_env_3_1_g(L, a, st));
-    if (L.lNL == 6 && L.lNC == 4) return launch_result(launch_limb_env_6_4_g(L, a, st));
+    const bool spec = getenv("ABR_LIMB_GENERAL") == nullptr;
+    if (L.lNL == 3 && L.lNC == 1) return launch_result(spec && L.l_mx == 2 ? launch_limb_env_3_1_f2(L, a, st) : launch_limb_env_3_1_g(L, a, st));
+    if (L.lNL == 6 && L.lNC == 4) return launch_result(spec && L.l_mx == 86 ? launch_limb_env_6_4_b(L, a, st) : launch_limb_env_6_4_g(L, a, st));
     return fail(ABR_ECAPACITY, "no compiled limb kernel for this model");
   }
   LaunchCfg cfg{m->max_smem};

@@ -55,18 +55,24 @@ __host__ __device__ constexpr int FD(int p) { return p == 0 ? 0 : 5 + p; }  // f
 __host__ __device__ constexpr int LD(int p) { return 5 + p; }               // last dof of a position
 __host__ __device__ constexpr int TR(int i, int j) { return i * (i + 1) / 2 + j; }
 
-// per-lane sharing info. LGC >= 0 is the FLAT pattern resolved at compile time: only the trunk is
-// shared, by all 2^LGC lanes (quadrupeds, hexapods, hands ...), so every merge below the trunk and
-// every level test folds away; LGC = -1 reads the general (nested) pattern from the lane table.
+// per-lane sharing info. LGC >= 0 fixes the sharing PATTERN at compile time: LGC holds 2 bits per chain
+// position = log2 of the largest lane group sharing a body there (position 0, the trunk, is shared by all
+// 2^(LGC & 3) lanes), so merges at unshared positions and their level tests fold away; which lanes share and
+// who owns is still read per lane. LGC = 2 is the flat quadruped pattern (only the trunk shared, by 4 lanes),
+// LGC = 86 the biped's (trunk by 4, three torso positions by 2). LGC = -1 reads the pattern from the table.
 template <int LGC> struct ShareT {
   int own;   // bit p: this lane is the owner of its body at position p (always set on private bodies)
   int lvl;   // 2 bits per position: log2 of the lane-group size sharing the body
   int mx;    // 2 bits per position: max of lvl over the lanes (uniform)
   int lg_;   // log2(G)
-  __device__ __forceinline__ bool o(int p) const { if (LGC >= 0) return p == 0 ? (own & 1) : true; return (own >> p) & 1; }
-  __device__ __forceinline__ int l(int p) const { if (LGC >= 0) return p == 0 ? LGC : 0; return (lvl >> (2 * p)) & 3; }
-  __device__ __forceinline__ int m(int p) const { if (LGC >= 0) return p == 0 ? LGC : 0; return (mx >> (2 * p)) & 3; }
-  __device__ __forceinline__ int lg() const { return LGC >= 0 ? LGC : lg_; }
+  __device__ __forceinline__ int m(int p) const { if (LGC >= 0) return (LGC >> (2 * p)) & 3; return (mx >> (2 * p)) & 3; }
+  __device__ __forceinline__ bool o(int p) const { if (LGC >= 0 && m(p) == 0) return true; return (own >> p) & 1; }
+  __device__ __forceinline__ int l(int p) const {
+    if (LGC >= 0 && m(p) == 0) return 0;
+    if (LGC >= 0 && p == 0) return LGC & 3;
+    return (lvl >> (2 * p)) & 3;
+  }
+  __device__ __forceinline__ int lg() const { return LGC >= 0 ? (LGC & 3) : lg_; }
 };
 
 // sum over the lane group of level `lv` (per lane, uniform within a group); mxl is uniform
@@ -907,7 +913,7 @@ __global__ void __launch_bounds__(kMaxTPB) k_limb_rollout(const __grid_constant_
     for (int i = threadIdx.x; i < nu; i += blockDim.x) crd[i] = A.cost.rd[i];
   }
   __syncthreads();
-  const int lg = (LGC >= 0) ? LGC : L.lg2G;
+  const int lg = (LGC >= 0) ? (LGC & 3) : L.lg2G;
   const int g = threadIdx.x & ((1 << lg) - 1);
   const int wraw = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> lg);
   const bool valid = wraw < A.nworld;
@@ -1015,7 +1021,7 @@ __global__ void __launch_bounds__(kMaxTPB) k_limb_env(const __grid_constant__ La
   const int nu = L.nu, nq = L.nq, nv = L.nv;
   for (int i = threadIdx.x; i < ntab; i += blockDim.x) smem[i] = A.blob[L.f_ltab + i];
   __syncthreads();
-  const int lg = (LGC >= 0) ? LGC : L.lg2G;
+  const int lg = (LGC >= 0) ? (LGC & 3) : L.lg2G;
   const int g = threadIdx.x & ((1 << lg) - 1);
   const int wraw = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> lg);
   const bool valid = wraw < A.E;
@@ -1095,7 +1101,7 @@ template <int NL, int NC, class Args, class K> int launch_limb(K kern, const Lay
 
 }  // namespace limb
 
-// LGC: -1 = general sharing pattern (suffix g), 2 = flat 4-lane pattern (suffix f2)
+// LGC: -1 = general sharing pattern (suffix g), 2 = flat 4-lane pattern (suffix f2), 86 = biped pattern (suffix b)
 #define ABR_DECLARE_LIMB_LAUNCHERS(NL, NC, TAG)                                                        \
   int launch_limb_rollout_##NL##_##NC##_##TAG(const Layout&, const RolloutArgs&, cudaStream_t);        \
   int launch_limb_env_##NL##_##NC##_##TAG(const Layout&, const EnvArgs&, cudaStream_t);
@@ -1109,6 +1115,7 @@ template <int NL, int NC, class Args, class K> int launch_limb(K kern, const Lay
 ABR_DECLARE_LIMB_LAUNCHERS(3, 1, f2)
 ABR_DECLARE_LIMB_LAUNCHERS(3, 1, g)
 ABR_DECLARE_LIMB_LAUNCHERS(6, 4, g)
+ABR_DECLARE_LIMB_LAUNCHERS(6, 4, b)
 
 }  // namespace abr
 #endif

@@ -1,0 +1,6 @@
+// limb-path kernels for the biped / exoskeleton class: chains of up to 6 joints, 4 contacts per path,
+// sharing pattern "trunk by 4 lanes, three torso positions by 2" resolved at compile time
+#include "abr_limb.cuh"
+namespace abr {
+ABR_DEFINE_LIMB_LAUNCHERS(6, 4, 86, b)
+}

@@ -850,7 +850,9 @@ __device__ __forceinline__ void euler(Lane<NL, NC>& s, const LaneCfg<LGC>& C, fl
 
 // ------------------------------------------------------------------------------ kernels
 constexpr int kTPB = 32;      // default: one warp per CTA (32/G worlds); small CTAs spread a 4096-world batch over every SM sub-partition
-constexpr int kMaxTPB = 256;  // larger CTAs run their warps in lockstep (one barrier per step) so they share instruction fetches
+#ifndef ABR_LIMB_MINB
+#define ABR_LIMB_MINB 1  // resident CTAs per SM the register allocation must allow (1 = up to 255 registers)
+#endif
 
 template <int NL, int NC, int LGC> __device__ __forceinline__ LaneCfg<LGC> make_cfg(const Layout& L, const float* T, int g) {
   constexpr Map mp{NL, NC};
@@ -900,7 +902,7 @@ template <int NL, int NC, int LGC> __device__ __forceinline__ void store_x(const
 
 // shoot (shooting.py:22-48) / the sampler's rollouts (shooting.py:140-153) on the limb path
 template <int NL, int NC, int LGC>
-__global__ void __launch_bounds__(kMaxTPB) k_limb_rollout(const __grid_constant__ Layout L, const __grid_constant__ RolloutArgs A) {
+__global__ void __launch_bounds__(kTPB, ABR_LIMB_MINB) k_limb_rollout(const __grid_constant__ Layout L, const __grid_constant__ RolloutArgs A) {
   extern __shared__ __align__(16) float smem[];
   constexpr Map mp{NL, NC};
   constexpr int N = 6 + NL, NTRI = N * (N + 1) / 2;
@@ -955,7 +957,6 @@ __global__ void __launch_bounds__(kMaxTPB) k_limb_rollout(const __grid_constant_
   // t = -1 is mjx.forward with ctrl = 0, which seeds qacc_warmstart (shooting.py:36)
 #pragma unroll 1
   for (int t = resume ? t_first : -1; t < t_last; t++) {
-    if (blockDim.x > 32) __syncthreads();
     if (t >= 0) {
 #pragma unroll
       for (int p = 1; p <= NL; p++) {
@@ -1013,7 +1014,7 @@ __global__ void __launch_bounds__(kMaxTPB) k_limb_rollout(const __grid_constant_
 
 // MjxEnv.pipeline_init / pipeline_step (rl/base.py:81-96) with the auto-reset blend, on the limb path
 template <int NL, int NC, int LGC>
-__global__ void __launch_bounds__(kMaxTPB) k_limb_env(const __grid_constant__ Layout L, const __grid_constant__ EnvArgs A) {
+__global__ void __launch_bounds__(kTPB, ABR_LIMB_MINB) k_limb_env(const __grid_constant__ Layout L, const __grid_constant__ EnvArgs A) {
   extern __shared__ __align__(16) float smem[];
   constexpr Map mp{NL, NC};
   constexpr int N = 6 + NL, NTRI = N * (N + 1) / 2;
@@ -1089,10 +1090,8 @@ template <int NL, int NC, class Args, class K> int launch_limb(K kern, const Lay
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   if (e != cudaSuccess) return (int)e;
   const long threads = (long)nworld << L.lg2G;
-  int tpb = kTPB;
-  if (const char* e = getenv("ABR_LIMB_TPB")) { const int v = atoi(e); if (v == 32 || v == 64 || v == 128 || v == 256) tpb = v; }
-  const int grid = (int)((threads + tpb - 1) / tpb);
-  kern<<<grid, tpb, sm, st>>>(L, a);
+  const int grid = (int)((threads + kTPB - 1) / kTPB);
+  kern<<<grid, kTPB, sm, st>>>(L, a);
   return (int)cudaGetLastError();
 }
 

@@ -34,6 +34,9 @@ CTRL_NOISE, JITTER = 0.1, 0.05
 # work" variant (no unused post-iteration Hessian), home state: add=sub=mul=div=sqrt=sin=cos=pow=1.
 F_WS = 46349.0
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
+# dram__bytes_read.sum + dram__bytes_write.sum of the C2 launch (one `ncu --set full` capture of this file's
+# own kernel launch, profiles/r1_limb_v3_c2_summary.txt): 198.16 MB + 5.24 MB vs 197.23 MB algorithmic
+NCU_DRAM_BYTES_C2 = 198_161_920 + 5_236_480
 
 
 def peaks():
@@ -124,6 +127,80 @@ def cpu_arm(mj, budget_s, nthreads):
     worlds = max(nthreads, worlds // nthreads * nthreads)
     rate = run(worlds, HORIZON)
     return rate, f"{worlds} worlds x {HORIZON} steps of the C2 workload, float32 oracle port, {nthreads} threads"
+
+
+def _timed(torch, stream, fn, reps):
+    fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for _ in range(reps):
+        fn()
+    b.record(stream)
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def extra_configs(mj, m, cf, q0, torch, device, stream, L, peak_tf):
+    """The other BASELINE.json configs on one GPU (context for the headline, not bench lines of their own):
+    a large Barkour batch (roofline at full occupancy), C3 biped 16384 x 1000, the C4 sample sweep x 32 steps,
+    C5 env-step throughput with auto-reset at 8192 envs."""
+    from ambersim_b200 import _lib, mjx
+    from ambersim_b200.rl.base import VectorEnvStepper
+    from ambersim_b200.trajopt.cost import StaticGoalQuadraticCost
+    from ambersim_b200.trajopt.shooting import VanillaPredictiveSampler, VanillaPredictiveSamplerParams
+    from ambersim_b200.utils.io_utils import load_mj_model_from_file
+
+    f = dict(dtype=torch.float32, device=device)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    g = torch.Generator(device=device)
+    g.manual_seed(7)
+    ex = {}
+
+    def rollout_rate(mjm, model, cost, key, W, N, noise):
+        x0 = torch.tensor(np.concatenate([mjm.key_qpos(key), np.zeros(mjm.nv)]), **f).repeat(W, 1)
+        x0[:, 7:mjm.nq] += (torch.rand((W, mjm.nq - 7), generator=g, **f) - 0.5) * 2 * JITTER
+        lim = torch.tensor(mjm.actuator_ctrlrange, **f)
+        us = torch.tensor(mjm.key_ctrl(key), **f) + noise * torch.randn((W, N, mjm.nu), generator=g, **f)
+        us = torch.minimum(torch.maximum(us, lim[:, 0]), lim[:, 1]).contiguous()
+        costs = torch.empty(W, **f)
+        h, ch = model.handle(device.index or 0), cost.device_cost(device.index or 0)
+        ms = _timed(torch, stream, lambda: _lib.check(L.abr_rollout_dev(h.ptr, p(x0), mjm.nq + mjm.nv, p(us), N * mjm.nu, W, N, None, ch.ptr,
+                                                                        p(costs), C.c_void_p(stream.cuda_stream))), 2)
+        return W * N / (ms * 1e-3), bool(torch.isfinite(costs).all())
+
+    rate, fin = rollout_rate(mj, m, cf, "home", 65536, 250, CTRL_NOISE)
+    ex["barkour_65536x250"] = {"world_steps_per_s": rate, "frac_of_ffma_peak": F_WS * rate / 1e12 / peak_tf, "costs_finite": fin}
+    bj = load_mj_model_from_file("models/biped_standin/biped_exo_standin.xml")
+    bm = mjx.device_put(bj)
+    bq0 = np.concatenate([bj.key_qpos("stand"), np.zeros(bj.nv)])
+    bnx = bj.nq + bj.nv
+    bcf = StaticGoalQuadraticCost(np.eye(bnx), 10.0 * np.eye(bnx), 0.01 * np.eye(bj.nu), bq0)
+    rate, fin = rollout_rate(bj, bm, bcf, "stand", 16384, 1000, CTRL_NOISE)
+    ex["c3_biped_16384x1000"] = {"world_steps_per_s": rate, "costs_finite": fin,
+                                 "model": "biped_exo_standin (nq=28 nv=27 nu=21 nbody=23 ncon=8 nefc=53; Newton it=1 ls=6 Euler dt=.004)"}
+    sweep = {}
+    prm = VanillaPredictiveSamplerParams(key=3, x0=torch.tensor(q0, **f), us_guess=torch.tensor(mj.key_ctrl("home"), **f).repeat(32, 1))
+    for S in (1024, 4096, 16384, 65536, 262144, 1048576):
+        ps = VanillaPredictiveSampler(model=m, cost_function=cf, nsamples=S, stdev=0.1)
+        sweep[str(S)] = _timed(torch, stream, lambda: ps.optimize(prm), 3)
+    ex["c4_solve_ms_by_samples_x32"] = sweep
+    E, T = 8192, 200
+    qpos0 = torch.tensor(mj.key_qpos("home"), **f).repeat(E, 1)
+    qpos0[:, 7:] += (torch.rand((E, mj.nq - 7), generator=g, **f) - 0.5) * 2 * JITTER
+    env = VectorEnvStepper(m, qpos0, torch.zeros(E, mj.nv, **f), nsubsteps=1)
+    lim = torch.tensor(mj.actuator_ctrlrange, **f)
+    acts = torch.minimum(torch.maximum(torch.tensor(mj.key_ctrl("home"), **f) + CTRL_NOISE * torch.randn((T, E, mj.nu), generator=g, **f), lim[:, 0]), lim[:, 1])
+    done = torch.rand((T, E), generator=g, **f) < 1e-3
+
+    def env_loop():
+        for t in range(T):
+            env.step(acts[t], done[t])
+
+    ms = _timed(torch, stream, env_loop, 2)
+    ex["c5_env_steps_per_s_8192"] = {"value": E * T / (ms * 1e-3), "launches_per_env_step": 1,
+                                     "note": "physics only (policy excluded), auto-reset blend in the step prologue, one launch per env step"}
+    return ex
 
 
 def main():
@@ -232,7 +309,8 @@ def main():
     achieved_tf = F_WS * per_gpu_ws / 1e12
     alg_bytes = WORLDS * HORIZON * mj.nu * 4 + WORLDS * (mj.nq + mj.nv) * 4 + WORLDS * 4
     out["roofline"] = {"bound": "fp32", "achieved": achieved_tf, "peak": tf.value, "unit": "TFLOP/s", "frac": achieved_tf / tf.value,
-                       "traffic": None, "peak_kind": "FFMA microkernel timed in this run (abr_ffma_peak)",
+                       "traffic": NCU_DRAM_BYTES_C2 if not args.lanes else None, "traffic_unit": "bytes per launch (ncu dram read+write)",
+                       "peak_kind": "FFMA microkernel timed in this run (abr_ffma_peak)",
                        "peak_nominal": NOMINAL_FP32_TFLOPS, "frac_of_nominal": achieved_tf / NOMINAL_FP32_TFLOPS,
                        "flop_per_world_step": F_WS,
                        "hbm": {"achieved": alg_bytes / (ms_per_step * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
@@ -281,10 +359,12 @@ def main():
             torch.cuda.synchronize(device)
             out["extra"] = {"vps_4096x32_solve_ms": a.elapsed_time(b) / reps,
                             "vps_note": "VanillaPredictiveSampler.optimize, device-resident inputs: rollouts + argmin + winner gather (3 launches)"}
-            rate, sample = cpu_arm(mj, args.cpu_seconds, ncores)
-            out["cpu_baseline"] = {"value": rate, "unit": "world-steps/s", "cores": ncores, "kind": "port", "sample": sample,
-                                   "note": "oracle port (float32); the reference's own CPU path (MJX on JAX-CPU, MuJoCo C) is not "
-                                           "installable in this image"}
+            if world == 1:  # the other configs and the CPU baseline are reported by the single-GPU run only
+                out["extra"].update(extra_configs(mj, m, cf, q0, torch, device, stream, L, tf.value))
+                rate, sample = cpu_arm(mj, args.cpu_seconds, ncores)
+                out["cpu_baseline"] = {"value": rate, "unit": "world-steps/s", "cores": ncores, "kind": "port", "sample": sample,
+                                       "note": "oracle port (float32); the reference's own CPU path (MJX on JAX-CPU, MuJoCo C) is not "
+                                               "installable in this image"}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -53,6 +53,7 @@ def lib():
     L.abr_model_set_opt.argtypes = [vp, C.POINTER(S["AbrOpt"])]
     L.abr_model_get_opt.argtypes = [vp, C.POINTER(S["AbrOpt"])]
     L.abr_model_info.argtypes = [vp, ip, ip, ip, ip, ip]
+    L.abr_limb_plan_host.argtypes = [C.POINTER(S["AbrModelHost"]), ip, ip, C.c_int, ip, ip]
     L.abr_model_set_lanes.argtypes = [vp, C.c_int]
     L.abr_cost_create.argtypes = [C.POINTER(S["AbrQuadCostHost"]), C.c_int, C.POINTER(vp)]
     L.abr_cost_destroy.argtypes = [vp]
@@ -61,6 +62,7 @@ def lib():
     ps = [vp, vp, vp, vp, vp, C.c_ulonglong, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, vp, vp, vp, vp, vp]
     L.abr_predictive_sample_dev.argtypes = ps + [vp]
     L.abr_predictive_sample_host.argtypes = ps
+    L.abr_mpc_dev.argtypes = [vp, vp, vp, vp, C.c_ulonglong, C.c_int, C.c_int, C.c_float, C.c_int, vp, vp, vp, vp, vp]
     L.abr_forward_dev.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, vp]
     L.abr_env_step_dev.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp]
     L.abr_debug_forward_host.argtypes = [vp, fp, fp, fp, fp, C.c_char_p, fp, C.c_int, ip]

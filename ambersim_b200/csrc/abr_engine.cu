@@ -667,6 +667,24 @@ __global__ void k_gather_winner(const float* xs_all, const float* us_all, const 
   if (us_star) for (int i = threadIdx.x; i < nus; i += blockDim.x) us_star[(size_t)b * nus + i] = us_all[w * nus + i];
 }
 
+// one MPC tick's bookkeeping: plant state <- winner's state after its first control, logs, shifted guess
+__global__ void k_mpc_advance(const float* xs_star, const float* us_star, const int* best_idx, const float* best_cost, int N, int nx, int nu,
+                              int tick, float* x, float* us_guess, float* xs_log, float* us_log, float* cost_log, int* idx_log) {
+  const int i = threadIdx.x;
+  if (xs_log && tick == 0) for (int k = i; k < nx; k += blockDim.x) xs_log[k] = x[k];
+  for (int k = i; k < nx; k += blockDim.x) {
+    const float v = xs_star[nx + k];
+    x[k] = v;
+    if (xs_log) xs_log[(size_t)(tick + 1) * nx + k] = v;
+  }
+  for (int k = i; k < N * nu; k += blockDim.x) {
+    const int t = k / nu;
+    us_guess[k] = us_star[(t + 1 < N ? k + nu : k)];
+  }
+  if (us_log) for (int k = i; k < nu; k += blockDim.x) us_log[(size_t)tick * nu + k] = us_star[k];
+  if (i == 0) { if (cost_log) cost_log[tick] = best_cost[0]; if (idx_log) idx_log[tick] = best_idx[0]; }
+}
+
 // FP32 FMA-pipe peak: 8 independent FFMA chains per thread
 __global__ void __launch_bounds__(1024) k_ffma(float* out, int iters, float a, float b) {
   float x0 = threadIdx.x, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
@@ -841,6 +859,38 @@ int abr_model_set_lanes(AbrModel* m, int lanes) {
   if (lanes != 0 && lanes != 1 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32) return fail(ABR_EINVAL, "lanes must be 0, 1, 4, 8, 16 or 32");
   if (lanes == 1 && !m->lay.limb_ok) return fail(ABR_EUNSUPPORTED, "lanes = 1 pins the limb path, which this model/options are not eligible for");
   m->lanes = lanes;
+  return ABR_OK;
+}
+
+int abr_limb_plan_host(const AbrModelHost* host, int* info, int* lane_body, int cap, int* lane_own, int* lane_lvl) {
+  if (!host || !info) return fail(ABR_EINVAL, "abr_limb_plan_host: null argument");
+  HostModel hm;
+  copy_host_model(host, hm);
+  Layout L;
+  std::vector<float> mf; std::vector<int> mi;
+  int rc = build_blob(hm, true, L, mf, mi);
+  if (rc) return rc;
+  memset(info, 0, sizeof(int) * 8);
+  info[0] = L.limb_ok; info[5] = L.nefc; info[6] = L.ncon;
+  if (!L.limb_ok) return ABR_OK;
+  info[1] = L.lg2G; info[2] = L.lNL; info[3] = L.lNC; info[4] = L.l_mx;
+  const limb::Map mp{L.lNL, L.lNC};
+  const float* T = mf.data() + L.f_ltab;
+  auto geti = [&](int slot, int g) { int v; memcpy(&v, &T[(size_t)slot * limb::kStride + g], 4); return v; };
+  int used = 0;
+  for (int g = 0; g < limb::kStride; g++) {
+    bool any = false;
+    for (int p = 0; p <= L.lNL; p++) {
+      int body = -1;
+      if (p == 0) body = (g < (1 << L.lg2G)) ? 1 : -1;
+      else { const int d = geti(mp.ijnt(p) + 1, g); body = d >= 0 ? hm.dof_bodyid[d] : -1; any = any || d >= 0; }
+      if (lane_body && g * (L.lNL + 1) + p < cap) lane_body[g * (L.lNL + 1) + p] = body;
+    }
+    if (any) used++;
+    if (lane_own) lane_own[g] = geti(mp.ish(), g);
+    if (lane_lvl) lane_lvl[g] = geti(mp.ish() + 1, g);
+  }
+  info[7] = used;
   return ABR_OK;
 }
 
@@ -1043,6 +1093,27 @@ int abr_predictive_sample_host(AbrModel* m, const AbrCost* cost, const float* x0
   CK(cudaMemcpyAsync(best_idx, d_bi, sizeof(int) * B, cudaMemcpyDeviceToHost, m->stream));
   CK(cudaMemcpyAsync(best_cost, d_bc, sizeof(float) * B, cudaMemcpyDeviceToHost, m->stream));
   CK(cudaStreamSynchronize(m->stream));
+  return ABR_OK;
+}
+
+int abr_mpc_dev(AbrModel* m, const AbrCost* cost, float* x, float* us_guess, unsigned long long seed, int S, int N, float stdev, int nticks,
+                float* xs_log, float* us_log, float* cost_log, int* idx_log, void* stream) {
+  if (!m || !cost || !x || !us_guess) return fail(ABR_EINVAL, "abr_mpc_dev: null argument");
+  if (S <= 0 || N <= 0 || nticks < 0) return fail(ABR_EINVAL, "abr_mpc_dev: bad sizes");
+  CK(cudaSetDevice(m->device));
+  const int nx = m->lay.nx, nu = m->lay.nu;
+  int rc = m->s_out.ensure(sizeof(float) * ((size_t)(N + 1) * nx + (size_t)N * nu + 8));
+  if (rc) return rc;
+  float* xs_star = (float*)m->s_out.p; float* us_star = xs_star + (size_t)(N + 1) * nx;
+  float* best_cost = us_star + (size_t)N * nu; int* best_idx = (int*)(best_cost + 1);
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int tick = 0; tick < nticks; tick++) {
+    rc = abr_predictive_sample_dev(m, cost, x, us_guess, nullptr, seed + (unsigned long long)tick, 1, S, N, stdev, 0, S, xs_star, us_star,
+                                   best_idx, best_cost, nullptr, stream);
+    if (rc) return rc;
+    k_mpc_advance<<<1, 128, 0, st>>>(xs_star, us_star, best_idx, best_cost, N, nx, nu, tick, x, us_guess, xs_log, us_log, cost_log, idx_log);
+    CK(cudaGetLastError());
+  }
   return ABR_OK;
 }
 

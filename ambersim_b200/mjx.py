@@ -168,6 +168,28 @@ class Data:
         return dataclasses.replace(self, **kw)
 
 
+def limb_plan(mj_model: MjModel, opt: Optional[Option] = None) -> dict:
+    """The limb-path decomposition the engine derives for a model (host-only, no device needed):
+    eligibility, lanes per world, the serving kernel's (NL, NC), the sharing pattern and, per lane, the
+    body at each chain position with its owner / sharing-level bits. Debugging aid, not part of mjx."""
+    import ctypes as C
+
+    host, _keep = _abi.pack_model(mj_model, opt)
+    info = (C.c_int * 8)()
+    body = (C.c_int * (8 * 17))()
+    own, lvl = (C.c_int * 8)(), (C.c_int * 8)()
+    _lib.check(_lib.lib().abr_limb_plan_host(C.byref(host), info, body, len(body), own, lvl))
+    out = dict(eligible=bool(info[0]), lanes=1 << info[1], NL=info[2], NC=info[3], pattern=info[4], nefc=info[5], ncon=info[6],
+               lanes_used=info[7], paths=[], own=[], level=[])
+    if out["eligible"]:
+        n = info[2] + 1
+        for g in range(out["lanes"]):
+            out["paths"].append([body[g * n + p] for p in range(n)])
+            out["own"].append([(own[g] >> p) & 1 for p in range(n)])
+            out["level"].append([(lvl[g] >> (2 * p)) & 3 for p in range(n)])
+    return out
+
+
 def device_put(mj_model: MjModel) -> Model:
     """mjx.device_put(mj_model): flatten the MjModel into the structure-of-arrays the engine uploads."""
     if isinstance(mj_model, Model):

@@ -215,6 +215,30 @@ class VanillaPredictiveSampler(ShootingAlgorithm):
             return xs_star, us_star, info
         return xs_star, us_star
 
+    def mpc(self, params: VanillaPredictiveSamplerParams, nticks: int):
+        """Receding-horizon loop on the device (engine extension; how `optimize` is driven in practice): nticks x
+        {solve from the current state with key + tick; the plant takes one physics step under us*[0]; the guess
+        becomes us* shifted by one step}. Equivalent to calling `optimize` in a Python loop, without the host
+        round trips. Returns (xs (nticks+1, nx) visited states, us (nticks, nu) applied controls, info)."""
+        m, L = self.model, _lib.lib()
+        if not isinstance(self.cost_function, StaticGoalQuadraticCost):
+            raise NotImplementedError("mpc() needs a StaticGoalQuadraticCost (fused on the device)")
+        dev = params.us_guess.device if isinstance(params.us_guess, torch.Tensor) and params.us_guess.is_cuda else mjx._dev()
+        f = dict(dtype=torch.float32, device=dev)
+        ug = torch.as_tensor(params.us_guess, **f).clone().contiguous()
+        x = torch.as_tensor(params.x0, **f).clone().contiguous()
+        if ug.dim() != 2 or x.dim() != 1:
+            raise ValueError("mpc() takes one problem: x0 (nx,), us_guess (N, nu)")
+        N = ug.shape[0]
+        xs_log, us_log = torch.empty((nticks + 1, m.nx), **f), torch.empty((nticks, m.nu), **f)
+        cost_log, idx_log = torch.empty((nticks,), **f), torch.empty((nticks,), dtype=torch.int32, device=dev)
+        h = m.handle(dev.index or 0)
+        ch = self.cost_function.device_cost(dev.index or 0).ptr
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(L.abr_mpc_dev(h.ptr, ch, _ptr(x), _ptr(ug), _seed_of(params.key), int(self.nsamples), N, float(self.stdev), int(nticks),
+                                 _ptr(xs_log), _ptr(us_log), _ptr(cost_log), _ptr(idx_log), stream))
+        return xs_log, us_log, dict(best_cost=cost_log, best_idx=idx_log, us_guess=ug, x=x)
+
     def _optimize_generic(self, params: VanillaPredictiveSamplerParams, return_info: bool):
         """User-defined CostFunction: sample + clip on the host framework, roll every sample on the
         engine, evaluate `cost_function.cost` on the returned trajectories (reference order,

@@ -185,6 +185,10 @@ def extra_configs(mj, m, cf, q0, torch, device, stream, L, peak_tf):
         ps = VanillaPredictiveSampler(model=m, cost_function=cf, nsamples=S, stdev=0.1)
         sweep[str(S)] = _timed(torch, stream, lambda: ps.optimize(prm), 3)
     ex["c4_solve_ms_by_samples_x32"] = sweep
+    ps = VanillaPredictiveSampler(model=m, cost_function=cf, nsamples=4096, stdev=0.1)
+    ticks = 50
+    ex["mpc_4096x32_ms_per_tick"] = {"value": _timed(torch, stream, lambda: ps.mpc(prm, ticks), 2) / ticks,
+                                     "note": "abr_mpc_dev: solve + plant step + guess shift on the device, 50 ticks, no host round trips"}
     E, T = 8192, 200
     qpos0 = torch.tensor(mj.key_qpos("home"), **f).repeat(E, 1)
     qpos0[:, 7:] += (torch.rand((E, mj.nq - 7), generator=g, **f) - 0.5) * 2 * JITTER

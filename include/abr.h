@@ -212,6 +212,13 @@ int abr_model_info(const AbrModel* m, int* ncon, int* ne, int* nl, int* nefc, in
  * equalities; otherwise the generic kernels), 1 = limb kernels or ABR_EUNSUPPORTED,
  * 4/8/16/32 = generic kernels with that many lanes per world */
 int abr_model_set_lanes(AbrModel* m, int lanes);
+/* Host-only (no device needed): the limb-path plan the engine derives for a model.
+ * info[8] = {eligible, log2(lanes per world), chain length NL of the serving kernel, contacts per path NC,
+ *            sharing pattern (2 bits per chain position), nefc, ncon, lanes actually carrying a path};
+ * lane_body[8*(NL+1)] = body id at (lane, chain position) or -1 (padding / dummy lane);
+ * lane_own[8] / lane_lvl[8] = per-lane owner bits and sharing levels (2 bits per position).
+ * Arrays may be NULL; cap = ints available in lane_body. */
+int abr_limb_plan_host(const AbrModelHost* host, int* info, int* lane_body, int cap, int* lane_own, int* lane_lvl);
 
 int abr_cost_create(const AbrQuadCostHost* host, int device, AbrCost** out);
 int abr_cost_destroy(AbrCost* c);
@@ -269,6 +276,17 @@ int abr_env_step_dev(AbrModel* m, float* qpos, float* qvel, float* qacc_warmstar
 int abr_debug_forward_host(AbrModel* m, const float* qpos, const float* qvel, const float* ctrl,
                            const float* qacc_warmstart, const char* name, float* out, int cap,
                            int* n);
+
+/* ---- receding-horizon loop on the device (how `optimize` is driven in practice) --------
+ * nticks x { predictive-sampling solve (as abr_predictive_sample_dev with B = 1, seed + tick) from the
+ * current state x; the plant takes ONE physics step under us*[0] (= row 1 of the winner's trajectory);
+ * the next guess is us* shifted by one step with its last control repeated }. No host round trip
+ * between ticks: every launch is stream-ordered.
+ * x [nx] in/out, us_guess [N,nu] in/out; logs (nullable): xs_log [nticks+1,nx] (row 0 = initial x),
+ * us_log [nticks,nu] applied controls, cost_log [nticks] winner costs, idx_log [nticks] winner samples. */
+int abr_mpc_dev(AbrModel* m, const AbrCost* cost, float* x, float* us_guess, unsigned long long seed,
+                int S, int N, float stdev, int nticks, float* xs_log, float* us_log, float* cost_log,
+                int* idx_log, void* stream);
 
 /* FP32 FMA-pipe peak microbenchmark (roofline denominator): returns TFLOP/s */
 int abr_ffma_peak(int device, double* tflops, double* ms);

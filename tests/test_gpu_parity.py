@@ -28,7 +28,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 STAGES = ["xpos", "xquat", "xipos", "cinert", "cdof", "qM", "cvel", "cdof_dot", "contact_dist", "contact_pos", "contact_frame",
           "qfrc_smooth", "qacc_smooth", "efc_J", "efc_D", "efc_aref", "qacc", "efc_force", "qfrc_constraint"]
-MODEL_KEY = {"barkour": "home", "biped": "stand", "tripod": "home"}
+MODEL_KEY = {"barkour": "home", "biped": "stand", "tripod": "home", "tripod3": "home"}
 BH_OPT = dict(timestep=0.002, iterations=1, ls_iterations=4, integrator=0, solver=2, disableflags=16)  # the reference test's options
 
 
@@ -37,7 +37,7 @@ def t32(a):
 
 
 def sample_state(mj, name, rng):
-    key = {"barkour": "home", "biped": "stand", "tripod": "home"}.get(name)
+    key = MODEL_KEY.get(name)
     q = mj.key_qpos(key) if key else mj.qpos0.copy()
     if name == "bh280":
         q = q + rng.uniform(0.0, 0.5, mj.nq)
@@ -75,7 +75,7 @@ def test_forward_stage_parity(load_model, name):
             assert np.abs(r - g).max() <= 2e-4 * max(1e-6, np.abs(r).max()), f
 
 
-@pytest.mark.parametrize("name", ["pendulum", "bh280", "barkour", "biped", "tripod"])
+@pytest.mark.parametrize("name", ["pendulum", "bh280", "barkour", "biped", "tripod", "tripod3"])
 @pytest.mark.parametrize("variant", ["default", "rk4", "cg", "eulerdamp", "converged", "nowarm"])
 def test_single_step_parity_option_variants(load_model, name, variant):
     opt = dict(default={}, rk4=dict(integrator=1), cg=dict(solver=1, iterations=8, ls_iterations=10),
@@ -121,7 +121,7 @@ def test_contact_free_rollout_parity(load_model, name, lanes):
     assert np.allclose(costs, quad_cost(ref, us, eye, 10 * eye, 0.01 * np.eye(mj.nu), 0.0), rtol=1e-3)
 
 
-@pytest.mark.parametrize("name", ["barkour", "biped", "tripod"])
+@pytest.mark.parametrize("name", ["barkour", "biped", "tripod", "tripod3"])
 @pytest.mark.parametrize("lanes", [1, 4, 8, 16, 32])  # 1 = the limb (path-decomposed) kernels, 4..32 = generic group sizes
 def test_contact_rollout_teacher_forced(load_model, name, lanes):
     mj, m, o = model_with(load_model, name)
@@ -384,7 +384,7 @@ def test_ffma_peak_is_plausible():
 
 
 # ------------------------------------------------------------------ limb (path-decomposed) kernels
-@pytest.mark.parametrize("name", ["barkour", "biped", "tripod"])
+@pytest.mark.parametrize("name", ["barkour", "biped", "tripod", "tripod3"])
 def test_limb_path_is_default_and_matches_generic(load_model, name, monkeypatch):
     """Eligible models run on the limb kernels by default (lanes = 0 or 1); pinning a generic group size
     gives the same trajectory and costs up to float32 rounding, and the general-sharing build of the limb
@@ -475,3 +475,29 @@ def test_host_rollout_pipelined_slices_equal_one_launch(load_model, monkeypatch)
     assert np.array_equal(res["sliced"][0], res["single"][0])
     assert np.array_equal(np.asarray(res["sliced"][1]), np.asarray(res["single"][1]))
     assert np.isfinite(res["sliced"][0]).all()
+
+
+@pytest.mark.parametrize("name", ["barkour", "bh280"])
+def test_mpc_loop_on_device_equals_python_loop(load_model, name):
+    """abr_mpc_dev (solve, step the plant under us*[0], shift the guess; no host round trips) reproduces the
+    Python loop over `optimize` bit for bit."""
+    mj, m, _ = model_with(load_model, name)
+    nx = mj.nq + mj.nv
+    x0 = np.concatenate([mj.key_qpos("home"), np.zeros(mj.nv)]) if name == "barkour" else 0.1 * np.ones(nx)
+    ug = np.tile(mj.key_ctrl("home"), (8, 1)) if name == "barkour" else np.zeros((8, mj.nu))
+    xg = x0.copy()
+    xg[0] += 0.3  # ask for some motion
+    cf = StaticGoalQuadraticCost(np.eye(nx), 10 * np.eye(nx), 0.01 * np.eye(mj.nu), xg)
+    ps = VanillaPredictiveSampler(model=m, cost_function=cf, nsamples=48, stdev=0.1)
+    T = 6
+    xs_d, us_d, info = ps.mpc(VanillaPredictiveSamplerParams(key=11, x0=t32(x0), us_guess=t32(ug)), T)
+    x, g = t32(x0), t32(ug)
+    xs_p, us_p, idx_p = [x.clone()], [], []
+    for t in range(T):
+        xs, us, inf = ps.optimize(VanillaPredictiveSamplerParams(key=11 + t, x0=x, us_guess=g), return_info=True)
+        x = xs[1].clone()
+        g = torch.cat((us[1:], us[-1:]), dim=0)
+        xs_p.append(x.clone()); us_p.append(us[0].clone()); idx_p.append(int(inf["best_idx"]))
+    assert torch.equal(xs_d, torch.stack(xs_p)) and torch.equal(us_d, torch.stack(us_p))
+    assert info["best_idx"].cpu().tolist() == idx_p
+    assert torch.equal(info["us_guess"], g) and torch.equal(info["x"], x)

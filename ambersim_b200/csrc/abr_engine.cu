@@ -574,6 +574,17 @@ static int build_blob(const HostModel& m, bool alias, Layout& L, std::vector<flo
         for (int i = 0; i < 3; i++) { setf(sc + 24 + i, g, fa[i]); setf(sc + 27 + i, g, fb[i]); setf(sc + 30 + i, g, fcx[i]); }
         seti(mp.icon(c), g, bdepth[m.geom_bodyid[g2]]); seti(mp.icon(c) + 1, g, m.pair_condim[p]);
       }
+      // contact-body form: each lane's contacts all on its leaf body, against one plane
+      L.l_cb = 1;
+      {
+        std::vector<int> lane_plane(limb::kStride, -1);
+        for (int ci = 0; ci < L.ncon; ci++) {
+          const int p = con_pair[ci], g1 = m.pair_geom1[p], b2 = m.geom_bodyid[m.pair_geom2[p]], g = con_lane[ci];
+          if (childnum[b2] != 0) L.l_cb = 0;                                  // not a leaf
+          if (lane_plane[g] >= 0 && lane_plane[g] != g1) L.l_cb = 0;          // a second plane
+          lane_plane[g] = g1;
+        }
+      }
       while (P.f.size() % 4) P.f.push_back(0.f);
       L.limb_ok = 1; L.lNL = NLi; L.lNC = NCi; L.l_mx = mxbits; L.l_mass = (float)mass;
       L.lg2G = 0;
@@ -729,7 +740,7 @@ static int launch_rollout(const AbrModel* m, const Layout& L, const RolloutArgs&
   if (use_limb(m, L, a.cost.enabled && !a.cost.diag, false)) {
     const bool spec = getenv("ABR_LIMB_GENERAL") == nullptr;  // compile-time sharing patterns: 2 = flat 4 lanes, 86 = biped
     if (L.lNL == 3 && L.lNC == 1) return launch_result(spec && L.l_mx == 2 ? launch_limb_rollout_3_1_f2(L, a, st) : launch_limb_rollout_3_1_g(L, a, st));
-    if (L.lNL == 6 && L.lNC == 4) return launch_result(spec && L.l_mx == 86 ? launch_limb_rollout_6_4_b(L, a, st) : launch_limb_rollout_6_4_g(L, a, st));
+    if (L.lNL == 6 && L.lNC == 4) return launch_result(spec && L.l_mx == 86 && L.l_cb ? launch_limb_rollout_6_4_b(L, a, st) : launch_limb_rollout_6_4_g(L, a, st));
     return fail(ABR_ECAPACITY, "no compiled limb kernel for this model");
   }
   LaunchCfg cfg{m->max_smem};
@@ -745,7 +756,7 @@ static int launch_env(const AbrModel* m, const Layout& L, const EnvArgs& a, cuda
   if (use_limb(m, L, false, a.dbg != nullptr)) {
     const bool spec = getenv("ABR_LIMB_GENERAL") == nullptr;
     if (L.lNL == 3 && L.lNC == 1) return launch_result(spec && L.l_mx == 2 ? launch_limb_env_3_1_f2(L, a, st) : launch_limb_env_3_1_g(L, a, st));
-    if (L.lNL == 6 && L.lNC == 4) return launch_result(spec && L.l_mx == 86 ? launch_limb_env_6_4_b(L, a, st) : launch_limb_env_6_4_g(L, a, st));
+    if (L.lNL == 6 && L.lNC == 4) return launch_result(spec && L.l_mx == 86 && L.l_cb ? launch_limb_env_6_4_b(L, a, st) : launch_limb_env_6_4_g(L, a, st));
     return fail(ABR_ECAPACITY, "no compiled limb kernel for this model");
   }
   LaunchCfg cfg{m->max_smem};

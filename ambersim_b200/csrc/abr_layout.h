@@ -77,6 +77,7 @@ struct Layout {
   int l_mx;         // 2 bits per chain position: log2 of the largest lane group sharing a body there
   int f_ltab;       // float-pool offset of the per-lane table (limb::Map, row stride limb::kStride)
   float l_mass;     // total mass of the tree (subtree CoM denominator)
+  int l_cb;         // every lane's contacts sit on the lane's leaf body and touch one plane (contact-body form)
   int w_rk;         // RK4 save area: qpos0[nq] qvel0[nv] warm0[nv] sv[nv] sa[nv] kq[nv]
   int world_stride; // floats per world
 };

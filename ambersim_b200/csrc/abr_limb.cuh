@@ -117,6 +117,10 @@ template <int K> __device__ __forceinline__ float normalize_k(float (&x)[K]) {
   return nrm;
 }
 static __device__ __noinline__ float pow_cold(float x, float p) { return powf(x, p); }
+// the sampler's counter-based normal: out of line so the shoot-mode loop body does not carry three copies of it
+static __device__ __noinline__ float philox_normal_ool(unsigned long long seed, uint32_t sample, uint32_t problem, uint32_t index) {
+  return philox_normal(seed, sample, problem, index);
+}
 
 // ------------------------------------------------------------------------------ dense local L'DL
 // A: packed lower triangle in "share" form on shared rows. Leaves-first elimination (MuJoCo's
@@ -246,35 +250,63 @@ __device__ __forceinline__ void row_kbi(const float* prm /* smem, stride kStride
 struct LSP { float alpha, cost, d0, d1; };
 
 // constraint rows of one lane: NL joint-limit rows (chain dof 6 + r), then 4 pyramid rows per contact slot
-template <int NL, int NC> struct Rows {
+// CB ("contact body") = every contact of a lane sits on the lane's leaf body and touches one plane: the contact
+// Jacobian is then J_c = [g_c ; fr]' cdof with g_c[k] = off_c x fr[k], so instead of the 3 x N basis per contact
+// the lane keeps 9 floats per contact and works through 6-vectors (body twist, total wrench, a 6x6 weight).
+template <int NL, int NC, bool CB> struct Rows {
   static constexpr int N = 6 + NL, NR = NL + 4 * NC, NCC = NC > 0 ? NC : 1;
   float D[NR], aref[NR], lsg[NL];
-  float B[NCC][3][N];       // contact Jacobian basis: normal, tangent 1, tangent 2
-  float mu1[NCC], mu2[NCC]; // 0 on condim-1 slots
+  float B[CB ? 1 : NCC][3][CB ? 1 : N];  // contact Jacobian basis: normal, tangent 1, tangent 2
+  float g[CB ? NCC : 1][3][3];           // CB: off_c x frame_k
+  float fr[3][3];                        // CB: the plane's contact frame
+  float mu1[NCC], mu2[NCC];              // 0 on condim-1 slots
 };
+// CB: per-contact (normal, tangent1, tangent2) components of J x from the leaf body's twist V = sum_d cdof[d] x[d]
+template <int NL, int NC> __device__ __forceinline__ void contact_bv(const Rows<NL, NC, true>& R, const float (&cdof)[6 + NL][6], const float (&x)[6 + NL],
+                                                                     float (&bv)[NC > 0 ? NC : 1][3]) {
+  float V[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int d = 0; d < 6 + NL; d++)
+#pragma unroll
+    for (int i = 0; i < 6; i++) V[i] = fmaf(cdof[d][i], x[d], V[i]);
+  float lin[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) lin[k] = R.fr[k][0] * V[3] + R.fr[k][1] * V[4] + R.fr[k][2] * V[5];
+#pragma unroll
+  for (int c = 0; c < NC; c++)
+#pragma unroll
+    for (int k = 0; k < 3; k++) bv[c][k] = fmaf(R.g[c][k][0], V[0], fmaf(R.g[c][k][1], V[1], fmaf(R.g[c][k][2], V[2], lin[k])));
+}
 // out = J x for the structured Jacobian
-template <int NL, int NC> __device__ __forceinline__ void mul_j(const Rows<NL, NC>& R, const float (&x)[6 + NL], float (&out)[NL + 4 * NC]) {
+template <int NL, int NC, bool CB> __device__ __forceinline__ void mul_j(const Rows<NL, NC, CB>& R, const float (&cdof)[6 + NL][6], const float (&x)[6 + NL],
+                                                                   float (&out)[NL + 4 * NC]) {
   constexpr int N = 6 + NL;
 #pragma unroll
   for (int r = 0; r < NL; r++) out[r] = R.lsg[r] * x[6 + r];
+  float bv[NC > 0 ? NC : 1][3];
+  if constexpr (CB) {
+    contact_bv<NL, NC>(R, cdof, x, bv);
+  } else {
+#pragma unroll
+    for (int c = 0; c < NC; c++)
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        float t = 0.f;
+#pragma unroll
+        for (int d = 0; d < N; d++) t = fmaf(R.B[c][k][d], x[d], t);
+        bv[c][k] = t;
+      }
+  }
 #pragma unroll
   for (int c = 0; c < NC; c++) {
-    float bv[3];
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-      float t = 0.f;
-#pragma unroll
-      for (int d = 0; d < N; d++) t = fmaf(R.B[c][k][d], x[d], t);
-      bv[k] = t;
-    }
-    out[NL + 4 * c + 0] = fmaf(R.mu1[c], bv[1], bv[0]);
-    out[NL + 4 * c + 1] = fmaf(-R.mu1[c], bv[1], bv[0]);
-    out[NL + 4 * c + 2] = fmaf(R.mu2[c], bv[2], bv[0]);
-    out[NL + 4 * c + 3] = fmaf(-R.mu2[c], bv[2], bv[0]);
+    out[NL + 4 * c + 0] = fmaf(R.mu1[c], bv[c][1], bv[c][0]);
+    out[NL + 4 * c + 1] = fmaf(-R.mu1[c], bv[c][1], bv[c][0]);
+    out[NL + 4 * c + 2] = fmaf(R.mu2[c], bv[c][2], bv[c][0]);
+    out[NL + 4 * c + 3] = fmaf(-R.mu2[c], bv[c][2], bv[c][0]);
   }
 }
 // cost = 0.5 sum_active D Jaref^2 + 0.5 (Ma - fs).(a - as); uniform over the world's lanes
-template <int NL, int NC, class SH> __device__ __forceinline__ float solver_cost(const Rows<NL, NC>& R, const SH& S, const float (&x)[6 + NL], const float (&Mx)[6 + NL],
+template <int NL, int NC, bool CB, class SH> __device__ __forceinline__ float solver_cost(const Rows<NL, NC, CB>& R, const SH& S, const float (&x)[6 + NL], const float (&Mx)[6 + NL],
                                                                        const float (&Jx)[NL + 4 * NC], const float (&fs)[6 + NL], const float (&as)[6 + NL], float& gauss) {
   float sc = 0.f, g = 0.f;
 #pragma unroll
@@ -306,7 +338,7 @@ template <int NR> __device__ __forceinline__ LSP ls_eval(const float (&Jaref)[NR
 
 // mjx.forward for one lane: on exit s.a = qacc, s.warm = qacc; M, fs, fc are returned for the
 // implicit-damping Euler variant.
-template <int NL, int NC, int LGC>
+template <int NL, int NC, int LGC, bool CB>
 __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, float (&M)[(6 + NL) * (7 + NL) / 2], float (&fs)[6 + NL], float (&fc)[6 + NL]) {
   constexpr int NP = NL + 1, N = 6 + NL, NTRI = N * (N + 1) / 2, NR = NL + 4 * NC;
   constexpr Map mp{NL, NC};
@@ -426,7 +458,7 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
     for (int i = 0; i < 3; i++) { cdof[d][i] = hinge ? xax[p][i] : 0.f; cdof[d][3 + i] = hinge ? cr[i] : xax[p][i]; }
   }
   // ---------------------------------------------------------------- collision (plane - sphere) + Jacobian basis
-  Rows<NL, NC> R;
+  Rows<NL, NC, CB> R;
   float cdist[NC > 0 ? NC : 1];
 #pragma unroll
   for (int c = 0; c < NC; c++) {
@@ -457,17 +489,26 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
     cdist[c] = dist;
     const float kk = rad + 0.5f * dist;
     const float off[3] = {sp[0] - n[0] * kk - com[0], sp[1] - n[1] * kk - com[1], sp[2] - n[2] * kk - com[2]};
-    const int ld = (pc < 0) ? -1 : 5 + pc;
-#pragma unroll
-    for (int d = 0; d < N; d++) {
-      float cr[3];
-      v_cross(cdof[d], off, cr);
-      const float jp[3] = {cdof[d][3] + cr[0], cdof[d][4] + cr[1], cdof[d][5] + cr[2]};
-      const bool on = d <= ld;
+    if constexpr (CB) {
 #pragma unroll
       for (int k = 0; k < 3; k++) {
         const float fr[3] = {LTF(mp.con(c) + 24 + 3 * k), LTF(mp.con(c) + 25 + 3 * k), LTF(mp.con(c) + 26 + 3 * k)};
-        R.B[c][k][d] = on ? v_dot(fr, jp) : 0.f;
+        v_cross(off, fr, R.g[c][k]);
+        if (c == 0) { R.fr[k][0] = fr[0]; R.fr[k][1] = fr[1]; R.fr[k][2] = fr[2]; }
+      }
+    } else {
+      const int ld = (pc < 0) ? -1 : 5 + pc;
+#pragma unroll
+      for (int d = 0; d < N; d++) {
+        float cr[3];
+        v_cross(cdof[d], off, cr);
+        const float jp[3] = {cdof[d][3] + cr[0], cdof[d][4] + cr[1], cdof[d][5] + cr[2]};
+        const bool on = d <= ld;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          const float fr[3] = {LTF(mp.con(c) + 24 + 3 * k), LTF(mp.con(c) + 25 + 3 * k), LTF(mp.con(c) + 26 + 3 * k)};
+          R.B[c][k][d] = on ? v_dot(fr, jp) : 0.f;
+        }
       }
     }
   }
@@ -621,46 +662,54 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
     R.lsg[r] = active ? sg : 0.f;
     row_kbi(&LTF(mp.jnt(p) + 14), pos, sg * s.v[d], LTF(mp.jnt(p) + 14 + 7), active, R.D[r], R.aref[r]);
   }
+  {
+    float bva[NC > 0 ? NC : 1][3];
+    if constexpr (CB) {
+      contact_bv<NL, NC>(R, cdof, s.v, bva);
+    } else {
 #pragma unroll
-  for (int c = 0; c < NC; c++) {
-    const float* prm = &LTF(mp.con(c) + 4);
-    const float pos = cdist[c] - prm[13 * kStride];
-    const bool act0 = (pos < 0.f) && (LTI(mp.icon(c)) >= 0);
-    const bool pyr = LTI(mp.icon(c) + 1) == 3;
-    float bv[3];
+      for (int c = 0; c < NC; c++)
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
-      float t = 0.f;
+        for (int k = 0; k < 3; k++) {
+          float t = 0.f;
 #pragma unroll
-      for (int d = 0; d < N; d++) t = fmaf(R.B[c][k][d], s.v[d], t);
-      bv[k] = t;
+          for (int d = 0; d < N; d++) t = fmaf(R.B[c][k][d], s.v[d], t);
+          bva[c][k] = t;
+        }
     }
 #pragma unroll
-    for (int sub = 0; sub < 4; sub++) {
-      const int r = NL + 4 * c + sub;
-      const float mu = (sub < 2) ? R.mu1[c] : R.mu2[c];
-      const float jvel = bv[0] + ((sub & 1) ? -mu : mu) * bv[1 + (sub >> 1)];
-      const float invw = (sub < 2 || !pyr) ? prm[7 * kStride] : prm[10 * kStride];
-      row_kbi(prm, pos, jvel, invw, act0 && (pyr || sub == 0), R.D[r], R.aref[r]);
+    for (int c = 0; c < NC; c++) {
+      const float* prm = &LTF(mp.con(c) + 4);
+      const float pos = cdist[c] - prm[13 * kStride];
+      const bool act0 = (pos < 0.f) && (LTI(mp.icon(c)) >= 0);
+      const bool pyr = LTI(mp.icon(c) + 1) == 3;
+#pragma unroll
+      for (int sub = 0; sub < 4; sub++) {
+        const int r = NL + 4 * c + sub;
+        const float mu = (sub < 2) ? R.mu1[c] : R.mu2[c];
+        const float jvel = bva[c][0] + ((sub & 1) ? -mu : mu) * bva[c][1 + (sub >> 1)];
+        const float invw = (sub < 2 || !pyr) ? prm[7 * kStride] : prm[10 * kStride];
+        row_kbi(prm, pos, jvel, invw, act0 && (pyr || sub == 0), R.D[r], R.aref[r]);
+      }
     }
   }
   // ---------------------------------------------------------------- solver.solve (Newton)
   float Ma[N], Jaref[NR];
   float gauss, cost;
   mul_m<N>(M, as, Ma, S);
-  mul_j<NL, NC>(R, as, Jaref);
+  mul_j<NL, NC, CB>(R, cdof, as, Jaref);
 #pragma unroll
   for (int r = 0; r < NR; r++) Jaref[r] -= R.aref[r];
-  cost = solver_cost<NL, NC>(R, S, as, Ma, Jaref, fs, as, gauss);
+  cost = solver_cost<NL, NC, CB>(R, S, as, Ma, Jaref, fs, as, gauss);
 #pragma unroll
   for (int d = 0; d < N; d++) s.a[d] = as[d];
   if (!(C.disableflags & ABR_DSBL_WARMSTART)) {
     float Mw[N], Jw[NR], g2;
     mul_m<N>(M, s.warm, Mw, S);
-    mul_j<NL, NC>(R, s.warm, Jw);
+    mul_j<NL, NC, CB>(R, cdof, s.warm, Jw);
 #pragma unroll
     for (int r = 0; r < NR; r++) Jw[r] -= R.aref[r];
-    const float c2 = solver_cost<NL, NC>(R, S, s.warm, Mw, Jw, fs, as, g2);
+    const float c2 = solver_cost<NL, NC, CB>(R, S, s.warm, Mw, Jw, fs, as, g2);
     const bool use = c2 < cost;
     cost = use ? c2 : cost; gauss = use ? g2 : gauss;
 #pragma unroll
@@ -679,15 +728,32 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
       for (int d = 0; d < N; d++) up[d] = 0.f;
 #pragma unroll
       for (int r = 0; r < NL; r++) { const float f = (Jaref[r] < 0.f) ? -R.D[r] * Jaref[r] : 0.f; up[6 + r] = R.lsg[r] * f; }
+      float Wt[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, Fl[3] = {0.f, 0.f, 0.f};  // CB: total wrench on the leaf body
 #pragma unroll
       for (int c = 0; c < NC; c++) {
         float f[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) { const int r = NL + 4 * c + k; f[k] = (Jaref[r] < 0.f) ? -R.D[r] * Jaref[r] : 0.f; }
         const float mu1 = R.mu1[c], mu2 = R.mu2[c];
-        const float F0 = f[0] + f[1] + f[2] + f[3], F1 = mu1 * (f[0] - f[1]), F2 = mu2 * (f[2] - f[3]);
+        const float F[3] = {f[0] + f[1] + f[2] + f[3], mu1 * (f[0] - f[1]), mu2 * (f[2] - f[3])};
+        if constexpr (CB) {
 #pragma unroll
-        for (int d = 0; d < N; d++) up[d] += R.B[c][0][d] * F0 + R.B[c][1][d] * F1 + R.B[c][2][d] * F2;
+          for (int k = 0; k < 3; k++) {
+            Fl[k] += F[k];
+#pragma unroll
+            for (int i = 0; i < 3; i++) Wt[i] = fmaf(R.g[c][k][i], F[k], Wt[i]);
+          }
+        } else {
+#pragma unroll
+          for (int d = 0; d < N; d++) up[d] += R.B[c][0][d] * F[0] + R.B[c][1][d] * F[1] + R.B[c][2][d] * F[2];
+        }
+      }
+      if constexpr (CB && NC > 0) {
+#pragma unroll
+        for (int i = 0; i < 3; i++) Wt[3 + i] = R.fr[0][i] * Fl[0] + R.fr[1][i] * Fl[1] + R.fr[2][i] * Fl[2];
+#pragma unroll
+        for (int d = 0; d < N; d++)
+          up[d] += cdof[d][0] * Wt[0] + cdof[d][1] * Wt[1] + cdof[d][2] * Wt[2] + cdof[d][3] * Wt[3] + cdof[d][4] * Wt[4] + cdof[d][5] * Wt[5];
       }
 #pragma unroll
       for (int d = 0; d < N; d++) {
@@ -708,6 +774,11 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
         if (j <= i) H[TR(i, j)] = S.o(PD(i)) ? M[TR(i, j)] : 0.f;
 #pragma unroll
     for (int r = 0; r < NL; r++) H[TR(6 + r, 6 + r)] += (Jaref[r] < 0.f) ? R.D[r] * R.lsg[r] * R.lsg[r] : 0.f;
+    float K[21];  // CB: 6x6 weight of the leaf body's twist, sum_c [g_c; fr] W_c [g_c; fr]'
+    if constexpr (CB) {
+#pragma unroll
+      for (int e = 0; e < 21; e++) K[e] = 0.f;
+    }
 #pragma unroll
     for (int c = 0; c < NC; c++) {
       const int r0 = NL + 4 * c;
@@ -716,13 +787,48 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
       const float w2 = (Jaref[r0 + 2] < 0.f) ? R.D[r0 + 2] : 0.f, w3 = (Jaref[r0 + 3] < 0.f) ? R.D[r0 + 3] : 0.f;
       const float W00 = w0 + w1 + w2 + w3, W01 = mu1 * (w0 - w1), W02 = mu2 * (w2 - w3);
       const float W11 = mu1 * mu1 * (w0 + w1), W22 = mu2 * mu2 * (w2 + w3);
+      if constexpr (CB) {
+        float w[3][6], U[3][6];
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+#pragma unroll
+          for (int i = 0; i < 3; i++) { w[k][i] = R.g[c][k][i]; w[k][3 + i] = R.fr[k][i]; }
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+          U[0][i] = W00 * w[0][i] + W01 * w[1][i] + W02 * w[2][i];
+          U[1][i] = W01 * w[0][i] + W11 * w[1][i];
+          U[2][i] = W02 * w[0][i] + W22 * w[2][i];
+        }
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+#pragma unroll
+          for (int j = 0; j < 6; j++)
+            if (j <= i) K[TR(i, j)] += w[0][i] * U[0][j] + w[1][i] * U[1][j] + w[2][i] * U[2][j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+          const float b0 = R.B[c][0][j], b1 = R.B[c][1][j], b2 = R.B[c][2][j];
+          const float o0 = W00 * b0 + W01 * b1 + W02 * b2, o1 = W01 * b0 + W11 * b1, o2 = W02 * b0 + W22 * b2;
+#pragma unroll
+          for (int i = 0; i < N; i++)
+            if (i >= j) H[TR(i, j)] += R.B[c][0][i] * o0 + R.B[c][1][i] * o1 + R.B[c][2][i] * o2;
+        }
+      }
+    }
+    if constexpr (CB && NC > 0) {
 #pragma unroll
       for (int j = 0; j < N; j++) {
-        const float b0 = R.B[c][0][j], b1 = R.B[c][1][j], b2 = R.B[c][2][j];
-        const float o0 = W00 * b0 + W01 * b1 + W02 * b2, o1 = W01 * b0 + W11 * b1, o2 = W02 * b0 + W22 * b2;
+        float KC[6];
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+          float t = 0.f;
+#pragma unroll
+          for (int b = 0; b < 6; b++) t = fmaf(K[a >= b ? TR(a, b) : TR(b, a)], cdof[j][b], t);
+          KC[a] = t;
+        }
 #pragma unroll
         for (int i = 0; i < N; i++)
-          if (i >= j) H[TR(i, j)] += R.B[c][0][i] * o0 + R.B[c][1][i] * o1 + R.B[c][2][i] * o2;
+          if (i >= j) H[TR(i, j)] += cdof[i][0] * KC[0] + cdof[i][1] * KC[1] + cdof[i][2] * KC[2] + cdof[i][3] * KC[3] + cdof[i][4] * KC[4] + cdof[i][5] * KC[5];
       }
     }
     ldl_factor<N>(H, hD, S);
@@ -745,7 +851,7 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
     for (int d = 0; d < N; d++) search[d] = -mg[d];
     // ---- exact line search (solver._linesearch)
     mul_m<N>(M, search, mv, S);
-    mul_j<NL, NC>(R, search, jv);
+    mul_j<NL, NC, CB>(R, cdof, search, jv);
     float sn = 0.f, sMa = 0.f, sq = 0.f, smv = 0.f;
 #pragma unroll
     for (int d = 0; d < N; d++) {
@@ -799,7 +905,7 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
     for (int r = 0; r < NR; r++) Jaref[r] = fmaf(jv[r], alpha, Jaref[r]);
     if (C.iterations != 1) {
       float g2;
-      const float c2 = solver_cost<NL, NC>(R, S, s.a, Ma, Jaref, fs, as, g2);
+      const float c2 = solver_cost<NL, NC, CB>(R, S, s.a, Ma, Jaref, fs, as, g2);
       if (live) { prev_cost = cost; cost = c2; gauss = g2; }
     }
   }
@@ -901,7 +1007,7 @@ template <int NL, int NC, int LGC> __device__ __forceinline__ void store_x(const
 }
 
 // shoot (shooting.py:22-48) / the sampler's rollouts (shooting.py:140-153) on the limb path
-template <int NL, int NC, int LGC>
+template <int NL, int NC, int LGC, bool CB>
 __global__ void __launch_bounds__(kTPB, ABR_LIMB_MINB) k_limb_rollout(const __grid_constant__ Layout L, const __grid_constant__ RolloutArgs A) {
   extern __shared__ __align__(16) float smem[];
   constexpr Map mp{NL, NC};
@@ -969,7 +1075,7 @@ __global__ void __launch_bounds__(kTPB, ABR_LIMB_MINB) k_limb_rollout(const __gr
             float nz = 0.f;
             if (sample > 0) {
               if (A.noise) nz = A.noise[(((size_t)prob * (A.S_total - 1) + (sample - 1)) * Nh + t) * nu + ga];
-              else nz = philox_normal(A.seed, (uint32_t)sample, (uint32_t)prob, (uint32_t)(t * nu + ga));
+              else nz = philox_normal_ool(A.seed, (uint32_t)sample, (uint32_t)prob, (uint32_t)(t * nu + ga));
             }
             const float vv = A.us[(size_t)prob * A.us_stride + (size_t)t * nu + ga] + nz * A.stdev;
             u = fminf(fmaxf(vv, LTF(mp.jnt(p) + 24)), LTF(mp.jnt(p) + 25));  // clip to actuator_ctrlrange (shooting.py:146-148)
@@ -983,7 +1089,7 @@ __global__ void __launch_bounds__(kTPB, ABR_LIMB_MINB) k_limb_rollout(const __gr
       }
     }
     float M[NTRI], fs[N], fc[N];
-    forward<NL, NC, LGC>(s, C, M, fs, fc);
+    forward<NL, NC, LGC, CB>(s, C, M, fs, fc);
     if (t >= 0) {
       euler<NL, NC, LGC>(s, C, M, fs, fc);
       if (xs && valid) store_x<NL, NC, LGC>(s, C, xs + (size_t)(t + 1) * nx, nq);
@@ -1013,7 +1119,7 @@ __global__ void __launch_bounds__(kTPB, ABR_LIMB_MINB) k_limb_rollout(const __gr
 }
 
 // MjxEnv.pipeline_init / pipeline_step (rl/base.py:81-96) with the auto-reset blend, on the limb path
-template <int NL, int NC, int LGC>
+template <int NL, int NC, int LGC, bool CB>
 __global__ void __launch_bounds__(kTPB, ABR_LIMB_MINB) k_limb_env(const __grid_constant__ Layout L, const __grid_constant__ EnvArgs A) {
   extern __shared__ __align__(16) float smem[];
   constexpr Map mp{NL, NC};
@@ -1051,7 +1157,7 @@ __global__ void __launch_bounds__(kTPB, ABR_LIMB_MINB) k_limb_env(const __grid_c
 #pragma unroll 1
   for (int it = 0; it < nfw; it++) {
     float M[NTRI], fs[N], fc[N];
-    forward<NL, NC, LGC>(s, C, M, fs, fc);
+    forward<NL, NC, LGC, CB>(s, C, M, fs, fc);
     if (!A.forward_only) euler<NL, NC, LGC>(s, C, M, fs, fc);
   }
   if (valid) {
@@ -1104,12 +1210,12 @@ template <int NL, int NC, class Args, class K> int launch_limb(K kern, const Lay
 #define ABR_DECLARE_LIMB_LAUNCHERS(NL, NC, TAG)                                                        \
   int launch_limb_rollout_##NL##_##NC##_##TAG(const Layout&, const RolloutArgs&, cudaStream_t);        \
   int launch_limb_env_##NL##_##NC##_##TAG(const Layout&, const EnvArgs&, cudaStream_t);
-#define ABR_DEFINE_LIMB_LAUNCHERS(NL, NC, LGC, TAG)                                                    \
+#define ABR_DEFINE_LIMB_LAUNCHERS(NL, NC, LGC, CB, TAG)                                                   \
   int launch_limb_rollout_##NL##_##NC##_##TAG(const Layout& L, const RolloutArgs& a, cudaStream_t st) { \
-    return limb::launch_limb<NL, NC>(limb::k_limb_rollout<NL, NC, LGC>, L, a, a.nworld, 3 * L.nx + L.nu, st); \
+    return limb::launch_limb<NL, NC>(limb::k_limb_rollout<NL, NC, LGC, CB>, L, a, a.nworld, 3 * L.nx + L.nu, st); \
   }                                                                                                    \
   int launch_limb_env_##NL##_##NC##_##TAG(const Layout& L, const EnvArgs& a, cudaStream_t st) {        \
-    return limb::launch_limb<NL, NC>(limb::k_limb_env<NL, NC, LGC>, L, a, a.E, 0, st);                 \
+    return limb::launch_limb<NL, NC>(limb::k_limb_env<NL, NC, LGC, CB>, L, a, a.E, 0, st);                 \
   }
 ABR_DECLARE_LIMB_LAUNCHERS(3, 1, f2)
 ABR_DECLARE_LIMB_LAUNCHERS(3, 1, g)

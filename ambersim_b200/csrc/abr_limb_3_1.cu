@@ -2,5 +2,5 @@
 // the flat 4-lane sharing pattern resolved at compile time
 #include "abr_limb.cuh"
 namespace abr {
-ABR_DEFINE_LIMB_LAUNCHERS(3, 1, 2, f2)
+ABR_DEFINE_LIMB_LAUNCHERS(3, 1, 2, false, f2)
 }

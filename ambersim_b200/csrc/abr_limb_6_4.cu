@@ -2,5 +2,5 @@
 // any sharing pattern
 #include "abr_limb.cuh"
 namespace abr {
-ABR_DEFINE_LIMB_LAUNCHERS(6, 4, -1, g)
+ABR_DEFINE_LIMB_LAUNCHERS(6, 4, -1, false, g)
 }

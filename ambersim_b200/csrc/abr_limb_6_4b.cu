@@ -2,5 +2,5 @@
 // sharing pattern "trunk by 4 lanes, three torso positions by 2" resolved at compile time
 #include "abr_limb.cuh"
 namespace abr {
-ABR_DEFINE_LIMB_LAUNCHERS(6, 4, 86, b)
+ABR_DEFINE_LIMB_LAUNCHERS(6, 4, 86, true, b)
 }

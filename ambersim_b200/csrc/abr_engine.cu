@@ -949,8 +949,9 @@ int abr_cost_destroy(AbrCost* c) {
 
 int abr_rollout_dev(AbrModel* m, const float* x0, int x0_stride, const float* us, int us_stride, int nworld, int N,
                     float* xs_out, const AbrCost* cost, float* costs_out, void* stream) {
-  if (!m || !x0 || (!us && N > 0)) return fail(ABR_EINVAL, "abr_rollout_dev: null argument");
   if (nworld < 0 || N < 0) return fail(ABR_EINVAL, "abr_rollout_dev: negative size");
+  if (m && nworld == 0) return ABR_OK;  // an empty batch has no buffers to point at
+  if (!m || !x0 || (!us && N > 0)) return fail(ABR_EINVAL, "abr_rollout_dev: null argument");
   if (cost && (cost->nx != m->lay.nx || cost->nu != m->lay.nu)) return fail(ABR_EINVAL, "abr_rollout_dev: cost dimensions do not match the model");
   if (costs_out && !cost) return fail(ABR_EINVAL, "abr_rollout_dev: costs_out without a cost");
   CK(cudaSetDevice(m->device));
@@ -965,9 +966,9 @@ int abr_rollout_dev(AbrModel* m, const float* x0, int x0_stride, const float* us
 
 int abr_rollout_host(AbrModel* m, const float* x0, int x0_stride, const float* us, int us_stride, int nworld, int N,
                      float* xs_out, const AbrCost* cost, float* costs_out) {
-  if (!m || !x0 || (!us && N > 0)) return fail(ABR_EINVAL, "abr_rollout_host: null argument");
   if (nworld < 0 || N < 0) return fail(ABR_EINVAL, "abr_rollout_host: negative size");
-  if (nworld == 0) return ABR_OK;
+  if (m && nworld == 0) return ABR_OK;
+  if (!m || !x0 || (!us && N > 0)) return fail(ABR_EINVAL, "abr_rollout_host: null argument");
   CK(cudaSetDevice(m->device));
   const int nx = m->lay.nx, nu = m->lay.nu;
   const size_t n_x0 = x0_stride ? (size_t)nworld * nx : nx;
@@ -1129,8 +1130,9 @@ int abr_mpc_dev(AbrModel* m, const AbrCost* cost, float* x, float* us_guess, uns
 }
 
 int abr_forward_dev(AbrModel* m, float* qpos, float* qvel, const float* ctrl, float* qacc_warmstart, float* qacc, int E, void* stream) {
-  if (!m || !qpos || !qvel) return fail(ABR_EINVAL, "abr_forward_dev: null argument");
   if (E < 0) return fail(ABR_EINVAL, "abr_forward_dev: negative size");
+  if (m && E == 0) return ABR_OK;
+  if (!m || !qpos || !qvel) return fail(ABR_EINVAL, "abr_forward_dev: null argument");
   CK(cudaSetDevice(m->device));
   EnvArgs a;
   memset(&a, 0, sizeof(a));
@@ -1142,8 +1144,9 @@ int abr_forward_dev(AbrModel* m, float* qpos, float* qvel, const float* ctrl, fl
 int abr_env_step_dev(AbrModel* m, float* qpos, float* qvel, float* qacc_warmstart, float* time, const float* ctrl, int E,
                      int nsubsteps, const unsigned char* reset_mask, const float* first_qpos, const float* first_qvel,
                      const float* first_qacc_warmstart, void* stream) {
-  if (!m || !qpos || !qvel || !qacc_warmstart) return fail(ABR_EINVAL, "abr_env_step_dev: null argument");
   if (E < 0 || nsubsteps < 0) return fail(ABR_EINVAL, "abr_env_step_dev: negative size");
+  if (m && E == 0) return ABR_OK;
+  if (!m || !qpos || !qvel || !qacc_warmstart) return fail(ABR_EINVAL, "abr_env_step_dev: null argument");
   if (reset_mask && (!first_qpos || !first_qvel)) return fail(ABR_EINVAL, "abr_env_step_dev: reset_mask without first state");
   CK(cudaSetDevice(m->device));
   EnvArgs a;

@@ -169,6 +169,16 @@ def extra_configs(mj, m, cf, q0, torch, device, stream, L, peak_tf):
                                                                         p(costs), C.c_void_p(stream.cuda_stream))), 2)
         return W * N / (ms * 1e-3), bool(torch.isfinite(costs).all())
 
+    # C1: the reference test's own configuration (tests/trajopt/test_predictive_sampler.py:17-52): bh280, contacts off,
+    # 100 samples x horizon 10, stdev 0.01 (fixed base + joint equalities: served by the generic kernels)
+    hj = load_mj_model_from_file("models/barrett_hand/bh280.xml")
+    hm = mjx.device_put(hj)
+    hm = hm.replace(opt=hm.opt.replace(timestep=0.002, iterations=1, ls_iterations=4, integrator=0, solver=2, disableflags=16))
+    hnx = hj.nq + hj.nv
+    hcf = StaticGoalQuadraticCost(np.eye(hnx), 10.0 * np.eye(hnx), 0.01 * np.eye(hj.nu), np.zeros(hnx))
+    hps = VanillaPredictiveSampler(model=hm, cost_function=hcf, nsamples=100, stdev=0.01)
+    hprm = VanillaPredictiveSamplerParams(key=0, x0=torch.zeros(hnx, **f), us_guess=torch.zeros((10, hj.nu), **f))
+    ex["c1_bh280_vps_100x10_solve_ms"] = _timed(torch, stream, lambda: hps.optimize(hprm), 5)
     rate, fin = rollout_rate(mj, m, cf, "home", 65536, 250, CTRL_NOISE)
     ex["barkour_65536x250"] = {"world_steps_per_s": rate, "frac_of_ffma_peak": F_WS * rate / 1e12 / peak_tf, "costs_finite": fin}
     bj = load_mj_model_from_file("models/biped_standin/biped_exo_standin.xml")

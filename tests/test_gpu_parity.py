@@ -501,3 +501,35 @@ def test_mpc_loop_on_device_equals_python_loop(load_model, name):
     assert torch.equal(xs_d, torch.stack(xs_p)) and torch.equal(us_d, torch.stack(us_p))
     assert info["best_idx"].cpu().tolist() == idx_p
     assert torch.equal(info["us_guess"], g) and torch.equal(info["x"], x)
+
+
+def test_limb_path_edge_cases(load_model):
+    """Empty batches, N = 0, a shared x0 row, ragged batch sizes (not a multiple of the worlds per warp) and a
+    diverging world (NaN stays in its own world and sorts first in the argmin) on the limb kernels."""
+    mj, m, o = model_with(load_model, "barkour")
+    m.set_lanes(1)
+    nx = mj.nq + mj.nv
+    q0 = np.concatenate([mj.key_qpos("home"), np.zeros(mj.nv)])
+    cf = StaticGoalQuadraticCost(np.eye(nx), 10 * np.eye(nx), 0.01 * np.eye(mj.nu), q0)
+    assert shoot(m, t32(np.zeros((0, nx))), t32(np.zeros((0, 5, mj.nu)))).shape == (0, 6, nx)  # no worlds
+    x = shoot(m, t32(q0), t32(np.zeros((0, mj.nu))))  # N = 0: just x0
+    assert x.shape == (1, nx) and np.array_equal(x.cpu().numpy()[0], q0.astype(np.float32))
+    rng = np.random.default_rng(3)
+    for W in (1, 7, 9, 33):  # 8 worlds per warp on this model
+        us = np.clip(mj.key_ctrl("home") + 0.1 * rng.normal(size=(W, 6, mj.nu)), mj.actuator_ctrlrange[:, 0], mj.actuator_ctrlrange[:, 1])
+        a = shoot(m, t32(q0), t32(us)).cpu().numpy()  # shared x0 row (x0_stride = 0)
+        b = shoot(m, t32(np.tile(q0, (W, 1))), t32(us)).cpu().numpy()
+        assert np.array_equal(a, b)
+        assert np.abs(a - o.rollout(np.tile(q0, (W, 1)), us)).max() < 2e-3
+        c1 = shoot_cost(m, t32(q0), t32(us), cf).cpu().numpy()
+        assert np.array_equal(c1[:1], shoot_cost(m, t32(q0), t32(us[:1]), cf).cpu().numpy())  # batch-independent bits
+    # one world starts from a non-finite state: its neighbours in the warp are untouched, its cost is NaN
+    W = 16
+    us = np.tile(mj.key_ctrl("home"), (W, 6, 1))
+    x0 = np.tile(q0, (W, 1))
+    x0[5, 2] = np.nan
+    xs = shoot(m, t32(x0), t32(us)).cpu().numpy()
+    costs = shoot_cost(m, t32(x0), t32(us), cf).cpu().numpy()
+    ok = [w for w in range(W) if w != 5]
+    assert np.isfinite(xs[ok]).all() and np.isfinite(costs[ok]).all() and np.isnan(costs[5])
+    assert np.array_equal(xs[ok[0]], xs[ok[-1]])

@@ -1157,6 +1157,28 @@ int abr_env_step_dev(AbrModel* m, float* qpos, float* qvel, float* qacc_warmstar
   return launch_env(m, m->lay, a, (cudaStream_t)stream);
 }
 
+int abr_env_task_step_dev(AbrModel* m, float* qpos, float* qvel, float* qacc_warmstart, float* time, const float* ctrl, int E, int nsubsteps,
+                          const float* first_qpos, const float* first_qvel, const float* first_qacc_warmstart, const AbrCost* reward,
+                          float z_min, int max_steps, int* steps, float* obs, float* reward_out, unsigned char* done,
+                          unsigned char* truncation, void* stream) {
+  if (E < 0 || nsubsteps < 1 || max_steps < 0) return fail(ABR_EINVAL, "abr_env_task_step_dev: bad sizes");
+  if (m && E == 0) return ABR_OK;
+  if (!m || !qpos || !qvel || !qacc_warmstart || !ctrl || !first_qpos || !first_qvel || !reward || !steps || !reward_out || !done)
+    return fail(ABR_EINVAL, "abr_env_task_step_dev: null argument");
+  if (reward->nx != m->lay.nx || reward->nu != m->lay.nu) return fail(ABR_EINVAL, "abr_env_task_step_dev: reward dimensions do not match the model");
+  if (!reward->diag) return fail(ABR_EUNSUPPORTED, "abr_env_task_step_dev: the fused reward takes diagonal Q and R");
+  CK(cudaSetDevice(m->device));
+  const CostView cv = cost_view(reward);
+  EnvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.blob = m->d_blob; a.qpos = qpos; a.qvel = qvel; a.warm = qacc_warmstart; a.time = time; a.ctrl = ctrl;
+  a.first_qpos = first_qpos; a.first_qvel = first_qvel; a.first_warm = first_qacc_warmstart;
+  a.E = E; a.nsubsteps = nsubsteps; a.forward_only = 0;
+  a.t_steps = steps; a.t_obs = obs; a.t_reward = reward_out; a.t_done = done; a.t_trunc = truncation;
+  a.t_qd = cv.qd; a.t_rd = cv.rd; a.t_xg = cv.xg; a.t_zmin = z_min; a.t_max_steps = max_steps;
+  return launch_env(m, m->lay, a, (cudaStream_t)stream);
+}
+
 int abr_debug_forward_host(AbrModel* m, const float* qpos, const float* qvel, const float* ctrl, const float* qacc_warmstart,
                            const char* name, float* out, int cap, int* n) {
   if (!m || !qpos || !qvel || !name || !out || !n) return fail(ABR_EINVAL, "abr_debug_forward_host: null argument");

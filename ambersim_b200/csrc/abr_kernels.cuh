@@ -187,6 +187,12 @@ struct EnvArgs {
   int E, nsubsteps;
   int forward_only;
   float* dbg;  // nullable: world 0's whole shared-memory region after forward
+  // fused task epilogue (abr_env_task_step_dev; t_steps == nullptr = off): obs = (qpos, qvel), reward =
+  // -(0.5 (x-xg)' diag(qd) (x-xg) + 0.5 u' diag(rd) u), done = floating-base height below t_zmin or the
+  // episode counter reaching t_max_steps; finished envs leave the launch already reset to their first state
+  int* t_steps; float* t_obs; float* t_reward; unsigned char* t_done; unsigned char* t_trunc;
+  const float* t_qd; const float* t_rd; const float* t_xg;
+  float t_zmin; int t_max_steps;
 };
 
 template <int G>
@@ -202,6 +208,7 @@ __global__ void __launch_bounds__(ABR_TPB, ABR_MINB) k_env(const __grid_constant
   const int nq = L.nq, nv = L.nv, nu = L.nu;
   init_world<G>(c);
   const bool reset = A.reset_mask && A.reset_mask[w];
+  const bool was_done = A.t_steps && A.t_done[w];  // AutoResetWrapper zeroes the counter of an env that finished last step
   const float* sq = reset ? A.first_qpos : A.qpos;
   const float* sv = reset ? A.first_qvel : A.qvel;
   const float* sw = reset ? A.first_warm : A.warm;
@@ -216,6 +223,36 @@ __global__ void __launch_bounds__(ABR_TPB, ABR_MINB) k_env(const __grid_constant
       if (A.forward_only || post_forward<G>(c, stage)) break;
     }
   }
+  bool fin = false;
+  if (A.t_steps) {  // EpisodeWrapper + AutoResetWrapper semantics around obs / reward / done of the stepped state
+    __syncwarp();
+    float r = 0.f;
+    for (int i = c.lane; i < nq; i += G) { const float e = c.W[L.w_qpos + i] - A.t_xg[i]; r = fmaf(A.t_qd[i] * e, e, r); }
+    for (int i = c.lane; i < nv; i += G) { const float e = c.W[L.w_qvel + i] - A.t_xg[nq + i]; r = fmaf(A.t_qd[nq + i] * e, e, r); }
+    for (int i = c.lane; i < nu; i += G) { const float u = c.W[L.w_ctrl + i]; r = fmaf(A.t_rd[i] * u, u, r); }
+    r = gsum<G>(r);
+    const int st = ((reset || was_done) ? 0 : A.t_steps[w]) + 1;
+    const bool term = !(c.W[L.w_qpos + 2] >= A.t_zmin);  // a non-finite height terminates too
+    const bool trunc = A.t_max_steps > 0 && st >= A.t_max_steps;
+    fin = term || trunc;
+    __syncwarp();
+    if (valid && c.lane == 0) {
+      A.t_reward[w] = -0.5f * r; A.t_done[w] = fin ? 1 : 0; A.t_steps[w] = st;
+      if (A.t_trunc) A.t_trunc[w] = (trunc && !term) ? 1 : 0;
+    }
+    if (fin) {
+      for (int i = c.lane; i < nq; i += G) c.W[L.w_qpos + i] = A.first_qpos[(size_t)w * nq + i];
+      for (int i = c.lane; i < nv; i += G) {
+        c.W[L.w_qvel + i] = A.first_qvel[(size_t)w * nv + i];
+        c.W[L.w_warm + i] = A.first_warm ? A.first_warm[(size_t)w * nv + i] : 0.f;
+      }
+    }
+    __syncwarp();
+    if (valid && A.t_obs) {
+      for (int i = c.lane; i < nq; i += G) A.t_obs[(size_t)w * (nq + nv) + i] = c.W[L.w_qpos + i];
+      for (int i = c.lane; i < nv; i += G) A.t_obs[(size_t)w * (nq + nv) + nq + i] = c.W[L.w_qvel + i];
+    }
+  }
   if (valid) {
     for (int i = c.lane; i < nq; i += G) A.qpos[(size_t)w * nq + i] = c.W[L.w_qpos + i];
     for (int i = c.lane; i < nv; i += G) {
@@ -225,7 +262,7 @@ __global__ void __launch_bounds__(ABR_TPB, ABR_MINB) k_env(const __grid_constant
     }
     if (A.time && c.lane == 0) {
       const float t0 = reset ? 0.f : A.time[w];
-      A.time[w] = A.forward_only ? t0 : t0 + L.timestep * (float)A.nsubsteps;
+      A.time[w] = fin ? 0.f : (A.forward_only ? t0 : t0 + L.timestep * (float)A.nsubsteps);
     }
     if (A.dbg && wraw == 0) for (int i = c.lane; i < L.world_stride; i += G) A.dbg[i] = c.W[i];
   }

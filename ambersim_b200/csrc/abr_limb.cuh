@@ -1135,6 +1135,7 @@ __global__ void __launch_bounds__(kTPB, ABR_LIMB_MINB) k_limb_env(const __grid_c
   const int w = valid ? wraw : A.E - 1;
   const LaneCfg<LGC> C = make_cfg<NL, NC, LGC>(L, smem, g);
   const bool reset = A.reset_mask && A.reset_mask[w];
+  const bool was_done = A.t_steps && A.t_done[w];  // AutoResetWrapper zeroes the counter of an env that finished last step
   const float* sq = (reset ? A.first_qpos : A.qpos) + (size_t)w * nq;
   const float* sv = (reset ? A.first_qvel : A.qvel) + (size_t)w * nv;
   const float* sw = reset ? A.first_warm : A.warm;
@@ -1160,6 +1161,40 @@ __global__ void __launch_bounds__(kTPB, ABR_LIMB_MINB) k_limb_env(const __grid_c
     forward<NL, NC, LGC, CB>(s, C, M, fs, fc);
     if (!A.forward_only) euler<NL, NC, LGC>(s, C, M, fs, fc);
   }
+  bool fin = false;
+  if (A.t_steps) {  // EpisodeWrapper + AutoResetWrapper semantics around obs / reward / done of the stepped state
+    float r = quad_x_diag<NL, NC, LGC>(s, C, A.t_qd, A.t_xg, nq);
+#pragma unroll
+    for (int p = 1; p <= NL; p++) {
+      const int ga = LTI(mp.ijnt(p) + 3);
+      if (ga >= 0 && C.S.o(p)) r = fmaf(A.t_rd[ga] * s.ctrl[p - 1], s.ctrl[p - 1], r);
+    }
+    r = gall(r, lg);
+    const int st = ((reset || was_done) ? 0 : A.t_steps[w]) + 1;
+    const bool term = !(s.qt[2] >= A.t_zmin);  // a non-finite height terminates too
+    const bool trunc = A.t_max_steps > 0 && st >= A.t_max_steps;
+    fin = term || trunc;
+    if (valid && g == 0) {
+      A.t_reward[w] = -0.5f * r; A.t_done[w] = fin ? 1 : 0; A.t_steps[w] = st;
+      if (A.t_trunc) A.t_trunc[w] = (trunc && !term) ? 1 : 0;
+    }
+    if (fin) {  // leave the launch already reset: where(done, first_state, state)
+      const float* fq = A.first_qpos + (size_t)w * nq; const float* fv = A.first_qvel + (size_t)w * nv;
+      const float* fw = A.first_warm ? A.first_warm + (size_t)w * nv : nullptr;
+#pragma unroll
+      for (int i = 0; i < 7; i++) s.qt[i] = fq[i];
+#pragma unroll
+      for (int i = 0; i < 6; i++) { s.v[i] = fv[i]; s.warm[i] = fw ? fw[i] : 0.f; }
+#pragma unroll
+      for (int p = 1; p <= NL; p++) {
+        const int gd = LTI(mp.ijnt(p) + 1), gq = LTI(mp.ijnt(p) + 2);
+        s.qc[p - 1] = (gd >= 0) ? fq[gq] : 0.f;
+        s.v[5 + p] = (gd >= 0) ? fv[gd] : 0.f;
+        s.warm[5 + p] = (gd >= 0 && fw) ? fw[gd] : 0.f;
+      }
+    }
+    if (valid && A.t_obs) store_x<NL, NC, LGC>(s, C, A.t_obs + (size_t)w * (nq + nv), nq);
+  }
   if (valid) {
     float* oq = A.qpos + (size_t)w * nq; float* ov = A.qvel + (size_t)w * nv;
     float* ow = A.warm ? A.warm + (size_t)w * nv : nullptr; float* oa = A.qacc ? A.qacc + (size_t)w * nv : nullptr;
@@ -1174,7 +1209,7 @@ __global__ void __launch_bounds__(kTPB, ABR_LIMB_MINB) k_limb_env(const __grid_c
       }
       if (A.time) {
         const float t0 = reset ? 0.f : A.time[w];
-        A.time[w] = A.forward_only ? t0 : t0 + L.timestep * (float)A.nsubsteps;
+        A.time[w] = fin ? 0.f : (A.forward_only ? t0 : t0 + L.timestep * (float)A.nsubsteps);
       }
     }
 #pragma unroll

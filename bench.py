@@ -146,7 +146,7 @@ def extra_configs(mj, m, cf, q0, torch, device, stream, L, peak_tf):
     a large Barkour batch (roofline at full occupancy), C3 biped 16384 x 1000, the C4 sample sweep x 32 steps,
     C5 env-step throughput with auto-reset at 8192 envs."""
     from ambersim_b200 import _lib, mjx
-    from ambersim_b200.rl.base import VectorEnvStepper
+    from ambersim_b200.rl.wrappers import FusedQuadraticTaskEnv, QuadraticTaskEnv
     from ambersim_b200.trajopt.cost import StaticGoalQuadraticCost
     from ambersim_b200.trajopt.shooting import VanillaPredictiveSampler, VanillaPredictiveSamplerParams
     from ambersim_b200.utils.io_utils import load_mj_model_from_file
@@ -199,21 +199,24 @@ def extra_configs(mj, m, cf, q0, torch, device, stream, L, peak_tf):
     ticks = 50
     ex["mpc_4096x32_ms_per_tick"] = {"value": _timed(torch, stream, lambda: ps.mpc(prm, ticks), 2) / ticks,
                                      "note": "abr_mpc_dev: solve + plant step + guess shift on the device, 50 ticks, no host round trips"}
-    E, T = 8192, 200
-    qpos0 = torch.tensor(mj.key_qpos("home"), **f).repeat(E, 1)
-    qpos0[:, 7:] += (torch.rand((E, mj.nq - 7), generator=g, **f) - 0.5) * 2 * JITTER
-    env = VectorEnvStepper(m, qpos0, torch.zeros(E, mj.nv, **f), nsubsteps=1)
+    # C5: obs = (qpos, qvel), reward = -quadratic cost, done = 1000 steps or base height < 0.1, auto-reset to the
+    # env's first state: abr_env_task_step_dev does physics + obs + reward + done + counter + reset blend in ONE launch
+    E, T, NA = 8192, 1200, 200
+    tenv = FusedQuadraticTaskEnv(QuadraticTaskEnv(mj, cf, mj.key_qpos("home"), num_envs=E, z_min=0.1, jitter=JITTER), 1000)
+    tenv.reset(7)
     lim = torch.tensor(mj.actuator_ctrlrange, **f)
-    acts = torch.minimum(torch.maximum(torch.tensor(mj.key_ctrl("home"), **f) + CTRL_NOISE * torch.randn((T, E, mj.nu), generator=g, **f), lim[:, 0]), lim[:, 1])
-    done = torch.rand((T, E), generator=g, **f) < 1e-3
+    acts = torch.minimum(torch.maximum(torch.tensor(mj.key_ctrl("home"), **f) + CTRL_NOISE * torch.randn((NA, E, mj.nu), generator=g, **f), lim[:, 0]), lim[:, 1])
 
     def env_loop():
         for t in range(T):
-            env.step(acts[t], done[t])
+            tenv.step(None, acts[t % NA])
 
     ms = _timed(torch, stream, env_loop, 2)
-    ex["c5_env_steps_per_s_8192"] = {"value": E * T / (ms * 1e-3), "launches_per_env_step": 1,
-                                     "note": "physics only (policy excluded), auto-reset blend in the step prologue, one launch per env step"}
+    st = tenv.step(None, acts[0])
+    ex["c5_env_steps_per_s_8192"] = {"value": E * T / (ms * 1e-3), "launches_per_env_step": 1, "episode_length": 1000, "z_min": 0.1,
+                                     "reward_finite": bool(torch.isfinite(st.reward).all()), "mean_episode_step": float(st.info["steps"].float().mean()),
+                                     "note": "whole env step (policy excluded): physics + obs + reward + done + episode counter + auto-reset "
+                                             "blend fused in one launch per env step (abr_env_task_step_dev)"}
     return ex
 
 

@@ -269,6 +269,26 @@ int abr_env_step_dev(AbrModel* m, float* qpos, float* qvel, float* qacc_warmstar
                      const float* first_qpos, const float* first_qvel,
                      const float* first_qacc_warmstart, void* stream);
 
+/* ---- one whole training-env step in ONE launch: MjxEnv.step of a quadratic
+ * tracking task wrapped in brax's EpisodeWrapper + AutoResetWrapper, E envs in place, DEVICE pointers.
+ *   physics : nsubsteps x mjx.step with ctrl held (rl/base.py:88-96)
+ *   reward  : -(0.5 (x-xg)' Q (x-xg) + 0.5 u' R u) on the stepped state x = (qpos, qvel) and the action as
+ *             given (`reward`: an AbrCost with DIAGONAL Q and R; Qf is not used)
+ *   done    : qpos[2] < z_min (floating-base height; pass -INFINITY to disable; a non-finite height also
+ *             terminates) or, when max_steps > 0, steps[e] + 1 >= max_steps (EpisodeWrapper's episode_length;
+ *             truncation[e] = 1 when only the length ended the episode)
+ *   reset   : AutoResetWrapper: where(done, first_state, state) on qpos / qvel / qacc_warmstart / time and obs;
+ *             reward and done keep the finished step's values; an env whose done[e] is set on entry starts
+ *             counting from 0 again (done is in/out: clear it before the first step)
+ *   obs     : nullable [E,nq+nv] = (qpos, qvel) of the state the env leaves the launch in
+ * steps [E] int in/out episode counters; reward_out [E]; done [E] bytes; truncation nullable [E] bytes. */
+int abr_env_task_step_dev(AbrModel* m, float* qpos, float* qvel, float* qacc_warmstart, float* time,
+                          const float* ctrl, int E, int nsubsteps, const float* first_qpos,
+                          const float* first_qvel, const float* first_qacc_warmstart,
+                          const AbrCost* reward, float z_min, int max_steps, int* steps, float* obs,
+                          float* reward_out, unsigned char* done, unsigned char* truncation,
+                          void* stream);
+
 /* ---- stage dump for parity tests (tests only): one world, mjx.forward, HOST pointers ------
  * name in {"xpos","xquat","xipos","ximat","subtree_com","cinert","cdof","qM","cvel","cdof_dot",
  * "qfrc_bias","qfrc_passive","qfrc_actuator","qfrc_smooth","qacc_smooth","efc_J","efc_D",

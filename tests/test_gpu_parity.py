@@ -533,3 +533,69 @@ def test_limb_path_edge_cases(load_model):
     ok = [w for w in range(W) if w != 5]
     assert np.isfinite(xs[ok]).all() and np.isfinite(costs[ok]).all() and np.isnan(costs[5])
     assert np.array_equal(xs[ok[0]], xs[ok[-1]])
+
+
+@pytest.mark.parametrize("name,lanes", [("barkour", 0), ("barkour", 8), ("biped", 0), ("tripod", 0)])
+def test_fused_task_env_equals_wrapper_chain(load_model, name, lanes):
+    """abr_env_task_step_dev (physics + obs + reward + done + episode counter + auto-reset in ONE launch) against
+    AutoResetWrapper(EpisodeWrapper(QuadraticTaskEnv)) built from torch ops around pipeline_step: identical physics
+    state, done / truncation flags and step counters, rewards to float rounding; and the first step's reward and
+    state against the oracle. The episode length (7) and the height threshold make both kinds of episode end occur."""
+    from ambersim_b200.rl.wrappers import AutoResetWrapper, EpisodeWrapper, FusedQuadraticTaskEnv, QuadraticTaskEnv
+
+    mj = load_model(name)
+    key = MODEL_KEY[name]
+    nx = mj.nq + mj.nv
+    rng = np.random.default_rng(11)
+    qd, rd = rng.uniform(0.5, 2.0, nx), rng.uniform(0.01, 0.1, mj.nu)
+    xg = np.concatenate([mj.key_qpos(key), np.zeros(mj.nv)])
+    cf = StaticGoalQuadraticCost(np.diag(qd), np.eye(nx), np.diag(rd), xg)
+    E, T, LEN = 37, 40, 7
+    lo, hi = mj.actuator_ctrlrange[:, 0], mj.actuator_ctrlrange[:, 1]
+    acts = t32(np.clip(mj.key_ctrl(key) + 0.6 * rng.standard_normal((T, E, mj.nu)), lo, hi))
+
+    def make(z_min):
+        env = QuadraticTaskEnv(mj, cf, mj.key_qpos(key), num_envs=E, z_min=z_min, jitter=0.1, physics_steps_per_control_step=2)
+        if lanes:
+            env.sys.set_lanes(lanes)
+        return env
+
+    # height threshold = the 30 % quantile of the lowest base height over the first episode: some envs terminate before the length does
+    pre = make(-np.inf)
+    sp = pre.reset(5)
+    zlow = sp.pipeline_state.qpos[:, 2].clone()
+    for t in range(LEN - 1):
+        sp = pre.step(sp, acts[t])
+        zlow = torch.minimum(zlow, sp.pipeline_state.qpos[:, 2])
+    z_min = float(torch.quantile(zlow, 0.3))
+    make = (lambda f: (lambda: f(z_min)))(make)
+    ref_env = AutoResetWrapper(EpisodeWrapper(make(), LEN))
+    fused = FusedQuadraticTaskEnv(make(), LEN)
+    s_ref, s_f = ref_env.reset(5), fused.reset(5)
+    assert torch.equal(s_ref.obs, s_f.obs)
+    # first step against the oracle (float64): state within the single-step bound, reward to 1e-4 relative
+    o = Oracle(mj)
+    d0 = s_ref.pipeline_state
+    q0, v0, w0 = (t.cpu().numpy() for t in (d0.qpos, d0.qvel, d0.qacc_warmstart))
+    n_term = n_trunc = 0
+    for t in range(T):
+        s_ref = ref_env.step(s_ref, acts[t])
+        s_f = fused.step(s_f, acts[t])
+        dr, df = s_ref.pipeline_state, s_f.pipeline_state
+        for a, b in ((dr.qpos, df.qpos), (dr.qvel, df.qvel), (dr.qacc_warmstart, df.qacc_warmstart), (s_ref.obs, s_f.obs)):
+            assert torch.equal(a, b), f"step {t}"
+        assert torch.allclose(dr.time, df.time, atol=1e-6)
+        assert torch.equal(s_ref.done.bool(), s_f.done.bool()) and torch.equal(s_ref.info["steps"], s_f.info["steps"])
+        assert torch.equal(s_ref.info["truncation"].bool(), s_f.info["truncation"].bool())
+        assert torch.allclose(s_ref.reward, s_f.reward, rtol=1e-5, atol=1e-5)
+        n_trunc += int(s_f.info["truncation"].sum())
+        n_term += int((s_f.done.bool() & ~s_f.info["truncation"].bool()).sum())
+        if t == 0:
+            for e in range(0, E, 6):
+                qr, vr, _, _ = o.step(q0[e], v0[e], acts[0, e].cpu().numpy(), w0[e], nsteps=2)
+                xr = np.concatenate([qr, vr])
+                rr = -0.5 * (np.sum(qd * (xr - xg) ** 2) + np.sum(rd * acts[0, e].cpu().numpy().astype(np.float64) ** 2))
+                assert np.isclose(float(s_f.reward[e]), rr, rtol=1e-3, atol=1e-4)
+                if not bool(s_f.done[e]):
+                    assert np.all(np.abs(df.qpos[e].cpu().numpy() - qr) <= 2e-5 + 2e-4 * np.abs(qr))
+    assert n_trunc > 0 and n_term > 0

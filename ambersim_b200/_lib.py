@@ -66,6 +66,11 @@ def lib():
     L.abr_forward_dev.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, vp]
     L.abr_env_step_dev.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp]
     L.abr_env_task_step_dev.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, C.c_float, C.c_int, vp, vp, vp, vp, vp, vp]
+    L.abr_xchg_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_size_t, C.POINTER(vp), C.c_char_p]
+    L.abr_xchg_connect.argtypes = [vp, C.c_char_p]
+    L.abr_xchg_merge_best_dev.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp]
+    L.abr_xchg_timed_out.argtypes = [vp, ip]
+    L.abr_xchg_destroy.argtypes = [vp]
     L.abr_debug_forward_host.argtypes = [vp, fp, fp, fp, fp, C.c_char_p, fp, C.c_int, ip]
     L.abr_ffma_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     if L.abr_sizeof_model_host() != C.sizeof(S["AbrModelHost"]) or L.abr_sizeof_opt() != C.sizeof(S["AbrOpt"]):

@@ -24,6 +24,7 @@ using namespace abr;
 // ================================================================================ errors
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+namespace abr { int set_error(int code, const std::string& msg) { return fail(code, msg); } }  // for the other translation units
 #define CK(call)                                                                          \
   do {                                                                                    \
     cudaError_t e_ = (call);                                                              \

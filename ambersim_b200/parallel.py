@@ -6,6 +6,10 @@ the single-GPU result. The only exchange is one all_gather of a small per-rank r
 {best_cost, best_idx, us*[N,nu], xs*[N+1,nx]}; every rank then takes the first minimum (NaN counts
 as minimal, lower global index wins ties) so all ranks end with identical winners and no dependent
 broadcast is needed. Rollout / env-step throughput needs no collective at all (replicas).
+
+Two implementations of that exchange: `merge_best` (torch.distributed all_gather: NCCL on GPUs, gloo in
+the CPU tests) and `PeerExchange` (ONE kernel launch per rank that stores the record into every peer's
+buffer over NVLink P2P and selects the winner, csrc/abr_xchg.cu; GPUs of one box only).
 """
 from __future__ import annotations
 
@@ -55,8 +59,64 @@ def merge_best(best_cost: torch.Tensor, best_idx: torch.Tensor, xs_star: torch.T
             sel[:, 1].to(best_idx.dtype), sel[:, 0].to(best_cost.dtype))
 
 
-def sharded_optimize(sampler, params, group=None):
-    """VanillaPredictiveSampler.optimize with `sampler.nsamples` samples split over the ranks."""
+class PeerExchange:
+    """The winner exchange as one kernel over NVLink peer memory (abr_xchg_*). Collective: build it on every
+    rank of `group` (ranks = GPUs of one box), then pass it to `sharded_optimize(..., exchange=...)`.
+
+    `capacity` bounds B * (2 + N*nu + (N+1)*nx) floats per call."""
+
+    def __init__(self, device: torch.device, capacity: int, group=None):
+        import ctypes as C
+
+        from ambersim_b200 import _lib
+
+        self._L = _lib.lib()
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.device = torch.device(device)
+        self._h = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        _lib.check(self._L.abr_xchg_create(self.device.index or 0, self.world, self.rank, int(capacity), C.byref(self._h), handle))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle.raw, group=group)
+        _lib.check(self._L.abr_xchg_connect(self._h, b"".join(handles)))
+        self._group = group
+        dist.barrier(group)
+
+    def merge_best(self, best_cost, best_idx, xs_star, us_star):
+        import ctypes as C
+
+        from ambersim_b200 import _lib
+
+        B = best_cost.shape[0]
+        cost, idx = best_cost.reshape(B).float().contiguous(), best_idx.reshape(B).to(torch.int32).contiguous()
+        xs, us = xs_star.reshape(B, -1).float().contiguous(), us_star.reshape(B, -1).float().contiguous()
+        xs_o, us_o, idx_o, cost_o = torch.empty_like(xs), torch.empty_like(us), torch.empty_like(idx), torch.empty_like(cost)
+        p = lambda t: C.c_void_p(t.data_ptr())
+        _lib.check(self._L.abr_xchg_merge_best_dev(self._h, p(cost), p(idx), p(xs), p(us), B, xs.shape[1], us.shape[1], p(xs_o), p(us_o),
+                                                   p(idx_o), p(cost_o), C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        return xs_o.reshape(xs_star.shape).to(xs_star.dtype), us_o.reshape(us_star.shape).to(us_star.dtype), idx_o.to(best_idx.dtype), cost_o
+
+    def timed_out(self) -> bool:
+        import ctypes as C
+
+        from ambersim_b200 import _lib
+
+        torch.cuda.synchronize(self.device)
+        flag = C.c_int()
+        _lib.check(self._L.abr_xchg_timed_out(self._h, C.byref(flag)))
+        return bool(flag.value)
+
+    def close(self):
+        if self._h:
+            torch.cuda.synchronize(self.device)
+            dist.barrier(self._group)  # nobody unmaps a buffer a peer may still be writing
+            self._L.abr_xchg_destroy(self._h)
+            self._h = None
+
+
+def sharded_optimize(sampler, params, group=None, exchange: "PeerExchange" = None):
+    """VanillaPredictiveSampler.optimize with `sampler.nsamples` samples split over the ranks.
+    `exchange`: a `PeerExchange` for the winner exchange (default: all_gather through torch.distributed)."""
     import dataclasses
 
     if not dist.is_initialized():
@@ -71,7 +131,10 @@ def sharded_optimize(sampler, params, group=None):
     if not batched:
         xs, us = xs[None], us[None]
         info = {k: (v[None] if hasattr(v, "dim") else v) for k, v in info.items()}
-    xs, us, idx, cost = merge_best(info["best_cost"].reshape(-1), info["best_idx"].reshape(-1), xs, us, group)
+    if exchange is not None:
+        xs, us, idx, cost = exchange.merge_best(info["best_cost"].reshape(-1), info["best_idx"].reshape(-1), xs, us)
+    else:
+        xs, us, idx, cost = merge_best(info["best_cost"].reshape(-1), info["best_idx"].reshape(-1), xs, us, group)
     if not batched:
         xs, us = xs[0], us[0]
     return xs, us

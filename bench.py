@@ -359,6 +359,32 @@ def main():
                       "api": "abr_rollout_host (pinned host buffers in, costs out)", "timer": "host wall clock around K calls"}
         out["e2e_matches_device"] = bool(torch.equal(costs_h.to(device), costs))
 
+        sharded = None
+        if world > 1:
+            # ---- C4 on N GPUs: samples sharded by global id, winners exchanged by ONE peer-memory kernel per rank (abr_xchg_*)
+            from ambersim_b200.parallel import PeerExchange, sharded_optimize
+
+            xch = PeerExchange(device, capacity=2 + 32 * mj.nu + 33 * (mj.nq + mj.nv))
+            prm_s = VanillaPredictiveSamplerParams(key=3, x0=torch.tensor(q0, dtype=torch.float32, device=device),
+                                                   us_guess=torch.tensor(mj.key_ctrl("home"), dtype=torch.float32, device=device).repeat(32, 1))
+            sharded = {}
+            for S in (4096, 65536, 1048576):
+                ps_s = VanillaPredictiveSampler(model=m, cost_function=cf, nsamples=S, stdev=0.1)
+                for _ in range(3):
+                    sharded_optimize(ps_s, prm_s, exchange=xch)
+                barrier()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                for _ in range(5):
+                    sharded_optimize(ps_s, prm_s, exchange=xch)
+                b.record(stream)
+                torch.cuda.synchronize(device)
+                t = torch.tensor([a.elapsed_time(b) / 5], device=device)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                sharded[str(S)] = float(t)
+            if xch.timed_out():
+                raise SystemExit("peer-memory exchange timed out")
+            xch.close()
         if rank == 0:
             # ---- second half of BASELINE's metric: 4096-sample x 32-step predictive-sampling solve latency
             ps = VanillaPredictiveSampler(model=m, cost_function=cf, nsamples=4096, stdev=0.1)
@@ -376,6 +402,9 @@ def main():
             torch.cuda.synchronize(device)
             out["extra"] = {"vps_4096x32_solve_ms": a.elapsed_time(b) / reps,
                             "vps_note": "VanillaPredictiveSampler.optimize, device-resident inputs: rollouts + argmin + winner gather (3 launches)"}
+            if sharded is not None:
+                out["extra"]["c4_sharded_solve_ms_by_samples_x32"] = sharded
+                out["extra"]["c4_sharded_note"] = f"samples split over {world} GPUs by global id; one peer-memory exchange kernel per rank (no NCCL call)"
             if world == 1:  # the other configs and the CPU baseline are reported by the single-GPU run only
                 out["extra"].update(extra_configs(mj, m, cf, q0, torch, device, stream, L, tf.value))
                 rate, sample = cpu_arm(mj, args.cpu_seconds, ncores)

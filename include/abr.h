@@ -308,6 +308,26 @@ int abr_mpc_dev(AbrModel* m, const AbrCost* cost, float* x, float* us_guess, uns
                 int S, int N, float stdev, int nticks, float* xs_log, float* us_log, float* cost_log,
                 int* idx_log, void* stream);
 
+/* ---- the sampler's cross-GPU exchange over NVLink peer memory: one process per GPU of ONE box ----
+ * Each rank creates an exchange buffer (device memory it owns) and gets a CUDA IPC handle for it; the host
+ * framework hands every rank all R handles (e.g. torch.distributed.all_gather_object) for abr_xchg_connect.
+ * abr_xchg_merge_best_dev is then collective and stream-ordered: every rank passes its local winners
+ * {best_cost [B], best_idx [B] (global sample ids), xs_star [B,nxs], us_star [B,nus]} (DEVICE pointers) and ONE
+ * launch stores them into all peers' buffers (P2P stores + system-scope release flags), waits for the R records of
+ * this call and writes the global first minimum (NaN minimal, lowest sample id wins ties) to the outputs: identical
+ * on every rank, no NCCL call, no host round trip. max_record_floats bounds B * (2 + nxs + nus).
+ * abr_xchg_timed_out reports (after a stream sync) whether a peer failed to arrive within about 2 s. */
+#define ABR_XCHG_HANDLE_BYTES 64
+typedef struct AbrXchg AbrXchg;
+int abr_xchg_create(int device, int nranks, int rank, size_t max_record_floats, AbrXchg** out,
+                    unsigned char* handle_out /* [ABR_XCHG_HANDLE_BYTES] */);
+int abr_xchg_connect(AbrXchg* x, const unsigned char* handles /* [nranks][ABR_XCHG_HANDLE_BYTES] */);
+int abr_xchg_merge_best_dev(AbrXchg* x, const float* best_cost, const int* best_idx, const float* xs_star,
+                            const float* us_star, int B, int nxs, int nus, float* xs_out, float* us_out,
+                            int* idx_out, float* cost_out, void* stream);
+int abr_xchg_timed_out(AbrXchg* x, int* timed_out);
+int abr_xchg_destroy(AbrXchg* x);
+
 /* FP32 FMA-pipe peak microbenchmark (roofline denominator): returns TFLOP/s */
 int abr_ffma_peak(int device, double* tflops, double* ms);
 

@@ -385,6 +385,34 @@ def main():
             if xch.timed_out():
                 raise SystemExit("peer-memory exchange timed out")
             xch.close()
+            # ---- the north-star operating point on every GPU at once: 65536 worlds per GPU (full occupancy), 250 steps
+            WB, NB = 65536, 250
+            gb = torch.Generator(device=device)
+            gb.manual_seed(2000 + rank)
+            fb = dict(dtype=torch.float32, device=device)
+            xb = torch.tensor(q0, **fb).repeat(WB, 1)
+            xb[:, 7:19] += (torch.rand((WB, 12), generator=gb, **fb) - 0.5) * 2 * JITTER
+            limb_ = torch.tensor(mj.actuator_ctrlrange, **fb)
+            ub = torch.tensor(mj.key_ctrl("home"), **fb) + CTRL_NOISE * torch.randn((WB, NB, mj.nu), generator=gb, **fb)
+            ub = torch.minimum(torch.maximum(ub, limb_[:, 0]), limb_[:, 1]).contiguous()
+            cb = torch.empty(WB, **fb)
+            big = lambda: _lib.check(L.abr_rollout_dev(h.ptr, p(xb), mj.nq + mj.nv, p(ub), NB * mj.nu, WB, NB, None, ch.ptr, p(cb),
+                                                       C.c_void_p(stream.cuda_stream)))
+            for _ in range(2):
+                big()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(3):
+                big()
+            b.record(stream)
+            torch.cuda.synchronize(device)
+            t = torch.tensor([a.elapsed_time(b) / 3], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            rate_b = world * WB * NB / (float(t) * 1e-3)
+            sharded_big = {"world_steps_per_s": rate_b, "worlds_per_gpu": WB, "horizon": NB, "frac_of_ffma_peak": F_WS * rate_b / world / 1e12 / tf.value,
+                           "costs_finite": bool(torch.isfinite(cb).all())}
+            del xb, ub, cb
         if rank == 0:
             # ---- second half of BASELINE's metric: 4096-sample x 32-step predictive-sampling solve latency
             ps = VanillaPredictiveSampler(model=m, cost_function=cf, nsamples=4096, stdev=0.1)
@@ -404,6 +432,7 @@ def main():
                             "vps_note": "VanillaPredictiveSampler.optimize, device-resident inputs: rollouts + argmin + winner gather (3 launches)"}
             if sharded is not None:
                 out["extra"]["c4_sharded_solve_ms_by_samples_x32"] = sharded
+                out["extra"]["barkour_65536_per_gpu_x250"] = sharded_big
                 out["extra"]["c4_sharded_note"] = f"samples split over {world} GPUs by global id; one peer-memory exchange kernel per rank (no NCCL call)"
             if world == 1:  # the other configs and the CPU baseline are reported by the single-GPU run only
                 out["extra"].update(extra_configs(mj, m, cf, q0, torch, device, stream, L, tf.value))

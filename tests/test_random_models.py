@@ -1,0 +1,101 @@
+"""Randomised models of the limb-kernel class (tests/_randmodel.py): host-side plan invariants on the CPU, and on the
+GPU the limb kernels and the generic kernels against the float64 oracle, teacher-forced, from settled contact states.
+Tolerances are the single-step bounds of tests/test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+from ambersim_b200 import mjx
+from ambersim_b200.utils.io_utils import load_mj_model_from_file
+from oracle.oracle import Oracle
+from tests._randmodel import random_limb_model
+
+CONFIGS = {"quad": (3, 1, 4), "long": (6, 4, 4), "wide": (3, 1, 8)}
+
+
+def _load(tmp_path, seed, cfg, **kw):
+    xml, q, c = random_limb_model(seed, *CONFIGS[cfg], **kw)
+    f = tmp_path / f"rand_{cfg}_{seed}.xml"
+    f.write_text(xml)
+    return load_mj_model_from_file(str(f)), q, c
+
+
+@pytest.mark.parametrize("cfg", list(CONFIGS))
+def test_random_model_plans_cover_every_body_once(tmp_path, cfg):
+    eligible = 0
+    for seed in range(12):
+        mj, q, c = _load(tmp_path, seed, cfg)
+        assert len(q) == mj.nq and len(c) == mj.nu
+        p = mjx.limb_plan(mj)
+        if not p["eligible"]:
+            continue
+        eligible += 1
+        owned = {}
+        for g, path in enumerate(p["paths"]):
+            assert path[0] == 1 or path[0] == -1  # every carried path starts at the trunk (dummy lanes are all -1)
+            for k, b in enumerate(path):
+                if b > 0 and p["own"][g][k]:
+                    assert b not in owned, f"body {b} owned twice (seed {seed})"
+                    owned[b] = g
+                if b > 0 and k > 0:
+                    assert mj.body_parentid[b] == path[k - 1]
+        assert sorted(owned) == list(range(1, mj.nbody)), f"seed {seed}: bodies without an owner lane"
+        # lanes sharing a body agree on its sharing level, and the level is log2 of the number of sharing lanes
+        for k in range(p["NL"] + 1):
+            groups = {}
+            for g, path in enumerate(p["paths"]):
+                if path[k] > 0:
+                    groups.setdefault(path[k], []).append(g)
+            for b, lanes in groups.items():
+                assert {p["level"][g][k] for g in lanes} == {int(np.ceil(np.log2(len(lanes))))} or len(lanes) == 1
+    assert eligible >= 6
+
+
+@pytest.mark.parametrize("cfg", list(CONFIGS))
+def test_random_model_oracle_float32_tracks_float64(tmp_path, cfg):
+    mj, q, c = _load(tmp_path, 3, cfg)
+    o = Oracle(mj)
+    x0 = np.concatenate([q, np.zeros(mj.nv)])[None]
+    us = np.tile(c, (1, 60, 1))
+    a, b = o.rollout(x0, us), o.rollout(x0, us, prec=1)
+    assert np.isfinite(a).all() and np.abs(a - b).max() < 5e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", list(CONFIGS))
+@pytest.mark.parametrize("seed", range(10))
+def test_random_model_step_parity(tmp_path, cfg, seed):
+    import torch
+
+    mj, q, c = _load(tmp_path, seed, cfg, iterations=1 + seed % 2)
+    o = Oracle(mj)
+    rng = np.random.default_rng(100 + seed)
+    lo, hi = mj.actuator_ctrlrange[:, 0], mj.actuator_ctrlrange[:, 1]
+    clip = lambda u: np.where(mj.actuator_ctrllimited > 0, np.clip(u, lo, hi), u)
+    # settle onto the floor under the home controls, then a teacher-forced stretch with noisy controls
+    settle = o.rollout(np.concatenate([q, np.zeros(mj.nv)])[None], np.tile(clip(c), (1, 150, 1)))[0, -1]
+    N = 24
+    us = clip(c + 0.2 * rng.normal(size=(N, mj.nu)))
+    qq, vv = settle[: mj.nq].copy(), settle[mj.nq:].copy()
+    ww = o.forward(qq, vv)["qacc_warmstart"]
+    qs, vs, ws, q1, v1, w1, q32, v32 = [], [], [], [], [], [], [], []
+    for t in range(N):
+        qs.append(qq); vs.append(vv); ws.append(ww)
+        a32 = o.step(qq, vv, us[t], ww, prec=1)
+        qq, vv, ww, _ = o.step(qq, vv, us[t], ww)
+        q1.append(qq); v1.append(vv); w1.append(ww); q32.append(a32[0]); v32.append(a32[1])
+    q1, v1, q32, v32 = (np.stack(a) for a in (q1, v1, q32, v32))
+    t32 = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float32, device="cuda")
+    plan = mjx.limb_plan(mj)
+    ran = []
+    for lanes in ((1, 8) if plan["eligible"] else (8, 32)):
+        m = mjx.device_put(mj)
+        m.set_lanes(lanes)
+        d = mjx.Data(qpos=t32(np.stack(qs)), qvel=t32(np.stack(vs)), ctrl=t32(us), qacc=torch.zeros(N, mj.nv, device="cuda"),
+                     qacc_warmstart=t32(np.stack(ws)), time=torch.zeros(N, device="cuda"))
+        d1 = mjx.step(m, d)
+        gq, gv = d1.qpos.cpu().numpy(), d1.qvel.cpu().numpy()
+        assert np.all(np.abs(gq - q1) <= 1e-5 + 1e-4 * np.abs(q1) + 3 * np.abs(q32 - q1)), f"qpos, lanes {lanes}"
+        vmax = np.maximum(1.0, np.abs(v1).max(axis=1))
+        assert np.all(np.abs(gv - v1).max(axis=1) <= 1e-4 * vmax + 3 * np.abs(v32 - v1).max(axis=1)), f"qvel, lanes {lanes}"
+        ran.append(gq)
+    assert not np.array_equal(ran[0], ran[1])  # two different kernels really ran

@@ -15,6 +15,11 @@ reps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
 model = sys.argv[5] if len(sys.argv) > 5 else "barkour"
 path, key = {"barkour": ("models/barkour_standin/barkour_vb_standin.xml", "home"), "biped": ("models/biped_standin/biped_exo_standin.xml", "stand")}[model]
 mj = load_mj_model_from_file(path); m = mjx.device_put(mj)
+import os
+if os.environ.get("ABR_PROF_DISABLE"):  # extra mjtDisableBit flags (e.g. 256 = no warm start, 1 = no constraints): smaller code footprint per step
+    m = m.replace(opt=m.opt.replace(disableflags=int(m.opt.disableflags) | int(os.environ["ABR_PROF_DISABLE"])))
+if os.environ.get("ABR_PROF_LS"):
+    m = m.replace(opt=m.opt.replace(ls_iterations=int(os.environ["ABR_PROF_LS"])))
 if lanes: m.set_lanes(lanes)
 g = torch.Generator(device="cuda"); g.manual_seed(1)
 f = dict(dtype=torch.float32, device="cuda")

@@ -12,7 +12,10 @@ from pathlib import Path
 from ambersim_b200 import _abi
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libabr.so"
+import os
+
+# ABR_LIB: an alternative build of the same library (A/B experiments with compile-time knobs); the default is the in-tree one
+LIB_PATH = Path(os.environ["ABR_LIB"]).resolve() if os.environ.get("ABR_LIB") else _PKG / "libabr.so"
 _lib = None
 
 ABR_OK, ABR_EINVAL, ABR_EUNSUPPORTED, ABR_ECUDA, ABR_ENODEVICE, ABR_ECAPACITY = 0, -1, -2, -3, -4, -5

@@ -35,8 +35,8 @@ CTRL_NOISE, JITTER = 0.1, 0.05
 F_WS = 46349.0
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
 # dram__bytes_read.sum + dram__bytes_write.sum of the C2 launch (one `ncu --set full` capture of this file's
-# own kernel launch, profiles/r1_limb_v3_c2_summary.txt): 198.16 MB + 5.24 MB vs 197.23 MB algorithmic
-NCU_DRAM_BYTES_C2 = 198_161_920 + 5_236_480
+# own kernel launch, profiles/r1_limb_final_c2_summary.txt + .ncu-rep): 198.61 MB + 4.88 MB vs 197.23 MB algorithmic
+NCU_DRAM_BYTES_C2 = 198_606_336 + 4_884_992
 
 
 def peaks():

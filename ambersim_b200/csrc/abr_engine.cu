@@ -81,6 +81,7 @@ struct AbrModel {
   int max_smem = 0;
   cudaStream_t stream = nullptr;  // for the *_host entry points
   cudaStream_t copy_stream = nullptr;  // host->device slices of a pipelined abr_rollout_host
+  const float* dr = nullptr; int dr_E = 0;  // abr_env_set_randomization
   std::vector<cudaEvent_t> ev;
   Scratch s_costs, s_in, s_out, s_dbg, s_traj, s_carry;
 };
@@ -752,8 +753,13 @@ static int launch_rollout(const AbrModel* m, const Layout& L, const RolloutArgs&
     default: return launch_result(launch_rollout_32(cfg, L, a, st));
   }
 }
-static int launch_env(const AbrModel* m, const Layout& L, const EnvArgs& a, cudaStream_t st) {
-  if (a.E <= 0) return ABR_OK;
+static int launch_env(const AbrModel* m, const Layout& L, const EnvArgs& a_in, cudaStream_t st) {
+  if (a_in.E <= 0) return ABR_OK;
+  EnvArgs a = a_in;
+  if (m->dr) {
+    if (a.E != m->dr_E) return fail(ABR_EINVAL, "env call: batch size differs from the one given to abr_env_set_randomization");
+    a.dr = m->dr;
+  }
   if (use_limb(m, L, false, a.dbg != nullptr)) {
     const bool spec = getenv("ABR_LIMB_GENERAL") == nullptr;
     if (L.lNL == 3 && L.lNC == 1) return launch_result(spec && L.l_mx == 2 ? launch_limb_env_3_1_f2(L, a, st) : launch_limb_env_3_1_g(L, a, st));
@@ -1156,6 +1162,12 @@ int abr_env_step_dev(AbrModel* m, float* qpos, float* qvel, float* qacc_warmstar
   a.reset_mask = reset_mask; a.first_qpos = first_qpos; a.first_qvel = first_qvel; a.first_warm = first_qacc_warmstart;
   a.E = E; a.nsubsteps = nsubsteps; a.forward_only = 0;
   return launch_env(m, m->lay, a, (cudaStream_t)stream);
+}
+
+int abr_env_set_randomization(AbrModel* m, const float* dr, int E) {
+  if (!m || E < 0 || (dr && E == 0)) return fail(ABR_EINVAL, "abr_env_set_randomization: bad argument");
+  m->dr = dr; m->dr_E = dr ? E : 0;
+  return ABR_OK;
 }
 
 int abr_env_task_step_dev(AbrModel* m, float* qpos, float* qvel, float* qacc_warmstart, float* time, const float* ctrl, int E, int nsubsteps,

@@ -193,6 +193,7 @@ struct EnvArgs {
   int* t_steps; float* t_obs; float* t_reward; unsigned char* t_done; unsigned char* t_trunc;
   const float* t_qd; const float* t_rd; const float* t_xg;
   float t_zmin; int t_max_steps;
+  const float* dr;  // nullable [E,2]: per-env contact friction scale, actuator strength scale (abr_env_set_randomization)
 };
 
 template <int G>
@@ -206,6 +207,7 @@ __global__ void __launch_bounds__(ABR_TPB, ABR_MINB) k_env(const __grid_constant
   const int w = valid ? wraw : A.E - 1;
   Ctx c{L, smem, reinterpret_cast<const int*>(smem + L.n_mf), smem + L.n_mf + L.n_mi + grp * L.world_stride, (int)(threadIdx.x % G)};
   const int nq = L.nq, nv = L.nv, nu = L.nu;
+  if (A.dr) { c.frs = A.dr[2 * (size_t)w]; c.acs = A.dr[2 * (size_t)w + 1]; }
   init_world<G>(c);
   const bool reset = A.reset_mask && A.reset_mask[w];
   const bool was_done = A.t_steps && A.t_done[w];  // AutoResetWrapper zeroes the counter of an env that finished last step

@@ -223,6 +223,7 @@ template <int LGC> struct LaneCfg {
   const float* T;  // table + lane-in-group
   ShareT<LGC> S;
   float dt, grav[3], mass, tol, ls_tol, meaninertia;
+  float frs, acs;  // per-world domain randomisation: contact friction scale, actuator strength scale (1 = the model's own)
   int iterations, ls_iterations, disableflags, nefc, nv;
 };
 
@@ -465,7 +466,7 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
     const int pc = LTI(mp.icon(c));
     {
       const bool pyr = LTI(mp.icon(c) + 1) == 3;
-      R.mu1[c] = pyr ? LTF(mp.con(c) + 4 + 11) : 0.f; R.mu2[c] = pyr ? LTF(mp.con(c) + 4 + 12) : 0.f;
+      R.mu1[c] = pyr ? C.frs * LTF(mp.con(c) + 4 + 11) : 0.f; R.mu2[c] = pyr ? C.frs * LTF(mp.con(c) + 4 + 12) : 0.f;
     }
     float bx[3] = {xpos[0][0], xpos[0][1], xpos[0][2]}, bq[4] = {xquat[0][0], xquat[0][1], xquat[0][2], xquat[0][3]};
 #pragma unroll
@@ -628,7 +629,7 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
           if (af & 4) gain += prm[5 * kStride] * len + prm[6 * kStride] * vel;
           float bs = 0.f;
           if (af & 8) bs = prm[7 * kStride] + prm[8 * kStride] * len + prm[9 * kStride] * vel;
-          float af_ = gain * ct + bs;
+          float af_ = (gain * ct + bs) * C.acs;
           if (af & 2) af_ = fminf(fmaxf(af_, prm[2 * kStride]), prm[3 * kStride]);
           af_ *= gear;
           t += ((fl & kJAct) && act_on) ? af_ : 0.f;
@@ -688,7 +689,11 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
         const int r = NL + 4 * c + sub;
         const float mu = (sub < 2) ? R.mu1[c] : R.mu2[c];
         const float jvel = bva[c][0] + ((sub & 1) ? -mu : mu) * bva[c][1 + (sub >> 1)];
-        const float invw = (sub < 2 || !pyr) ? prm[7 * kStride] : prm[10 * kStride];
+        float invw = (sub < 2 || !pyr) ? prm[7 * kStride] : prm[10 * kStride];
+        if (pyr && C.frs != 1.f) {  // the pyramid's invweight is t (1 + mu^2) 2 mu^2 / impratio: rescale it with the friction
+          const float mu0 = prm[(sub < 2 ? 11 : 12) * kStride];
+          invw *= C.frs * C.frs * (1.f + mu * mu) / (1.f + mu0 * mu0);
+        }
         row_kbi(prm, pos, jvel, invw, act0 && (pyr || sub == 0), R.D[r], R.aref[r]);
       }
     }
@@ -966,6 +971,7 @@ template <int NL, int NC, int LGC> __device__ __forceinline__ LaneCfg<LGC> make_
   C.T = T + g;
   C.S.own = LTI(mp.ish()); C.S.lvl = LTI(mp.ish() + 1); C.S.mx = L.l_mx; C.S.lg_ = L.lg2G;
   C.dt = L.timestep; C.grav[0] = L.gravity[0]; C.grav[1] = L.gravity[1]; C.grav[2] = L.gravity[2];
+  C.frs = 1.f; C.acs = 1.f;
   C.mass = L.l_mass; C.tol = L.tolerance; C.ls_tol = L.ls_tolerance; C.meaninertia = L.meaninertia;
   C.iterations = L.iterations; C.ls_iterations = L.ls_iterations; C.disableflags = L.disableflags; C.nefc = L.nefc; C.nv = L.nv;
   return C;
@@ -1133,7 +1139,8 @@ __global__ void __launch_bounds__(kTPB, ABR_LIMB_MINB) k_limb_env(const __grid_c
   const int wraw = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> lg);
   const bool valid = wraw < A.E;
   const int w = valid ? wraw : A.E - 1;
-  const LaneCfg<LGC> C = make_cfg<NL, NC, LGC>(L, smem, g);
+  LaneCfg<LGC> C = make_cfg<NL, NC, LGC>(L, smem, g);
+  if (A.dr) { C.frs = A.dr[2 * (size_t)w]; C.acs = A.dr[2 * (size_t)w + 1]; }
   const bool reset = A.reset_mask && A.reset_mask[w];
   const bool was_done = A.t_steps && A.t_done[w];  // AutoResetWrapper zeroes the counter of an env that finished last step
   const float* sq = (reset ? A.first_qpos : A.qpos) + (size_t)w * nq;

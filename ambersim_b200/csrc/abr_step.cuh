@@ -30,6 +30,8 @@ struct Ctx {
   const int* mi;    // model int pool (shared memory)
   float* W;         // this world's shared-memory region
   int lane;         // lane within the group
+  float frs = 1.f;  // per-world domain randomisation: contact friction scale ...
+  float acs = 1.f;  // ... and actuator strength scale (abr_env_set_randomization)
 };
 
 // ------------------------------------------------------------------------------ small math
@@ -603,7 +605,7 @@ template <int G> __device__ void mul_j(const Ctx& c, const float* v, float* out)
       s = bv[3 * idx];
       if (MI(con_condim)[idx] == 3) {
         const float* prm = MF(con_prm) + kConPrm * MI(con_pair)[idx];
-        const float mu = prm[11 + (sub >> 1)];
+        const float mu = c.frs * prm[11 + (sub >> 1)];
         s += ((sub & 1) ? -mu : mu) * bv[3 * idx + 1 + (sub >> 1)];
       }
     }
@@ -623,8 +625,8 @@ template <int G> __device__ void mul_jt(const Ctx& c, const float* f, float* out
       const float* prm = MF(con_prm) + kConPrm * MI(con_pair)[ci];
       const float f0 = f[r0], f1 = f[r0 + 1], f2 = f[r0 + 2], f3 = f[r0 + 3];
       Fc[3 * ci] = f0 + f1 + f2 + f3;
-      Fc[3 * ci + 1] = prm[11] * (f0 - f1);
-      Fc[3 * ci + 2] = prm[12] * (f2 - f3);
+      Fc[3 * ci + 1] = c.frs * prm[11] * (f0 - f1);
+      Fc[3 * ci + 2] = c.frs * prm[12] * (f2 - f3);
     } else {
       Fc[3 * ci] = f[r0]; Fc[3 * ci + 1] = 0.f; Fc[3 * ci + 2] = 0.f;
     }
@@ -711,9 +713,11 @@ template <int G> __device__ void stage_rows(const Ctx& c) {
       invw = prm[7];
       if (MI(con_condim)[idx] == 3) {
         const int k = sub >> 1;
-        const float mu = prm[11 + k];
+        const float mu0 = prm[11 + k], mu = c.frs * mu0;
         jvel += ((sub & 1) ? -mu : mu) * bv[3 * idx + 1 + k];
         invw = (k == 0) ? prm[7] : prm[10];
+        // the pyramid's invweight is t (1 + mu^2) 2 mu^2 / impratio: rescale it with the friction
+        if (c.frs != 1.f) invw *= c.frs * c.frs * (1.f + mu * mu) / (1.f + mu0 * mu0);
       }
     }
     float Dr = 0.f, ar = 0.f;
@@ -827,7 +831,7 @@ template <int G> __device__ void stage_velocity(const Ctx& c) {
       if (flags & 4) gain += prm[5] * len + prm[6] * vel;
       float bias = 0.f;
       if (flags & 8) bias = prm[7] + prm[8] * len + prm[9] * vel;
-      f = gain * ct + bias;
+      f = (gain * ct + bias) * c.acs;
       if (flags & 2) f = fminf(fmaxf(f, prm[2]), prm[3]);
       f *= prm[10];
     }
@@ -905,7 +909,7 @@ template <int G> __device__ void solver_hessian(const Ctx& c, const float* Jaref
     float o0, o1, o2;
     if (MI(con_condim)[ci] == 3) {
       const float* prm = MF(con_prm) + kConPrm * MI(con_pair)[ci];
-      const float mu1 = prm[11], mu2 = prm[12];
+      const float mu1 = c.frs * prm[11], mu2 = c.frs * prm[12];
       const float w0 = (Jaref[r0] < 0.f) ? D[r0] : 0.f, w1 = (Jaref[r0 + 1] < 0.f) ? D[r0 + 1] : 0.f;
       const float w2 = (Jaref[r0 + 2] < 0.f) ? D[r0 + 2] : 0.f, w3 = (Jaref[r0 + 3] < 0.f) ? D[r0 + 3] : 0.f;
       const float W00 = w0 + w1 + w2 + w3, W01 = mu1 * (w0 - w1), W02 = mu2 * (w2 - w3);

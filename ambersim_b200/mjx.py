@@ -256,13 +256,29 @@ def step(m: Model, d: Data, nsubsteps: int = 1) -> Data:
     batch = _batch_shape(m, d)
     qpos, qvel = _flat(d.qpos, m.nq, dev, batch), _flat(d.qvel, m.nv, dev, batch)
     ctrl, warm = _flat(d.ctrl, m.nu, dev, batch), _flat(d.qacc_warmstart, m.nv, dev, batch)
-    time = torch.as_tensor(d.time, dtype=torch.float32, device=dev).expand(*batch).reshape(-1).contiguous().clone()
+    time = torch.as_tensor(d.time, dtype=torch.float32, device=dev).broadcast_to(batch).reshape(-1).contiguous().clone()
     E = qpos.shape[0]
     _lib.check(_lib.lib().abr_env_step_dev(h.ptr, _ptr(qpos), _ptr(qvel), _ptr(warm), _ptr(time), _ptr(ctrl), E,
                                            int(nsubsteps), None, None, None, None, _stream(dev)))
     rs = lambda t, n: t.reshape(*batch, n)
     return d.replace(qpos=rs(qpos, m.nq), qvel=rs(qvel, m.nv), ctrl=rs(ctrl, m.nu), qacc_warmstart=rs(warm, m.nv),
                      time=time.reshape(batch))
+
+
+def set_randomization(m: Model, dr: Optional[torch.Tensor]) -> None:
+    """Per-env domain randomisation for the env entry points (forward / step with a leading batch of E envs):
+    dr (E, 2) = {contact friction scale, actuator strength scale} on the device, or None to switch it off.
+    The tensor is referenced, not copied: it is kept alive on the model until replaced."""
+    if dr is None:
+        for h in m._handles.values():
+            _lib.check(_lib.lib().abr_env_set_randomization(h.ptr, None, 0))
+        m._dr = None
+        return
+    dr = dr.to(torch.float32).contiguous()
+    assert dr.dim() == 2 and dr.shape[1] == 2 and dr.is_cuda
+    h = m.handle(dr.device.index or 0)
+    _lib.check(_lib.lib().abr_env_set_randomization(h.ptr, _ptr(dr), dr.shape[0]))
+    m._dr = dr
 
 
 def debug_forward(m: Model, qpos, qvel, ctrl=None, qacc_warmstart=None, names=()):

@@ -145,7 +145,10 @@ class FusedQuadraticTaskEnv:
     The state tensors are updated IN PLACE (the returned `State` aliases the env's buffers): this is the
     training hot loop, not a functional API. `step` never synchronises."""
 
-    def __init__(self, env: QuadraticTaskEnv, episode_length: int):
+    def __init__(self, env: QuadraticTaskEnv, episode_length: int, randomization: Optional[torch.Tensor] = None):
+        """randomization: optional (num_envs, 2) tensor of per-env {contact friction scale, actuator strength scale}
+        (abr_env_set_randomization): every env then steps its own variant of the model."""
+        self.randomization = randomization
         if not torch.equal(env.reward_fn.Q, torch.diag(torch.diagonal(env.reward_fn.Q))) or \
                 not torch.equal(env.reward_fn.R, torch.diag(torch.diagonal(env.reward_fn.R))):
             raise NotImplementedError("the fused reward takes diagonal Q and R")
@@ -156,10 +159,14 @@ class FusedQuadraticTaskEnv:
         return self.env
 
     def reset(self, rng) -> State:
+        E = self.env.num_envs
+        if self.randomization is not None:  # installed before pipeline_init so the cached first state's warm start sees it too
+            dev0 = mjx._dev(self.env._device)
+            self._dr = self.randomization.to(device=dev0, dtype=torch.float32).reshape(E, 2).contiguous()
+            mjx.set_randomization(self.env.sys, self._dr)
         s = self.env.reset(rng)
         d = s.pipeline_state
         dev = d.qpos.device
-        E = self.env.num_envs
         self._first = tuple(t.contiguous().clone() for t in (d.qpos, d.qvel, d.qacc_warmstart))
         self._buf = dict(qpos=d.qpos.contiguous().clone(), qvel=d.qvel.contiguous().clone(), warm=d.qacc_warmstart.contiguous().clone(),
                          time=torch.zeros(E, device=dev), steps=torch.zeros(E, dtype=torch.int32, device=dev),

@@ -269,6 +269,15 @@ int abr_env_step_dev(AbrModel* m, float* qpos, float* qvel, float* qacc_warmstar
                      const float* first_qpos, const float* first_qvel,
                      const float* first_qacc_warmstart, void* stream);
 
+/* ---- per-env domain randomisation of model parameters (ambersim/trajopt/base.py:49-58 rationale) ----
+ * dr: DEVICE pointer [E,2] = {contact friction scale, actuator strength scale} per env, or NULL to switch it off.
+ * The friction scale multiplies both tangential coefficients of every contact of the env (and rescales the
+ * pyramid rows' invweight accordingly, as if pair_friction had been scaled before mjx.device_put); the actuator
+ * scale multiplies gainprm and biasprm (the actuator force before its forcerange clamp). The pointer is kept,
+ * not copied (caller-owned, must outlive the env calls); abr_forward_dev / abr_env_step_dev /
+ * abr_env_task_step_dev then require the same E. */
+int abr_env_set_randomization(AbrModel* m, const float* dr, int E);
+
 /* ---- one whole training-env step in ONE launch: MjxEnv.step of a quadratic
  * tracking task wrapped in brax's EpisodeWrapper + AutoResetWrapper, E envs in place, DEVICE pointers.
  *   physics : nsubsteps x mjx.step with ctrl held (rl/base.py:88-96)

@@ -599,3 +599,46 @@ def test_fused_task_env_equals_wrapper_chain(load_model, name, lanes):
                 if not bool(s_f.done[e]):
                     assert np.all(np.abs(df.qpos[e].cpu().numpy() - qr) <= 2e-5 + 2e-4 * np.abs(qr))
     assert n_trunc > 0 and n_term > 0
+
+
+@pytest.mark.parametrize("name,lanes", [("barkour", 0), ("barkour", 8), ("biped", 0), ("tripod", 0), ("tripod", 16)])
+def test_env_domain_randomization(load_model, name, lanes):
+    """abr_env_set_randomization: every env steps its own variant of the model (contact friction scale, actuator strength
+    scale). Each env is compared with an oracle built from a model whose pair_friction / gainprm / biasprm were scaled
+    BEFORE loading; scale (1, 1) reproduces the unrandomised step bit for bit."""
+    import copy
+
+    mj, m, _ = model_with(load_model, name)
+    if lanes:
+        m.set_lanes(lanes)
+    rng = np.random.default_rng(17)
+    dr = np.array([[1.0, 1.0], [0.5, 1.0], [1.6, 0.8], [0.7, 1.3], [1.0, 0.6], [0.3, 1.15]])
+    E = len(dr)
+    q, v, c = sample_state(mj, name, rng)
+    v[:2] += 0.5  # sliding feet: the friction rows are active
+    w = rng.normal(size=mj.nv)
+    tile = lambda a: t32(np.tile(a, (E, 1)))
+    d = mjx.Data(qpos=tile(q), qvel=tile(v), ctrl=tile(c), qacc=torch.zeros(E, mj.nv, device=DEV), qacc_warmstart=tile(w),
+                 time=torch.zeros(E, device=DEV))
+    plain = mjx.step(m, d)
+    mjx.set_randomization(m, t32(dr))
+    out = mjx.step(m, d)
+    with pytest.raises(_lib.AbrError):  # a different batch size than the randomisation table is an error, not a guess
+        mjx.step(m, mjx.Data(qpos=t32(q), qvel=t32(v), ctrl=t32(c), qacc=t32(v), qacc_warmstart=t32(w), time=torch.zeros((), device=DEV)))
+    mjx.set_randomization(m, None)
+    assert torch.equal(mjx.step(m, d).qpos, plain.qpos)
+    assert torch.equal(out.qpos[0], plain.qpos[0]) and torch.equal(out.qvel[0], plain.qvel[0])
+    assert not torch.equal(out.qvel[1], plain.qvel[1]) and not torch.equal(out.qvel[4], plain.qvel[4])
+    for e in range(E):
+        mj_e = copy.deepcopy(mj)
+        mj_e.pair_friction = np.array(mj.pair_friction, dtype=np.float64).copy()
+        mj_e.pair_friction[:, :2] *= dr[e, 0]
+        mj_e.actuator_gainprm = np.array(mj.actuator_gainprm, dtype=np.float64) * dr[e, 1]
+        mj_e.actuator_biasprm = np.array(mj.actuator_biasprm, dtype=np.float64) * dr[e, 1]
+        o = Oracle(mj_e, m.opt)
+        qr, vr, wr, _ = o.step(q, v, c, w)
+        q32, v32, _, _ = o.step(q, v, c, w, prec=1)
+        assert np.all(np.abs(out.qpos[e].cpu().numpy() - qr) <= 1e-5 + 1e-4 * np.abs(qr) + 3 * np.abs(q32 - qr)), f"env {e}"
+        assert np.abs(out.qvel[e].cpu().numpy() - vr).max() <= 1e-4 * max(1.0, np.abs(vr).max()) + 3 * np.abs(v32 - vr).max(), f"env {e}"
+    # the randomised oracles really differ from each other by far more than the tolerance
+    assert np.abs(out.qvel[1].cpu().numpy() - out.qvel[2].cpu().numpy()).max() > 1e-3

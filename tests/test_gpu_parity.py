@@ -642,3 +642,46 @@ def test_env_domain_randomization(load_model, name, lanes):
         assert np.abs(out.qvel[e].cpu().numpy() - vr).max() <= 1e-4 * max(1.0, np.abs(vr).max()) + 3 * np.abs(v32 - vr).max(), f"env {e}"
     # the randomised oracles really differ from each other by far more than the tolerance
     assert np.abs(out.qvel[1].cpu().numpy() - out.qvel[2].cpu().numpy()).max() > 1e-3
+
+
+@pytest.mark.parametrize("name", ["bh280", "barkour"])
+def test_finite_difference_shooting(load_model, name):
+    """Gradient-based shooting on the engine: the central-difference gradient (2 N nu + 1 rollouts in one launch) equals the
+    float64 oracle's on the contact-free hand, and on both models the descent never raises the cost and ends below the
+    start, with the returned trajectory being the rollout of the returned controls."""
+    from ambersim_b200.trajopt.shooting import FiniteDifferenceShooting, ShootingParams
+
+    mj, m, o = model_with(load_model, name)
+    rng = np.random.default_rng(23)
+    nx, N = mj.nq + mj.nv, 6
+    if name == "bh280":
+        x0 = np.zeros(nx)
+        xg = np.concatenate([rng.uniform(0.1, 0.6, mj.nq), np.zeros(mj.nv)])
+        us = rng.uniform(0.0, 0.3, (N, mj.nu))
+    else:
+        x0 = np.concatenate([mj.key_qpos("home"), np.zeros(mj.nv)])
+        xg = x0.copy()
+        xg[7:mj.nq] += rng.uniform(-0.2, 0.2, mj.nq - 7)
+        us = np.tile(mj.key_ctrl("home"), (N, 1))
+    Q, Qf, R = np.eye(nx), 10 * np.eye(nx), 0.01 * np.eye(mj.nu)
+    cf = StaticGoalQuadraticCost(Q, Qf, R, xg)
+    fd = FiniteDifferenceShooting(model=m, cost_function=cf, iterations=6, eps=1e-2)
+    c0, g = fd.gradient(t32(x0), t32(us))
+    if name == "bh280":
+        ref = np.zeros((N, mj.nu))
+        for t in range(N):
+            for u in range(mj.nu):
+                up, dn = us.copy(), us.copy()
+                up[t, u] += 1e-2
+                dn[t, u] -= 1e-2
+                cp, cm = (quad_cost(o.rollout(x0[None], a[None]), a[None], Q, Qf, R, xg)[0] for a in (up, dn))
+                ref[t, u] = (cp - cm) / 2e-2
+        assert np.abs(g.cpu().numpy() - ref).max() <= 2e-2 * np.abs(ref).max()
+    xs, us_star, info = fd.optimize(ShootingParams(x0=t32(x0), us_guess=t32(us)), return_info=True)
+    costs = info["costs"].cpu().numpy()
+    assert np.isclose(costs[0], float(c0), rtol=1e-6)
+    assert np.all(np.diff(costs) <= 0) and costs[-1] < 0.98 * costs[0]
+    assert torch.equal(xs, shoot(m, t32(x0), us_star))
+    lo, hi = mj.actuator_ctrlrange[:, 0], mj.actuator_ctrlrange[:, 1]
+    lim = mj.actuator_ctrllimited > 0
+    assert np.all((us_star.cpu().numpy() >= lo - 1e-6)[:, lim]) and np.all((us_star.cpu().numpy() <= hi + 1e-6)[:, lim])

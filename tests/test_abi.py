@@ -49,3 +49,37 @@ def test_product_does_not_import_the_oracle():
         text = f.read_text()
         assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
         assert "abr_oracle" not in text, f
+
+
+def test_argument_validation_needs_no_device():
+    """Bad arguments are refused with ABR_EINVAL before any CUDA call (error codes + abr_last_error, never an exception or a crash)."""
+    L = _lib.lib()
+    assert L.abr_rollout_dev(None, None, 0, None, 0, 4, 4, None, None, None, None) == _lib.ABR_EINVAL
+    assert b"abr_rollout_dev" in L.abr_last_error()
+    assert L.abr_rollout_dev(None, None, 0, None, 0, -1, 4, None, None, None, None) == _lib.ABR_EINVAL
+    assert L.abr_rollout_host(None, None, 0, None, 0, 4, 4, None, None, None) == _lib.ABR_EINVAL
+    assert L.abr_forward_dev(None, None, None, None, None, None, 3, None) == _lib.ABR_EINVAL
+    assert L.abr_env_step_dev(None, None, None, None, None, None, 3, 1, None, None, None, None, None) == _lib.ABR_EINVAL
+    assert L.abr_env_task_step_dev(None, None, None, None, None, None, 3, 1, None, None, None, None, 0.0, 10, None, None, None, None, None,
+                                   None) == _lib.ABR_EINVAL
+    assert L.abr_env_task_step_dev(None, None, None, None, None, None, 3, 0, None, None, None, None, 0.0, 10, None, None, None, None, None,
+                                   None) == _lib.ABR_EINVAL  # nsubsteps < 1
+    assert L.abr_env_set_randomization(None, None, 0) == _lib.ABR_EINVAL
+    assert L.abr_predictive_sample_dev(None, None, None, None, None, 0, 1, 8, 4, 0.1, 0, 8, None, None, None, None, None, None) == _lib.ABR_EINVAL
+    assert L.abr_mpc_dev(None, None, None, None, 0, 8, 4, 0.1, 2, None, None, None, None, None) == _lib.ABR_EINVAL
+    handle = C.create_string_buffer(64)
+    x = C.c_void_p()
+    for nranks, rank, cap in ((0, 0, 16), (9, 0, 16), (2, 2, 16), (2, -1, 16), (2, 0, 0)):
+        assert L.abr_xchg_create(0, nranks, rank, cap, C.byref(x), handle) == _lib.ABR_EINVAL
+    assert L.abr_xchg_create(0, 2, 0, 16, None, handle) == _lib.ABR_EINVAL
+    assert L.abr_xchg_connect(None, handle) == _lib.ABR_EINVAL
+    assert L.abr_xchg_merge_best_dev(None, None, None, None, None, 1, 4, 2, None, None, None, None, None) == _lib.ABR_EINVAL
+    assert L.abr_xchg_destroy(None) == _lib.ABR_OK and L.abr_model_destroy(None) == _lib.ABR_OK and L.abr_cost_destroy(None) == _lib.ABR_OK
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful on a box without a GPU")
+def test_exchange_refuses_without_a_device():
+    L = _lib.lib()
+    handle = C.create_string_buffer(64)
+    x = C.c_void_p()
+    assert L.abr_xchg_create(0, 2, 0, 16, C.byref(x), handle) == _lib.ABR_ENODEVICE

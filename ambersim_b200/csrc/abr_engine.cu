@@ -954,6 +954,28 @@ int abr_cost_destroy(AbrCost* c) {
   return ABR_OK;
 }
 
+int abr_model_reserve(AbrModel* m, int nworld, int N, int B, int S) {
+  if (!m || nworld < 0 || N < 0 || B < 0 || S < 0) return fail(ABR_EINVAL, "abr_model_reserve: bad argument");
+  CK(cudaSetDevice(m->device));
+  const size_t nx = m->lay.nx, nu = m->lay.nu, nxs = (size_t)(N + 1) * nx, nus = (size_t)N * nu;
+  int rc = ABR_OK;
+  if (B > 0 && S > 0) {  // sampler: per-sample costs, kept trajectories (when under the cap), host staging of one solve
+    rc = m->s_costs.ensure(sizeof(float) * (size_t)B * S);
+    size_t keep_cap = (size_t)256 << 20;
+    if (const char* e = getenv("ABR_KEEP_TRAJ_MB")) keep_cap = (size_t)atol(e) << 20;
+    const size_t traj_bytes = sizeof(float) * (size_t)B * S * (nxs + nus);
+    if (!rc && traj_bytes <= keep_cap) rc = m->s_traj.ensure(traj_bytes + 16);
+    if (!rc) rc = m->s_in.ensure(sizeof(float) * ((size_t)B * nx + (size_t)B * nus * S + 4));
+    if (!rc) rc = m->s_out.ensure(sizeof(float) * ((size_t)B * (nxs + nus) + (size_t)B * S + 2 * (size_t)B + 8));
+  }
+  if (!rc && nworld > 0) {  // host rollouts: controls and states in, trajectories and costs out, the slice carry
+    rc = m->s_in.ensure(sizeof(float) * ((size_t)nworld * (nx + nus) + 4));
+    if (!rc) rc = m->s_out.ensure(sizeof(float) * ((size_t)nworld * (nxs + 1) + 4));
+    if (!rc) rc = m->s_carry.ensure(sizeof(float) * (size_t)nworld * (m->lay.nq + 2 * m->lay.nv + 8));
+  }
+  return rc;
+}
+
 int abr_rollout_dev(AbrModel* m, const float* x0, int x0_stride, const float* us, int us_stride, int nworld, int N,
                     float* xs_out, const AbrCost* cost, float* costs_out, void* stream) {
   if (nworld < 0 || N < 0) return fail(ABR_EINVAL, "abr_rollout_dev: negative size");

@@ -220,6 +220,12 @@ int abr_model_set_lanes(AbrModel* m, int lanes);
  * Arrays may be NULL; cap = ints available in lane_body. */
 int abr_limb_plan_host(const AbrModelHost* host, int* info, int* lane_body, int cap, int* lane_own, int* lane_lvl);
 
+/* Memory: the handle owns its scratch (per-sample costs, kept sample trajectories, staging of the *_host calls, the
+ * slice carry) and grows it on first use; steady-state calls allocate nothing. abr_model_reserve sizes it up front
+ * for rollouts of nworld worlds x N steps and solves of B problems x S samples x N steps, so that no later call of
+ * at most those sizes allocates (the role of a workspace query + caller-provided workspace). */
+int abr_model_reserve(AbrModel* m, int nworld, int N, int B, int S);
+
 int abr_cost_create(const AbrQuadCostHost* host, int device, AbrCost** out);
 int abr_cost_destroy(AbrCost* c);
 

@@ -685,3 +685,19 @@ def test_finite_difference_shooting(load_model, name):
     lo, hi = mj.actuator_ctrlrange[:, 0], mj.actuator_ctrlrange[:, 1]
     lim = mj.actuator_ctrllimited > 0
     assert np.all((us_star.cpu().numpy() >= lo - 1e-6)[:, lim]) and np.all((us_star.cpu().numpy() <= hi + 1e-6)[:, lim])
+
+
+def test_model_reserve_presizes_scratch(load_model, vps_data=None):
+    """abr_model_reserve sizes the handle-owned scratch up front; results are unchanged by it."""
+    mj, m, _ = model_with(load_model, "barkour")
+    nx = mj.nq + mj.nv
+    q0 = np.concatenate([mj.key_qpos("home"), np.zeros(mj.nv)])
+    cf = StaticGoalQuadraticCost(np.eye(nx), 10 * np.eye(nx), 0.01 * np.eye(mj.nu), q0)
+    ps = VanillaPredictiveSampler(model=m, cost_function=cf, nsamples=256, stdev=0.1)
+    prm = VanillaPredictiveSamplerParams(key=1, x0=t32(q0), us_guess=t32(np.tile(mj.key_ctrl("home"), (16, 1))))
+    xs_a, us_a = ps.optimize(prm)
+    m2 = mjx.device_put(mj).replace(opt=m.opt)
+    h = m2.handle()
+    _lib.check(_lib.lib().abr_model_reserve(h.ptr, 512, 64, 1, 256))
+    xs_b, us_b = VanillaPredictiveSampler(model=m2, cost_function=cf, nsamples=256, stdev=0.1).optimize(prm)
+    assert torch.equal(xs_a, xs_b) and torch.equal(us_a, us_b)

@@ -701,3 +701,27 @@ def test_model_reserve_presizes_scratch(load_model, vps_data=None):
     _lib.check(_lib.lib().abr_model_reserve(h.ptr, 512, 64, 1, 256))
     xs_b, us_b = VanillaPredictiveSampler(model=m2, cost_function=cf, nsamples=256, stdev=0.1).optimize(prm)
     assert torch.equal(xs_a, xs_b) and torch.equal(us_a, us_b)
+
+
+@pytest.mark.parametrize("name", ["pendulum", "bh280", "barkour", "biped"])
+def test_committed_golden_fixtures(load_model, name):
+    """The CUDA path against the fixtures committed under tests/golden/ (float64 oracle rollouts written by
+    tools/make_oracle_fixtures.py; an MJX dump, mjx_<model>.npz from tools/dump_mjx_golden.py, is used too when present):
+    same inputs, same options, free-running 20-step rollouts within the rollout bounds of this file's header."""
+    from pathlib import Path
+
+    gold = Path(__file__).parent / "golden"
+    used = 0
+    for path, tol_free, tol_contact in ((gold / f"oracle_{name}.npz", 1e-3, 5e-3), (gold / f"mjx_{name}.npz", 2e-3, 1e-2)):
+        if not path.exists():
+            continue
+        z = np.load(path)
+        opt = {k[4:]: (float(z[k]) if k == "opt_timestep" else int(z[k])) for k in z.files if k.startswith("opt_")}
+        mj, m, o = model_with(load_model, name, **opt)
+        xs = shoot(m, t32(z["x0"]), t32(z["us"])).cpu().numpy()
+        assert xs.shape == z["xs"].shape
+        drift32 = np.abs(o.rollout(z["x0"], z["us"], prec=1) - z["xs"]).max() if "oracle" in path.name else 0.0
+        tol = tol_free if name in ("pendulum", "bh280") else tol_contact
+        assert np.abs(xs - z["xs"]).max() < max(tol, 3 * drift32), path.name
+        used += 1
+    assert used >= 1

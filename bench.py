@@ -466,7 +466,30 @@ def main():
                 ps.optimize(prm)
             b.record(stream)
             torch.cuda.synchronize(device)
-            out["extra"] = {"vps_4096x32_solve_ms": a.elapsed_time(b) / reps,
+            # the same solve replayed from a CUDA graph (the *_dev calls are stream-ordered and allocation-free once warm)
+            graph_ms = None
+            try:
+                side = torch.cuda.Stream(device)
+                side.wait_stream(stream)
+                with torch.cuda.stream(side):
+                    ps.optimize(prm)
+                stream.wait_stream(side)
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    ps.optimize(prm)
+                for _ in range(3):
+                    gr.replay()
+                torch.cuda.synchronize(device)
+                ga, gb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ga.record(stream)
+                for _ in range(reps):
+                    gr.replay()
+                gb.record(stream)
+                torch.cuda.synchronize(device)
+                graph_ms = ga.elapsed_time(gb) / reps
+            except Exception as e:  # reported, not fatal: the direct-launch number above is the metric
+                graph_ms = f"capture failed: {e}"
+            out["extra"] = {"vps_4096x32_solve_ms": a.elapsed_time(b) / reps, "vps_4096x32_solve_ms_cuda_graph": graph_ms,
                             "vps_note": "VanillaPredictiveSampler.optimize, device-resident inputs: rollouts + argmin + winner gather (3 launches)"}
             if sharded is not None:
                 out["extra"]["c4_sharded_solve_ms_by_samples_x32"] = sharded

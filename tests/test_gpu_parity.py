@@ -725,3 +725,36 @@ def test_committed_golden_fixtures(load_model, name):
         assert np.abs(xs - z["xs"]).max() < max(tol, 3 * drift32), path.name
         used += 1
     assert used >= 1
+
+
+def test_solve_is_cuda_graph_capturable(load_model):
+    """The *_dev entry points are stream-ordered, never synchronise and (after a first call has sized the scratch) never
+    allocate: a predictive-sampling solve captures into a CUDA graph and replays with bit-identical results on new inputs."""
+    mj, m, _ = model_with(load_model, "barkour")
+    nx = mj.nq + mj.nv
+    q0 = np.concatenate([mj.key_qpos("home"), np.zeros(mj.nv)])
+    cf = StaticGoalQuadraticCost(np.eye(nx), 10 * np.eye(nx), 0.01 * np.eye(mj.nu), q0)
+    ps = VanillaPredictiveSampler(model=m, cost_function=cf, nsamples=512, stdev=0.2)
+    rng = np.random.default_rng(5)
+    x_in = t32(q0)
+    g_in = t32(np.tile(mj.key_ctrl("home"), (8, 1)))
+    prm = VanillaPredictiveSamplerParams(key=9, x0=x_in, us_guess=g_in)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            ps.optimize(prm)  # sizes the handle's scratch outside the capture
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        xs_g, us_g = ps.optimize(prm)
+    for trial in range(3):
+        x_new = q0.copy()
+        x_new[7:19] += rng.uniform(-0.1, 0.1, 12)
+        x_in.copy_(t32(x_new))
+        g_in.copy_(t32(np.clip(mj.key_ctrl("home") + 0.2 * rng.normal(size=(8, mj.nu)), mj.actuator_ctrlrange[:, 0], mj.actuator_ctrlrange[:, 1])))
+        graph.replay()
+        torch.cuda.synchronize()
+        xs_r, us_r = xs_g.clone(), us_g.clone()
+        xs_d, us_d = ps.optimize(prm)
+        assert torch.equal(xs_r, xs_d) and torch.equal(us_r, us_d), f"trial {trial}"

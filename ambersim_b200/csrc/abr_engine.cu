@@ -717,6 +717,14 @@ static int pick_lanes(const AbrModel* m, int nworld) {
   if (m->lanes > 1) return m->lanes;
   const char* e = getenv("ABR_LANES");
   if (e && atoi(e) > 1) return atoi(e);
+  // small models (a hand, a pendulum) have too little work per world for 32 lanes: as soon as narrower groups still give
+  // every SM sub-partition a warp, they win (bh280, 4096 x 32 solve: 2.07 ms with 8 lanes, 3.55 ms with 32)
+  if (m->lay.nv <= 10) {
+    const long subparts = 4L * m->num_sms;
+    if ((long)nworld * 8 / 32 >= subparts / 2) return 8;
+    if ((long)nworld * 16 / 32 >= subparts / 2) return 16;
+    return 32;
+  }
   // enough worlds to fill the machine with narrow groups -> better lane efficiency
   const long per_sm = (long)nworld / m->num_sms;
   if (per_sm >= 256) return 8;

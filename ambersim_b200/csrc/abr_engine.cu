@@ -1022,7 +1022,7 @@ int abr_rollout_host(AbrModel* m, const float* x0, int x0_stride, const float* u
   // Pipelined form (limb kernels, long horizons): the controls go up in horizon slices on a copy stream
   // while the previous slice's steps run; state and running cost pass between the slice launches in `carry`.
   int nslice = 1;
-  if (us_stride != 0 && N >= 64 && getenv("ABR_NO_PIPELINE") == nullptr && use_limb(m, m->lay, costs_out && cost && !cost->diag, false)) nslice = 8;
+  if (us_stride != 0 && N >= 64 && getenv("ABR_NO_PIPELINE") == nullptr && use_limb(m, m->lay, costs_out && cost && !cost->diag, false)) nslice = 16;
   if (const char* e = getenv("ABR_SLICES")) { const int v = atoi(e); if (v >= 1 && v <= 64 && nslice > 1) nslice = v; }
   if (nslice == 1) {
     if (n_us) CK(cudaMemcpyAsync(d_us, us, sizeof(float) * n_us, cudaMemcpyHostToDevice, m->stream));

@@ -33,6 +33,7 @@ CTRL_NOISE, JITTER = 0.1, 0.05
 # algorithmic FLOPs of one world-step: op-counting build of the CPU oracle, "necessary
 # work" variant (no unused post-iteration Hessian), home state: add=sub=mul=div=sqrt=sin=cos=pow=1.
 F_WS = 46349.0
+F_WS_BIPED = 130142.0  # same counter, biped stand-in at its standing keyframe
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
 # dram__bytes_read.sum + dram__bytes_write.sum of the C2 launch (one `ncu --set full` capture of this file's
 # own kernel launch, profiles/r1_limb_final_c2_summary.txt + .ncu-rep): 198.61 MB + 4.88 MB vs 197.23 MB algorithmic
@@ -225,7 +226,8 @@ def extra_configs(mj, m, cf, q0, torch, device, stream, L, peak_tf):
     bnx = bj.nq + bj.nv
     bcf = StaticGoalQuadraticCost(np.eye(bnx), 10.0 * np.eye(bnx), 0.01 * np.eye(bj.nu), bq0)
     rate, fin = rollout_rate(bj, bm, bcf, "stand", 16384, 1000, CTRL_NOISE)
-    ex["c3_biped_16384x1000"] = {"world_steps_per_s": rate, "costs_finite": fin,
+    ex["c3_biped_16384x1000"] = {"world_steps_per_s": rate, "costs_finite": fin, "flop_per_world_step": F_WS_BIPED,
+                                 "frac_of_ffma_peak": F_WS_BIPED * rate / 1e12 / peak_tf,
                                  "model": "biped_exo_standin (nq=28 nv=27 nu=21 nbody=23 ncon=8 nefc=53; Newton it=1 ls=6 Euler dt=.004)"}
     sweep = {}
     prm = VanillaPredictiveSamplerParams(key=3, x0=torch.tensor(q0, **f), us_guess=torch.tensor(mj.key_ctrl("home"), **f).repeat(32, 1))

@@ -17,10 +17,8 @@ def random_limb_model(seed: int, max_chain: int = 3, max_con: int = 1, max_leave
     """Returns (xml, home_qpos, home_ctrl). Chains have <= max_chain joints between trunk and leaf and at most
     max_con foot spheres per root-to-leaf path (the capacity of the compiled limb kernels: (3,1) and (6,4))."""
     rng = np.random.default_rng(seed)
-    bodies, joints, acts, qpos, ctrl = [], [], [], [], []
-    counter = [0]
-
-    leaves = [0]
+    acts, qpos, ctrl = [], [], []
+    counter, leaves = [0], [0]
 
     def body(pos, remaining, budget_con, prefix, may_fork):
         """One chain body at `pos` in its parent's frame, with `remaining` more bodies below it on this path."""

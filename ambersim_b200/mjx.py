@@ -194,6 +194,10 @@ def device_put(mj_model: MjModel) -> Model:
     """mjx.device_put(mj_model): flatten the MjModel into the structure-of-arrays the engine uploads."""
     if isinstance(mj_model, Model):
         return mj_model
+    from ambersim_b200.utils import mjmodel
+
+    if mjmodel.looks_like_mjmodel(mj_model):  # a real mujoco.MjModel (io_utils.py:225, rl/base.py:52): flatten it first
+        mj_model = mjmodel.from_mjmodel(mj_model)
     return Model(mj_model)
 
 

@@ -4,8 +4,8 @@
     mj_to_mjx_model_and_data(mj_model) -> (mjx.Model, mjx.Data)
     load_mjx_model_and_data_from_file(filepath, force_float) -> (mjx.Model, mjx.Data)
 
-`mujoco` is not installable here, so MJCF files are compiled by ambersim_b200.utils.mjcf (a real
-`mujoco.MjModel` cannot be flattened without that package). URDF munging (reference
+`mujoco` is not installable here, so MJCF files are compiled by ambersim_b200.utils.mjcf; a real
+`mujoco.MjModel` handed in by a caller who has the package is flattened by ambersim_b200.utils.mjmodel. URDF munging (reference
 io_utils.py:18-136) is MuJoCo-compiler work and out of scope.
 """
 from __future__ import annotations
@@ -59,11 +59,7 @@ def load_mj_model_from_file(
 
 def mj_to_mjx_model_and_data(mj_model, device=None) -> Tuple[mjx.Model, mjx.Data]:
     """Converts a host model to an (mjx.Model, mjx.Data) pair (reference io_utils.py:222-241)."""
-    if not isinstance(mj_model, (mjcf.MjModel, mjx.Model)):
-        raise NotImplementedError(
-            "flattening a mujoco.MjModel needs the `mujoco` package, which is absent from this image; "
-            "load the MJCF through load_mj_model_from_file instead")
-    model = mjx.device_put(mj_model)
+    model = mjx.device_put(mj_model)  # this repo's compiled model, or a real mujoco.MjModel (flattened by utils/mjmodel.py)
     data = mjx.make_data(model, device=device)
     return model, data
 

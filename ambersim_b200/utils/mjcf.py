@@ -237,6 +237,100 @@ def _expand_includes(root: ET.Element, base: Path) -> None:
 
 
 # ---------------------------------------------------------------------------- the compiler
+def enumerate_pairs(m: "MjModel", G, excludes, explicit=()) -> None:
+    """Static enumeration of colliding geom pairs + parameter mixing, shared by the MJCF compiler and the
+    mujoco.MjModel adapter (utils/mjmodel.py). G: one dict per geom (type, body, contype, conaffinity, condim, priority,
+    friction[3], solmix, solref[2], solimp[5], margin, gap, name); excludes: set of (body, body) pairs; explicit:
+    pre-mixed <contact><pair> entries (dicts with g1, g2, condim, friction[5], solref, solimp, includemargin).
+
+    Restates what MJX does at trace time: contype/conaffinity filter, same
+    weld-body and parent-child filters, type-pair dispatch, friction=max, solref/solimp mixed
+    by solmix, includemargin = max(margin) - max(gap), condim = max; priority overrides.
+    """
+    pairs = []
+    unsupported = 0
+    reason = ""
+    filterparent = not (m.opt.disableflags & _DISABLE_BITS["filterparent"])
+    for i in range(m.ngeom):
+        for k in range(i + 1, m.ngeom):
+            a, b = G[i], G[k]
+            if not ((a["contype"] & b["conaffinity"]) or (b["contype"] & a["conaffinity"])):
+                continue
+            b1, b2 = a["body"], b["body"]
+            w1, w2 = m.body_weldid[b1], m.body_weldid[b2]
+            if w1 == w2:
+                continue
+            if filterparent and w1 != 0 and w2 != 0:
+                wp1 = m.body_weldid[m.body_parentid[w1]]
+                wp2 = m.body_weldid[m.body_parentid[w2]]
+                if wp1 == w2 or wp2 == w1:
+                    continue
+            if (min(b1, b2), max(b1, b2)) in excludes:
+                continue
+            g1, g2 = (i, k) if a["type"] <= b["type"] else (k, i)
+            key = (G[g1]["type"], G[g2]["type"])
+            if key not in _PAIR_KIND:
+                unsupported += 1
+                reason = f"geom pair types {key} ({G[g1]['name']}, {G[g2]['name']})"
+                continue
+            A, B = G[g1], G[g2]
+            if A["priority"] != B["priority"]:
+                hi = A if A["priority"] > B["priority"] else B
+                friction, solref, solimp, condim = hi["friction"], hi["solref"], hi["solimp"], hi["condim"]
+            else:
+                s1, s2 = A["solmix"], B["solmix"]
+                if s1 >= MJ_MINVAL and s2 >= MJ_MINVAL:
+                    mix = s1 / (s1 + s2)
+                elif s1 < MJ_MINVAL and s2 < MJ_MINVAL:
+                    mix = 0.5
+                elif s1 < MJ_MINVAL:
+                    mix = 0.0
+                else:
+                    mix = 1.0
+                friction = np.maximum(A["friction"], B["friction"])
+                if A["solref"][0] > 0 and B["solref"][0] > 0:
+                    solref = mix * A["solref"] + (1 - mix) * B["solref"]
+                else:
+                    solref = np.minimum(A["solref"], B["solref"])
+                solimp = mix * A["solimp"] + (1 - mix) * B["solimp"]
+                condim = max(A["condim"], B["condim"])
+            if condim not in (1, 3):
+                unsupported += 1
+                reason = f"condim {condim}"
+                continue
+            margin = max(A["margin"], B["margin"])
+            gap = max(A["gap"], B["gap"])
+            pairs.append(dict(g1=g1, g2=g2, kind=_PAIR_KIND[key], condim=condim,
+                              friction=np.array([friction[0], friction[0], friction[1], friction[2], friction[2]]),
+                              solref=solref, solimp=solimp, includemargin=margin - gap))
+    for e in explicit:
+        g1, g2 = (e["g1"], e["g2"]) if G[e["g1"]]["type"] <= G[e["g2"]]["type"] else (e["g2"], e["g1"])
+        key = (G[g1]["type"], G[g2]["type"])
+        if key not in _PAIR_KIND or e["condim"] not in (1, 3):
+            unsupported += 1
+            reason = f"explicit pair of geom types {key}, condim {e['condim']}"
+            continue
+        pairs.append(dict(g1=g1, g2=g2, kind=_PAIR_KIND[key], condim=int(e["condim"]), friction=np.asarray(e["friction"], dtype=np.float64),
+                          solref=np.asarray(e["solref"], dtype=np.float64), solimp=np.asarray(e["solimp"], dtype=np.float64),
+                          includemargin=float(e["includemargin"])))
+    npair = len(pairs)
+    m.npair = npair
+    m.pair_geom1 = np.array([p["g1"] for p in pairs], dtype=np.int32)
+    m.pair_geom2 = np.array([p["g2"] for p in pairs], dtype=np.int32)
+    m.pair_kind = np.array([p["kind"] for p in pairs], dtype=np.int32)
+    m.pair_condim = np.array([p["condim"] for p in pairs], dtype=np.int32)
+    m.pair_friction = np.array([p["friction"] for p in pairs]).reshape(npair, 5)
+    m.pair_solref = np.array([p["solref"] for p in pairs]).reshape(npair, 2)
+    m.pair_solimp = np.array([p["solimp"] for p in pairs]).reshape(npair, 5)
+    m.pair_includemargin = np.array([p["includemargin"] for p in pairs], dtype=np.float64)
+    m.n_unsupported_pairs = unsupported
+    m.unsupported_reason = reason
+    if m.opt.cone != 0:
+        m.n_unsupported_pairs += 1
+        m.unsupported_reason = "elliptic friction cone"
+
+
+
 class _Compiler:
     def __init__(self, root: ET.Element, force_float: bool = False) -> None:
         self.root = root
@@ -538,6 +632,12 @@ class _Compiler:
         m.geom_conaffinity = np.array([g["conaffinity"] for g in self.geoms], dtype=np.int32)
         m.geom_condim = np.array([g["condim"] for g in self.geoms], dtype=np.int32)
         m.geom_friction = np.array([g["friction"] for g in self.geoms]).reshape(ngeom, 3)
+        m.geom_priority = np.array([g["priority"] for g in self.geoms], dtype=np.int32)
+        m.geom_solmix = np.array([g["solmix"] for g in self.geoms], dtype=np.float64)
+        m.geom_solref = np.array([g["solref"] for g in self.geoms]).reshape(ngeom, 2)
+        m.geom_solimp = np.array([g["solimp"] for g in self.geoms]).reshape(ngeom, 5)
+        m.geom_margin = np.array([g["margin"] for g in self.geoms], dtype=np.float64)
+        m.geom_gap = np.array([g["gap"] for g in self.geoms], dtype=np.float64)
 
         m.names = dict(
             body=[b["name"] for b in self.bodies], joint=[j["name"] for j in self.joints],
@@ -654,90 +754,14 @@ class _Compiler:
         m.names["equality"] = [e["name"] for e in eqs]
 
     def _pairs(self, m: MjModel) -> None:
-        """Static enumeration of colliding geom pairs + parameter mixing.
-
-        Restates what MJX does at trace time: contype/conaffinity filter, same
-        weld-body and parent-child filters, type-pair dispatch, friction=max, solref/solimp mixed
-        by solmix, includemargin = max(margin) - max(gap), condim = max; priority overrides.
-        """
         excludes = set()
         for cnode in self.root.findall("contact"):
             for ex in cnode.findall("exclude"):
                 b1 = m.names["body"].index(ex.get("body1"))
                 b2 = m.names["body"].index(ex.get("body2"))
                 excludes.add((min(b1, b2), max(b1, b2)))
-        pairs = []
-        unsupported = 0
-        reason = ""
-        G = self.geoms
-        filterparent = not (m.opt.disableflags & _DISABLE_BITS["filterparent"])
-        for i in range(m.ngeom):
-            for k in range(i + 1, m.ngeom):
-                a, b = G[i], G[k]
-                if not ((a["contype"] & b["conaffinity"]) or (b["contype"] & a["conaffinity"])):
-                    continue
-                b1, b2 = a["body"], b["body"]
-                w1, w2 = m.body_weldid[b1], m.body_weldid[b2]
-                if w1 == w2:
-                    continue
-                if filterparent and w1 != 0 and w2 != 0:
-                    wp1 = m.body_weldid[m.body_parentid[w1]]
-                    wp2 = m.body_weldid[m.body_parentid[w2]]
-                    if wp1 == w2 or wp2 == w1:
-                        continue
-                if (min(b1, b2), max(b1, b2)) in excludes:
-                    continue
-                g1, g2 = (i, k) if a["type"] <= b["type"] else (k, i)
-                key = (G[g1]["type"], G[g2]["type"])
-                if key not in _PAIR_KIND:
-                    unsupported += 1
-                    reason = f"geom pair types {key} ({G[g1]['name']}, {G[g2]['name']})"
-                    continue
-                A, B = G[g1], G[g2]
-                if A["priority"] != B["priority"]:
-                    hi = A if A["priority"] > B["priority"] else B
-                    friction, solref, solimp, condim = hi["friction"], hi["solref"], hi["solimp"], hi["condim"]
-                else:
-                    s1, s2 = A["solmix"], B["solmix"]
-                    if s1 >= MJ_MINVAL and s2 >= MJ_MINVAL:
-                        mix = s1 / (s1 + s2)
-                    elif s1 < MJ_MINVAL and s2 < MJ_MINVAL:
-                        mix = 0.5
-                    elif s1 < MJ_MINVAL:
-                        mix = 0.0
-                    else:
-                        mix = 1.0
-                    friction = np.maximum(A["friction"], B["friction"])
-                    if A["solref"][0] > 0 and B["solref"][0] > 0:
-                        solref = mix * A["solref"] + (1 - mix) * B["solref"]
-                    else:
-                        solref = np.minimum(A["solref"], B["solref"])
-                    solimp = mix * A["solimp"] + (1 - mix) * B["solimp"]
-                    condim = max(A["condim"], B["condim"])
-                if condim not in (1, 3):
-                    unsupported += 1
-                    reason = f"condim {condim}"
-                    continue
-                margin = max(A["margin"], B["margin"])
-                gap = max(A["gap"], B["gap"])
-                pairs.append(dict(g1=g1, g2=g2, kind=_PAIR_KIND[key], condim=condim,
-                                  friction=np.array([friction[0], friction[0], friction[1], friction[2], friction[2]]),
-                                  solref=solref, solimp=solimp, includemargin=margin - gap))
-        npair = len(pairs)
-        m.npair = npair
-        m.pair_geom1 = np.array([p["g1"] for p in pairs], dtype=np.int32)
-        m.pair_geom2 = np.array([p["g2"] for p in pairs], dtype=np.int32)
-        m.pair_kind = np.array([p["kind"] for p in pairs], dtype=np.int32)
-        m.pair_condim = np.array([p["condim"] for p in pairs], dtype=np.int32)
-        m.pair_friction = np.array([p["friction"] for p in pairs]).reshape(npair, 5)
-        m.pair_solref = np.array([p["solref"] for p in pairs]).reshape(npair, 2)
-        m.pair_solimp = np.array([p["solimp"] for p in pairs]).reshape(npair, 5)
-        m.pair_includemargin = np.array([p["includemargin"] for p in pairs], dtype=np.float64)
-        m.n_unsupported_pairs = unsupported
-        m.unsupported_reason = reason
-        if m.opt.cone != 0:
-            m.n_unsupported_pairs += 1
-            m.unsupported_reason = "elliptic friction cone"
+        m.exclude_signature = np.array(sorted((b1 << 16) + b2 for b1, b2 in excludes), dtype=np.int32)  # mjModel.exclude_signature
+        enumerate_pairs(m, self.geoms, excludes)
 
     # ------------------------------------------------------------------ mj_setConst at qpos0
     def _set_const(self, m: MjModel) -> None:

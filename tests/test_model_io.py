@@ -104,3 +104,61 @@ def test_default_classes_and_keyframes():
     assert np.allclose(b.jnt_axis[3], [0, -1, 0])  # knee class
     assert np.allclose(b.key_ctrl("home"), [0, 0.5, 1.0] * 4)
     assert b.pair_kind.tolist() == [0, 0, 0, 0] and np.allclose(b.pair_friction[0], [1.0, 1.0, 0.02, 0.01, 0.01])  # elementwise max with the plane
+
+
+def test_real_mjmodel_layout_round_trip(tmp_path):
+    """mjx.device_put(mujoco.MjModel) (io_utils.py:225): the adapter reads MuJoCo's own field names and shapes. `mujoco` is not
+    installable here, so every model of the suite (and a few random ones) is written out in mujoco.MjModel's layout and read back:
+    all model fields, the derived contact pairs, the options and the oracle's trajectory must survive unchanged."""
+    import numpy as np
+
+    from ambersim_b200 import mjx
+    from ambersim_b200.utils import mjmodel
+    from ambersim_b200.utils.io_utils import load_mj_model_from_file
+    from oracle.oracle import Oracle
+    from tests._randmodel import random_limb_model
+    from tests.conftest import MODELS
+
+    paths = [v[0] for v in MODELS.values()]
+    for seed in (1, 4):
+        f = tmp_path / f"r{seed}.xml"
+        f.write_text(random_limb_model(seed, 3, 1, 8)[0])
+        paths.append(str(f))
+    for path in paths:
+        m = load_mj_model_from_file(path)
+        ns = mjmodel.to_mujoco_layout(m)
+        assert mjmodel.looks_like_mjmodel(ns) and not mjmodel.looks_like_mjmodel(m)
+        assert ns.actuator_trnid.shape == (m.nu, 2) and ns.actuator_gear.shape == (m.nu, 6) and ns.actuator_gainprm.shape == (m.nu, 10)
+        m2 = mjmodel.from_mjmodel(ns)
+        for f in mjx._MODEL_FIELDS:
+            a, b = np.asarray(getattr(m, f)), np.asarray(getattr(m2, f))
+            assert a.shape == b.shape and np.array_equal(a, b), (path, f)
+        assert all(np.array_equal(getattr(m2.opt, k), getattr(m.opt, k)) for k in vars(m.opt))
+        assert m2.stat.meaninertia == m.stat.meaninertia and m2.n_unsupported_pairs == m.n_unsupported_pairs
+        assert len(m2.keyframes) == len(m.keyframes)
+        model = mjx.device_put(ns)  # the public entry point takes the foreign object directly
+        assert (model.nq, model.nv, model.nu, model.npair) == (m.nq, m.nv, m.nu, m.npair)
+        x0 = np.concatenate([m.qpos0, np.zeros(m.nv)])[None]
+        us = np.zeros((1, 5, m.nu))
+        kw = dict(disableflags=m.opt.disableflags | 16) if m.n_unsupported_pairs else {}
+        assert np.array_equal(Oracle(m, m.opt.replace(**kw)).rollout(x0, us), Oracle(m2, m2.opt.replace(**kw)).rollout(x0, us))
+
+
+def test_real_mjmodel_unsupported_features_raise():
+    import numpy as np
+    import pytest
+
+    from ambersim_b200.utils import mjmodel
+    from ambersim_b200.utils.io_utils import load_mj_model_from_file
+
+    base = load_mj_model_from_file("models/barkour_standin/barkour_vb_standin.xml")
+    for mutate in (lambda ns: setattr(ns, "na", 2), lambda ns: setattr(ns, "ntendon", 1), lambda ns: ns.jnt_type.__setitem__(3, 1),
+                   lambda ns: ns.actuator_dyntype.__setitem__(0, 1), lambda ns: ns.actuator_trntype.__setitem__(0, 3),
+                   lambda ns: setattr(ns.opt, "integrator", 2), lambda ns: ns.dof_frictionloss.__setitem__(7, 0.1)):
+        ns = mjmodel.to_mujoco_layout(base)
+        mutate(ns)
+        with pytest.raises(NotImplementedError):
+            mjmodel.from_mjmodel(ns)
+    ns = mjmodel.to_mujoco_layout(base)
+    ns.opt.cone = 1  # elliptic cones: loads (like a model with unsupported geoms), refuses to run with contacts on
+    assert mjmodel.from_mjmodel(ns).n_unsupported_pairs > 0

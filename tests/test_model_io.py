@@ -162,3 +162,43 @@ def test_real_mjmodel_unsupported_features_raise():
     ns = mjmodel.to_mujoco_layout(base)
     ns.opt.cone = 1  # elliptic cones: loads (like a model with unsupported geoms), refuses to run with contacts on
     assert mjmodel.from_mjmodel(ns).n_unsupported_pairs > 0
+
+
+def test_mujoco_model_dump_if_present():
+    """Real-MuJoCo pin of the MJCF compiler and of the mujoco.MjModel adapter: consumed when tools/dump_mjx_golden.py has been
+    run on a machine that has mujoco (it stores the compiled MjModel field by field next to the MJX rollouts)."""
+    from pathlib import Path
+    from types import SimpleNamespace
+
+    import numpy as np
+    import pytest
+
+    from ambersim_b200 import mjx
+    from ambersim_b200.utils import mjmodel
+    from ambersim_b200.utils.io_utils import load_mj_model_from_file
+    from tests.conftest import MODELS
+
+    gold = Path(__file__).parent / "golden"
+    used = 0
+    for name in ("pendulum", "bh280", "barkour", "biped"):
+        path = gold / f"mjx_{name}.npz"
+        if not path.exists():
+            continue
+        z = np.load(path)
+        if "model_nq" not in z.files:
+            continue
+        ns = SimpleNamespace(opt=SimpleNamespace(), stat=SimpleNamespace(meaninertia=float(z["model_stat_meaninertia"])))
+        for k in z.files:
+            if k.startswith("model_opt_"):
+                setattr(ns.opt, k[10:], z[k] if z[k].ndim else z[k].item())
+            elif k.startswith("model_") and k != "model_stat_meaninertia":
+                setattr(ns, k[6:], z[k] if z[k].ndim else z[k].item())
+        theirs = mjmodel.from_mjmodel(ns)
+        ours = load_mj_model_from_file(MODELS[name][0])
+        for f in mjx._MODEL_FIELDS:
+            a, b = np.asarray(getattr(ours, f), dtype=np.float64), np.asarray(getattr(theirs, f), dtype=np.float64)
+            assert a.shape == b.shape and np.allclose(a, b, rtol=1e-6, atol=1e-9), (name, f)
+        assert np.isclose(ours.stat.meaninertia, theirs.stat.meaninertia, rtol=1e-6)
+        used += 1
+    if not used:
+        pytest.skip("no MuJoCo model dump (mujoco is not installable in this image)")

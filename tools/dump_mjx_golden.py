@@ -43,7 +43,23 @@ for name, (rel, key, kw) in MODELS.items():
         return jnp.concatenate((x0[None], xs))
 
     xs = np.asarray(jax.jit(shoot)(jnp.asarray(x0, jnp.float32), jnp.asarray(us, jnp.float32)))
+    # the compiled MjModel itself, field by field (MuJoCo's own layout): pins this repo's MJCF compiler (mj_setConst constants,
+    # defaults, frames) and its mujoco.MjModel adapter through tests/test_model_io.py::test_mujoco_model_dump_if_present
+    fields = ("body_parentid body_rootid body_weldid body_jntnum body_jntadr body_dofnum body_dofadr body_pos body_quat body_ipos body_iquat "
+              "body_inertia body_invweight0 body_mass body_subtreemass jnt_type jnt_qposadr jnt_dofadr jnt_bodyid jnt_limited jnt_solref jnt_solimp "
+              "jnt_pos jnt_axis jnt_range jnt_stiffness jnt_margin dof_bodyid dof_jntid dof_parentid dof_armature dof_damping dof_invweight0 "
+              "dof_frictionloss qpos0 qpos_spring geom_type geom_bodyid geom_size geom_pos geom_quat geom_friction geom_solref geom_solimp "
+              "geom_contype geom_conaffinity geom_condim geom_priority geom_solmix geom_margin geom_gap eq_type eq_obj1id eq_obj2id eq_active0 "
+              "eq_solref eq_solimp eq_data actuator_trntype actuator_dyntype actuator_trnid actuator_gaintype actuator_biastype "
+              "actuator_ctrllimited actuator_forcelimited actuator_ctrlrange actuator_forcerange actuator_gainprm actuator_biasprm actuator_gear "
+              "exclude_signature key_qpos key_qvel key_ctrl").split()
+    model = {f"model_{f}": np.asarray(getattr(mj_model, f)) for f in fields if hasattr(mj_model, f)}
+    for f in ("nq", "nv", "nu", "na", "nbody", "njnt", "ngeom", "neq", "ntendon", "nmocap", "npair", "nkey"):
+        model[f"model_{f}"] = int(getattr(mj_model, f))
+    for f in ("timestep", "impratio", "tolerance", "ls_tolerance", "gravity", "integrator", "cone", "jacobian", "solver", "iterations", "ls_iterations", "disableflags"):
+        model[f"model_opt_{f}"] = np.asarray(getattr(mj_model.opt, f))
+    model["model_stat_meaninertia"] = float(mj_model.stat.meaninertia)
     np.savez_compressed(ROOT / "tests/golden" / f"mjx_{name}.npz", x0=x0, us=us, xs=xs, opt_timestep=mj_model.opt.timestep,
                         opt_iterations=mj_model.opt.iterations, opt_ls_iterations=mj_model.opt.ls_iterations,
-                        opt_disableflags=mj_model.opt.disableflags, mujoco_version=mujoco.__version__)
+                        opt_disableflags=mj_model.opt.disableflags, mujoco_version=mujoco.__version__, **model)
     print("wrote", name, xs.shape)

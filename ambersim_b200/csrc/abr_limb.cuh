@@ -116,6 +116,27 @@ template <int K> __device__ __forceinline__ float normalize_k(float (&x)[K]) {
   for (int i = 0; i < K; i++) x[i] *= inv;
   return nrm;
 }
+// The trunk's translational dofs are the unit twists e_3, e_4, e_5 (cdof[q] = [0 0 0 | e_q], q < 3). Multiplying by their
+// zeros cannot be folded by the compiler (IEEE: 0 * x is not 0 for every x), so the loops over dofs go through these two
+// helpers, which after unrolling reduce to a register pick for q < 3 (same values: only exact zeros are dropped).
+template <int N> __device__ __forceinline__ float cdof_dot(const float (&cdof)[N][6], int d, const float* f) {
+  if (d < 3) return f[3 + d];
+  return cdof[d][0] * f[0] + cdof[d][1] * f[1] + cdof[d][2] * f[2] + cdof[d][3] * f[3] + cdof[d][4] * f[4] + cdof[d][5] * f[5];
+}
+template <int N> __device__ __forceinline__ void cdof_axpy(const float (&cdof)[N][6], int d, float x, float (&V)[6]) {
+  if (d < 3) { V[3 + d] += x; return; }
+#pragma unroll
+  for (int i = 0; i < 6; i++) V[i] = fmaf(cdof[d][i], x, V[i]);
+}
+// inert_mul(I, e_{3+q}): the momentum of a unit translation along axis q
+__device__ __forceinline__ void inert_mul_unit(const float* I, int q, float* r) {
+  const float e[3] = {q == 0 ? 1.f : 0.f, q == 1 ? 1.f : 0.f, q == 2 ? 1.f : 0.f};
+  // cross(I + 6, e_q) with the zero products dropped
+  r[0] = (q == 1) ? -I[8] : ((q == 2) ? I[7] : 0.f);
+  r[1] = (q == 0) ? I[8] : ((q == 2) ? -I[6] : 0.f);
+  r[2] = (q == 0) ? -I[7] : ((q == 1) ? I[6] : 0.f);
+  r[3] = I[9] * e[0]; r[4] = I[9] * e[1]; r[5] = I[9] * e[2];
+}
 static __device__ __noinline__ float pow_cold(float x, float p) { return powf(x, p); }
 // the sampler's counter-based normal: out of line so the shoot-mode loop body does not carry three copies of it
 static __device__ __noinline__ float philox_normal_ool(unsigned long long seed, uint32_t sample, uint32_t problem, uint32_t index) {
@@ -267,9 +288,7 @@ template <int NL, int NC> __device__ __forceinline__ void contact_bv(const Rows<
                                                                      float (&bv)[NC > 0 ? NC : 1][3]) {
   float V[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int d = 0; d < 6 + NL; d++)
-#pragma unroll
-    for (int i = 0; i < 6; i++) V[i] = fmaf(cdof[d][i], x[d], V[i]);
+  for (int d = 0; d < 6 + NL; d++) cdof_axpy(cdof, d, x[d], V);
   float lin[3];
 #pragma unroll
   for (int k = 0; k < 3; k++) lin[k] = R.fr[k][0] * V[3] + R.fr[k][1] * V[4] + R.fr[k][2] * V[5];
@@ -501,14 +520,14 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
       const int ld = (pc < 0) ? -1 : 5 + pc;
 #pragma unroll
       for (int d = 0; d < N; d++) {
-        float cr[3];
-        v_cross(cdof[d], off, cr);
+        float cr[3] = {0.f, 0.f, 0.f};
+        if (d >= 3) v_cross(cdof[d], off, cr);  // a translational trunk dof moves the contact point by its own unit vector
         const float jp[3] = {cdof[d][3] + cr[0], cdof[d][4] + cr[1], cdof[d][5] + cr[2]};
         const bool on = d <= ld;
 #pragma unroll
         for (int k = 0; k < 3; k++) {
           const float fr[3] = {LTF(mp.con(c) + 24 + 3 * k), LTF(mp.con(c) + 25 + 3 * k), LTF(mp.con(c) + 26 + 3 * k)};
-          R.B[c][k][d] = on ? v_dot(fr, jp) : 0.f;
+          R.B[c][k][d] = on ? ((d < 3) ? fr[d] : v_dot(fr, jp)) : 0.f;
         }
       }
     }
@@ -531,11 +550,11 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
       for (int i = 0; i < N; i++) {
         if (PD(i) == p) {
           float buf[6];
-          inert_mul(crb, cdof[i], buf);
+          if (i < 3) inert_mul_unit(crb, i, buf); else inert_mul(crb, cdof[i], buf);
 #pragma unroll
           for (int j = 0; j < N; j++) {
             if (j <= i) {
-              float t = cdof[j][0] * buf[0] + cdof[j][1] * buf[1] + cdof[j][2] * buf[2] + cdof[j][3] * buf[3] + cdof[j][4] * buf[4] + cdof[j][5] * buf[5];
+              float t = cdof_dot(cdof, j, buf);
               if (i == j) t += (i < 6) ? LTF(mp.trunk() + 6 + i) : LTF(mp.jnt(PD(i)) + 10);
               M[TR(i, j)] = t;
             }
@@ -563,9 +582,11 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
     float ca[6] = {0.f, 0.f, 0.f, grav ? -C.grav[0] : 0.f, grav ? -C.grav[1] : 0.f, grav ? -C.grav[2] : 0.f};
     // trunk (free joint): translations first, then rotations against the translated cvel
 #pragma unroll
-    for (int q = 0; q < 3; q++)
+    for (int q = 0; q < 3; q++) {
+      cv[3 + q] = s.v[q];
 #pragma unroll
-      for (int i = 0; i < 6; i++) { cv[i] = fmaf(cdof[q][i], s.v[q], cv[i]); cdd[q][i] = 0.f; }
+      for (int i = 0; i < 6; i++) cdd[q][i] = 0.f;
+    }
 #pragma unroll
     for (int q = 3; q < 6; q++) motion_cross(cv, cdof[q], cdd[q]);
 #pragma unroll
@@ -610,7 +631,7 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
 #pragma unroll
       for (int d = 0; d < N; d++) {
         if (PD(d) != p) continue;
-        const float bias = cdof[d][0] * f[0] + cdof[d][1] * f[1] + cdof[d][2] * f[2] + cdof[d][3] * f[3] + cdof[d][4] * f[4] + cdof[d][5] * f[5];
+        const float bias = cdof_dot(cdof, d, f);
         float t = 0.f;
         if (p == 0) {
           if (passive_on) t = -LTF(mp.trunk() + d) * s.v[d];
@@ -758,7 +779,7 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
         for (int i = 0; i < 3; i++) Wt[3 + i] = R.fr[0][i] * Fl[0] + R.fr[1][i] * Fl[1] + R.fr[2][i] * Fl[2];
 #pragma unroll
         for (int d = 0; d < N; d++)
-          up[d] += cdof[d][0] * Wt[0] + cdof[d][1] * Wt[1] + cdof[d][2] * Wt[2] + cdof[d][3] * Wt[3] + cdof[d][4] * Wt[4] + cdof[d][5] * Wt[5];
+          up[d] += cdof_dot(cdof, d, Wt);
       }
 #pragma unroll
       for (int d = 0; d < N; d++) {
@@ -829,11 +850,11 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
           float t = 0.f;
 #pragma unroll
           for (int b = 0; b < 6; b++) t = fmaf(K[a >= b ? TR(a, b) : TR(b, a)], cdof[j][b], t);
-          KC[a] = t;
+          KC[a] = (j < 3) ? K[a >= 3 + j ? TR(a, 3 + j) : TR(3 + j, a)] : t;
         }
 #pragma unroll
         for (int i = 0; i < N; i++)
-          if (i >= j) H[TR(i, j)] += cdof[i][0] * KC[0] + cdof[i][1] * KC[1] + cdof[i][2] * KC[2] + cdof[i][3] * KC[3] + cdof[i][4] * KC[4] + cdof[i][5] * KC[5];
+          if (i >= j) H[TR(i, j)] += cdof_dot(cdof, i, KC);
       }
     }
     ldl_factor<N>(H, hD, S);

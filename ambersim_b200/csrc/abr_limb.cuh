@@ -85,6 +85,15 @@ __device__ __forceinline__ float gs(float x, int lv, int mxl) {
 __device__ __forceinline__ float gall(float x, int lg) { return gs(x, lg, lg); }
 
 
+// 1/x as the bare MUFU.RCP (about 1 ulp): the operands here (clamped pivots, impedances in (0,1), regularisers >= mjMINVAL,
+// line-search curvatures) never reach the magnitudes whose scaling fix-ups make the compiler's `1.f / x` nine instructions long
+__device__ __forceinline__ float rcp_fast(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float safe_div_fast(float a, float b) { return a * rcp_fast(b + ((b == 0.f) ? kMinVal : 0.f)); }
+
 // sin/cos with a three-constant Cody-Waite reduction and Cephes minimax polynomials (about 1 ulp for
 // |x| < 1e5): branch-free, so the straight-line step carries no Payne-Hanek slow path per call site.
 __device__ __forceinline__ void sincos_bf(float x, float& sn, float& cs) {
@@ -158,7 +167,7 @@ template <int N, class SH> __device__ __forceinline__ void ldl_factor(float (&A)
         for (int j = 0; j < N; j++)
           if (PD(i) == p && j <= i) A[TR(i, j)] = gs(A[TR(i, j)], lv, mxl);
     }
-    const float d = 1.f / fmaxf(A[TR(k, k)], kMinVal);
+    const float d = rcp_fast(fmaxf(A[TR(k, k)], kMinVal));
     invD[k] = d;
     const bool ownp = S.o(p);
 #pragma unroll
@@ -264,8 +273,8 @@ __device__ __forceinline__ void row_kbi(const float* prm /* smem, stride kStride
   float imp = dmin + y * (dmax - dmin);
   imp = fminf(fmaxf(imp, dmin), dmax);
   if (x > 1.f) imp = dmax;
-  const float R = fmaxf(invw * (1.f - imp) / imp, kMinVal);
-  D = active ? 1.f / R : 0.f;
+  const float R = fmaxf(invw * (1.f - imp) * rcp_fast(imp), kMinVal);
+  D = active ? rcp_fast(R) : 0.f;
   aref = active ? -b * jvel - k * imp * pos : 0.f;
 }
 
@@ -330,7 +339,8 @@ template <int NL, int NC, bool CB, class SH> __device__ __forceinline__ float so
                                                                        const float (&Jx)[NL + 4 * NC], const float (&fs)[6 + NL], const float (&as)[6 + NL], float& gauss) {
   float sc = 0.f, g = 0.f;
 #pragma unroll
-  for (int r = 0; r < NL + 4 * NC; r++) sc += (Jx[r] < 0.f) ? R.D[r] * Jx[r] * Jx[r] : 0.f;
+  for (int r = 0; r < NL + 4 * NC; r++)
+    if (Jx[r] < 0.f) sc = fmaf(R.D[r] * Jx[r], Jx[r], sc);
 #pragma unroll
   for (int d = 0; d < 6 + NL; d++) g += S.o(PD(d)) ? (Mx[d] - fs[d]) * (x[d] - as[d]) : 0.f;
   sc = gall(sc, S.lg()); g = gall(g, S.lg());
@@ -344,8 +354,7 @@ template <int NR> __device__ __forceinline__ LSP ls_eval(const float (&Jaref)[NR
   float q0 = 0.f, q1 = 0.f, q2 = 0.f;
 #pragma unroll
   for (int r = 0; r < NR; r++) {
-    const bool on = fmaf(alpha, jv[r], Jaref[r]) < 0.f;
-    q0 += on ? a0[r] : 0.f; q1 += on ? a1[r] : 0.f; q2 += on ? a2[r] : 0.f;
+    if (fmaf(alpha, jv[r], Jaref[r]) < 0.f) { q0 += a0[r]; q1 += a1[r]; q2 += a2[r]; }  // three predicated adds, no selects
   }
   q0 = gall(q0, lg) + qg0; q1 = gall(q1, lg) + qg1; q2 = gall(q2, lg) + qg2;
   LSP pt;
@@ -895,7 +904,7 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
     }
 #define LS_EVAL(al) ls_eval<NR>(Jaref, jv, la0, la1, la2, (al), qg0, qg1, qg2, S.lg())
     const LSP p0 = LS_EVAL(0.f);
-    const LSP l0 = LS_EVAL(-safe_div(p0.d0, p0.d1));
+    const LSP l0 = LS_EVAL(-safe_div_fast(p0.d0, p0.d1));
     const bool lesser = l0.d0 < p0.d0;
     LSP hi = lesser ? p0 : l0;
     LSP lo = lesser ? l0 : p0;
@@ -907,8 +916,8 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
       done = done || ((lo.d0 < 0.f) && (lo.d0 > -gtol));
       done = done || ((hi.d0 > 0.f) && (hi.d0 < gtol));
       if (!__any_sync(ABR_FULL, !done)) break;
-      const LSP lo_next = LS_EVAL(lo.alpha - safe_div(lo.d0, lo.d1));
-      const LSP hi_next = LS_EVAL(hi.alpha - safe_div(hi.d0, hi.d1));
+      const LSP lo_next = LS_EVAL(lo.alpha - safe_div_fast(lo.d0, lo.d1));
+      const LSP hi_next = LS_EVAL(hi.alpha - safe_div_fast(hi.d0, hi.d1));
       const LSP mid = LS_EVAL(0.5f * (lo.alpha + hi.alpha));
       if (!done) {
         const bool swap_lo_next = (lo.d0 > 0.f) || (lo.d0 < lo_next.d0);

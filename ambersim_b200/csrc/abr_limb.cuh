@@ -92,6 +92,11 @@ __device__ __forceinline__ float rcp_fast(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
+__device__ __forceinline__ float sqrt_fast(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ float safe_div_fast(float a, float b) { return a * rcp_fast(b + ((b == 0.f) ? kMinVal : 0.f)); }
 
 // sin/cos with a three-constant Cody-Waite reduction and Cephes minimax polynomials (about 1 ulp for
@@ -119,8 +124,8 @@ template <int K> __device__ __forceinline__ float normalize_k(float (&x)[K]) {
   float ss = 0.f;
 #pragma unroll
   for (int i = 0; i < K; i++) ss = fmaf(x[i], x[i], ss);
-  const float nrm = sqrtf(ss);
-  const float inv = 1.f / ((nrm == 0.f) ? 1e-6f : nrm);
+  const float nrm = sqrt_fast(ss);
+  const float inv = rcp_fast((nrm == 0.f) ? 1e-6f : nrm);
 #pragma unroll
   for (int i = 0; i < K; i++) x[i] *= inv;
   return nrm;
@@ -252,7 +257,7 @@ template <int NL, int NC> struct Lane {
 template <int LGC> struct LaneCfg {
   const float* T;  // table + lane-in-group
   ShareT<LGC> S;
-  float dt, grav[3], mass, tol, ls_tol, meaninertia;
+  float dt, grav[3], mass, inv_mass, tol, ls_tol, meaninertia;
   float frs, acs;  // per-world domain randomisation: contact friction scale, actuator strength scale (1 = the model's own)
   int iterations, ls_iterations, disableflags, nefc, nv;
 };
@@ -342,7 +347,8 @@ template <int NL, int NC, bool CB, class SH> __device__ __forceinline__ float so
   for (int r = 0; r < NL + 4 * NC; r++)
     if (Jx[r] < 0.f) sc = fmaf(R.D[r] * Jx[r], Jx[r], sc);
 #pragma unroll
-  for (int d = 0; d < 6 + NL; d++) g += S.o(PD(d)) ? (Mx[d] - fs[d]) * (x[d] - as[d]) : 0.f;
+  for (int d = 0; d < 6 + NL; d++)
+    if (S.o(PD(d))) g = fmaf(Mx[d] - fs[d], x[d] - as[d], g);
   sc = gall(sc, S.lg()); g = gall(g, S.lg());
   gauss = 0.5f * g;
   return 0.5f * sc + 0.5f * g;
@@ -436,7 +442,7 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
       sx = fmaf(xipos[p][0], ms, sx); sy = fmaf(xipos[p][1], ms, sy); sz = fmaf(xipos[p][2], ms, sz);
     }
     sx = gall(sx, S.lg()); sy = gall(sy, S.lg()); sz = gall(sz, S.lg());
-    const float im = 1.f / C.mass;
+    const float im = C.inv_mass;
     com[0] = sx * im; com[1] = sy * im; com[2] = sz * im;
   }
   float cinert[NP][10];
@@ -780,7 +786,7 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
           }
         } else {
 #pragma unroll
-          for (int d = 0; d < N; d++) up[d] += R.B[c][0][d] * F[0] + R.B[c][1][d] * F[1] + R.B[c][2][d] * F[2];
+          for (int d = 0; d < N; d++) up[d] = fmaf(R.B[c][2][d], F[2], fmaf(R.B[c][1][d], F[1], fmaf(R.B[c][0][d], F[0], up[d])));
         }
       }
       if constexpr (CB && NC > 0) {
@@ -808,7 +814,8 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
       for (int j = 0; j < N; j++)
         if (j <= i) H[TR(i, j)] = S.o(PD(i)) ? M[TR(i, j)] : 0.f;
 #pragma unroll
-    for (int r = 0; r < NL; r++) H[TR(6 + r, 6 + r)] += (Jaref[r] < 0.f) ? R.D[r] * R.lsg[r] * R.lsg[r] : 0.f;
+    for (int r = 0; r < NL; r++)
+      if (Jaref[r] < 0.f) H[TR(6 + r, 6 + r)] = fmaf(R.D[r] * R.lsg[r], R.lsg[r], H[TR(6 + r, 6 + r)]);
     float K[21];  // CB: 6x6 weight of the leaf body's twist, sum_c [g_c; fr] W_c [g_c; fr]'
     if constexpr (CB) {
 #pragma unroll
@@ -838,7 +845,7 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
         for (int i = 0; i < 6; i++)
 #pragma unroll
           for (int j = 0; j < 6; j++)
-            if (j <= i) K[TR(i, j)] += w[0][i] * U[0][j] + w[1][i] * U[1][j] + w[2][i] * U[2][j];
+            if (j <= i) K[TR(i, j)] = fmaf(w[2][i], U[2][j], fmaf(w[1][i], U[1][j], fmaf(w[0][i], U[0][j], K[TR(i, j)])));
       } else {
 #pragma unroll
         for (int j = 0; j < N; j++) {
@@ -846,7 +853,7 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
           const float o0 = W00 * b0 + W01 * b1 + W02 * b2, o1 = W01 * b0 + W11 * b1, o2 = W02 * b0 + W22 * b2;
 #pragma unroll
           for (int i = 0; i < N; i++)
-            if (i >= j) H[TR(i, j)] += R.B[c][0][i] * o0 + R.B[c][1][i] * o1 + R.B[c][2][i] * o2;
+            if (i >= j) H[TR(i, j)] = fmaf(R.B[c][2][i], o2, fmaf(R.B[c][1][i], o1, fmaf(R.B[c][0][i], o0, H[TR(i, j)])));
         }
       }
     }
@@ -893,7 +900,7 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
       if (S.o(PD(d))) { const float t = search[d]; sn += t * t; sMa += t * Ma[d]; sq += t * fs[d]; smv += t * mv[d]; }
     }
     sn = gall(sn, S.lg()); sMa = gall(sMa, S.lg()); sq = gall(sq, S.lg()); smv = gall(smv, S.lg());
-    const float smag = sqrtf(sn) * C.meaninertia * (float)max(1, C.nv);
+    const float smag = sqrt_fast(sn) * C.meaninertia * (float)max(1, C.nv);
     const float gtol = C.tol * C.ls_tol * smag;
     const float qg0 = gauss, qg1 = sMa - sq, qg2 = 0.5f * smv;
     float la0[NR], la1[NR], la2[NR];
@@ -1002,7 +1009,7 @@ template <int NL, int NC, int LGC> __device__ __forceinline__ LaneCfg<LGC> make_
   C.S.own = LTI(mp.ish()); C.S.lvl = LTI(mp.ish() + 1); C.S.mx = L.l_mx; C.S.lg_ = L.lg2G;
   C.dt = L.timestep; C.grav[0] = L.gravity[0]; C.grav[1] = L.gravity[1]; C.grav[2] = L.gravity[2];
   C.frs = 1.f; C.acs = 1.f;
-  C.mass = L.l_mass; C.tol = L.tolerance; C.ls_tol = L.ls_tolerance; C.meaninertia = L.meaninertia;
+  C.mass = L.l_mass; C.inv_mass = 1.f / L.l_mass; C.tol = L.tolerance; C.ls_tol = L.ls_tolerance; C.meaninertia = L.meaninertia;
   C.iterations = L.iterations; C.ls_iterations = L.ls_iterations; C.disableflags = L.disableflags; C.nefc = L.nefc; C.nv = L.nv;
   return C;
 }

@@ -36,8 +36,8 @@ F_WS = 46349.0
 F_WS_BIPED = 130142.0  # same counter, biped stand-in at its standing keyframe
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
 # dram__bytes_read.sum + dram__bytes_write.sum of the C2 launch (one `ncu --set full` capture of this file's
-# own kernel launch, profiles/r1_limb_final_c2_summary.txt + .ncu-rep): 198.61 MB + 4.88 MB vs 197.23 MB algorithmic
-NCU_DRAM_BYTES_C2 = 198_606_336 + 4_884_992
+# own kernel launch, profiles/r1_limb_final2_c2_summary.txt + .ncu-rep): 198.28 MB + 4.36 MB vs 197.23 MB algorithmic
+NCU_DRAM_BYTES_C2 = 198_281_216 + 4_361_216
 
 
 def peaks():
@@ -56,7 +56,7 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc, self.stop, self.t, self.max_mhz = index, [], None, threading.Event(), None, None
-        self.reason_bits = 0
+        self.reason_bits, self.stamped, self.t0, self.t1 = 0, [], None, None
         try:
             import pynvml
 
@@ -74,19 +74,27 @@ class ClockSampler:
         nv = self.nv
         while not self.stop.is_set():
             try:
-                self.rows.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
-                self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
-            except Exception:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 try:
-                    self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                    bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
                 except Exception:
-                    pass
-            time.sleep(0.003)
+                    bits = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))  # older NVML name of the same mask
+                self.stamped.append((time.perf_counter(), mhz, bits))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def start(self):
+        """Begin polling ahead of the timed region (the first NVML queries take tens of ms)."""
+        if self.nv is not None and self.t is None:
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+        return self
 
     def __enter__(self):
         if self.nv is not None:
-            self.t = threading.Thread(target=self._poll, daemon=True)
-            self.t.start()
+            self.start()
+            self.t0 = time.perf_counter()
             return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
@@ -102,6 +110,7 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def __exit__(self, *a):
+        self.t1 = time.perf_counter()
         self.stop.set()
         if self.nv is not None and self.t:
             self.t.join(timeout=2)
@@ -115,6 +124,13 @@ class ClockSampler:
     def summary(self):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         if self.nv is not None:
+            inside = [r for r in self.stamped if self.t0 is not None and self.t0 <= r[0] <= (self.t1 or r[0])]
+            if not inside and self.stamped:  # a region shorter than one poll: the closest sample stands in
+                mid = 0.5 * ((self.t0 or 0) + (self.t1 or 0))
+                inside = [min(self.stamped, key=lambda r: abs(r[0] - mid))]
+            self.rows = [r[1] for r in inside]
+            for r in inside:
+                self.reason_bits |= r[2]
             bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}  # nvml.h nvmlClocksEventReason*
             return {"sm_mhz": statistics.median(self.rows) if self.rows else None, "sm_max_mhz": self.max_mhz,
                     "reasons": [n for n in names if self.reason_bits & bits[n]], "samples": len(self.rows), "source": "nvml"}
@@ -350,11 +366,12 @@ def main():
         torch.cuda.synchronize(device)
 
     K, Wm = max(1, args.steps), max(3, args.warmup)
+    clk = ClockSampler(local).start()
     for _ in range(Wm):
         one_step()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
+    with clk:
         e0.record(stream)
         for _ in range(K):
             one_step()

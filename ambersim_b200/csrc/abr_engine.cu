@@ -512,12 +512,44 @@ static int build_blob(const HostModel& m, bool alias, Layout& L, std::vector<flo
             if (g == lane0[body]) ownbits |= 1 << p;
             lvlbits |= lv << (2 * p);
             if (lv > ((mxbits >> (2 * p)) & 3)) mxbits = (mxbits & ~(3 << (2 * p))) | (lv << (2 * p));
-            for (int i = 0; i < 3; i++) { setf(sb + i, g, m.body_pos[3 * body + i]); setf(sb + 7 + i, g, m.body_ipos[3 * body + i]); setf(sb + 15 + i, g, m.body_inertia[3 * body + i]); }
-            for (int i = 0; i < 4; i++) { setf(sb + 3 + i, g, m.body_quat[4 * body + i]); setf(sb + 10 + i, g, m.body_iquat[4 * body + i]); }
+            // constants of the body folded into its PARENT frame (double precision, once): see the kinematics block of abr_limb.cuh
+            const double bq[4] = {m.body_quat[4 * body], m.body_quat[4 * body + 1], m.body_quat[4 * body + 2], m.body_quat[4 * body + 3]};
+            const double iq[4] = {m.body_iquat[4 * body], m.body_iquat[4 * body + 1], m.body_iquat[4 * body + 2], m.body_iquat[4 * body + 3]};
+            auto qmat = [](const double* q, double* R) {
+              R[0] = q[0] * q[0] + q[1] * q[1] - q[2] * q[2] - q[3] * q[3]; R[1] = 2 * (q[1] * q[2] - q[0] * q[3]); R[2] = 2 * (q[1] * q[3] + q[0] * q[2]);
+              R[3] = 2 * (q[1] * q[2] + q[0] * q[3]); R[4] = q[0] * q[0] - q[1] * q[1] + q[2] * q[2] - q[3] * q[3]; R[5] = 2 * (q[2] * q[3] - q[0] * q[1]);
+              R[6] = 2 * (q[1] * q[3] - q[0] * q[2]); R[7] = 2 * (q[2] * q[3] + q[0] * q[1]); R[8] = q[0] * q[0] - q[1] * q[1] - q[2] * q[2] + q[3] * q[3];
+            };
+            double Rb[9], Ri[9];
+            qmat(bq, Rb); qmat(iq, Ri);
+            double jp[3] = {0, 0, 0}, jx[3] = {0, 0, 0};
+            if (p > 0) {
+              const int j = m.body_jntadr[body];
+              for (int i = 0; i < 3; i++) { jp[i] = m.jnt_pos[3 * j + i]; jx[i] = m.jnt_axis[3 * j + i]; }
+            }
+            for (int i = 0; i < 3; i++) {
+              setf(sb + i, g, (float)(m.body_pos[3 * body + i] + Rb[3 * i] * jp[0] + Rb[3 * i + 1] * jp[1] + Rb[3 * i + 2] * jp[2]));
+              setf(sb + 21 + i, g, (float)(Rb[3 * i] * jx[0] + Rb[3 * i + 1] * jx[1] + Rb[3 * i + 2] * jx[2]));
+              setf(sb + 7 + i, g, m.body_ipos[3 * body + i]);
+            }
+            for (int i = 0; i < 4; i++) setf(sb + 3 + i, g, (float)bq[i]);
+            // body_quat o (0, axis)
+            setf(sb + 10, g, (float)(-bq[1] * jx[0] - bq[2] * jx[1] - bq[3] * jx[2]));
+            setf(sb + 11, g, (float)(bq[0] * jx[0] + bq[2] * jx[2] - bq[3] * jx[1]));
+            setf(sb + 12, g, (float)(bq[0] * jx[1] - bq[1] * jx[2] + bq[3] * jx[0]));
+            setf(sb + 13, g, (float)(bq[0] * jx[2] + bq[1] * jx[1] - bq[2] * jx[0]));
             setf(sb + 14, g, m.body_mass[body]);
+            // inertia tensor in the body frame: Ri diag(inertia) Ri'
+            const double in[3] = {m.body_inertia[3 * body], m.body_inertia[3 * body + 1], m.body_inertia[3 * body + 2]};
+            const int ra[6] = {0, 1, 2, 0, 0, 1}, cb[6] = {0, 1, 2, 1, 2, 2};
+            for (int e = 0; e < 6; e++) {
+              double t = 0;
+              for (int k = 0; k < 3; k++) t += Ri[3 * ra[e] + k] * in[k] * Ri[3 * cb[e] + k];
+              setf(sb + 15 + e, g, (float)t);
+            }
           } else {
             ownbits |= 1 << p;  // padding is private
-            setf(sb + 3, g, 1.f); setf(sb + 10, g, 1.f);
+            setf(sb + 3, g, 1.f);
           }
           if (p == 0) continue;
           const int sj = mp.jnt(p), si = mp.ijnt(p);

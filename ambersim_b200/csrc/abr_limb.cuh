@@ -31,7 +31,8 @@ namespace limb {
 
 // ---- per-lane model table: word (slot, lane) lives at T[slot * kStride + lane]
 constexpr int kStride = 8;  // max lanes per world
-constexpr int kBodyW = 18;  // body_pos3 body_quat4 body_ipos3 body_iquat4 mass inertia3
+constexpr int kBodyW = 24;  // anchor in the parent frame (body_pos + R(body_quat) jnt_pos)3 | body_quat4 | body_ipos3 | body_quat o (0, jnt_axis)4 |
+                            // mass | inertia tensor in the body frame (xx yy zz xy xz yz)6 | joint axis in the parent frame3
 constexpr int kJntW = 35;   // jnt_pos3 jnt_axis3 qpos0 qpos_spring stiffness damping armature range2 margin | limit prm[10] | act prm[11]
 constexpr int kConW = 33;   // geom_pos3 radius | con prm[14] | plane normal3 point3 frame9
 constexpr int kJntI = 4;    // flags, global dof, global qpos adr, global actuator
@@ -150,6 +151,24 @@ __device__ __forceinline__ void inert_mul_unit(const float* I, int q, float* r) 
   r[1] = (q == 0) ? I[8] : ((q == 2) ? -I[6] : 0.f);
   r[2] = (q == 0) ? -I[7] : ((q == 1) ? I[6] : 0.f);
   r[3] = I[9] * e[0]; r[4] = I[9] * e[1]; r[5] = I[9] * e[2];
+}
+__device__ __forceinline__ void m_rot(const float (&R)[9], const float* v, float* r) {
+  r[0] = R[0] * v[0] + R[1] * v[1] + R[2] * v[2];
+  r[1] = R[3] * v[0] + R[4] * v[1] + R[5] * v[2];
+  r[2] = R[6] * v[0] + R[7] * v[1] + R[8] * v[2];
+}
+// R Ib R' for a symmetric Ib = (xx yy zz xy xz yz): the body-frame inertia tensor in the world frame, same packing
+__device__ __forceinline__ void rot_inertia(const float (&R)[9], const float* I, float* out) {
+  float T[9];
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    T[3 * r + 0] = R[3 * r] * I[0] + R[3 * r + 1] * I[3] + R[3 * r + 2] * I[4];
+    T[3 * r + 1] = R[3 * r] * I[3] + R[3 * r + 1] * I[1] + R[3 * r + 2] * I[5];
+    T[3 * r + 2] = R[3 * r] * I[4] + R[3 * r + 1] * I[5] + R[3 * r + 2] * I[2];
+  }
+  constexpr int ra[6] = {0, 1, 2, 0, 0, 1}, cb[6] = {0, 1, 2, 1, 2, 2};
+#pragma unroll
+  for (int e = 0; e < 6; e++) out[e] = T[3 * ra[e]] * R[3 * cb[e]] + T[3 * ra[e] + 1] * R[3 * cb[e] + 1] + T[3 * ra[e] + 2] * R[3 * cb[e] + 2];
 }
 static __device__ __noinline__ float pow_cold(float x, float p) { return powf(x, p); }
 // the sampler's counter-based normal: out of line so the shoot-mode loop body does not carry three copies of it
@@ -293,8 +312,11 @@ template <int NL, int NC, bool CB> struct Rows {
   static constexpr int N = 6 + NL, NR = NL + 4 * NC, NCC = NC > 0 ? NC : 1;
   float D[NR], aref[NR], lsg[NL];
   float B[CB ? 1 : NCC][3][CB ? 1 : N];  // contact Jacobian basis: normal, tangent 1, tangent 2
-  float g[CB ? NCC : 1][3][3];           // CB: off_c x frame_k
+  float g[CB ? NCC : 1][3][3];           // CB: (contact point - leaf body origin) x frame_k
   float fr[3][3];                        // CB: the plane's contact frame
+  float sref[3];                         // CB: leaf body origin - subtree CoM. The contact algebra is done about the leaf body's
+                                         // origin (levers of a few cm) and shifted to / from the CoM-referenced twists once per 6-vector:
+                                         // about the CoM the 6x6 weight would carry D * (1 m)^2 terms that cancel to D * (5 cm)^2
   float mu1[NCC], mu2[NCC];              // 0 on condim-1 slots
 };
 // CB: per-contact (normal, tangent1, tangent2) components of J x from the leaf body's twist V = sum_d cdof[d] x[d]
@@ -303,9 +325,10 @@ template <int NL, int NC> __device__ __forceinline__ void contact_bv(const Rows<
   float V[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int d = 0; d < 6 + NL; d++) cdof_axpy(cdof, d, x[d], V);
-  float lin[3];
+  float sh[3], lin[3];
+  v_cross(V, R.sref, sh);  // linear velocity at the leaf body's origin
 #pragma unroll
-  for (int k = 0; k < 3; k++) lin[k] = R.fr[k][0] * V[3] + R.fr[k][1] * V[4] + R.fr[k][2] * V[5];
+  for (int k = 0; k < 3; k++) lin[k] = R.fr[k][0] * (V[3] + sh[0]) + R.fr[k][1] * (V[4] + sh[1]) + R.fr[k][2] * (V[5] + sh[2]);
 #pragma unroll
   for (int c = 0; c < NC; c++)
 #pragma unroll
@@ -379,7 +402,12 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
   constexpr Map mp{NL, NC};
   const ShareT<LGC>& S = C.S;
   // ---------------------------------------------------------------- kinematics (smooth.kinematics)
-  float xpos[NP][3], xquat[NP][4], xipos[NP][3], xanc[NP][3], xax[NP][3];
+  // One rotation matrix per body. Everything constant in the PARENT frame is folded into the table (joint anchor
+  // body_pos + R(body_quat) jnt_pos, joint axis R(body_quat) jnt_axis, and body_quat o (0, jnt_axis), so that
+  // body_quat o q_joint = cos(a/2) body_quat + sin(a/2) [body_quat o (0, axis)]); the body's inertia is carried as its
+  // body-frame tensor, so the inertial-frame quaternion never has to be composed at run time.
+  float xpos[NP][3], xquat[NP][4], xipos[NP][3], xanc[NP][3], xax[NP][3], irot[NP][6];
+  float R0[9], Rp[9];
   {
     float q[4] = {s.qt[3], s.qt[4], s.qt[5], s.qt[6]};
     normalize_k<4>(q);
@@ -388,11 +416,16 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
     for (int i = 0; i < 3; i++) { xpos[0][i] = s.qt[i]; xanc[0][i] = s.qt[i]; xax[0][i] = (i == 2) ? 1.f : 0.f; }
 #pragma unroll
     for (int i = 0; i < 4; i++) xquat[0][i] = q[i];
+    q_to_mat(q, R0);
+#pragma unroll
+    for (int i = 0; i < 9; i++) Rp[i] = R0[i];
     const float ip[3] = {LTF(mp.body(0) + 7), LTF(mp.body(0) + 8), LTF(mp.body(0) + 9)};
+    const float Ib[6] = {LTF(mp.body(0) + 15), LTF(mp.body(0) + 16), LTF(mp.body(0) + 17), LTF(mp.body(0) + 18), LTF(mp.body(0) + 19), LTF(mp.body(0) + 20)};
     float r[3];
-    q_rot(ip, q, r);
+    m_rot(R0, ip, r);
 #pragma unroll
     for (int i = 0; i < 3; i++) xipos[0][i] = xpos[0][i] + r[i];
+    rot_inertia(R0, Ib, irot[0]);
   }
   int jflags[NP];
   jflags[0] = 0;
@@ -401,25 +434,25 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
     const int fl = LTI(mp.ijnt(p));
     jflags[p] = fl;
     const int type = fl & kJTypeMask;
-    const float bp[3] = {LTF(mp.body(p)), LTF(mp.body(p) + 1), LTF(mp.body(p) + 2)};
+    const float ca[3] = {LTF(mp.body(p)), LTF(mp.body(p) + 1), LTF(mp.body(p) + 2)};
     const float bq[4] = {LTF(mp.body(p) + 3), LTF(mp.body(p) + 4), LTF(mp.body(p) + 5), LTF(mp.body(p) + 6)};
+    const float bj[4] = {LTF(mp.body(p) + 10), LTF(mp.body(p) + 11), LTF(mp.body(p) + 12), LTF(mp.body(p) + 13)};
+    const float cx[3] = {LTF(mp.body(p) + 21), LTF(mp.body(p) + 22), LTF(mp.body(p) + 23)};
     const float jp[3] = {LTF(mp.jnt(p)), LTF(mp.jnt(p) + 1), LTF(mp.jnt(p) + 2)};
-    const float jx[3] = {LTF(mp.jnt(p) + 3), LTF(mp.jnt(p) + 4), LTF(mp.jnt(p) + 5)};
-    float r[3], pos[3], quat[4], axis[3], anchor[3];
-    q_rot(bp, xquat[p - 1], r);
+    float r[3], pos[3], axis[3], anchor[3];
+    m_rot(Rp, ca, r);
 #pragma unroll
-    for (int i = 0; i < 3; i++) pos[i] = xpos[p - 1][i] + r[i];
-    q_mul(xquat[p - 1], bq, quat);
-    q_rot(jp, quat, r);
-#pragma unroll
-    for (int i = 0; i < 3; i++) anchor[i] = r[i] + pos[i];
-    q_rot(jx, quat, axis);
+    for (int i = 0; i < 3; i++) anchor[i] = xpos[p - 1][i] + r[i];
+    m_rot(Rp, cx, axis);
     const float dq = s.qc[p - 1] - LTF(mp.jnt(p) + 6);
     // hinge: rotate about the joint axis and re-anchor; slide: translate along the axis
-    float ql[4], qn[4];
-    axis_angle_quat_bf(jx, (type == kJHinge) ? dq : 0.f, ql);
-    q_mul(quat, ql, qn);
-    q_rot(jp, qn, r);
+    float sn, cs, qloc[4], qn[4], Rn[9];
+    sincos_bf(((type == kJHinge) ? dq : 0.f) * 0.5f, sn, cs);
+#pragma unroll
+    for (int i = 0; i < 4; i++) qloc[i] = fmaf(sn, bj[i], cs * bq[i]);
+    q_mul(xquat[p - 1], qloc, qn);
+    q_to_mat(qn, Rn);
+    m_rot(Rn, jp, r);
     const float sl = (type == kJSlide) ? dq : 0.f;
 #pragma unroll
     for (int i = 0; i < 3; i++) pos[i] = anchor[i] - r[i] + axis[i] * sl;
@@ -428,9 +461,13 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
 #pragma unroll
     for (int i = 0; i < 4; i++) xquat[p][i] = qn[i];
     const float ip[3] = {LTF(mp.body(p) + 7), LTF(mp.body(p) + 8), LTF(mp.body(p) + 9)};
-    q_rot(ip, qn, r);
+    const float Ib[6] = {LTF(mp.body(p) + 15), LTF(mp.body(p) + 16), LTF(mp.body(p) + 17), LTF(mp.body(p) + 18), LTF(mp.body(p) + 19), LTF(mp.body(p) + 20)};
+    m_rot(Rn, ip, r);
 #pragma unroll
     for (int i = 0; i < 3; i++) xipos[p][i] = pos[i] + r[i];
+    rot_inertia(Rn, Ib, irot[p]);
+#pragma unroll
+    for (int i = 0; i < 9; i++) Rp[i] = Rn[i];
   }
   // ---------------------------------------------------------------- com_pos: subtree CoM, cinert, cdof
   float com[3];
@@ -450,32 +487,23 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
   for (int p = 0; p < NP; p++) {
     const float off[3] = {xipos[p][0] - com[0], xipos[p][1] - com[1], xipos[p][2] - com[2]};
     const float ms = LTF(mp.body(p) + 14);
-    const float iq[4] = {LTF(mp.body(p) + 10), LTF(mp.body(p) + 11), LTF(mp.body(p) + 12), LTF(mp.body(p) + 13)};
-    const float in[3] = {LTF(mp.body(p) + 15), LTF(mp.body(p) + 16), LTF(mp.body(p) + 17)};
-    float q2[4], R[9];
-    q_mul(xquat[p], iq, q2);
-    q_to_mat(q2, R);
     const float oo = v_dot(off, off);
     constexpr int ra[6] = {0, 1, 2, 0, 0, 1}, cb[6] = {0, 1, 2, 1, 2, 2};
 #pragma unroll
     for (int e = 0; e < 6; e++) {
       const int r_ = ra[e], c_ = cb[e];
-      float t = R[3 * r_] * in[0] * R[3 * c_] + R[3 * r_ + 1] * in[1] * R[3 * c_ + 1] + R[3 * r_ + 2] * in[2] * R[3 * c_ + 2];
-      t += ms * ((r_ == c_ ? oo : 0.f) - off[r_] * off[c_]);
-      cinert[p][e] = t;
+      cinert[p][e] = irot[p][e] + ms * ((r_ == c_ ? oo : 0.f) - off[r_] * off[c_]);
     }
     cinert[p][6] = off[0] * ms; cinert[p][7] = off[1] * ms; cinert[p][8] = off[2] * ms; cinert[p][9] = ms;
   }
   float cdof[N][6];
   {
     const float off[3] = {com[0] - xanc[0][0], com[1] - xanc[0][1], com[2] - xanc[0][2]};
-    float R[9];
-    q_to_mat(xquat[0], R);
 #pragma unroll
     for (int q = 0; q < 3; q++) {
 #pragma unroll
       for (int i = 0; i < 6; i++) cdof[q][i] = (i == 3 + q) ? 1.f : 0.f;
-      const float ax[3] = {R[q], R[3 + q], R[6 + q]};
+      const float ax[3] = {R0[q], R0[3 + q], R0[6 + q]};
       float cr[3];
       v_cross(ax, off, cr);
       cdof[3 + q][0] = ax[0]; cdof[3 + q][1] = ax[1]; cdof[3 + q][2] = ax[2];
@@ -525,11 +553,12 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
     const float kk = rad + 0.5f * dist;
     const float off[3] = {sp[0] - n[0] * kk - com[0], sp[1] - n[1] * kk - com[1], sp[2] - n[2] * kk - com[2]};
     if constexpr (CB) {
+      const float offb[3] = {r[0] - n[0] * kk, r[1] - n[1] * kk, r[2] - n[2] * kk};  // contact point - body origin
 #pragma unroll
       for (int k = 0; k < 3; k++) {
         const float fr[3] = {LTF(mp.con(c) + 24 + 3 * k), LTF(mp.con(c) + 25 + 3 * k), LTF(mp.con(c) + 26 + 3 * k)};
-        v_cross(off, fr, R.g[c][k]);
-        if (c == 0) { R.fr[k][0] = fr[0]; R.fr[k][1] = fr[1]; R.fr[k][2] = fr[2]; }
+        v_cross(offb, fr, R.g[c][k]);
+        if (c == 0) { R.fr[k][0] = fr[0]; R.fr[k][1] = fr[1]; R.fr[k][2] = fr[2]; R.sref[k] = bx[k] - com[k]; }
       }
     } else {
       const int ld = (pc < 0) ? -1 : 5 + pc;
@@ -792,6 +821,12 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
       if constexpr (CB && NC > 0) {
 #pragma unroll
         for (int i = 0; i < 3; i++) Wt[3 + i] = R.fr[0][i] * Fl[0] + R.fr[1][i] * Fl[1] + R.fr[2][i] * Fl[2];
+        {
+          float sh[3];
+          v_cross(R.sref, Wt + 3, sh);  // torque about the CoM = torque about the body origin + sref x force
+#pragma unroll
+          for (int i = 0; i < 3; i++) Wt[i] += sh[i];
+        }
 #pragma unroll
         for (int d = 0; d < N; d++)
           up[d] += cdof_dot(cdof, d, Wt);
@@ -860,14 +895,20 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
     if constexpr (CB && NC > 0) {
 #pragma unroll
       for (int j = 0; j < N; j++) {
-        float KC[6];
+        float cj[6], KC[6], sh[3] = {0.f, 0.f, 0.f};
+        if (j >= 3) v_cross(cdof[j], R.sref, sh);  // dof j's twist at the leaf body's origin (a pure translation does not change)
+#pragma unroll
+        for (int b = 0; b < 3; b++) { cj[b] = cdof[j][b]; cj[3 + b] = cdof[j][3 + b] + sh[b]; }
 #pragma unroll
         for (int a = 0; a < 6; a++) {
           float t = 0.f;
 #pragma unroll
-          for (int b = 0; b < 6; b++) t = fmaf(K[a >= b ? TR(a, b) : TR(b, a)], cdof[j][b], t);
+          for (int b = 0; b < 6; b++) t = fmaf(K[a >= b ? TR(a, b) : TR(b, a)], cj[b], t);
           KC[a] = (j < 3) ? K[a >= 3 + j ? TR(a, 3 + j) : TR(3 + j, a)] : t;
         }
+        v_cross(R.sref, KC + 3, sh);  // back to the CoM reference: the "torque" part picks up sref x "force" part
+#pragma unroll
+        for (int b = 0; b < 3; b++) KC[b] += sh[b];
 #pragma unroll
         for (int i = 0; i < N; i++)
           if (i >= j) H[TR(i, j)] += cdof_dot(cdof, i, KC);

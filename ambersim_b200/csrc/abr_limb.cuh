@@ -363,16 +363,19 @@ template <int NL, int NC, bool CB> __device__ __forceinline__ void mul_j(const R
   }
 }
 // cost = 0.5 sum_active D Jaref^2 + 0.5 (Ma - fs).(a - as); uniform over the world's lanes
-template <int NL, int NC, bool CB, class SH> __device__ __forceinline__ float solver_cost(const Rows<NL, NC, CB>& R, const SH& S, const float (&x)[6 + NL], const float (&Mx)[6 + NL],
+template <int NL, int NC, bool CB, class SH, bool AT_AS = false> __device__ __forceinline__ float solver_cost(const Rows<NL, NC, CB>& R, const SH& S, const float (&x)[6 + NL], const float (&Mx)[6 + NL],
                                                                        const float (&Jx)[NL + 4 * NC], const float (&fs)[6 + NL], const float (&as)[6 + NL], float& gauss) {
   float sc = 0.f, g = 0.f;
 #pragma unroll
   for (int r = 0; r < NL + 4 * NC; r++)
     if (Jx[r] < 0.f) sc = fmaf(R.D[r] * Jx[r], Jx[r], sc);
+  if (!AT_AS) {  // at x = qacc_smooth the Gauss term (M x - f).(x - as) is exactly zero
 #pragma unroll
-  for (int d = 0; d < 6 + NL; d++)
-    if (S.o(PD(d))) g = fmaf(Mx[d] - fs[d], x[d] - as[d], g);
-  sc = gall(sc, S.lg()); g = gall(g, S.lg());
+    for (int d = 0; d < 6 + NL; d++)
+      if (S.o(PD(d))) g = fmaf(Mx[d] - fs[d], x[d] - as[d], g);
+    g = gall(g, S.lg());
+  }
+  sc = gall(sc, S.lg());
   gauss = 0.5f * g;
   return 0.5f * sc + 0.5f * g;
 }
@@ -770,7 +773,7 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
   mul_j<NL, NC, CB>(R, cdof, as, Jaref);
 #pragma unroll
   for (int r = 0; r < NR; r++) Jaref[r] -= R.aref[r];
-  cost = solver_cost<NL, NC, CB>(R, S, as, Ma, Jaref, fs, as, gauss);
+  cost = solver_cost<NL, NC, CB, ShareT<LGC>, true>(R, S, as, Ma, Jaref, fs, as, gauss);
 #pragma unroll
   for (int d = 0; d < N; d++) s.a[d] = as[d];
   if (!(C.disableflags & ABR_DSBL_WARMSTART)) {
@@ -1075,6 +1078,25 @@ template <int NL, int NC, int LGC> __device__ __forceinline__ float quad_x_diag(
   }
   return acc;
 }
+// The same sum from a per-lane table in shared memory built once per launch (rollout kernel): slot k of lane l holds
+// {running weight, terminal weight, goal} at ct[(3 k + {0,1,2}) * 32 + l] with zero weights where the lane does not own the
+// entry, so the per-step evaluation is two loads with immediate offsets + three FP instructions per state entry.
+// Slots: 0..6 trunk qpos, 7..12 trunk qvel, then (q, v) per chain position; after them one control weight per position.
+template <int NL> __device__ __forceinline__ constexpr int cost_slots() { return 13 + 2 * NL; }
+template <int NL, int NC> __device__ __forceinline__ float quad_x_tab(const Lane<NL, NC>& s, const float* ct /* + lane + (terminal ? 32 : 0) */, const float* cg /* goal column + lane */) {
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < 7; i++) { const float e = s.qt[i] - cg[(3 * i) * 32]; acc = fmaf(ct[(3 * i) * 32] * e, e, acc); }
+#pragma unroll
+  for (int i = 0; i < 6; i++) { const float e = s.v[i] - cg[(3 * (7 + i)) * 32]; acc = fmaf(ct[(3 * (7 + i)) * 32] * e, e, acc); }
+#pragma unroll
+  for (int p = 1; p <= NL; p++) {
+    const int k = 13 + 2 * (p - 1);
+    const float e = s.qc[p - 1] - cg[(3 * k) * 32]; acc = fmaf(ct[(3 * k) * 32] * e, e, acc);
+    const float e2 = s.v[5 + p] - cg[(3 * (k + 1)) * 32]; acc = fmaf(ct[(3 * (k + 1)) * 32] * e2, e2, acc);
+  }
+  return acc;
+}
 template <int NL, int NC, int LGC> __device__ __forceinline__ void store_x(const Lane<NL, NC>& s, const LaneCfg<LGC>& C, float* x, int nq) {
   constexpr Map mp{NL, NC};
   if (C.S.o(0)) {
@@ -1137,10 +1159,31 @@ __global__ void __launch_bounds__(kTPB, ABR_LIMB_MINB) k_limb_rollout(const __gr
     s.a[5 + p] = 0.f;
   }
   float* xs = A.xs_out ? A.xs_out + (size_t)w * (Nh + 1) * nx : nullptr;
+  // per-lane cost table (see quad_x_tab): weights of entries this lane does not own are zero
+  constexpr int NS = cost_slots<NL>();
+  float* ctab = cxg + nx + threadIdx.x;
+  if (A.cost.enabled) {
+    const bool own0 = C.S.o(0);
+#pragma unroll
+    for (int i = 0; i < 13; i++) {
+      const int gi = (i < 7) ? i : nq + (i - 7);
+      ctab[(3 * i) * 32] = own0 ? cqd[gi] : 0.f; ctab[(3 * i + 1) * 32] = own0 ? cqf[gi] : 0.f; ctab[(3 * i + 2) * 32] = cxg[gi];
+    }
+#pragma unroll
+    for (int p = 1; p <= NL; p++) {
+      const int gd = LTI(mp.ijnt(p) + 1), gq = LTI(mp.ijnt(p) + 2), ga = LTI(mp.ijnt(p) + 3);
+      const bool own = gd >= 0 && C.S.o(p);
+      const int k = 13 + 2 * (p - 1);
+      ctab[(3 * k) * 32] = own ? cqd[gq] : 0.f; ctab[(3 * k + 1) * 32] = own ? cqf[gq] : 0.f; ctab[(3 * k + 2) * 32] = own ? cxg[gq] : 0.f;
+      ctab[(3 * k + 3) * 32] = own ? cqd[nq + gd] : 0.f; ctab[(3 * k + 4) * 32] = own ? cqf[nq + gd] : 0.f; ctab[(3 * k + 5) * 32] = own ? cxg[nq + gd] : 0.f;
+      ctab[(3 * NS + (p - 1)) * 32] = (ga >= 0 && C.S.o(p)) ? crd[ga] : 0.f;
+    }
+  }
+  const float* cgoal = ctab + 2 * 32;
   float cacc = 0.f;
   if (!resume) {
     if (xs && valid) store_x<NL, NC, LGC>(s, C, xs, nq);
-    if (A.cost.enabled) cacc += quad_x_diag<NL, NC, LGC>(s, C, Nh > 0 ? cqd : cqf, cxg, nq);
+    if (A.cost.enabled) cacc += quad_x_tab<NL, NC>(s, ctab + (Nh > 0 ? 0 : 32), cgoal);
   } else {
     cacc = carry[nx + L.nv + g];
   }
@@ -1166,10 +1209,10 @@ __global__ void __launch_bounds__(kTPB, ABR_LIMB_MINB) k_limb_rollout(const __gr
           }
           if (C.S.o(p)) {
             if (A.us_out && valid) A.us_out[((size_t)w * Nh + t) * nu + ga] = u;
-            if (A.cost.enabled) cacc = fmaf(crd[ga] * u, u, cacc);
           }
         }
         s.ctrl[p - 1] = u;
+        if (A.cost.enabled) cacc = fmaf(ctab[(3 * NS + (p - 1)) * 32] * u, u, cacc);
       }
     }
     float M[NTRI], fs[N], fc[N];
@@ -1177,7 +1220,7 @@ __global__ void __launch_bounds__(kTPB, ABR_LIMB_MINB) k_limb_rollout(const __gr
     if (t >= 0) {
       euler<NL, NC, LGC>(s, C, M, fs, fc);
       if (xs && valid) store_x<NL, NC, LGC>(s, C, xs + (size_t)(t + 1) * nx, nq);
-      if (A.cost.enabled) cacc += quad_x_diag<NL, NC, LGC>(s, C, (t == Nh - 1) ? cqf : cqd, cxg, nq);
+      if (A.cost.enabled) cacc += quad_x_tab<NL, NC>(s, ctab + ((t == Nh - 1) ? 32 : 0), cgoal);
     }
   }
   if (t_last < Nh) {  // hand the state to the next slice
@@ -1332,7 +1375,8 @@ template <int NL, int NC, class Args, class K> int launch_limb(K kern, const Lay
   int launch_limb_env_##NL##_##NC##_##TAG(const Layout&, const EnvArgs&, cudaStream_t);
 #define ABR_DEFINE_LIMB_LAUNCHERS(NL, NC, LGC, CB, TAG)                                                   \
   int launch_limb_rollout_##NL##_##NC##_##TAG(const Layout& L, const RolloutArgs& a, cudaStream_t st) { \
-    return limb::launch_limb<NL, NC>(limb::k_limb_rollout<NL, NC, LGC, CB>, L, a, a.nworld, 3 * L.nx + L.nu, st); \
+    return limb::launch_limb<NL, NC>(limb::k_limb_rollout<NL, NC, LGC, CB>, L, a, a.nworld,                 \
+                                     3 * L.nx + L.nu + (3 * (13 + 2 * NL) + NL) * limb::kTPB, st);         \
   }                                                                                                    \
   int launch_limb_env_##NL##_##NC##_##TAG(const Layout& L, const EnvArgs& a, cudaStream_t st) {        \
     return limb::launch_limb<NL, NC>(limb::k_limb_env<NL, NC, LGC, CB>, L, a, a.E, 0, st);                 \

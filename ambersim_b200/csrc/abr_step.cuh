@@ -85,15 +85,14 @@ __device__ __forceinline__ float v_normalize(float* x, int n) {
 }
 // cinert = (Ixx,Iyy,Izz,Ixy,Ixz,Iyz, m*off[3], m)
 __device__ __forceinline__ void inert_mul(const float* I, const float* v, float* r) {
-  float a0 = I[0] * v[0] + I[3] * v[1] + I[4] * v[2];
-  float a1 = I[3] * v[0] + I[1] * v[1] + I[5] * v[2];
-  float a2 = I[4] * v[0] + I[5] * v[1] + I[2] * v[2];
-  float c1[3], c2[3];
-  v_cross(I + 6, v + 3, c1);
-  v_cross(I + 6, v, c2);
-  float l0 = I[9] * v[3] - c2[0], l1 = I[9] * v[4] - c2[1], l2 = I[9] * v[5] - c2[2];
-  r[0] = a0 + c1[0]; r[1] = a1 + c1[1]; r[2] = a2 + c1[2];
-  r[3] = l0; r[4] = l1; r[5] = l2;
+  // angular: I3 w + (m c) x v_lin ; linear: m v_lin - (m c) x w. One FMA chain per component (no separate cross + add).
+  const float r0 = fmaf(-I[8], v[4], fmaf(I[7], v[5], fmaf(I[4], v[2], fmaf(I[3], v[1], I[0] * v[0]))));
+  const float r1 = fmaf(-I[6], v[5], fmaf(I[8], v[3], fmaf(I[5], v[2], fmaf(I[1], v[1], I[3] * v[0]))));
+  const float r2 = fmaf(-I[7], v[3], fmaf(I[6], v[4], fmaf(I[2], v[2], fmaf(I[5], v[1], I[4] * v[0]))));
+  const float l0 = fmaf(I[8], v[1], fmaf(-I[7], v[2], I[9] * v[3]));
+  const float l1 = fmaf(I[6], v[2], fmaf(-I[8], v[0], I[9] * v[4]));
+  const float l2 = fmaf(I[7], v[0], fmaf(-I[6], v[1], I[9] * v[5]));
+  r[0] = r0; r[1] = r1; r[2] = r2; r[3] = l0; r[4] = l1; r[5] = l2;
 }
 __device__ __forceinline__ void motion_cross(const float* u, const float* v, float* r) {
   float a[3], b[3], cc[3];

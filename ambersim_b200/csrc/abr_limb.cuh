@@ -793,9 +793,10 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
   float prev_cost = INFINITY;
   const float scale = 1.f / (C.meaninertia * (float)max(1, C.nv));
   bool live = true;
+  const bool need_fc = !(C.disableflags & ABR_DSBL_EULERDAMP);  // qfrc_constraint of the final point is only read by the implicit-damping Euler step
   for (int niter = 0;; niter++) {
-    // efc_force and qfrc_constraint at the current point
-    {
+    // efc_force and qfrc_constraint at the current point (skipped at the final point when nothing reads it)
+    if (niter < C.iterations || need_fc) {
       float up[N];
 #pragma unroll
       for (int d = 0; d < N; d++) up[d] = 0.f;

@@ -769,7 +769,9 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
   // ---------------------------------------------------------------- solver.solve (Newton)
   float Ma[N], Jaref[NR];
   float gauss, cost;
-  mul_m<N>(M, as, Ma, S);
+  // M qacc_smooth is qfrc_smooth itself (as = M^-1 fs): MJX multiplies it out again and gets fs back up to rounding
+#pragma unroll
+  for (int d = 0; d < N; d++) Ma[d] = fs[d];
   mul_j<NL, NC, CB>(R, cdof, as, Jaref);
 #pragma unroll
   for (int r = 0; r < NR; r++) Jaref[r] -= R.aref[r];

@@ -145,12 +145,11 @@ template <int N> __device__ __forceinline__ void cdof_axpy(const float (&cdof)[N
 }
 // inert_mul(I, e_{3+q}): the momentum of a unit translation along axis q
 __device__ __forceinline__ void inert_mul_unit(const float* I, int q, float* r) {
-  const float e[3] = {q == 0 ? 1.f : 0.f, q == 1 ? 1.f : 0.f, q == 2 ? 1.f : 0.f};
   // cross(I + 6, e_q) with the zero products dropped
   r[0] = (q == 1) ? -I[8] : ((q == 2) ? I[7] : 0.f);
   r[1] = (q == 0) ? I[8] : ((q == 2) ? -I[6] : 0.f);
   r[2] = (q == 0) ? -I[7] : ((q == 1) ? I[6] : 0.f);
-  r[3] = I[9] * e[0]; r[4] = I[9] * e[1]; r[5] = I[9] * e[2];
+  r[3] = (q == 0) ? I[9] : 0.f; r[4] = (q == 1) ? I[9] : 0.f; r[5] = (q == 2) ? I[9] : 0.f;
 }
 __device__ __forceinline__ void m_rot(const float (&R)[9], const float* v, float* r) {
   r[0] = R[0] * v[0] + R[1] * v[1] + R[2] * v[2];
@@ -284,9 +283,11 @@ template <int LGC> struct LaneCfg {
 #define LTF(slot) (C.T[(slot) * kStride])
 #define LTI(slot) (__float_as_int(C.T[(slot) * kStride]))
 
-// kbi: impedance, D and aref of one active row (constraint._kbi / _row in SURVEY App. A.7)
-__device__ __forceinline__ void row_kbi(const float* prm /* smem, stride kStride */, float pos, float jvel, float invw, bool active, float& D, float& aref) {
-  const float k = prm[0 * kStride], b = prm[1 * kStride], dmin = prm[2 * kStride], dmax = prm[3 * kStride];
+// kbi: impedance, D and aref of one active row (constraint._kbi / _row in SURVEY App. A.7), split so that the four pyramid
+// rows of a contact (same penetration, same solref / solimp) evaluate the impedance once
+struct Kbi { float b, kip, g; };  // damping b, stiffness * impedance * pos, (1 - imp) / imp
+__device__ __forceinline__ Kbi kbi_imp(const float* prm /* smem, stride kStride */, float pos) {
+  const float k = prm[0 * kStride], dmin = prm[2 * kStride], dmax = prm[3 * kStride];
   const float iw = prm[4 * kStride], mid = prm[5 * kStride], power = prm[6 * kStride];
   const float x = fabsf(pos) * iw;
   float ia, ib;
@@ -297,9 +298,17 @@ __device__ __forceinline__ void row_kbi(const float* prm /* smem, stride kStride
   float imp = dmin + y * (dmax - dmin);
   imp = fminf(fmaxf(imp, dmin), dmax);
   if (x > 1.f) imp = dmax;
-  const float R = fmaxf(invw * (1.f - imp) * rcp_fast(imp), kMinVal);
+  Kbi o;
+  o.b = prm[1 * kStride]; o.kip = k * imp * pos; o.g = (1.f - imp) * rcp_fast(imp);
+  return o;
+}
+__device__ __forceinline__ void kbi_row(const Kbi& q, float jvel, float invw, bool active, float& D, float& aref) {
+  const float R = fmaxf(invw * q.g, kMinVal);
   D = active ? rcp_fast(R) : 0.f;
-  aref = active ? -b * jvel - k * imp * pos : 0.f;
+  aref = active ? -q.b * jvel - q.kip : 0.f;
+}
+__device__ __forceinline__ void row_kbi(const float* prm, float pos, float jvel, float invw, bool active, float& D, float& aref) {
+  kbi_row(kbi_imp(prm, pos), jvel, invw, active, D, aref);
 }
 
 struct LSP { float alpha, cost, d0, d1; };
@@ -752,6 +761,7 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
       const float pos = cdist[c] - prm[13 * kStride];
       const bool act0 = (pos < 0.f) && (LTI(mp.icon(c)) >= 0);
       const bool pyr = LTI(mp.icon(c) + 1) == 3;
+      const Kbi kq = kbi_imp(prm, pos);
 #pragma unroll
       for (int sub = 0; sub < 4; sub++) {
         const int r = NL + 4 * c + sub;
@@ -762,7 +772,7 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
           const float mu0 = prm[(sub < 2 ? 11 : 12) * kStride];
           invw *= C.frs * C.frs * (1.f + mu * mu) / (1.f + mu0 * mu0);
         }
-        row_kbi(prm, pos, jvel, invw, act0 && (pyr || sub == 0), R.D[r], R.aref[r]);
+        kbi_row(kq, jvel, invw, act0 && (pyr || sub == 0), R.D[r], R.aref[r]);
       }
     }
   }

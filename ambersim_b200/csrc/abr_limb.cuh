@@ -261,6 +261,21 @@ template <int N, class SH> __device__ __forceinline__ void mul_m(const float (&M
   }
 }
 
+// ------------------------------------------------------------------------------ compile-time specialisation
+// Code that a launch never executes still sits in the horizon loop's instruction stream and costs fetch bandwidth
+// (measured: the implicit-damping Euler block, the multi-iteration blocks, the trajectory stores and the other
+// mode's control path together cost 8 % at every batch size). SPEC < 0 keeps every decision at run time (any options);
+// SPEC >= 0 fixes them: bit 0 = eulerdamp enabled, bit 1 = more than one Newton iteration, bit 2 = trajectories /
+// controls are written out, bit 3 = sampler mode (controls generated from the guess + noise). The launcher picks the
+// variant from the model's options and the call's arguments; the built fast variants have bits 0 and 1 clear.
+template <int SPEC> struct Spec {
+  static constexpr bool gen = SPEC < 0;
+  __device__ __forceinline__ static bool edamp(int disableflags) { return gen ? !(disableflags & ABR_DSBL_EULERDAMP) : ((SPEC & 1) != 0); }
+  __device__ __forceinline__ static bool multi(int iterations) { return gen ? iterations != 1 : ((SPEC & 2) != 0); }
+  __device__ __forceinline__ static bool out(const void* p) { return gen ? p != nullptr : (((SPEC & 4) != 0) && p != nullptr); }
+  __device__ __forceinline__ static bool sampler(int mode) { return gen ? mode == 1 : ((SPEC & 8) != 0); }
+};
+
 // ------------------------------------------------------------------------------ lane state
 template <int NL, int NC> struct Lane {
   static constexpr int NP = NL + 1, N = 6 + NL, NTRI = N * (N + 1) / 2, NR = NL + 4 * NC;
@@ -408,7 +423,7 @@ template <int NR> __device__ __forceinline__ LSP ls_eval(const float (&Jaref)[NR
 
 // mjx.forward for one lane: on exit s.a = qacc, s.warm = qacc; M, fs, fc are returned for the
 // implicit-damping Euler variant.
-template <int NL, int NC, int LGC, bool CB>
+template <int NL, int NC, int LGC, bool CB, int SPEC>
 __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, float (&M)[(6 + NL) * (7 + NL) / 2], float (&fs)[6 + NL], float (&fc)[6 + NL]) {
   constexpr int NP = NL + 1, N = 6 + NL, NTRI = N * (N + 1) / 2, NR = NL + 4 * NC;
   constexpr Map mp{NL, NC};
@@ -805,7 +820,7 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
   float prev_cost = INFINITY;
   const float scale = 1.f / (C.meaninertia * (float)max(1, C.nv));
   bool live = true;
-  const bool need_fc = !(C.disableflags & ABR_DSBL_EULERDAMP);  // qfrc_constraint of the final point is only read by the implicit-damping Euler step
+  const bool need_fc = Spec<SPEC>::edamp(C.disableflags);  // qfrc_constraint of the final point is only read by the implicit-damping Euler step
   for (int niter = 0;; niter++) {
     // efc_force and qfrc_constraint at the current point (skipped at the final point when nothing reads it)
     if (niter < C.iterations || need_fc) {
@@ -935,7 +950,7 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
 #pragma unroll
     for (int d = 0; d < N; d++) mg[d] = grad[d];
     ldl_solve<N>(H, hD, mg, S);
-    if (C.iterations != 1) {
+    if (Spec<SPEC>::multi(C.iterations)) {
       float gn = 0.f;
 #pragma unroll
       for (int d = 0; d < N; d++) gn += S.o(PD(d)) ? grad[d] * grad[d] : 0.f;
@@ -1002,7 +1017,7 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
     for (int d = 0; d < N; d++) { s.a[d] = fmaf(search[d], alpha, s.a[d]); Ma[d] = fmaf(mv[d], alpha, Ma[d]); }
 #pragma unroll
     for (int r = 0; r < NR; r++) Jaref[r] = fmaf(jv[r], alpha, Jaref[r]);
-    if (C.iterations != 1) {
+    if (Spec<SPEC>::multi(C.iterations)) {
       float g2;
       const float c2 = solver_cost<NL, NC, CB>(R, S, s.a, Ma, Jaref, fs, as, g2);
       if (live) { prev_cost = cost; cost = c2; gauss = g2; }
@@ -1013,12 +1028,12 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
 }
 
 // forward.euler (+ implicit joint damping unless EULERDAMP is disabled) and position integration
-template <int NL, int NC, int LGC>
+template <int NL, int NC, int LGC, int SPEC>
 __device__ __forceinline__ void euler(Lane<NL, NC>& s, const LaneCfg<LGC>& C, float (&M)[(6 + NL) * (7 + NL) / 2], const float (&fs)[6 + NL], const float (&fc)[6 + NL]) {
   constexpr int N = 6 + NL;
   constexpr Map mp{NL, NC};
   const float dt = C.dt;
-  if (!(C.disableflags & ABR_DSBL_EULERDAMP)) {
+  if (Spec<SPEC>::edamp(C.disableflags)) {
     float hD[N], rhs[N];
 #pragma unroll
     for (int i = 0; i < N; i++) {
@@ -1126,7 +1141,7 @@ template <int NL, int NC, int LGC> __device__ __forceinline__ void store_x(const
 }
 
 // shoot (shooting.py:22-48) / the sampler's rollouts (shooting.py:140-153) on the limb path
-template <int NL, int NC, int LGC, bool CB>
+template <int NL, int NC, int LGC, bool CB, int SPEC>
 __global__ void __launch_bounds__(kTPB, ABR_LIMB_MINB) k_limb_rollout(const __grid_constant__ Layout L, const __grid_constant__ RolloutArgs A) {
   extern __shared__ __align__(16) float smem[];
   constexpr Map mp{NL, NC};
@@ -1147,7 +1162,7 @@ __global__ void __launch_bounds__(kTPB, ABR_LIMB_MINB) k_limb_rollout(const __gr
   const int w = valid ? wraw : A.nworld - 1;
   const LaneCfg<LGC> C = make_cfg<NL, NC, LGC>(L, smem, g);
   int prob = w, sample = 0;
-  if (A.mode == 1) {
+  if (Spec<SPEC>::sampler(A.mode)) {
     if (A.sample_ids) { prob = w; sample = A.sample_ids[w]; }
     else { prob = w / A.S; sample = A.sample_offset + (w - prob * A.S); }
   }
@@ -1156,7 +1171,7 @@ __global__ void __launch_bounds__(kTPB, ABR_LIMB_MINB) k_limb_rollout(const __gr
   const int cstride = nq + 2 * L.nv + 8;
   float* carry = A.carry ? A.carry + (size_t)w * cstride : nullptr;
   // a resumed slice reads the state its predecessor left in `carry` (same layout as x0, then qacc_warmstart)
-  const float* x0 = resume ? carry : A.x0 + (size_t)(A.mode == 1 ? prob : w) * A.x0_stride;
+  const float* x0 = resume ? carry : A.x0 + (size_t)(Spec<SPEC>::sampler(A.mode) ? prob : w) * A.x0_stride;
   Lane<NL, NC> s;
 #pragma unroll
   for (int i = 0; i < 7; i++) s.qt[i] = x0[i];
@@ -1171,7 +1186,7 @@ __global__ void __launch_bounds__(kTPB, ABR_LIMB_MINB) k_limb_rollout(const __gr
     s.ctrl[p - 1] = 0.f;
     s.a[5 + p] = 0.f;
   }
-  float* xs = A.xs_out ? A.xs_out + (size_t)w * (Nh + 1) * nx : nullptr;
+  float* xs = Spec<SPEC>::out(A.xs_out) ? A.xs_out + (size_t)w * (Nh + 1) * nx : nullptr;
   // per-lane cost table (see quad_x_tab): weights of entries this lane does not own are zero
   constexpr int NS = cost_slots<NL>();
   float* ctab = cxg + nx + threadIdx.x;
@@ -1209,7 +1224,7 @@ __global__ void __launch_bounds__(kTPB, ABR_LIMB_MINB) k_limb_rollout(const __gr
         const int ga = LTI(mp.ijnt(p) + 3);
         float u = 0.f;
         if (ga >= 0) {
-          if (A.mode == 0) {
+          if (!Spec<SPEC>::sampler(A.mode)) {
             u = A.us[(size_t)w * A.us_stride + (size_t)t * nu + ga];
           } else {
             float nz = 0.f;
@@ -1221,7 +1236,7 @@ __global__ void __launch_bounds__(kTPB, ABR_LIMB_MINB) k_limb_rollout(const __gr
             u = fminf(fmaxf(vv, LTF(mp.jnt(p) + 24)), LTF(mp.jnt(p) + 25));  // clip to actuator_ctrlrange (shooting.py:146-148)
           }
           if (C.S.o(p)) {
-            if (A.us_out && valid) A.us_out[((size_t)w * Nh + t) * nu + ga] = u;
+            if (Spec<SPEC>::out(A.us_out) && valid) A.us_out[((size_t)w * Nh + t) * nu + ga] = u;
           }
         }
         s.ctrl[p - 1] = u;
@@ -1229,9 +1244,9 @@ __global__ void __launch_bounds__(kTPB, ABR_LIMB_MINB) k_limb_rollout(const __gr
       }
     }
     float M[NTRI], fs[N], fc[N];
-    forward<NL, NC, LGC, CB>(s, C, M, fs, fc);
+    forward<NL, NC, LGC, CB, SPEC>(s, C, M, fs, fc);
     if (t >= 0) {
-      euler<NL, NC, LGC>(s, C, M, fs, fc);
+      euler<NL, NC, LGC, SPEC>(s, C, M, fs, fc);
       if (xs && valid) store_x<NL, NC, LGC>(s, C, xs + (size_t)(t + 1) * nx, nq);
       if (A.cost.enabled) cacc += quad_x_tab<NL, NC>(s, ctab + ((t == Nh - 1) ? 32 : 0), cgoal);
     }
@@ -1259,7 +1274,7 @@ __global__ void __launch_bounds__(kTPB, ABR_LIMB_MINB) k_limb_rollout(const __gr
 }
 
 // MjxEnv.pipeline_init / pipeline_step (rl/base.py:81-96) with the auto-reset blend, on the limb path
-template <int NL, int NC, int LGC, bool CB>
+template <int NL, int NC, int LGC, bool CB, int SPEC>
 __global__ void __launch_bounds__(kTPB, ABR_LIMB_MINB) k_limb_env(const __grid_constant__ Layout L, const __grid_constant__ EnvArgs A) {
   extern __shared__ __align__(16) float smem[];
   constexpr Map mp{NL, NC};
@@ -1299,8 +1314,8 @@ __global__ void __launch_bounds__(kTPB, ABR_LIMB_MINB) k_limb_env(const __grid_c
 #pragma unroll 1
   for (int it = 0; it < nfw; it++) {
     float M[NTRI], fs[N], fc[N];
-    forward<NL, NC, LGC, CB>(s, C, M, fs, fc);
-    if (!A.forward_only) euler<NL, NC, LGC>(s, C, M, fs, fc);
+    forward<NL, NC, LGC, CB, SPEC>(s, C, M, fs, fc);
+    if (!A.forward_only) euler<NL, NC, LGC, SPEC>(s, C, M, fs, fc);
   }
   bool fin = false;
   if (A.t_steps) {  // EpisodeWrapper + AutoResetWrapper semantics around obs / reward / done of the stepped state
@@ -1382,22 +1397,28 @@ template <int NL, int NC, class Args, class K> int launch_limb(K kern, const Lay
 
 }  // namespace limb
 
-// LGC: -1 = general sharing pattern (suffix g), 2 = flat 4-lane pattern (suffix f2), 86 = biped pattern (suffix b)
-#define ABR_DECLARE_LIMB_LAUNCHERS(NL, NC, TAG)                                                        \
-  int launch_limb_rollout_##NL##_##NC##_##TAG(const Layout&, const RolloutArgs&, cudaStream_t);        \
-  int launch_limb_env_##NL##_##NC##_##TAG(const Layout&, const EnvArgs&, cudaStream_t);
-#define ABR_DEFINE_LIMB_LAUNCHERS(NL, NC, LGC, CB, TAG)                                                   \
-  int launch_limb_rollout_##NL##_##NC##_##TAG(const Layout& L, const RolloutArgs& a, cudaStream_t st) { \
-    return limb::launch_limb<NL, NC>(limb::k_limb_rollout<NL, NC, LGC, CB>, L, a, a.nworld,                 \
-                                     3 * L.nx + L.nu + (3 * (13 + 2 * NL) + NL) * limb::kTPB, st);         \
-  }                                                                                                    \
-  int launch_limb_env_##NL##_##NC##_##TAG(const Layout& L, const EnvArgs& a, cudaStream_t st) {        \
-    return limb::launch_limb<NL, NC>(limb::k_limb_env<NL, NC, LGC, CB>, L, a, a.E, 0, st);                 \
+// LGC: -1 = general sharing pattern (suffix g), 2 = flat 4-lane pattern (suffix f2), 86 = biped pattern (suffix b).
+// STAG: sg = general (SPEC -1), s0 / s4 / s8 / s12 = the fast variants (see limb::Spec).
+#define ABR_DECLARE_LIMB_ROLLOUT(NL, NC, TAG, STAG) int launch_limb_rollout_##NL##_##NC##_##TAG##_##STAG(const Layout&, const RolloutArgs&, cudaStream_t);
+#define ABR_DECLARE_LIMB_ENV(NL, NC, TAG, STAG) int launch_limb_env_##NL##_##NC##_##TAG##_##STAG(const Layout&, const EnvArgs&, cudaStream_t);
+#define ABR_DEFINE_LIMB_ROLLOUT(NL, NC, LGC, CB, TAG, SPEC, STAG)                                                         \
+  int launch_limb_rollout_##NL##_##NC##_##TAG##_##STAG(const Layout& L, const RolloutArgs& a, cudaStream_t st) {           \
+    return limb::launch_limb<NL, NC>(limb::k_limb_rollout<NL, NC, LGC, CB, SPEC>, L, a, a.nworld,                          \
+                                     3 * L.nx + L.nu + (3 * (13 + 2 * NL) + NL) * limb::kTPB, st);                        \
   }
-ABR_DECLARE_LIMB_LAUNCHERS(3, 1, f2)
-ABR_DECLARE_LIMB_LAUNCHERS(3, 1, g)
-ABR_DECLARE_LIMB_LAUNCHERS(6, 4, g)
-ABR_DECLARE_LIMB_LAUNCHERS(6, 4, b)
+#define ABR_DEFINE_LIMB_ENV(NL, NC, LGC, CB, TAG, SPEC, STAG)                                                             \
+  int launch_limb_env_##NL##_##NC##_##TAG##_##STAG(const Layout& L, const EnvArgs& a, cudaStream_t st) {                   \
+    return limb::launch_limb<NL, NC>(limb::k_limb_env<NL, NC, LGC, CB, SPEC>, L, a, a.E, 0, st);                           \
+  }
+#define ABR_DECLARE_LIMB_FAMILY_FAST(NL, NC, TAG)                                                                         \
+  ABR_DECLARE_LIMB_ROLLOUT(NL, NC, TAG, sg) ABR_DECLARE_LIMB_ROLLOUT(NL, NC, TAG, s0) ABR_DECLARE_LIMB_ROLLOUT(NL, NC, TAG, s4) \
+  ABR_DECLARE_LIMB_ROLLOUT(NL, NC, TAG, s8) ABR_DECLARE_LIMB_ROLLOUT(NL, NC, TAG, s12)                                    \
+  ABR_DECLARE_LIMB_ENV(NL, NC, TAG, sg) ABR_DECLARE_LIMB_ENV(NL, NC, TAG, s0)
+#define ABR_DECLARE_LIMB_FAMILY_GENERAL(NL, NC, TAG) ABR_DECLARE_LIMB_ROLLOUT(NL, NC, TAG, sg) ABR_DECLARE_LIMB_ENV(NL, NC, TAG, sg)
+ABR_DECLARE_LIMB_FAMILY_FAST(3, 1, f2)
+ABR_DECLARE_LIMB_FAMILY_GENERAL(3, 1, g)
+ABR_DECLARE_LIMB_FAMILY_GENERAL(6, 4, g)
+ABR_DECLARE_LIMB_FAMILY_FAST(6, 4, b)
 
 }  // namespace abr
 #endif

@@ -267,13 +267,16 @@ template <int N, class SH> __device__ __forceinline__ void mul_m(const float (&M
 // mode's control path together cost 8 % at every batch size). SPEC < 0 keeps every decision at run time (any options);
 // SPEC >= 0 fixes them: bit 0 = eulerdamp enabled, bit 1 = more than one Newton iteration, bit 2 = trajectories /
 // controls are written out, bit 3 = sampler mode (controls generated from the guess + noise). The launcher picks the
-// variant from the model's options and the call's arguments; the built fast variants have bits 0 and 1 clear.
+// variant from the model's options and the call's arguments; the built fast variants have bits 0 and 1 clear and also
+// assume the rest of the common configuration: no other disable flag set and the default impedance power 2 on every row.
 template <int SPEC> struct Spec {
   static constexpr bool gen = SPEC < 0;
   __device__ __forceinline__ static bool edamp(int disableflags) { return gen ? !(disableflags & ABR_DSBL_EULERDAMP) : ((SPEC & 1) != 0); }
   __device__ __forceinline__ static bool multi(int iterations) { return gen ? iterations != 1 : ((SPEC & 2) != 0); }
   __device__ __forceinline__ static bool out(const void* p) { return gen ? p != nullptr : (((SPEC & 4) != 0) && p != nullptr); }
   __device__ __forceinline__ static bool sampler(int mode) { return gen ? mode == 1 : ((SPEC & 8) != 0); }
+  __device__ __forceinline__ static int flags(int disableflags) { return gen ? disableflags : (int)ABR_DSBL_EULERDAMP; }
+  static constexpr bool pow2 = SPEC >= 0;
 };
 
 // ------------------------------------------------------------------------------ lane state
@@ -301,14 +304,19 @@ template <int LGC> struct LaneCfg {
 // kbi: impedance, D and aref of one active row (constraint._kbi / _row in SURVEY App. A.7), split so that the four pyramid
 // rows of a contact (same penetration, same solref / solimp) evaluate the impedance once
 struct Kbi { float b, kip, g; };  // damping b, stiffness * impedance * pos, (1 - imp) / imp
-__device__ __forceinline__ Kbi kbi_imp(const float* prm /* smem, stride kStride */, float pos) {
+template <bool POW2> __device__ __forceinline__ Kbi kbi_imp(const float* prm /* smem, stride kStride */, float pos) {
   const float k = prm[0 * kStride], dmin = prm[2 * kStride], dmax = prm[3 * kStride];
-  const float iw = prm[4 * kStride], mid = prm[5 * kStride], power = prm[6 * kStride];
+  const float iw = prm[4 * kStride], mid = prm[5 * kStride];
   const float x = fabsf(pos) * iw;
   float ia, ib;
-  if (power == 2.f) { ia = x * x; const float t = 1.f - x; ib = t * t; }
-  else if (power == 1.f) { ia = x; ib = 1.f - x; }
-  else { ia = pow_cold(x, power); ib = pow_cold(1.f - x, power); }
+  if (POW2) {
+    ia = x * x; const float t = 1.f - x; ib = t * t;
+  } else {
+    const float power = prm[6 * kStride];
+    if (power == 2.f) { ia = x * x; const float t = 1.f - x; ib = t * t; }
+    else if (power == 1.f) { ia = x; ib = 1.f - x; }
+    else { ia = pow_cold(x, power); ib = pow_cold(1.f - x, power); }
+  }
   const float y = (x < mid) ? prm[8 * kStride] * ia : 1.f - prm[9 * kStride] * ib;
   float imp = dmin + y * (dmax - dmin);
   imp = fminf(fmaxf(imp, dmin), dmax);
@@ -322,8 +330,8 @@ __device__ __forceinline__ void kbi_row(const Kbi& q, float jvel, float invw, bo
   D = active ? rcp_fast(R) : 0.f;
   aref = active ? -q.b * jvel - q.kip : 0.f;
 }
-__device__ __forceinline__ void row_kbi(const float* prm, float pos, float jvel, float invw, bool active, float& D, float& aref) {
-  kbi_row(kbi_imp(prm, pos), jvel, invw, active, D, aref);
+template <bool POW2> __device__ __forceinline__ void row_kbi(const float* prm, float pos, float jvel, float invw, bool active, float& D, float& aref) {
+  kbi_row(kbi_imp<POW2>(prm, pos), jvel, invw, active, D, aref);
 }
 
 struct LSP { float alpha, cost, d0, d1; };
@@ -753,7 +761,7 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
     const bool active = (pos < 0.f) && (jflags[p] & kJLimited) && S.o(p);
     const float sg = (dmin < dmax) ? 1.f : -1.f;
     R.lsg[r] = active ? sg : 0.f;
-    row_kbi(&LTF(mp.jnt(p) + 14), pos, sg * s.v[d], LTF(mp.jnt(p) + 14 + 7), active, R.D[r], R.aref[r]);
+    row_kbi<Spec<SPEC>::pow2>(&LTF(mp.jnt(p) + 14), pos, sg * s.v[d], LTF(mp.jnt(p) + 14 + 7), active, R.D[r], R.aref[r]);
   }
   {
     float bva[NC > 0 ? NC : 1][3];
@@ -776,7 +784,7 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
       const float pos = cdist[c] - prm[13 * kStride];
       const bool act0 = (pos < 0.f) && (LTI(mp.icon(c)) >= 0);
       const bool pyr = LTI(mp.icon(c) + 1) == 3;
-      const Kbi kq = kbi_imp(prm, pos);
+      const Kbi kq = kbi_imp<Spec<SPEC>::pow2>(prm, pos);
 #pragma unroll
       for (int sub = 0; sub < 4; sub++) {
         const int r = NL + 4 * c + sub;
@@ -1074,7 +1082,7 @@ constexpr int kTPB = 32;      // default: one warp per CTA (32/G worlds); small 
 #define ABR_LIMB_MINB 1  // resident CTAs per SM the register allocation must allow (1 = up to 255 registers)
 #endif
 
-template <int NL, int NC, int LGC> __device__ __forceinline__ LaneCfg<LGC> make_cfg(const Layout& L, const float* T, int g) {
+template <int NL, int NC, int LGC, int SPEC = -1> __device__ __forceinline__ LaneCfg<LGC> make_cfg(const Layout& L, const float* T, int g) {
   constexpr Map mp{NL, NC};
   LaneCfg<LGC> C;
   C.T = T + g;
@@ -1082,7 +1090,7 @@ template <int NL, int NC, int LGC> __device__ __forceinline__ LaneCfg<LGC> make_
   C.dt = L.timestep; C.grav[0] = L.gravity[0]; C.grav[1] = L.gravity[1]; C.grav[2] = L.gravity[2];
   C.frs = 1.f; C.acs = 1.f;
   C.mass = L.l_mass; C.inv_mass = 1.f / L.l_mass; C.tol = L.tolerance; C.ls_tol = L.ls_tolerance; C.meaninertia = L.meaninertia;
-  C.iterations = L.iterations; C.ls_iterations = L.ls_iterations; C.disableflags = L.disableflags; C.nefc = L.nefc; C.nv = L.nv;
+  C.iterations = Spec<SPEC>::gen ? L.iterations : 1; C.ls_iterations = L.ls_iterations; C.disableflags = Spec<SPEC>::flags(L.disableflags); C.nefc = L.nefc; C.nv = L.nv;
   return C;
 }
 
@@ -1160,7 +1168,7 @@ __global__ void __launch_bounds__(kTPB, ABR_LIMB_MINB) k_limb_rollout(const __gr
   const int wraw = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> lg);
   const bool valid = wraw < A.nworld;
   const int w = valid ? wraw : A.nworld - 1;
-  const LaneCfg<LGC> C = make_cfg<NL, NC, LGC>(L, smem, g);
+  const LaneCfg<LGC> C = make_cfg<NL, NC, LGC, SPEC>(L, smem, g);
   int prob = w, sample = 0;
   if (Spec<SPEC>::sampler(A.mode)) {
     if (A.sample_ids) { prob = w; sample = A.sample_ids[w]; }
@@ -1288,7 +1296,7 @@ __global__ void __launch_bounds__(kTPB, ABR_LIMB_MINB) k_limb_env(const __grid_c
   const int wraw = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> lg);
   const bool valid = wraw < A.E;
   const int w = valid ? wraw : A.E - 1;
-  LaneCfg<LGC> C = make_cfg<NL, NC, LGC>(L, smem, g);
+  LaneCfg<LGC> C = make_cfg<NL, NC, LGC, SPEC>(L, smem, g);
   if (A.dr) { C.frs = A.dr[2 * (size_t)w]; C.acs = A.dr[2 * (size_t)w + 1]; }
   const bool reset = A.reset_mask && A.reset_mask[w];
   const bool was_done = A.t_steps && A.t_done[w];  // AutoResetWrapper zeroes the counter of an env that finished last step

@@ -621,7 +621,8 @@ static int build_blob(const HostModel& m, bool alias, Layout& L, std::vector<flo
       }
       while (P.f.size() % 4) P.f.push_back(0.f);
       L.limb_ok = 1; L.lNL = NLi; L.lNC = NCi; L.l_mx = mxbits; L.l_mass = (float)mass;
-      L.l_pow2 = 1;
+      L.l_pow2 = 1; L.l_hinge = 1;
+      for (int j = 0; j < nj; j++) if (m.jnt_type[j] == ABR_JNT_SLIDE) L.l_hinge = 0;
       for (size_t i = 0; i < lim_prm.size(); i += kRowPrm) if (lim_prm[i + 6] != 2.f) L.l_pow2 = 0;
       for (size_t i = 0; i < con_prm.size(); i += kConPrm) if (con_prm[i + 6] != 2.f) L.l_pow2 = 0;
       L.lg2G = 0;
@@ -784,10 +785,10 @@ static int launch_rollout(const AbrModel* m, const Layout& L, const RolloutArgs&
   if (a.nworld <= 0) return ABR_OK;
   if (use_limb(m, L, a.cost.enabled && !a.cost.diag, false)) {
     const bool spec = getenv("ABR_LIMB_GENERAL") == nullptr;  // compile-time sharing patterns: 2 = flat 4 lanes, 86 = biped
-    // fast variants (limb::Spec): the common options (only eulerdamp disabled, one Newton iteration, default impedance power), specialised on
+    // fast variants (limb::Spec): the common options (only eulerdamp disabled, one Newton iteration, default impedance power, hinge joints), specialised on
     // the mode and on whether anything is written out;
     // every other combination of options runs the general variant of the same kernel (ABR_LIMB_NOSPEC forces it)
-    const bool fast = L.disableflags == ABR_DSBL_EULERDAMP && L.iterations == 1 && L.l_pow2 && getenv("ABR_LIMB_NOSPEC") == nullptr;
+    const bool fast = L.disableflags == ABR_DSBL_EULERDAMP && L.iterations == 1 && L.l_pow2 && L.l_hinge && getenv("ABR_LIMB_NOSPEC") == nullptr;
     const int sv = !fast ? -1 : ((a.xs_out || a.us_out) ? 4 : 0) | (a.mode == 1 ? 8 : 0);
 #define ABR_PICK_ROLLOUT(NL, NC, TAG)                                                                      \
   (sv == 0 ? launch_limb_rollout_##NL##_##NC##_##TAG##_s0(L, a, st) : sv == 4 ? launch_limb_rollout_##NL##_##NC##_##TAG##_s4(L, a, st) \
@@ -815,7 +816,7 @@ static int launch_env(const AbrModel* m, const Layout& L, const EnvArgs& a_in, c
   }
   if (use_limb(m, L, false, a.dbg != nullptr)) {
     const bool spec = getenv("ABR_LIMB_GENERAL") == nullptr;
-    const bool fast = L.disableflags == ABR_DSBL_EULERDAMP && L.iterations == 1 && L.l_pow2 && getenv("ABR_LIMB_NOSPEC") == nullptr;
+    const bool fast = L.disableflags == ABR_DSBL_EULERDAMP && L.iterations == 1 && L.l_pow2 && L.l_hinge && getenv("ABR_LIMB_NOSPEC") == nullptr;
     if (L.lNL == 3 && L.lNC == 1)
       return launch_result(spec && L.l_mx == 2 ? (fast ? launch_limb_env_3_1_f2_s0(L, a, st) : launch_limb_env_3_1_f2_sg(L, a, st)) : launch_limb_env_3_1_g_sg(L, a, st));
     if (L.lNL == 6 && L.lNC == 4)

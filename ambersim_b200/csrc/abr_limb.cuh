@@ -268,7 +268,7 @@ template <int N, class SH> __device__ __forceinline__ void mul_m(const float (&M
 // SPEC >= 0 fixes them: bit 0 = eulerdamp enabled, bit 1 = more than one Newton iteration, bit 2 = trajectories /
 // controls are written out, bit 3 = sampler mode (controls generated from the guess + noise). The launcher picks the
 // variant from the model's options and the call's arguments; the built fast variants have bits 0 and 1 clear and also
-// assume the rest of the common configuration: no other disable flag set and the default impedance power 2 on every row.
+// assume the rest of the common configuration: no other disable flag set, the default impedance power 2 on every row, hinge joints only.
 template <int SPEC> struct Spec {
   static constexpr bool gen = SPEC < 0;
   __device__ __forceinline__ static bool edamp(int disableflags) { return gen ? !(disableflags & ABR_DSBL_EULERDAMP) : ((SPEC & 1) != 0); }
@@ -277,6 +277,7 @@ template <int SPEC> struct Spec {
   __device__ __forceinline__ static bool sampler(int mode) { return gen ? mode == 1 : ((SPEC & 8) != 0); }
   __device__ __forceinline__ static int flags(int disableflags) { return gen ? disableflags : (int)ABR_DSBL_EULERDAMP; }
   static constexpr bool pow2 = SPEC >= 0;
+  static constexpr bool hinges = SPEC >= 0;  // every chain joint is a hinge (padding positions have a zero axis either way)
 };
 
 // ------------------------------------------------------------------------------ lane state
@@ -482,13 +483,13 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
     const float dq = s.qc[p - 1] - LTF(mp.jnt(p) + 6);
     // hinge: rotate about the joint axis and re-anchor; slide: translate along the axis
     float sn, cs, qloc[4], qn[4], Rn[9];
-    sincos_bf(((type == kJHinge) ? dq : 0.f) * 0.5f, sn, cs);
+    sincos_bf(((Spec<SPEC>::hinges || type == kJHinge) ? dq : 0.f) * 0.5f, sn, cs);
 #pragma unroll
     for (int i = 0; i < 4; i++) qloc[i] = fmaf(sn, bj[i], cs * bq[i]);
     q_mul(xquat[p - 1], qloc, qn);
     q_to_mat(qn, Rn);
     m_rot(Rn, jp, r);
-    const float sl = (type == kJSlide) ? dq : 0.f;
+    const float sl = (!Spec<SPEC>::hinges && type == kJSlide) ? dq : 0.f;
 #pragma unroll
     for (int i = 0; i < 3; i++) pos[i] = anchor[i] - r[i] + axis[i] * sl;
 #pragma unroll
@@ -548,7 +549,7 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
 #pragma unroll
   for (int p = 1; p < NP; p++) {
     const int d = 5 + p;
-    const bool hinge = (jflags[p] & kJTypeMask) == kJHinge;
+    const bool hinge = Spec<SPEC>::hinges || (jflags[p] & kJTypeMask) == kJHinge;
     const float off[3] = {com[0] - xanc[p][0], com[1] - xanc[p][1], com[2] - xanc[p][2]};
     float cr[3];
     v_cross(xax[p], off, cr);

@@ -758,3 +758,36 @@ def test_solve_is_cuda_graph_capturable(load_model):
         xs_r, us_r = xs_g.clone(), us_g.clone()
         xs_d, us_d = ps.optimize(prm)
         assert torch.equal(xs_r, xs_d) and torch.equal(us_r, us_d), f"trial {trial}"
+
+
+@pytest.mark.parametrize("name", ["barkour", "biped"])
+def test_limb_fast_variants_match_the_general_variant(load_model, name, monkeypatch):
+    """The compile-time variants of the limb kernels (no eulerdamp / multi-iteration / output / other-mode code in the loop) against the
+    general variant of the same kernel (ABR_LIMB_NOSPEC): rollouts with and without trajectories, sampler costs, env steps."""
+    mj, m, o = model_with(load_model, name)
+    rng = np.random.default_rng(31)
+    key = MODEL_KEY[name]
+    W, N = 16, 10
+    nx = mj.nq + mj.nv
+    x0 = np.tile(np.concatenate([mj.key_qpos(key), np.zeros(mj.nv)]), (W, 1))
+    x0[:, 7:mj.nq] += rng.uniform(-0.05, 0.05, (W, mj.nq - 7))
+    us = np.clip(mj.key_ctrl(key) + 0.1 * rng.normal(size=(W, N, mj.nu)), mj.actuator_ctrlrange[:, 0], mj.actuator_ctrlrange[:, 1])
+    cf = StaticGoalQuadraticCost(np.eye(nx), 10 * np.eye(nx), 0.01 * np.eye(mj.nu), x0[0])
+
+    def run():
+        mm = mjx.device_put(mj).replace(opt=m.opt)
+        xs = shoot(mm, t32(x0), t32(us)).cpu().numpy()
+        costs = shoot_cost(mm, t32(x0), t32(us), cf).cpu().numpy()
+        ps = VanillaPredictiveSampler(model=mm, cost_function=cf, nsamples=64, stdev=0.1)
+        _, _, info = ps.optimize(VanillaPredictiveSamplerParams(key=2, x0=t32(x0[0]), us_guess=t32(us[0])), return_info=True)
+        d = mjx.Data(qpos=t32(x0[:, :mj.nq]), qvel=t32(x0[:, mj.nq:]), ctrl=t32(us[:, 0]), qacc=torch.zeros(W, mj.nv, device=DEV),
+                     qacc_warmstart=torch.zeros(W, mj.nv, device=DEV), time=torch.zeros(W, device=DEV))
+        return xs, costs, info["costs"].cpu().numpy(), mjx.step(mm, d).qvel.cpu().numpy()
+
+    fast = run()
+    monkeypatch.setenv("ABR_LIMB_NOSPEC", "1")
+    general = run()
+    assert np.abs(fast[0] - general[0]).max() < 2e-3 and np.allclose(fast[1], general[1], rtol=2e-3)
+    assert np.allclose(fast[2], general[2], rtol=2e-3) and np.abs(fast[3] - general[3]).max() < 1e-3
+    ref = o.rollout(x0, us)
+    assert np.abs(general[0] - ref).max() < 5e-3 and np.abs(fast[0] - ref).max() < 5e-3

@@ -1,6 +1,6 @@
 """Random floating-base limb models (MJCF text) for the parity tests: a trunk on a free joint with 2-8 leaf paths,
 chains of random length, optional forks (bodies shared by several paths), hinge / slide joints with random axes,
-anchors and body-frame rotations, random inertias, damping, armature, springs, limits, position / motor actuators
+anchors and body-frame rotations, random inertias with tilted principal axes, damping, armature, springs, limits, position / motor actuators
 with control and force ranges (some joints unactuated), sphere feet with condim 1 or 3 and random friction on
 random bodies of a path, and a tilted floor. Everything a model of the limb-kernel class can contain
 (abr_limb.cuh eligibility); the generic kernels and the oracle take the same file."""
@@ -13,9 +13,11 @@ def _f(a):
     return " ".join(f"{x:.5g}" for x in np.atleast_1d(a))
 
 
-def random_limb_model(seed: int, max_chain: int = 3, max_con: int = 1, max_leaves: int = 4, iterations: int = 1, forks: bool = True):
+def random_limb_model(seed: int, max_chain: int = 3, max_con: int = 1, max_leaves: int = 4, iterations: int = 1, forks: bool = True, quad: bool = False):
     """Returns (xml, home_qpos, home_ctrl). Chains have <= max_chain joints between trunk and leaf and at most
-    max_con foot spheres per root-to-leaf path (the capacity of the compiled limb kernels: (3,1) and (6,4))."""
+    max_con foot spheres per root-to-leaf path (the capacity of the compiled limb kernels: (3,1) and (6,4)).
+    quad: the flat four-limb class with the common options (hinges only, no forks, eulerdamp disabled), i.e. a model the
+    compile-time fast variants of the limb kernels serve."""
     rng = np.random.default_rng(seed)
     acts, qpos, ctrl = [], [], []
     counter, leaves = [0], [0]
@@ -25,7 +27,7 @@ def random_limb_model(seed: int, max_chain: int = 3, max_con: int = 1, max_leave
         k = counter[0]
         counter[0] += 1
         name = f"{prefix}{k}"
-        slide = rng.random() < 0.2
+        slide = (not quad) and rng.random() < 0.2
         axis = rng.normal(size=3)
         axis /= np.linalg.norm(axis)
         limited = rng.random() < 0.7
@@ -43,7 +45,8 @@ def random_limb_model(seed: int, max_chain: int = 3, max_con: int = 1, max_leave
         inertia = mass * rng.uniform(0.002, 0.012, 3)
         length = float(rng.uniform(0.08, 0.16))
         xml = [f'<body name="{name}" pos="{_f(pos)}" euler="{_f(rng.uniform(-0.3, 0.3, 3))}">',
-               f'<inertial pos="{_f(rng.uniform(-0.02, 0.02, 3))}" mass="{mass:.4g}" diaginertia="{_f(inertia)}"/>',
+               f'<inertial pos="{_f(rng.uniform(-0.02, 0.02, 3))}" mass="{mass:.4g}" diaginertia="{_f(inertia)}"'
+               + (f' euler="{_f(rng.uniform(-0.8, 0.8, 3))}"' if rng.random() < 0.5 else "") + "/>",  # tilted principal axes on half of the bodies
                f"<joint {jattr}/>"]
         qpos.append(q0)
         r = rng.random()
@@ -78,19 +81,19 @@ def random_limb_model(seed: int, max_chain: int = 3, max_con: int = 1, max_leave
         return "\n".join(xml)
 
     limbs = []
-    nlimb = int(rng.integers(2, min(4, max_leaves) + 1))
+    nlimb = 4 if quad else int(rng.integers(2, min(4, max_leaves) + 1))
     leaves[0] = nlimb
     for limb in range(nlimb):
         n = int(rng.integers(1, max_chain + 1))
         ang = 2 * np.pi * limb / nlimb + rng.uniform(-0.2, 0.2)
-        limbs.append(body(np.array([0.18 * np.cos(ang), 0.18 * np.sin(ang), -0.03]), n - 1, max_con, f"l{limb}_", forks))
+        limbs.append(body(np.array([0.18 * np.cos(ang), 0.18 * np.sin(ang), -0.03]), n - 1, max_con, f"l{limb}_", forks and not quad))
     height = 0.45
     trunk_mass = float(rng.uniform(2.0, 5.0))
     tilt = rng.uniform(-0.05, 0.05, 2)
     belly = '<geom name="belly" class="foot" size="0.05" pos="0 0 -0.1" condim="1"/>' if rng.random() < 0.3 else ""
     xml = f"""<mujoco model="random_limb_{seed}">
   <compiler angle="radian" autolimits="true"/>
-  <option timestep="0.003" iterations="{iterations}" ls_iterations="6" integrator="Euler" solver="Newton"><flag eulerdamp="{'enable' if rng.random() < 0.5 else 'disable'}"/></option>
+  <option timestep="0.003" iterations="{iterations}" ls_iterations="6" integrator="Euler" solver="Newton"><flag eulerdamp="{'enable' if (not quad and rng.random() < 0.5) else 'disable'}"/></option>
   <default>
     <geom contype="0" conaffinity="0"/>
     <default class="foot"><geom type="sphere" contype="1" conaffinity="0"/></default>
@@ -98,7 +101,7 @@ def random_limb_model(seed: int, max_chain: int = 3, max_con: int = 1, max_leave
   <worldbody>
     <geom name="floor" type="plane" size="0 0 0.05" euler="{_f(tilt)} 0" contype="0" conaffinity="1" condim="3"/>
     <body name="base" pos="0 0 {height}">
-      <inertial pos="{_f(rng.uniform(-0.02, 0.02, 3))}" mass="{trunk_mass:.4g}" diaginertia="{_f(trunk_mass * rng.uniform(0.01, 0.03, 3))}"/>
+      <inertial pos="{_f(rng.uniform(-0.02, 0.02, 3))}" mass="{trunk_mass:.4g}" diaginertia="{_f(trunk_mass * rng.uniform(0.01, 0.03, 3))}" euler="{_f(rng.uniform(-0.5, 0.5, 3))}"/>
       <freejoint name="base"/>
       {belly}
       {chr(10).join(limbs)}

@@ -9,10 +9,12 @@ from ambersim_b200.utils.io_utils import load_mj_model_from_file
 from oracle.oracle import Oracle
 from tests._randmodel import random_limb_model
 
-CONFIGS = {"quad": (3, 1, 4), "long": (6, 4, 4), "wide": (3, 1, 8)}
+CONFIGS = {"quad": (3, 1, 4), "long": (6, 4, 4), "wide": (3, 1, 8), "fastquad": (3, 1, 4)}
 
 
 def _load(tmp_path, seed, cfg, **kw):
+    if cfg == "fastquad":  # flat four-limb class with the common options: served by the compile-time fast variants
+        kw = {**kw, "quad": True, "iterations": 1}
     xml, q, c = random_limb_model(seed, *CONFIGS[cfg], **kw)
     f = tmp_path / f"rand_{cfg}_{seed}.xml"
     f.write_text(xml)
@@ -48,6 +50,8 @@ def test_random_model_plans_cover_every_body_once(tmp_path, cfg):
             for b, lanes in groups.items():
                 assert {p["level"][g][k] for g in lanes} == {int(np.ceil(np.log2(len(lanes))))} or len(lanes) == 1
     assert eligible >= 6
+    if cfg == "fastquad":
+        assert eligible == 12 and all(mjx.limb_plan(_load(tmp_path, s, cfg)[0])["pattern"] == 2 for s in range(4))
 
 
 @pytest.mark.parametrize("cfg", list(CONFIGS))

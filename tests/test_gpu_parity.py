@@ -791,3 +791,35 @@ def test_limb_fast_variants_match_the_general_variant(load_model, name, monkeypa
     assert np.allclose(fast[2], general[2], rtol=2e-3) and np.abs(fast[3] - general[3]).max() < 1e-3
     ref = o.rollout(x0, us)
     assert np.abs(general[0] - ref).max() < 5e-3 and np.abs(fast[0] - ref).max() < 5e-3
+
+
+def test_peer_exchange_single_rank_and_argument_checks():
+    """abr_xchg_* with one rank (the degenerate collective: the record goes through the rank's own exchange buffer, flags and
+    selection included) returns the local winners unchanged, call after call (epoch parity alternates); capacity and size errors
+    are refused. The multi-GPU equality is checked by tools/mgpu_check.py under torchrun (profiles/r1_mgpu_check_*)."""
+    import ctypes as C
+
+    L = _lib.lib()
+    B, nxs, nus = 3, 33 * 37, 32 * 12
+    x, handle = C.c_void_p(), C.create_string_buffer(64)
+    _lib.check(L.abr_xchg_create(0, 1, 0, B * (2 + nxs + nus), C.byref(x), handle))
+    _lib.check(L.abr_xchg_connect(x, handle.raw))
+    p = lambda t: C.c_void_p(t.data_ptr())
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    g = torch.Generator(device=DEV).manual_seed(0)
+    for call in range(5):
+        cost = torch.rand(B, generator=g, device=DEV)
+        cost[1] = float("nan")
+        idx = torch.randint(0, 10000, (B,), generator=g, device=DEV, dtype=torch.int32)
+        xs, us = torch.randn((B, nxs), generator=g, device=DEV), torch.randn((B, nus), generator=g, device=DEV)
+        xs_o, us_o, idx_o, cost_o = torch.empty_like(xs), torch.empty_like(us), torch.empty_like(idx), torch.empty_like(cost)
+        _lib.check(L.abr_xchg_merge_best_dev(x, p(cost), p(idx), p(xs), p(us), B, nxs, nus, p(xs_o), p(us_o), p(idx_o), p(cost_o), stream))
+        torch.cuda.synchronize()
+        assert torch.equal(xs_o, xs) and torch.equal(us_o, us) and torch.equal(idx_o, idx)
+        assert torch.equal(torch.isnan(cost_o), torch.isnan(cost)) and torch.equal(cost_o[[0, 2]], cost[[0, 2]])
+    flag = C.c_int(-1)
+    _lib.check(L.abr_xchg_timed_out(x, C.byref(flag)))
+    assert flag.value == 0
+    assert L.abr_xchg_merge_best_dev(x, p(cost), p(idx), p(xs), p(us), B + 1, nxs, nus, p(xs_o), p(us_o), p(idx_o), p(cost_o), stream) == _lib.ABR_ECAPACITY
+    assert L.abr_xchg_merge_best_dev(x, p(cost), p(idx), p(xs), p(us), 0, nxs, nus, p(xs_o), p(us_o), p(idx_o), p(cost_o), stream) == _lib.ABR_EINVAL
+    _lib.check(L.abr_xchg_destroy(x))

@@ -785,14 +785,17 @@ static int launch_rollout(const AbrModel* m, const Layout& L, const RolloutArgs&
   if (a.nworld <= 0) return ABR_OK;
   if (use_limb(m, L, a.cost.enabled && !a.cost.diag, false)) {
     const bool spec = getenv("ABR_LIMB_GENERAL") == nullptr;  // compile-time sharing patterns: 2 = flat 4 lanes, 86 = biped
-    // fast variants (limb::Spec): the common options (only eulerdamp disabled, one Newton iteration, default impedance power, hinge joints), specialised on
+    // fast variants (limb::Spec): the common options (no disable flag other than eulerdamp, one Newton iteration, default impedance power, hinge joints), specialised on
     // the mode and on whether anything is written out;
     // every other combination of options runs the general variant of the same kernel (ABR_LIMB_NOSPEC forces it)
-    const bool fast = L.disableflags == ABR_DSBL_EULERDAMP && L.iterations == 1 && L.l_pow2 && L.l_hinge && getenv("ABR_LIMB_NOSPEC") == nullptr;
-    const int sv = !fast ? -1 : ((a.xs_out || a.us_out) ? 4 : 0) | (a.mode == 1 ? 8 : 0);
+    const bool fast = (L.disableflags == ABR_DSBL_EULERDAMP || L.disableflags == 0) && L.iterations == 1 && L.l_pow2 && L.l_hinge &&
+                      getenv("ABR_LIMB_NOSPEC") == nullptr;
+    const int sv = !fast ? -1 : (L.disableflags == 0 ? 1 : 0) | ((a.xs_out || a.us_out) ? 4 : 0) | (a.mode == 1 ? 8 : 0);
 #define ABR_PICK_ROLLOUT(NL, NC, TAG)                                                                      \
   (sv == 0 ? launch_limb_rollout_##NL##_##NC##_##TAG##_s0(L, a, st) : sv == 4 ? launch_limb_rollout_##NL##_##NC##_##TAG##_s4(L, a, st) \
    : sv == 8 ? launch_limb_rollout_##NL##_##NC##_##TAG##_s8(L, a, st) : sv == 12 ? launch_limb_rollout_##NL##_##NC##_##TAG##_s12(L, a, st) \
+   : sv == 1 ? launch_limb_rollout_##NL##_##NC##_##TAG##_s1(L, a, st) : sv == 5 ? launch_limb_rollout_##NL##_##NC##_##TAG##_s5(L, a, st) \
+   : sv == 9 ? launch_limb_rollout_##NL##_##NC##_##TAG##_s9(L, a, st) : sv == 13 ? launch_limb_rollout_##NL##_##NC##_##TAG##_s13(L, a, st) \
    : launch_limb_rollout_##NL##_##NC##_##TAG##_sg(L, a, st))
     if (L.lNL == 3 && L.lNC == 1) return launch_result(spec && L.l_mx == 2 ? ABR_PICK_ROLLOUT(3, 1, f2) : launch_limb_rollout_3_1_g_sg(L, a, st));
     if (L.lNL == 6 && L.lNC == 4) return launch_result(spec && L.l_mx == 86 && L.l_cb ? ABR_PICK_ROLLOUT(6, 4, b) : launch_limb_rollout_6_4_g_sg(L, a, st));
@@ -816,11 +819,15 @@ static int launch_env(const AbrModel* m, const Layout& L, const EnvArgs& a_in, c
   }
   if (use_limb(m, L, false, a.dbg != nullptr)) {
     const bool spec = getenv("ABR_LIMB_GENERAL") == nullptr;
-    const bool fast = L.disableflags == ABR_DSBL_EULERDAMP && L.iterations == 1 && L.l_pow2 && L.l_hinge && getenv("ABR_LIMB_NOSPEC") == nullptr;
+    const bool fast = (L.disableflags == ABR_DSBL_EULERDAMP || L.disableflags == 0) && L.iterations == 1 && L.l_pow2 && L.l_hinge &&
+                      getenv("ABR_LIMB_NOSPEC") == nullptr;
+    const bool ed = L.disableflags == 0;
     if (L.lNL == 3 && L.lNC == 1)
-      return launch_result(spec && L.l_mx == 2 ? (fast ? launch_limb_env_3_1_f2_s0(L, a, st) : launch_limb_env_3_1_f2_sg(L, a, st)) : launch_limb_env_3_1_g_sg(L, a, st));
+      return launch_result(spec && L.l_mx == 2 ? (fast ? (ed ? launch_limb_env_3_1_f2_s1(L, a, st) : launch_limb_env_3_1_f2_s0(L, a, st)) : launch_limb_env_3_1_f2_sg(L, a, st))
+                                               : launch_limb_env_3_1_g_sg(L, a, st));
     if (L.lNL == 6 && L.lNC == 4)
-      return launch_result(spec && L.l_mx == 86 && L.l_cb ? (fast ? launch_limb_env_6_4_b_s0(L, a, st) : launch_limb_env_6_4_b_sg(L, a, st)) : launch_limb_env_6_4_g_sg(L, a, st));
+      return launch_result(spec && L.l_mx == 86 && L.l_cb ? (fast ? (ed ? launch_limb_env_6_4_b_s1(L, a, st) : launch_limb_env_6_4_b_s0(L, a, st)) : launch_limb_env_6_4_b_sg(L, a, st))
+                                                         : launch_limb_env_6_4_g_sg(L, a, st));
     return fail(ABR_ECAPACITY, "no compiled limb kernel for this model");
   }
   LaunchCfg cfg{m->max_smem};

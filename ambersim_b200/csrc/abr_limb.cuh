@@ -267,15 +267,15 @@ template <int N, class SH> __device__ __forceinline__ void mul_m(const float (&M
 // mode's control path together cost 8 % at every batch size). SPEC < 0 keeps every decision at run time (any options);
 // SPEC >= 0 fixes them: bit 0 = eulerdamp enabled, bit 1 = more than one Newton iteration, bit 2 = trajectories /
 // controls are written out, bit 3 = sampler mode (controls generated from the guess + noise). The launcher picks the
-// variant from the model's options and the call's arguments; the built fast variants have bits 0 and 1 clear and also
-// assume the rest of the common configuration: no other disable flag set, the default impedance power 2 on every row, hinge joints only.
+// variant from the model's options and the call's arguments; the built fast variants have bit 1 clear (both values of bit 0) and also
+// assume the rest of the common configuration: no disable flag set other than eulerdamp, the default impedance power 2 on every row, hinge joints only.
 template <int SPEC> struct Spec {
   static constexpr bool gen = SPEC < 0;
   __device__ __forceinline__ static bool edamp(int disableflags) { return gen ? !(disableflags & ABR_DSBL_EULERDAMP) : ((SPEC & 1) != 0); }
   __device__ __forceinline__ static bool multi(int iterations) { return gen ? iterations != 1 : ((SPEC & 2) != 0); }
   __device__ __forceinline__ static bool out(const void* p) { return gen ? p != nullptr : (((SPEC & 4) != 0) && p != nullptr); }
   __device__ __forceinline__ static bool sampler(int mode) { return gen ? mode == 1 : ((SPEC & 8) != 0); }
-  __device__ __forceinline__ static int flags(int disableflags) { return gen ? disableflags : (int)ABR_DSBL_EULERDAMP; }
+  __device__ __forceinline__ static int flags(int disableflags) { return gen ? disableflags : ((SPEC & 1) ? 0 : (int)ABR_DSBL_EULERDAMP); }
   static constexpr bool pow2 = SPEC >= 0;
   static constexpr bool hinges = SPEC >= 0;  // every chain joint is a hinge (padding positions have a zero axis either way)
 };
@@ -1422,7 +1422,9 @@ template <int NL, int NC, class Args, class K> int launch_limb(K kern, const Lay
 #define ABR_DECLARE_LIMB_FAMILY_FAST(NL, NC, TAG)                                                                         \
   ABR_DECLARE_LIMB_ROLLOUT(NL, NC, TAG, sg) ABR_DECLARE_LIMB_ROLLOUT(NL, NC, TAG, s0) ABR_DECLARE_LIMB_ROLLOUT(NL, NC, TAG, s4) \
   ABR_DECLARE_LIMB_ROLLOUT(NL, NC, TAG, s8) ABR_DECLARE_LIMB_ROLLOUT(NL, NC, TAG, s12)                                    \
-  ABR_DECLARE_LIMB_ENV(NL, NC, TAG, sg) ABR_DECLARE_LIMB_ENV(NL, NC, TAG, s0)
+  ABR_DECLARE_LIMB_ROLLOUT(NL, NC, TAG, s1) ABR_DECLARE_LIMB_ROLLOUT(NL, NC, TAG, s5)                                     \
+  ABR_DECLARE_LIMB_ROLLOUT(NL, NC, TAG, s9) ABR_DECLARE_LIMB_ROLLOUT(NL, NC, TAG, s13)                                    \
+  ABR_DECLARE_LIMB_ENV(NL, NC, TAG, sg) ABR_DECLARE_LIMB_ENV(NL, NC, TAG, s0) ABR_DECLARE_LIMB_ENV(NL, NC, TAG, s1)
 #define ABR_DECLARE_LIMB_FAMILY_GENERAL(NL, NC, TAG) ABR_DECLARE_LIMB_ROLLOUT(NL, NC, TAG, sg) ABR_DECLARE_LIMB_ENV(NL, NC, TAG, sg)
 ABR_DECLARE_LIMB_FAMILY_FAST(3, 1, f2)
 ABR_DECLARE_LIMB_FAMILY_GENERAL(3, 1, g)

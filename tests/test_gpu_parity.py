@@ -760,11 +760,13 @@ def test_solve_is_cuda_graph_capturable(load_model):
         assert torch.equal(xs_r, xs_d) and torch.equal(us_r, us_d), f"trial {trial}"
 
 
+@pytest.mark.parametrize("eulerdamp", [False, True])
 @pytest.mark.parametrize("name", ["barkour", "biped"])
-def test_limb_fast_variants_match_the_general_variant(load_model, name, monkeypatch):
+def test_limb_fast_variants_match_the_general_variant(load_model, name, eulerdamp, monkeypatch):
     """The compile-time variants of the limb kernels (no eulerdamp / multi-iteration / output / other-mode code in the loop) against the
-    general variant of the same kernel (ABR_LIMB_NOSPEC): rollouts with and without trajectories, sampler costs, env steps."""
-    mj, m, o = model_with(load_model, name)
+    general variant of the same kernel (ABR_LIMB_NOSPEC): rollouts with and without trajectories, sampler costs, env steps; with the
+    models' own options (eulerdamp disabled) and with MuJoCo's default (implicit joint damping in the Euler step)."""
+    mj, m, o = model_with(load_model, name, disableflags=0 if eulerdamp else 16384)
     rng = np.random.default_rng(31)
     key = MODEL_KEY[name]
     W, N = 16, 10

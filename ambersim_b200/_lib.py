@@ -58,6 +58,7 @@ def lib():
     L.abr_model_info.argtypes = [vp, ip, ip, ip, ip, ip]
     L.abr_limb_plan_host.argtypes = [C.POINTER(S["AbrModelHost"]), ip, ip, C.c_int, ip, ip]
     L.abr_model_set_lanes.argtypes = [vp, C.c_int]
+    L.abr_model_describe.argtypes = [vp, C.c_char_p, C.c_int]
     L.abr_model_reserve.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
     L.abr_cost_create.argtypes = [C.POINTER(S["AbrQuadCostHost"]), C.c_int, C.POINTER(vp)]
     L.abr_cost_destroy.argtypes = [vp]

@@ -936,6 +936,26 @@ int abr_model_info(const AbrModel* m, int* ncon, int* ne, int* nl, int* nefc, in
   return ABR_OK;
 }
 
+int abr_model_describe(const AbrModel* m, char* buf, int cap) {
+  if (!m || !buf || cap <= 0) return fail(ABR_EINVAL, "abr_model_describe: bad argument");
+  const Layout& L = m->lay;
+  char tmp[256];
+  if (use_limb(m, L, false, false)) {
+    const bool spec = getenv("ABR_LIMB_GENERAL") == nullptr;
+    const bool flat = L.lNL == 3 && L.lNC == 1 && spec && L.l_mx == 2, bip = L.lNL == 6 && L.lNC == 4 && spec && L.l_mx == 86 && L.l_cb;
+    const bool fast = (flat || bip) && (L.disableflags == ABR_DSBL_EULERDAMP || L.disableflags == 0) && L.iterations == 1 && L.l_pow2 && L.l_hinge &&
+                      getenv("ABR_LIMB_NOSPEC") == nullptr;
+    snprintf(tmp, sizeof(tmp), "limb kernels <NL=%d, NC=%d, %s>, %d lanes per world, %s variant", L.lNL, L.lNC,
+             flat ? "flat 4-lane pattern" : (bip ? "biped pattern, contact-body form" : "sharing pattern from the table"), 1 << L.lg2G,
+             fast ? (L.disableflags == 0 ? "fast (eulerdamp on)" : "fast (eulerdamp off)") : "general");
+  } else {
+    snprintf(tmp, sizeof(tmp), "generic kernels, %s lanes per world%s", m->lanes > 1 ? std::to_string(m->lanes).c_str() : "8 / 16 / 32 (by batch size)",
+             L.limb_ok ? " (limb kernels available: abr_model_set_lanes(m, 0 or 1))" : "");
+  }
+  snprintf(buf, (size_t)cap, "%s", tmp);
+  return ABR_OK;
+}
+
 int abr_model_set_lanes(AbrModel* m, int lanes) {
   if (!m) return fail(ABR_EINVAL, "abr_model_set_lanes: null model");
   if (lanes != 0 && lanes != 1 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32) return fail(ABR_EINVAL, "lanes must be 0, 1, 4, 8, 16 or 32");

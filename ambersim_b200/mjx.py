@@ -133,6 +133,14 @@ class Model:
             _lib.check(_lib.lib().abr_model_set_lanes(h.ptr, lanes))
         return self
 
+    def describe(self, device: Optional[int] = None) -> str:
+        """Which kernel family / variant serves this model with its current options (engine extension)."""
+        import ctypes
+
+        buf = ctypes.create_string_buffer(256)
+        _lib.check(_lib.lib().abr_model_describe(self.handle(device).ptr, buf, 256))
+        return buf.value.decode()
+
     def handle(self, device: Optional[int] = None) -> _Handle:
         if device is None:
             device = torch.cuda.current_device() if torch.cuda.is_available() else 0

@@ -207,6 +207,9 @@ int abr_model_set_opt(AbrModel* m, const AbrOpt* opt);
 int abr_model_get_opt(const AbrModel* m, AbrOpt* opt);
 /* static sizes derived at create: ncon, ne, nl, nefc, tree depth, lanes per world chosen */
 int abr_model_info(const AbrModel* m, int* ncon, int* ne, int* nl, int* nefc, int* depth);
+/* one line of text: which kernel family and variant serves this model with its current options (e.g.
+ * "limb kernels <NL=3, NC=1, flat 4-lane pattern>, 4 lanes per world, fast (eulerdamp off) variant") */
+int abr_model_describe(const AbrModel* m, char* buf, int cap);
 /* kernel family: 0 = auto (limb kernels, one lane per root-to-leaf path, when the model is eligible:
  * floating base, one hinge/slide joint per other body, plane-sphere contacts, Newton + Euler, no
  * equalities; otherwise the generic kernels), 1 = limb kernels or ABR_EUNSUPPORTED,

@@ -66,6 +66,7 @@ def test_argument_validation_needs_no_device():
                                    None) == _lib.ABR_EINVAL  # nsubsteps < 1
     assert L.abr_env_set_randomization(None, None, 0) == _lib.ABR_EINVAL
     assert L.abr_model_reserve(None, 4, 4, 1, 8) == _lib.ABR_EINVAL
+    assert L.abr_model_describe(None, C.create_string_buffer(8), 8) == _lib.ABR_EINVAL
     assert L.abr_predictive_sample_dev(None, None, None, None, None, 0, 1, 8, 4, 0.1, 0, 8, None, None, None, None, None, None) == _lib.ABR_EINVAL
     assert L.abr_mpc_dev(None, None, None, None, 0, 8, 4, 0.1, 2, None, None, None, None, None) == _lib.ABR_EINVAL
     handle = C.create_string_buffer(64)

@@ -421,6 +421,18 @@ def test_limb_path_is_default_and_matches_generic(load_model, name, monkeypatch)
     assert np.abs(xs_g - out[1][0]).max() < 2e-3
 
 
+def test_model_describe_names_the_serving_kernels(load_model):
+    mj, m, _ = model_with(load_model, "barkour")
+    assert "limb kernels <NL=3, NC=1, flat 4-lane pattern>" in m.describe() and "fast (eulerdamp off)" in m.describe()
+    assert "fast (eulerdamp on)" in m.replace(opt=m.opt.replace(disableflags=0)).describe()
+    assert "general variant" in m.replace(opt=m.opt.replace(iterations=3)).describe()
+    assert "biped pattern, contact-body form" in model_with(load_model, "biped")[1].describe()
+    assert "sharing pattern from the table" in model_with(load_model, "tripod")[1].describe()
+    assert m.describe().count("\n") == 0 and "generic kernels" in model_with(load_model, "bh280")[1].describe()
+    m.set_lanes(16)
+    assert "generic kernels, 16 lanes" in m.describe()
+
+
 def test_limb_path_eligibility(load_model):
     """Fixed-base models, equality constraints, CG and RK4 stay on the generic kernels: pinning the limb
     path there is an error, not a silent fallback."""

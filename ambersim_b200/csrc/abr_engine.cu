@@ -797,8 +797,11 @@ static int launch_rollout(const AbrModel* m, const Layout& L, const RolloutArgs&
    : sv == 1 ? launch_limb_rollout_##NL##_##NC##_##TAG##_s1(L, a, st) : sv == 5 ? launch_limb_rollout_##NL##_##NC##_##TAG##_s5(L, a, st) \
    : sv == 9 ? launch_limb_rollout_##NL##_##NC##_##TAG##_s9(L, a, st) : sv == 13 ? launch_limb_rollout_##NL##_##NC##_##TAG##_s13(L, a, st) \
    : launch_limb_rollout_##NL##_##NC##_##TAG##_sg(L, a, st))
-    if (L.lNL == 3 && L.lNC == 1) return launch_result(spec && L.l_mx == 2 ? ABR_PICK_ROLLOUT(3, 1, f2) : launch_limb_rollout_3_1_g_sg(L, a, st));
-    if (L.lNL == 6 && L.lNC == 4) return launch_result(spec && L.l_mx == 86 && L.l_cb ? ABR_PICK_ROLLOUT(6, 4, b) : launch_limb_rollout_6_4_g_sg(L, a, st));
+    if (L.lNL == 3 && L.lNC == 1)
+      return launch_result(spec && L.l_mx == 2 ? ABR_PICK_ROLLOUT(3, 1, f2) : spec && L.l_mx == 3 ? ABR_PICK_ROLLOUT(3, 1, f3) : launch_limb_rollout_3_1_g_sg(L, a, st));
+    if (L.lNL == 6 && L.lNC == 4)
+      return launch_result(spec && L.l_cb && L.l_mx == 86 ? ABR_PICK_ROLLOUT(6, 4, b) : spec && L.l_cb && L.l_mx == 1 ? ABR_PICK_ROLLOUT(6, 4, l2)
+                           : spec && L.l_cb && L.l_mx == 2 ? ABR_PICK_ROLLOUT(6, 4, f2) : launch_limb_rollout_6_4_g_sg(L, a, st));
 #undef ABR_PICK_ROLLOUT
     return fail(ABR_ECAPACITY, "no compiled limb kernel for this model");
   }
@@ -822,12 +825,15 @@ static int launch_env(const AbrModel* m, const Layout& L, const EnvArgs& a_in, c
     const bool fast = (L.disableflags == ABR_DSBL_EULERDAMP || L.disableflags == 0) && L.iterations == 1 && L.l_pow2 && L.l_hinge &&
                       getenv("ABR_LIMB_NOSPEC") == nullptr;
     const bool ed = L.disableflags == 0;
+#define ABR_PICK_ENV(NL, NC, TAG)                                                                             \
+  (fast ? (ed ? launch_limb_env_##NL##_##NC##_##TAG##_s1(L, a, st) : launch_limb_env_##NL##_##NC##_##TAG##_s0(L, a, st)) \
+        : launch_limb_env_##NL##_##NC##_##TAG##_sg(L, a, st))
     if (L.lNL == 3 && L.lNC == 1)
-      return launch_result(spec && L.l_mx == 2 ? (fast ? (ed ? launch_limb_env_3_1_f2_s1(L, a, st) : launch_limb_env_3_1_f2_s0(L, a, st)) : launch_limb_env_3_1_f2_sg(L, a, st))
-                                               : launch_limb_env_3_1_g_sg(L, a, st));
+      return launch_result(spec && L.l_mx == 2 ? ABR_PICK_ENV(3, 1, f2) : spec && L.l_mx == 3 ? ABR_PICK_ENV(3, 1, f3) : launch_limb_env_3_1_g_sg(L, a, st));
     if (L.lNL == 6 && L.lNC == 4)
-      return launch_result(spec && L.l_mx == 86 && L.l_cb ? (fast ? (ed ? launch_limb_env_6_4_b_s1(L, a, st) : launch_limb_env_6_4_b_s0(L, a, st)) : launch_limb_env_6_4_b_sg(L, a, st))
-                                                         : launch_limb_env_6_4_g_sg(L, a, st));
+      return launch_result(spec && L.l_cb && L.l_mx == 86 ? ABR_PICK_ENV(6, 4, b) : spec && L.l_cb && L.l_mx == 1 ? ABR_PICK_ENV(6, 4, l2)
+                           : spec && L.l_cb && L.l_mx == 2 ? ABR_PICK_ENV(6, 4, f2) : launch_limb_env_6_4_g_sg(L, a, st));
+#undef ABR_PICK_ENV
     return fail(ABR_ECAPACITY, "no compiled limb kernel for this model");
   }
   LaunchCfg cfg{m->max_smem};
@@ -942,11 +948,14 @@ int abr_model_describe(const AbrModel* m, char* buf, int cap) {
   char tmp[256];
   if (use_limb(m, L, false, false)) {
     const bool spec = getenv("ABR_LIMB_GENERAL") == nullptr;
-    const bool flat = L.lNL == 3 && L.lNC == 1 && spec && L.l_mx == 2, bip = L.lNL == 6 && L.lNC == 4 && spec && L.l_mx == 86 && L.l_cb;
-    const bool fast = (flat || bip) && (L.disableflags == ABR_DSBL_EULERDAMP || L.disableflags == 0) && L.iterations == 1 && L.l_pow2 && L.l_hinge &&
+    const bool k31 = L.lNL == 3 && L.lNC == 1, k64 = L.lNL == 6 && L.lNC == 4;
+    const bool flat = spec && ((k31 && (L.l_mx == 2 || L.l_mx == 3)) || (k64 && L.l_cb && (L.l_mx == 1 || L.l_mx == 2))), bip = k64 && spec && L.l_mx == 86 && L.l_cb;
+    const bool lite = k64 && !bip;  // these families build the eulerdamp-off fast variants only
+    const bool fast = (flat || bip) && (L.disableflags == ABR_DSBL_EULERDAMP || (L.disableflags == 0 && !lite)) && L.iterations == 1 && L.l_pow2 && L.l_hinge &&
                       getenv("ABR_LIMB_NOSPEC") == nullptr;
     snprintf(tmp, sizeof(tmp), "limb kernels <NL=%d, NC=%d, %s>, %d lanes per world, %s variant", L.lNL, L.lNC,
-             flat ? "flat 4-lane pattern" : (bip ? "biped pattern, contact-body form" : "sharing pattern from the table"), 1 << L.lg2G,
+             flat ? (L.l_mx == 1 ? "flat 2-lane pattern" : (L.l_mx == 3 ? "flat 8-lane pattern" : "flat 4-lane pattern"))
+                  : (bip ? "biped pattern, contact-body form" : "sharing pattern from the table"), 1 << L.lg2G,
              fast ? (L.disableflags == 0 ? "fast (eulerdamp on)" : "fast (eulerdamp off)") : "general");
   } else {
     snprintf(tmp, sizeof(tmp), "generic kernels, %s lanes per world%s", m->lanes > 1 ? std::to_string(m->lanes).c_str() : "8 / 16 / 32 (by batch size)",

@@ -1419,6 +1419,14 @@ template <int NL, int NC, class Args, class K> int launch_limb(K kern, const Lay
   int launch_limb_env_##NL##_##NC##_##TAG##_##STAG(const Layout& L, const EnvArgs& a, cudaStream_t st) {                   \
     return limb::launch_limb<NL, NC>(limb::k_limb_env<NL, NC, LGC, CB, SPEC>, L, a, a.E, 0, st);                           \
   }
+#define ABR_ALIAS_LIMB_ROLLOUT(NL, NC, TAG, STAG)                                                                           \
+  int launch_limb_rollout_##NL##_##NC##_##TAG##_##STAG(const Layout& L, const RolloutArgs& a, cudaStream_t st) {           \
+    return launch_limb_rollout_##NL##_##NC##_##TAG##_sg(L, a, st);                                                        \
+  }
+#define ABR_ALIAS_LIMB_ENV(NL, NC, TAG, STAG)                                                                               \
+  int launch_limb_env_##NL##_##NC##_##TAG##_##STAG(const Layout& L, const EnvArgs& a, cudaStream_t st) {                   \
+    return launch_limb_env_##NL##_##NC##_##TAG##_sg(L, a, st);                                                            \
+  }
 #define ABR_DECLARE_LIMB_FAMILY_FAST(NL, NC, TAG)                                                                         \
   ABR_DECLARE_LIMB_ROLLOUT(NL, NC, TAG, sg) ABR_DECLARE_LIMB_ROLLOUT(NL, NC, TAG, s0) ABR_DECLARE_LIMB_ROLLOUT(NL, NC, TAG, s4) \
   ABR_DECLARE_LIMB_ROLLOUT(NL, NC, TAG, s8) ABR_DECLARE_LIMB_ROLLOUT(NL, NC, TAG, s12)                                    \
@@ -1426,10 +1434,16 @@ template <int NL, int NC, class Args, class K> int launch_limb(K kern, const Lay
   ABR_DECLARE_LIMB_ROLLOUT(NL, NC, TAG, s9) ABR_DECLARE_LIMB_ROLLOUT(NL, NC, TAG, s13)                                    \
   ABR_DECLARE_LIMB_ENV(NL, NC, TAG, sg) ABR_DECLARE_LIMB_ENV(NL, NC, TAG, s0) ABR_DECLARE_LIMB_ENV(NL, NC, TAG, s1)
 #define ABR_DECLARE_LIMB_FAMILY_GENERAL(NL, NC, TAG) ABR_DECLARE_LIMB_ROLLOUT(NL, NC, TAG, sg) ABR_DECLARE_LIMB_ENV(NL, NC, TAG, sg)
+// families (compile-time sharing patterns): f2 = flat 4 lanes (quadruped; with 6-joint chains: a humanoid without waist joints), f3 = flat 8
+// lanes (hexapod), l2 = flat 2 lanes (legs only: exoskeleton / biped without arms), b = biped with a torso chain shared by the arm paths;
+// g = any pattern, read from the lane table (3x slower: the merges and their level tests are then run-time work at every position)
 ABR_DECLARE_LIMB_FAMILY_FAST(3, 1, f2)
+ABR_DECLARE_LIMB_FAMILY_FAST(3, 1, f3)
 ABR_DECLARE_LIMB_FAMILY_GENERAL(3, 1, g)
 ABR_DECLARE_LIMB_FAMILY_GENERAL(6, 4, g)
 ABR_DECLARE_LIMB_FAMILY_FAST(6, 4, b)
+ABR_DECLARE_LIMB_FAMILY_FAST(6, 4, l2)
+ABR_DECLARE_LIMB_FAMILY_FAST(6, 4, f2)
 
 }  // namespace abr
 #endif

@@ -13,11 +13,13 @@ def _f(a):
     return " ".join(f"{x:.5g}" for x in np.atleast_1d(a))
 
 
-def random_limb_model(seed: int, max_chain: int = 3, max_con: int = 1, max_leaves: int = 4, iterations: int = 1, forks: bool = True, quad: bool = False):
+def random_limb_model(seed: int, max_chain: int = 3, max_con: int = 1, max_leaves: int = 4, iterations: int = 1, forks: bool = True, quad: bool = False,
+                      nlimb: int = 0, leaf_contacts_only: bool = False):
     """Returns (xml, home_qpos, home_ctrl). Chains have <= max_chain joints between trunk and leaf and at most
     max_con foot spheres per root-to-leaf path (the capacity of the compiled limb kernels: (3,1) and (6,4)).
     quad: the flat four-limb class with the common options (hinges only, no forks, eulerdamp disabled), i.e. a model the
-    compile-time fast variants of the limb kernels serve."""
+    compile-time fast variants of the limb kernels serve. nlimb > 0 with quad=True gives the other flat classes (2 = legs only, 6 = hexapod);
+    leaf_contacts_only keeps every foot on a leaf body (the contact-body form of the long-chain kernels)."""
     rng = np.random.default_rng(seed)
     acts, qpos, ctrl = [], [], []
     counter, leaves = [0], [0]
@@ -65,7 +67,7 @@ def random_limb_model(seed: int, max_chain: int = 3, max_con: int = 1, max_leave
             ctrl.append(0.0)
         # feet: a leaf gets them while the path still has budget; inner bodies sometimes
         ncon_here = 0
-        if budget_con > 0 and (remaining == 0 or rng.random() < 0.25):
+        if budget_con > 0 and (remaining == 0 or (not leaf_contacts_only and rng.random() < 0.25)):
             ncon_here = int(rng.integers(1, (min(budget_con, 2) if remaining else budget_con) + 1))
             for c in range(ncon_here):
                 cd = 3 if rng.random() < 0.75 else 1
@@ -81,11 +83,11 @@ def random_limb_model(seed: int, max_chain: int = 3, max_con: int = 1, max_leave
         return "\n".join(xml)
 
     limbs = []
-    nlimb = 4 if quad else int(rng.integers(2, min(4, max_leaves) + 1))
+    nlimb = nlimb if nlimb > 0 else (4 if quad else int(rng.integers(2, min(4, max_leaves) + 1)))
     leaves[0] = nlimb
     for limb in range(nlimb):
         n = int(rng.integers(1, max_chain + 1))
-        ang = 2 * np.pi * limb / nlimb + rng.uniform(-0.2, 0.2)
+        ang = 2 * np.pi * limb / nlimb + rng.uniform(-0.2, 0.2) / max(1, nlimb // 4)
         limbs.append(body(np.array([0.18 * np.cos(ang), 0.18 * np.sin(ang), -0.03]), n - 1, max_con, f"l{limb}_", forks and not quad))
     height = 0.45
     trunk_mass = float(rng.uniform(2.0, 5.0))

@@ -9,12 +9,15 @@ from ambersim_b200.utils.io_utils import load_mj_model_from_file
 from oracle.oracle import Oracle
 from tests._randmodel import random_limb_model
 
-CONFIGS = {"quad": (3, 1, 4), "long": (6, 4, 4), "wide": (3, 1, 8), "fastquad": (3, 1, 4)}
+CONFIGS = {"quad": (3, 1, 4), "long": (6, 4, 4), "wide": (3, 1, 8), "fastquad": (3, 1, 4), "hexa": (3, 1, 8), "legs2": (6, 4, 2), "flat4long": (6, 4, 4)}
+# flat classes with the common options, served by compile-time sharing patterns and the fast variants of the limb kernels
+FLAT = {"fastquad": dict(quad=True), "hexa": dict(quad=True, nlimb=6), "legs2": dict(quad=True, nlimb=2, leaf_contacts_only=True),
+        "flat4long": dict(quad=True, nlimb=4, leaf_contacts_only=True)}
 
 
 def _load(tmp_path, seed, cfg, **kw):
-    if cfg == "fastquad":  # flat four-limb class with the common options: served by the compile-time fast variants
-        kw = {**kw, "quad": True, "iterations": 1}
+    if cfg in FLAT:
+        kw = {**kw, **FLAT[cfg], "iterations": 1}
     xml, q, c = random_limb_model(seed, *CONFIGS[cfg], **kw)
     f = tmp_path / f"rand_{cfg}_{seed}.xml"
     f.write_text(xml)
@@ -50,8 +53,10 @@ def test_random_model_plans_cover_every_body_once(tmp_path, cfg):
             for b, lanes in groups.items():
                 assert {p["level"][g][k] for g in lanes} == {int(np.ceil(np.log2(len(lanes))))} or len(lanes) == 1
     assert eligible >= 6
-    if cfg == "fastquad":
-        assert eligible == 12 and all(mjx.limb_plan(_load(tmp_path, s, cfg)[0])["pattern"] == 2 for s in range(4))
+    if cfg in FLAT:
+        want = {"fastquad": (2, 4), "hexa": (3, 8), "legs2": (1, 2), "flat4long": (2, 4)}[cfg]
+        plans = [p for p in (mjx.limb_plan(_load(tmp_path, s, cfg)[0]) for s in range(12)) if p["eligible"]]
+        assert eligible >= 10 and all((p["pattern"], p["lanes"]) == want for p in plans)  # a trunk contact on top of four feet overflows a lane
 
 
 @pytest.mark.parametrize("cfg", list(CONFIGS))

@@ -34,6 +34,7 @@ CTRL_NOISE, JITTER = 0.1, 0.05
 # work" variant (no unused post-iteration Hessian), home state: add=sub=mul=div=sqrt=sin=cos=pow=1.
 F_WS = 46349.0
 F_WS_BIPED = 130142.0  # same counter, biped stand-in at its standing keyframe
+F_WS_EXO_LEGS = 67283.0  # same counter, legs-only exoskeleton stand-in
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
 # dram__bytes_read.sum + dram__bytes_write.sum of the C2 launch (one `ncu --set full` capture of this file's
 # own kernel launch, profiles/r1_limb_final4_c2_summary.txt + .ncu-rep): 198.25 MB + 5.07 MB vs 197.23 MB algorithmic
@@ -245,6 +246,16 @@ def extra_configs(mj, m, cf, q0, torch, device, stream, L, peak_tf):
     ex["c3_biped_16384x1000"] = {"world_steps_per_s": rate, "costs_finite": fin, "flop_per_world_step": F_WS_BIPED,
                                  "frac_of_ffma_peak": F_WS_BIPED * rate / 1e12 / peak_tf,
                                  "model": "biped_exo_standin (nq=28 nv=27 nu=21 nbody=23 ncon=8 nefc=53; Newton it=1 ls=6 Euler dt=.004)"}
+    # the same class without torso and arms (an exoskeleton is legs only): the flat 2-lane family of the limb kernels
+    ej = load_mj_model_from_file("models/biped_standin/exo_legs_standin.xml")
+    em = mjx.device_put(ej)
+    eq0 = np.concatenate([ej.key_qpos("stand"), np.zeros(ej.nv)])
+    enx = ej.nq + ej.nv
+    ecf = StaticGoalQuadraticCost(np.eye(enx), 10.0 * np.eye(enx), 0.01 * np.eye(ej.nu), eq0)
+    rate, fin = rollout_rate(ej, em, ecf, "stand", 16384, 1000, CTRL_NOISE)
+    ex["c3b_exo_legs_16384x1000"] = {"world_steps_per_s": rate, "costs_finite": fin, "flop_per_world_step": F_WS_EXO_LEGS,
+                                     "frac_of_ffma_peak": F_WS_EXO_LEGS * rate / 1e12 / peak_tf, "kernels": em.describe(),
+                                     "model": "exo_legs_standin (nq=19 nv=18 nu=12 nbody=14 ncon=8 nefc=44; Newton it=1 ls=6 Euler dt=.004)"}
     sweep = {}
     prm = VanillaPredictiveSamplerParams(key=3, x0=torch.tensor(q0, **f), us_guess=torch.tensor(mj.key_ctrl("home"), **f).repeat(32, 1))
     for S in (1024, 4096, 16384, 65536, 262144, 1048576):

@@ -19,6 +19,7 @@ MODELS = {
     "bh280": ("models/barrett_hand/bh280.xml", None),
     "barkour": ("models/barkour_standin/barkour_vb_standin.xml", "home"),
     "biped": ("models/biped_standin/biped_exo_standin.xml", "stand"),
+    "exolegs": ("models/biped_standin/exo_legs_standin.xml", "stand"),  # legs only: the flat 2-lane class of the limb kernels
     # test-only fixture for the limb kernels: 3 limbs (dummy lane), a forked limb (nested sharing), padding,
     # slide joint, condim-1 contacts, a trunk contact, a tilted floor
     "tripod": (str(ROOT / "tests/models/tripod.xml"), "home"),

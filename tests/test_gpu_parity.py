@@ -28,7 +28,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 STAGES = ["xpos", "xquat", "xipos", "cinert", "cdof", "qM", "cvel", "cdof_dot", "contact_dist", "contact_pos", "contact_frame",
           "qfrc_smooth", "qacc_smooth", "efc_J", "efc_D", "efc_aref", "qacc", "efc_force", "qfrc_constraint"]
-MODEL_KEY = {"barkour": "home", "biped": "stand", "tripod": "home", "tripod3": "home"}
+MODEL_KEY = {"barkour": "home", "biped": "stand", "exolegs": "stand", "tripod": "home", "tripod3": "home"}
 BH_OPT = dict(timestep=0.002, iterations=1, ls_iterations=4, integrator=0, solver=2, disableflags=16)  # the reference test's options
 
 
@@ -75,7 +75,7 @@ def test_forward_stage_parity(load_model, name):
             assert np.abs(r - g).max() <= 2e-4 * max(1e-6, np.abs(r).max()), f
 
 
-@pytest.mark.parametrize("name", ["pendulum", "bh280", "barkour", "biped", "tripod", "tripod3"])
+@pytest.mark.parametrize("name", ["pendulum", "bh280", "barkour", "biped", "exolegs", "tripod", "tripod3"])
 @pytest.mark.parametrize("variant", ["default", "rk4", "cg", "eulerdamp", "converged", "nowarm"])
 def test_single_step_parity_option_variants(load_model, name, variant):
     opt = dict(default={}, rk4=dict(integrator=1), cg=dict(solver=1, iterations=8, ls_iterations=10),
@@ -121,7 +121,7 @@ def test_contact_free_rollout_parity(load_model, name, lanes):
     assert np.allclose(costs, quad_cost(ref, us, eye, 10 * eye, 0.01 * np.eye(mj.nu), 0.0), rtol=1e-3)
 
 
-@pytest.mark.parametrize("name", ["barkour", "biped", "tripod", "tripod3"])
+@pytest.mark.parametrize("name", ["barkour", "biped", "exolegs", "tripod", "tripod3"])
 @pytest.mark.parametrize("lanes", [1, 4, 8, 16, 32])  # 1 = the limb (path-decomposed) kernels, 4..32 = generic group sizes
 def test_contact_rollout_teacher_forced(load_model, name, lanes):
     mj, m, o = model_with(load_model, name)
@@ -384,7 +384,7 @@ def test_ffma_peak_is_plausible():
 
 
 # ------------------------------------------------------------------ limb (path-decomposed) kernels
-@pytest.mark.parametrize("name", ["barkour", "biped", "tripod", "tripod3"])
+@pytest.mark.parametrize("name", ["barkour", "biped", "exolegs", "tripod", "tripod3"])
 def test_limb_path_is_default_and_matches_generic(load_model, name, monkeypatch):
     """Eligible models run on the limb kernels by default (lanes = 0 or 1); pinning a generic group size
     gives the same trajectory and costs up to float32 rounding, and the general-sharing build of the limb
@@ -773,7 +773,7 @@ def test_solve_is_cuda_graph_capturable(load_model):
 
 
 @pytest.mark.parametrize("eulerdamp", [False, True])
-@pytest.mark.parametrize("name", ["barkour", "biped"])
+@pytest.mark.parametrize("name", ["barkour", "biped", "exolegs"])
 def test_limb_fast_variants_match_the_general_variant(load_model, name, eulerdamp, monkeypatch):
     """The compile-time variants of the limb kernels (no eulerdamp / multi-iteration / output / other-mode code in the loop) against the
     general variant of the same kernel (ABR_LIMB_NOSPEC): rollouts with and without trajectories, sampler costs, env steps; with the

@@ -335,7 +335,7 @@ template <bool POW2> __device__ __forceinline__ void row_kbi(const float* prm, f
   kbi_row(kbi_imp<POW2>(prm, pos), jvel, invw, active, D, aref);
 }
 
-struct LSP { float alpha, cost, d0, d1; };
+struct LSP { float alpha, d0, d1, q1, q2; };  // the point's cost is alpha^2 q2 + alpha q1 + q0(alpha): q0 is only summed for the points whose cost is read
 
 // constraint rows of one lane: NL joint-limit rows (chain dof 6 + r), then 4 pyramid rows per contact slot
 // CB ("contact body") = every contact of a lane sits on the lane's leaf body and touches one plane: the contact
@@ -412,22 +412,30 @@ template <int NL, int NC, bool CB, class SH, bool AT_AS = false> __device__ __fo
   gauss = 0.5f * g;
   return 0.5f * sc + 0.5f * g;
 }
-// one point of the exact line search: (cost, d0, d1) at alpha. a0/a1/a2 are the per-row quadratic
+// one point of the exact line search: (d0, d1) at alpha. a0/a1/a2 are the per-row quadratic
 // coefficients 0.5 D ja^2, D ja jv, 0.5 D jv^2 (a row counts while ja + alpha jv < 0).
-template <int NR> __device__ __forceinline__ LSP ls_eval(const float (&Jaref)[NR], const float (&jv)[NR], const float (&a0)[NR], const float (&a1)[NR],
-                                                         const float (&a2)[NR], float alpha, float qg0, float qg1, float qg2, int lg) {
-  float q0 = 0.f, q1 = 0.f, q2 = 0.f;
+template <int NR> __device__ __forceinline__ LSP ls_eval(const float (&Jaref)[NR], const float (&jv)[NR], const float (&a1)[NR],
+                                                         const float (&a2)[NR], float alpha, float qg1, float qg2, int lg) {
+  float q1 = 0.f, q2 = 0.f;
 #pragma unroll
   for (int r = 0; r < NR; r++) {
-    if (fmaf(alpha, jv[r], Jaref[r]) < 0.f) { q0 += a0[r]; q1 += a1[r]; q2 += a2[r]; }  // three predicated adds, no selects
+    if (fmaf(alpha, jv[r], Jaref[r]) < 0.f) { q1 += a1[r]; q2 += a2[r]; }  // predicated adds, no selects
   }
-  q0 = gall(q0, lg) + qg0; q1 = gall(q1, lg) + qg1; q2 = gall(q2, lg) + qg2;
+  q1 = gall(q1, lg) + qg1; q2 = gall(q2, lg) + qg2;
   LSP pt;
-  pt.alpha = alpha;
-  pt.cost = alpha * alpha * q2 + alpha * q1 + q0;
+  pt.alpha = alpha; pt.q1 = q1; pt.q2 = q2;
   pt.d0 = 2.f * alpha * q2 + q1;
   pt.d1 = 2.f * q2 + ((q2 == 0.f) ? kMinVal : 0.f);
   return pt;
+}
+// the cost of a point (the loop's decisions only read d0 / d1, so q0 is summed for the three points whose cost is compared)
+template <int NR> __device__ __forceinline__ float ls_cost(const float (&Jaref)[NR], const float (&jv)[NR], const float (&a0)[NR], const LSP& pt, float qg0, int lg) {
+  float q0 = 0.f;
+#pragma unroll
+  for (int r = 0; r < NR; r++)
+    if (fmaf(pt.alpha, jv[r], Jaref[r]) < 0.f) q0 += a0[r];
+  q0 = gall(q0, lg) + qg0;
+  return pt.alpha * pt.alpha * pt.q2 + pt.alpha * pt.q1 + q0;
 }
 
 // mjx.forward for one lane: on exit s.a = qacc, s.warm = qacc; M, fs, fc are returned for the
@@ -990,7 +998,7 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
       const float ja = Jaref[r], w = jv[r], Dr = R.D[r];
       la0[r] = 0.5f * ja * ja * Dr; la1[r] = w * ja * Dr; la2[r] = 0.5f * w * w * Dr;
     }
-#define LS_EVAL(al) ls_eval<NR>(Jaref, jv, la0, la1, la2, (al), qg0, qg1, qg2, S.lg())
+#define LS_EVAL(al) ls_eval<NR>(Jaref, jv, la1, la2, (al), qg1, qg2, S.lg())
     const LSP p0 = LS_EVAL(0.f);
     const LSP l0 = LS_EVAL(-safe_div_fast(p0.d0, p0.d1));
     const bool lesser = l0.d0 < p0.d0;
@@ -1020,8 +1028,9 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
         it++;
       }
     }
-    const bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
-    const float alpha = (improved && live) ? ((lo.cost < hi.cost) ? lo.alpha : hi.alpha) : 0.f;
+    const float c_p0 = ls_cost<NR>(Jaref, jv, la0, p0, qg0, S.lg()), c_lo = ls_cost<NR>(Jaref, jv, la0, lo, qg0, S.lg()), c_hi = ls_cost<NR>(Jaref, jv, la0, hi, qg0, S.lg());
+    const bool improved = (c_lo < c_p0) || (c_hi < c_p0);
+    const float alpha = (improved && live) ? ((c_lo < c_hi) ? lo.alpha : hi.alpha) : 0.f;
 #pragma unroll
     for (int d = 0; d < N; d++) { s.a[d] = fmaf(search[d], alpha, s.a[d]); Ma[d] = fmaf(mv[d], alpha, Ma[d]); }
 #pragma unroll
@@ -1078,7 +1087,18 @@ __device__ __forceinline__ void euler(Lane<NL, NC>& s, const LaneCfg<LGC>& C, fl
 #undef LS_EVAL
 
 // ------------------------------------------------------------------------------ kernels
-constexpr int kTPB = 32;      // default: one warp per CTA (32/G worlds); small CTAs spread a 4096-world batch over every SM sub-partition
+constexpr int kTPB = 32;      // smallest CTA: one warp (32/G worlds)
+constexpr int kMaxTPB = 256;  // largest CTA: 8 warps = every register of an SM at 255 registers per thread
+// CTA size of a launch ("instruction delivery"). The straight-line step does not fit the SM's instruction
+// cache, so every SM streams it from the GPC-level cache each step; the warps of one SM run in loose lockstep and share that
+// stream, while the SMs of a GPC compete for it. A small batch therefore runs faster on FEWER SMs with MORE warps each:
+// the per-GPC instruction traffic drops with the number of streaming SMs. ABR_LIMB_TPB overrides the policy (probes).
+inline int pick_tpb(long nwarps) {
+  const char* ev = getenv("ABR_LIMB_TPB");
+  const int env = ev ? atoi(ev) : 0;
+  if (env >= 32 && env <= kMaxTPB && env % 32 == 0) return env;
+  return nwarps <= 16 ? 128 : kMaxTPB;  // measured: profiles/r2_tpb_sweep*.txt (a handful of warps: one per sub-partition)
+}
 #ifndef ABR_LIMB_MINB
 #define ABR_LIMB_MINB 1  // resident CTAs per SM the register allocation must allow (1 = up to 255 registers)
 #endif
@@ -1151,7 +1171,7 @@ template <int NL, int NC, int LGC> __device__ __forceinline__ void store_x(const
 
 // shoot (shooting.py:22-48) / the sampler's rollouts (shooting.py:140-153) on the limb path
 template <int NL, int NC, int LGC, bool CB, int SPEC>
-__global__ void __launch_bounds__(kTPB, ABR_LIMB_MINB) k_limb_rollout(const __grid_constant__ Layout L, const __grid_constant__ RolloutArgs A) {
+__global__ void __launch_bounds__(kMaxTPB, ABR_LIMB_MINB) k_limb_rollout(const __grid_constant__ Layout L, const __grid_constant__ RolloutArgs A) {
   extern __shared__ __align__(16) float smem[];
   constexpr Map mp{NL, NC};
   constexpr int N = 6 + NL, NTRI = N * (N + 1) / 2;
@@ -1198,7 +1218,7 @@ __global__ void __launch_bounds__(kTPB, ABR_LIMB_MINB) k_limb_rollout(const __gr
   float* xs = Spec<SPEC>::out(A.xs_out) ? A.xs_out + (size_t)w * (Nh + 1) * nx : nullptr;
   // per-lane cost table (see quad_x_tab): weights of entries this lane does not own are zero
   constexpr int NS = cost_slots<NL>();
-  float* ctab = cxg + nx + threadIdx.x;
+  float* ctab = cxg + nx + (threadIdx.x >> 5) * ((3 * NS + NL) * 32) + (threadIdx.x & 31);  // one table per warp
   if (A.cost.enabled) {
     const bool own0 = C.S.o(0);
 #pragma unroll
@@ -1217,6 +1237,22 @@ __global__ void __launch_bounds__(kTPB, ABR_LIMB_MINB) k_limb_rollout(const __gr
     }
   }
   const float* cgoal = ctab + 2 * 32;
+  // explicit controls are fetched one step ahead with cp.async into a two-deep per-thread slot (no registers held across the
+  // step, no exposed L2 / HBM latency at the top of it): word (buffer b, position p) of a thread at upre[(b * NL + p - 1) * blockDim.x]
+  float* upre = cxg + nx + (blockDim.x >> 5) * ((3 * NS + NL) * 32) + threadIdx.x;
+  const bool prefetch = !Spec<SPEC>::sampler(A.mode);
+  auto fetch_u = [&](int t) {
+#pragma unroll
+    for (int p = 1; p <= NL; p++) {
+      const int ga = LTI(mp.ijnt(p) + 3);
+      if (ga >= 0) {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(upre + ((t & 1) * NL + (p - 1)) * blockDim.x);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(A.us + (size_t)w * A.us_stride + (size_t)t * nu + ga) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (prefetch && (resume ? t_first : 0) < t_last) fetch_u(resume ? t_first : 0);
   float cacc = 0.f;
   if (!resume) {
     if (xs && valid) store_x<NL, NC, LGC>(s, C, xs, nq);
@@ -1228,13 +1264,14 @@ __global__ void __launch_bounds__(kTPB, ABR_LIMB_MINB) k_limb_rollout(const __gr
 #pragma unroll 1
   for (int t = resume ? t_first : -1; t < t_last; t++) {
     if (t >= 0) {
+      if (prefetch) asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
       for (int p = 1; p <= NL; p++) {
         const int ga = LTI(mp.ijnt(p) + 3);
         float u = 0.f;
         if (ga >= 0) {
           if (!Spec<SPEC>::sampler(A.mode)) {
-            u = A.us[(size_t)w * A.us_stride + (size_t)t * nu + ga];
+            u = upre[((t & 1) * NL + (p - 1)) * blockDim.x];
           } else {
             float nz = 0.f;
             if (sample > 0) {
@@ -1251,6 +1288,7 @@ __global__ void __launch_bounds__(kTPB, ABR_LIMB_MINB) k_limb_rollout(const __gr
         s.ctrl[p - 1] = u;
         if (A.cost.enabled) cacc = fmaf(ctab[(3 * NS + (p - 1)) * 32] * u, u, cacc);
       }
+      if (prefetch && t + 1 < t_last) fetch_u(t + 1);
     }
     float M[NTRI], fs[N], fc[N];
     forward<NL, NC, LGC, CB, SPEC>(s, C, M, fs, fc);
@@ -1284,7 +1322,7 @@ __global__ void __launch_bounds__(kTPB, ABR_LIMB_MINB) k_limb_rollout(const __gr
 
 // MjxEnv.pipeline_init / pipeline_step (rl/base.py:81-96) with the auto-reset blend, on the limb path
 template <int NL, int NC, int LGC, bool CB, int SPEC>
-__global__ void __launch_bounds__(kTPB, ABR_LIMB_MINB) k_limb_env(const __grid_constant__ Layout L, const __grid_constant__ EnvArgs A) {
+__global__ void __launch_bounds__(kMaxTPB, ABR_LIMB_MINB) k_limb_env(const __grid_constant__ Layout L, const __grid_constant__ EnvArgs A) {
   extern __shared__ __align__(16) float smem[];
   constexpr Map mp{NL, NC};
   constexpr int N = 6 + NL, NTRI = N * (N + 1) / 2;
@@ -1390,14 +1428,16 @@ __global__ void __launch_bounds__(kTPB, ABR_LIMB_MINB) k_limb_env(const __grid_c
   }
 }
 
-template <int NL, int NC, class Args, class K> int launch_limb(K kern, const Layout& L, const Args& a, int nworld, int extra_floats, cudaStream_t st) {
+// extra_floats: per CTA; extra_per_thread: per thread of the CTA
+template <int NL, int NC, class Args, class K> int launch_limb(K kern, const Layout& L, const Args& a, int nworld, int extra_floats, int extra_per_thread, cudaStream_t st) {
   constexpr Map mp{NL, NC};
-  const size_t sm = sizeof(float) * ((size_t)mp.total() * kStride + extra_floats);
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-  if (e != cudaSuccess) return (int)e;
   const long threads = (long)nworld << L.lg2G;
-  const int grid = (int)((threads + kTPB - 1) / kTPB);
-  kern<<<grid, kTPB, sm, st>>>(L, a);
+  const int tpb = pick_tpb((threads + 31) / 32);
+  const size_t sm = sizeof(float) * ((size_t)mp.total() * kStride + extra_floats + (size_t)extra_per_thread * tpb);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * ((size_t)mp.total() * kStride + extra_floats + (size_t)extra_per_thread * kMaxTPB)));
+  if (e != cudaSuccess) return (int)e;
+  const int grid = (int)((threads + tpb - 1) / tpb);
+  kern<<<grid, tpb, sm, st>>>(L, a);
   return (int)cudaGetLastError();
 }
 
@@ -1413,11 +1453,11 @@ template <int NL, int NC, class Args, class K> int launch_limb(K kern, const Lay
 #define ABR_DEFINE_LIMB_ROLLOUT(NL, NC, LGC, CB, TAG, SPEC, STAG)                                                         \
   int launch_limb_rollout_##NL##_##NC##_##TAG##_##STAG(const Layout& L, const RolloutArgs& a, cudaStream_t st) {           \
     return limb::launch_limb<NL, NC>(limb::k_limb_rollout<NL, NC, LGC, CB, SPEC>, L, a, a.nworld,                          \
-                                     3 * L.nx + L.nu + (3 * (13 + 2 * NL) + NL) * limb::kTPB, st);                        \
+                                     3 * L.nx + L.nu, 3 * (13 + 2 * NL) + 3 * NL, st);                                        \
   }
 #define ABR_DEFINE_LIMB_ENV(NL, NC, LGC, CB, TAG, SPEC, STAG)                                                             \
   int launch_limb_env_##NL##_##NC##_##TAG##_##STAG(const Layout& L, const EnvArgs& a, cudaStream_t st) {                   \
-    return limb::launch_limb<NL, NC>(limb::k_limb_env<NL, NC, LGC, CB, SPEC>, L, a, a.E, 0, st);                           \
+    return limb::launch_limb<NL, NC>(limb::k_limb_env<NL, NC, LGC, CB, SPEC>, L, a, a.E, 0, 0, st);                           \
   }
 #define ABR_ALIAS_LIMB_ROLLOUT(NL, NC, TAG, STAG)                                                                           \
   int launch_limb_rollout_##NL##_##NC##_##TAG##_##STAG(const Layout& L, const RolloutArgs& a, cudaStream_t st) {           \

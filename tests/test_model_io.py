@@ -180,7 +180,7 @@ def test_mujoco_model_dump_if_present():
 
     gold = Path(__file__).parent / "golden"
     used = 0
-    for name in ("pendulum", "bh280", "barkour", "biped"):
+    for name in ("pendulum", "bh280", "barkour", "biped", "exolegs"):
         path = gold / f"mjx_{name}.npz"
         if not path.exists():
             continue

@@ -1,0 +1,128 @@
+"""Algorithm-independent cross-checks: the oracle and the engine share the loader's flattened
+model and MJX's algorithms, so a common-mode mistake passes every oracle-vs-engine parity test. These tests restate
+the same physics along different routes (oracle/independent.py) and compare:
+
+* the loader's mj_setConst constants vs numerically differentiated kinematics + a kinetic-energy mass matrix;
+* the oracle's CRBA + RNE + factorisation `qacc_smooth` vs Featherstone's articulated-body algorithm;
+* the oracle's converged Newton solve vs a generic scipy minimiser of the primal constraint cost, in contact.
+
+Parity with MJX itself stays UNPINNED (no MJX here); these pin the oracle against physics it must obey."""
+import numpy as np
+import pytest
+
+from oracle import independent as ind
+from oracle.oracle import Oracle
+
+ALL = ["pendulum", "bh280", "barkour", "biped", "exolegs", "tripod", "tripod3"]
+KEYS = {"barkour": "home", "biped": "stand", "exolegs": "stand", "tripod": "home", "tripod3": "home"}
+
+
+def _random_state(m, name, rng, spread=0.3):
+    q = m.key_qpos(KEYS[name]) if name in KEYS else m.qpos0.copy()
+    if m.jnt_type[0] == 0:
+        q[7:] += rng.uniform(-spread, spread, m.nq - 7)
+        quat = rng.normal(size=4)
+        q[3:7] = quat / np.linalg.norm(quat)
+    else:
+        q = q + rng.uniform(0.0, 0.5, m.nq)
+    return q, rng.normal(size=m.nv)
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_setconst_against_numeric_route(load_model, name):
+    m = load_model(name)
+    sc = ind.setconst_numeric(m)
+    assert np.allclose(sc["qM0"], m.qM0, rtol=0, atol=1e-8 * np.abs(m.qM0).max())
+    assert np.allclose(sc["dof_invweight0"], m.dof_invweight0, rtol=1e-7)
+    assert np.allclose(sc["body_invweight0"], m.body_invweight0, rtol=1e-7, atol=1e-12)
+    assert np.isclose(sc["meaninertia"], m.stat.meaninertia, rtol=1e-8)
+    assert np.array_equal(sc["body_subtreemass"], m.body_subtreemass)
+
+
+def test_setconst_pendulum_closed_form(load_model):
+    """One hinge: dof_invweight0 = 1 / I_axis, body_invweight0 = (r^2 / I / 3 summed over the two in-plane axes, 1 / I / 3)."""
+    m = load_model("pendulum")
+    b = int(m.dof_bodyid[0])
+    I = float(m.qM0[0, 0])
+    assert np.isclose(m.dof_invweight0[0], 1.0 / I, rtol=1e-12)
+    assert np.isclose(m.stat.meaninertia, I, rtol=1e-12)
+    xpos, xrot, xipos, _ = ind.kinematics(m, m.qpos0)
+    j = int(m.body_jntadr[b])
+    r = xipos[b] - (xpos[b] + xrot[b] @ m.jnt_pos[j])
+    axis = xrot[b] @ m.jnt_axis[j]
+    lever = np.cross(axis, r)
+    assert np.isclose(m.body_invweight0[b, 0], lever @ lever / I / 3, rtol=1e-10)
+    assert np.isclose(m.body_invweight0[b, 1], 1.0 / I / 3, rtol=1e-10)
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_forward_dynamics_against_articulated_body_algorithm(load_model, name):
+    m = load_model(name)
+    rng = np.random.default_rng(11)
+    o = Oracle(m, m.opt.replace(disableflags=1))  # constraints off: qacc is qacc_smooth
+    for _ in range(3):
+        q, v = _random_state(m, name, rng)
+        c = rng.normal(size=m.nu) * 0.3
+        f = o.forward(q, v, c)
+        tau = f["qfrc_passive"] + f["qfrc_actuator"]
+        qa = ind.aba(m, q, v, tau, m.opt.gravity)
+        # model parameters reach the oracle as float32 (the ABI's precision): 1e-6 relative
+        assert np.abs(qa - f["qacc_smooth"]).max() < 2e-6 * max(1.0, np.abs(f["qacc_smooth"]).max())
+        M = ind.mass_matrix_energy(m, q)
+        assert np.abs(M - f["qM"]).max() < 1e-6 * np.abs(f["qM"]).max()
+
+
+@pytest.mark.parametrize("name", ["barkour", "biped", "exolegs", "tripod", "bh280"])
+def test_constraint_solve_against_generic_minimiser(load_model, name):
+    m = load_model(name)
+    rng = np.random.default_rng(13)
+    base = m.opt.replace(disableflags=16) if name == "bh280" else m.opt
+    conv = Oracle(m, base.replace(solver=2, iterations=200, ls_iterations=50, tolerance=1e-14))
+    for trial in range(3):
+        if name == "bh280":
+            q, v = rng.uniform(-0.3, 0.8, m.nq), rng.normal(size=m.nv)  # past the lower joint limits, equalities active
+        else:
+            q, v = _random_state(m, name, rng, spread=0.15)
+            q[3:7] = m.key_qpos(KEYS[name])[3:7]
+            q[2] -= 0.01 + 0.01 * trial  # feet pressed into the floor
+        c = rng.normal(size=m.nu) * 0.2
+        f = conv.forward(q, v, c)
+        assert f["efc_D"].size and (f["efc_D"] > 0).any()
+        a = ind.constraint_minimum(f["qM"], f["qacc_smooth"], f["efc_J"], f["efc_D"], f["efc_aref"], conv.ne)
+        scale = max(1.0, np.abs(f["qacc"]).max())
+        assert np.abs(a - f["qacc"]).max() < 1e-6 * scale
+        # and the single-iteration configuration the benchmarks run lowers the same cost from the same start
+        one = Oracle(m, base).forward(q, v, c, qacc_warmstart=f["qacc_smooth"])
+
+        def cost(x):
+            r = f["efc_J"] @ x - f["efc_aref"]
+            act = (np.arange(r.size) < conv.ne) | (r < 0)
+            e = x - f["qacc_smooth"]
+            return 0.5 * e @ f["qM"] @ e + 0.5 * np.sum(f["efc_D"] * r * r * act)
+
+        assert cost(a) <= cost(one["qacc"]) + 1e-9 * abs(cost(a)) <= cost(f["qacc_smooth"]) + 1e-9 * abs(cost(a))
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_models_setconst_and_aba(tmp_path, seed):
+    """The same three routes on random trees (tilted inertial frames, slides, forks, random anchors and axes)."""
+    from ambersim_b200.utils.io_utils import load_mj_model_from_file
+    from tests._randmodel import random_limb_model
+
+    xml, home, _ = random_limb_model(100 + seed, max_chain=3 + (seed % 2) * 3, max_con=1 + (seed % 2) * 3, max_leaves=4)
+    p = tmp_path / f"rand{seed}.xml"
+    p.write_text(xml)
+    m = load_mj_model_from_file(str(p))
+    sc = ind.setconst_numeric(m)
+    assert np.allclose(sc["dof_invweight0"], m.dof_invweight0, rtol=1e-6)
+    assert np.allclose(sc["body_invweight0"], m.body_invweight0, rtol=1e-6, atol=1e-12)
+    assert np.isclose(sc["meaninertia"], m.stat.meaninertia, rtol=1e-8)
+    rng = np.random.default_rng(seed)
+    q = np.array(home, dtype=np.float64)
+    q[7:] += rng.uniform(-0.05, 0.05, m.nq - 7)
+    quat = rng.normal(size=4)
+    q[3:7] = quat / np.linalg.norm(quat)
+    v = rng.normal(size=m.nv)
+    f = Oracle(m, m.opt.replace(disableflags=1)).forward(q, v, rng.normal(size=m.nu) * 0.1)
+    qa = ind.aba(m, q, v, f["qfrc_passive"] + f["qfrc_actuator"], m.opt.gravity)
+    assert np.abs(qa - f["qacc_smooth"]).max() < 5e-6 * max(1.0, np.abs(f["qacc_smooth"]).max())

@@ -1,8 +1,12 @@
-"""Run on a machine that HAS mujoco + mujoco-mjx + jax (not this image): dumps reference rollouts of
-the repo's models into tests/golden/mjx_<model>.npz so that tests/test_oracle_physics.py
-(test_mjx_golden_if_present) can pin the oracle against real MJX outputs.
+"""Run on a machine that HAS mujoco + mujoco-mjx + jax (not this image): dumps, for each of the repo's five models,
+(1) a reference rollout through the reference's own `shoot`, (2) every per-stage `mjx.Data` field of one `mjx.forward`
+at a seeded state (controls and warm start included) and (3) the compiled `MjModel` field by field (mj_setConst
+constants, defaults, frames) into tests/golden/mjx_<model>.npz. tests/test_oracle_physics.py
+(test_mjx_golden_if_present, test_mjx_golden_stages_if_present) and tests/test_model_io.py
+(test_mujoco_model_dump_if_present) consume them and PIN the oracle and the loader against real MJX / MuJoCo.
 
-    python tools/dump_mjx_golden.py
+One command, anywhere with network:   pip install "mujoco>=3.0.1,<3.2" "mujoco-mjx>=3.0.1,<3.2" "jax[cpu]" && python tools/dump_mjx_golden.py
+then commit tests/golden/mjx_*.npz. Until such a file lands, parity with MJX is UNPINNED (README).
 """
 import sys
 from pathlib import Path
@@ -19,7 +23,11 @@ except ImportError as e:  # pragma: no cover
     sys.exit(f"needs jax + mujoco + mujoco-mjx: {e}")
 
 MODELS = {"pendulum": ("pendulum/scene.xml", None, {}), "bh280": ("barrett_hand/bh280.xml", None, dict(timestep=0.002, iterations=1, ls_iterations=4, disableflags=16)),
-          "barkour": ("barkour_standin/barkour_vb_standin.xml", "home", {}), "biped": ("biped_standin/biped_exo_standin.xml", "stand", {})}
+          "barkour": ("barkour_standin/barkour_vb_standin.xml", "home", {}), "biped": ("biped_standin/biped_exo_standin.xml", "stand", {}),
+          "exolegs": ("biped_standin/exo_legs_standin.xml", "stand", {})}
+STAGES = ("xpos xquat xmat xipos ximat xanchor xaxis geom_xpos geom_xmat subtree_com cinert cdof crb qM qLD actuator_length actuator_velocity "
+          "actuator_force qfrc_actuator cvel cdof_dot qfrc_passive qfrc_bias qfrc_smooth qacc_smooth efc_J efc_D efc_aref efc_pos efc_force "
+          "qfrc_constraint qacc qacc_warmstart").split()
 for name, (rel, key, kw) in MODELS.items():
     mj_model = mujoco.MjModel.from_xml_path(str(ROOT / "ambersim_b200/models" / rel))
     for k, v in kw.items():
@@ -43,6 +51,19 @@ for name, (rel, key, kw) in MODELS.items():
         return jnp.concatenate((x0[None], xs))
 
     xs = np.asarray(jax.jit(shoot)(jnp.asarray(x0, jnp.float32), jnp.asarray(us, jnp.float32)))
+    # one mjx.forward at a seeded state, every intermediate field (the stage-by-stage pin of the oracle)
+    sq = q.copy()
+    if key:
+        sq[7:] += rng.uniform(-0.1, 0.1, mj_model.nq - 7)
+        sq[2] -= 0.004  # feet pressed into the floor: contact rows active
+    sv, sc, sw = 0.3 * rng.normal(size=mj_model.nv), us[0], rng.normal(size=mj_model.nv)
+    d = mjx.make_data(m).replace(qpos=jnp.asarray(sq, jnp.float32), qvel=jnp.asarray(sv, jnp.float32), ctrl=jnp.asarray(sc, jnp.float32),
+                                 qacc_warmstart=jnp.asarray(sw, jnp.float32))
+    d = jax.jit(mjx.forward)(m, d)
+    stage = {f"stage_{f}": np.asarray(getattr(d, f)) for f in STAGES if hasattr(d, f)}
+    if hasattr(d, "contact"):
+        stage.update(stage_contact_dist=np.asarray(d.contact.dist), stage_contact_pos=np.asarray(d.contact.pos), stage_contact_frame=np.asarray(d.contact.frame))
+    stage.update(stage_in_qpos=sq, stage_in_qvel=sv, stage_in_ctrl=sc, stage_in_qacc_warmstart=sw)
     # the compiled MjModel itself, field by field (MuJoCo's own layout): pins this repo's MJCF compiler (mj_setConst constants,
     # defaults, frames) and its mujoco.MjModel adapter through tests/test_model_io.py::test_mujoco_model_dump_if_present
     fields = ("body_parentid body_rootid body_weldid body_jntnum body_jntadr body_dofnum body_dofadr body_pos body_quat body_ipos body_iquat "
@@ -61,5 +82,5 @@ for name, (rel, key, kw) in MODELS.items():
     model["model_stat_meaninertia"] = float(mj_model.stat.meaninertia)
     np.savez_compressed(ROOT / "tests/golden" / f"mjx_{name}.npz", x0=x0, us=us, xs=xs, opt_timestep=mj_model.opt.timestep,
                         opt_iterations=mj_model.opt.iterations, opt_ls_iterations=mj_model.opt.ls_iterations,
-                        opt_disableflags=mj_model.opt.disableflags, mujoco_version=mujoco.__version__, **model)
+                        opt_disableflags=mj_model.opt.disableflags, mujoco_version=mujoco.__version__, **model, **stage)
     print("wrote", name, xs.shape)

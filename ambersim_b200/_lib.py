@@ -85,6 +85,13 @@ def lib():
     return L
 
 
+def xchg_handle_bytes() -> int:
+    """ABR_XCHG_HANDLE_BYTES of include/abr.h (the header is the single source of the ABI)."""
+    import re
+
+    return int(re.search(r"#define ABR_XCHG_HANDLE_BYTES (\d+)", _abi.HEADER.read_text()).group(1))
+
+
 def check(rc: int) -> None:
     if rc != ABR_OK:
         msg = lib().abr_last_error().decode()

@@ -89,8 +89,12 @@ __global__ void __launch_bounds__(256) k_xchg_merge(const XchgArgs A) {
     }
   }
   __syncthreads();
-  if (s_timeout) {  // a peer never arrived: report instead of hanging (status word read back by the host wrapper on request)
+  if (s_timeout) {  // a peer never arrived: report instead of hanging. The outputs carry a sentinel (cost +inf, id -1, zeros) so
+                    // that a caller who does not poll abr_xchg_timed_out can never mistake stale memory for a winner
     if (threadIdx.x == 0) reinterpret_cast<unsigned*>(own)[2 * kMaxRanks] = A.epoch;
+    for (int b = threadIdx.x; b < A.B; b += blockDim.x) { A.cost_out[b] = INFINITY; A.idx_out[b] = -1; }
+    if (A.us_out) for (size_t i = threadIdx.x; i < (size_t)A.B * A.nus; i += blockDim.x) A.us_out[i] = 0.f;
+    if (A.xs_out) for (size_t i = threadIdx.x; i < (size_t)A.B * A.nxs; i += blockDim.x) A.xs_out[i] = 0.f;
     return;
   }
   for (int b = 0; b < A.B; b++) {
@@ -118,6 +122,7 @@ struct AbrXchg {
   bool opened[kMaxRanks] = {};
   bool connected = false;
   unsigned epoch = 0;
+  bool poisoned = false;  // a call timed out: the epoch-parity double buffering no longer protects the records
 };
 
 extern "C" {
@@ -128,7 +133,10 @@ int abr_xchg_create(int device, int nranks, int rank, size_t max_record_floats, 
     return set_error(ABR_EINVAL, "abr_xchg_create: bad sizes (1..8 ranks of one box)");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return set_error(ABR_ENODEVICE, "abr_xchg_create: no CUDA device");
+  int dev_before = -1;
+  cudaGetDevice(&dev_before);
   XCK(cudaSetDevice(device));
+  struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{dev_before};
   AbrXchg* x = new AbrXchg();
   x->device = device; x->R = nranks; x->rank = rank;
   x->slot_floats = (max_record_floats + 31) / 32 * 32;
@@ -142,8 +150,16 @@ int abr_xchg_create(int device, int nranks, int rank, size_t max_record_floats, 
     delete x;
     return set_error(ABR_ECUDA, std::string("abr_xchg_create: ") + cudaGetErrorString(e));
   }
-  static_assert(sizeof(cudaIpcMemHandle_t) == ABR_XCHG_HANDLE_BYTES, "handle size");
+  static_assert(sizeof(cudaIpcMemHandle_t) + sizeof(cudaUUID_t) == ABR_XCHG_HANDLE_BYTES, "handle size");
   memcpy(handle_out, &h, sizeof(h));
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) {
+    cudaFree(x->own);
+    delete x;
+    return set_error(ABR_ECUDA, std::string("abr_xchg_create: ") + cudaGetErrorString(e));
+  }
+  memcpy(handle_out + sizeof(h), &prop.uuid, sizeof(cudaUUID_t));  // lets abr_xchg_connect refuse two ranks on one GPU
   x->peer[rank] = x->own;
   *out = x;
   return ABR_OK;
@@ -151,6 +167,15 @@ int abr_xchg_create(int device, int nranks, int rank, size_t max_record_floats, 
 
 int abr_xchg_connect(AbrXchg* x, const unsigned char* handles) {
   if (!x || !handles) return set_error(ABR_EINVAL, "abr_xchg_connect: null argument");
+  // The kernel spin-waits for its peers' records: two ranks sharing one GPU could wait on each other forever (their kernels
+  // need not be co-resident). One process per GPU is the contract; refuse anything else.
+  for (int a = 0; a < x->R; a++)
+    for (int b = a + 1; b < x->R; b++)
+      if (memcmp(handles + (size_t)a * ABR_XCHG_HANDLE_BYTES + sizeof(cudaIpcMemHandle_t),
+                 handles + (size_t)b * ABR_XCHG_HANDLE_BYTES + sizeof(cudaIpcMemHandle_t), sizeof(cudaUUID_t)) == 0)
+        return set_error(ABR_EINVAL, "abr_xchg_connect: ranks " + std::to_string(a) + " and " + std::to_string(b) + " are on the same GPU (one rank per GPU)");
+  int dev_before = -1;
+  cudaGetDevice(&dev_before);
   XCK(cudaSetDevice(x->device));
   for (int r = 0; r < x->R; r++) {
     if (r == x->rank || x->opened[r]) continue;
@@ -161,6 +186,7 @@ int abr_xchg_connect(AbrXchg* x, const unsigned char* handles) {
     x->peer[r] = (float*)p; x->opened[r] = true;
   }
   x->connected = true;
+  if (dev_before >= 0) cudaSetDevice(dev_before);
   return ABR_OK;
 }
 
@@ -170,6 +196,9 @@ int abr_xchg_merge_best_dev(AbrXchg* x, const float* best_cost, const int* best_
   if (B <= 0 || nxs < 0 || nus < 0 || (nxs > 0 && !xs_star) || (nus > 0 && !us_star)) return set_error(ABR_EINVAL, "abr_xchg_merge_best_dev: bad sizes");
   if (!x->connected && x->R > 1) return set_error(ABR_EINVAL, "abr_xchg_merge_best_dev: abr_xchg_connect has not been called");
   if ((size_t)B * (2 + nus + nxs) > x->slot_floats) return set_error(ABR_ECAPACITY, "abr_xchg_merge_best_dev: records exceed the capacity given at create");
+  if (x->poisoned) return set_error(ABR_EINVAL, "abr_xchg_merge_best_dev: an earlier call timed out; destroy and re-create the exchange on every rank");
+  int dev_before = -1;
+  cudaGetDevice(&dev_before);
   XCK(cudaSetDevice(x->device));
   x->epoch += 1;
   XchgArgs a;
@@ -181,16 +210,25 @@ int abr_xchg_merge_best_dev(AbrXchg* x, const float* best_cost, const int* best_
   a.xs_out = xs_out; a.us_out = us_out; a.idx_out = idx_out; a.cost_out = cost_out;
   a.spin_cycles = 4000000000LL;  // about 2 s at 1.9 GHz: a peer that never arrives is reported, not waited for forever
   k_xchg_merge<<<x->R, 256, 0, (cudaStream_t)stream>>>(a);
-  XCK(cudaGetLastError());
+  const cudaError_t le = cudaGetLastError();
+  if (dev_before >= 0) cudaSetDevice(dev_before);
+  if (le != cudaSuccess) return set_error(ABR_ECUDA, std::string("k_xchg_merge: ") + cudaGetErrorString(le));
   return ABR_OK;
 }
 
 int abr_xchg_timed_out(AbrXchg* x, int* timed_out) {
   if (!x || !timed_out) return set_error(ABR_EINVAL, "abr_xchg_timed_out: null argument");
+  int dev_before = -1;
+  cudaGetDevice(&dev_before);
   XCK(cudaSetDevice(x->device));
   unsigned v = 0;
   XCK(cudaMemcpy(&v, reinterpret_cast<unsigned*>(x->own) + 2 * kMaxRanks, sizeof(v), cudaMemcpyDeviceToHost));
-  *timed_out = v != 0 ? 1 : 0;
+  if (v != 0) {  // read-and-clear: the status word reports each timeout once; the handle refuses further exchanges
+    x->poisoned = true;
+    XCK(cudaMemset(reinterpret_cast<unsigned*>(x->own) + 2 * kMaxRanks, 0, sizeof(unsigned)));
+  }
+  if (dev_before >= 0) cudaSetDevice(dev_before);
+  *timed_out = (v != 0 || x->poisoned) ? 1 : 0;
   return ABR_OK;
 }
 

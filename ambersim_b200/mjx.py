@@ -118,6 +118,9 @@ class Model:
         """`model.replace(opt=model.opt.replace(...))` (tests/trajopt/test_predictive_sampler.py:22-31)."""
         m = Model(self._mj, opt=kw.pop("opt", self.opt))
         m._lanes = self._lanes
+        for f in _MODEL_FIELDS:  # start from THIS model's fields, so chained replaces keep earlier overrides
+            setattr(m, f, getattr(self, f))
+        m.stat = self.stat
         for k, v in kw.items():
             if k not in _MODEL_FIELDS:
                 raise AttributeError(f"Model has no field {k!r}")

@@ -45,18 +45,20 @@ def merge_best(best_cost: torch.Tensor, best_idx: torch.Tensor, xs_star: torch.T
         return xs_star, us_star, best_idx, best_cost
     R = dist.get_world_size(group)
     B = best_cost.shape[0]
-    rec = torch.cat((best_cost.reshape(B, 1).float(), best_idx.reshape(B, 1).float(),
+    # the global sample id travels as its int32 BITS inside the float record (exact for every id; a float32 value would
+    # collide above 2^24 samples), as the peer-memory kernel does (abr_xchg.cu)
+    rec = torch.cat((best_cost.reshape(B, 1).float(), best_idx.reshape(B, 1).to(torch.int32).view(torch.float32),
                      us_star.reshape(B, -1).float(), xs_star.reshape(B, -1).float()), dim=1).contiguous()
     flat = torch.empty((R * B, rec.shape[1]), dtype=rec.dtype, device=rec.device)
     dist.all_gather_into_tensor(flat, rec, group=group)  # concatenated layout works on nccl and gloo
     out = flat.reshape(R, B, rec.shape[1])
     costs = out[:, :, 0]
-    idx = out[:, :, 1].to(torch.int64)
+    idx = out[:, :, 1].contiguous().view(torch.int32).to(torch.int64)
     pick = first_min_index(costs, idx)  # (B,)
     sel = out[pick, torch.arange(B, device=rec.device)]  # (B, rec)
     nu_n = us_star[0].numel()
     return (sel[:, 2 + nu_n:].reshape(xs_star.shape).to(xs_star.dtype), sel[:, 2:2 + nu_n].reshape(us_star.shape).to(us_star.dtype),
-            sel[:, 1].to(best_idx.dtype), sel[:, 0].to(best_cost.dtype))
+            sel[:, 1].contiguous().view(torch.int32).to(best_idx.dtype), sel[:, 0].to(best_cost.dtype))
 
 
 class PeerExchange:
@@ -74,15 +76,22 @@ class PeerExchange:
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.device = torch.device(device)
         self._h = C.c_void_p()
-        handle = C.create_string_buffer(64)
-        _lib.check(self._L.abr_xchg_create(self.device.index or 0, self.world, self.rank, int(capacity), C.byref(self._h), handle))
+        if self.device.type != "cuda":
+            raise ValueError("PeerExchange needs a CUDA device")
+        dev_index = torch.cuda.current_device() if self.device.index is None else self.device.index
+        self.device = torch.device("cuda", dev_index)
+        handle = C.create_string_buffer(_lib.xchg_handle_bytes())
+        _lib.check(self._L.abr_xchg_create(dev_index, self.world, self.rank, int(capacity), C.byref(self._h), handle))
         handles = [None] * self.world
         dist.all_gather_object(handles, handle.raw, group=group)
-        _lib.check(self._L.abr_xchg_connect(self._h, b"".join(handles)))
+        _lib.check(self._L.abr_xchg_connect(self._h, b"".join(handles)))  # ABR_EINVAL when two ranks share one GPU
         self._group = group
         dist.barrier(group)
 
-    def merge_best(self, best_cost, best_idx, xs_star, us_star):
+    def merge_best(self, best_cost, best_idx, xs_star, us_star, check: bool = True):
+        """check=True reads the winner ids back (one small device->host sync) and raises `TimeoutError` when a peer
+        failed to arrive (the kernel then returns the sentinel id -1 / cost +inf, never stale memory). Latency-critical
+        loops pass check=False and poll `timed_out()` at their own pace."""
         import ctypes as C
 
         from ambersim_b200 import _lib
@@ -94,6 +103,9 @@ class PeerExchange:
         p = lambda t: C.c_void_p(t.data_ptr())
         _lib.check(self._L.abr_xchg_merge_best_dev(self._h, p(cost), p(idx), p(xs), p(us), B, xs.shape[1], us.shape[1], p(xs_o), p(us_o),
                                                    p(idx_o), p(cost_o), C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        if check and bool((idx_o < 0).any()):
+            self.timed_out()  # clears the status word; the handle now refuses further exchanges
+            raise TimeoutError("PeerExchange.merge_best: a peer did not publish its record within ~2 s; re-create the exchange on every rank")
         return xs_o.reshape(xs_star.shape).to(xs_star.dtype), us_o.reshape(us_star.shape).to(us_star.dtype), idx_o.to(best_idx.dtype), cost_o
 
     def timed_out(self) -> bool:
@@ -114,13 +126,14 @@ class PeerExchange:
             self._h = None
 
 
-def sharded_optimize(sampler, params, group=None, exchange: "PeerExchange" = None):
+def sharded_optimize(sampler, params, group=None, exchange: "PeerExchange" = None, check: bool = True, return_info: bool = False):
     """VanillaPredictiveSampler.optimize with `sampler.nsamples` samples split over the ranks.
-    `exchange`: a `PeerExchange` for the winner exchange (default: all_gather through torch.distributed)."""
+    `exchange`: a `PeerExchange` for the winner exchange (default: all_gather through torch.distributed); `check` as in
+    `PeerExchange.merge_best`. return_info adds {"best_idx", "best_cost"} of the global winner."""
     import dataclasses
 
     if not dist.is_initialized():
-        return sampler.optimize(params)
+        return sampler.optimize(params, return_info=return_info)
     rank, R = dist.get_rank(group), dist.get_world_size(group)
     S = int(sampler.nsamples)
     lo, hi = shard_range(S, rank, R)
@@ -132,9 +145,11 @@ def sharded_optimize(sampler, params, group=None, exchange: "PeerExchange" = Non
         xs, us = xs[None], us[None]
         info = {k: (v[None] if hasattr(v, "dim") else v) for k, v in info.items()}
     if exchange is not None:
-        xs, us, idx, cost = exchange.merge_best(info["best_cost"].reshape(-1), info["best_idx"].reshape(-1), xs, us)
+        xs, us, idx, cost = exchange.merge_best(info["best_cost"].reshape(-1), info["best_idx"].reshape(-1), xs, us, check=check)
     else:
         xs, us, idx, cost = merge_best(info["best_cost"].reshape(-1), info["best_idx"].reshape(-1), xs, us, group)
     if not batched:
-        xs, us = xs[0], us[0]
+        xs, us, idx, cost = xs[0], us[0], idx[0], cost[0]
+    if return_info:
+        return xs, us, {"best_idx": idx, "best_cost": cost}
     return xs, us

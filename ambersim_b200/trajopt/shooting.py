@@ -131,9 +131,13 @@ class VanillaPredictiveSamplerParams(ShootingParams):
 
 
 def _seed_of(key) -> int:
+    """An int, or ONE jax-style key (two uint32 words). A batch of keys is rejected: batched problems draw independent
+    noise from the one key through the problem index of the counter (the reference vmaps over split keys instead)."""
     if isinstance(key, (int, np.integer)):
         return int(key) & 0xFFFFFFFFFFFFFFFF
     k = key.detach().cpu().numpy() if isinstance(key, torch.Tensor) else np.asarray(key)
+    if k.size > 2:
+        raise ValueError(f"key must be an int or one (2,) key, got shape {tuple(k.shape)}: pass one key for the whole batch")
     k = k.reshape(-1).astype(np.uint64)
     if k.size == 1:
         return int(k[0])
@@ -166,6 +170,9 @@ class VanillaPredictiveSampler(ShootingAlgorithm):
             return self._optimize_generic(params, return_info)
         on_device = isinstance(params.us_guess, torch.Tensor) and params.us_guess.is_cuda
         seed = _seed_of(params.key)
+        ug_nd = params.us_guess.dim() if isinstance(params.us_guess, torch.Tensor) else np.ndim(params.us_guess)
+        if ug_nd not in (2, 3):
+            raise ValueError(f"us_guess must be (N, nu) or (B, N, nu), got {ug_nd} dimensions")
         if on_device:
             dev = params.us_guess.device
             ug = params.us_guess.to(torch.float32)

@@ -447,21 +447,47 @@ def main():
         sharded = None
         if world > 1:
             # ---- C4 on N GPUs: samples sharded by global id, winners exchanged by ONE peer-memory kernel per rank (abr_xchg_*)
-            from ambersim_b200.parallel import PeerExchange, sharded_optimize
+            from ambersim_b200.parallel import PeerExchange, shard_range, sharded_optimize
 
             xch = PeerExchange(device, capacity=2 + 32 * mj.nu + 33 * (mj.nq + mj.nv))
             prm_s = VanillaPredictiveSamplerParams(key=3, x0=torch.tensor(q0, dtype=torch.float32, device=device),
                                                    us_guess=torch.tensor(mj.key_ctrl("home"), dtype=torch.float32, device=device).repeat(32, 1))
+            # correctness first (driver-visible): the sharded solve must equal the single-GPU solve BIT FOR BIT on every rank,
+            # through both exchanges (peer-memory kernel, NCCL all-gather). The start is off the goal and the guess is poor, so
+            # the winner is a noised sample that can live on any rank.
+            rs = np.random.default_rng(0)
+            xq = q0.copy()
+            xq[7:19] += rs.uniform(-0.15, 0.15, 12)
+            gq = np.clip(mj.key_ctrl("home") + 0.3 * rs.standard_normal((32, mj.nu)), mj.actuator_ctrlrange[:, 0], mj.actuator_ctrlrange[:, 1])
+            prm_c = VanillaPredictiveSamplerParams(key=11, x0=torch.tensor(xq, dtype=torch.float32, device=device),
+                                                   us_guess=torch.tensor(gq, dtype=torch.float32, device=device))
+            equal, sharded_ok = {}, True
+            for S in (4096, 65536):
+                ps_c = VanillaPredictiveSampler(model=m, cost_function=cf, nsamples=S, stdev=0.2)
+                xs1, us1, i1 = ps_c.optimize(prm_c, return_info=True)  # every rank also solves the whole problem alone
+                res = {}
+                for name, kw in (("peer_memory", dict(exchange=xch)), ("nccl_all_gather", {})):
+                    xsN, usN, iN = sharded_optimize(ps_c, prm_c, return_info=True, **kw)
+                    same = torch.equal(xs1, xsN) and torch.equal(us1, usN) and int(i1["best_idx"]) == int(iN["best_idx"]) and \
+                        float(i1["best_cost"]) == float(iN["best_cost"])
+                    flag = torch.tensor([1 if same else 0], device=device)
+                    dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # ... on EVERY rank
+                    res[name] = bool(int(flag))
+                    sharded_ok = sharded_ok and res[name]
+                best = int(i1["best_idx"])
+                res["winner_idx"] = best
+                res["winner_rank"] = next(r for r in range(world) if shard_range(S, r, world)[0] <= best < shard_range(S, r, world)[1])
+                equal[str(S)] = res
             sharded = {}
-            for S in (4096, 65536, 1048576):
+            for S in (1024, 4096, 16384, 65536, 262144, 1048576):
                 ps_s = VanillaPredictiveSampler(model=m, cost_function=cf, nsamples=S, stdev=0.1)
                 for _ in range(3):
-                    sharded_optimize(ps_s, prm_s, exchange=xch)
+                    sharded_optimize(ps_s, prm_s, exchange=xch, check=False)
                 barrier()
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record(stream)
                 for _ in range(5):
-                    sharded_optimize(ps_s, prm_s, exchange=xch)
+                    sharded_optimize(ps_s, prm_s, exchange=xch, check=False)
                 b.record(stream)
                 torch.cuda.synchronize(device)
                 t = torch.tensor([a.elapsed_time(b) / 5], device=device)
@@ -498,6 +524,30 @@ def main():
             sharded_big = {"world_steps_per_s": rate_b, "worlds_per_gpu": WB, "horizon": NB, "frac_of_ffma_peak": F_WS * rate_b / world / 1e12 / tf.value,
                            "costs_finite": bool(torch.isfinite(cb).all())}
             del xb, ub, cb
+            # ---- C5 (BASELINE configs[4]) on every GPU at once: 8192 envs per GPU with auto-reset, whole env step in one launch
+            from ambersim_b200.rl.wrappers import FusedQuadraticTaskEnv, QuadraticTaskEnv
+
+            E5, T5, NA5 = 8192, 600, 200
+            tenv = FusedQuadraticTaskEnv(QuadraticTaskEnv(mj, cf, mj.key_qpos("home"), num_envs=E5, z_min=0.1, jitter=JITTER), 1000)
+            tenv.reset(7 + rank)
+            acts = torch.minimum(torch.maximum(torch.tensor(mj.key_ctrl("home"), **fb) + CTRL_NOISE * torch.randn((NA5, E5, mj.nu), generator=gb, **fb),
+                                               limb_[:, 0]), limb_[:, 1])
+
+            def env_loop():
+                for t_ in range(T5):
+                    tenv.step(None, acts[t_ % NA5])
+
+            env_loop()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            env_loop()
+            b.record(stream)
+            torch.cuda.synchronize(device)
+            t = torch.tensor([a.elapsed_time(b)], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            c5_rate = world * E5 * T5 / (float(t) * 1e-3)
+            del tenv, acts
         if rank == 0:
             # ---- second half of BASELINE's metric: 4096-sample x 32-step predictive-sampling solve latency
             ps = VanillaPredictiveSampler(model=m, cost_function=cf, nsamples=4096, stdev=0.1)
@@ -540,6 +590,10 @@ def main():
                             "vps_note": "VanillaPredictiveSampler.optimize, device-resident inputs: rollouts + argmin + winner gather (3 launches)"}
             if sharded is not None:
                 out["extra"]["c4_sharded_solve_ms_by_samples_x32"] = sharded
+                out["extra"]["sharded_equals_single"] = equal
+                out["extra"]["sharded_equals_single_all"] = sharded_ok
+                out["extra"]["c5_env_steps_per_s"] = {"value": c5_rate, "envs_per_gpu": 8192, "n_gpus": world, "launches_per_env_step": 1,
+                                                      "note": "replicas: 8192 envs per GPU with auto-reset, max-over-ranks device time"}
                 out["extra"]["barkour_65536_per_gpu_x250"] = sharded_big
                 out["extra"]["c4_sharded_note"] = f"samples split over {world} GPUs by global id; one peer-memory exchange kernel per rank (no NCCL call)"
             if world == 1:  # the other configs and the CPU baseline are reported by the single-GPU run only
@@ -553,6 +607,8 @@ def main():
         dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(out), flush=True)
+    if world > 1 and not args.no_extra and not sharded_ok:
+        sys.exit(3)  # the sharded solve disagreed with the single-GPU solve: the line above says where
 
 
 if __name__ == "__main__":

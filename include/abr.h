@@ -334,8 +334,13 @@ int abr_mpc_dev(AbrModel* m, const AbrCost* cost, float* x, float* us_guess, uns
  * launch stores them into all peers' buffers (P2P stores + system-scope release flags), waits for the R records of
  * this call and writes the global first minimum (NaN minimal, lowest sample id wins ties) to the outputs: identical
  * on every rank, no NCCL call, no host round trip. max_record_floats bounds B * (2 + nxs + nus).
- * abr_xchg_timed_out reports (after a stream sync) whether a peer failed to arrive within about 2 s. */
-#define ABR_XCHG_HANDLE_BYTES 64
+ * A peer that fails to arrive within about 2 s is reported, not waited for: that call's outputs are a sentinel
+ * (cost +inf, idx -1, zeros), abr_xchg_timed_out (which synchronises the device) returns 1 once and clears the
+ * status word, and the handle refuses further exchanges (ABR_EINVAL): the epoch-parity double buffering no
+ * longer protects the records, so every rank destroys and re-creates its exchange.
+ * abr_xchg_connect returns ABR_EINVAL when two ranks sit on the same GPU (the kernel spin-waits across ranks).
+ * None of these calls changes the caller's current CUDA device. */
+#define ABR_XCHG_HANDLE_BYTES 80 /* cudaIpcMemHandle_t (64) + the GPU's UUID (16): abr_xchg_connect refuses two ranks on one GPU */
 typedef struct AbrXchg AbrXchg;
 int abr_xchg_create(int device, int nranks, int rank, size_t max_record_floats, AbrXchg** out,
                     unsigned char* handle_out /* [ABR_XCHG_HANDLE_BYTES] */);

@@ -69,7 +69,7 @@ def test_argument_validation_needs_no_device():
     assert L.abr_model_describe(None, C.create_string_buffer(8), 8) == _lib.ABR_EINVAL
     assert L.abr_predictive_sample_dev(None, None, None, None, None, 0, 1, 8, 4, 0.1, 0, 8, None, None, None, None, None, None) == _lib.ABR_EINVAL
     assert L.abr_mpc_dev(None, None, None, None, 0, 8, 4, 0.1, 2, None, None, None, None, None) == _lib.ABR_EINVAL
-    handle = C.create_string_buffer(64)
+    handle = C.create_string_buffer(_lib.xchg_handle_bytes())
     x = C.c_void_p()
     for nranks, rank, cap in ((0, 0, 16), (9, 0, 16), (2, 2, 16), (2, -1, 16), (2, 0, 0)):
         assert L.abr_xchg_create(0, nranks, rank, cap, C.byref(x), handle) == _lib.ABR_EINVAL
@@ -82,6 +82,6 @@ def test_argument_validation_needs_no_device():
 @pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful on a box without a GPU")
 def test_exchange_refuses_without_a_device():
     L = _lib.lib()
-    handle = C.create_string_buffer(64)
+    handle = C.create_string_buffer(_lib.xchg_handle_bytes())
     x = C.c_void_p()
     assert L.abr_xchg_create(0, 2, 0, 16, C.byref(x), handle) == _lib.ABR_ENODEVICE

@@ -822,7 +822,7 @@ def test_peer_exchange_single_rank_and_argument_checks():
 
     L = _lib.lib()
     B, nxs, nus = 3, 33 * 37, 32 * 12
-    x, handle = C.c_void_p(), C.create_string_buffer(64)
+    x, handle = C.c_void_p(), C.create_string_buffer(_lib.xchg_handle_bytes())
     _lib.check(L.abr_xchg_create(0, 1, 0, B * (2 + nxs + nus), C.byref(x), handle))
     _lib.check(L.abr_xchg_connect(x, handle.raw))
     p = lambda t: C.c_void_p(t.data_ptr())

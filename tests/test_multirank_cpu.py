@@ -35,7 +35,8 @@ def _worker(rank, world, port, q):
     B, N, nx, nu = 3, 4, 5, 2
     g = torch.Generator().manual_seed(100 + rank)
     cost = torch.tensor([[1.0, 5.0, float("nan")], [0.5, 5.0, 2.0]])[rank]
-    idx = torch.tensor([[3, 10, 8], [40, 33, 41]], dtype=torch.int32)[rank]
+    # column 1 ties on cost with global ids above 2^24 that differ by one: exact only if the id travels as int32 bits
+    idx = torch.tensor([[3, 16777218, 8], [40, 16777217, 41]], dtype=torch.int32)[rank]
     xs, us = torch.randn((B, N + 1, nx), generator=g), torch.randn((B, N, nu), generator=g)
     out = merge_best(cost, idx, xs, us)
     q.put((rank, [t.numpy() for t in out], xs.numpy(), us.numpy()))
@@ -55,9 +56,9 @@ def test_merge_best_two_ranks():
     for a, b in zip(o0, o1):
         assert np.array_equal(a, b, equal_nan=True)  # identical winners on both ranks
     xs, us, idx, cost = o0
-    assert idx.tolist() == [40, 10, 8]  # lower cost; tie -> lower global index; NaN counts as minimal
-    assert np.array_equal(xs[0], xs1[0]) and np.array_equal(xs[1], xs0[1]) and np.array_equal(xs[2], xs0[2])
-    assert np.array_equal(us[0], us1[0]) and np.array_equal(us[1], us0[1])
+    assert idx.tolist() == [40, 16777217, 8]  # lower cost; tie -> lower global index (not representable in float32); NaN counts as minimal
+    assert np.array_equal(xs[0], xs1[0]) and np.array_equal(xs[1], xs1[1]) and np.array_equal(xs[2], xs0[2])
+    assert np.array_equal(us[0], us1[0]) and np.array_equal(us[1], us1[1])
 
 
 def test_philox_known_answers():

@@ -459,24 +459,25 @@ def main():
             xq = q0.copy()
             xq[7:19] += rs.uniform(-0.15, 0.15, 12)
             gq = np.clip(mj.key_ctrl("home") + 0.3 * rs.standard_normal((32, mj.nu)), mj.actuator_ctrlrange[:, 0], mj.actuator_ctrlrange[:, 1])
-            prm_c = VanillaPredictiveSamplerParams(key=11, x0=torch.tensor(xq, dtype=torch.float32, device=device),
-                                                   us_guess=torch.tensor(gq, dtype=torch.float32, device=device))
             equal, sharded_ok = {}, True
             for S in (4096, 65536):
                 ps_c = VanillaPredictiveSampler(model=m, cost_function=cf, nsamples=S, stdev=0.2)
-                xs1, us1, i1 = ps_c.optimize(prm_c, return_info=True)  # every rank also solves the whole problem alone
-                res = {}
-                for name, kw in (("peer_memory", dict(exchange=xch)), ("nccl_all_gather", {})):
-                    xsN, usN, iN = sharded_optimize(ps_c, prm_c, return_info=True, **kw)
-                    same = torch.equal(xs1, xsN) and torch.equal(us1, usN) and int(i1["best_idx"]) == int(iN["best_idx"]) and \
-                        float(i1["best_cost"]) == float(iN["best_cost"])
-                    flag = torch.tensor([1 if same else 0], device=device)
-                    dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # ... on EVERY rank
-                    res[name] = bool(int(flag))
-                    sharded_ok = sharded_ok and res[name]
-                best = int(i1["best_idx"])
-                res["winner_idx"] = best
-                res["winner_rank"] = next(r for r in range(world) if shard_range(S, r, world)[0] <= best < shard_range(S, r, world)[1])
+                res = {"peer_memory": True, "nccl_all_gather": True, "winner_idx": [], "winner_rank": []}
+                for key_c in (11, 12, 13, 14):  # several noise streams, so that winners land on different ranks
+                    prm_c = VanillaPredictiveSamplerParams(key=key_c, x0=torch.tensor(xq, dtype=torch.float32, device=device),
+                                                           us_guess=torch.tensor(gq, dtype=torch.float32, device=device))
+                    xs1, us1, i1 = ps_c.optimize(prm_c, return_info=True)  # every rank also solves the whole problem alone
+                    for name, kw in (("peer_memory", dict(exchange=xch)), ("nccl_all_gather", {})):
+                        xsN, usN, iN = sharded_optimize(ps_c, prm_c, return_info=True, **kw)
+                        same = torch.equal(xs1, xsN) and torch.equal(us1, usN) and int(i1["best_idx"]) == int(iN["best_idx"]) and \
+                            float(i1["best_cost"]) == float(iN["best_cost"])
+                        flag = torch.tensor([1 if same else 0], device=device)
+                        dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # ... on EVERY rank
+                        res[name] = res[name] and bool(int(flag))
+                        sharded_ok = sharded_ok and res[name]
+                    best = int(i1["best_idx"])
+                    res["winner_idx"].append(best)
+                    res["winner_rank"].append(next(r for r in range(world) if shard_range(S, r, world)[0] <= best < shard_range(S, r, world)[1]))
                 equal[str(S)] = res
             sharded = {}
             for S in (1024, 4096, 16384, 65536, 262144, 1048576):

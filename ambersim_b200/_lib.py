@@ -71,6 +71,8 @@ def lib():
     L.abr_forward_dev.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, vp]
     L.abr_env_step_dev.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp]
     L.abr_env_set_randomization.argtypes = [vp, vp, C.c_int]
+    L.abr_forward_fields_dev.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, C.POINTER(S["AbrDataFields"]), vp]
+    L.abr_env_step_fields_dev.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.POINTER(S["AbrDataFields"]), vp]
     L.abr_env_task_step_dev.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, C.c_float, C.c_int, vp, vp, vp, vp, vp, vp]
     L.abr_xchg_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_size_t, C.POINTER(vp), C.c_char_p]
     L.abr_xchg_connect.argtypes = [vp, C.c_char_p]

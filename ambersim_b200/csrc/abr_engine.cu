@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -18,6 +19,7 @@
 #include "abr_layout.h"
 #include "abr_kernels.cuh"
 #include "abr_limb.cuh"
+#include "abr_hand.cuh"
 
 using namespace abr;
 
@@ -436,6 +438,66 @@ static int build_blob(const HostModel& m, bool alias, Layout& L, std::vector<flo
     L.i_cd_adr = P.addi(cd_adr); L.i_cd_dof = P.addi(cd_dof);
   }
 
+  // ---- per-lane table constants shared by the limb (abr_limb.cuh) and hand (abr_hand.cuh) kernels
+  using SetF = std::function<void(int, int, float)>;
+  using SetI = std::function<void(int, int, int)>;
+  auto fold_body = [&](const SetF& setf, int sb, int g, int body, bool has_joint) {
+    // constants of the body folded into its PARENT frame (double precision, once): see the kinematics block of abr_limb.cuh
+    const double bq[4] = {m.body_quat[4 * body], m.body_quat[4 * body + 1], m.body_quat[4 * body + 2], m.body_quat[4 * body + 3]};
+    const double iq[4] = {m.body_iquat[4 * body], m.body_iquat[4 * body + 1], m.body_iquat[4 * body + 2], m.body_iquat[4 * body + 3]};
+    auto qmat = [](const double* q, double* R) {
+      R[0] = q[0] * q[0] + q[1] * q[1] - q[2] * q[2] - q[3] * q[3]; R[1] = 2 * (q[1] * q[2] - q[0] * q[3]); R[2] = 2 * (q[1] * q[3] + q[0] * q[2]);
+      R[3] = 2 * (q[1] * q[2] + q[0] * q[3]); R[4] = q[0] * q[0] - q[1] * q[1] + q[2] * q[2] - q[3] * q[3]; R[5] = 2 * (q[2] * q[3] - q[0] * q[1]);
+      R[6] = 2 * (q[1] * q[3] - q[0] * q[2]); R[7] = 2 * (q[2] * q[3] + q[0] * q[1]); R[8] = q[0] * q[0] - q[1] * q[1] - q[2] * q[2] + q[3] * q[3];
+    };
+    double Rb[9], Ri[9];
+    qmat(bq, Rb); qmat(iq, Ri);
+    double jp[3] = {0, 0, 0}, jx[3] = {0, 0, 0};
+    if (has_joint) {
+      const int j = m.body_jntadr[body];
+      for (int i = 0; i < 3; i++) { jp[i] = m.jnt_pos[3 * j + i]; jx[i] = m.jnt_axis[3 * j + i]; }
+    }
+    for (int i = 0; i < 3; i++) {
+      setf(sb + i, g, (float)(m.body_pos[3 * body + i] + Rb[3 * i] * jp[0] + Rb[3 * i + 1] * jp[1] + Rb[3 * i + 2] * jp[2]));
+      setf(sb + 21 + i, g, (float)(Rb[3 * i] * jx[0] + Rb[3 * i + 1] * jx[1] + Rb[3 * i + 2] * jx[2]));
+      setf(sb + 7 + i, g, m.body_ipos[3 * body + i]);
+    }
+    for (int i = 0; i < 4; i++) setf(sb + 3 + i, g, (float)bq[i]);
+    // body_quat o (0, axis)
+    setf(sb + 10, g, (float)(-bq[1] * jx[0] - bq[2] * jx[1] - bq[3] * jx[2]));
+    setf(sb + 11, g, (float)(bq[0] * jx[0] + bq[2] * jx[2] - bq[3] * jx[1]));
+    setf(sb + 12, g, (float)(bq[0] * jx[1] - bq[1] * jx[2] + bq[3] * jx[0]));
+    setf(sb + 13, g, (float)(bq[0] * jx[2] + bq[1] * jx[1] - bq[2] * jx[0]));
+    setf(sb + 14, g, m.body_mass[body]);
+    // inertia tensor in the body frame: Ri diag(inertia) Ri'
+    const double in[3] = {m.body_inertia[3 * body], m.body_inertia[3 * body + 1], m.body_inertia[3 * body + 2]};
+    const int ra[6] = {0, 1, 2, 0, 0, 1}, cb[6] = {0, 1, 2, 1, 2, 2};
+    for (int e = 0; e < 6; e++) {
+      double t = 0;
+      for (int k = 0; k < 3; k++) t += Ri[3 * ra[e] + k] * in[k] * Ri[3 * cb[e] + k];
+      setf(sb + 15 + e, g, (float)t);
+    }
+  };
+  auto fold_joint = [&](const SetF& setf, const SetI& seti, int sj, int si, int g, int body) {
+    const int j = m.body_jntadr[body], d = m.jnt_dofadr[j], qa = m.jnt_qposadr[j];
+    for (int i = 0; i < 3; i++) { setf(sj + i, g, m.jnt_pos[3 * j + i]); setf(sj + 3 + i, g, m.jnt_axis[3 * j + i]); }
+    setf(sj + 6, g, m.qpos0[qa]); setf(sj + 7, g, m.qpos_spring[qa]); setf(sj + 8, g, m.jnt_stiffness[j]);
+    setf(sj + 9, g, m.dof_damping[d]); setf(sj + 10, g, m.dof_armature[d]);
+    setf(sj + 11, g, m.jnt_range[2 * j]); setf(sj + 12, g, m.jnt_range[2 * j + 1]); setf(sj + 13, g, m.jnt_margin[j]);
+    int flags = m.jnt_type[j] == ABR_JNT_HINGE ? limb::kJHinge : limb::kJSlide;
+    if (dof_limrow[d] >= 0) {
+      flags |= limb::kJLimited;
+      for (int i = 0; i < kRowPrm; i++) setf(sj + 14 + i, g, lim_prm[(size_t)kRowPrm * dof_limrow[d] + i]);
+    }
+    int act = -1;
+    if (dof_actnum[d] == 1) {
+      act = dof_act[dof_actadr[d]];
+      flags |= limb::kJAct | (act_flags[act] << limb::kJActShift);
+      for (int i = 0; i < kActPrm; i++) setf(sj + 24 + i, g, act_prm[(size_t)kActPrm * act + i]);
+    }
+    seti(si, g, flags); seti(si + 1, g, d); seti(si + 2, g, qa); seti(si + 3, g, act);
+  };
+
   // ---- limb (path) decomposition: tables of abr_limb.cuh
   L.limb_ok = 0;
   {
@@ -512,41 +574,7 @@ static int build_blob(const HostModel& m, bool alias, Layout& L, std::vector<flo
             if (g == lane0[body]) ownbits |= 1 << p;
             lvlbits |= lv << (2 * p);
             if (lv > ((mxbits >> (2 * p)) & 3)) mxbits = (mxbits & ~(3 << (2 * p))) | (lv << (2 * p));
-            // constants of the body folded into its PARENT frame (double precision, once): see the kinematics block of abr_limb.cuh
-            const double bq[4] = {m.body_quat[4 * body], m.body_quat[4 * body + 1], m.body_quat[4 * body + 2], m.body_quat[4 * body + 3]};
-            const double iq[4] = {m.body_iquat[4 * body], m.body_iquat[4 * body + 1], m.body_iquat[4 * body + 2], m.body_iquat[4 * body + 3]};
-            auto qmat = [](const double* q, double* R) {
-              R[0] = q[0] * q[0] + q[1] * q[1] - q[2] * q[2] - q[3] * q[3]; R[1] = 2 * (q[1] * q[2] - q[0] * q[3]); R[2] = 2 * (q[1] * q[3] + q[0] * q[2]);
-              R[3] = 2 * (q[1] * q[2] + q[0] * q[3]); R[4] = q[0] * q[0] - q[1] * q[1] + q[2] * q[2] - q[3] * q[3]; R[5] = 2 * (q[2] * q[3] - q[0] * q[1]);
-              R[6] = 2 * (q[1] * q[3] - q[0] * q[2]); R[7] = 2 * (q[2] * q[3] + q[0] * q[1]); R[8] = q[0] * q[0] - q[1] * q[1] - q[2] * q[2] + q[3] * q[3];
-            };
-            double Rb[9], Ri[9];
-            qmat(bq, Rb); qmat(iq, Ri);
-            double jp[3] = {0, 0, 0}, jx[3] = {0, 0, 0};
-            if (p > 0) {
-              const int j = m.body_jntadr[body];
-              for (int i = 0; i < 3; i++) { jp[i] = m.jnt_pos[3 * j + i]; jx[i] = m.jnt_axis[3 * j + i]; }
-            }
-            for (int i = 0; i < 3; i++) {
-              setf(sb + i, g, (float)(m.body_pos[3 * body + i] + Rb[3 * i] * jp[0] + Rb[3 * i + 1] * jp[1] + Rb[3 * i + 2] * jp[2]));
-              setf(sb + 21 + i, g, (float)(Rb[3 * i] * jx[0] + Rb[3 * i + 1] * jx[1] + Rb[3 * i + 2] * jx[2]));
-              setf(sb + 7 + i, g, m.body_ipos[3 * body + i]);
-            }
-            for (int i = 0; i < 4; i++) setf(sb + 3 + i, g, (float)bq[i]);
-            // body_quat o (0, axis)
-            setf(sb + 10, g, (float)(-bq[1] * jx[0] - bq[2] * jx[1] - bq[3] * jx[2]));
-            setf(sb + 11, g, (float)(bq[0] * jx[0] + bq[2] * jx[2] - bq[3] * jx[1]));
-            setf(sb + 12, g, (float)(bq[0] * jx[1] - bq[1] * jx[2] + bq[3] * jx[0]));
-            setf(sb + 13, g, (float)(bq[0] * jx[2] + bq[1] * jx[1] - bq[2] * jx[0]));
-            setf(sb + 14, g, m.body_mass[body]);
-            // inertia tensor in the body frame: Ri diag(inertia) Ri'
-            const double in[3] = {m.body_inertia[3 * body], m.body_inertia[3 * body + 1], m.body_inertia[3 * body + 2]};
-            const int ra[6] = {0, 1, 2, 0, 0, 1}, cb[6] = {0, 1, 2, 1, 2, 2};
-            for (int e = 0; e < 6; e++) {
-              double t = 0;
-              for (int k = 0; k < 3; k++) t += Ri[3 * ra[e] + k] * in[k] * Ri[3 * cb[e] + k];
-              setf(sb + 15 + e, g, (float)t);
-            }
+            fold_body(setf, sb, g, body, p > 0);
           } else {
             ownbits |= 1 << p;  // padding is private
             setf(sb + 3, g, 1.f);
@@ -555,23 +583,7 @@ static int build_blob(const HostModel& m, bool alias, Layout& L, std::vector<flo
           const int sj = mp.jnt(p), si = mp.ijnt(p);
           for (int i = 0; i < kRowPrm; i++) setf(sj + 14 + i, g, benign[i]);
           if (body >= 0) {
-            const int j = m.body_jntadr[body], d = m.jnt_dofadr[j], qa = m.jnt_qposadr[j];
-            for (int i = 0; i < 3; i++) { setf(sj + i, g, m.jnt_pos[3 * j + i]); setf(sj + 3 + i, g, m.jnt_axis[3 * j + i]); }
-            setf(sj + 6, g, m.qpos0[qa]); setf(sj + 7, g, m.qpos_spring[qa]); setf(sj + 8, g, m.jnt_stiffness[j]);
-            setf(sj + 9, g, m.dof_damping[d]); setf(sj + 10, g, m.dof_armature[d]);
-            setf(sj + 11, g, m.jnt_range[2 * j]); setf(sj + 12, g, m.jnt_range[2 * j + 1]); setf(sj + 13, g, m.jnt_margin[j]);
-            int flags = m.jnt_type[j] == ABR_JNT_HINGE ? limb::kJHinge : limb::kJSlide;
-            if (dof_limrow[d] >= 0) {
-              flags |= limb::kJLimited;
-              for (int i = 0; i < kRowPrm; i++) setf(sj + 14 + i, g, lim_prm[(size_t)kRowPrm * dof_limrow[d] + i]);
-            }
-            int act = -1;
-            if (dof_actnum[d] == 1) {
-              act = dof_act[dof_actadr[d]];
-              flags |= limb::kJAct | (act_flags[act] << limb::kJActShift);
-              for (int i = 0; i < kActPrm; i++) setf(sj + 24 + i, g, act_prm[(size_t)kActPrm * act + i]);
-            }
-            seti(si, g, flags); seti(si + 1, g, d); seti(si + 2, g, qa); seti(si + 3, g, act);
+            fold_joint(setf, seti, sj, si, g, body);
           } else {
             setf(sj + 10, g, 1.f);  // unit armature keeps the padded dof's pivot at 1
             seti(si, g, 0); seti(si + 1, g, -1); seti(si + 2, g, -1); seti(si + 3, g, -1);
@@ -628,6 +640,97 @@ static int build_blob(const HostModel& m, bool alias, Layout& L, std::vector<flo
       L.lg2G = 0;
       while ((1 << L.lg2G) < G) L.lg2G++;
       L.f_ltab = P.addf(T);
+    }
+  }
+
+  // ---- hand decomposition (abr_hand.cuh): fixed-base chains + joint equalities, one lane per chain off a static body
+  L.hand_ok = 0;
+  {
+    bool ok = getenv("ABR_NO_HAND") == nullptr && !L.limb_ok && opt.solver == ABR_SOLVER_NEWTON && opt.integrator == ABR_INT_EULER &&
+              L.ncon == 0 && L.ne <= hand::kNE && nv >= 1 && nb >= 2;
+    std::vector<int> moving(nb, 0), pos_in_chain(nb, 0), lane_of(nb, -1), starts;
+    for (int b = 1; b < nb && ok; b++) {
+      const int par = m.body_parentid[b];
+      if (m.body_jntnum[b] == 0) { ok = !moving[par]; continue; }  // a static body may only hang off static bodies
+      const int j = m.body_jntadr[b];
+      ok = m.body_jntnum[b] == 1 && (m.jnt_type[j] == ABR_JNT_HINGE || m.jnt_type[j] == ABR_JNT_SLIDE);
+      moving[b] = 1;
+      if (moving[par]) { pos_in_chain[b] = pos_in_chain[par] + 1; lane_of[b] = lane_of[par]; }
+      else { pos_in_chain[b] = 1; lane_of[b] = (int)starts.size(); starts.push_back(b); }
+    }
+    for (int b = 1; b < nb && ok; b++) {  // chains do not fork: at most one moving child per moving body
+      if (!moving[b]) continue;
+      int kids = 0;
+      for (int q = 0; q < childnum[b]; q++) kids += moving[child[childadr[b] + q]];
+      ok = kids <= 1 && pos_in_chain[b] <= 3;
+    }
+    for (int d = 0; d < nv && ok; d++) ok = dof_actnum[d] <= 1;
+    ok = ok && !starts.empty() && (int)starts.size() <= hand::kLanes;
+    if (ok) {
+      constexpr int NLh = 3;
+      const hand::Map mp{NLh};
+      const int G = hand::kLanes;  // always four lanes per world: chains padded with dummy lanes (the dense Newton system is of order 4 NL)
+      std::vector<float> T((size_t)mp.total() * limb::kStride, 0.f);
+      auto setf = [&](int slot, int g, float v) { T[(size_t)slot * limb::kStride + g] = v; };
+      auto seti = [&](int slot, int g, int v) { float f; memcpy(&f, &v, 4); T[(size_t)slot * limb::kStride + g] = f; };
+      const float benign[kRowPrm] = {0.f, 0.f, 0.9f, 0.95f, 1000.f, 0.5f, 2.f, 1.f, 2.f, 2.f};
+      // world pose of every static body (double precision, once)
+      std::vector<double> wp(3 * nb, 0.0), wq(4 * nb, 0.0);
+      wq[0] = 1.0;
+      for (int b = 1; b < nb; b++) {
+        if (moving[b]) continue;
+        const int par = m.body_parentid[b];
+        const double* q = &wq[4 * par];
+        const double R[9] = {q[0] * q[0] + q[1] * q[1] - q[2] * q[2] - q[3] * q[3], 2 * (q[1] * q[2] - q[0] * q[3]), 2 * (q[1] * q[3] + q[0] * q[2]),
+                             2 * (q[1] * q[2] + q[0] * q[3]), q[0] * q[0] - q[1] * q[1] + q[2] * q[2] - q[3] * q[3], 2 * (q[2] * q[3] - q[0] * q[1]),
+                             2 * (q[1] * q[3] - q[0] * q[2]), 2 * (q[2] * q[3] + q[0] * q[1]), q[0] * q[0] - q[1] * q[1] - q[2] * q[2] + q[3] * q[3]};
+        for (int i = 0; i < 3; i++)
+          wp[3 * b + i] = wp[3 * par + i] + R[3 * i] * m.body_pos[3 * b] + R[3 * i + 1] * m.body_pos[3 * b + 1] + R[3 * i + 2] * m.body_pos[3 * b + 2];
+        const double a[4] = {q[0], q[1], q[2], q[3]}, c[4] = {m.body_quat[4 * b], m.body_quat[4 * b + 1], m.body_quat[4 * b + 2], m.body_quat[4 * b + 3]};
+        wq[4 * b] = a[0] * c[0] - a[1] * c[1] - a[2] * c[2] - a[3] * c[3];
+        wq[4 * b + 1] = a[0] * c[1] + a[1] * c[0] + a[2] * c[3] - a[3] * c[2];
+        wq[4 * b + 2] = a[0] * c[2] - a[1] * c[3] + a[2] * c[0] + a[3] * c[1];
+        wq[4 * b + 3] = a[0] * c[3] + a[1] * c[2] - a[2] * c[1] + a[3] * c[0];
+      }
+      for (int g = 0; g < limb::kStride; g++) {
+        setf(mp.base() + 3, g, 1.f);
+        if (g < (int)starts.size()) {
+          const int par = m.body_parentid[starts[g]];
+          for (int i = 0; i < 3; i++) setf(mp.base() + i, g, (float)wp[3 * par + i]);
+          for (int i = 0; i < 4; i++) setf(mp.base() + 3 + i, g, (float)wq[4 * par + i]);
+        }
+        for (int p = 1; p <= NLh; p++) {
+          int body = -1;
+          for (int b = 1; b < nb; b++) if (moving[b] && lane_of[b] == g && pos_in_chain[b] == p) body = b;
+          const int sb = mp.body(p), sj = mp.jnt(p), si = mp.ijnt(p);
+          for (int i = 0; i < kRowPrm; i++) setf(sj + 14 + i, g, benign[i]);
+          if (body >= 0) {
+            fold_body(setf, sb, g, body, true);
+            fold_joint(setf, seti, sj, si, g, body);
+          } else {
+            setf(sb + 3, g, 1.f);
+            setf(sj + 10, g, 1.f);  // unit armature keeps the padded dof's pivot at 1
+            seti(si, g, 0); seti(si + 1, g, -1); seti(si + 2, g, -1); seti(si + 3, g, -1);
+          }
+        }
+        for (int r = 0; r < hand::kNE; r++) {
+          const int se = mp.eq(r);
+          for (int i = 0; i < kRowPrm; i++) setf(se + i, g, benign[i]);
+          seti(mp.ieq(r), g, 0); seti(mp.ieq(r) + 1, g, 0);
+          if (r >= L.ne) continue;
+          for (int i = 0; i < kRowPrm; i++) setf(se + i, g, eq_prm[(size_t)kRowPrm * r + i]);
+          for (int i = 0; i < 5; i++) setf(se + kRowPrm + i, g, eq_data[(size_t)5 * r + i]);
+          setf(se + kRowPrm + 5, g, 1.f);
+          const int b1 = m.jnt_bodyid[eq_j1[r]], b2 = eq_j2[r] >= 0 ? m.jnt_bodyid[eq_j2[r]] : -1;
+          if (lane_of[b1] == g) seti(mp.ieq(r), g, pos_in_chain[b1]);
+          if (b2 >= 0 && lane_of[b2] == g) seti(mp.ieq(r) + 1, g, pos_in_chain[b2]);
+        }
+      }
+      while (P.f.size() % 4) P.f.push_back(0.f);
+      L.hand_ok = 1; L.lNL = NLh; L.lNC = 0;
+      L.lg2G = 0;
+      while ((1 << L.lg2G) < G) L.lg2G++;
+      L.f_htab = P.addf(T);
     }
   }
 
@@ -781,8 +884,16 @@ static bool use_limb(const AbrModel* m, const Layout& L, bool dense_cost, bool d
   if (!lanes) { const char* e = getenv("ABR_LANES"); if (e) lanes = atoi(e); }
   return lanes == 0 || lanes == 1;
 }
+// the hand path serves fixed-base chains with joint equalities (abr_hand.cuh) unless a generic group size was pinned
+static bool use_hand(const AbrModel* m, const Layout& L, bool dense_cost) {
+  if (!L.hand_ok || dense_cost) return false;
+  int lanes = m->lanes;
+  if (!lanes) { const char* e = getenv("ABR_LANES"); if (e) lanes = atoi(e); }
+  return lanes == 0 || lanes == 1;
+}
 static int launch_rollout(const AbrModel* m, const Layout& L, const RolloutArgs& a, cudaStream_t st) {
   if (a.nworld <= 0) return ABR_OK;
+  if (use_hand(m, L, a.cost.enabled && !a.cost.diag) && a.t_begin == 0 && a.t_end == a.N) return launch_result(launch_hand_rollout_3(L, a, st));
   if (use_limb(m, L, a.cost.enabled && !a.cost.diag, false)) {
     const bool spec = getenv("ABR_LIMB_GENERAL") == nullptr;  // compile-time sharing patterns: 2 = flat 4 lanes, 86 = biped
     // fast variants (limb::Spec): the common options (no disable flag other than eulerdamp, one Newton iteration, default impedance power, hinge joints), specialised on
@@ -820,7 +931,7 @@ static int launch_env(const AbrModel* m, const Layout& L, const EnvArgs& a_in, c
     if (a.E != m->dr_E) return fail(ABR_EINVAL, "env call: batch size differs from the one given to abr_env_set_randomization");
     a.dr = m->dr;
   }
-  if (use_limb(m, L, false, a.dbg != nullptr)) {
+  if (use_limb(m, L, false, a.dbg != nullptr || a.fo_on)) {
     const bool spec = getenv("ABR_LIMB_GENERAL") == nullptr;
     const bool fast = (L.disableflags == ABR_DSBL_EULERDAMP || L.disableflags == 0) && L.iterations == 1 && L.l_pow2 && L.l_hinge &&
                       getenv("ABR_LIMB_NOSPEC") == nullptr;
@@ -957,6 +1068,9 @@ int abr_model_describe(const AbrModel* m, char* buf, int cap) {
              flat ? (L.l_mx == 1 ? "flat 2-lane pattern" : (L.l_mx == 3 ? "flat 8-lane pattern" : "flat 4-lane pattern"))
                   : (bip ? "biped pattern, contact-body form" : "sharing pattern from the table"), 1 << L.lg2G,
              fast ? (L.disableflags == 0 ? "fast (eulerdamp on)" : "fast (eulerdamp off)") : "general");
+  } else if (use_hand(m, L, false)) {
+    snprintf(tmp, sizeof(tmp), "hand kernels <NL=%d> (fixed-base chains, %d joint-equality rows), %d lanes per world; env calls: generic kernels",
+             L.lNL, L.ne, 1 << L.lg2G);
   } else {
     snprintf(tmp, sizeof(tmp), "generic kernels, %s lanes per world%s", m->lanes > 1 ? std::to_string(m->lanes).c_str() : "8 / 16 / 32 (by batch size)",
              L.limb_ok ? " (limb kernels available: abr_model_set_lanes(m, 0 or 1))" : "");
@@ -968,7 +1082,7 @@ int abr_model_describe(const AbrModel* m, char* buf, int cap) {
 int abr_model_set_lanes(AbrModel* m, int lanes) {
   if (!m) return fail(ABR_EINVAL, "abr_model_set_lanes: null model");
   if (lanes != 0 && lanes != 1 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32) return fail(ABR_EINVAL, "lanes must be 0, 1, 4, 8, 16 or 32");
-  if (lanes == 1 && !m->lay.limb_ok) return fail(ABR_EUNSUPPORTED, "lanes = 1 pins the limb path, which this model/options are not eligible for");
+  if (lanes == 1 && !m->lay.limb_ok && !m->lay.hand_ok) return fail(ABR_EUNSUPPORTED, "lanes = 1 pins the limb / hand path, which this model/options are not eligible for");
   m->lanes = lanes;
   return ABR_OK;
 }
@@ -1261,6 +1375,33 @@ int abr_forward_dev(AbrModel* m, float* qpos, float* qvel, const float* ctrl, fl
   a.blob = m->d_blob; a.qpos = qpos; a.qvel = qvel; a.warm = qacc_warmstart; a.qacc = qacc; a.ctrl = ctrl;
   a.E = E; a.nsubsteps = 0; a.forward_only = 1;
   return launch_env(m, m->lay, a, (cudaStream_t)stream);
+}
+
+// mjx.forward / mjx.step with the derived mjx.Data fields an env reads written in the same launch (rl/base.py:98-125)
+static int fields_call(AbrModel* m, float* qpos, float* qvel, const float* ctrl, float* warm, float* qacc, float* time, int E, int nsubsteps,
+                       bool forward_only, const AbrDataFields* fields, void* stream, const char* who) {
+  if (E < 0 || nsubsteps < 0) return fail(ABR_EINVAL, std::string(who) + ": negative size");
+  if (m && E == 0) return ABR_OK;
+  if (!m || !qpos || !qvel || !fields || (!forward_only && !warm)) return fail(ABR_EINVAL, std::string(who) + ": null argument");
+  int dev_before = -1;
+  cudaGetDevice(&dev_before);
+  CK(cudaSetDevice(m->device));
+  EnvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.blob = m->d_blob; a.qpos = qpos; a.qvel = qvel; a.warm = warm; a.qacc = qacc; a.time = time; a.ctrl = ctrl;
+  a.E = E; a.nsubsteps = nsubsteps; a.forward_only = forward_only ? 1 : 0;
+  a.fo = *fields; a.fo_on = 1;
+  const int rc = launch_env(m, m->lay_dbg, a, (cudaStream_t)stream);  // the un-aliased layout: every intermediate survives the step
+  if (dev_before >= 0) cudaSetDevice(dev_before);
+  return rc;
+}
+int abr_forward_fields_dev(AbrModel* m, float* qpos, float* qvel, const float* ctrl, float* qacc_warmstart, float* qacc, int E,
+                           const AbrDataFields* fields, void* stream) {
+  return fields_call(m, qpos, qvel, ctrl, qacc_warmstart, qacc, nullptr, E, 0, true, fields, stream, "abr_forward_fields_dev");
+}
+int abr_env_step_fields_dev(AbrModel* m, float* qpos, float* qvel, float* qacc_warmstart, float* time, const float* ctrl, int E,
+                            int nsubsteps, const AbrDataFields* fields, void* stream) {
+  return fields_call(m, qpos, qvel, ctrl, qacc_warmstart, nullptr, time, E, nsubsteps, false, fields, stream, "abr_env_step_fields_dev");
 }
 
 int abr_env_step_dev(AbrModel* m, float* qpos, float* qvel, float* qacc_warmstart, float* time, const float* ctrl, int E,

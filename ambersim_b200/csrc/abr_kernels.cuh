@@ -194,6 +194,7 @@ struct EnvArgs {
   const float* t_qd; const float* t_rd; const float* t_xg;
   float t_zmin; int t_max_steps;
   const float* dr;  // nullable [E,2]: per-env contact friction scale, actuator strength scale (abr_env_set_randomization)
+  AbrDataFields fo; int fo_on;  // derived mjx.Data fields written per world (abr_*_fields_dev; needs the un-aliased layout)
 };
 
 template <int G>
@@ -267,6 +268,19 @@ __global__ void __launch_bounds__(ABR_TPB, ABR_MINB) k_env(const __grid_constant
       A.time[w] = fin ? 0.f : (A.forward_only ? t0 : t0 + L.timestep * (float)A.nsubsteps);
     }
     if (A.dbg && wraw == 0) for (int i = c.lane; i < L.world_stride; i += G) A.dbg[i] = c.W[i];
+    if (A.fo_on) {
+      __syncwarp();
+      auto put = [&](float* dst, int off, int n) {
+        if (dst) for (int i = c.lane; i < n; i += G) dst[(size_t)w * n + i] = c.W[off + i];
+      };
+      const int nb = L.nbody;
+      put(A.fo.xpos, L.w_xpos, 3 * nb); put(A.fo.xquat, L.w_xquat, 4 * nb); put(A.fo.xipos, L.w_xipos, 3 * nb);
+      put(A.fo.xanchor, L.w_xanchor, 3 * L.njnt); put(A.fo.xaxis, L.w_xaxis, 3 * L.njnt); put(A.fo.cinert, L.w_cinert, 10 * nb);
+      put(A.fo.cdof, L.w_cdof, 6 * nv); put(A.fo.cvel, L.w_cvel, 6 * nb); put(A.fo.cdof_dot, L.w_cdofdot, 6 * nv);
+      put(A.fo.qfrc_smooth, L.w_fs, nv); put(A.fo.qacc_smooth, L.w_as, nv); put(A.fo.qfrc_constraint, L.w_fc, nv);
+      put(A.fo.efc_force, L.w_force, L.nefc); put(A.fo.efc_D, L.w_D, L.nefc); put(A.fo.efc_aref, L.w_aref, L.nefc);
+      put(A.fo.contact_dist, L.w_cdist, L.ncon); put(A.fo.contact_pos, L.w_cpos, 3 * L.ncon); put(A.fo.contact_frame, L.w_cframe, 9 * L.ncon);
+    }
   }
 }
 

@@ -80,6 +80,8 @@ struct Layout {
   int l_cb;         // every lane's contacts sit on the lane's leaf body and touch one plane (contact-body form)
   int l_hinge;      // every chain joint is a hinge (assumed by the fast variants)
   int l_pow2;       // every limit / contact row of the limb table has the default impedance power 2 (assumed by the fast variants)
+  int hand_ok;      // fixed-base chains + joint equalities, no contacts: served by the hand kernels (abr_hand.cuh); uses lNL, lg2G
+  int f_htab;       // float-pool offset of the per-lane table (hand::Map, row stride limb::kStride)
   int w_rk;         // RK4 save area: qpos0[nq] qvel0[nv] warm0[nv] sv[nv] sa[nv] kq[nv]
   int world_stride; // floats per world
 };

@@ -174,9 +174,54 @@ class Data:
     qacc: torch.Tensor
     qacc_warmstart: torch.Tensor
     time: torch.Tensor
+    # derived fields (mjx.Data names and layouts), filled on request by forward(..., fields=...) / step(..., fields=...):
+    # what an env's compute_obs / compute_reward reads (rl/base.py:98-125). None until requested.
+    xpos: Optional[torch.Tensor] = None
+    xquat: Optional[torch.Tensor] = None
+    xipos: Optional[torch.Tensor] = None
+    xanchor: Optional[torch.Tensor] = None
+    xaxis: Optional[torch.Tensor] = None
+    cinert: Optional[torch.Tensor] = None
+    cdof: Optional[torch.Tensor] = None
+    cvel: Optional[torch.Tensor] = None
+    cdof_dot: Optional[torch.Tensor] = None
+    qfrc_smooth: Optional[torch.Tensor] = None
+    qacc_smooth: Optional[torch.Tensor] = None
+    qfrc_constraint: Optional[torch.Tensor] = None
+    efc_force: Optional[torch.Tensor] = None
+    efc_D: Optional[torch.Tensor] = None
+    efc_aref: Optional[torch.Tensor] = None
+    contact_dist: Optional[torch.Tensor] = None
+    contact_pos: Optional[torch.Tensor] = None
+    contact_frame: Optional[torch.Tensor] = None
 
     def replace(self, **kw) -> "Data":
         return dataclasses.replace(self, **kw)
+
+
+DERIVED_FIELDS = ("xpos", "xquat", "xipos", "xanchor", "xaxis", "cinert", "cdof", "cvel", "cdof_dot", "qfrc_smooth", "qacc_smooth",
+                  "qfrc_constraint", "efc_force", "efc_D", "efc_aref", "contact_dist", "contact_pos", "contact_frame")
+
+
+def _field_shapes(m: "Model", h) -> dict:
+    nb, nv, nj, ne, nc = m.nbody, m.nv, m.njnt, h.nefc, h.ncon
+    return dict(xpos=(nb, 3), xquat=(nb, 4), xipos=(nb, 3), xanchor=(nj, 3), xaxis=(nj, 3), cinert=(nb, 10), cdof=(nv, 6), cvel=(nb, 6),
+                cdof_dot=(nv, 6), qfrc_smooth=(nv,), qacc_smooth=(nv,), qfrc_constraint=(nv,), efc_force=(ne,), efc_D=(ne,), efc_aref=(ne,),
+                contact_dist=(nc,), contact_pos=(nc, 3), contact_frame=(nc, 3, 3))
+
+
+def _alloc_fields(m: "Model", h, fields, E: int, dev):
+    """(AbrDataFields struct, {name: tensor [E, ...]}) for the requested derived fields."""
+    S = _abi.structs()["AbrDataFields"]()
+    shapes = _field_shapes(m, h)
+    out = {}
+    for name in fields:
+        if name not in shapes:
+            raise AttributeError(f"Data has no derived field {name!r} (available: {', '.join(DERIVED_FIELDS)})")
+        t = torch.empty((E,) + shapes[name], dtype=torch.float32, device=dev)
+        out[name] = t
+        setattr(S, name, C.cast(C.c_void_p(t.data_ptr()), C.POINTER(C.c_float)))
+    return S, out
 
 
 def limb_plan(mj_model: MjModel, opt: Optional[Option] = None) -> dict:
@@ -249,8 +294,9 @@ def _batch_shape(m: Model, d: Data) -> tuple:
     return b1 if len(b1) >= len(b2) else b2
 
 
-def forward(m: Model, d: Data) -> Data:
-    """mjx.forward(m, d): fills qacc and qacc_warmstart; qpos gets its quaternions normalised."""
+def forward(m: Model, d: Data, fields=()) -> Data:
+    """mjx.forward(m, d): fills qacc and qacc_warmstart; qpos gets its quaternions normalised.
+    fields: names of derived mjx.Data fields (DERIVED_FIELDS) to fill as well, batched, in the same launch."""
     dev = d.qpos.device
     h = m.handle(dev.index or 0)
     batch = _batch_shape(m, d)
@@ -258,14 +304,21 @@ def forward(m: Model, d: Data) -> Data:
     ctrl, warm = _flat(d.ctrl, m.nu, dev, batch), _flat(d.qacc_warmstart, m.nv, dev, batch)
     qacc = torch.empty_like(qvel)
     E = qpos.shape[0]
-    _lib.check(_lib.lib().abr_forward_dev(h.ptr, _ptr(qpos), _ptr(qvel), _ptr(ctrl), _ptr(warm), _ptr(qacc), E, _stream(dev)))
+    extra = {}
+    if fields:
+        S, extra = _alloc_fields(m, h, fields, E, dev)
+        _lib.check(_lib.lib().abr_forward_fields_dev(h.ptr, _ptr(qpos), _ptr(qvel), _ptr(ctrl), _ptr(warm), _ptr(qacc), E, C.byref(S), _stream(dev)))
+    else:
+        _lib.check(_lib.lib().abr_forward_dev(h.ptr, _ptr(qpos), _ptr(qvel), _ptr(ctrl), _ptr(warm), _ptr(qacc), E, _stream(dev)))
     rs = lambda t, n: t.reshape(*batch, n)
     return d.replace(qpos=rs(qpos, m.nq), qvel=rs(qvel, m.nv), ctrl=rs(ctrl, m.nu), qacc=rs(qacc, m.nv),
-                     qacc_warmstart=rs(warm, m.nv))
+                     qacc_warmstart=rs(warm, m.nv), **{k: v.reshape(*batch, *v.shape[1:]) for k, v in extra.items()})
 
 
-def step(m: Model, d: Data, nsubsteps: int = 1) -> Data:
-    """mjx.step(m, d) (x nsubsteps with ctrl held: MjxEnv.pipeline_step, rl/base.py:88-96)."""
+def step(m: Model, d: Data, nsubsteps: int = 1, fields=()) -> Data:
+    """mjx.step(m, d) (x nsubsteps with ctrl held: MjxEnv.pipeline_step, rl/base.py:88-96).
+    fields: derived mjx.Data fields to fill as well: those of the last forward pass, i.e. of the state before the final
+    integration, exactly what mjx.step leaves in mjx.Data."""
     dev = d.qpos.device
     h = m.handle(dev.index or 0)
     batch = _batch_shape(m, d)
@@ -273,11 +326,17 @@ def step(m: Model, d: Data, nsubsteps: int = 1) -> Data:
     ctrl, warm = _flat(d.ctrl, m.nu, dev, batch), _flat(d.qacc_warmstart, m.nv, dev, batch)
     time = torch.as_tensor(d.time, dtype=torch.float32, device=dev).broadcast_to(batch).reshape(-1).contiguous().clone()
     E = qpos.shape[0]
-    _lib.check(_lib.lib().abr_env_step_dev(h.ptr, _ptr(qpos), _ptr(qvel), _ptr(warm), _ptr(time), _ptr(ctrl), E,
-                                           int(nsubsteps), None, None, None, None, _stream(dev)))
+    extra = {}
+    if fields:
+        S, extra = _alloc_fields(m, h, fields, E, dev)
+        _lib.check(_lib.lib().abr_env_step_fields_dev(h.ptr, _ptr(qpos), _ptr(qvel), _ptr(warm), _ptr(time), _ptr(ctrl), E, int(nsubsteps),
+                                                      C.byref(S), _stream(dev)))
+    else:
+        _lib.check(_lib.lib().abr_env_step_dev(h.ptr, _ptr(qpos), _ptr(qvel), _ptr(warm), _ptr(time), _ptr(ctrl), E,
+                                               int(nsubsteps), None, None, None, None, _stream(dev)))
     rs = lambda t, n: t.reshape(*batch, n)
     return d.replace(qpos=rs(qpos, m.nq), qvel=rs(qvel, m.nv), ctrl=rs(ctrl, m.nu), qacc_warmstart=rs(warm, m.nv),
-                     time=time.reshape(batch))
+                     time=time.reshape(batch), **{k: v.reshape(*batch, *v.shape[1:]) for k, v in extra.items()})
 
 
 def set_randomization(m: Model, dr: Optional[torch.Tensor]) -> None:

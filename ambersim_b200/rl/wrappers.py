@@ -100,7 +100,8 @@ class AutoResetWrapper(Wrapper):
             return torch.where(d, first, cur)
 
         first, cur = state.info["first_pipeline_state"], state.pipeline_state
-        data = cur.replace(**{f.name: where_done(getattr(first, f.name), getattr(cur, f.name)) for f in dataclasses.fields(cur)})
+        data = cur.replace(**{f.name: where_done(getattr(first, f.name), getattr(cur, f.name)) for f in dataclasses.fields(cur)
+                              if getattr(cur, f.name) is not None and getattr(first, f.name) is not None})  # derived fields are optional
         return state.replace(pipeline_state=data, obs=where_done(state.info["first_obs"], state.obs))
 
 

@@ -234,7 +234,11 @@ def extra_configs(mj, m, cf, q0, torch, device, stream, L, peak_tf):
     hcf = StaticGoalQuadraticCost(np.eye(hnx), 10.0 * np.eye(hnx), 0.01 * np.eye(hj.nu), np.zeros(hnx))
     hps = VanillaPredictiveSampler(model=hm, cost_function=hcf, nsamples=100, stdev=0.01)
     hprm = VanillaPredictiveSamplerParams(key=0, x0=torch.zeros(hnx, **f), us_guess=torch.zeros((10, hj.nu), **f))
-    ex["c1_bh280_vps_100x10_solve_ms"] = _timed(torch, stream, lambda: hps.optimize(hprm), 5)
+    ex["c1_bh280_vps_100x10_solve_ms"] = _timed(torch, stream, lambda: hps.optimize(hprm), 20)
+    ex["c1_bh280_kernels"] = hm.describe()
+    hps4 = VanillaPredictiveSampler(model=hm, cost_function=hcf, nsamples=4096, stdev=0.01)
+    hprm4 = VanillaPredictiveSamplerParams(key=0, x0=torch.zeros(hnx, **f), us_guess=torch.zeros((32, hj.nu), **f))
+    ex["bh280_vps_4096x32_solve_ms"] = _timed(torch, stream, lambda: hps4.optimize(hprm4), 10)
     rate, fin = rollout_rate(mj, m, cf, "home", 65536, 250, CTRL_NOISE)
     ex["barkour_65536x250"] = {"world_steps_per_s": rate, "frac_of_ffma_peak": F_WS * rate / 1e12 / peak_tf, "costs_finite": fin}
     bj = load_mj_model_from_file("models/biped_standin/biped_exo_standin.xml")

@@ -278,6 +278,27 @@ int abr_env_step_dev(AbrModel* m, float* qpos, float* qvel, float* qacc_warmstar
                      const float* first_qpos, const float* first_qvel,
                      const float* first_qacc_warmstart, void* stream);
 
+/* ---- derived mjx.Data fields, batched (the fields a user env's compute_obs / compute_reward reads: rl/base.py:98-125) ----
+ * Nullable DEVICE pointers, row-major [E, ...], float32, mjx.Data field names and layouts:
+ * xpos [E,nbody,3] xquat [E,nbody,4] xipos [E,nbody,3] xanchor [E,njnt,3] xaxis [E,njnt,3] cinert [E,nbody,10]
+ * cdof [E,nv,6] cvel [E,nbody,6] cdof_dot [E,nv,6] qfrc_smooth [E,nv] qacc_smooth [E,nv] qfrc_constraint [E,nv]
+ * efc_force / efc_D / efc_aref [E,nefc] contact_dist [E,ncon] contact_pos [E,ncon,3] contact_frame [E,ncon,9]
+ * (nefc, ncon: abr_model_info; rows in MJX's order equality, limit, contact). */
+/* ABR_STRUCT_BEGIN AbrDataFields */
+typedef struct AbrDataFields {
+  float* xpos; float* xquat; float* xipos; float* xanchor; float* xaxis; float* cinert; float* cdof; float* cvel;
+  float* cdof_dot; float* qfrc_smooth; float* qacc_smooth; float* qfrc_constraint; float* efc_force; float* efc_D;
+  float* efc_aref; float* contact_dist; float* contact_pos; float* contact_frame;
+} AbrDataFields;
+/* ABR_STRUCT_END */
+/* abr_forward_dev / abr_env_step_dev (no reset prologue) that also write the requested derived fields of E worlds in the same
+ * launch. After a step they are the fields of the LAST forward pass, i.e. of the state before the final integration: exactly
+ * what mjx.step leaves in mjx.Data. Served by the generic kernels (the register-resident limb kernels keep no body arrays). */
+int abr_forward_fields_dev(AbrModel* m, float* qpos, float* qvel, const float* ctrl, float* qacc_warmstart, float* qacc,
+                           int E, const AbrDataFields* fields, void* stream);
+int abr_env_step_fields_dev(AbrModel* m, float* qpos, float* qvel, float* qacc_warmstart, float* time, const float* ctrl,
+                            int E, int nsubsteps, const AbrDataFields* fields, void* stream);
+
 /* ---- per-env domain randomisation of model parameters (ambersim/trajopt/base.py:49-58 rationale) ----
  * dr: DEVICE pointer [E,2] = {contact friction scale, actuator strength scale} per env, or NULL to switch it off.
  * The friction scale multiplies both tangential coefficients of every contact of the env (and rescales the

@@ -23,7 +23,8 @@ MODELS = {
     # test-only fixture for the limb kernels: 3 limbs (dummy lane), a forked limb (nested sharing), padding,
     # slide joint, condim-1 contacts, a trunk contact, a tilted floor
     "tripod": (str(ROOT / "tests/models/tripod.xml"), "home"),
-    "tripod3": (str(ROOT / "tests/models/tripod3.xml"), "home"),  # three leaf paths: the 4-lane group carries a dummy lane
+    "tripod3": (str(ROOT / "tests/models/tripod3.xml"), "home"),
+    "fixedbase": (str(ROOT / "tests/models/fixedbase.xml"), None),  # hand kernels: static base, three chains, four joint equalities  # three leaf paths: the 4-lane group carries a dummy lane
 }
 
 

@@ -306,7 +306,9 @@ def test_generic_cost_function_path(vps_data):
     a = ps.optimize(VanillaPredictiveSamplerParams(key=0, x0=x0, us_guess=ug, noise=nz))
     b = VanillaPredictiveSampler(model=model, cost_function=Mine(), nsamples=100, stdev=0.01).optimize(
         VanillaPredictiveSamplerParams(key=0, x0=x0, us_guess=ug, noise=nz))
-    assert torch.allclose(a[1], b[1]) and torch.allclose(a[0], b[0], atol=1e-5)
+    # the fused path forms guess + stdev * noise with one FMA on the device, torch with a multiply and an add: the controls agree
+    # to an ulp, and the stiff joint couplings of the hand amplify that over the horizon
+    assert torch.allclose(a[1], b[1]) and torch.allclose(a[0], b[0], rtol=2e-4, atol=2e-4)
 
 
 # ------------------------------------------------------------------ env step
@@ -450,9 +452,15 @@ def test_model_describe_names_the_serving_kernels(load_model):
 
 
 def test_limb_path_eligibility(load_model):
-    """Fixed-base models, equality constraints, CG and RK4 stay on the generic kernels: pinning the limb
-    path there is an error, not a silent fallback."""
-    for name, opt in (("pendulum", {}), ("bh280", {}), ("barkour", dict(solver=1)), ("barkour", dict(integrator=1))):
+    """CG and RK4 stay on the generic kernels, and so does a fixed-base model with contacts on: pinning the limb / hand path
+    there is an error, not a silent fallback. Fixed-base chains with joint equalities and no contacts (pendulum, bh280 under
+    the reference fixture's options) are served by the hand kernels."""
+    for name in ("pendulum", "bh280"):
+        mj, m, _ = model_with(load_model, name)
+        m.set_lanes(1)
+        assert "hand kernels" in m.describe()
+        assert shoot(m, t32(np.zeros(mj.nq + mj.nv)), t32(np.zeros((2, mj.nu)))).shape == (3, mj.nq + mj.nv)
+    for name, opt in (("bh280", dict(solver=1)), ("pendulum", dict(integrator=1)), ("barkour", dict(solver=1)), ("barkour", dict(integrator=1))):
         mj, m, _ = model_with(load_model, name, **opt)
         with pytest.raises(Exception):
             m.set_lanes(1)
@@ -853,3 +861,101 @@ def test_peer_exchange_single_rank_and_argument_checks():
     assert L.abr_xchg_merge_best_dev(x, p(cost), p(idx), p(xs), p(us), B + 1, nxs, nus, p(xs_o), p(us_o), p(idx_o), p(cost_o), stream) == _lib.ABR_ECAPACITY
     assert L.abr_xchg_merge_best_dev(x, p(cost), p(idx), p(xs), p(us), 0, nxs, nus, p(xs_o), p(us_o), p(idx_o), p(cost_o), stream) == _lib.ABR_EINVAL
     _lib.check(L.abr_xchg_destroy(x))
+
+
+# ------------------------------------------------------------------ derived mjx.Data fields, batched
+@pytest.mark.parametrize("name", ["barkour", "bh280", "biped"])
+def test_batched_derived_fields_match_oracle(load_model, name):
+    """forward(..., fields=...) / step(..., fields=...) fill the mjx.Data fields an env's compute_obs reads (rl/base.py:98-125)
+    for a whole batch in the launch that does the physics; every world is compared with the float64 oracle. After a step the
+    fields are those of the last forward pass (the state BEFORE the final integration), as mjx.step leaves them."""
+    mj, model, o = model_with(load_model, name)
+    rng = np.random.default_rng(21)
+    E = 24
+    key = {"barkour": "home", "biped": "stand"}.get(name)
+    q0 = mj.key_qpos(key) if key else mj.qpos0.copy()
+    qs = np.tile(q0, (E, 1))
+    if key:
+        qs[:, 7:] += rng.uniform(-0.1, 0.1, (E, mj.nq - 7))
+        qs[:, 2] -= rng.uniform(0.0, 0.01, E)
+    else:
+        qs += rng.uniform(0.0, 0.5, (E, mj.nq))
+    vs, cs, ws = 0.3 * rng.normal(size=(E, mj.nv)), 0.2 * rng.normal(size=(E, mj.nu)), rng.normal(size=(E, mj.nv))
+    if key:
+        cs += mj.key_ctrl(key)
+    names = list(mjx.DERIVED_FIELDS)
+    d = mjx.Data(qpos=t32(qs), qvel=t32(vs), ctrl=t32(cs), qacc=torch.zeros((E, mj.nv), device=DEV), qacc_warmstart=t32(ws),
+                 time=torch.zeros(E, device=DEV))
+    f = mjx.forward(model, d, fields=names)
+    plain = mjx.forward(model, d)
+    assert float((f.qacc - plain.qacc).abs().max()) < 5e-4 * float(plain.qacc.abs().max())  # limb kernels (plain) vs generic kernels (fields)
+    for e in range(E):
+        ref = o.forward(qs[e], vs[e], cs[e], ws[e])
+        for n in names:
+            got = getattr(f, n)[e].cpu().numpy().astype(np.float64).ravel()
+            r = ref[n].ravel()
+            if n in ("efc_force", "efc_D", "efc_aref") and r.size != got.size:
+                continue
+            assert r.size == got.size, n
+            if r.size:
+                assert np.abs(r - got).max() <= 3e-4 * max(1e-6, np.abs(r).max()) + 1e-6, (n, e)
+    # step: the state advances like the plain step; the fields are the pre-integration ones of the same launch
+    s = mjx.step(model, f.replace(qacc_warmstart=plain.qacc_warmstart), fields=("xpos", "cvel", "contact_dist"))
+    s_plain = mjx.step(model, plain)
+    assert torch.allclose(s.qpos, s_plain.qpos, atol=2e-5) and torch.allclose(s.qvel, s_plain.qvel, rtol=1e-3, atol=2e-4)
+    assert torch.allclose(s.xpos, f.xpos, atol=1e-6) and torch.allclose(s.cvel, f.cvel, atol=1e-5)
+
+
+# ------------------------------------------------------------------ hand kernels: fixed-base chains + joint equalities (VERDICT r1 item 5)
+HAND_VARIANTS = [dict(), dict(disableflags=16 | 16384), dict(iterations=3, ls_iterations=8), dict(disableflags=16 | 256), dict(disableflags=16 | 2),
+                 dict(disableflags=16 | 8), dict(disableflags=16 | 32 | 64)]
+
+
+@pytest.mark.parametrize("name", ["bh280", "fixedbase"])
+def test_hand_kernels_serve_fixed_base_models_and_match_oracle(load_model, name):
+    """The reference's own model (bh280: palm welded to the world, three finger chains, four joint equalities of which one ties
+    two fingers together) runs on the register-resident hand kernels (abr_hand.cuh): rollouts against the float64 oracle and
+    against the generic kernels, under the reference fixture's options and six option variants."""
+    for var in HAND_VARIANTS:
+        opt = dict(timestep=0.002, iterations=1, ls_iterations=4, integrator=0, solver=2, disableflags=16)
+        opt.update(var)
+        mj = load_model(name)
+        m = mjx.device_put(mj)
+        m = m.replace(opt=m.opt.replace(**opt))
+        o = Oracle(mj, m.opt)
+        assert "hand kernels" in m.describe(), m.describe()
+        rng = np.random.default_rng(31)
+        W, N = 12, 25
+        lo, hi = mj.jnt_range[:, 0], mj.jnt_range[:, 1]
+        span = np.where(hi > lo, hi - lo, 1.0)
+        x0 = np.concatenate([np.where(hi > lo, lo, -0.5) + span * rng.uniform(-0.15, 1.15, (W, mj.nq)), 0.5 * rng.normal(size=(W, mj.nv))], axis=1)
+        us = rng.normal(size=(W, N, mj.nu)) * 1.5
+        xs = shoot(m, t32(x0), t32(us)).cpu().numpy()
+        ref = o.rollout(x0, us)
+        ref32 = o.rollout(x0, us, prec=1)
+        drift = np.abs(ref32 - ref).max(axis=(0, 2))
+        err = np.abs(xs - ref).max(axis=(0, 2))
+        scale = max(1.0, np.abs(ref).max())
+        assert err[1] < 2e-5 * scale, (var, err[1])
+        assert np.all(err < np.maximum(2e-3 * scale, 10 * drift)), (var, err, drift)
+        m.set_lanes(8)
+        gen = shoot(m, t32(x0), t32(us)).cpu().numpy()
+        m.set_lanes(0)
+        assert np.abs(gen - xs).max() < np.maximum(2e-3 * scale, 10 * drift.max())
+        assert np.array_equal(xs[:, 0], x0.astype(np.float32))  # row 0 = the caller's x0 verbatim (shooting.py:47)
+
+
+def test_hand_kernels_sampler_equals_generic_winner(vps_data):
+    """The reference fixture (bh280, 100 samples x horizon 10) through the hand kernels: same winner as the generic kernels."""
+    ps, model, cf, o = vps_data
+    rng = np.random.default_rng(5)
+    x0, ug = t32(rng.uniform(0.0, 0.4, (4, 16))), t32(rng.normal(size=(4, 10, 4)))
+    p = VanillaPredictiveSamplerParams(key=9, x0=x0, us_guess=ug)
+    assert "hand kernels" in model.describe()
+    xs, us, info = ps.optimize(p, return_info=True)
+    model.set_lanes(8)
+    xs_g, us_g, info_g = ps.optimize(p, return_info=True)
+    model.set_lanes(0)
+    assert torch.allclose(info["costs"], info_g["costs"], rtol=2e-4)
+    assert torch.equal(us, us_g) or torch.allclose(info["best_cost"], info_g["best_cost"], rtol=2e-4)
+    assert np.array_equal(info["best_idx"].cpu().numpy(), np.argmin(info["costs"].cpu().numpy(), axis=1))

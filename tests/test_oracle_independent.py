@@ -13,7 +13,7 @@ import pytest
 from oracle import independent as ind
 from oracle.oracle import Oracle
 
-ALL = ["pendulum", "bh280", "barkour", "biped", "exolegs", "tripod", "tripod3"]
+ALL = ["pendulum", "bh280", "barkour", "biped", "exolegs", "tripod", "tripod3", "fixedbase"]
 KEYS = {"barkour": "home", "biped": "stand", "exolegs": "stand", "tripod": "home", "tripod3": "home"}
 
 
@@ -72,14 +72,14 @@ def test_forward_dynamics_against_articulated_body_algorithm(load_model, name):
         assert np.abs(M - f["qM"]).max() < 1e-6 * np.abs(f["qM"]).max()
 
 
-@pytest.mark.parametrize("name", ["barkour", "biped", "exolegs", "tripod", "bh280"])
+@pytest.mark.parametrize("name", ["barkour", "biped", "exolegs", "tripod", "bh280", "fixedbase"])
 def test_constraint_solve_against_generic_minimiser(load_model, name):
     m = load_model(name)
     rng = np.random.default_rng(13)
-    base = m.opt.replace(disableflags=16) if name == "bh280" else m.opt
+    base = m.opt.replace(disableflags=16) if name in ("bh280", "fixedbase") else m.opt
     conv = Oracle(m, base.replace(solver=2, iterations=200, ls_iterations=50, tolerance=1e-14))
     for trial in range(3):
-        if name == "bh280":
+        if name in ("bh280", "fixedbase"):
             q, v = rng.uniform(-0.3, 0.8, m.nq), rng.normal(size=m.nv)  # past the lower joint limits, equalities active
         else:
             q, v = _random_state(m, name, rng, spread=0.15)

@@ -35,7 +35,13 @@ class State:
 
 
 class MjxEnv(ABC):
-    """API for an engine-backed system for training and inference."""
+    """API for an engine-backed system for training and inference.
+
+    `data_fields`: names of derived `mjx.Data` fields (`mjx.DERIVED_FIELDS`: xpos, xquat, cvel, contact_dist, efc_force, ...)
+    that `compute_obs` / `compute_reward` read (the pattern ambersim/rl/base.py:98-125 is designed for). They are filled for
+    the whole batch by the launch that does the physics; leave it empty when obs / reward only need qpos / qvel."""
+
+    data_fields: tuple = ()
 
     def __init__(self, mj_model: MjModel, physics_steps_per_control_step: int = 1, device=None) -> None:
         assert physics_steps_per_control_step >= 1
@@ -71,12 +77,12 @@ class MjxEnv(ABC):
         data = data.replace(qpos=qpos, qvel=qvel, ctrl=torch.zeros(*batch, self.sys.nu, device=dev),
                             qacc_warmstart=torch.zeros(*batch, self.sys.nv, device=dev),
                             time=torch.zeros(batch, device=dev))
-        return mjx.forward(self.sys, data)
+        return mjx.forward(self.sys, data, fields=self.data_fields)
 
     def pipeline_step(self, data: mjx.Data, ctrl: torch.Tensor) -> mjx.Data:
         """Holds ctrl and takes physics_steps_per_control_step physics steps (reference rl/base.py:88-96)."""
         ctrl = torch.as_tensor(ctrl, dtype=torch.float32, device=data.qpos.device)
-        return mjx.step(self.sys, data.replace(ctrl=ctrl), nsubsteps=self._physics_steps_per_control_step)
+        return mjx.step(self.sys, data.replace(ctrl=ctrl), nsubsteps=self._physics_steps_per_control_step, fields=self.data_fields)
 
     def compute_reward(self, data: mjx.Data, info: Dict[str, Any]) -> torch.Tensor:
         raise NotImplementedError

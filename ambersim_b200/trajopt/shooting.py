@@ -274,6 +274,84 @@ class VanillaPredictiveSampler(ShootingAlgorithm):
 
 
 @dataclasses.dataclass
+class SplineShootingParams(VanillaPredictiveSamplerParams):
+    """`us_guess` holds K control KNOTS (K, nu) / (B, K, nu), not N zero-order-hold controls: the alternate parameterisation
+    `ShootingParams.N` anticipates (reference shooting.py:66-73), so the horizon is given explicitly."""
+
+    horizon: int = 0
+
+    @property
+    def N(self) -> int:
+        return int(self.horizon)
+
+
+@dataclasses.dataclass
+class SplinePredictiveSampler(VanillaPredictiveSampler):
+    """Predictive sampling over control knots (engine extension): the K knots are spread evenly over the N-step
+    horizon and interpolated ("zoh", "linear" or "cubic" Catmull-Rom) into the per-step controls; the Gaussian noise is drawn
+    on the KNOTS (stdev per knot entry, sample 0 = the un-noised knots) and interpolated the same way, so a sample's controls
+    are interp(knots + stdev z) clipped to actuator_ctrlrange. The rollouts, costs, argmin and winner run fused on the engine
+    exactly as for `VanillaPredictiveSampler` (through its caller-supplied-noise path). Returns (xs_star, knots_star)."""
+
+    interp: str = "linear"
+
+    def weights(self, K: int, N: int, device=None) -> torch.Tensor:
+        """(N, K) interpolation matrix: row t holds the weights of the knots in the control applied at step t."""
+        W = torch.zeros((N, K), dtype=torch.float64)
+        if K == 1:
+            W[:, 0] = 1.0
+        else:
+            for t in range(N):
+                s = t * (K - 1) / max(1, N - 1) if N > 1 else 0.0  # knot coordinate of step t: first knot at t = 0, last at t = N - 1
+                k = min(int(np.floor(s)), K - 2)
+                a = s - k
+                if self.interp == "zoh":
+                    W[t, k if a < 1.0 else k + 1] = 1.0
+                elif self.interp == "linear":
+                    W[t, k] += 1.0 - a
+                    W[t, k + 1] += a
+                elif self.interp == "cubic":  # Catmull-Rom through the knots, end knots repeated
+                    c = [(-a**3 + 2 * a**2 - a) / 2, (3 * a**3 - 5 * a**2 + 2) / 2, (-3 * a**3 + 4 * a**2 + a) / 2, (a**3 - a**2) / 2]
+                    for j, cj in zip((k - 1, k, k + 1, k + 2), c):
+                        W[t, min(max(j, 0), K - 1)] += cj
+                else:
+                    raise ValueError(f"interp must be 'zoh', 'linear' or 'cubic', got {self.interp!r}")
+        return W.to(dtype=torch.float32, device=device)
+
+    def optimize(self, params: SplineShootingParams, return_info: bool = False):
+        if not isinstance(self.cost_function, StaticGoalQuadraticCost):
+            raise NotImplementedError("SplinePredictiveSampler needs a StaticGoalQuadraticCost (fused on the device)")
+        knots = torch.as_tensor(params.us_guess, dtype=torch.float32)
+        dev = knots.device if knots.is_cuda else mjx._dev()
+        knots = knots.to(dev)
+        batched = knots.dim() == 3
+        kb = knots if batched else knots[None]
+        B, K, nu = kb.shape
+        N, S = int(params.N), int(self.nsamples)
+        if N <= 0:
+            raise ValueError("SplineShootingParams.horizon must be the number of physics steps")
+        W = self.weights(K, N, dev)
+        g = torch.Generator(device=dev)
+        g.manual_seed(_seed_of(params.key) & 0x7FFFFFFFFFFFFFFF)
+        z = torch.randn((B, max(S - 1, 1), K, nu), generator=g, dtype=torch.float32, device=dev)  # row s - 1 = sample s (a spare row when S = 1)
+        dense = dataclasses.replace(params, us_guess=torch.einsum("tk,bku->btu", W, kb), noise=torch.einsum("tk,bsku->bstu", W, z[:, :S - 1]),
+                                    x0=torch.as_tensor(params.x0, dtype=torch.float32, device=dev).expand(B, self.model.nx))
+        vanilla = VanillaPredictiveSampler(model=self.model, cost_function=self.cost_function, nsamples=S, stdev=self.stdev)
+        xs, us, info = vanilla.optimize(VanillaPredictiveSamplerParams(x0=dense.x0, us_guess=dense.us_guess, key=params.key, noise=dense.noise),
+                                        return_info=True)
+        idx = info["best_idx"].long()
+        pick = z[torch.arange(B, device=dev), (idx - 1).clamp(min=0)] * (idx > 0).float()[:, None, None]
+        knots_star = kb + float(self.stdev) * pick
+        if not batched:
+            xs, us, knots_star = xs[0], us[0], knots_star[0]
+            info = {k: (v[0] if hasattr(v, "dim") and v.dim() > 0 else v) for k, v in info.items()}
+        if return_info:
+            info["us_star"] = us
+            return xs, knots_star, info
+        return xs, knots_star
+
+
+@dataclasses.dataclass
 class FiniteDifferenceShooting(ShootingAlgorithm):
     """Gradient-based single shooting on the engine (extension; the reference shapes its API for it, base.py:67-69 and
     cost.py:87-178, without shipping one): the gradient of the trajectory cost with respect to every control entry is a

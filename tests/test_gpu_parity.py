@@ -959,3 +959,81 @@ def test_hand_kernels_sampler_equals_generic_winner(vps_data):
     assert torch.allclose(info["costs"], info_g["costs"], rtol=2e-4)
     assert torch.equal(us, us_g) or torch.allclose(info["best_cost"], info_g["best_cost"], rtol=2e-4)
     assert np.array_equal(info["best_idx"].cpu().numpy(), np.argmin(info["costs"].cpu().numpy(), axis=1))
+
+
+def test_user_env_reads_derived_data_fields(load_model):
+    """A user-defined MjxEnv whose observation and reward read derived mjx.Data fields (body positions, body twists, contact
+    distances: the pattern rl/base.py:98-125 is designed for), wrapped in the Episode / AutoReset wrappers: the fields arrive
+    batched from the physics launch and match the oracle's; auto-reset blends them like every other leaf of the state."""
+    from ambersim_b200.rl.base import MjxEnv, State
+    from ambersim_b200.rl.wrappers import AutoResetWrapper, EpisodeWrapper
+
+    mj = load_model("barkour")
+
+    class FootEnv(MjxEnv):
+        data_fields = ("xpos", "cvel", "contact_dist")
+
+        def reset(self, rng):
+            g = torch.Generator(device=DEV).manual_seed(int(rng))
+            q = t32(np.tile(mj.key_qpos("home"), (16, 1)))
+            q[:, 7:] += (torch.rand((16, mj.nq - 7), generator=g, device=DEV) - 0.5) * 0.1
+            d = self.pipeline_init(q, torch.zeros((16, mj.nv), device=DEV))
+            z = torch.zeros(16, device=DEV)
+            return State(d, self.compute_obs(d, {}), z, z.clone())
+
+        def compute_obs(self, data, info):
+            return torch.cat((data.xpos[:, 1], data.cvel[:, 1], data.contact_dist), dim=-1)  # trunk position, trunk twist, foot clearances
+
+        def compute_reward(self, data, info):
+            return -data.contact_dist.clamp(min=0).sum(-1)
+
+        def step(self, state, action):
+            d = self.pipeline_step(state.pipeline_state, action)
+            done = (d.qpos[:, 2] < 0.15).float()
+            return state.replace(pipeline_state=d, obs=self.compute_obs(d, state.info), reward=self.compute_reward(d, state.info), done=done)
+
+    env = AutoResetWrapper(EpisodeWrapper(FootEnv(mj), episode_length=5))
+    s = env.reset(3)
+    assert s.obs.shape == (16, 3 + 6 + 4)
+    o = Oracle(mj)
+    ref = o.forward(s.pipeline_state.qpos[2].cpu().numpy(), np.zeros(mj.nv))
+    assert np.allclose(s.obs[2, :3].cpu().numpy(), ref["xpos"][1], atol=1e-5) and np.allclose(s.obs[2, 9:].cpu().numpy(), ref["contact_dist"], atol=1e-5)
+    acts = t32(np.tile(mj.key_ctrl("home"), (16, 1)))
+    prev = s
+    for t in range(6):
+        s = env.step(s, acts)
+        assert torch.isfinite(s.obs).all() and torch.isfinite(s.reward).all()
+        if t == 0:  # mjx.step leaves the fields of the state BEFORE the integration: the trunk position of the previous qpos
+            assert torch.allclose(s.pipeline_state.xpos[:, 1], prev.pipeline_state.qpos[:, :3], atol=1e-6)
+    assert bool((s.info["steps"] <= 5).all())
+
+
+def test_spline_predictive_sampler(load_model):
+    """Knot-parameterised predictive sampling (the alternate parameterisation ShootingParams.N anticipates, shooting.py:66-73):
+    the interpolation weights are a partition of unity that reproduces the knots, sample 0 is the un-noised spline, the winner's
+    knots regenerate the winner's controls, and the winner is no worse than the guess."""
+    from ambersim_b200.trajopt.shooting import SplinePredictiveSampler, SplineShootingParams
+
+    mj, m, o = model_with(load_model, "barkour")
+    nx = mj.nq + mj.nv
+    q0 = np.concatenate([mj.key_qpos("home"), np.zeros(mj.nv)])
+    cf = StaticGoalQuadraticCost(np.eye(nx), 10 * np.eye(nx), 0.01 * np.eye(mj.nu), q0)
+    rng = np.random.default_rng(2)
+    x0 = q0.copy()
+    x0[7:19] += rng.uniform(-0.1, 0.1, 12)
+    knots = np.clip(mj.key_ctrl("home") + 0.2 * rng.standard_normal((5, mj.nu)), mj.actuator_ctrlrange[:, 0], mj.actuator_ctrlrange[:, 1])
+    lim = t32(mj.actuator_ctrlrange)
+    for interp in ("zoh", "linear", "cubic"):
+        ps = SplinePredictiveSampler(model=m, cost_function=cf, nsamples=256, stdev=0.1, interp=interp)
+        W = ps.weights(5, 33)
+        assert torch.allclose(W.sum(1), torch.ones(33)) and torch.allclose(W[::8], torch.eye(5), atol=1e-6)
+        xs, ks, info = ps.optimize(SplineShootingParams(key=4, x0=t32(x0), us_guess=t32(knots), horizon=33), return_info=True)
+        assert xs.shape == (34, nx) and ks.shape == (5, mj.nu)
+        us_from_knots = torch.minimum(torch.maximum(W.to(DEV) @ ks, lim[:, 0]), lim[:, 1])
+        assert torch.allclose(info["us_star"], us_from_knots, atol=1e-5)
+        assert torch.allclose(shoot(m, t32(x0), info["us_star"]), xs, atol=1e-4)
+        guess_cost = shoot_cost(m, t32(x0), torch.minimum(torch.maximum(W.to(DEV) @ t32(knots), lim[:, 0]), lim[:, 1])[None], cf)[0]
+        assert float(info["best_cost"]) <= float(guess_cost) * (1 + 1e-5)
+        one = SplinePredictiveSampler(model=m, cost_function=cf, nsamples=1, stdev=0.1, interp=interp)
+        _, k1 = one.optimize(SplineShootingParams(key=4, x0=t32(x0), us_guess=t32(knots), horizon=33))
+        assert torch.equal(k1, t32(knots))

@@ -46,6 +46,8 @@ struct HostModel {  // deep copy of AbrModelHost
   std::vector<float> dof_armature, dof_damping, dof_invweight0;
   std::vector<int> geom_type, geom_bodyid;
   std::vector<float> geom_size, geom_pos, geom_quat;
+  std::vector<int> geom_vertadr, geom_vertnum;  // convex vertex sets of box / mesh geoms
+  std::vector<float> vert;
   std::vector<int> pair_geom1, pair_geom2, pair_kind, pair_condim;
   std::vector<float> pair_friction, pair_solref, pair_solimp, pair_includemargin;
   std::vector<int> eq_type, eq_obj1id, eq_obj2id, eq_active;
@@ -121,6 +123,7 @@ static void copy_host_model(const AbrModelHost* h, HostModel& m) {
   m.dof_invweight0 = vcopy(h->dof_invweight0, nv);
   m.geom_type = vcopy(h->geom_type, ng); m.geom_bodyid = vcopy(h->geom_bodyid, ng);
   m.geom_size = vcopy(h->geom_size, 3 * ng); m.geom_pos = vcopy(h->geom_pos, 3 * ng); m.geom_quat = vcopy(h->geom_quat, 4 * ng);
+  m.geom_vertadr = vcopy(h->geom_vertadr, ng); m.geom_vertnum = vcopy(h->geom_vertnum, ng); m.vert = vcopy(h->vert, 3 * h->nvert);
   m.pair_geom1 = vcopy(h->pair_geom1, np); m.pair_geom2 = vcopy(h->pair_geom2, np);
   m.pair_kind = vcopy(h->pair_kind, np); m.pair_condim = vcopy(h->pair_condim, np);
   m.pair_friction = vcopy(h->pair_friction, 5 * np); m.pair_solref = vcopy(h->pair_solref, 2 * np);
@@ -162,7 +165,7 @@ static void row_prm(const AbrOpt& opt, const float* solref, const float* solimp,
   out[9] = (float)(1.0 / std::pow(1.0 - mid, power - 1.0));
 }
 
-static int pair_ncon(int kind) { return kind == ABR_PAIR_PLANE_CAPSULE ? 2 : 1; }
+static int pair_ncon(int kind) { return kind == ABR_PAIR_PLANE_CONVEX ? 4 : (kind == ABR_PAIR_PLANE_CAPSULE ? 2 : 1); }
 
 static int build_blob(const HostModel& m, bool alias, Layout& L, std::vector<float>& mf, std::vector<int>& mi) {
   memset(&L, 0, sizeof(L));
@@ -201,6 +204,7 @@ static int build_blob(const HostModel& m, bool alias, Layout& L, std::vector<flo
   L.f_dof_armature = P.addf(m.dof_armature); L.f_dof_damping = P.addf(m.dof_damping);
   L.f_qpos0 = P.addf(m.qpos0); L.f_qpos_spring = P.addf(m.qpos_spring);
   L.f_geom_size = P.addf(m.geom_size); L.f_geom_pos = P.addf(m.geom_pos); L.f_geom_quat = P.addf(m.geom_quat);
+  L.f_vert = P.addf(m.vert);  // mesh / box vertices live in the model blob (geom frame)
 
   // ---- tree tables
   std::vector<int> depth(nb, 0), rootslot(nb, 0), roots;
@@ -232,6 +236,7 @@ static int build_blob(const HostModel& m, bool alias, Layout& L, std::vector<flo
   L.i_dof_body = P.addi(m.dof_bodyid); L.i_dof_jnt = P.addi(m.dof_jntid);
   L.i_root_body = P.addi(roots);
   L.i_geom_body = P.addi(m.geom_bodyid);
+  L.i_geom_vertadr = P.addi(m.geom_vertadr); L.i_geom_vertnum = P.addi(m.geom_vertnum);
   L.i_pair_g1 = P.addi(m.pair_geom1); L.i_pair_g2 = P.addi(m.pair_geom2); L.i_pair_kind = P.addi(m.pair_kind);
 
   // M sparsity (ancestor pairs) and packed-index table

@@ -297,7 +297,72 @@ template <int G> __device__ void stage_collision(const Ctx& c) {
     const float* s1 = MF(geom_size) + 3 * g1;
     const float* s2 = MF(geom_size) + 3 * g2;
     float dist, pos[3], fr[9];
-    if (kind == ABR_PAIR_PLANE_SPHERE || kind == ABR_PAIR_PLANE_CAPSULE) {
+    if (kind == ABR_PAIR_PLANE_CONVEX) {
+      // mjx collision_convex.plane_convex: vertices in the convex geom's frame,
+      // support = penetration depth, manifold of up to 4 vertices among those within 1 mm of the deepest (first maximum wins, like
+      // jnp.argmax); a vertex picked twice yields an inactive contact (dist = 1). Each of the pair's 4 contact slots redoes the
+      // selection (the slots run on different lanes) and keeps its own vertex.
+      const int va = MI(geom_vertadr)[g2], nvt = MI(geom_vertnum)[g2];
+      const float* V = MF(vert) + 3 * va;
+      const float n[3] = {m1[2], m1[5], m1[8]};
+      const float dp[3] = {p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]};
+      float pl[3], nl[3];
+      for (int i = 0; i < 3; i++) { pl[i] = m2[i] * dp[0] + m2[3 + i] * dp[1] + m2[6 + i] * dp[2]; nl[i] = m2[i] * n[0] + m2[3 + i] * n[1] + m2[6 + i] * n[2]; }
+      float smax = -1e30f;
+#pragma unroll 1
+      for (int k = 0; k < nvt; k++) { const float d[3] = {pl[0] - V[3 * k], pl[1] - V[3 * k + 1], pl[2] - V[3 * k + 2]}; smax = fmaxf(smax, v_dot(d, nl)); }
+      const float thr = fmaxf(0.f, smax - 1e-3f);
+      auto sup = [&](int k) { const float d[3] = {pl[0] - V[3 * k], pl[1] - V[3 * k + 1], pl[2] - V[3 * k + 2]}; return v_dot(d, nl); };
+      auto msk = [&](int k) { return (sup(k) > thr) ? 0.f : -1e6f; };
+      int idx[4] = {0, 0, 0, 0};
+      float bv = -1e30f;
+#pragma unroll 1
+      for (int k = 0; k < nvt; k++) { const float v = msk(k); if (v > bv) { bv = v; idx[0] = k; } }
+      const float a[3] = {V[3 * idx[0]], V[3 * idx[0] + 1], V[3 * idx[0] + 2]};
+      bv = -1e30f;
+#pragma unroll 1
+      for (int k = 0; k < nvt; k++) {
+        const float d[3] = {a[0] - V[3 * k], a[1] - V[3 * k + 1], a[2] - V[3 * k + 2]};
+        const float v = v_dot(d, d) + msk(k);
+        if (v > bv) { bv = v; idx[1] = k; }
+      }
+      const float b[3] = {V[3 * idx[1]], V[3 * idx[1] + 1], V[3 * idx[1] + 2]};
+      const float amb[3] = {a[0] - b[0], a[1] - b[1], a[2] - b[2]};
+      float ab[3];
+      v_cross(nl, amb, ab);
+      bv = -1e30f;
+#pragma unroll 1
+      for (int k = 0; k < nvt; k++) {
+        const float d[3] = {a[0] - V[3 * k], a[1] - V[3 * k + 1], a[2] - V[3 * k + 2]};
+        const float v = fabsf(v_dot(d, ab)) + msk(k);
+        if (v > bv) { bv = v; idx[2] = k; }
+      }
+      const float cc[3] = {V[3 * idx[2]], V[3 * idx[2] + 1], V[3 * idx[2] + 2]};
+      const float amc[3] = {a[0] - cc[0], a[1] - cc[1], a[2] - cc[2]}, bmc[3] = {b[0] - cc[0], b[1] - cc[1], b[2] - cc[2]};
+      float ac[3], bc[3];
+      v_cross(nl, amc, ac);
+      v_cross(nl, bmc, bc);
+      bv = -1e30f;
+#pragma unroll 1
+      for (int h = 0; h < 2; h++) {  // concatenate([dist_bp, dist_ap]).argmax() % nvert
+#pragma unroll 1
+        for (int k = 0; k < nvt; k++) {
+          const float* o = h == 0 ? b : a;
+          const float* ax = h == 0 ? bc : ac;
+          const float d[3] = {o[0] - V[3 * k], o[1] - V[3 * k + 1], o[2] - V[3 * k + 2]};
+          const float v = fabsf(v_dot(d, ax)) + msk(k);
+          if (v > bv) { bv = v; idx[3] = k; }
+        }
+      }
+      int mine = idx[0];
+      bool unique = true;
+      for (int q = 1; q < 4; q++)
+        if (sub == q) { mine = idx[q]; for (int j = 0; j < q; j++) if (idx[j] == idx[q]) unique = false; }
+      dist = unique ? -sup(mine) : 1.f;
+      const float* v = V + 3 * mine;
+      for (int i = 0; i < 3; i++) pos[i] = p2[i] + m2[3 * i] * v[0] + m2[3 * i + 1] * v[1] + m2[3 * i + 2] * v[2] - 0.5f * dist * n[i];
+      make_frame(n, fr);
+    } else if (kind == ABR_PAIR_PLANE_SPHERE || kind == ABR_PAIR_PLANE_CAPSULE) {
       float n[3] = {m1[2], m1[5], m1[8]};
       float sp[3] = {p2[0], p2[1], p2[2]};
       float rad = s2[0];

@@ -27,16 +27,18 @@ _GEOM_TYPES = {
     "ellipsoid": GEOM_ELLIPSOID, "cylinder": GEOM_CYLINDER, "box": GEOM_BOX, "mesh": GEOM_MESH,
 }
 _JNT_TYPES = {"free": JNT_FREE, "ball": JNT_BALL, "slide": JNT_SLIDE, "hinge": JNT_HINGE}
-PAIR_PLANE_SPHERE, PAIR_PLANE_CAPSULE, PAIR_SPHERE_SPHERE, PAIR_SPHERE_CAPSULE, PAIR_CAPSULE_CAPSULE = range(5)
+PAIR_PLANE_SPHERE, PAIR_PLANE_CAPSULE, PAIR_SPHERE_SPHERE, PAIR_SPHERE_CAPSULE, PAIR_CAPSULE_CAPSULE, PAIR_PLANE_CONVEX = range(6)
 _PAIR_KIND = {
     (GEOM_PLANE, GEOM_SPHERE): PAIR_PLANE_SPHERE,
     (GEOM_PLANE, GEOM_CAPSULE): PAIR_PLANE_CAPSULE,
+    (GEOM_PLANE, GEOM_BOX): PAIR_PLANE_CONVEX,   # plane against a convex vertex set: up to 4 contacts (mjx collision_convex.plane_convex)
+    (GEOM_PLANE, GEOM_MESH): PAIR_PLANE_CONVEX,
     (GEOM_SPHERE, GEOM_SPHERE): PAIR_SPHERE_SPHERE,
     (GEOM_SPHERE, GEOM_CAPSULE): PAIR_SPHERE_CAPSULE,
     (GEOM_CAPSULE, GEOM_CAPSULE): PAIR_CAPSULE_CAPSULE,
 }
 PAIR_NCON = {PAIR_PLANE_SPHERE: 1, PAIR_PLANE_CAPSULE: 2, PAIR_SPHERE_SPHERE: 1, PAIR_SPHERE_CAPSULE: 1,
-             PAIR_CAPSULE_CAPSULE: 1}
+             PAIR_CAPSULE_CAPSULE: 1, PAIR_PLANE_CONVEX: 4}
 _DISABLE_BITS = {
     "constraint": 1, "equality": 2, "frictionloss": 4, "limit": 8, "contact": 16, "passive": 32,
     "gravity": 64, "clampctrl": 128, "warmstart": 256, "filterparent": 512, "actuation": 1024,
@@ -223,6 +225,39 @@ class _Defaults:
         return out
 
 
+def convex_vertices(points: np.ndarray) -> np.ndarray:
+    """Vertices of the convex hull of a point set, in their original order (MuJoCo / MJX collide a mesh geom as the convex
+    hull of its vertices). Degenerate sets (fewer than 4 points, coplanar) are returned unchanged."""
+    pts = np.asarray(points, dtype=np.float64).reshape(-1, 3)
+    if len(pts) < 4:
+        return pts
+    try:
+        from scipy.spatial import ConvexHull
+
+        keep = np.sort(np.unique(ConvexHull(pts).vertices))
+        return pts[keep]
+    except Exception:
+        return pts
+
+
+def box_vertices(size) -> np.ndarray:
+    """The 8 corners of a box geom (half extents `size`), in the order mjx builds them: x slowest, z fastest."""
+    s = np.asarray(size, dtype=np.float64)[:3]
+    return np.array([[sx * s[0], sy * s[1], sz * s[2]] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)])
+
+
+def read_obj_vertices(path) -> np.ndarray:
+    """`v x y z` lines of a Wavefront OBJ file."""
+    out = []
+    for line in Path(path).read_text().splitlines():
+        t = line.split()
+        if len(t) >= 4 and t[0] == "v":
+            out.append([float(t[1]), float(t[2]), float(t[3])])
+    if not out:
+        raise ValueError(f"{path}: no vertices")
+    return np.array(out)
+
+
 def _expand_includes(root: ET.Element, base: Path) -> None:
     for parent in list(root.iter()):
         for i, child in enumerate(list(parent)):
@@ -350,6 +385,10 @@ class _Compiler:
         self.bodies: List[dict] = []
         self.joints: List[dict] = []
         self.geoms: List[dict] = []
+        # <asset><mesh>: vertices inline (`vertex="x y z ..."`) or from an OBJ file under <compiler meshdir>, optional `scale`
+        self.meshes: Dict[str, np.ndarray] = {}
+        self.base_dir = Path(".")
+        self.meshdir = comp.get("meshdir", "") if comp is not None else ""
 
     # -- orientation of a frame-carrying element (quat | euler | axisangle | zaxis | xyaxes)
     def _orientation(self, attrs: Dict[str, str]) -> np.ndarray:
@@ -463,11 +502,29 @@ class _Compiler:
                     f"body {body['name']!r} moves but has no <inertial>; inertia-from-geom is not supported")
             self._walk(bnode, bid, cc)
 
+    def _load_meshes(self) -> None:
+        for anode in self.root.findall("asset"):
+            for mn in anode.findall("mesh"):
+                attrs = self.defaults.resolve("mesh", mn.get("class"))
+                attrs.update(mn.attrib)
+                if "vertex" in attrs:
+                    v = _floats(attrs["vertex"]).reshape(-1, 3)
+                elif "file" in attrs:
+                    f = self.base_dir / self.meshdir / attrs["file"]
+                    if f.suffix.lower() != ".obj":
+                        raise NotImplementedError(f"mesh file {f.name}: only Wavefront OBJ is read")
+                    v = read_obj_vertices(f)
+                else:
+                    raise ValueError("<mesh> needs `vertex` or `file`")
+                scale = _floats(attrs.get("scale"), 3, [1, 1, 1])
+                name = attrs.get("name") or Path(attrs.get("file", f"mesh{len(self.meshes)}")).stem
+                self.meshes[name] = convex_vertices(v * scale)
+
     def _geoms(self, node: ET.Element, bid: int, childclass: Optional[str]) -> None:
         for gn in node.findall("geom"):
             attrs = self.defaults.resolve("geom", gn.get("class", childclass))
             attrs.update(gn.attrib)
-            gtype = _GEOM_TYPES[attrs.get("type", "sphere")]
+            gtype = _GEOM_TYPES[attrs.get("type", "mesh" if "mesh" in attrs else "sphere")]
             size = np.zeros(3)
             s = _floats(attrs.get("size"))
             if s is not None:
@@ -480,8 +537,16 @@ class _Compiler:
                 pos = 0.5 * (a + b)
                 quat = _quat_z_to_vec(b - a)
                 size[1] = 0.5 * np.linalg.norm(b - a)
+            verts = np.zeros((0, 3))
+            if gtype == GEOM_BOX:
+                verts = box_vertices(size)
+            elif gtype == GEOM_MESH:
+                if attrs.get("mesh") not in self.meshes:
+                    raise ValueError(f"geom {attrs.get('name')!r}: unknown mesh {attrs.get('mesh')!r}")
+                verts = self.meshes[attrs["mesh"]]  # kept in the file's coordinates = the geom frame (MuJoCo re-centres meshes on their
+                #                                     inertial frame and compensates in geom_pos / geom_quat: same world-frame vertices)
             self.geoms.append(dict(
-                name=attrs.get("name", f"geom{len(self.geoms)}"), type=gtype, body=bid, size=size, pos=pos,
+                name=attrs.get("name", f"geom{len(self.geoms)}"), type=gtype, body=bid, size=size, pos=pos, verts=verts,
                 quat=quat, contype=int(attrs.get("contype", 1)), conaffinity=int(attrs.get("conaffinity", 1)),
                 condim=int(attrs.get("condim", 3)), priority=int(attrs.get("priority", 0)),
                 friction=_floats(attrs.get("friction"), 3, [1.0, 0.005, 0.0001]),
@@ -530,6 +595,7 @@ class _Compiler:
         self.bodies.append(dict(name="world", parent=0, pos=np.zeros(3), quat=np.array([1.0, 0, 0, 0]),
                                 ipos=np.zeros(3), iquat=np.array([1.0, 0, 0, 0]), mass=0.0,
                                 inertia=np.zeros(3), has_inertial=False, joints=[]))
+        self._load_meshes()
         for wb in root.findall("worldbody"):
             self._geoms(wb, 0, None)
             self._walk(wb, 0, None)
@@ -638,6 +704,16 @@ class _Compiler:
         m.geom_solimp = np.array([g["solimp"] for g in self.geoms]).reshape(ngeom, 5)
         m.geom_margin = np.array([g["margin"] for g in self.geoms], dtype=np.float64)
         m.geom_gap = np.array([g["gap"] for g in self.geoms], dtype=np.float64)
+        # convex vertex sets of box / mesh geoms, in the geom frame (the engine's model blob carries them)
+        adr, num, pool = [], [], []
+        for g in self.geoms:
+            adr.append(sum(num))
+            num.append(len(g["verts"]))
+            pool.extend(g["verts"].tolist())
+        m.geom_vertadr = np.array(adr, dtype=np.int32)
+        m.geom_vertnum = np.array(num, dtype=np.int32)
+        m.nvert = int(sum(num))
+        m.vert = np.array(pool, dtype=np.float64).reshape(m.nvert, 3)
 
         m.names = dict(
             body=[b["name"] for b in self.bodies], joint=[j["name"] for j in self.joints],
@@ -865,6 +941,8 @@ def compile_mjcf(path, force_float: bool = False) -> MjModel:
     if root.tag != "mujoco":
         raise ValueError(f"{path} is not an MJCF file")
     _expand_includes(root, path.parent)
-    m = _Compiler(root, force_float=force_float).compile()
+    comp = _Compiler(root, force_float=force_float)
+    comp.base_dir = path.parent
+    m = comp.compile()
     m.source = str(path)
     return m

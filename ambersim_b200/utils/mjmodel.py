@@ -106,6 +106,20 @@ def from_mjmodel(mj) -> mjcf.MjModel:
         setattr(m, k, _arr(getattr(mj, k), np.int32, (ngeom,)))
     for k in ("geom_solmix", "geom_margin", "geom_gap"):
         setattr(m, k, _arr(getattr(mj, k), np.float64, (ngeom,)))
+    # convex vertex sets: the 8 corners of a box, the hull vertices of a mesh (mj.mesh_vert / mesh_vertadr / mesh_vertnum via geom_dataid)
+    adr, num, pool = [], [], []
+    dataid = _arr(getattr(mj, "geom_dataid", np.full(ngeom, -1)), np.int32, (ngeom,))
+    for g in range(ngeom):
+        v = np.zeros((0, 3))
+        if int(m.geom_type[g]) == mjcf.GEOM_BOX:
+            v = mjcf.box_vertices(m.geom_size[g])
+        elif int(m.geom_type[g]) == mjcf.GEOM_MESH and dataid[g] >= 0 and hasattr(mj, "mesh_vert"):
+            a, n = int(np.ravel(mj.mesh_vertadr)[dataid[g]]), int(np.ravel(mj.mesh_vertnum)[dataid[g]])
+            v = mjcf.convex_vertices(_arr(mj.mesh_vert, np.float64).reshape(-1, 3)[a:a + n])
+        adr.append(sum(num)); num.append(len(v)); pool.extend(np.asarray(v).tolist())
+    m.geom_vertadr, m.geom_vertnum = np.array(adr, dtype=np.int32), np.array(num, dtype=np.int32)
+    m.nvert = int(sum(num))
+    m.vert = np.array(pool, dtype=np.float64).reshape(m.nvert, 3)
     geoms = [dict(name=f"geom{g}", type=int(m.geom_type[g]), body=int(m.geom_bodyid[g]), contype=int(m.geom_contype[g]),
                   conaffinity=int(m.geom_conaffinity[g]), condim=int(m.geom_condim[g]), priority=int(m.geom_priority[g]),
                   friction=m.geom_friction[g], solmix=float(m.geom_solmix[g]), solref=m.geom_solref[g], solimp=m.geom_solimp[g],
@@ -183,6 +197,18 @@ def to_mujoco_layout(m: mjcf.MjModel) -> SimpleNamespace:
             "actuator_gaintype actuator_biastype actuator_ctrllimited actuator_forcelimited actuator_ctrlrange actuator_forcerange").split()
     for k in same:
         setattr(ns, k, np.array(getattr(m, k)))
+    # meshes: one mjModel mesh per mesh geom (geom_dataid -> mesh_vertadr / mesh_vertnum / mesh_vert), boxes carry no data
+    dataid, madr, mnum, mv = [], [], [], []
+    for g in range(m.ngeom):
+        if int(m.geom_type[g]) == mjcf.GEOM_MESH:
+            dataid.append(len(madr)); madr.append(len(mv)); mnum.append(int(m.geom_vertnum[g]))
+            mv.extend(np.asarray(m.vert)[m.geom_vertadr[g]:m.geom_vertadr[g] + m.geom_vertnum[g]].tolist())
+        else:
+            dataid.append(-1)
+    ns.geom_dataid = np.array(dataid, dtype=np.int32)
+    ns.mesh_vertadr, ns.mesh_vertnum = np.array(madr, dtype=np.int32), np.array(mnum, dtype=np.int32)
+    ns.mesh_vert = np.array(mv, dtype=np.float64).reshape(-1, 3)
+    ns.nmesh = len(madr)
     ns.dof_frictionloss = np.zeros(m.nv)
     ns.eq_active0 = np.array(m.eq_active, dtype=np.uint8)
     nu = m.nu

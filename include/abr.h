@@ -49,14 +49,15 @@ extern "C" {
 
 /* enums (values = MuJoCo's) */
 enum { ABR_JNT_FREE = 0, ABR_JNT_BALL = 1, ABR_JNT_SLIDE = 2, ABR_JNT_HINGE = 3 };
-enum { ABR_GEOM_PLANE = 0, ABR_GEOM_SPHERE = 2, ABR_GEOM_CAPSULE = 3 };
+enum { ABR_GEOM_PLANE = 0, ABR_GEOM_SPHERE = 2, ABR_GEOM_CAPSULE = 3, ABR_GEOM_BOX = 6, ABR_GEOM_MESH = 7 };
 enum { ABR_INT_EULER = 0, ABR_INT_RK4 = 1 };
 enum { ABR_SOLVER_CG = 1, ABR_SOLVER_NEWTON = 2 };
 enum { ABR_EQ_JOINT = 2 };
 enum { ABR_GAIN_FIXED = 0, ABR_GAIN_AFFINE = 1 };
 enum { ABR_BIAS_NONE = 0, ABR_BIAS_AFFINE = 1 };
 enum { ABR_PAIR_PLANE_SPHERE = 0, ABR_PAIR_PLANE_CAPSULE = 1, ABR_PAIR_SPHERE_SPHERE = 2,
-       ABR_PAIR_SPHERE_CAPSULE = 3, ABR_PAIR_CAPSULE_CAPSULE = 4 };
+       ABR_PAIR_SPHERE_CAPSULE = 3, ABR_PAIR_CAPSULE_CAPSULE = 4,
+       ABR_PAIR_PLANE_CONVEX = 5 /* plane vs box / mesh: 4 contacts (mjx collision_convex.plane_convex) */ };
 /* mjtDisableBit */
 enum {
   ABR_DSBL_CONSTRAINT = 1, ABR_DSBL_EQUALITY = 2, ABR_DSBL_FRICTIONLOSS = 4, ABR_DSBL_LIMIT = 8,
@@ -99,7 +100,7 @@ typedef struct AbrModelHost {
   int ngeom;
   int neq;
   int npair;       /* statically enumerated colliding geom pairs (MJX enumerates at trace time) */
-  int reserved0;
+  int nvert;       /* vertices of all convex (box / mesh) geoms */
   AbrOpt opt;
   /* bodies [nbody] */
   const int* body_parentid;
@@ -142,6 +143,9 @@ typedef struct AbrModelHost {
   const float* geom_size;       /* [ngeom,3] */
   const float* geom_pos;        /* [ngeom,3] */
   const float* geom_quat;       /* [ngeom,4] */
+  const int* geom_vertadr;      /* [ngeom] first vertex of a box / mesh geom in `vert` */
+  const int* geom_vertnum;      /* [ngeom] number of vertices (0 for non-convex-set geoms) */
+  const float* vert;            /* [nvert,3] convex-hull vertices in the geom frame (boxes: the 8 corners) */
   /* static contact pairs [npair]; mixing of friction/solref/solimp/margin done by the loader */
   const int* pair_geom1;
   const int* pair_geom2;

@@ -202,7 +202,7 @@ template <class T> void cho_solve(const T* L, const T* b, T* x, int n) {
 // ----------------------------------------------------------------------------- the simulator
 struct Sizes { int ncon, ne, nl, nefc; };
 
-inline int pair_ncon(int kind) { return kind == ABR_PAIR_PLANE_CAPSULE ? 2 : 1; }
+inline int pair_ncon(int kind) { return kind == ABR_PAIR_PLANE_CONVEX ? 4 : (kind == ABR_PAIR_PLANE_CAPSULE ? 2 : 1); }
 
 Sizes compute_sizes(const AbrModelHost* m) {
   Sizes s{0, 0, 0, 0};
@@ -476,6 +476,67 @@ template <class T> struct Sim {
           for (int i = 0; i < 3; i++) sp[i] = p2[i] + (s == 0 ? axis[i] * half : -(axis[i] * half));
           plane_sphere_core(n, p1, sp, rad, &con_dist[c], &con_pos[3 * c]);
           for (int i = 0; i < 3; i++) { con_frame[9 * c + i] = n[i]; con_frame[9 * c + 3 + i] = b[i]; con_frame[9 * c + 6 + i] = cr[i]; }
+          con_pair[c++] = p;
+        }
+      } else if (kind == ABR_PAIR_PLANE_CONVEX) {
+        // mjx collision_convex.plane_convex [MEMORY, MJX 3.1.x]: everything in the convex geom's frame. support = penetration
+        // depth of each vertex; the manifold is picked among the vertices within 1 mm of the deepest one by _manifold_points
+        // (a = first masked vertex, b = furthest from a, c = furthest from the line ab, d = furthest from the edges ac / bc;
+        // jnp.argmax = FIRST maximum); a vertex picked twice gives an inactive contact (dist = 1).
+        const int va = m->geom_vertadr[g2], nvt = m->geom_vertnum[g2];
+        T n[3] = {m1[2], m1[5], m1[8]};
+        T dp[3] = {p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]};
+        T pl[3], nl[3];  // plane point and normal in the convex frame: mat' (.)
+        for (int i = 0; i < 3; i++) { pl[i] = m2[i] * dp[0] + m2[3 + i] * dp[1] + m2[6 + i] * dp[2]; nl[i] = m2[i] * n[0] + m2[3 + i] * n[1] + m2[6 + i] * n[2]; }
+        std::vector<T> vx(3 * nvt), support(nvt), mask(nvt);
+        T smax = T(-1e30);
+        for (int k = 0; k < nvt; k++) {
+          for (int i = 0; i < 3; i++) vx[3 * k + i] = F(m->vert, 3 * (va + k) + i);
+          T d[3] = {pl[0] - vx[3 * k], pl[1] - vx[3 * k + 1], pl[2] - vx[3 * k + 2]};
+          support[k] = dot3(d, nl);
+          if (support[k] > smax) smax = support[k];
+        }
+        const T thr = Max(T(0), smax - T(1e-3));
+        for (int k = 0; k < nvt; k++) mask[k] = (support[k] > thr) ? T(0) : T(-1e6);
+        auto argmax = [&](auto score) { int best = 0; T bv = score(0); for (int k = 1; k < nvt; k++) { T v = score(k); if (v > bv) { bv = v; best = k; } } return best; };
+        const int ia = argmax([&](int k) { return mask[k]; });
+        const T* a = &vx[3 * ia];
+        const int ib = argmax([&](int k) { T d[3] = {a[0] - vx[3 * k], a[1] - vx[3 * k + 1], a[2] - vx[3 * k + 2]}; return dot3(d, d) + mask[k]; });
+        const T* b = &vx[3 * ib];
+        T amb[3] = {a[0] - b[0], a[1] - b[1], a[2] - b[2]}, ab[3];
+        cross(nl, amb, ab);
+        const int ic = argmax([&](int k) { T d[3] = {a[0] - vx[3 * k], a[1] - vx[3 * k + 1], a[2] - vx[3 * k + 2]}; return Abs(dot3(d, ab)) + mask[k]; });
+        const T* cc = &vx[3 * ic];
+        T amc[3] = {a[0] - cc[0], a[1] - cc[1], a[2] - cc[2]}, bmc[3] = {b[0] - cc[0], b[1] - cc[1], b[2] - cc[2]}, ac[3], bc[3];
+        cross(nl, amc, ac);
+        cross(nl, bmc, bc);
+        // concatenate([dist_bp, dist_ap]).argmax() % nvert: the b-edge scores come first
+        int id = 0;
+        {
+          T bv = T(-1e30);
+          for (int h = 0; h < 2; h++)
+            for (int k = 0; k < nvt; k++) {
+              const T* o = h == 0 ? b : a;
+              const T* ax = h == 0 ? bc : ac;
+              T d[3] = {o[0] - vx[3 * k], o[1] - vx[3 * k + 1], o[2] - vx[3 * k + 2]};
+              T v = Abs(dot3(d, ax)) + mask[k];
+              if (v > bv) { bv = v; id = k; }
+            }
+        }
+        const int idx[4] = {ia, ib, ic, id};
+        T fr[9];
+        make_frame(n, fr);
+        for (int q = 0; q < 4; q++) {
+          bool unique = true;
+          for (int j = 0; j < q; j++) if (idx[j] == idx[q]) unique = false;
+          const T dist = unique ? -support[idx[q]] : T(1);
+          const T* v = &vx[3 * idx[q]];
+          for (int i = 0; i < 3; i++) {
+            const T wp = p2[i] + m2[3 * i] * v[0] + m2[3 * i + 1] * v[1] + m2[3 * i + 2] * v[2];
+            con_pos[3 * c + i] = wp - T(0.5) * dist * n[i];
+          }
+          con_dist[c] = dist;
+          for (int i = 0; i < 9; i++) con_frame[9 * c + i] = fr[i];
           con_pair[c++] = p;
         }
       } else if (kind == ABR_PAIR_SPHERE_SPHERE) {

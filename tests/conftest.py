@@ -24,7 +24,8 @@ MODELS = {
     # slide joint, condim-1 contacts, a trunk contact, a tilted floor
     "tripod": (str(ROOT / "tests/models/tripod.xml"), "home"),
     "tripod3": (str(ROOT / "tests/models/tripod3.xml"), "home"),
-    "fixedbase": (str(ROOT / "tests/models/fixedbase.xml"), None),  # hand kernels: static base, three chains, four joint equalities  # three leaf paths: the 4-lane group carries a dummy lane
+    "fixedbase": (str(ROOT / "tests/models/fixedbase.xml"), None),
+    "boxbot": (str(ROOT / "tests/models/boxbot.xml"), "home"),  # plane - convex collision: a box and a convex mesh foot (4 contacts each) + a sphere  # hand kernels: static base, three chains, four joint equalities  # three leaf paths: the 4-lane group carries a dummy lane
 }
 
 

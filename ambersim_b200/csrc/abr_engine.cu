@@ -936,6 +936,7 @@ static int launch_env(const AbrModel* m, const Layout& L, const EnvArgs& a_in, c
     if (a.E != m->dr_E) return fail(ABR_EINVAL, "env call: batch size differs from the one given to abr_env_set_randomization");
     a.dr = m->dr;
   }
+  if (use_hand(m, L, false) && !a.dbg && !a.fo_on && !a.t_steps && !a.dr) return launch_result(launch_hand_env_3(L, a, st));
   if (use_limb(m, L, false, a.dbg != nullptr || a.fo_on)) {
     const bool spec = getenv("ABR_LIMB_GENERAL") == nullptr;
     const bool fast = (L.disableflags == ABR_DSBL_EULERDAMP || L.disableflags == 0) && L.iterations == 1 && L.l_pow2 && L.l_hinge &&
@@ -1074,7 +1075,7 @@ int abr_model_describe(const AbrModel* m, char* buf, int cap) {
                   : (bip ? "biped pattern, contact-body form" : "sharing pattern from the table"), 1 << L.lg2G,
              fast ? (L.disableflags == 0 ? "fast (eulerdamp on)" : "fast (eulerdamp off)") : "general");
   } else if (use_hand(m, L, false)) {
-    snprintf(tmp, sizeof(tmp), "hand kernels <NL=%d> (fixed-base chains, %d joint-equality rows), %d lanes per world; env calls: generic kernels",
+    snprintf(tmp, sizeof(tmp), "hand kernels <NL=%d> (fixed-base chains, %d joint-equality rows), %d lanes per world",
              L.lNL, L.ne, 1 << L.lg2G);
   } else {
     snprintf(tmp, sizeof(tmp), "generic kernels, %s lanes per world%s", m->lanes > 1 ? std::to_string(m->lanes).c_str() : "8 / 16 / 32 (by batch size)",

@@ -216,9 +216,9 @@ template <int NL> __device__ __forceinline__ void forward(Lane<NL>& s, const Cfg
 #pragma unroll
   for (int i = 0; i < N; i++) as[i] = fs[i];
   ldl_solve<N>(F, invD, as, S);
-  if (C.nefc == 0) {
+  if (C.nefc == 0) {  // no constraint rows: MJX returns qacc_smooth without entering the solver, qacc_warmstart keeps its value
 #pragma unroll
-    for (int i = 0; i < N; i++) { s.a[i] = as[i]; s.warm[i] = as[i]; fc[i] = 0.f; }
+    for (int i = 0; i < N; i++) { s.a[i] = as[i]; fc[i] = 0.f; }
     return;
   }
   // ---------------------------------------------------------------- constraint rows: global equality rows, local limit rows
@@ -572,6 +572,77 @@ __global__ void __launch_bounds__(128) k_hand_rollout(const __grid_constant__ La
   }
 }
 
+// MjxEnv.pipeline_init / pipeline_step (rl/base.py:81-96) with the auto-reset blend, for fixed-base chains (the reference's own
+// RL example is the pendulum, rl/pendulum/swingup.py). The fused task epilogue and per-env randomisation stay on the generic kernels.
+template <int NL>
+__global__ void __launch_bounds__(128) k_hand_env(const __grid_constant__ Layout L, const __grid_constant__ EnvArgs A) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr Map mp{NL};
+  constexpr int NTRI = NL * (NL + 1) / 2;
+  const int ntab = mp.total() * kStride;
+  const int nu = L.nu, nq = L.nq, nv = L.nv;
+  for (int i = threadIdx.x; i < ntab; i += blockDim.x) smem[i] = A.blob[L.f_htab + i];
+  __syncthreads();
+  const int lg = L.lg2G;
+  const int g = threadIdx.x & ((1 << lg) - 1);
+  const int wraw = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> lg);
+  const bool valid = wraw < A.E;
+  const int w = valid ? wraw : A.E - 1;
+  const Cfg C = make_cfg(L, smem, g);
+  const bool reset = A.reset_mask && A.reset_mask[w];
+  const float* sq = (reset ? A.first_qpos : A.qpos) + (size_t)w * nq;
+  const float* sv = (reset ? A.first_qvel : A.qvel) + (size_t)w * nv;
+  const float* sw = reset ? A.first_warm : A.warm;
+  if (sw) sw += (size_t)w * nv;
+  Lane<NL> s;
+  int gd[NL], gq[NL];
+#pragma unroll
+  for (int p = 1; p <= NL; p++) {
+    gd[p - 1] = HTI(mp.ijnt(p) + 1); gq[p - 1] = HTI(mp.ijnt(p) + 2);
+    const int ga = HTI(mp.ijnt(p) + 3);
+    s.q[p - 1] = (gd[p - 1] >= 0) ? sq[gq[p - 1]] : 0.f;
+    s.v[p - 1] = (gd[p - 1] >= 0) ? sv[gd[p - 1]] : 0.f;
+    s.warm[p - 1] = (gd[p - 1] >= 0 && sw) ? sw[gd[p - 1]] : 0.f;
+    s.ctrl[p - 1] = (ga >= 0 && A.ctrl) ? A.ctrl[(size_t)w * nu + ga] : 0.f;
+    s.a[p - 1] = 0.f;
+  }
+  const int nfw = A.forward_only ? 1 : A.nsubsteps;
+#pragma unroll 1
+  for (int it = 0; it < nfw; it++) {
+    float M[NTRI], fs[NL], fc[NL];
+    forward<NL>(s, C, M, fs, fc);
+    if (!A.forward_only) euler<NL>(s, C, M, fs, fc);
+  }
+  if (valid) {
+    float* oq = A.qpos + (size_t)w * nq; float* ov = A.qvel + (size_t)w * nv;
+    float* ow = A.warm ? A.warm + (size_t)w * nv : nullptr; float* oa = A.qacc ? A.qacc + (size_t)w * nv : nullptr;
+#pragma unroll
+    for (int d = 0; d < NL; d++) {
+      if (gd[d] >= 0) {
+        oq[gq[d]] = s.q[d];
+        if (!A.forward_only) ov[gd[d]] = s.v[d];
+        if (ow) ow[gd[d]] = s.warm[d];
+        if (oa) oa[gd[d]] = s.a[d];
+      }
+    }
+    if (A.time && g == 0) {
+      const float t0 = reset ? 0.f : A.time[w];
+      A.time[w] = A.forward_only ? t0 : t0 + L.timestep * (float)A.nsubsteps;
+    }
+  }
+}
+
+template <int NL> int launch_hand_env_t(const Layout& L, const EnvArgs& a, cudaStream_t st) {
+  constexpr Map mp{NL};
+  const long threads = (long)a.E << L.lg2G;
+  const int tpb = threads <= 32 ? 32 : (threads <= 64 * 148 ? 64 : 128);
+  const size_t sm = sizeof(float) * ((size_t)mp.total() * kStride);
+  cudaError_t e = cudaFuncSetAttribute(k_hand_env<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  if (e != cudaSuccess) return (int)e;
+  k_hand_env<NL><<<(int)((threads + tpb - 1) / tpb), tpb, sm, st>>>(L, a);
+  return (int)cudaGetLastError();
+}
+
 template <int NL> int launch_hand_rollout_t(const Layout& L, const RolloutArgs& a, cudaStream_t st) {
   constexpr Map mp{NL};
   const long threads = (long)a.nworld << L.lg2G;
@@ -590,6 +661,7 @@ template <int NL> int launch_hand_rollout_t(const Layout& L, const RolloutArgs& 
 }  // namespace hand
 
 int launch_hand_rollout_3(const Layout& L, const RolloutArgs& a, cudaStream_t st);
+int launch_hand_env_3(const Layout& L, const EnvArgs& a, cudaStream_t st);
 
 }  // namespace abr
 #endif

@@ -112,8 +112,15 @@ def test_engine_matches_oracle_on_convex_contacts(load_model):
     for e in range(E):
         ref = o.forward(f.qpos[e].cpu().numpy(), vs[e], cs[e], np.zeros(mj.nv))
         active += int((ref["contact_dist"] < 0).sum())
-        assert np.abs(ref["contact_dist"] - f.contact_dist[e].cpu().numpy()).max() < 2e-6
-        assert np.abs(ref["contact_pos"] - f.contact_pos[e].cpu().numpy()).max() < 2e-6
+        gd, gp = f.contact_dist[e].cpu().numpy(), f.contact_pos[e].cpu().numpy()
+        for c0, c1 in ((0, 4), (4, 8), (8, 9)):  # box pair, mesh pair, sphere
+            if (ref["contact_dist"][c0:c1] < 0).any():
+                assert np.abs(ref["contact_dist"][c0:c1] - gd[c0:c1]).max() < 2e-6
+                assert np.abs(ref["contact_pos"][c0:c1] - gp[c0:c1]).max() < 2e-6
+            else:
+                # nothing penetrates: every vertex carries the mask offset -1e6, which swallows the float32 scores (ulp 0.06), so the
+                # manifold picked among the SEPARATED vertices depends on the precision (in MJX's float32 too); the contacts are inactive
+                assert np.all(gd[c0:c1] > 0)
         assert np.abs(ref["contact_frame"] - f.contact_frame[e].cpu().numpy()).max() < 2e-6
         for n in ("efc_D", "efc_aref", "efc_force", "qfrc_constraint", "qacc_smooth"):
             r, g = ref[n].ravel(), getattr(f, n)[e].cpu().numpy().ravel()

@@ -446,7 +446,8 @@ def test_model_describe_names_the_serving_kernels(load_model):
     assert "general variant" in m.replace(opt=m.opt.replace(iterations=3)).describe()
     assert "biped pattern, contact-body form" in model_with(load_model, "biped")[1].describe()
     assert "sharing pattern from the table" in model_with(load_model, "tripod")[1].describe()
-    assert m.describe().count("\n") == 0 and "generic kernels" in model_with(load_model, "bh280")[1].describe()
+    assert m.describe().count("\n") == 0 and "hand kernels <NL=3>" in model_with(load_model, "bh280")[1].describe()
+    assert "generic kernels" in model_with(load_model, "bh280", solver=1)[1].describe() and "generic kernels" in model_with(load_model, "boxbot")[1].describe()
     m.set_lanes(16)
     assert "generic kernels, 16 lanes" in m.describe()
 

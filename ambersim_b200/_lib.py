@@ -60,6 +60,8 @@ def lib():
     L.abr_model_set_lanes.argtypes = [vp, C.c_int]
     L.abr_model_describe.argtypes = [vp, C.c_char_p, C.c_int]
     L.abr_model_reserve.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.abr_workspace_bytes.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]
+    L.abr_model_set_workspace.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int]
     L.abr_cost_create.argtypes = [C.POINTER(S["AbrQuadCostHost"]), C.c_int, C.POINTER(vp)]
     L.abr_cost_destroy.argtypes = [vp]
     L.abr_rollout_dev.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]

@@ -57,11 +57,25 @@ struct HostModel {  // deep copy of AbrModelHost
   std::vector<float> qpos0, qpos_spring;
 };
 
+// The entry points run on the model's device and leave the caller's current device as they found it (a single-process
+// multi-GPU host framework keeps its own notion of "current").
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err;
+  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); err = cudaSetDevice(dev); }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define ABR_ON_DEVICE(dev)                                                                                                   \
+  DeviceGuard device_guard_(dev);                                                                                           \
+  if (device_guard_.err != cudaSuccess) return fail(ABR_ECUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(device_guard_.err))
+
 struct Scratch {
   void* p = nullptr;
   size_t cap = 0;
+  bool external = false;  // carved from a caller-provided workspace (abr_model_set_workspace): never grown, never freed here
   int ensure(size_t bytes) {
     if (bytes <= cap) return ABR_OK;
+    if (external) return fail(ABR_ECAPACITY, "the caller-provided workspace is too small for this call (abr_workspace_bytes sizes it)");
     if (p) cudaFree(p);
     p = nullptr; cap = 0;
     cudaError_t e = cudaMalloc(&p, bytes);
@@ -69,7 +83,8 @@ struct Scratch {
     cap = bytes;
     return ABR_OK;
   }
-  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  void release() { if (p && !external) cudaFree(p); p = nullptr; cap = 0; external = false; }
+  void adopt(void* ptr, size_t bytes) { release(); p = ptr; cap = bytes; external = true; }
 };
 
 struct AbrModel {
@@ -88,6 +103,7 @@ struct AbrModel {
   const float* dr = nullptr; int dr_E = 0;  // abr_env_set_randomization
   std::vector<cudaEvent_t> ev;
   Scratch s_costs, s_in, s_out, s_dbg, s_traj, s_carry;
+  Scratch s_mpc;  // abr_mpc_dev's winner buffers: its own, so that a *_host call on the handle's stream never shares scratch with it
 };
 
 struct AbrCost {
@@ -979,7 +995,7 @@ static int rebuild(AbrModel* m) {
   std::vector<float> f2; std::vector<int> i2;
   rc = build_blob(m->hm, false, m->lay_dbg, f2, i2);
   if (rc) return rc;
-  CK(cudaSetDevice(m->device));
+  ABR_ON_DEVICE(m->device);
   if (m->d_blob) { cudaFree(m->d_blob); m->d_blob = nullptr; }
   const size_t bytes = sizeof(float) * ((size_t)m->lay.n_mf + m->lay.n_mi);
   CK(cudaMalloc(&m->d_blob, bytes));
@@ -1008,6 +1024,7 @@ int abr_model_create(const AbrModelHost* host, int device, AbrModel** out) {
   *out = nullptr;
   if (abr_device_count() <= 0) return fail(ABR_ENODEVICE, "no CUDA device: the engine has no CPU path");
   if (host->nq < 0 || host->nv < 0 || host->nbody < 1) return fail(ABR_EINVAL, "abr_model_create: bad sizes");
+  ABR_ON_DEVICE(device);  // the blob, the handle's streams and its scratch all live on `device`
   AbrModel* m = new AbrModel();
   m->device = device;
   copy_host_model(host, m->hm);
@@ -1024,9 +1041,9 @@ int abr_model_create(const AbrModelHost* host, int device, AbrModel** out) {
 
 int abr_model_destroy(AbrModel* m) {
   if (!m) return ABR_OK;
-  cudaSetDevice(m->device);
+  DeviceGuard guard(m->device);
   if (m->d_blob) cudaFree(m->d_blob);
-  m->s_costs.release(); m->s_in.release(); m->s_out.release(); m->s_dbg.release(); m->s_traj.release(); m->s_carry.release();
+  m->s_costs.release(); m->s_in.release(); m->s_out.release(); m->s_dbg.release(); m->s_traj.release(); m->s_carry.release(); m->s_mpc.release();
   for (cudaEvent_t e : m->ev) cudaEventDestroy(e);
   if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
   if (m->stream) cudaStreamDestroy(m->stream);
@@ -1150,7 +1167,8 @@ int abr_cost_create(const AbrQuadCostHost* h, int device, AbrCost** out) {
   for (int i = 0; i < nu; i++) p[i] = h->R[i * nu + i];
   AbrCost* c = new AbrCost();
   c->device = device; c->nx = nx; c->nu = nu; c->diag = diag ? 1 : 0;
-  if (cudaSetDevice(device) != cudaSuccess || cudaMalloc(&c->d, sizeof(float) * buf.size()) != cudaSuccess ||
+  DeviceGuard guard(device);
+  if (guard.err != cudaSuccess || cudaMalloc(&c->d, sizeof(float) * buf.size()) != cudaSuccess ||
       cudaMemcpy(c->d, buf.data(), sizeof(float) * buf.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
     delete c;
     return fail(ABR_ECUDA, std::string("abr_cost_create: ") + cudaGetErrorString(cudaGetLastError()));
@@ -1161,7 +1179,7 @@ int abr_cost_create(const AbrQuadCostHost* h, int device, AbrCost** out) {
 
 int abr_cost_destroy(AbrCost* c) {
   if (!c) return ABR_OK;
-  cudaSetDevice(c->device);
+  DeviceGuard guard(c->device);
   if (c->d) cudaFree(c->d);
   delete c;
   return ABR_OK;
@@ -1169,7 +1187,7 @@ int abr_cost_destroy(AbrCost* c) {
 
 int abr_model_reserve(AbrModel* m, int nworld, int N, int B, int S) {
   if (!m || nworld < 0 || N < 0 || B < 0 || S < 0) return fail(ABR_EINVAL, "abr_model_reserve: bad argument");
-  CK(cudaSetDevice(m->device));
+  ABR_ON_DEVICE(m->device);
   const size_t nx = m->lay.nx, nu = m->lay.nu, nxs = (size_t)(N + 1) * nx, nus = (size_t)N * nu;
   int rc = ABR_OK;
   if (B > 0 && S > 0) {  // sampler: per-sample costs, kept trajectories (when under the cap), host staging of one solve
@@ -1189,6 +1207,42 @@ int abr_model_reserve(AbrModel* m, int nworld, int N, int B, int S) {
   return rc;
 }
 
+// ---- caller-provided workspace for the stream-ordered (*_dev) calls: SURVEY 8(b)'s "no hidden allocation on the hot path"
+// Layout of the workspace: [per-sample costs B*S][kept trajectories B*S*((N+1) nx + N nu), when under the keep cap][mpc winner buffers]
+static void workspace_plan(const AbrModel* m, int N, int B, int S, size_t out[3]) {
+  const size_t nx = m->lay.nx, nu = m->lay.nu, nxs = (size_t)(N + 1) * nx, nus = (size_t)N * nu;
+  auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  size_t keep_cap = (size_t)256 << 20;
+  if (const char* e = getenv("ABR_KEEP_TRAJ_MB")) keep_cap = (size_t)atol(e) << 20;
+  const size_t traj = sizeof(float) * (size_t)B * S * (nxs + nus);
+  out[0] = up(sizeof(float) * (size_t)B * S);
+  out[1] = (B > 0 && S > 0 && traj <= keep_cap) ? up(traj + 16) : 0;
+  out[2] = up(sizeof(float) * (nxs + nus + 8));
+}
+int abr_workspace_bytes(const AbrModel* m, int N, int B, int S, size_t* bytes) {
+  if (!m || !bytes || N < 0 || B < 0 || S < 0) return fail(ABR_EINVAL, "abr_workspace_bytes: bad argument");
+  size_t part[3];
+  workspace_plan(m, N, B, S, part);
+  *bytes = part[0] + part[1] + part[2];
+  return ABR_OK;
+}
+int abr_model_set_workspace(AbrModel* m, void* workspace, size_t bytes, int N, int B, int S) {
+  if (!m || N < 0 || B < 0 || S < 0) return fail(ABR_EINVAL, "abr_model_set_workspace: bad argument");
+  if (!workspace) {  // back to handle-owned scratch (grown on first use / by abr_model_reserve)
+    m->s_costs.release(); m->s_traj.release(); m->s_mpc.release();
+    return ABR_OK;
+  }
+  size_t part[3];
+  workspace_plan(m, N, B, S, part);
+  if (bytes < part[0] + part[1] + part[2]) return fail(ABR_ECAPACITY, "abr_model_set_workspace: workspace smaller than abr_workspace_bytes for these sizes");
+  if (((uintptr_t)workspace & 15) != 0) return fail(ABR_EINVAL, "abr_model_set_workspace: workspace must be 16-byte aligned");
+  char* w = (char*)workspace;
+  m->s_costs.adopt(w, part[0]);
+  m->s_traj.adopt(w + part[0], part[1]);
+  m->s_mpc.adopt(w + part[0] + part[1], part[2]);
+  return ABR_OK;
+}
+
 int abr_rollout_dev(AbrModel* m, const float* x0, int x0_stride, const float* us, int us_stride, int nworld, int N,
                     float* xs_out, const AbrCost* cost, float* costs_out, void* stream) {
   if (nworld < 0 || N < 0) return fail(ABR_EINVAL, "abr_rollout_dev: negative size");
@@ -1196,7 +1250,7 @@ int abr_rollout_dev(AbrModel* m, const float* x0, int x0_stride, const float* us
   if (!m || !x0 || (!us && N > 0)) return fail(ABR_EINVAL, "abr_rollout_dev: null argument");
   if (cost && (cost->nx != m->lay.nx || cost->nu != m->lay.nu)) return fail(ABR_EINVAL, "abr_rollout_dev: cost dimensions do not match the model");
   if (costs_out && !cost) return fail(ABR_EINVAL, "abr_rollout_dev: costs_out without a cost");
-  CK(cudaSetDevice(m->device));
+  ABR_ON_DEVICE(m->device);
   RolloutArgs a;
   memset(&a, 0, sizeof(a));
   a.blob = m->d_blob; a.x0 = x0; a.x0_stride = x0_stride; a.us = us; a.us_stride = us_stride;
@@ -1211,7 +1265,9 @@ int abr_rollout_host(AbrModel* m, const float* x0, int x0_stride, const float* u
   if (nworld < 0 || N < 0) return fail(ABR_EINVAL, "abr_rollout_host: negative size");
   if (m && nworld == 0) return ABR_OK;
   if (!m || !x0 || (!us && N > 0)) return fail(ABR_EINVAL, "abr_rollout_host: null argument");
-  CK(cudaSetDevice(m->device));
+  if (cost && (cost->nx != m->lay.nx || cost->nu != m->lay.nu)) return fail(ABR_EINVAL, "abr_rollout_host: cost dimensions do not match the model");
+  if (costs_out && !cost) return fail(ABR_EINVAL, "abr_rollout_host: costs_out without a cost");
+  ABR_ON_DEVICE(m->device);
   const int nx = m->lay.nx, nu = m->lay.nu;
   const size_t n_x0 = x0_stride ? (size_t)nworld * nx : nx;
   const size_t n_us = us_stride ? (size_t)nworld * N * nu : (size_t)N * nu;
@@ -1272,7 +1328,7 @@ int abr_predictive_sample_dev(AbrModel* m, const AbrCost* cost, const float* x0,
   if (!m || !cost || !x0 || !us_guess || !best_idx || !best_cost) return fail(ABR_EINVAL, "abr_predictive_sample_dev: null argument");
   if (B <= 0 || S <= 0 || N < 0 || sample_offset < 0 || sample_offset + S > S_total) return fail(ABR_EINVAL, "abr_predictive_sample_dev: bad sizes");
   if (cost->nx != m->lay.nx || cost->nu != m->lay.nu) return fail(ABR_EINVAL, "abr_predictive_sample_dev: cost dimensions do not match the model");
-  CK(cudaSetDevice(m->device));
+  ABR_ON_DEVICE(m->device);
   cudaStream_t st = (cudaStream_t)stream;
   float* d_costs = costs_out;
   if (!d_costs) {
@@ -1293,7 +1349,8 @@ int abr_predictive_sample_dev(AbrModel* m, const AbrCost* cost, const float* x0,
   const size_t traj_bytes = sizeof(float) * (size_t)B * S * (nxs + nus);
   size_t keep_cap = (size_t)256 << 20;
   if (const char* e = getenv("ABR_KEEP_TRAJ_MB")) keep_cap = (size_t)atol(e) << 20;
-  const bool keep = (xs_star || us_star) && traj_bytes <= keep_cap;
+  bool keep = (xs_star || us_star) && traj_bytes <= keep_cap;
+  if (keep && m->s_traj.external && m->s_traj.cap < traj_bytes + 16) keep = false;  // caller's workspace has no room: re-roll the winners
   float* xs_all = nullptr; float* us_all = nullptr;
   if (keep) {
     int rc = m->s_traj.ensure(traj_bytes + 16);
@@ -1323,7 +1380,7 @@ int abr_predictive_sample_host(AbrModel* m, const AbrCost* cost, const float* x0
                                float* xs_star, float* us_star, int* best_idx, float* best_cost, float* costs_out) {
   if (!m || !cost || !x0 || !us_guess || !best_idx || !best_cost) return fail(ABR_EINVAL, "abr_predictive_sample_host: null argument");
   if (B <= 0 || S <= 0 || N < 0) return fail(ABR_EINVAL, "abr_predictive_sample_host: bad sizes");
-  CK(cudaSetDevice(m->device));
+  ABR_ON_DEVICE(m->device);
   const int nx = m->lay.nx, nu = m->lay.nu;
   const size_t n_x0 = (size_t)B * nx, n_ug = (size_t)B * N * nu;
   const size_t n_nz = noise ? (size_t)B * (S_total - 1) * N * nu : 0;
@@ -1354,11 +1411,11 @@ int abr_mpc_dev(AbrModel* m, const AbrCost* cost, float* x, float* us_guess, uns
                 float* xs_log, float* us_log, float* cost_log, int* idx_log, void* stream) {
   if (!m || !cost || !x || !us_guess) return fail(ABR_EINVAL, "abr_mpc_dev: null argument");
   if (S <= 0 || N <= 0 || nticks < 0) return fail(ABR_EINVAL, "abr_mpc_dev: bad sizes");
-  CK(cudaSetDevice(m->device));
+  ABR_ON_DEVICE(m->device);
   const int nx = m->lay.nx, nu = m->lay.nu;
-  int rc = m->s_out.ensure(sizeof(float) * ((size_t)(N + 1) * nx + (size_t)N * nu + 8));
+  int rc = m->s_mpc.ensure(sizeof(float) * ((size_t)(N + 1) * nx + (size_t)N * nu + 8));
   if (rc) return rc;
-  float* xs_star = (float*)m->s_out.p; float* us_star = xs_star + (size_t)(N + 1) * nx;
+  float* xs_star = (float*)m->s_mpc.p; float* us_star = xs_star + (size_t)(N + 1) * nx;
   float* best_cost = us_star + (size_t)N * nu; int* best_idx = (int*)(best_cost + 1);
   cudaStream_t st = (cudaStream_t)stream;
   for (int tick = 0; tick < nticks; tick++) {
@@ -1375,7 +1432,7 @@ int abr_forward_dev(AbrModel* m, float* qpos, float* qvel, const float* ctrl, fl
   if (E < 0) return fail(ABR_EINVAL, "abr_forward_dev: negative size");
   if (m && E == 0) return ABR_OK;
   if (!m || !qpos || !qvel) return fail(ABR_EINVAL, "abr_forward_dev: null argument");
-  CK(cudaSetDevice(m->device));
+  ABR_ON_DEVICE(m->device);
   EnvArgs a;
   memset(&a, 0, sizeof(a));
   a.blob = m->d_blob; a.qpos = qpos; a.qvel = qvel; a.warm = qacc_warmstart; a.qacc = qacc; a.ctrl = ctrl;
@@ -1389,17 +1446,13 @@ static int fields_call(AbrModel* m, float* qpos, float* qvel, const float* ctrl,
   if (E < 0 || nsubsteps < 0) return fail(ABR_EINVAL, std::string(who) + ": negative size");
   if (m && E == 0) return ABR_OK;
   if (!m || !qpos || !qvel || !fields || (!forward_only && !warm)) return fail(ABR_EINVAL, std::string(who) + ": null argument");
-  int dev_before = -1;
-  cudaGetDevice(&dev_before);
-  CK(cudaSetDevice(m->device));
+  ABR_ON_DEVICE(m->device);
   EnvArgs a;
   memset(&a, 0, sizeof(a));
   a.blob = m->d_blob; a.qpos = qpos; a.qvel = qvel; a.warm = warm; a.qacc = qacc; a.time = time; a.ctrl = ctrl;
   a.E = E; a.nsubsteps = nsubsteps; a.forward_only = forward_only ? 1 : 0;
   a.fo = *fields; a.fo_on = 1;
-  const int rc = launch_env(m, m->lay_dbg, a, (cudaStream_t)stream);  // the un-aliased layout: every intermediate survives the step
-  if (dev_before >= 0) cudaSetDevice(dev_before);
-  return rc;
+  return launch_env(m, m->lay_dbg, a, (cudaStream_t)stream);  // the un-aliased layout: every intermediate survives the step
 }
 int abr_forward_fields_dev(AbrModel* m, float* qpos, float* qvel, const float* ctrl, float* qacc_warmstart, float* qacc, int E,
                            const AbrDataFields* fields, void* stream) {
@@ -1417,7 +1470,7 @@ int abr_env_step_dev(AbrModel* m, float* qpos, float* qvel, float* qacc_warmstar
   if (m && E == 0) return ABR_OK;
   if (!m || !qpos || !qvel || !qacc_warmstart) return fail(ABR_EINVAL, "abr_env_step_dev: null argument");
   if (reset_mask && (!first_qpos || !first_qvel)) return fail(ABR_EINVAL, "abr_env_step_dev: reset_mask without first state");
-  CK(cudaSetDevice(m->device));
+  ABR_ON_DEVICE(m->device);
   EnvArgs a;
   memset(&a, 0, sizeof(a));
   a.blob = m->d_blob; a.qpos = qpos; a.qvel = qvel; a.warm = qacc_warmstart; a.time = time; a.ctrl = ctrl;
@@ -1442,7 +1495,7 @@ int abr_env_task_step_dev(AbrModel* m, float* qpos, float* qvel, float* qacc_war
     return fail(ABR_EINVAL, "abr_env_task_step_dev: null argument");
   if (reward->nx != m->lay.nx || reward->nu != m->lay.nu) return fail(ABR_EINVAL, "abr_env_task_step_dev: reward dimensions do not match the model");
   if (!reward->diag) return fail(ABR_EUNSUPPORTED, "abr_env_task_step_dev: the fused reward takes diagonal Q and R");
-  CK(cudaSetDevice(m->device));
+  ABR_ON_DEVICE(m->device);
   const CostView cv = cost_view(reward);
   EnvArgs a;
   memset(&a, 0, sizeof(a));
@@ -1457,7 +1510,7 @@ int abr_env_task_step_dev(AbrModel* m, float* qpos, float* qvel, float* qacc_war
 int abr_debug_forward_host(AbrModel* m, const float* qpos, const float* qvel, const float* ctrl, const float* qacc_warmstart,
                            const char* name, float* out, int cap, int* n) {
   if (!m || !qpos || !qvel || !name || !out || !n) return fail(ABR_EINVAL, "abr_debug_forward_host: null argument");
-  CK(cudaSetDevice(m->device));
+  ABR_ON_DEVICE(m->device);
   const Layout& L = m->lay_dbg;
   const int nq = L.nq, nv = L.nv, nu = L.nu;
   int rc = m->s_dbg.ensure(sizeof(float) * ((size_t)nq + 3 * nv + nu + L.world_stride + 8));
@@ -1559,7 +1612,7 @@ int abr_debug_forward_host(AbrModel* m, const float* qpos, const float* qvel, co
 int abr_ffma_peak(int device, double* tflops, double* ms_out) {
   if (!tflops) return fail(ABR_EINVAL, "abr_ffma_peak: null argument");
   if (abr_device_count() <= 0) return fail(ABR_ENODEVICE, "no CUDA device");
-  CK(cudaSetDevice(device));
+  ABR_ON_DEVICE(device);
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   float* d = nullptr;

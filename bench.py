@@ -36,9 +36,11 @@ F_WS = 46349.0
 F_WS_BIPED = 130142.0  # same counter, biped stand-in at its standing keyframe
 F_WS_EXO_LEGS = 67283.0  # same counter, legs-only exoskeleton stand-in
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
-# dram__bytes_read.sum + dram__bytes_write.sum of the C2 launch (one `ncu --set full` capture of this file's
-# own kernel launch, profiles/r1_limb_final4_c2_summary.txt + .ncu-rep): 198.25 MB + 5.07 MB vs 197.23 MB algorithmic
-NCU_DRAM_BYTES_C2 = 198_252_800 + 5_068_288
+# dram__bytes_read.sum + dram__bytes_write.sum of the C2 launch: one `ncu --set full` capture of THIS file's own kernel launch with
+# the kernels as shipped (round 2: `ncu ... -k regex:k_limb_rollout --launch-skip 3 -c 1 python bench.py --steps 2 --warmup 3 --no-extra`,
+# profiles/r2_c2_final_summary.txt): 198.31 MB read + 4.24 MB written vs 197.23 MB algorithmic (the controls). A profiler capture,
+# not a live counter of the run that prints it: `roofline.traffic_source` says so.
+NCU_DRAM_BYTES_C2 = 198_308_608 + 4_243_200
 
 
 def peaks():
@@ -416,6 +418,7 @@ def main():
     alg_bytes = WORLDS * HORIZON * mj.nu * 4 + WORLDS * (mj.nq + mj.nv) * 4 + WORLDS * 4
     out["roofline"] = {"bound": "fp32", "achieved": achieved_tf, "peak": tf.value, "unit": "TFLOP/s", "frac": achieved_tf / tf.value,
                        "traffic": NCU_DRAM_BYTES_C2 if not args.lanes else None, "traffic_unit": "bytes per launch (ncu dram read+write)",
+                       "traffic_source": "profiles/r2_c2_final_summary.txt: ncu --set full capture of this launch (same command, kernels as shipped), not measured live",
                        "peak_kind": "FFMA microkernel timed in this run (abr_ffma_peak)",
                        "peak_nominal": NOMINAL_FP32_TFLOPS, "frac_of_nominal": achieved_tf / NOMINAL_FP32_TFLOPS,
                        "flop_per_world_step": F_WS,

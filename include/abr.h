@@ -232,6 +232,14 @@ int abr_limb_plan_host(const AbrModelHost* host, int* info, int* lane_body, int 
  * for rollouts of nworld worlds x N steps and solves of B problems x S samples x N steps, so that no later call of
  * at most those sizes allocates (the role of a workspace query + caller-provided workspace). */
 int abr_model_reserve(AbrModel* m, int nworld, int N, int B, int S);
+/* Caller-provided workspace for the stream-ordered calls ("no hidden allocation on the hot path"): abr_workspace_bytes
+ * returns the DEVICE bytes abr_predictive_sample_dev / abr_mpc_dev need for solves of up to B problems x S samples x N steps;
+ * abr_model_set_workspace hands the handle such a buffer (caller-owned, 16-byte aligned, must outlive the calls). From then on
+ * those calls never call cudaMalloc / cudaFree: a larger solve returns ABR_ECAPACITY instead (a sweep whose kept trajectories do
+ * not fit re-rolls its winners). workspace == NULL returns to handle-owned scratch. The rollout / env / forward _dev calls
+ * use no scratch at all; the *_host calls stage through handle-owned buffers on the handle's own stream. */
+int abr_workspace_bytes(const AbrModel* m, int N, int B, int S, size_t* bytes);
+int abr_model_set_workspace(AbrModel* m, void* workspace, size_t bytes, int N, int B, int S);
 
 int abr_cost_create(const AbrQuadCostHost* host, int device, AbrCost** out);
 int abr_cost_destroy(AbrCost* c);

@@ -11,6 +11,8 @@ BASELINE.json's full sizes. Tolerances (float32 kernel vs float64 oracle; SURVEY
   * argmin: bit-exact against numpy.argmin of the device's own costs, and equal to the oracle's
     index whenever the oracle's best-vs-second gap exceeds the cost tolerance.
 """
+import ctypes as C
+
 import numpy as np
 import pytest
 import torch
@@ -1038,3 +1040,34 @@ def test_spline_predictive_sampler(load_model):
         one = SplinePredictiveSampler(model=m, cost_function=cf, nsamples=1, stdev=0.1, interp=interp)
         _, k1 = one.optimize(SplineShootingParams(key=4, x0=t32(x0), us_guess=t32(knots), horizon=33))
         assert torch.equal(k1, t32(knots))
+
+
+def test_caller_provided_workspace(load_model):
+    """`abr_workspace_bytes` + a caller-owned workspace, after which the stream-ordered solve calls never allocate: same
+    winners bit for bit as with handle-owned scratch, ABR_ECAPACITY (not a cudaMalloc) for a solve the workspace was not sized for,
+    and a sweep whose kept trajectories do not fit the workspace re-rolls its winners instead."""
+    mj, m, _ = model_with(load_model, "barkour")
+    nx = mj.nq + mj.nv
+    q0 = np.concatenate([mj.key_qpos("home"), np.zeros(mj.nv)])
+    cf = StaticGoalQuadraticCost(np.eye(nx), 10 * np.eye(nx), 0.01 * np.eye(mj.nu), q0)
+    prm = VanillaPredictiveSamplerParams(key=2, x0=t32(q0), us_guess=t32(np.tile(mj.key_ctrl("home"), (16, 1))))
+    ps = VanillaPredictiveSampler(model=m, cost_function=cf, nsamples=512, stdev=0.1)
+    ref = ps.optimize(prm, return_info=True)
+    L, h = _lib.lib(), m.handle(0)
+    need = C.c_size_t()
+    _lib.check(L.abr_workspace_bytes(h.ptr, 16, 1, 512, C.byref(need)))
+    assert need.value >= 4 * 512 * (17 * nx + 16 * mj.nu)
+    ws = torch.empty(need.value, dtype=torch.uint8, device=DEV)
+    assert L.abr_model_set_workspace(h.ptr, C.c_void_p(ws.data_ptr()), need.value - 1024, 16, 1, 512) == _lib.ABR_ECAPACITY
+    _lib.check(L.abr_model_set_workspace(h.ptr, C.c_void_p(ws.data_ptr()), need.value, 16, 1, 512))
+    got = ps.optimize(prm, return_info=True)
+    assert torch.equal(ref[0], got[0]) and torch.equal(ref[1], got[1]) and int(ref[2]["best_idx"]) == int(got[2]["best_idx"])
+    big = VanillaPredictiveSampler(model=m, cost_function=cf, nsamples=4096, stdev=0.1)
+    with pytest.raises(_lib.AbrError) as e:
+        big.optimize(prm)  # per-sample costs of 4096 samples do not fit a workspace sized for 512
+    assert e.value.code == _lib.ABR_ECAPACITY
+    xs_m, us_m, _ = ps.mpc(prm, 3)
+    _lib.check(L.abr_model_set_workspace(h.ptr, None, 0, 0, 0, 0))  # back to handle-owned scratch
+    xs_o, us_o, _ = ps.mpc(prm, 3)
+    assert torch.equal(xs_m, xs_o) and torch.equal(us_m, us_o)
+    assert torch.isfinite(big.optimize(prm)[0]).all()

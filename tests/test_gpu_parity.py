@@ -1071,3 +1071,26 @@ def test_caller_provided_workspace(load_model):
     xs_o, us_o, _ = ps.mpc(prm, 3)
     assert torch.equal(xs_m, xs_o) and torch.equal(us_m, us_o)
     assert torch.isfinite(big.optimize(prm)[0]).all()
+
+
+def test_limb_kernels_are_bit_identical_across_cta_sizes(load_model, monkeypatch):
+    """The CTA size of a limb launch (limb::pick_tpb: 8 warps per CTA share one SM's instruction stream) is a scheduling choice:
+    the same worlds give the same bits whether a warp runs alone in its CTA or with seven others, for shoot, the fused cost and
+    the sampler."""
+    for name, key in (("barkour", "home"), ("biped", "stand")):
+        mj, m, _ = model_with(load_model, name)
+        nx = mj.nq + mj.nv
+        rng = np.random.default_rng(9)
+        W, N = 100, 12
+        x0 = np.tile(np.concatenate([mj.key_qpos(key), np.zeros(mj.nv)]), (W, 1))
+        x0[:, 7:mj.nq] += rng.uniform(-0.05, 0.05, (W, mj.nq - 7))
+        us = mj.key_ctrl(key) + 0.1 * rng.standard_normal((W, N, mj.nu))
+        cf = StaticGoalQuadraticCost(np.eye(nx), 10 * np.eye(nx), 0.01 * np.eye(mj.nu), x0[0])
+        ps = VanillaPredictiveSampler(model=m, cost_function=cf, nsamples=300, stdev=0.1)
+        prm = VanillaPredictiveSamplerParams(key=1, x0=t32(x0[0]), us_guess=t32(us[0]))
+        out = []
+        for tpb in ("32", "96", "256"):
+            monkeypatch.setenv("ABR_LIMB_TPB", tpb)
+            out.append((shoot(m, t32(x0), t32(us)), shoot_cost(m, t32(x0), t32(us), cf), *ps.optimize(prm)))
+        for o in out[1:]:
+            assert all(torch.equal(a, b) for a, b in zip(out[0], o))

@@ -1088,7 +1088,10 @@ __device__ __forceinline__ void euler(Lane<NL, NC>& s, const LaneCfg<LGC>& C, fl
 
 // ------------------------------------------------------------------------------ kernels
 constexpr int kTPB = 32;      // smallest CTA: one warp (32/G worlds)
-constexpr int kMaxTPB = 256;  // largest CTA: 8 warps = every register of an SM at 255 registers per thread
+#ifndef ABR_LIMB_MAXTPB
+#define ABR_LIMB_MAXTPB 256
+#endif
+constexpr int kMaxTPB = ABR_LIMB_MAXTPB;  // largest CTA: 8 warps = every register of an SM at 255 registers per thread
 // CTA size of a launch ("instruction delivery"). The straight-line step does not fit the SM's instruction
 // cache, so every SM streams it from the GPC-level cache each step; the warps of one SM run in loose lockstep and share that
 // stream, while the SMs of a GPC compete for it. A small batch therefore runs faster on FEWER SMs with MORE warps each:

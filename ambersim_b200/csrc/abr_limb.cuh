@@ -414,11 +414,13 @@ template <int NL, int NC, bool CB, class SH, bool AT_AS = false> __device__ __fo
 }
 // one point of the exact line search: (d0, d1) at alpha. a0/a1/a2 are the per-row quadratic
 // coefficients 0.5 D ja^2, D ja jv, 0.5 D jv^2 (a row counts while ja + alpha jv < 0).
-template <int NR> __device__ __forceinline__ LSP ls_eval(const float (&Jaref)[NR], const float (&jv)[NR], const float (&a1)[NR],
+// Rows below R0 are skipped: the caller passes R0 = NL when no lane of the warp has an active joint-limit row (their
+// coefficients are exact zeros then, so the sums are the same numbers).
+template <int NR, int R0> __device__ __forceinline__ LSP ls_eval(const float (&Jaref)[NR], const float (&jv)[NR], const float (&a1)[NR],
                                                          const float (&a2)[NR], float alpha, float qg1, float qg2, int lg) {
   float q1 = 0.f, q2 = 0.f;
 #pragma unroll
-  for (int r = 0; r < NR; r++) {
+  for (int r = R0; r < NR; r++) {
     if (fmaf(alpha, jv[r], Jaref[r]) < 0.f) { q1 += a1[r]; q2 += a2[r]; }  // predicated adds, no selects
   }
   q1 = gall(q1, lg) + qg1; q2 = gall(q2, lg) + qg2;
@@ -429,13 +431,59 @@ template <int NR> __device__ __forceinline__ LSP ls_eval(const float (&Jaref)[NR
   return pt;
 }
 // the cost of a point (the loop's decisions only read d0 / d1, so q0 is summed for the three points whose cost is compared)
-template <int NR> __device__ __forceinline__ float ls_cost(const float (&Jaref)[NR], const float (&jv)[NR], const float (&a0)[NR], const LSP& pt, float qg0, int lg) {
+template <int NR, int R0> __device__ __forceinline__ float ls_cost(const float (&Jaref)[NR], const float (&jv)[NR], const float (&a0)[NR], const LSP& pt, float qg0, int lg) {
   float q0 = 0.f;
 #pragma unroll
-  for (int r = 0; r < NR; r++)
+  for (int r = R0; r < NR; r++)
     if (fmaf(pt.alpha, jv[r], Jaref[r]) < 0.f) q0 += a0[r];
   q0 = gall(q0, lg) + qg0;
   return pt.alpha * pt.alpha * pt.q2 + pt.alpha * pt.q1 + q0;
+}
+
+// solver._linesearch: the exact line search along jv from Jaref; returns the step length. D are the rows' weights (0 on inactive
+// rows), (qg0, qg1, qg2) the Gauss part of the cost along the search direction. The trip count is warp-uniform.
+template <int NR, int R0> __device__ __forceinline__ float line_search(const float (&Jaref)[NR], const float (&jv)[NR], const float (&D)[NR], float qg0, float qg1,
+                                                                     float qg2, float gtol, int ls_iterations, int lg, bool live) {
+  float la0[NR], la1[NR], la2[NR];
+#pragma unroll
+  for (int r = R0; r < NR; r++) {
+    const float ja = Jaref[r], w = jv[r], Dr = D[r];
+    la0[r] = 0.5f * ja * ja * Dr; la1[r] = w * ja * Dr; la2[r] = 0.5f * w * w * Dr;
+  }
+#define LS_EVAL(al) ls_eval<NR, R0>(Jaref, jv, la1, la2, (al), qg1, qg2, lg)
+  const LSP p0 = LS_EVAL(0.f);
+  const LSP l0 = LS_EVAL(-safe_div_fast(p0.d0, p0.d1));
+  const bool lesser = l0.d0 < p0.d0;
+  LSP hi = lesser ? p0 : l0;
+  LSP lo = lesser ? l0 : p0;
+  bool swap = true;
+  int it = 0;
+  while (true) {
+    bool done = it >= ls_iterations;
+    done = done || !swap;
+    done = done || ((lo.d0 < 0.f) && (lo.d0 > -gtol));
+    done = done || ((hi.d0 > 0.f) && (hi.d0 < gtol));
+    if (!__any_sync(ABR_FULL, !done)) break;
+    const LSP lo_next = LS_EVAL(lo.alpha - safe_div_fast(lo.d0, lo.d1));
+    const LSP hi_next = LS_EVAL(hi.alpha - safe_div_fast(hi.d0, hi.d1));
+    const LSP mid = LS_EVAL(0.5f * (lo.alpha + hi.alpha));
+    if (!done) {
+      const bool swap_lo_next = (lo.d0 > 0.f) || (lo.d0 < lo_next.d0);
+      if (swap_lo_next) lo = lo_next;
+      const bool swap_lo_mid = (mid.d0 < 0.f) && (lo.d0 < mid.d0);
+      if (swap_lo_mid) lo = mid;
+      const bool swap_hi_next = (hi.d0 < 0.f) || (hi.d0 > hi_next.d0);
+      if (swap_hi_next) hi = hi_next;
+      const bool swap_hi_mid = (mid.d0 > 0.f) && (hi.d0 > mid.d0);
+      if (swap_hi_mid) hi = mid;
+      swap = swap_lo_next || swap_lo_mid || swap_hi_next || swap_hi_mid;
+      it++;
+    }
+  }
+#undef LS_EVAL
+  const float c_p0 = ls_cost<NR, R0>(Jaref, jv, la0, p0, qg0, lg), c_lo = ls_cost<NR, R0>(Jaref, jv, la0, lo, qg0, lg), c_hi = ls_cost<NR, R0>(Jaref, jv, la0, hi, qg0, lg);
+  const bool improved = (c_lo < c_p0) || (c_hi < c_p0);
+  return (improved && live) ? ((c_lo < c_hi) ? lo.alpha : hi.alpha) : 0.f;
 }
 
 // mjx.forward for one lane: on exit s.a = qacc, s.warm = qacc; M, fs, fc are returned for the
@@ -761,16 +809,33 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
     return;
   }
   // ---------------------------------------------------------------- constraint rows (make_constraint)
+  // joint limits: the impedance / reference acceleration of a row is only evaluated when some lane of the warp has an active
+  // limit (warp-uniform branch); otherwise the rows are the exact zeros an inactive row gets anyway
+  bool anylim;
+  {
+    float lpos[NL], lsgn[NL];
+    bool lact[NL], any = false;
 #pragma unroll
-  for (int p = 1; p < NP; p++) {
-    const int d = 5 + p, r = p - 1;
-    const float q = s.qc[p - 1];
-    const float dmin = q - LTF(mp.jnt(p) + 11), dmax = LTF(mp.jnt(p) + 12) - q;
-    const float pos = fminf(dmin, dmax) - LTF(mp.jnt(p) + 13);
-    const bool active = (pos < 0.f) && (jflags[p] & kJLimited) && S.o(p);
-    const float sg = (dmin < dmax) ? 1.f : -1.f;
-    R.lsg[r] = active ? sg : 0.f;
-    row_kbi<Spec<SPEC>::pow2>(&LTF(mp.jnt(p) + 14), pos, sg * s.v[d], LTF(mp.jnt(p) + 14 + 7), active, R.D[r], R.aref[r]);
+    for (int p = 1; p < NP; p++) {
+      const float q = s.qc[p - 1];
+      const float dmin = q - LTF(mp.jnt(p) + 11), dmax = LTF(mp.jnt(p) + 12) - q;
+      lpos[p - 1] = fminf(dmin, dmax) - LTF(mp.jnt(p) + 13);
+      lact[p - 1] = (lpos[p - 1] < 0.f) && (jflags[p] & kJLimited) && S.o(p);
+      lsgn[p - 1] = (dmin < dmax) ? 1.f : -1.f;
+      any = any || lact[p - 1];
+    }
+    anylim = __any_sync(ABR_FULL, any);
+    if (anylim) {
+#pragma unroll
+      for (int p = 1; p < NP; p++) {
+        const int d = 5 + p, r = p - 1;
+        R.lsg[r] = lact[r] ? lsgn[r] : 0.f;
+        row_kbi<Spec<SPEC>::pow2>(&LTF(mp.jnt(p) + 14), lpos[r], lsgn[r] * s.v[d], LTF(mp.jnt(p) + 14 + 7), lact[r], R.D[r], R.aref[r]);
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < NL; r++) { R.lsg[r] = 0.f; R.D[r] = 0.f; R.aref[r] = 0.f; }
+    }
   }
   {
     float bva[NC > 0 ? NC : 1][3];
@@ -992,45 +1057,9 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
     const float smag = sqrt_fast(sn) * C.meaninertia * (float)max(1, C.nv);
     const float gtol = C.tol * C.ls_tol * smag;
     const float qg0 = gauss, qg1 = sMa - sq, qg2 = 0.5f * smv;
-    float la0[NR], la1[NR], la2[NR];
-#pragma unroll
-    for (int r = 0; r < NR; r++) {
-      const float ja = Jaref[r], w = jv[r], Dr = R.D[r];
-      la0[r] = 0.5f * ja * ja * Dr; la1[r] = w * ja * Dr; la2[r] = 0.5f * w * w * Dr;
-    }
-#define LS_EVAL(al) ls_eval<NR>(Jaref, jv, la1, la2, (al), qg1, qg2, S.lg())
-    const LSP p0 = LS_EVAL(0.f);
-    const LSP l0 = LS_EVAL(-safe_div_fast(p0.d0, p0.d1));
-    const bool lesser = l0.d0 < p0.d0;
-    LSP hi = lesser ? p0 : l0;
-    LSP lo = lesser ? l0 : p0;
-    bool swap = true;
-    int it = 0;
-    while (true) {
-      bool done = it >= C.ls_iterations;
-      done = done || !swap;
-      done = done || ((lo.d0 < 0.f) && (lo.d0 > -gtol));
-      done = done || ((hi.d0 > 0.f) && (hi.d0 < gtol));
-      if (!__any_sync(ABR_FULL, !done)) break;
-      const LSP lo_next = LS_EVAL(lo.alpha - safe_div_fast(lo.d0, lo.d1));
-      const LSP hi_next = LS_EVAL(hi.alpha - safe_div_fast(hi.d0, hi.d1));
-      const LSP mid = LS_EVAL(0.5f * (lo.alpha + hi.alpha));
-      if (!done) {
-        const bool swap_lo_next = (lo.d0 > 0.f) || (lo.d0 < lo_next.d0);
-        if (swap_lo_next) lo = lo_next;
-        const bool swap_lo_mid = (mid.d0 < 0.f) && (lo.d0 < mid.d0);
-        if (swap_lo_mid) lo = mid;
-        const bool swap_hi_next = (hi.d0 < 0.f) || (hi.d0 > hi_next.d0);
-        if (swap_hi_next) hi = hi_next;
-        const bool swap_hi_mid = (mid.d0 > 0.f) && (hi.d0 > mid.d0);
-        if (swap_hi_mid) hi = mid;
-        swap = swap_lo_next || swap_lo_mid || swap_hi_next || swap_hi_mid;
-        it++;
-      }
-    }
-    const float c_p0 = ls_cost<NR>(Jaref, jv, la0, p0, qg0, S.lg()), c_lo = ls_cost<NR>(Jaref, jv, la0, lo, qg0, S.lg()), c_hi = ls_cost<NR>(Jaref, jv, la0, hi, qg0, S.lg());
-    const bool improved = (c_lo < c_p0) || (c_hi < c_p0);
-    const float alpha = (improved && live) ? ((c_lo < c_hi) ? lo.alpha : hi.alpha) : 0.f;
+    // joint-limit rows are rarely active: when no lane of the warp has one, the line search runs over the contact rows only
+    const float alpha = anylim ? line_search<NR, 0>(Jaref, jv, R.D, qg0, qg1, qg2, gtol, C.ls_iterations, S.lg(), live)
+                               : line_search<NR, (NL < NR ? NL : 0)>(Jaref, jv, R.D, qg0, qg1, qg2, gtol, C.ls_iterations, S.lg(), live);
 #pragma unroll
     for (int d = 0; d < N; d++) { s.a[d] = fmaf(search[d], alpha, s.a[d]); Ma[d] = fmaf(mv[d], alpha, Ma[d]); }
 #pragma unroll
@@ -1083,8 +1112,6 @@ __device__ __forceinline__ void euler(Lane<NL, NC>& s, const LaneCfg<LGC>& C, fl
 #pragma unroll
   for (int p = 1; p <= NL; p++) s.qc[p - 1] = fmaf(dt, s.v[5 + p], s.qc[p - 1]);
 }
-
-#undef LS_EVAL
 
 // ------------------------------------------------------------------------------ kernels
 constexpr int kTPB = 32;      // smallest CTA: one warp (32/G worlds)

@@ -19,6 +19,9 @@ def stage(ln):
         if i <= ln: name = n
         else: break
     return name
+def _i(x):
+    try: return int(x)
+    except ValueError: return 0
 fname = "?"; hdr = None; agg = collections.Counter(); smp = collections.Counter(); noi = collections.Counter()
 for r in rows:
     if len(r) == 2 and r[0] == "File Path": fname = r[1].rsplit("/", 1)[-1]; continue
@@ -29,7 +32,7 @@ for r in rows:
     try: ln = int(r[0])
     except ValueError: continue
     k = stage(ln) if fname == "abr_limb.cuh" else fname
-    agg[k] += int(r[iI] or 0); smp[k] += int(r[iS] or 0); noi[k] += int(r[iN] or 0)
+    agg[k] += _i(r[iI]); smp[k] += _i(r[iS]); noi[k] += _i(r[iN])
 tot = sum(agg.values()); tots = sum(smp.values())
 print(f"executed warp-instructions {tot:,}; stall samples {tots:,} (no_instruction {sum(noi.values()):,})")
 for k, v in agg.most_common(32): print(f"{100*v/tot:5.1f}% inst {100*smp[k]/max(tots,1):5.1f}% samples {100*noi[k]/max(smp[k],1):5.1f}% of them no_inst   {k}")

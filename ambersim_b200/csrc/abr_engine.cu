@@ -48,6 +48,9 @@ struct HostModel {  // deep copy of AbrModelHost
   std::vector<float> geom_size, geom_pos, geom_quat;
   std::vector<int> geom_vertadr, geom_vertnum;  // convex vertex sets of box / mesh geoms
   std::vector<float> vert;
+  int nface = 0, nfacevert = 0, nedge = 0;  // hull topology of the convex geoms
+  std::vector<int> geom_faceadr, geom_facenum, face_vertadr, face_vertnum, face_vert, geom_edgeadr, geom_edgenum, edge_vert;
+  std::vector<float> face_normal;
   std::vector<int> pair_geom1, pair_geom2, pair_kind, pair_condim;
   std::vector<float> pair_friction, pair_solref, pair_solimp, pair_includemargin;
   std::vector<int> eq_type, eq_obj1id, eq_obj2id, eq_active;
@@ -140,6 +143,11 @@ static void copy_host_model(const AbrModelHost* h, HostModel& m) {
   m.geom_type = vcopy(h->geom_type, ng); m.geom_bodyid = vcopy(h->geom_bodyid, ng);
   m.geom_size = vcopy(h->geom_size, 3 * ng); m.geom_pos = vcopy(h->geom_pos, 3 * ng); m.geom_quat = vcopy(h->geom_quat, 4 * ng);
   m.geom_vertadr = vcopy(h->geom_vertadr, ng); m.geom_vertnum = vcopy(h->geom_vertnum, ng); m.vert = vcopy(h->vert, 3 * h->nvert);
+  m.nface = h->nface; m.nfacevert = h->nfacevert; m.nedge = h->nedge;
+  m.geom_faceadr = vcopy(h->geom_faceadr, ng); m.geom_facenum = vcopy(h->geom_facenum, ng);
+  m.face_vertadr = vcopy(h->face_vertadr, h->nface); m.face_vertnum = vcopy(h->face_vertnum, h->nface);
+  m.face_vert = vcopy(h->face_vert, h->nfacevert); m.face_normal = vcopy(h->face_normal, 3 * h->nface);
+  m.geom_edgeadr = vcopy(h->geom_edgeadr, ng); m.geom_edgenum = vcopy(h->geom_edgenum, ng); m.edge_vert = vcopy(h->edge_vert, 2 * h->nedge);
   m.pair_geom1 = vcopy(h->pair_geom1, np); m.pair_geom2 = vcopy(h->pair_geom2, np);
   m.pair_kind = vcopy(h->pair_kind, np); m.pair_condim = vcopy(h->pair_condim, np);
   m.pair_friction = vcopy(h->pair_friction, 5 * np); m.pair_solref = vcopy(h->pair_solref, 2 * np);
@@ -181,7 +189,10 @@ static void row_prm(const AbrOpt& opt, const float* solref, const float* solimp,
   out[9] = (float)(1.0 / std::pow(1.0 - mid, power - 1.0));
 }
 
-static int pair_ncon(int kind) { return kind == ABR_PAIR_PLANE_CONVEX ? 4 : (kind == ABR_PAIR_PLANE_CAPSULE ? 2 : 1); }
+static int pair_ncon(int kind) {
+  if (kind == ABR_PAIR_PLANE_CONVEX || kind == ABR_PAIR_CONVEX_CONVEX) return 4;
+  return (kind == ABR_PAIR_PLANE_CAPSULE || kind == ABR_PAIR_CAPSULE_CONVEX) ? 2 : 1;
+}
 
 static int build_blob(const HostModel& m, bool alias, Layout& L, std::vector<float>& mf, std::vector<int>& mi) {
   memset(&L, 0, sizeof(L));
@@ -221,6 +232,7 @@ static int build_blob(const HostModel& m, bool alias, Layout& L, std::vector<flo
   L.f_qpos0 = P.addf(m.qpos0); L.f_qpos_spring = P.addf(m.qpos_spring);
   L.f_geom_size = P.addf(m.geom_size); L.f_geom_pos = P.addf(m.geom_pos); L.f_geom_quat = P.addf(m.geom_quat);
   L.f_vert = P.addf(m.vert);  // mesh / box vertices live in the model blob (geom frame)
+  L.f_face_normal = P.addf(m.face_normal);
 
   // ---- tree tables
   std::vector<int> depth(nb, 0), rootslot(nb, 0), roots;
@@ -253,6 +265,9 @@ static int build_blob(const HostModel& m, bool alias, Layout& L, std::vector<flo
   L.i_root_body = P.addi(roots);
   L.i_geom_body = P.addi(m.geom_bodyid);
   L.i_geom_vertadr = P.addi(m.geom_vertadr); L.i_geom_vertnum = P.addi(m.geom_vertnum);
+  L.i_geom_faceadr = P.addi(m.geom_faceadr); L.i_geom_facenum = P.addi(m.geom_facenum);
+  L.i_face_vertadr = P.addi(m.face_vertadr); L.i_face_vertnum = P.addi(m.face_vertnum); L.i_face_vert = P.addi(m.face_vert);
+  L.i_geom_edgeadr = P.addi(m.geom_edgeadr); L.i_geom_edgenum = P.addi(m.geom_edgenum); L.i_edge_vert = P.addi(m.edge_vert);
   L.i_pair_g1 = P.addi(m.pair_geom1); L.i_pair_g2 = P.addi(m.pair_geom2); L.i_pair_kind = P.addi(m.pair_kind);
 
   // M sparsity (ancestor pairs) and packed-index table

@@ -36,7 +36,7 @@ struct Layout {
   int f_jnt_pos, f_jnt_axis, f_jnt_range, f_jnt_margin, f_jnt_stiffness;
   int f_dof_armature, f_dof_damping;
   int f_qpos0, f_qpos_spring;
-  int f_geom_size, f_geom_pos, f_geom_quat, f_vert;
+  int f_geom_size, f_geom_pos, f_geom_quat, f_vert, f_face_normal;
   int f_eq_prm, f_eq_data, f_lim_prm, f_con_prm, f_act_prm;
   // ---- int pool offsets
   int i_body_parent, i_body_jntadr, i_body_jntnum, i_body_dofadr, i_body_dofnum, i_body_rootslot;
@@ -51,6 +51,7 @@ struct Layout {
   int i_con_pair, i_con_sub, i_con_row, i_con_condim, i_con_dofmask;
   int i_row_info;   // per efc row: kind (0 eq, 1 limit, 2 contact) | idx << 2 | sub << 20
   int i_pair_g1, i_pair_g2, i_pair_kind, i_geom_body, i_geom_vertadr, i_geom_vertnum;
+  int i_geom_faceadr, i_geom_facenum, i_face_vertadr, i_face_vertnum, i_face_vert, i_geom_edgeadr, i_geom_edgenum, i_edge_vert;
   int i_act_jnt, i_act_flags;
   // ---- tree-sparse linear algebra (valid when every constraint couples dofs of one ancestor
   //      chain only, so H = M + J'DJ keeps M's branch-induced sparsity and L'DL has no fill-in)

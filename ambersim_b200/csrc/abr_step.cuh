@@ -273,6 +273,108 @@ template <int G> __device__ void stage_com(const Ctx& c) {
   __syncwarp();
 }
 
+
+// ------------------------------------------------------------------------------ convex collision primitives
+// mjx math.py / collision_convex.py: the pieces of sphere - convex, capsule - convex and convex - convex collision.
+// Everything works on small per-lane arrays: a polygon has at most ABR_MAX_FACE_VERTS corners.
+__device__ __forceinline__ void closest_segment_point(const float* a, const float* b, const float* pt, float* out) {
+  const float ab[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, pa[3] = {pt[0] - a[0], pt[1] - a[1], pt[2] - a[2]};
+  const float t = fminf(fmaxf(v_dot(pa, ab) / (v_dot(ab, ab) + 1e-6f), 0.f), 1.f);
+  for (int i = 0; i < 3; i++) out[i] = a[i] + t * ab[i];
+}
+__device__ inline void closest_segment_to_segment_points(const float* a0, const float* a1, const float* b0, const float* b1, float* best_a, float* best_b) {
+  float da[3], db[3];
+  for (int i = 0; i < 3; i++) { da[i] = a1[i] - a0[i]; db[i] = b1[i] - b0[i]; }
+  const float ha = 0.5f * v_normalize(da, 3), hb = 0.5f * v_normalize(db, 3);
+  float am[3], bm[3], tr[3];
+  for (int i = 0; i < 3; i++) { am[i] = a0[i] + da[i] * ha; bm[i] = b0[i] + db[i] * hb; tr[i] = am[i] - bm[i]; }
+  const float dd = v_dot(da, db), dat = v_dot(da, tr), dbt = v_dot(db, tr);
+  const float ota = (-dat + dd * dbt) / (1.f - dd * dd + 1e-6f);
+  const float otb = dbt + ota * dd;
+  const float ta = fminf(fmaxf(ota, -ha), ha), tb = fminf(fmaxf(otb, -hb), hb);
+  float pa[3], pb[3], na[3], nb[3];
+  for (int i = 0; i < 3; i++) { pa[i] = am[i] + da[i] * ta; pb[i] = bm[i] + db[i] * tb; }
+  closest_segment_point(a0, a1, pb, na);
+  closest_segment_point(b0, b1, pa, nb);
+  const float e1[3] = {na[0] - pb[0], na[1] - pb[1], na[2] - pb[2]}, e2[3] = {pa[0] - nb[0], pa[1] - nb[1], pa[2] - nb[2]};
+  const bool first = v_dot(e1, e1) < v_dot(e2, e2);
+  for (int i = 0; i < 3; i++) { best_a[i] = first ? na[i] : pa[i]; best_b[i] = first ? pb[i] : nb[i]; }
+}
+__device__ __forceinline__ void project_pt_onto_plane(const float* pt, const float* plane_pt, const float* n, float* out) {
+  const float d[3] = {pt[0] - plane_pt[0], pt[1] - plane_pt[1], pt[2] - plane_pt[2]};
+  const float dist = v_dot(d, n);
+  for (int i = 0; i < 3; i++) out[i] = pt[i] - dist * n[i];
+}
+// _clip_edge_to_planes against the side planes of the counter-clockwise polygon P (np corners, normal nrm): plane k passes through
+// corner k-1 with the outward normal (P[k] - P[k-1]) x nrm
+__device__ inline bool clip_edge_to_poly(const float* p0, const float* p1, const float* P, int np, const float* nrm, float* out0, float* out1) {
+  const float e01[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]}, e10[3] = {-e01[0], -e01[1], -e01[2]};
+  bool any_both = false;
+  float best0 = -1e30f, best1 = -1e30f;
+  float n0[3] = {p0[0], p0[1], p0[2]}, n1[3] = {p1[0], p1[1], p1[2]};
+#pragma unroll 1
+  for (int k = 0; k < np; k++) {
+    const float* pp = P + 3 * ((k + np - 1) % np); const float* pe = P + 3 * k;
+    const float ed[3] = {pe[0] - pp[0], pe[1] - pp[1], pe[2] - pp[2]};
+    float pn[3];
+    v_cross(ed, nrm, pn);
+    const float d0[3] = {p0[0] - pp[0], p0[1] - pp[1], p0[2] - pp[2]}, d1[3] = {p1[0] - pp[0], p1[1] - pp[1], p1[2] - pp[2]};
+    const bool f0 = v_dot(d0, pn) > 1e-6f, f1 = v_dot(d1, pn) > 1e-6f;
+    any_both = any_both || (f0 && f1);
+    // _closest_segment_point_plane
+    const float dpl = v_dot(pp, pn), denom = v_dot(pn, e01);
+    const float t = fminf(fmaxf((dpl - v_dot(pn, p0)) / (denom + ((denom == 0.f) ? 1e-6f : 0.f)), 0.f), 1.f);
+    float c0[3], c1[3];
+    for (int i = 0; i < 3; i++) { const float cp = p0[i] + t * e01[i]; c0[i] = f0 ? cp : p0[i]; c1[i] = f1 ? cp : p1[i]; }
+    const float r0[3] = {c0[0] - p0[0], c0[1] - p0[1], c0[2] - p0[2]}, r1[3] = {c1[0] - p1[0], c1[1] - p1[1], c1[2] - p1[2]};
+    const float s0 = v_dot(r0, e01), s1 = v_dot(r1, e10);
+    if (s0 > best0) { best0 = s0; for (int i = 0; i < 3; i++) n0[i] = c0[i]; }
+    if (s1 > best1) { best1 = s1; for (int i = 0; i < 3; i++) n1[i] = c1[i]; }
+  }
+  bool mask = !any_both;
+  for (int i = 0; i < 3; i++) { out0[i] = mask ? n0[i] : p0[i]; out1[i] = mask ? n1[i] : p1[i]; }
+  const float dn[3] = {out0[0] - out1[0], out0[1] - out1[1], out0[2] - out1[2]};
+  if (v_dot(e10, dn) < 0.f) mask = false;
+  return mask;
+}
+// _manifold_points over n points (stride 3) with a bit mask; first maximum wins
+__device__ inline void manifold_points(const float* pts, unsigned mask, int n, const float* normal, int* idx) {
+  auto dm = [&](int k) { return ((mask >> k) & 1u) ? 0.f : -1e6f; };
+  int ia = 0, ib = 0, ic = 0, id = 0;
+  float bv = -1e30f;
+#pragma unroll 1
+  for (int k = 0; k < n; k++) { const float v = dm(k); if (v > bv) { bv = v; ia = k; } }
+  const float a[3] = {pts[3 * ia], pts[3 * ia + 1], pts[3 * ia + 2]};
+  bv = -1e30f;
+#pragma unroll 1
+  for (int k = 0; k < n; k++) { const float d[3] = {a[0] - pts[3 * k], a[1] - pts[3 * k + 1], a[2] - pts[3 * k + 2]}; const float v = v_dot(d, d) + dm(k); if (v > bv) { bv = v; ib = k; } }
+  const float b[3] = {pts[3 * ib], pts[3 * ib + 1], pts[3 * ib + 2]};
+  const float amb[3] = {a[0] - b[0], a[1] - b[1], a[2] - b[2]};
+  float ab[3];
+  v_cross(normal, amb, ab);
+  bv = -1e30f;
+#pragma unroll 1
+  for (int k = 0; k < n; k++) { const float d[3] = {a[0] - pts[3 * k], a[1] - pts[3 * k + 1], a[2] - pts[3 * k + 2]}; const float v = fabsf(v_dot(d, ab)) + dm(k); if (v > bv) { bv = v; ic = k; } }
+  const float cc[3] = {pts[3 * ic], pts[3 * ic + 1], pts[3 * ic + 2]};
+  const float amc[3] = {a[0] - cc[0], a[1] - cc[1], a[2] - cc[2]}, bmc[3] = {b[0] - cc[0], b[1] - cc[1], b[2] - cc[2]};
+  float ac[3], bc[3];
+  v_cross(normal, amc, ac);
+  v_cross(normal, bmc, bc);
+  bv = -1e30f;
+#pragma unroll 1
+  for (int h = 0; h < 2; h++) {
+#pragma unroll 1
+    for (int k = 0; k < n; k++) {
+      const float* o = h == 0 ? b : a;
+      const float* ax = h == 0 ? bc : ac;
+      const float d[3] = {o[0] - pts[3 * k], o[1] - pts[3 * k + 1], o[2] - pts[3 * k + 2]};
+      const float v = fabsf(v_dot(d, ax)) + dm(k);
+      if (v > bv) { bv = v; id = k; }
+    }
+  }
+  idx[0] = ia; idx[1] = ib; idx[2] = ic; idx[3] = id;
+}
+
 // collision_driver.collision (static pairs, primitives) + contact Jacobian basis B[c][3][nv]
 // (normal, tangent1, tangent2 rows of frame @ (jacp(body2) - jacp(body1))).
 template <int G> __device__ void stage_collision(const Ctx& c) {
@@ -362,6 +464,256 @@ template <int G> __device__ void stage_collision(const Ctx& c) {
       const float* v = V + 3 * mine;
       for (int i = 0; i < 3; i++) pos[i] = p2[i] + m2[3 * i] * v[0] + m2[3 * i + 1] * v[1] + m2[3 * i + 2] * v[2] - 0.5f * dist * n[i];
       make_frame(n, fr);
+    } else if (kind == ABR_PAIR_SPHERE_CONVEX) {
+      // collision_convex.sphere_convex, in the convex geom's frame: the face with the least penetration among those the sphere
+      // reaches behind, then the closest point of that polygon to the sphere centre
+      const float dp[3] = {p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]};
+      float sp[3];
+      for (int i = 0; i < 3; i++) sp[i] = m2[i] * dp[0] + m2[3 + i] * dp[1] + m2[6 + i] * dp[2];
+      const float rad = s1[0];
+      const int fa = MI(geom_faceadr)[g2], nf = MI(geom_facenum)[g2];
+      const float* V = MF(vert) + 3 * MI(geom_vertadr)[g2];
+      int best = 0;
+      float bestv = -1e30f;
+#pragma unroll 1
+      for (int f = 0; f < nf; f++) {
+        const float* nn = MF(face_normal) + 3 * (fa + f);
+        const float* v0 = V + 3 * MI(face_vert)[MI(face_vertadr)[fa + f]];
+        const float d[3] = {sp[0] - v0[0], sp[1] - v0[1], sp[2] - v0[2]};
+        float sup = v_dot(d, nn) - rad;
+        if (sup >= 0.f) sup = -1e12f;
+        if (sup > bestv) { bestv = sup; best = f; }
+      }
+      const int pa = MI(face_vertadr)[fa + best], pn = MI(face_vertnum)[fa + best];
+      const float* nn = MF(face_normal) + 3 * (fa + best);
+      float pt[3];
+      project_pt_onto_plane(sp, V + 3 * MI(face_vert)[pa], nn, pt);
+      bool inside = true;
+      int eidx = 0;
+      float ebest = 1e30f;
+#pragma unroll 1
+      for (int k = 0; k < pn; k++) {
+        const float* e0 = V + 3 * MI(face_vert)[pa + (k + pn - 1) % pn]; const float* e1 = V + 3 * MI(face_vert)[pa + k];
+        const float ed[3] = {e1[0] - e0[0], e1[1] - e0[1], e1[2] - e0[2]}, d[3] = {pt[0] - e0[0], pt[1] - e0[1], pt[2] - e0[2]};
+        float en[3];
+        v_cross(ed, nn, en);
+        float dd = v_dot(d, en);
+        if (!(dd <= 0.f)) inside = false;
+        if ((en[0] == 0.f && en[1] == 0.f && en[2] == 0.f) || dd < 0.f) dd = 1e12f;
+        if (dd < ebest) { ebest = dd; eidx = k; }
+      }
+      if (!inside) {
+        float q[3];
+        closest_segment_point(V + 3 * MI(face_vert)[pa + (eidx + pn - 1) % pn], V + 3 * MI(face_vert)[pa + eidx], pt, q);
+        pt[0] = q[0]; pt[1] = q[1]; pt[2] = q[2];
+      }
+      float n[3] = {pt[0] - sp[0], pt[1] - sp[1], pt[2] - sp[2]};
+      const float d = v_normalize(n, 3);
+      float pl[3], nw[3];
+      for (int i = 0; i < 3; i++) pl[i] = 0.5f * (pt[i] + sp[i] + n[i] * rad);
+      for (int i = 0; i < 3; i++) {
+        nw[i] = m2[3 * i] * n[0] + m2[3 * i + 1] * n[1] + m2[3 * i + 2] * n[2];
+        pos[i] = p2[i] + m2[3 * i] * pl[0] + m2[3 * i + 1] * pl[1] + m2[3 * i + 2] * pl[2];
+      }
+      dist = d - rad;
+      make_frame(nw, fr);
+    } else if (kind == ABR_PAIR_CAPSULE_CONVEX) {
+      // collision_convex.capsule_convex, in the convex geom's frame: the axis segment clipped to the side planes of the best face
+      // gives two face contacts; a face edge closer to the axis than the radius replaces the first by an edge contact
+      const float rad = s1[0], half = s1[1];
+      const float dp[3] = {p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]}, axw[3] = {m1[2], m1[5], m1[8]};
+      float cp[3], ax[3], c0[3], c1[3];
+      for (int i = 0; i < 3; i++) { cp[i] = m2[i] * dp[0] + m2[3 + i] * dp[1] + m2[6 + i] * dp[2]; ax[i] = m2[i] * axw[0] + m2[3 + i] * axw[1] + m2[6 + i] * axw[2]; }
+      for (int i = 0; i < 3; i++) { c0[i] = cp[i] - ax[i] * half; c1[i] = cp[i] + ax[i] * half; }
+      const int fa = MI(geom_faceadr)[g2], nf = MI(geom_facenum)[g2];
+      const float* V = MF(vert) + 3 * MI(geom_vertadr)[g2];
+      int best = 0;
+      float bestv = -1e30f;
+      bool has_support = true;
+#pragma unroll 1
+      for (int f = 0; f < nf; f++) {
+        const float* nn = MF(face_normal) + 3 * (fa + f);
+        const float* v0 = V + 3 * MI(face_vert)[MI(face_vertadr)[fa + f]];
+        const float d0[3] = {c0[0] - v0[0], c0[1] - v0[1], c0[2] - v0[2]}, d1[3] = {c1[0] - v0[0], c1[1] - v0[1], c1[2] - v0[2]};
+        float sup = fminf(v_dot(d0, nn), v_dot(d1, nn)) - rad;
+        if (!(sup < 0.f)) has_support = false;
+        if (sup >= 0.f) sup = -1e12f;
+        if (sup > bestv) { bestv = sup; best = f; }
+      }
+      const int pa = MI(face_vertadr)[fa + best], pn = MI(face_vertnum)[fa + best];
+      const float* nn = MF(face_normal) + 3 * (fa + best);
+      float P[3 * ABR_MAX_FACE_VERTS];
+      for (int k = 0; k < pn; k++) for (int i = 0; i < 3; i++) P[3 * k + i] = V[3 * MI(face_vert)[pa + k] + i];
+      float q[2][3];
+      const bool ok = clip_edge_to_poly(c0, c1, P, pn, nn, q[0], q[1]);
+      float fp[3];
+      for (int i = 0; i < 3; i++) q[sub][i] -= nn[i] * rad;
+      project_pt_onto_plane(q[sub], P, nn, fp);
+      const float df[3] = {fp[0] - q[sub][0], fp[1] - q[sub][1], fp[2] - q[sub][2]};
+      dist = -((ok && has_support) ? v_dot(df, nn) : -1.f);
+      float pl[3], nl[3];
+      for (int i = 0; i < 3; i++) { pl[i] = 0.5f * (q[sub][i] + fp[i]); nl[i] = -nn[i]; }
+      float ebest = 1e30f, ec[3] = {0.f, 0.f, 0.f}, cc[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
+      for (int k = 0; k < pn; k++) {
+        float a[3], b[3];
+        closest_segment_to_segment_points(P + 3 * ((k + pn - 1) % pn), P + 3 * k, c0, c1, a, b);
+        const float d[3] = {a[0] - b[0], a[1] - b[1], a[2] - b[2]};
+        const float dd = v_dot(d, d);
+        if (dd < ebest) { ebest = dd; for (int i = 0; i < 3; i++) { ec[i] = a[i]; cc[i] = b[i]; } }
+      }
+      float ea[3] = {cc[0] - ec[0], cc[1] - ec[1], cc[2] - ec[2]};
+      const float edist = v_normalize(ea, 3);
+      if (rad - edist > 0.f) {
+        if (sub == 0) {
+          for (int i = 0; i < 3; i++) { pl[i] = 0.5f * (ec[i] + cc[i] - ea[i] * rad); nl[i] = -ea[i]; }
+          dist = -(rad - edist);
+        } else {
+          dist = 1.f;
+        }
+      }
+      float nw[3];
+      for (int i = 0; i < 3; i++) {
+        nw[i] = m2[3 * i] * nl[0] + m2[3 * i + 1] * nl[1] + m2[3 * i + 2] * nl[2];
+        pos[i] = p2[i] + m2[3 * i] * pl[0] + m2[3 * i + 1] * pl[1] + m2[3 * i + 2] * pl[2];
+      }
+      make_frame(nw, fr);
+    } else if (kind == ABR_PAIR_CONVEX_CONVEX) {
+      // collision_convex.convex_convex: separating axes (face normals of both hulls, cross products of their edges) in the world
+      // frame, then the incident face clipped against the reference face (_create_contact_manifold, up to 4 contacts) or the closest
+      // points of the two edges (1 contact). An axis is carried into each hull's own frame, so the vertices are never transformed.
+      const float* VA = MF(vert) + 3 * MI(geom_vertadr)[g1]; const float* VB = MF(vert) + 3 * MI(geom_vertadr)[g2];
+      const int nva = MI(geom_vertnum)[g1], nvb = MI(geom_vertnum)[g2];
+      const int fa = MI(geom_faceadr)[g1], nfa = MI(geom_facenum)[g1], fb = MI(geom_faceadr)[g2], nfb = MI(geom_facenum)[g2];
+      const int ea = MI(geom_edgeadr)[g1], nea = MI(geom_edgenum)[g1], eb = MI(geom_edgeadr)[g2], neb = MI(geom_edgenum)[g2];
+      auto to_world = [&](const float* pg, const float* mg, const float* v, float* out) {
+        for (int i = 0; i < 3; i++) out[i] = pg[i] + mg[3 * i] * v[0] + mg[3 * i + 1] * v[1] + mg[3 * i + 2] * v[2];
+      };
+      auto rot_world = [&](const float* mg, const float* v, float* out) {
+        for (int i = 0; i < 3; i++) out[i] = mg[3 * i] * v[0] + mg[3 * i + 1] * v[1] + mg[3 * i + 2] * v[2];
+      };
+      auto axis_dist = [&](const float* axis, float& sign) {
+        float la[3], lb[3];
+        for (int i = 0; i < 3; i++) { la[i] = m1[i] * axis[0] + m1[3 + i] * axis[1] + m1[6 + i] * axis[2]; lb[i] = m2[i] * axis[0] + m2[3 + i] * axis[1] + m2[6 + i] * axis[2]; }
+        const float oa = v_dot(axis, p1), ob = v_dot(axis, p2);
+        float amax = -1e30f, amin = 1e30f, bmax = -1e30f, bmin = 1e30f;
+#pragma unroll 1
+        for (int k = 0; k < nva; k++) { const float v = oa + v_dot(la, VA + 3 * k); amax = fmaxf(amax, v); amin = fminf(amin, v); }
+#pragma unroll 1
+        for (int k = 0; k < nvb; k++) { const float v = ob + v_dot(lb, VB + 3 * k); bmax = fmaxf(bmax, v); bmin = fminf(bmin, v); }
+        const float d1 = amax - bmin, d2 = bmax - amin;
+        sign = (d1 > d2) ? -1.f : 1.f;
+        return fminf(d1, d2);
+      };
+      float fbest = 1e30f, fsign = 1.f, faxis[3] = {0.f, 0.f, 1.f};
+#pragma unroll 1
+      for (int f = 0; f < nfa + nfb; f++) {
+        float ax[3], sg;
+        if (f < nfa) rot_world(m1, MF(face_normal) + 3 * (fa + f), ax); else rot_world(m2, MF(face_normal) + 3 * (fb + f - nfa), ax);
+        const float d = axis_dist(ax, sg);
+        if (d < fbest) { fbest = d; fsign = sg; faxis[0] = ax[0]; faxis[1] = ax[1]; faxis[2] = ax[2]; }
+      }
+      float ebest = 1e30f, epair = -1e30f, esign = 1.f, eaxis[3] = {0.f, 0.f, 1.f};
+      int ei = 0, ej = 0;
+#pragma unroll 1
+      for (int j = 0; j < neb; j++) {
+        float b0[3], b1[3];
+        to_world(p2, m2, VB + 3 * MI(edge_vert)[2 * (eb + j)], b0);
+        to_world(p2, m2, VB + 3 * MI(edge_vert)[2 * (eb + j) + 1], b1);
+        float db[3] = {b0[0] - b1[0], b0[1] - b1[1], b0[2] - b1[2]};
+        v_normalize(db, 3);
+#pragma unroll 1
+        for (int i = 0; i < nea; i++) {
+          float a0[3], a1[3];
+          to_world(p1, m1, VA + 3 * MI(edge_vert)[2 * (ea + i)], a0);
+          to_world(p1, m1, VA + 3 * MI(edge_vert)[2 * (ea + i) + 1], a1);
+          float da[3] = {a0[0] - a1[0], a0[1] - a1[1], a0[2] - a1[2]};
+          v_normalize(da, 3);
+          float ax[3], sg;
+          v_cross(da, db, ax);
+          if (v_dot(ax, ax) < 1e-6f) continue;
+          v_normalize(ax, 3);
+          const float d = axis_dist(ax, sg);
+          // parallel edges tie on their common axis: the supporting pair (its own separation along the axis = the hulls') is taken
+          const float ma[3] = {a0[0] + a1[0], a0[1] + a1[1], a0[2] + a1[2]}, mb[3] = {b0[0] + b1[0], b0[1] + b1[1], b0[2] + b1[2]};
+          const float dpair = sg * 0.5f * (v_dot(ax, ma) - v_dot(ax, mb));
+          if (d < ebest - 1e-6f || (d < ebest + 1e-6f && dpair > epair)) {
+            ebest = fminf(ebest, d); epair = dpair; esign = sg; ei = i; ej = j; eaxis[0] = ax[0]; eaxis[1] = ax[1]; eaxis[2] = ax[2];
+          }
+        }
+      }
+      const bool edge_contact = ebest < fbest - 1e-5f;
+      float nab[3];
+      for (int i = 0; i < 3; i++) nab[i] = edge_contact ? esign * eaxis[i] : fsign * faxis[i];
+      dist = 1.f;
+      for (int i = 0; i < 3; i++) pos[i] = 0.5f * (p1[i] + p2[i]);
+      if (edge_contact) {
+        if (sub == 0) {
+          float a0[3], a1[3], b0[3], b1[3], ca[3], cb[3];
+          to_world(p1, m1, VA + 3 * MI(edge_vert)[2 * (ea + ei)], a0); to_world(p1, m1, VA + 3 * MI(edge_vert)[2 * (ea + ei) + 1], a1);
+          to_world(p2, m2, VB + 3 * MI(edge_vert)[2 * (eb + ej)], b0); to_world(p2, m2, VB + 3 * MI(edge_vert)[2 * (eb + ej) + 1], b1);
+          closest_segment_to_segment_points(a0, a1, b0, b1, ca, cb);
+          const float d[3] = {cb[0] - ca[0], cb[1] - ca[1], cb[2] - ca[2]};
+          dist = v_dot(d, nab);
+          for (int i = 0; i < 3; i++) pos[i] = 0.5f * (ca[i] + cb[i]);
+        }
+      } else {
+        int ia = 0, ib = 0;
+        float da = -1e30f, db = -1e30f;
+#pragma unroll 1
+        for (int f = 0; f < nfa; f++) { float nn[3]; rot_world(m1, MF(face_normal) + 3 * (fa + f), nn); const float v = v_dot(nn, nab); if (v > da) { da = v; ia = f; } }
+#pragma unroll 1
+        for (int f = 0; f < nfb; f++) { float nn[3]; rot_world(m2, MF(face_normal) + 3 * (fb + f), nn); const float v = -v_dot(nn, nab); if (v > db) { db = v; ib = f; } }
+        const bool ref_a = da >= db;
+        const int rf = ref_a ? fa + ia : fb + ib, sf = ref_a ? fb + ib : fa + ia;
+        const float* RVl = ref_a ? VA : VB; const float* SVl = ref_a ? VB : VA;
+        const float* rp = ref_a ? p1 : p2; const float* rm = ref_a ? m1 : m2;
+        const float* spp = ref_a ? p2 : p1; const float* sm = ref_a ? m2 : m1;
+        float rn[3], sn[3];
+        rot_world(rm, MF(face_normal) + 3 * rf, rn);
+        rot_world(sm, MF(face_normal) + 3 * sf, sn);
+        const int nr = MI(face_vertnum)[rf], ns = MI(face_vertnum)[sf];
+        float RP[3 * ABR_MAX_FACE_VERTS], SP[3 * ABR_MAX_FACE_VERTS], Q[3 * ABR_MAX_FACE_VERTS], inc[3 * 4 * ABR_MAX_FACE_VERTS];
+        for (int k = 0; k < nr; k++) to_world(rp, rm, RVl + 3 * MI(face_vert)[MI(face_vertadr)[rf] + k], RP + 3 * k);
+        for (int k = 0; k < ns; k++) to_world(spp, sm, SVl + 3 * MI(face_vert)[MI(face_vertadr)[sf] + k], SP + 3 * k);
+        unsigned mk = 0u;
+#pragma unroll 1
+        for (int k = 0; k < ns; k++) {
+          const bool ok = clip_edge_to_poly(SP + 3 * ((k + ns - 1) % ns), SP + 3 * k, RP, nr, rn, inc + 3 * (2 * k), inc + 3 * (2 * k + 1));
+          if (ok) mk |= 3u << (2 * k);
+        }
+        {
+          const float dpl = v_dot(SP, sn), denom = v_dot(rn, sn);
+          for (int k = 0; k < nr; k++) {
+            const float t = (dpl - v_dot(RP + 3 * k, sn)) / (denom + ((denom == 0.f) ? 1e-6f : 0.f));
+            for (int i = 0; i < 3; i++) Q[3 * k + i] = RP[3 * k + i] + t * rn[i];
+          }
+#pragma unroll 1
+          for (int k = 0; k < nr; k++) {
+            const bool ok = clip_edge_to_poly(Q + 3 * ((k + nr - 1) % nr), Q + 3 * k, SP, ns, sn, inc + 3 * (2 * (ns + k)), inc + 3 * (2 * (ns + k) + 1));
+            if (ok) mk |= 3u << (2 * (ns + k));
+          }
+        }
+        const int npt = 2 * (ns + nr);
+        // the points on the reference plane replace the incident ones in `Q`-sized scratch: keep both (inc: incident, ref: projected)
+        float ref[3 * 4 * ABR_MAX_FACE_VERTS];
+        unsigned mb = 0u;
+#pragma unroll 1
+        for (int k = 0; k < npt; k++) {
+          project_pt_onto_plane(inc + 3 * k, RP, rn, ref + 3 * k);
+          const float d[3] = {inc[3 * k] - RP[0], inc[3 * k + 1] - RP[1], inc[3 * k + 2] - RP[2]};
+          if (((mk >> k) & 1u) && (-v_dot(d, rn) > 1e-6f)) mb |= 1u << k;
+        }
+        int idx[4];
+        manifold_points(ref, mb, npt, rn, idx);
+        bool unique = true;
+        for (int j = 0; j < sub; j++) if (idx[j] == idx[sub]) unique = false;
+        const int me = idx[sub];
+        const float d[3] = {inc[3 * me] - ref[3 * me], inc[3 * me + 1] - ref[3 * me + 1], inc[3 * me + 2] - ref[3 * me + 2]};
+        dist = (((mb >> me) & 1u) && unique) ? v_dot(d, rn) : 1.f;
+        for (int i = 0; i < 3; i++) pos[i] = 0.5f * (inc[3 * me + i] + ref[3 * me + i]);
+      }
+      make_frame(nab, fr);
     } else if (kind == ABR_PAIR_PLANE_SPHERE || kind == ABR_PAIR_PLANE_CAPSULE) {
       float n[3] = {m1[2], m1[5], m1[8]};
       float sp[3] = {p2[0], p2[1], p2[2]};

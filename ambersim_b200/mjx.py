@@ -54,13 +54,14 @@ class SolverType(enum.IntEnum):
 
 
 _MODEL_FIELDS = [
-    "nq", "nv", "nu", "na", "nbody", "njnt", "ngeom", "neq", "npair", "nvert",
+    "nq", "nv", "nu", "na", "nbody", "njnt", "ngeom", "neq", "npair", "nvert", "nface", "nfacevert", "nedge",
     "body_parentid", "body_rootid", "body_jntnum", "body_jntadr", "body_dofnum", "body_dofadr", "body_pos",
     "body_quat", "body_ipos", "body_iquat", "body_mass", "body_subtreemass", "body_inertia", "body_invweight0",
     "jnt_type", "jnt_qposadr", "jnt_dofadr", "jnt_bodyid", "jnt_limited", "jnt_solref", "jnt_solimp", "jnt_pos",
     "jnt_axis", "jnt_stiffness", "jnt_range", "jnt_margin",
     "dof_bodyid", "dof_jntid", "dof_parentid", "dof_armature", "dof_damping", "dof_invweight0",
     "geom_type", "geom_bodyid", "geom_size", "geom_pos", "geom_quat", "geom_vertadr", "geom_vertnum", "vert",
+    "geom_faceadr", "geom_facenum", "face_vertadr", "face_vertnum", "face_vert", "face_normal", "geom_edgeadr", "geom_edgenum", "edge_vert",
     "pair_geom1", "pair_geom2", "pair_kind", "pair_condim", "pair_friction", "pair_solref", "pair_solimp",
     "pair_includemargin",
     "eq_type", "eq_obj1id", "eq_obj2id", "eq_active", "eq_solref", "eq_solimp", "eq_data",

@@ -27,7 +27,8 @@ _GEOM_TYPES = {
     "ellipsoid": GEOM_ELLIPSOID, "cylinder": GEOM_CYLINDER, "box": GEOM_BOX, "mesh": GEOM_MESH,
 }
 _JNT_TYPES = {"free": JNT_FREE, "ball": JNT_BALL, "slide": JNT_SLIDE, "hinge": JNT_HINGE}
-PAIR_PLANE_SPHERE, PAIR_PLANE_CAPSULE, PAIR_SPHERE_SPHERE, PAIR_SPHERE_CAPSULE, PAIR_CAPSULE_CAPSULE, PAIR_PLANE_CONVEX = range(6)
+(PAIR_PLANE_SPHERE, PAIR_PLANE_CAPSULE, PAIR_SPHERE_SPHERE, PAIR_SPHERE_CAPSULE, PAIR_CAPSULE_CAPSULE, PAIR_PLANE_CONVEX,
+ PAIR_SPHERE_CONVEX, PAIR_CAPSULE_CONVEX, PAIR_CONVEX_CONVEX) = range(9)
 _PAIR_KIND = {
     (GEOM_PLANE, GEOM_SPHERE): PAIR_PLANE_SPHERE,
     (GEOM_PLANE, GEOM_CAPSULE): PAIR_PLANE_CAPSULE,
@@ -36,9 +37,19 @@ _PAIR_KIND = {
     (GEOM_SPHERE, GEOM_SPHERE): PAIR_SPHERE_SPHERE,
     (GEOM_SPHERE, GEOM_CAPSULE): PAIR_SPHERE_CAPSULE,
     (GEOM_CAPSULE, GEOM_CAPSULE): PAIR_CAPSULE_CAPSULE,
+    # convex geoms against spheres, capsules and each other (mjx collision_convex.sphere_convex / capsule_convex / convex_convex)
+    (GEOM_SPHERE, GEOM_BOX): PAIR_SPHERE_CONVEX,
+    (GEOM_SPHERE, GEOM_MESH): PAIR_SPHERE_CONVEX,
+    (GEOM_CAPSULE, GEOM_BOX): PAIR_CAPSULE_CONVEX,
+    (GEOM_CAPSULE, GEOM_MESH): PAIR_CAPSULE_CONVEX,
+    (GEOM_BOX, GEOM_BOX): PAIR_CONVEX_CONVEX,
+    (GEOM_BOX, GEOM_MESH): PAIR_CONVEX_CONVEX,
+    (GEOM_MESH, GEOM_MESH): PAIR_CONVEX_CONVEX,
 }
 PAIR_NCON = {PAIR_PLANE_SPHERE: 1, PAIR_PLANE_CAPSULE: 2, PAIR_SPHERE_SPHERE: 1, PAIR_SPHERE_CAPSULE: 1,
-             PAIR_CAPSULE_CAPSULE: 1, PAIR_PLANE_CONVEX: 4}
+             PAIR_CAPSULE_CAPSULE: 1, PAIR_PLANE_CONVEX: 4, PAIR_SPHERE_CONVEX: 1, PAIR_CAPSULE_CONVEX: 2, PAIR_CONVEX_CONVEX: 4}
+MAX_FACE_VERTS = 8   # polygon faces larger than this stay triangulated (the kernels clip into fixed-size local arrays)
+MAX_CONVEX_VERTS = 64  # per geom, for the pairs that need the hull's faces and edges (sphere / capsule / convex - convex)
 _DISABLE_BITS = {
     "constraint": 1, "equality": 2, "frictionloss": 4, "limit": 8, "contact": 16, "passive": 32,
     "gravity": 64, "clampctrl": 128, "warmstart": 256, "filterparent": 512, "actuation": 1024,
@@ -240,6 +251,84 @@ def convex_vertices(points: np.ndarray) -> np.ndarray:
         return pts
 
 
+def convex_topology(verts: np.ndarray):
+    """Faces and edges of the convex hull of `verts` (all of them hull vertices): what sphere - convex, capsule - convex and
+    convex - convex collision need beyond the vertex set (mjx keeps the same per-mesh tables: polygon faces, face normals, unique
+    edges). Returns (faces, normals, edges): `faces` a list of vertex-index lists, counter-clockwise seen from outside, coplanar
+    hull triangles merged into one polygon (up to MAX_FACE_VERTS vertices; larger polygons stay triangles), `normals` the outward
+    unit normals, `edges` the unique polygon edges as (i, j) pairs with i < j. Degenerate sets (flat, fewer than 4 points) have no
+    faces."""
+    pts = np.asarray(verts, dtype=np.float64).reshape(-1, 3)
+    if len(pts) < 4:
+        return [], np.zeros((0, 3)), np.zeros((0, 2), dtype=np.int32)
+    try:
+        from scipy.spatial import ConvexHull
+
+        hull = ConvexHull(pts)
+    except Exception:
+        return [], np.zeros((0, 3)), np.zeros((0, 2), dtype=np.int32)
+    scale = max(1e-12, float(np.abs(pts).max()))
+    groups = []  # [normal, offset, set of vertex ids, list of triangles]
+    for tri, eq in zip(hull.simplices, hull.equations):
+        n, d = eq[:3], eq[3]
+        for grp in groups:
+            if np.dot(grp[0], n) > 1.0 - 1e-9 and abs(grp[1] - d) < 1e-9 * scale + 1e-12:
+                grp[2].update(int(i) for i in tri)
+                grp[3].append(tri)
+                break
+        else:
+            groups.append([n.copy(), float(d), set(int(i) for i in tri), [tri]])
+    faces, normals = [], []
+
+    def ordered(ids, n):
+        ids = sorted(ids)
+        c = pts[ids].mean(axis=0)
+        u = pts[ids[0]] - c
+        u = u - n * np.dot(u, n)
+        u /= max(np.linalg.norm(u), 1e-300)
+        w = np.cross(n, u)
+        ang = [np.arctan2(np.dot(pts[i] - c, w), np.dot(pts[i] - c, u)) for i in ids]
+        return [ids[k] for k in np.argsort(ang, kind="stable")]
+
+    for n, d, ids, tris in groups:
+        n = n / np.linalg.norm(n)
+        if len(ids) <= MAX_FACE_VERTS:
+            faces.append(ordered(ids, n))
+            normals.append(n)
+        else:
+            for tri in tris:
+                faces.append(ordered(set(int(i) for i in tri), n))
+                normals.append(n)
+    # canonical order (independent of qhull's facet order): by the direction of the normal, then by the lowest vertex id
+    order = sorted(range(len(faces)), key=lambda f: (tuple(np.round(-normals[f], 9)), min(faces[f])))
+    faces = [faces[f] for f in order]
+    normals = np.array([normals[f] for f in order]).reshape(-1, 3)
+    faces = [f[f.index(min(f)):] + f[:f.index(min(f))] for f in faces]  # start every polygon at its lowest vertex id
+    edges = sorted({(min(a, b), max(a, b)) for f in faces for a, b in zip(f, f[1:] + f[:1])})
+    if any(len(f) > MAX_FACE_VERTS for f in faces):
+        raise AssertionError("polygon larger than MAX_FACE_VERTS")
+    return faces, normals, np.array(edges, dtype=np.int32).reshape(-1, 2)
+
+
+def attach_convex_topology(m) -> None:
+    """Face / edge tables of every convex (box / mesh) geom of `m`, in the flat layout the model blob carries:
+    geom_faceadr / geom_facenum -> face_vertadr / face_vertnum -> face_vert (vertex ids LOCAL to the geom's vertex set),
+    face_normal (geom frame); geom_edgeadr / geom_edgenum -> edge_vert."""
+    fadr, fnum, fva, fvn, fv, fn, eadr, enum_, ev = [], [], [], [], [], [], [], [], []
+    for g in range(m.ngeom):
+        a, n = int(m.geom_vertadr[g]), int(m.geom_vertnum[g])
+        faces, normals, edges = convex_topology(m.vert[a:a + n]) if n else ([], np.zeros((0, 3)), np.zeros((0, 2), dtype=np.int32))
+        fadr.append(len(fva)); fnum.append(len(faces))
+        for f, nn in zip(faces, normals):
+            fva.append(len(fv)); fvn.append(len(f)); fv.extend(f); fn.append(nn)
+        eadr.append(len(ev)); enum_.append(len(edges)); ev.extend(edges.tolist())
+    i32 = lambda x: np.array(x, dtype=np.int32)
+    m.geom_faceadr, m.geom_facenum, m.face_vertadr, m.face_vertnum, m.face_vert = i32(fadr), i32(fnum), i32(fva), i32(fvn), i32(fv)
+    m.face_normal = np.array(fn, dtype=np.float64).reshape(-1, 3)
+    m.geom_edgeadr, m.geom_edgenum, m.edge_vert = i32(eadr), i32(enum_), i32(ev).reshape(-1, 2)
+    m.nface, m.nfacevert, m.nedge = len(fva), len(fv), len(ev)
+
+
 def box_vertices(size) -> np.ndarray:
     """The 8 corners of a box geom (half extents `size`), in the order mjx builds them: x slowest, z fastest."""
     s = np.asarray(size, dtype=np.float64)[:3]
@@ -348,6 +437,19 @@ def enumerate_pairs(m: "MjModel", G, excludes, explicit=()) -> None:
         pairs.append(dict(g1=g1, g2=g2, kind=_PAIR_KIND[key], condim=int(e["condim"]), friction=np.asarray(e["friction"], dtype=np.float64),
                           solref=np.asarray(e["solref"], dtype=np.float64), solimp=np.asarray(e["solimp"], dtype=np.float64),
                           includemargin=float(e["includemargin"])))
+    # sphere / capsule / convex - convex pairs work on the hull's faces and edges: the geom needs a proper (3-D) hull of bounded size
+    kept = []
+    for pr in pairs:
+        if pr["kind"] in (PAIR_SPHERE_CONVEX, PAIR_CAPSULE_CONVEX, PAIR_CONVEX_CONVEX):
+            bad = [g for g in ((pr["g2"],) if pr["kind"] != PAIR_CONVEX_CONVEX else (pr["g1"], pr["g2"]))
+                   if m.geom_facenum[g] == 0 or m.geom_vertnum[g] > MAX_CONVEX_VERTS]
+            if bad:
+                unsupported += 1
+                reason = (f"convex geom {G[bad[0]]['name']} has {int(m.geom_vertnum[bad[0]])} hull vertices and {int(m.geom_facenum[bad[0]])} faces "
+                          f"(needs a 3-D hull of at most {MAX_CONVEX_VERTS} vertices)")
+                continue
+        kept.append(pr)
+    pairs = kept
     npair = len(pairs)
     m.npair = npair
     m.pair_geom1 = np.array([p["g1"] for p in pairs], dtype=np.int32)
@@ -714,6 +816,7 @@ class _Compiler:
         m.geom_vertnum = np.array(num, dtype=np.int32)
         m.nvert = int(sum(num))
         m.vert = np.array(pool, dtype=np.float64).reshape(m.nvert, 3)
+        attach_convex_topology(m)
 
         m.names = dict(
             body=[b["name"] for b in self.bodies], joint=[j["name"] for j in self.joints],

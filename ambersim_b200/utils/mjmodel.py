@@ -120,6 +120,7 @@ def from_mjmodel(mj) -> mjcf.MjModel:
     m.geom_vertadr, m.geom_vertnum = np.array(adr, dtype=np.int32), np.array(num, dtype=np.int32)
     m.nvert = int(sum(num))
     m.vert = np.array(pool, dtype=np.float64).reshape(m.nvert, 3)
+    mjcf.attach_convex_topology(m)
     geoms = [dict(name=f"geom{g}", type=int(m.geom_type[g]), body=int(m.geom_bodyid[g]), contype=int(m.geom_contype[g]),
                   conaffinity=int(m.geom_conaffinity[g]), condim=int(m.geom_condim[g]), priority=int(m.geom_priority[g]),
                   friction=m.geom_friction[g], solmix=float(m.geom_solmix[g]), solref=m.geom_solref[g], solimp=m.geom_solimp[g],

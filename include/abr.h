@@ -57,7 +57,11 @@ enum { ABR_GAIN_FIXED = 0, ABR_GAIN_AFFINE = 1 };
 enum { ABR_BIAS_NONE = 0, ABR_BIAS_AFFINE = 1 };
 enum { ABR_PAIR_PLANE_SPHERE = 0, ABR_PAIR_PLANE_CAPSULE = 1, ABR_PAIR_SPHERE_SPHERE = 2,
        ABR_PAIR_SPHERE_CAPSULE = 3, ABR_PAIR_CAPSULE_CAPSULE = 4,
-       ABR_PAIR_PLANE_CONVEX = 5 /* plane vs box / mesh: 4 contacts (mjx collision_convex.plane_convex) */ };
+       ABR_PAIR_PLANE_CONVEX = 5,   /* plane vs box / mesh: 4 contacts (mjx collision_convex.plane_convex) */
+       ABR_PAIR_SPHERE_CONVEX = 6,  /* sphere vs box / mesh: 1 contact (collision_convex.sphere_convex) */
+       ABR_PAIR_CAPSULE_CONVEX = 7, /* capsule vs box / mesh: 2 contacts (collision_convex.capsule_convex) */
+       ABR_PAIR_CONVEX_CONVEX = 8   /* box / mesh vs box / mesh: separating axes + face clipping, 4 contacts (collision_convex.convex_convex) */ };
+enum { ABR_MAX_FACE_VERTS = 8, ABR_MAX_CONVEX_VERTS = 64 };
 /* mjtDisableBit */
 enum {
   ABR_DSBL_CONSTRAINT = 1, ABR_DSBL_EQUALITY = 2, ABR_DSBL_FRICTIONLOSS = 4, ABR_DSBL_LIMIT = 8,
@@ -101,6 +105,9 @@ typedef struct AbrModelHost {
   int neq;
   int npair;       /* statically enumerated colliding geom pairs (MJX enumerates at trace time) */
   int nvert;       /* vertices of all convex (box / mesh) geoms */
+  int nface;       /* polygon faces of all convex geoms */
+  int nfacevert;   /* polygon corners of all faces */
+  int nedge;       /* unique hull edges of all convex geoms */
   AbrOpt opt;
   /* bodies [nbody] */
   const int* body_parentid;
@@ -146,6 +153,16 @@ typedef struct AbrModelHost {
   const int* geom_vertadr;      /* [ngeom] first vertex of a box / mesh geom in `vert` */
   const int* geom_vertnum;      /* [ngeom] number of vertices (0 for non-convex-set geoms) */
   const float* vert;            /* [nvert,3] convex-hull vertices in the geom frame (boxes: the 8 corners) */
+  /* hull topology of the convex geoms (sphere / capsule / convex - convex pairs): polygon faces, counter-clockwise from outside */
+  const int* geom_faceadr;      /* [ngeom] first face of the geom in the face tables */
+  const int* geom_facenum;      /* [ngeom] number of faces (0: no 3-D hull) */
+  const int* face_vertadr;      /* [nface] first corner of the face in `face_vert` */
+  const int* face_vertnum;      /* [nface] corners of the face (3 .. ABR_MAX_FACE_VERTS) */
+  const int* face_vert;         /* [nfacevert] vertex ids LOCAL to the geom's vertex set */
+  const float* face_normal;     /* [nface,3] outward unit normal, geom frame */
+  const int* geom_edgeadr;      /* [ngeom] first edge of the geom in `edge_vert` */
+  const int* geom_edgenum;      /* [ngeom] number of unique hull edges */
+  const int* edge_vert;         /* [nedge,2] local vertex ids of an edge's end points */
   /* static contact pairs [npair]; mixing of friction/solref/solimp/margin done by the loader */
   const int* pair_geom1;
   const int* pair_geom2;

@@ -23,6 +23,7 @@
 #include <map>
 #include <string>
 #include <thread>
+#include <memory>
 #include <vector>
 
 #include "../include/abr.h"
@@ -199,10 +200,114 @@ template <class T> void cho_solve(const T* L, const T* b, T* x, int n) {
   }
 }
 
+
+// ----------------------------------------------------------------------------- convex collision helpers
+// mjx/_src/math.py + collision_convex.py [MEMORY, MJX 3.1.x; parity unpinned]: the geometric primitives of sphere - convex,
+// capsule - convex and convex - convex collision.
+template <class T> inline void closest_segment_point(const T* a, const T* b, const T* pt, T* out) {
+  T ab[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, pa[3] = {pt[0] - a[0], pt[1] - a[1], pt[2] - a[2]};
+  T t = Clip(dot3(pa, ab) / (dot3(ab, ab) + T(1e-6)), T(0), T(1));
+  for (int i = 0; i < 3; i++) out[i] = a[i] + t * ab[i];
+}
+// math.closest_segment_to_segment_points
+template <class T> inline void closest_segment_to_segment_points(const T* a0, const T* a1, const T* b0, const T* b1, T* best_a, T* best_b) {
+  T da[3], db[3];
+  for (int i = 0; i < 3; i++) { da[i] = a1[i] - a0[i]; db[i] = b1[i] - b0[i]; }
+  const T la = normalize(da, 3), lb = normalize(db, 3);
+  const T ha = la * T(0.5), hb = lb * T(0.5);
+  T am[3], bm[3], tr[3];
+  for (int i = 0; i < 3; i++) { am[i] = a0[i] + da[i] * ha; bm[i] = b0[i] + db[i] * hb; tr[i] = am[i] - bm[i]; }
+  const T dd = dot3(da, db), dat = dot3(da, tr), dbt = dot3(db, tr);
+  const T denom = T(1) - dd * dd;
+  const T ota = (-dat + dd * dbt) / (denom + T(1e-6));
+  const T otb = dbt + ota * dd;
+  const T ta = Clip(ota, -ha, ha), tb = Clip(otb, -hb, hb);
+  T pa[3], pb[3];
+  for (int i = 0; i < 3; i++) { pa[i] = am[i] + da[i] * ta; pb[i] = bm[i] + db[i] * tb; }
+  T na[3], nb[3];
+  closest_segment_point(a0, a1, pb, na);
+  closest_segment_point(b0, b1, pa, nb);
+  T e1[3] = {na[0] - pb[0], na[1] - pb[1], na[2] - pb[2]}, e2[3] = {pa[0] - nb[0], pa[1] - nb[1], pa[2] - nb[2]};
+  const bool first = dot3(e1, e1) < dot3(e2, e2);
+  for (int i = 0; i < 3; i++) { best_a[i] = first ? na[i] : pa[i]; best_b[i] = first ? pb[i] : nb[i]; }
+}
+template <class T> inline void project_pt_onto_plane(const T* pt, const T* plane_pt, const T* n, T* out) {
+  T d[3] = {pt[0] - plane_pt[0], pt[1] - plane_pt[1], pt[2] - plane_pt[2]};
+  const T dist = dot3(d, n);
+  for (int i = 0; i < 3; i++) out[i] = pt[i] - dist * n[i];
+}
+// collision_convex._closest_segment_point_plane: where the segment (a, b) meets the plane, clipped to the segment
+template <class T> inline void closest_segment_point_plane(const T* a, const T* b, const T* p0, const T* n, T* out) {
+  T ab[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
+  const T d = dot3(p0, n), denom = dot3(n, ab);
+  T t = (d - dot3(n, a)) / (denom + ((denom == T(0)) ? T(1e-6) : T(0)));
+  t = Clip(t, T(0), T(1));
+  for (int i = 0; i < 3; i++) out[i] = a[i] + t * ab[i];
+}
+// collision_convex._clip_edge_to_planes: the segment (p0, p1) cut by np side planes (point, outward normal); `ok` is false when
+// the segment lies entirely in front of one plane (then the original end points are returned) or the cut end points crossed
+template <class T> inline void clip_edge_to_planes(const T* p0, const T* p1, const T* plane_pts, const T* plane_normals, int np, T* out0, T* out1, bool* ok) {
+  T e01[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]}, e10[3] = {-e01[0], -e01[1], -e01[2]};
+  bool any_both = false;
+  T best0 = T(-1e30), best1 = T(-1e30);
+  T n0[3] = {p0[0], p0[1], p0[2]}, n1[3] = {p1[0], p1[1], p1[2]};
+  for (int k = 0; k < np; k++) {
+    const T* pp = plane_pts + 3 * k; const T* pn = plane_normals + 3 * k;
+    T d0[3] = {p0[0] - pp[0], p0[1] - pp[1], p0[2] - pp[2]}, d1[3] = {p1[0] - pp[0], p1[1] - pp[1], p1[2] - pp[2]};
+    const bool f0 = dot3(d0, pn) > T(1e-6), f1 = dot3(d1, pn) > T(1e-6);
+    any_both = any_both || (f0 && f1);
+    T cp[3];
+    closest_segment_point_plane(p0, p1, pp, pn, cp);
+    // the candidate for an end point is the cut point where that end is in front of the plane, the end point itself otherwise;
+    // the one furthest along the edge wins (first maximum)
+    T c0[3], c1[3];
+    for (int i = 0; i < 3; i++) { c0[i] = f0 ? cp[i] : p0[i]; c1[i] = f1 ? cp[i] : p1[i]; }
+    T r0[3] = {c0[0] - p0[0], c0[1] - p0[1], c0[2] - p0[2]}, r1[3] = {c1[0] - p1[0], c1[1] - p1[1], c1[2] - p1[2]};
+    const T s0 = dot3(r0, e01), s1 = dot3(r1, e10);
+    if (s0 > best0) { best0 = s0; for (int i = 0; i < 3; i++) n0[i] = c0[i]; }
+    if (s1 > best1) { best1 = s1; for (int i = 0; i < 3; i++) n1[i] = c1[i]; }
+  }
+  bool mask = !any_both;
+  for (int i = 0; i < 3; i++) { out0[i] = mask ? n0[i] : p0[i]; out1[i] = mask ? n1[i] : p1[i]; }
+  T dn[3] = {out0[0] - out1[0], out0[1] - out1[1], out0[2] - out1[2]};
+  if (dot3(e10, dn) < T(0)) mask = false;  // (p0 - p1).(new0 - new1) < 0: the cut points crossed
+  *ok = mask;
+}
+// collision_convex._manifold_points: up to four well-spread points of a masked planar point set (first maximum wins, as jnp.argmax)
+template <class T> inline void manifold_points(const T* pts, const bool* mask, int n, const T* normal, int idx[4]) {
+  auto dm = [&](int k) { return mask[k] ? T(0) : T(-1e6); };
+  auto argmax = [&](auto score) { int best = 0; T bv = score(0); for (int k = 1; k < n; k++) { T v = score(k); if (v > bv) { bv = v; best = k; } } return best; };
+  const int ia = argmax([&](int k) { return dm(k); });
+  const T* a = pts + 3 * ia;
+  const int ib = argmax([&](int k) { T d[3] = {a[0] - pts[3 * k], a[1] - pts[3 * k + 1], a[2] - pts[3 * k + 2]}; return dot3(d, d) + dm(k); });
+  const T* b = pts + 3 * ib;
+  T amb[3] = {a[0] - b[0], a[1] - b[1], a[2] - b[2]}, ab[3];
+  cross(normal, amb, ab);
+  const int ic = argmax([&](int k) { T d[3] = {a[0] - pts[3 * k], a[1] - pts[3 * k + 1], a[2] - pts[3 * k + 2]}; return Abs(dot3(d, ab)) + dm(k); });
+  const T* c = pts + 3 * ic;
+  T amc[3] = {a[0] - c[0], a[1] - c[1], a[2] - c[2]}, bmc[3] = {b[0] - c[0], b[1] - c[1], b[2] - c[2]}, ac[3], bc[3];
+  cross(normal, amc, ac);
+  cross(normal, bmc, bc);
+  int id = 0;
+  T bv = T(-1e30);
+  for (int h = 0; h < 2; h++)
+    for (int k = 0; k < n; k++) {
+      const T* o = h == 0 ? b : a;
+      const T* ax = h == 0 ? bc : ac;
+      T d[3] = {o[0] - pts[3 * k], o[1] - pts[3 * k + 1], o[2] - pts[3 * k + 2]};
+      const T v = Abs(dot3(d, ax)) + dm(k);
+      if (v > bv) { bv = v; id = k; }
+    }
+  idx[0] = ia; idx[1] = ib; idx[2] = ic; idx[3] = id;
+}
+
 // ----------------------------------------------------------------------------- the simulator
 struct Sizes { int ncon, ne, nl, nefc; };
 
-inline int pair_ncon(int kind) { return kind == ABR_PAIR_PLANE_CONVEX ? 4 : (kind == ABR_PAIR_PLANE_CAPSULE ? 2 : 1); }
+inline int pair_ncon(int kind) {
+  if (kind == ABR_PAIR_PLANE_CONVEX || kind == ABR_PAIR_CONVEX_CONVEX) return 4;
+  return (kind == ABR_PAIR_PLANE_CAPSULE || kind == ABR_PAIR_CAPSULE_CONVEX) ? 2 : 1;
+}
 
 Sizes compute_sizes(const AbrModelHost* m) {
   Sizes s{0, 0, 0, 0};
@@ -536,6 +641,278 @@ template <class T> struct Sim {
             con_pos[3 * c + i] = wp - T(0.5) * dist * n[i];
           }
           con_dist[c] = dist;
+          for (int i = 0; i < 9; i++) con_frame[9 * c + i] = fr[i];
+          con_pair[c++] = p;
+        }
+      } else if (kind == ABR_PAIR_SPHERE_CONVEX) {
+        // collision_convex.sphere_convex [MEMORY, MJX 3.1.x]: in the convex geom's frame. The face with the least penetration among
+        // those the sphere reaches behind; the closest point of that polygon to the sphere centre; one contact.
+        T dp[3] = {p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]}, sp[3];
+        for (int i = 0; i < 3; i++) sp[i] = m2[i] * dp[0] + m2[3 + i] * dp[1] + m2[6 + i] * dp[2];
+        const T rad = F(m->geom_size, 3 * g1);
+        const int fa = m->geom_faceadr[g2], nf = m->geom_facenum[g2], va = m->geom_vertadr[g2];
+        int best = 0;
+        T bestv = T(-1e30);
+        for (int f = 0; f < nf; f++) {
+          T nrm[3], v0[3], d[3];
+          const int k0 = m->face_vert[m->face_vertadr[fa + f]];
+          for (int i = 0; i < 3; i++) { nrm[i] = F(m->face_normal, 3 * (fa + f) + i); v0[i] = F(m->vert, 3 * (va + k0) + i); d[i] = sp[i] - v0[i]; }
+          T sup = dot3(d, nrm) - rad;
+          if (sup >= T(0)) sup = T(-1e12);
+          if (sup > bestv) { bestv = sup; best = f; }
+        }
+        const int pa = m->face_vertadr[fa + best], pn = m->face_vertnum[fa + best];
+        std::vector<T> P(3 * pn);
+        T nrm[3];
+        for (int i = 0; i < 3; i++) nrm[i] = F(m->face_normal, 3 * (fa + best) + i);
+        for (int k = 0; k < pn; k++) for (int i = 0; i < 3; i++) P[3 * k + i] = F(m->vert, 3 * (va + m->face_vert[pa + k]) + i);
+        T pt[3];
+        project_pt_onto_plane(sp, &P[0], nrm, pt);
+        bool inside = true;
+        int eidx = 0;
+        T ebest = T(1e30);
+        for (int k = 0; k < pn; k++) {
+          const T* e0 = &P[3 * ((k + pn - 1) % pn)]; const T* e1 = &P[3 * k];
+          T ed[3] = {e1[0] - e0[0], e1[1] - e0[1], e1[2] - e0[2]}, en[3], d[3] = {pt[0] - e0[0], pt[1] - e0[1], pt[2] - e0[2]};
+          cross(ed, nrm, en);
+          T dist = dot3(d, en);
+          if (!(dist <= T(0))) inside = false;
+          const bool degenerate = en[0] == T(0) && en[1] == T(0) && en[2] == T(0);
+          if (degenerate || dist < T(0)) dist = T(1e12);
+          if (dist < ebest) { ebest = dist; eidx = k; }
+        }
+        if (!inside) closest_segment_point(&P[3 * ((eidx + pn - 1) % pn)], &P[3 * eidx], pt, pt);
+        T n[3] = {pt[0] - sp[0], pt[1] - sp[1], pt[2] - sp[2]};
+        const T d = normalize(n, 3);
+        T pl[3];
+        for (int i = 0; i < 3; i++) pl[i] = T(0.5) * (pt[i] + sp[i] + n[i] * rad);
+        T nw[3];
+        for (int i = 0; i < 3; i++) {
+          nw[i] = m2[3 * i] * n[0] + m2[3 * i + 1] * n[1] + m2[3 * i + 2] * n[2];
+          con_pos[3 * c + i] = p2[i] + m2[3 * i] * pl[0] + m2[3 * i + 1] * pl[1] + m2[3 * i + 2] * pl[2];
+        }
+        con_dist[c] = d - rad;
+        make_frame(nw, &con_frame[9 * c]);
+        con_pair[c++] = p;
+      } else if (kind == ABR_PAIR_CAPSULE_CONVEX) {
+        // collision_convex.capsule_convex [MEMORY, MJX 3.1.x]: in the convex geom's frame. The capsule's axis segment clipped to the
+        // side planes of the best face gives two face contacts; a face edge closer to the axis than the radius replaces the first
+        // one by an edge contact (and switches the second off).
+        const T rad = F(m->geom_size, 3 * g1), half = F(m->geom_size, 3 * g1 + 1);
+        T dp[3] = {p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]}, cp[3], ax[3];
+        const T axw[3] = {m1[2], m1[5], m1[8]};
+        for (int i = 0; i < 3; i++) { cp[i] = m2[i] * dp[0] + m2[3 + i] * dp[1] + m2[6 + i] * dp[2]; ax[i] = m2[i] * axw[0] + m2[3 + i] * axw[1] + m2[6 + i] * axw[2]; }
+        T c0[3], c1[3];
+        for (int i = 0; i < 3; i++) { c0[i] = cp[i] - ax[i] * half; c1[i] = cp[i] + ax[i] * half; }
+        const int fa = m->geom_faceadr[g2], nf = m->geom_facenum[g2], va = m->geom_vertadr[g2];
+        int best = 0;
+        T bestv = T(-1e30);
+        bool has_support = true;
+        for (int f = 0; f < nf; f++) {
+          T nrm[3], v0[3], d0[3], d1[3];
+          const int k0 = m->face_vert[m->face_vertadr[fa + f]];
+          for (int i = 0; i < 3; i++) { nrm[i] = F(m->face_normal, 3 * (fa + f) + i); v0[i] = F(m->vert, 3 * (va + k0) + i); d0[i] = c0[i] - v0[i]; d1[i] = c1[i] - v0[i]; }
+          T sup = Min(dot3(d0, nrm), dot3(d1, nrm)) - rad;
+          if (!(sup < T(0))) has_support = false;
+          if (sup >= T(0)) sup = T(-1e12);
+          if (sup > bestv) { bestv = sup; best = f; }
+        }
+        const int pa = m->face_vertadr[fa + best], pn = m->face_vertnum[fa + best];
+        std::vector<T> P(3 * pn), E0(3 * pn), EN(3 * pn);
+        T nrm[3];
+        for (int i = 0; i < 3; i++) nrm[i] = F(m->face_normal, 3 * (fa + best) + i);
+        for (int k = 0; k < pn; k++) for (int i = 0; i < 3; i++) P[3 * k + i] = F(m->vert, 3 * (va + m->face_vert[pa + k]) + i);
+        for (int k = 0; k < pn; k++) {
+          const T* e0 = &P[3 * ((k + pn - 1) % pn)]; const T* e1 = &P[3 * k];
+          T ed[3] = {e1[0] - e0[0], e1[1] - e0[1], e1[2] - e0[2]};
+          cross(ed, nrm, &EN[3 * k]);
+          for (int i = 0; i < 3; i++) E0[3 * k + i] = e0[i];
+        }
+        T q[2][3];
+        bool ok;
+        clip_edge_to_planes(c0, c1, E0.data(), EN.data(), pn, q[0], q[1], &ok);
+        T pos[2][3], nl[2][3], dist[2];
+        for (int k = 0; k < 2; k++) {
+          T fp[3];
+          for (int i = 0; i < 3; i++) q[k][i] = q[k][i] - nrm[i] * rad;
+          project_pt_onto_plane(q[k], &P[0], nrm, fp);
+          T df[3] = {fp[0] - q[k][0], fp[1] - q[k][1], fp[2] - q[k][2]};
+          const T pen = (ok && has_support) ? dot3(df, nrm) : T(-1);
+          dist[k] = -pen;
+          for (int i = 0; i < 3; i++) { pos[k][i] = T(0.5) * (q[k][i] + fp[i]); nl[k][i] = -nrm[i]; }
+        }
+        // edge contact: the face edge closest to the capsule's axis
+        T ebest = T(1e30), ec[3] = {T(0), T(0), T(0)}, cc[3] = {T(0), T(0), T(0)};
+        for (int k = 0; k < pn; k++) {
+          T a[3], b[3];
+          closest_segment_to_segment_points(&E0[3 * k], &P[3 * k], c0, c1, a, b);
+          T d[3] = {a[0] - b[0], a[1] - b[1], a[2] - b[2]};
+          const T dd = dot3(d, d);
+          if (dd < ebest) { ebest = dd; for (int i = 0; i < 3; i++) { ec[i] = a[i]; cc[i] = b[i]; } }
+        }
+        T ea[3] = {cc[0] - ec[0], cc[1] - ec[1], cc[2] - ec[2]};
+        const T edist = normalize(ea, 3);
+        if (rad - edist > T(0)) {
+          for (int i = 0; i < 3; i++) { pos[0][i] = T(0.5) * (ec[i] + cc[i] - ea[i] * rad); nl[0][i] = -ea[i]; }
+          dist[0] = -(rad - edist);
+          dist[1] = T(1);
+        }
+        for (int k = 0; k < 2; k++) {
+          T nw[3];
+          for (int i = 0; i < 3; i++) {
+            nw[i] = m2[3 * i] * nl[k][0] + m2[3 * i + 1] * nl[k][1] + m2[3 * i + 2] * nl[k][2];
+            con_pos[3 * c + i] = p2[i] + m2[3 * i] * pos[k][0] + m2[3 * i + 1] * pos[k][1] + m2[3 * i + 2] * pos[k][2];
+          }
+          con_dist[c] = dist[k];
+          make_frame(nw, &con_frame[9 * c]);
+          con_pair[c++] = p;
+        }
+      } else if (kind == ABR_PAIR_CONVEX_CONVEX) {
+        // collision_convex.convex_convex [MEMORY, MJX 3.1.x]: separating-axis test over the face normals of both hulls and the
+        // cross products of their edges (world frame), then either the incident face clipped against the reference face (up to
+        // four contacts, _create_contact_manifold) or the closest points of the two edges (one contact). Face axes are preferred
+        // to an edge axis that is not better by more than 1e-5 m (a deviation: see DESIGN.md).
+        const int nva = m->geom_vertnum[g1], nvb = m->geom_vertnum[g2];
+        std::vector<T> VA(3 * nva), VB(3 * nvb);
+        auto to_world = [&](int g, const T* pg, const T* mg, int k, T* out) {
+          const int va = m->geom_vertadr[g];
+          T v[3] = {F(m->vert, 3 * (va + k)), F(m->vert, 3 * (va + k) + 1), F(m->vert, 3 * (va + k) + 2)};
+          for (int i = 0; i < 3; i++) out[i] = pg[i] + mg[3 * i] * v[0] + mg[3 * i + 1] * v[1] + mg[3 * i + 2] * v[2];
+        };
+        for (int k = 0; k < nva; k++) to_world(g1, p1, m1, k, &VA[3 * k]);
+        for (int k = 0; k < nvb; k++) to_world(g2, p2, m2, k, &VB[3 * k]);
+        const int fa = m->geom_faceadr[g1], nfa = m->geom_facenum[g1], fb = m->geom_faceadr[g2], nfb = m->geom_facenum[g2];
+        const int ea = m->geom_edgeadr[g1], nea = m->geom_edgenum[g1], eb = m->geom_edgeadr[g2], neb = m->geom_edgenum[g2];
+        auto face_normal_w = [&](int f, const T* mg, T* out) {
+          T nl[3] = {F(m->face_normal, 3 * f), F(m->face_normal, 3 * f + 1), F(m->face_normal, 3 * f + 2)};
+          for (int i = 0; i < 3; i++) out[i] = mg[3 * i] * nl[0] + mg[3 * i + 1] * nl[1] + mg[3 * i + 2] * nl[2];
+        };
+        auto axis_dist = [&](const T* axis, T* sign) {
+          T amax = T(-1e30), amin = T(1e30), bmax = T(-1e30), bmin = T(1e30);
+          for (int k = 0; k < nva; k++) { const T v = dot3(axis, &VA[3 * k]); amax = Max(amax, v); amin = Min(amin, v); }
+          for (int k = 0; k < nvb; k++) { const T v = dot3(axis, &VB[3 * k]); bmax = Max(bmax, v); bmin = Min(bmin, v); }
+          const T d1 = amax - bmin, d2 = bmax - amin;
+          *sign = (d1 > d2) ? T(-1) : T(1);
+          return Min(d1, d2);
+        };
+        T fbest = T(1e30), fsign = T(1), faxis[3] = {T(0), T(0), T(1)};
+        for (int f = 0; f < nfa + nfb; f++) {
+          T ax[3], sg;
+          if (f < nfa) face_normal_w(fa + f, m1, ax); else face_normal_w(fb + f - nfa, m2, ax);
+          const T d = axis_dist(ax, &sg);
+          if (d < fbest) { fbest = d; fsign = sg; for (int i = 0; i < 3; i++) faxis[i] = ax[i]; }
+        }
+        T ebest = T(1e30), epair = T(-1e30), esign = T(1), eaxis[3] = {T(0), T(0), T(1)};
+        int ei = 0, ej = 0;
+        for (int j = 0; j < neb; j++)
+          for (int i = 0; i < nea; i++) {
+            const T* a0 = &VA[3 * m->edge_vert[2 * (ea + i)]]; const T* a1 = &VA[3 * m->edge_vert[2 * (ea + i) + 1]];
+            const T* b0 = &VB[3 * m->edge_vert[2 * (eb + j)]]; const T* b1 = &VB[3 * m->edge_vert[2 * (eb + j) + 1]];
+            T da[3] = {a0[0] - a1[0], a0[1] - a1[1], a0[2] - a1[2]}, db[3] = {b0[0] - b1[0], b0[1] - b1[1], b0[2] - b1[2]};
+            normalize(da, 3);
+            normalize(db, 3);
+            T ax[3];
+            cross(da, db, ax);
+            if (dot3(ax, ax) < T(1e-6)) continue;  // (nearly) parallel edges span no axis
+            normalize(ax, 3);
+            T sg;
+            const T d = axis_dist(ax, &sg);
+            // parallel edges (a box has four per direction) span the same axis and tie on it: among those the SUPPORTING pair is
+            // taken, the one whose own separation along the axis equals the hulls' (a deviation: see DESIGN.md)
+            T ma[3] = {a0[0] + a1[0], a0[1] + a1[1], a0[2] + a1[2]}, mb[3] = {b0[0] + b1[0], b0[1] + b1[1], b0[2] + b1[2]};
+            const T dpair = sg * T(0.5) * (dot3(ax, ma) - dot3(ax, mb));
+            if (d < ebest - T(1e-6) || (d < ebest + T(1e-6) && dpair > epair)) {
+              ebest = Min(ebest, d); epair = dpair; esign = sg; ei = i; ej = j;
+              for (int k = 0; k < 3; k++) eaxis[k] = ax[k];
+            }
+          }
+        const bool edge_contact = ebest < fbest - T(1e-5);
+        T nab[3];  // from geom 1 to geom 2
+        for (int i = 0; i < 3; i++) nab[i] = edge_contact ? esign * eaxis[i] : fsign * faxis[i];
+        T cdist[4] = {T(1), T(1), T(1), T(1)}, cpos[4][3];
+        for (int k = 0; k < 4; k++) for (int i = 0; i < 3; i++) cpos[k][i] = T(0.5) * (p1[i] + p2[i]);
+        if (edge_contact) {
+          T ca[3], cb[3];
+          closest_segment_to_segment_points(&VA[3 * m->edge_vert[2 * (ea + ei)]], &VA[3 * m->edge_vert[2 * (ea + ei) + 1]],
+                                            &VB[3 * m->edge_vert[2 * (eb + ej)]], &VB[3 * m->edge_vert[2 * (eb + ej) + 1]], ca, cb);
+          T d[3] = {cb[0] - ca[0], cb[1] - ca[1], cb[2] - ca[2]};
+          cdist[0] = dot3(d, nab);
+          for (int i = 0; i < 3; i++) cpos[0][i] = T(0.5) * (ca[i] + cb[i]);
+        } else {
+          // the faces most aligned with the axis; the better aligned one is the reference (clipping) face
+          int ia = 0, ib = 0;
+          T da = T(-1e30), db = T(-1e30);
+          for (int f = 0; f < nfa; f++) { T nn[3]; face_normal_w(fa + f, m1, nn); const T v = dot3(nn, nab); if (v > da) { da = v; ia = f; } }
+          for (int f = 0; f < nfb; f++) { T nn[3]; face_normal_w(fb + f, m2, nn); const T v = -dot3(nn, nab); if (v > db) { db = v; ib = f; } }
+          const bool ref_a = da >= db;
+          const int rf = ref_a ? fa + ia : fb + ib, sf = ref_a ? fb + ib : fa + ia;
+          const T* RV = ref_a ? VA.data() : VB.data(); const T* SV = ref_a ? VB.data() : VA.data();
+          T rn[3], sn[3];
+          face_normal_w(rf, ref_a ? m1 : m2, rn);
+          face_normal_w(sf, ref_a ? m2 : m1, sn);
+          const int nr = m->face_vertnum[rf], ns = m->face_vertnum[sf];
+          std::vector<T> RP(3 * nr), SP(3 * ns), RE0(3 * nr), REN(3 * nr), SE0(3 * ns), SEN(3 * ns);
+          for (int k = 0; k < nr; k++) for (int i = 0; i < 3; i++) RP[3 * k + i] = RV[3 * m->face_vert[m->face_vertadr[rf] + k] + i];
+          for (int k = 0; k < ns; k++) for (int i = 0; i < 3; i++) SP[3 * k + i] = SV[3 * m->face_vert[m->face_vertadr[sf] + k] + i];
+          auto side_planes = [&](const std::vector<T>& Pp, int n, const T* nn, std::vector<T>& E0, std::vector<T>& EN) {
+            for (int k = 0; k < n; k++) {
+              const T* e0 = &Pp[3 * ((k + n - 1) % n)]; const T* e1 = &Pp[3 * k];
+              T ed[3] = {e1[0] - e0[0], e1[1] - e0[1], e1[2] - e0[2]};
+              cross(ed, nn, &EN[3 * k]);  // outward for a counter-clockwise polygon
+              for (int i = 0; i < 3; i++) E0[3 * k + i] = e0[i];
+            }
+          };
+          side_planes(RP, nr, rn, RE0, REN);
+          side_planes(SP, ns, sn, SE0, SEN);
+          // collision_convex._clip: subject edges against the reference side planes, then the reference edges (carried onto the
+          // subject plane along the reference normal) against the subject's side planes
+          const int npt = 2 * (ns + nr);
+          std::vector<T> inc(3 * npt), ref(3 * npt);
+          std::vector<char> mk(npt);
+          for (int k = 0; k < ns; k++) {
+            bool ok;
+            clip_edge_to_planes(&SE0[3 * k], &SP[3 * k], RE0.data(), REN.data(), nr, &inc[3 * (2 * k)], &inc[3 * (2 * k + 1)], &ok);
+            mk[2 * k] = mk[2 * k + 1] = ok;
+          }
+          {
+            const T dpl = dot3(&SP[0], sn), denom = dot3(rn, sn);
+            std::vector<T> Q0(3 * nr), Q1(3 * nr);
+            for (int k = 0; k < nr; k++)
+              for (int h = 0; h < 2; h++) {
+                const T* src = h == 0 ? &RE0[3 * k] : &RP[3 * k];
+                const T t = (dpl - dot3(src, sn)) / (denom + ((denom == T(0)) ? T(1e-6) : T(0)));
+                T* dst = h == 0 ? &Q0[3 * k] : &Q1[3 * k];
+                for (int i = 0; i < 3; i++) dst[i] = src[i] + t * rn[i];
+              }
+            for (int k = 0; k < nr; k++) {
+              bool ok;
+              clip_edge_to_planes(&Q0[3 * k], &Q1[3 * k], SE0.data(), SEN.data(), ns, &inc[3 * (2 * (ns + k))], &inc[3 * (2 * (ns + k) + 1)], &ok);
+              mk[2 * (ns + k)] = mk[2 * (ns + k) + 1] = ok;
+            }
+          }
+          std::vector<char> mask(npt);
+          std::unique_ptr<bool[]> mb(new bool[npt]);
+          for (int k = 0; k < npt; k++) {
+            project_pt_onto_plane(&inc[3 * k], &RP[0], rn, &ref[3 * k]);
+            T d[3] = {inc[3 * k] - RP[0], inc[3 * k + 1] - RP[1], inc[3 * k + 2] - RP[2]};
+            mb[k] = mk[k] && (-dot3(d, rn) > T(1e-6));  // the incident point lies behind the reference face
+          }
+          int idx[4];
+          manifold_points(ref.data(), mb.get(), npt, rn, idx);
+          for (int q = 0; q < 4; q++) {
+            bool unique = true;
+            for (int j = 0; j < q; j++) if (idx[j] == idx[q]) unique = false;
+            T d[3] = {inc[3 * idx[q]] - ref[3 * idx[q]], inc[3 * idx[q] + 1] - ref[3 * idx[q] + 1], inc[3 * idx[q] + 2] - ref[3 * idx[q] + 2]};
+            const T pen = -dot3(d, rn);
+            cdist[q] = (mb[idx[q]] && unique) ? -pen : T(1);
+            for (int i = 0; i < 3; i++) cpos[q][i] = T(0.5) * (inc[3 * idx[q] + i] + ref[3 * idx[q] + i]);
+          }
+        }
+        T fr[9];
+        make_frame(nab, fr);
+        for (int q = 0; q < 4; q++) {
+          con_dist[c] = cdist[q];
+          for (int i = 0; i < 3; i++) con_pos[3 * c + i] = cpos[q][i];
           for (int i = 0; i < 9; i++) con_frame[9 * c + i] = fr[i];
           con_pair[c++] = p;
         }

@@ -138,3 +138,216 @@ def test_engine_matches_oracle_on_convex_contacts(load_model):
         got = shoot(m, t(x), t(u[None])).cpu().numpy()[1]
         assert np.abs(got - nxt).max() < 5e-4 * max(1.0, np.abs(nxt).max()), k
         x = nxt
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# sphere - convex, capsule - convex, convex - convex (second slice). The oracle restates
+# mjx collision_convex.sphere_convex / capsule_convex / convex_convex [MEMORY, MJX 3.1.x; parity unpinned]; the CPU tests pin it
+# against answers that follow from the geometry, the GPU test compares the engine's generic kernels with it.
+PAIR = """<mujoco><option timestep="0.002"/><worldbody><geom name="base" type="box" size=".2 .2 .1" pos="0 0 .1"/>
+  <body pos="0 0 1"><freejoint/><inertial pos="0 0 0" mass="1" diaginertia=".01 .01 .01"/>{geom}</body></worldbody></mujoco>"""
+
+
+def _pair(tmp_path, geom):
+    f = tmp_path / "pair.xml"
+    f.write_text(PAIR.format(geom=geom))
+    return load_mj_model_from_file(str(f))
+
+
+def test_hull_topology_of_a_box_and_of_a_mesh(load_model):
+    faces, normals, edges = mjcf.convex_topology(mjcf.box_vertices([0.1, 0.2, 0.05]))
+    assert len(faces) == 6 and all(len(f) == 4 for f in faces) and len(edges) == 12
+    v = mjcf.box_vertices([0.1, 0.2, 0.05])
+    for f, n in zip(faces, normals):
+        c = v[f].mean(axis=0)
+        assert np.isclose(abs(n).max(), 1.0) and np.dot(c, n) > 0  # axis-aligned, outward
+        for a, b in zip(f, f[1:] + f[:1]):  # counter-clockwise seen from outside
+            assert np.dot(np.cross(v[a] - c, v[b] - c), n) > 0
+    m = load_model("blocks")
+    g = m.names["geom"].index("ramp")
+    assert m.geom_vertnum[g] == 6 and m.geom_facenum[g] == 5 and m.geom_edgenum[g] == 9  # a triangular prism
+    assert sorted(m.face_vertnum[m.geom_faceadr[g]:m.geom_faceadr[g] + 5].tolist()) == [3, 3, 4, 4, 4]
+    assert m.pair_kind.tolist() == [mjcf.PAIR_CONVEX_CONVEX, mjcf.PAIR_CAPSULE_CONVEX, mjcf.PAIR_SPHERE_CONVEX] + [mjcf.PAIR_CONVEX_CONVEX] * 3
+    # Euler's formula on every hull
+    for g in range(m.ngeom):
+        if m.geom_facenum[g]:
+            assert m.geom_vertnum[g] - m.geom_edgenum[g] + m.geom_facenum[g] == 2
+
+
+def test_sphere_against_a_box_face_edge_and_corner(tmp_path):
+    m = _pair(tmp_path, '<geom type="sphere" size=".1"/>')
+    assert m.pair_kind.tolist() == [mjcf.PAIR_SPHERE_CONVEX] and (m.pair_geom1[0], m.pair_geom2[0]) == (1, 0)
+    o = Oracle(m)
+    assert o.ncon == 1
+    f = o.forward([0.05, 0.02, 0.2 + 0.1 - 0.01, 1, 0, 0, 0], np.zeros(6))  # over the top face, 1 cm deep
+    assert np.isclose(f["contact_dist"][0], -0.01) and np.allclose(f["contact_pos"][0], [0.05, 0.02, 0.195])
+    assert np.allclose(f["contact_frame"][0, 0], [0, 0, -1])  # from the sphere (geom 1 of the pair) to the box
+    assert f["qfrc_constraint"][2] > 0 and np.allclose(f["qfrc_constraint"][[0, 1]], 0, atol=1e-9)
+    f = o.forward([0.25, 0.0, 0.25, 1, 0, 0, 0], np.zeros(6))  # beyond the edge x = z = 0.2
+    assert np.isclose(f["contact_dist"][0], np.hypot(0.05, 0.05) - 0.1) and np.allclose(f["contact_frame"][0, 0], [-np.sqrt(0.5), 0, -np.sqrt(0.5)], atol=1e-4)
+    f = o.forward([0.25, 0.25, 0.25, 1, 0, 0, 0], np.zeros(6))  # beyond the corner
+    assert np.isclose(f["contact_dist"][0], np.sqrt(3) * 0.05 - 0.1) and np.allclose(f["contact_frame"][0, 0], -np.ones(3) / np.sqrt(3), atol=1e-4)
+    f = o.forward([0.0, 0.0, 0.5, 1, 0, 0, 0], np.zeros(6))  # clear
+    # clear of the box: the top face is not "reached behind", so the literal algorithm measures against a side face's top edge
+    assert np.isclose(f["contact_dist"][0], np.hypot(0.3, 0.2) - 0.1) and np.all(f["efc_force"] == 0)
+
+
+def test_capsule_lying_standing_and_overhanging(tmp_path):
+    m = _pair(tmp_path, '<geom type="capsule" size=".05 .1" euler="0 90 0"/>')
+    assert m.pair_kind.tolist() == [mjcf.PAIR_CAPSULE_CONVEX]
+    o = Oracle(m)
+    assert o.ncon == 2
+    f = o.forward([0.0, 0.0, 0.2 + 0.05 - 0.004, 1, 0, 0, 0], np.zeros(6))  # lying on the top face: one contact under each end
+    assert np.allclose(f["contact_dist"], -0.004) and np.allclose(sorted(f["contact_pos"][:, 0]), [-0.1, 0.1]) and np.allclose(f["contact_pos"][:, 2], 0.198)
+    assert np.allclose(f["contact_frame"][:, 0], [0, 0, -1])
+    m = _pair(tmp_path, '<geom type="capsule" size=".05 .1"/>')
+    f = Oracle(m).forward([0.05, 0.0, 0.2 + 0.15 - 0.004, 1, 0, 0, 0], np.zeros(6))  # standing: the lower end only
+    assert np.isclose(f["contact_dist"][0], -0.004) and f["contact_dist"][1] > 0.19
+    m = _pair(tmp_path, '<geom type="capsule" size=".05 .3" euler="0 90 0"/>')
+    f = Oracle(m).forward([0.0, 0.0, 0.2 + 0.05 - 0.004, 1, 0, 0, 0], np.zeros(6))
+    # longer than the box: the axis passes within a radius of the face's edges, and the literal algorithm then reports ONE edge
+    # contact (the face contacts are dropped: the TODO in mjx's capsule_convex)
+    assert np.isclose(f["contact_dist"][0], -0.004) and f["contact_dist"][1] == 1.0 and np.isclose(abs(f["contact_pos"][0, 0]), 0.2)
+
+
+def test_box_on_box_face_contact_and_crossed_edges(tmp_path):
+    m = _pair(tmp_path, '<geom type="box" size=".05 .08 .03"/>')
+    assert m.pair_kind.tolist() == [mjcf.PAIR_CONVEX_CONVEX] and (m.pair_geom1[0], m.pair_geom2[0]) == (0, 1)
+    o = Oracle(m)
+    assert o.ncon == 4 and o.nefc == 16
+    for yaw in (0.0, 0.3):
+        f = o.forward([0.02, 0.01, 0.2 + 0.03 - 0.002, np.cos(yaw / 2), 0, 0, np.sin(yaw / 2)], np.zeros(6))
+        d = f["contact_dist"]
+        act = d < 0
+        assert act.sum() >= 3 and np.allclose(d[act], -0.002, atol=1e-9) and np.all(d[~act] == 1.0)
+        assert np.allclose(f["contact_frame"][:, 0], [0, 0, 1])  # from the base (geom 1 of the pair) up to the small box
+        c, s = np.cos(yaw), np.sin(yaw)
+        corners = {(round(0.02 + c * x - s * y, 5), round(0.01 + s * x + c * y, 5)) for x in (-0.05, 0.05) for y in (-0.08, 0.08)}
+        got = {(round(x, 5), round(y, 5)) for x, y in f["contact_pos"][act, :2]}
+        assert got <= corners and len(got) == act.sum()  # the small box's bottom corners
+        assert np.allclose(f["contact_pos"][act, 2], 0.199) and f["qfrc_constraint"][2] > 0
+    # crossed edges: the small box's edge (local corner x = -.05, z = -.03, running along its y axis) is laid across the base's edge
+    # x = z = 0.2 (which runs along y), perpendicular to it, its two faces symmetric about the diagonal n = (1, 0, 1) / sqrt 2
+    n = np.array([1.0, 0.0, 1.0]) / np.sqrt(2)
+    t = np.array([1.0, 0.0, -1.0]) / np.sqrt(2)
+    yh = np.array([0.0, 1.0, 0.0])
+    ax, az = (n - yh) / np.sqrt(2), (n + yh) / np.sqrt(2)
+    if np.dot(np.cross(ax, t), az) < 0:
+        ax, az = az, ax
+    R = np.stack([ax, t, az], axis=1)  # columns: images of the box's x, y, z axes
+    w = 0.5 * np.sqrt(max(1e-12, 1 + np.trace(R)))
+    q = np.array([w, (R[2, 1] - R[1, 2]) / (4 * w), (R[0, 2] - R[2, 0]) / (4 * w), (R[1, 0] - R[0, 1]) / (4 * w)])
+    pos = np.array([0.2, 0.0, 0.2]) - 0.003 * n - R @ np.array([-0.05, 0.0, -0.03])
+    f = o.forward([*pos, *q], np.zeros(6))
+    d = f["contact_dist"]
+    assert np.isclose(d[0], -0.003, atol=1e-6) and np.all(d[1:] == 1.0)  # one edge - edge contact
+    assert np.allclose(f["contact_frame"][0, 0], n, atol=1e-6)
+    assert np.allclose(f["contact_pos"][0], np.array([0.2, 0, 0.2]) - 0.0015 * n, atol=1e-6)
+
+
+def test_box_dropped_on_a_box_comes_to_rest_with_its_weight_carried(tmp_path):
+    m = _pair(tmp_path, '<geom type="box" size=".05 .08 .03" friction="0.9 0.01 0.001"/>')
+    o = Oracle(m, m.opt.replace(iterations=50, ls_iterations=50))
+    q0 = np.array([0.03, -0.02, 0.2 + 0.03 + 0.01, np.cos(0.2), 0.02, 0.03, np.sin(0.2)])
+    q0[3:] /= np.linalg.norm(q0[3:])
+    xs = o.rollout(np.concatenate([q0, np.zeros(6)]), np.zeros((1200, 0)))
+    q, v = xs[-1, :7], xs[-1, 7:]
+    assert np.abs(v).max() < 0.02 and abs(q[2] - 0.23) < 2e-3  # resting on the base's top face
+    f = o.forward(q, v)
+    assert np.sum(f["contact_dist"] < 0) >= 3
+    assert np.allclose(f["qfrc_constraint"][:3], [0, 0, 9.81], atol=0.05 * 9.81)
+
+
+def test_oversized_or_flat_hulls_are_refused_like_mjx(tmp_path):
+    flat = '<geom type="mesh" mesh="flat"/>'
+    xml = PAIR.format(geom=flat).replace("<worldbody>", '<asset><mesh name="flat" vertex="0 0 0  .1 0 0  .1 .1 0  0 .1 0"/></asset><worldbody>')
+    f = tmp_path / "flat.xml"
+    f.write_text(xml)
+    m = load_mj_model_from_file(str(f))
+    assert m.n_unsupported_pairs == 1 and "hull" in m.unsupported_reason
+    from ambersim_b200 import mjx
+    assert mjx.device_put(m).n_unsupported_pairs == 1  # the device handle refuses it (NotImplementedError) unless contacts are disabled
+
+
+@pytest.mark.gpu
+def test_engine_matches_oracle_on_sphere_capsule_and_convex_pairs(load_model):
+    import torch
+
+    from ambersim_b200 import mjx
+
+    mj = load_model("blocks")
+    m = mjx.device_put(mj)
+    assert "generic kernels" in m.describe()
+    o = Oracle(mj)
+    rng = np.random.default_rng(5)
+    E = 96
+    qs = np.tile(mj.key_qpos("home"), (E, 1))
+    qs[:, 0] = rng.uniform(-0.2, 0.45, E)
+    qs[:, 1] = rng.uniform(-0.2, 0.2, E)
+    qs[:, 2] = rng.uniform(0.3, 0.42, E)
+    quat = np.array([1, 0, 0, 0]) + 0.2 * rng.normal(size=(E, 4))
+    qs[:, 3:7] = quat / np.linalg.norm(quat, axis=1, keepdims=True)
+    qs[:, 7:] += rng.uniform(-0.6, 0.6, (E, 3))
+    vs = 0.3 * rng.normal(size=(E, mj.nv))
+    cs = mj.key_ctrl("home") + 0.2 * rng.normal(size=(E, mj.nu))
+    t = lambda a: torch.tensor(a, dtype=torch.float32, device="cuda")
+    names = ("contact_dist", "contact_pos", "contact_frame", "efc_force", "qfrc_constraint", "qacc_smooth")
+    d = mjx.Data(qpos=t(qs), qvel=t(vs), ctrl=t(cs), qacc=torch.zeros((E, mj.nv), device="cuda"), qacc_warmstart=torch.zeros((E, mj.nv), device="cuda"),
+                 time=torch.zeros(E, device="cuda"))
+    f = mjx.forward(m, d, fields=names)
+    spans = []
+    c0 = 0
+    for k in mj.pair_kind:
+        spans.append((c0, c0 + mjcf.PAIR_NCON[int(k)], int(k)))
+        c0 += mjcf.PAIR_NCON[int(k)]
+    seen = {mjcf.PAIR_SPHERE_CONVEX: 0, mjcf.PAIR_CAPSULE_CONVEX: 0, mjcf.PAIR_CONVEX_CONVEX: 0}
+    flips, checked = [], 0
+    def close(r, a, b, gd, gp, gf, tol):
+        return (np.abs(r["contact_dist"][a:b] - gd[a:b]).max() < tol and np.abs(r["contact_pos"][a:b] - gp[a:b]).max() < tol
+                and np.abs(r["contact_frame"][a:b] - gf[a:b]).max() < 10 * tol)
+
+    ties = 0
+    for e in range(E):
+        ref = o.forward(f.qpos[e].cpu().numpy(), vs[e], cs[e], np.zeros(mj.nv))
+        gd, gp, gf = f.contact_dist[e].cpu().numpy(), f.contact_pos[e].cpu().numpy(), f.contact_frame[e].cpu().numpy()
+        r32 = None
+        world_ok = True
+        for a, b, kind in spans:
+            rd = ref["contact_dist"][a:b]
+            if not (rd < 0).any() and not (gd[a:b] < 0).any():
+                continue  # separated in both: which (inactive) candidates are reported is precision dependent
+            checked += 1
+            if close(ref, a, b, gd, gp, gf, 5e-6):
+                seen[kind] += 1
+                continue
+            # _manifold_points breaks structural ties by rounding (the two off-diagonal corners of a rectangular contact patch are
+            # equally far from the diagonal), so the float64 oracle may keep another corner than float32 arithmetic does: such pairs
+            # must then equal the FLOAT32 oracle (MJX's own precision)
+            world_ok = False
+            if r32 is None:
+                r32 = o.forward(f.qpos[e].cpu().numpy(), vs[e], cs[e], np.zeros(mj.nv), prec=1)
+            if close(r32, a, b, gd, gp, gf, 2e-5):
+                ties += 1
+                seen[kind] += 1
+            else:
+                flips.append((e, kind, np.round(rd, 4).tolist(), np.round(r32["contact_dist"][a:b], 4).tolist(), np.round(gd[a:b], 4).tolist()))
+        if world_ok:
+            for n in ("efc_force", "qfrc_constraint", "qacc_smooth"):
+                r, g = ref[n].ravel(), getattr(f, n)[e].cpu().numpy().ravel()
+                assert np.abs(r - g).max() <= 5e-4 * max(1e-6, np.abs(r).max()) + 1e-5, (n, e)
+            assert np.abs(ref["qacc"] - f.qacc[e].cpu().numpy()).max() <= 1e-3 * max(1.0, np.abs(ref["qacc"]).max())
+    assert all(v >= 5 for v in seen.values()), seen  # every new pair function is exercised in contact
+    # what equals neither oracle are ties again (the device contracts multiply-adds, the float32 oracle on the CPU does not): a few per cent
+    assert len(flips) <= 0.05 * checked, (len(flips), checked, flips)
+    print(f"convex pairs in contact: {checked} checked, {ties} equal to the float32 oracle only (rounding-decided ties), {len(flips)} equal to neither", flips)
+    # teacher-forced steps: each device step from the oracle's own state, while the robot settles on the pedestal
+    from ambersim_b200.trajopt.shooting import shoot
+
+    x = np.concatenate([mj.key_qpos("home"), np.zeros(mj.nv)])
+    x[2] = 0.36
+    for k in range(60):
+        u = mj.key_ctrl("home") + 0.3 * rng.normal(size=mj.nu)
+        nxt = o.rollout(x, u[None])[1]
+        got = shoot(m, t(x), t(u[None])).cpu().numpy()[1]
+        assert np.abs(got - nxt).max() < 1e-3 * max(1.0, np.abs(nxt).max()), k
+        x = nxt

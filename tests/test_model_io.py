@@ -82,19 +82,21 @@ def test_model_mirror_and_unsupported(tmp_path):
     m2 = model.replace(opt=model.opt.replace(timestep=0.002, iterations=1, ls_iterations=4, disableflags=mjx.DisableBit.CONTACT))
     assert m2.opt.iterations == 1 and model.opt.iterations == 100 and m2.opt.disableflags == 16 and m2.nq == 8
     assert np.allclose(model.actuator_ctrlrange, [[-30, 30]] * 4)
-    # plane - box is served (convex vertex sets, 4 contacts per pair); a box against a sphere is outside the engine's collision
-    # functions: reported like MJX's NotImplementedError
+    # plane - box and box - sphere are served (convex vertex sets / hull faces); a cylinder is outside the engine's collision
+    # functions (as it is outside MJX's): reported like MJX's NotImplementedError
     xml = tmp_path / "box.xml"
     xml.write_text("""<mujoco><worldbody><geom type="plane" size="1 1 .1"/>
       <body pos="0 0 1"><freejoint/><inertial pos="0 0 0" mass="1" diaginertia=".1 .1 .1"/>
       <geom type="box" size=".1 .2 .3"/></body>
       <body pos="1 0 1"><freejoint/><inertial pos="0 0 0" mass="1" diaginertia=".1 .1 .1"/>
-      <geom type="sphere" size=".1"/></body></worldbody></mujoco>""")
+      <geom type="sphere" size=".1"/></body>
+      <body pos="2 0 1"><freejoint/><inertial pos="0 0 0" mass="1" diaginertia=".1 .1 .1"/>
+      <geom type="cylinder" size=".1 .2"/></body></worldbody></mujoco>""")
     mjb = load_mj_model_from_file(xml)
-    assert sorted(mjb.pair_kind.tolist()) == [0, 5] and mjb.nvert == 8 and mjb.geom_vertnum.tolist() == [0, 8, 0]
+    assert sorted(mjb.pair_kind.tolist()) == [0, 5, 6] and mjb.nvert == 8 and mjb.geom_vertnum.tolist() == [0, 8, 0, 0]
     assert np.allclose(np.abs(mjb.vert), [[0.1, 0.2, 0.3]] * 8) and len({tuple(v) for v in mjb.vert.tolist()}) == 8
     bad = mjx.device_put(mjb)
-    assert bad.n_unsupported_pairs == 1
+    assert bad.n_unsupported_pairs == 3  # the cylinder against the plane, the box and the sphere
     with pytest.raises(NotImplementedError):
         bad.handle(0)
     urdf = tmp_path / "x.urdf"

@@ -1039,6 +1039,34 @@ int abr_model_create(const AbrModelHost* host, int device, AbrModel** out) {
   *out = nullptr;
   if (abr_device_count() <= 0) return fail(ABR_ENODEVICE, "no CUDA device: the engine has no CPU path");
   if (host->nq < 0 || host->nv < 0 || host->nbody < 1) return fail(ABR_EINVAL, "abr_model_create: bad sizes");
+  {  // the collision functions index per-lane arrays of fixed size with the hull tables: check them here, once
+    const AbrModelHost* h = host;
+    if (h->npair < 0 || h->ngeom < 0 || h->nvert < 0 || h->nface < 0 || h->nfacevert < 0 || h->nedge < 0) return fail(ABR_EINVAL, "abr_model_create: bad sizes");
+    if (h->ngeom > 0 && (!h->geom_vertadr || !h->geom_vertnum || !h->geom_faceadr || !h->geom_facenum || !h->geom_edgeadr || !h->geom_edgenum))
+      return fail(ABR_EINVAL, "abr_model_create: null hull table");
+    if ((h->nface > 0 && (!h->face_vertadr || !h->face_vertnum || !h->face_normal)) || (h->nfacevert > 0 && !h->face_vert) || (h->nedge > 0 && !h->edge_vert) ||
+        (h->npair > 0 && (!h->pair_kind || !h->pair_geom1 || !h->pair_geom2)))
+      return fail(ABR_EINVAL, "abr_model_create: null hull / pair table");
+    for (int g = 0; g < h->ngeom; g++) {
+      const int va = h->geom_vertadr[g], vn = h->geom_vertnum[g], fa = h->geom_faceadr[g], fn = h->geom_facenum[g], ea = h->geom_edgeadr[g], en = h->geom_edgenum[g];
+      if (vn < 0 || va < 0 || va + vn > h->nvert || fn < 0 || fa < 0 || fa + fn > h->nface || en < 0 || ea < 0 || ea + en > h->nedge)
+        return fail(ABR_EINVAL, "abr_model_create: hull table of a geom out of range");
+      for (int f = fa; f < fa + fn; f++) {
+        const int ca = h->face_vertadr[f], cn = h->face_vertnum[f];
+        if (cn < 3 || cn > ABR_MAX_FACE_VERTS || ca < 0 || ca + cn > h->nfacevert) return fail(ABR_EINVAL, "abr_model_create: a hull face needs 3 .. ABR_MAX_FACE_VERTS corners");
+        for (int k = ca; k < ca + cn; k++) if (h->face_vert[k] < 0 || h->face_vert[k] >= vn) return fail(ABR_EINVAL, "abr_model_create: face corner out of the geom's vertex set");
+      }
+      for (int e = 2 * ea; e < 2 * (ea + en); e++) if (h->edge_vert[e] < 0 || h->edge_vert[e] >= vn) return fail(ABR_EINVAL, "abr_model_create: edge end point out of the geom's vertex set");
+    }
+    for (int p = 0; p < h->npair; p++) {
+      const int k = h->pair_kind[p], g1 = h->pair_geom1[p], g2 = h->pair_geom2[p];
+      if (k < 0 || k > ABR_PAIR_CONVEX_CONVEX || g1 < 0 || g1 >= h->ngeom || g2 < 0 || g2 >= h->ngeom) return fail(ABR_EINVAL, "abr_model_create: bad contact pair");
+      const bool hull2 = k == ABR_PAIR_SPHERE_CONVEX || k == ABR_PAIR_CAPSULE_CONVEX || k == ABR_PAIR_CONVEX_CONVEX;
+      if (hull2 && (h->geom_facenum[g2] < 1 || h->geom_vertnum[g2] > ABR_MAX_CONVEX_VERTS)) return fail(ABR_EINVAL, "abr_model_create: convex pair needs a hull with faces and at most ABR_MAX_CONVEX_VERTS vertices");
+      if (k == ABR_PAIR_CONVEX_CONVEX && (h->geom_facenum[g1] < 1 || h->geom_vertnum[g1] > ABR_MAX_CONVEX_VERTS)) return fail(ABR_EINVAL, "abr_model_create: convex pair needs a hull with faces and at most ABR_MAX_CONVEX_VERTS vertices");
+      if (k == ABR_PAIR_PLANE_CONVEX && h->geom_vertnum[g2] < 1) return fail(ABR_EINVAL, "abr_model_create: plane - convex pair without vertices");
+    }
+  }
   ABR_ON_DEVICE(device);  // the blob, the handle's streams and its scratch all live on `device`
   AbrModel* m = new AbrModel();
   m->device = device;

@@ -351,3 +351,25 @@ def test_engine_matches_oracle_on_sphere_capsule_and_convex_pairs(load_model):
         got = shoot(m, t(x), t(u[None])).cpu().numpy()[1]
         assert np.abs(got - nxt).max() < 1e-3 * max(1.0, np.abs(nxt).max()), k
         x = nxt
+
+
+@pytest.mark.gpu
+def test_c_abi_refuses_inconsistent_hull_tables(load_model):
+    """The collision functions index fixed-size per-lane arrays with the hull tables: abr_model_create checks them once."""
+    import copy
+    import ctypes as C
+
+    from ambersim_b200 import _abi, _lib
+
+    mj = load_model("blocks")
+    for field, value, what in (("face_vertnum", 9, "corners"), ("face_vert", 99, "vertex set"),
+                               ("edge_vert", -1, "vertex set"), ("pair_kind", 12, "pair")):
+        bad = copy.copy(mj)
+        arr = np.array(getattr(mj, field)).copy()
+        arr.ravel()[0] = value
+        setattr(bad, field, arr)
+        host, keep = _abi.pack_model(bad, bad.opt)
+        ptr = C.c_void_p()
+        rc = _lib.lib().abr_model_create(C.byref(host), 0, C.byref(ptr))
+        assert rc == _lib.ABR_EINVAL and what in _lib.lib().abr_last_error().decode(), (field, rc, _lib.lib().abr_last_error())
+        assert not ptr.value

@@ -668,50 +668,11 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
       }
     }
   }
-  // ---------------------------------------------------------------- crb + M (smooth.crb, support.make_m)
-  {
-    float crb[10], up[10];
-#pragma unroll
-    for (int i = 0; i < 10; i++) up[i] = 0.f;
-#pragma unroll
-    for (int p = NP - 1; p >= 0; p--) {
-      if (S.m(p)) {
-#pragma unroll
-        for (int i = 0; i < 10; i++) up[i] = gs(up[i], S.l(p), S.m(p));
-      }
-#pragma unroll
-      for (int i = 0; i < 10; i++) crb[i] = cinert[p][i] + up[i];
-      // rows of M for the dofs of this position
-#pragma unroll
-      for (int i = 0; i < N; i++) {
-        if (PD(i) == p) {
-          float buf[6];
-          if (i < 3) inert_mul_unit(crb, i, buf); else inert_mul(crb, cdof[i], buf);
-#pragma unroll
-          for (int j = 0; j < N; j++) {
-            if (j <= i) {
-              float t = cdof_dot(cdof, j, buf);
-              if (i == j) t += (i < 6) ? LTF(mp.trunk() + 6 + i) : LTF(mp.jnt(PD(i)) + 10);
-              M[TR(i, j)] = t;
-            }
-          }
-        }
-      }
-      const bool ownp = S.o(p);
-#pragma unroll
-      for (int i = 0; i < 10; i++) up[i] = ownp ? crb[i] : 0.f;
-    }
-  }
-  // ---------------------------------------------------------------- factor M
-  float F[NTRI], invD[N];
-#pragma unroll
-  for (int i = 0; i < N; i++)
-#pragma unroll
-    for (int j = 0; j < N; j++)
-      if (j <= i) F[TR(i, j)] = S.o(PD(i)) ? M[TR(i, j)] : 0.f;
-  ldl_factor<N>(F, invD, S);
   // ---------------------------------------------------------------- velocity pass: com_vel + rne + passive + actuation
-  {
+  // Run BEFORE crb + M on the long-chain families (cinert is then dead when the factorisation needs its registers: biped +3 %) and
+  // after the factorisation on the short-chain ones (Barkour class: the other order costs 2 %, profiles/r2_attempt_stage_order.txt).
+  constexpr bool kVelFirst = NL >= 5;
+  auto velocity_pass = [&]() {
     float cvel[NP][6], cfrc[NP][6], cdd[N][6];
     float cv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     const bool grav = !(C.disableflags & ABR_DSBL_GRAVITY);
@@ -797,7 +758,51 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
 #pragma unroll
       for (int i = 0; i < 6; i++) up[i] = ownp ? f[i] : 0.f;
     }
+  };
+  if constexpr (kVelFirst) velocity_pass();
+  // ---------------------------------------------------------------- crb + M (smooth.crb, support.make_m)
+  {
+    float crb[10], up[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) up[i] = 0.f;
+#pragma unroll
+    for (int p = NP - 1; p >= 0; p--) {
+      if (S.m(p)) {
+#pragma unroll
+        for (int i = 0; i < 10; i++) up[i] = gs(up[i], S.l(p), S.m(p));
+      }
+#pragma unroll
+      for (int i = 0; i < 10; i++) crb[i] = cinert[p][i] + up[i];
+      // rows of M for the dofs of this position
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        if (PD(i) == p) {
+          float buf[6];
+          if (i < 3) inert_mul_unit(crb, i, buf); else inert_mul(crb, cdof[i], buf);
+#pragma unroll
+          for (int j = 0; j < N; j++) {
+            if (j <= i) {
+              float t = cdof_dot(cdof, j, buf);
+              if (i == j) t += (i < 6) ? LTF(mp.trunk() + 6 + i) : LTF(mp.jnt(PD(i)) + 10);
+              M[TR(i, j)] = t;
+            }
+          }
+        }
+      }
+      const bool ownp = S.o(p);
+#pragma unroll
+      for (int i = 0; i < 10; i++) up[i] = ownp ? crb[i] : 0.f;
+    }
   }
+  // ---------------------------------------------------------------- factor M
+  float F[NTRI], invD[N];
+#pragma unroll
+  for (int i = 0; i < N; i++)
+#pragma unroll
+    for (int j = 0; j < N; j++)
+      if (j <= i) F[TR(i, j)] = S.o(PD(i)) ? M[TR(i, j)] : 0.f;
+  ldl_factor<N>(F, invD, S);
+  if constexpr (!kVelFirst) velocity_pass();
   // ---------------------------------------------------------------- qacc_smooth
   float as[N];
 #pragma unroll

@@ -38,9 +38,9 @@ F_WS_EXO_LEGS = 67283.0  # same counter, legs-only exoskeleton stand-in
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
 # dram__bytes_read.sum + dram__bytes_write.sum of the C2 launch: one `ncu --set full` capture of THIS file's own kernel launch with
 # the kernels as shipped (round 2: `ncu ... -k regex:k_limb_rollout --launch-skip 3 -c 1 python bench.py --steps 2 --warmup 3 --no-extra`,
-# profiles/r2_c2_final_summary.txt): 198.31 MB read + 4.24 MB written vs 197.23 MB algorithmic (the controls). A profiler capture,
+# profiles/r2_c2_final_summary.txt): 197.44 MB read + 3.83 MB written vs 197.23 MB algorithmic (the controls). A profiler capture,
 # not a live counter of the run that prints it: `roofline.traffic_source` says so.
-NCU_DRAM_BYTES_C2 = 198_308_608 + 4_243_200
+NCU_DRAM_BYTES_C2 = 197_443_328 + 3_826_688
 
 
 def peaks():

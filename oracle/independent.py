@@ -289,3 +289,70 @@ def constraint_minimum(M, qacc_smooth, J, D, aref, ne, x0=None):
             t *= 0.5
         a = a - t * step
     return a
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Convex collision along routes that share nothing with collision_convex's separating axes / face clipping: the minimum
+# translation that separates two polytopes is the distance from the origin to the boundary of their Minkowski difference
+# (scipy's qhull), and the distance from a point / a segment to a polytope is a small constrained least-squares problem.
+def geom_world_vertices(m, g, xpos, xrot):
+    """World-frame hull vertices of convex geom g (box / mesh) for body frames (xpos, xrot) from `kinematics`."""
+    b = int(m.geom_bodyid[g])
+    R = xrot[b] @ _qmat(m.geom_quat[g])
+    p = xpos[b] + xrot[b] @ m.geom_pos[g]
+    v = m.vert[m.geom_vertadr[g]:m.geom_vertadr[g] + m.geom_vertnum[g]]
+    return p + v @ R.T
+
+
+def polytope_penetration(VA, VB):
+    """(depth, normal): the smallest translation of B along `normal` (from A to B) that separates the two hulls; depth < 0 = the gap
+    along the best separating facet direction when they do not touch. Through the facets of hull(B - A)."""
+    from scipy.spatial import ConvexHull
+
+    D = (VB[None, :, :] - VA[:, None, :]).reshape(-1, 3)  # Minkowski difference B - A: contains the origin iff the hulls overlap
+    eq = ConvexHull(D).equations  # n.x + d <= 0 inside
+    # distance from the origin to each facet plane along its outward normal: -d (positive when the origin is inside)
+    # facet normal n: max_B n.b - min_A n.a = -d is smallest there, i.e. B lies on the -n side of A: the direction from A to B is -n
+    k = int(np.argmin(-eq[:, 3]))
+    return float(-eq[k, 3]), -eq[k, :3].copy()
+
+
+def point_polytope_distance(p, V):
+    """Euclidean distance from point p to hull(V) (0 inside) and the closest point, by SLSQP over convex weights."""
+    from scipy.optimize import minimize
+
+    n = len(V)
+    f = lambda w: float(np.sum((w @ V - p) ** 2))
+    g = lambda w: 2.0 * V @ (w @ V - p)
+    best = None
+    for w0 in (np.full(n, 1.0 / n), np.eye(n)[int(np.argmin(np.sum((V - p) ** 2, axis=1)))]):
+        r = minimize(f, w0, jac=g, bounds=[(0, 1)] * n, constraints=[{"type": "eq", "fun": lambda w: w.sum() - 1, "jac": lambda w: np.ones(n)}],
+                     method="SLSQP", options={"ftol": 1e-16, "maxiter": 500})
+        if best is None or r.fun < best.fun:
+            best = r
+    return float(np.sqrt(max(best.fun, 0.0))), best.x @ V
+
+
+def segment_polytope_distance(a, b, V):
+    """Distance between the segment (a, b) and hull(V): SLSQP over (t, convex weights)."""
+    from scipy.optimize import minimize
+
+    n = len(V)
+
+    def f(z):
+        return float(np.sum((a + z[0] * (b - a) - z[1:] @ V) ** 2))
+
+    def g(z):
+        e = a + z[0] * (b - a) - z[1:] @ V
+        return np.concatenate([[2.0 * e @ (b - a)], -2.0 * V @ e])
+
+    best = None
+    for t0 in (0.0, 0.5, 1.0):
+        pt = a + t0 * (b - a)
+        w0 = np.eye(n)[int(np.argmin(np.sum((V - pt) ** 2, axis=1)))]
+        r = minimize(f, np.concatenate([[t0], w0]), jac=g, bounds=[(0, 1)] * (n + 1),
+                     constraints=[{"type": "eq", "fun": lambda z: z[1:].sum() - 1, "jac": lambda z: np.concatenate([[0.0], np.ones(n)])}],
+                     method="SLSQP", options={"ftol": 1e-16, "maxiter": 500})
+        if best is None or r.fun < best.fun:
+            best = r
+    return float(np.sqrt(max(best.fun, 0.0)))

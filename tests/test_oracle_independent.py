@@ -126,3 +126,116 @@ def test_random_models_setconst_and_aba(tmp_path, seed):
     f = Oracle(m, m.opt.replace(disableflags=1)).forward(q, v, rng.normal(size=m.nu) * 0.1)
     qa = ind.aba(m, q, v, f["qfrc_passive"] + f["qfrc_actuator"], m.opt.gravity)
     assert np.abs(qa - f["qacc_smooth"]).max() < 5e-6 * max(1.0, np.abs(f["qacc_smooth"]).max())
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# Convex collision: the oracle's separating-axis / clipping restatement against routes that share nothing with it
+# (Minkowski-difference hull for the penetration of two polytopes, constrained least squares for point / segment distances).
+CONVEX_PAIR = """<mujoco><worldbody><geom name="base" type="{base}" {basearg} pos="0 0 .1"/>
+  <body pos="0 0 1"><freejoint/><inertial pos="0 0 0" mass="1" diaginertia=".01 .01 .01"/>{geom}</body></worldbody>
+  <asset><mesh name="gem" vertex="0 0 .07  .06 0 0  -.03 .05 0  -.03 -.05 0  0 0 -.05  .04 .04 .03"/>
+  <mesh name="slab" vertex="-.2 -.2 -.1  .2 -.2 -.1  .2 .2 -.1  -.2 .2 -.1  -.15 -.2 .1  .2 -.2 .1  .2 .15 .1  -.15 .15 .1"/></asset></mujoco>"""
+
+
+def _convex_pair(tmp_path, geom, base="box"):
+    from ambersim_b200.utils.io_utils import load_mj_model_from_file
+
+    f = tmp_path / "cp.xml"
+    f.write_text(CONVEX_PAIR.format(geom=geom, base=base, basearg='size=".2 .2 .1"' if base == "box" else 'mesh="slab"'))
+    return load_mj_model_from_file(str(f))
+
+
+@pytest.mark.parametrize("base", ["box", "mesh"])
+@pytest.mark.parametrize("geom", ['<geom type="box" size=".05 .08 .03"/>', '<geom type="mesh" mesh="gem"/>'])
+def test_convex_convex_against_the_minkowski_difference(tmp_path, geom, base):
+    m = _convex_pair(tmp_path, geom, base)
+    o = Oracle(m)
+    rng = np.random.default_rng(11)
+    g1, g2 = int(m.pair_geom1[0]), int(m.pair_geom2[0])
+    touching = edge = exact = preferred = 0
+    for _ in range(120):
+        q = np.concatenate([rng.uniform(-0.22, 0.22, 2), [rng.uniform(0.2, 0.3)], rng.normal(size=4)])
+        q[3:] /= np.linalg.norm(q[3:])
+        xpos, xrot, _, _ = ind.kinematics(m, q)
+        depth, normal = ind.polytope_penetration(ind.geom_world_vertices(m, g1, xpos, xrot), ind.geom_world_vertices(m, g2, xpos, xrot))
+        f = o.forward(q, np.zeros(6))
+        d, n = f["contact_dist"], f["contact_frame"][0, 0]
+        if depth < 1e-4:
+            assert not (d < -1e-4).any()  # separated (or grazing): no contact reports a penetration
+            continue
+        touching += 1
+        # the contact normal is the direction of least penetration (or a FACE normal within the 1e-5 m by which the restatement
+        # prefers face axes to edge - edge axes), and no contact point is deeper than the penetration along it
+        VA, VB = ind.geom_world_vertices(m, g1, xpos, xrot), ind.geom_world_vertices(m, g2, xpos, xrot)
+        along = float((VA @ n).max() - (VB @ n).min())
+        if not np.allclose(n, normal, atol=2e-6):
+            preferred += 1
+            assert depth - 2e-7 <= along <= depth + 1.1e-5, (q, n, normal, along, depth)
+        depth = along
+        assert d.min() >= -depth - 2e-7  # (the model's vertices cross the ABI as float32)
+        if (d == 1.0).sum() == 3:  # an edge - edge contact: its single point carries the whole penetration
+            edge += 1
+            assert np.isclose(d[0], -depth, atol=2e-7)
+        exact += int(np.isclose(d.min(), -depth, atol=2e-7))
+    assert touching >= 40 and edge >= 3 and preferred <= 0.1 * touching
+    # face contacts: the deepest clipped point reaches the full depth unless the deepest vertex lies outside the reference face's prism
+    assert exact >= 0.8 * touching, (exact, touching)
+
+
+def test_sphere_convex_against_point_polytope_distance(tmp_path):
+    for base in ("box", "mesh"):
+        m = _convex_pair(tmp_path, '<geom type="sphere" size=".06"/>', base)
+        o = Oracle(m)
+        rng = np.random.default_rng(12)
+        g2 = int(m.pair_geom2[0])
+        active = 0
+        for _ in range(60):
+            q = np.concatenate([rng.uniform(-0.27, 0.27, 2), [rng.uniform(0.2, 0.27)], [1, 0, 0, 0]])
+            xpos, xrot, _, _ = ind.kinematics(m, q)
+            V = ind.geom_world_vertices(m, g2, xpos, xrot)
+            dist, closest = ind.point_polytope_distance(q[:3], V)
+            f = o.forward(q, np.zeros(6))
+            if dist < 1e-6:
+                continue  # centre inside the hull: outside what the reference's function is meant for
+            if dist - 0.06 < 0:
+                active += 1
+                if base == "mesh":
+                    # sphere_convex measures against ONE face (the least penetrated one the sphere reaches behind): on a hull with
+                    # slanted sides the closest point of that polygon need not be the hull's closest point, so the reported distance
+                    # is an upper bound of the true one, tight to a fraction of a millimetre here
+                    assert dist - 0.06 - 1e-6 <= f["contact_dist"][0] <= dist - 0.06 + 5e-4, (q, f["contact_dist"], dist - 0.06)
+                    continue
+                assert np.isclose(f["contact_dist"][0], dist - 0.06, atol=1e-6), (q, f["contact_dist"], dist - 0.06)
+                # (mjx's closest_segment_point carries a 1e-6 regulariser in its denominator: micrometres along an edge)
+                assert np.allclose(f["contact_frame"][0, 0], (closest - q[:3]) / dist, atol=1e-3)
+                assert np.allclose(f["contact_pos"][0], closest + 0.5 * (0.06 - dist) * (closest - q[:3]) / dist, atol=1e-5)
+            else:
+                assert f["contact_dist"][0] > 0
+        assert active >= 15
+
+
+def test_capsule_convex_against_segment_polytope_distance(tmp_path):
+    m = _convex_pair(tmp_path, '<geom type="capsule" size=".03 .05"/>')
+    o = Oracle(m)
+    rng = np.random.default_rng(13)
+    g1, g2 = int(m.pair_geom1[0]), int(m.pair_geom2[0])
+    active = 0
+    for _ in range(80):
+        q = np.concatenate([rng.uniform(-0.12, 0.12, 2), [rng.uniform(0.2, 0.3)], rng.normal(size=4)])  # over the top face, away from its edges
+        q[3:] /= np.linalg.norm(q[3:])
+        xpos, xrot, _, _ = ind.kinematics(m, q)
+        V = ind.geom_world_vertices(m, g2, xpos, xrot)
+        R = xrot[int(m.geom_bodyid[g1])] @ ind._qmat(m.geom_quat[g1])
+        c = xpos[int(m.geom_bodyid[g1])] + xrot[int(m.geom_bodyid[g1])] @ m.geom_pos[g1]
+        a, b = c - 0.05 * R[:, 2], c + 0.05 * R[:, 2]
+        dist = ind.segment_polytope_distance(a, b, V)
+        f = o.forward(q, np.zeros(6))
+        if dist < 1e-6:
+            continue  # the axis itself is inside the box
+        if dist - 0.03 < -1e-6:
+            active += 1
+            assert np.isclose(f["contact_dist"].min(), dist - 0.03, atol=1e-6), (q, f["contact_dist"], dist - 0.03)
+            assert np.allclose(f["contact_frame"][int(np.argmin(f["contact_dist"])), 0], [0, 0, -1], atol=1e-6)  # capsule -> box, through the top face
+        elif dist - 0.03 > 1e-6:
+            assert not (f["contact_dist"] < 0).any()
+    assert active >= 20

@@ -22,7 +22,7 @@ from ambersim_b200.rl.base import VectorEnvStepper
 from ambersim_b200.rl.pendulum.swingup import PendulumSwingupEnv
 from ambersim_b200.trajopt.base import CostFunction, CostFunctionParams
 from ambersim_b200.trajopt.cost import StaticGoalQuadraticCost
-from ambersim_b200.trajopt.shooting import VanillaPredictiveSampler, VanillaPredictiveSamplerParams, shoot, shoot_cost
+from ambersim_b200.trajopt.shooting import VanillaPredictiveSampler, VanillaPredictiveSamplerParams, _seed_of, shoot, shoot_cost
 from oracle.oracle import Oracle, quad_cost
 from tests import _philox
 
@@ -540,6 +540,45 @@ def test_mpc_loop_on_device_equals_python_loop(load_model, name):
     assert torch.equal(xs_d, torch.stack(xs_p)) and torch.equal(us_d, torch.stack(us_p))
     assert info["best_idx"].cpu().tolist() == idx_p
     assert torch.equal(info["us_guess"], g) and torch.equal(info["x"], x)
+
+
+@pytest.mark.parametrize("name", ["barkour", "bh280"])
+def test_mpc_closed_loop_against_the_oracle(load_model, name):
+    """The receding-horizon loop end to end against the float64 oracle: every tick the oracle draws the same noise (numpy Philox),
+    rolls all samples, evaluates the quadratic cost, takes the first minimum, steps the plant under us*[0] and shifts the guess.
+    The device loop must pick the same winners (wherever the runner-up is resolvably worse) and visit the same states."""
+    mj, m, o = model_with(load_model, name)
+    nx, nu = mj.nq + mj.nv, mj.nu
+    x0 = np.concatenate([mj.key_qpos("home"), np.zeros(mj.nv)]) if name == "barkour" else 0.1 * np.ones(nx)
+    ug = np.tile(mj.key_ctrl("home"), (8, 1)) if name == "barkour" else np.zeros((8, nu))
+    xg = x0.copy()
+    xg[0] += 0.3
+    Q, Qf, R = np.eye(nx), 10 * np.eye(nx), 0.01 * np.eye(nu)
+    S, N, T, stdev = 48, 8, 6, 0.1
+    ps = VanillaPredictiveSampler(model=m, cost_function=StaticGoalQuadraticCost(Q, Qf, R, xg), nsamples=S, stdev=stdev)
+    xs_d, us_d, info = ps.mpc(VanillaPredictiveSamplerParams(key=11, x0=t32(x0), us_guess=t32(ug)), T)
+    xs_d, us_d, idx_d = xs_d.cpu().numpy(), us_d.cpu().numpy(), info["best_idx"].cpu().numpy()
+    lo, hi = mj.actuator_ctrlrange[:, 0], mj.actuator_ctrlrange[:, 1]
+    x, g = x0.astype(np.float32).astype(np.float64), ug.astype(np.float32).astype(np.float64)
+    agreed = 0
+    for t in range(T):
+        z = np.zeros((S, N, nu), np.float32)
+        z[1:] = _philox.normals(_seed_of(11 + t), np.arange(1, S)[:, None], 0, np.arange(N * nu)[None, :]).reshape(S - 1, N, nu)
+        us = np.clip((g.astype(np.float32) + z * np.float32(stdev)).astype(np.float64), lo, hi)
+        xs = o.rollout(x, us)
+        costs = quad_cost(xs, us, Q, Qf, R, xg)
+        order = np.argsort(costs, kind="stable")
+        best = int(order[0])
+        gap = (costs[order[1]] - costs[best]) / max(1.0, abs(costs[best]))
+        if int(idx_d[t]) != best:
+            assert gap < 1e-4, (t, best, int(idx_d[t]), gap)  # only an unresolvable runner-up may win instead
+            break
+        agreed += 1
+        assert np.abs(us_d[t] - us[best, 0]).max() < 1e-5
+        assert np.abs(xs_d[t + 1] - xs[best, 1]).max() < 2e-3 * max(1.0, np.abs(xs[best, 1]).max()), t
+        # continue from the DEVICE's state so that rounding does not accumulate into a different problem
+        x, g = xs_d[t + 1].astype(np.float64), np.concatenate([us[best, 1:], us[best, -1:]])
+    assert agreed >= 4
 
 
 def test_limb_path_edge_cases(load_model):

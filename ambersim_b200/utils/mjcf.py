@@ -268,16 +268,27 @@ def convex_topology(verts: np.ndarray):
     except Exception:
         return [], np.zeros((0, 3)), np.zeros((0, 2), dtype=np.int32)
     scale = max(1e-12, float(np.abs(pts).max()))
-    groups = []  # [normal, offset, set of vertex ids, list of triangles]
+    # coplanar hull triangles -> one group per supporting plane. Candidates are bucketed on the rounded plane equation and then
+    # compared exactly against the bucket's groups, so the merge stays a tolerance test but costs O(triangles)
+    groups, buckets = [], {}  # group: [normal, offset, set of vertex ids, list of triangles]
     for tri, eq in zip(hull.simplices, hull.equations):
         n, d = eq[:3], eq[3]
-        for grp in groups:
-            if np.dot(grp[0], n) > 1.0 - 1e-9 and abs(grp[1] - d) < 1e-9 * scale + 1e-12:
-                grp[2].update(int(i) for i in tri)
-                grp[3].append(tri)
+        key0 = np.round(np.concatenate([n, [d / scale]]) * 1e6).astype(np.int64)
+        hit = None
+        for dk in ((0, 0, 0, 0),) + tuple(tuple(int(i == j) * sg for j in range(4)) for i in range(4) for sg in (-1, 1)):
+            for gi in buckets.get(tuple(key0 + np.array(dk)), ()):
+                grp = groups[gi]
+                if np.dot(grp[0], n) > 1.0 - 1e-9 and abs(grp[1] - d) < 1e-9 * scale + 1e-12:
+                    hit = grp
+                    break
+            if hit is not None:
                 break
+        if hit is not None:
+            hit[2].update(int(i) for i in tri)
+            hit[3].append(tri)
         else:
             groups.append([n.copy(), float(d), set(int(i) for i in tri), [tri]])
+            buckets.setdefault(tuple(key0), []).append(len(groups) - 1)
     faces, normals = [], []
 
     def ordered(ids, n):

@@ -210,3 +210,38 @@ def test_mujoco_model_dump_if_present():
         used += 1
     if not used:
         pytest.skip("no MuJoCo model dump (mujoco is not installable in this image)")
+
+
+REF_BH280 = "/root/reference/ambersim/models/barrett_hand/bh280.xml"
+
+
+@pytest.mark.skipif(not __import__("os").path.exists(REF_BH280), reason="the reference tree is only present in the build container")
+def test_reference_bh280_file_with_its_collision_meshes():
+    """The reference's own model file (89 collision hulls from OBJ files, `bh280.xml:57-187`) goes through the loader: the articulated
+    model equals the shipped geometry-free fixture, the hulls are what SURVEY.md lists, and the trace-time pair enumeration shows why
+    the reference's sampler test switches contacts off (`tests/trajopt/test_predictive_sampler.py:29`)."""
+    from ambersim_b200.utils import mjcf
+    from oracle.oracle import Oracle
+
+    ref = load_mj_model_from_file(REF_BH280)
+    own = load_mj_model_from_file("models/barrett_hand/bh280.xml")
+    assert (ref.nq, ref.nv, ref.nu, ref.nbody, ref.neq) == (own.nq, own.nv, own.nu, own.nbody, own.neq) == (8, 8, 4, 10, 4)
+    for k in ("body_mass", "body_inertia", "body_ipos", "body_pos", "jnt_axis", "jnt_range", "dof_invweight0", "body_invweight0", "eq_data",
+              "actuator_ctrlrange", "dof_armature", "dof_damping"):
+        assert np.allclose(getattr(ref, k), getattr(own, k), rtol=1e-9, atol=1e-12), k
+    assert np.isclose(ref.stat.meaninertia, own.stat.meaninertia, rtol=1e-12)
+    col = [g for g in range(ref.ngeom) if ref.geom_type[g] == mjcf.GEOM_MESH and "collision" in ref.names["geom"][g]]
+    assert len(col) == 89 and ref.ngeom == 98
+    nv = ref.geom_vertnum[col]
+    assert nv.min() >= 4 and nv.max() == 1006  # hull vertices of the _col_ meshes
+    for g in col:  # every hull is a closed polyhedron: Euler's formula
+        assert ref.geom_vertnum[g] - ref.geom_edgenum[g] + ref.geom_facenum[g] == 2
+    # what MJX would enumerate at trace time with the default contype / conaffinity: thousands of hull - hull pairs
+    assert ref.npair + ref.n_unsupported_pairs > 3000 and ref.n_unsupported_pairs > 0 and "hull vertices" in ref.unsupported_reason
+    # with the reference test's options (contacts off) the constraint set is the fixture's: 4 equalities + 8 limits
+    opt = ref.opt.replace(disableflags=16, iterations=1, ls_iterations=4, timestep=0.002)
+    o = Oracle(ref, opt)
+    assert (o.ncon, o.ne, o.nl, o.nefc) == (0, 4, 8, 12)
+    f_ref = o.forward(0.1 * np.ones(8), np.zeros(8))
+    f_own = Oracle(own, own.opt.replace(disableflags=16, iterations=1, ls_iterations=4, timestep=0.002)).forward(0.1 * np.ones(8), np.zeros(8))
+    assert np.allclose(f_ref["qacc"], f_own["qacc"], rtol=1e-9, atol=1e-9)

@@ -26,6 +26,7 @@ MODELS = {
     "tripod3": (str(ROOT / "tests/models/tripod3.xml"), "home"),
     "fixedbase": (str(ROOT / "tests/models/fixedbase.xml"), None),
     "boxbot": (str(ROOT / "tests/models/boxbot.xml"), "home"),  # plane - convex collision: a box and a convex mesh foot (4 contacts each) + a sphere  # hand kernels: static base, three chains, four joint equalities  # three leaf paths: the 4-lane group carries a dummy lane
+    "bh280_hulls": (str(ROOT / "tests/models/bh280_hulls.xml"), None),  # the Barrett hand with the small hulls of its real collision geometry
     "blocks": (str(ROOT / "tests/models/blocks.xml"), "home"),  # sphere / capsule / convex - convex collision: box, capsule, sphere and mesh geoms over a static box and a static wedge
 }
 

@@ -269,27 +269,14 @@ def test_oversized_or_flat_hulls_are_refused_like_mjx(tmp_path):
     assert mjx.device_put(m).n_unsupported_pairs == 1  # the device handle refuses it (NotImplementedError) unless contacts are disabled
 
 
-@pytest.mark.gpu
-def test_engine_matches_oracle_on_sphere_capsule_and_convex_pairs(load_model):
+def _compare_contacts_with_the_oracles(mj, m, o, qs, vs, cs):
+    """mjx.forward on a batch of states: every pair in contact must equal the float64 oracle (5e-6) or, where _manifold_points breaks a
+    structural tie by rounding, the float32 oracle (MJX's own precision, 2e-5). Returns (pairs in contact per kind, ties, neither)."""
     import torch
 
     from ambersim_b200 import mjx
 
-    mj = load_model("blocks")
-    m = mjx.device_put(mj)
-    assert "generic kernels" in m.describe()
-    o = Oracle(mj)
-    rng = np.random.default_rng(5)
-    E = 96
-    qs = np.tile(mj.key_qpos("home"), (E, 1))
-    qs[:, 0] = rng.uniform(-0.2, 0.45, E)
-    qs[:, 1] = rng.uniform(-0.2, 0.2, E)
-    qs[:, 2] = rng.uniform(0.3, 0.42, E)
-    quat = np.array([1, 0, 0, 0]) + 0.2 * rng.normal(size=(E, 4))
-    qs[:, 3:7] = quat / np.linalg.norm(quat, axis=1, keepdims=True)
-    qs[:, 7:] += rng.uniform(-0.6, 0.6, (E, 3))
-    vs = 0.3 * rng.normal(size=(E, mj.nv))
-    cs = mj.key_ctrl("home") + 0.2 * rng.normal(size=(E, mj.nu))
+    E = len(qs)
     t = lambda a: torch.tensor(a, dtype=torch.float32, device="cuda")
     names = ("contact_dist", "contact_pos", "contact_frame", "efc_force", "qfrc_constraint", "qacc_smooth")
     d = mjx.Data(qpos=t(qs), qvel=t(vs), ctrl=t(cs), qacc=torch.zeros((E, mj.nv), device="cuda"), qacc_warmstart=torch.zeros((E, mj.nv), device="cuda"),
@@ -301,12 +288,12 @@ def test_engine_matches_oracle_on_sphere_capsule_and_convex_pairs(load_model):
         spans.append((c0, c0 + mjcf.PAIR_NCON[int(k)], int(k)))
         c0 += mjcf.PAIR_NCON[int(k)]
     seen = {mjcf.PAIR_SPHERE_CONVEX: 0, mjcf.PAIR_CAPSULE_CONVEX: 0, mjcf.PAIR_CONVEX_CONVEX: 0}
-    flips, checked = [], 0
+    flips, checked, ties = [], 0, 0
+
     def close(r, a, b, gd, gp, gf, tol):
         return (np.abs(r["contact_dist"][a:b] - gd[a:b]).max() < tol and np.abs(r["contact_pos"][a:b] - gp[a:b]).max() < tol
                 and np.abs(r["contact_frame"][a:b] - gf[a:b]).max() < 10 * tol)
 
-    ties = 0
     for e in range(E):
         ref = o.forward(f.qpos[e].cpu().numpy(), vs[e], cs[e], np.zeros(mj.nv))
         gd, gp, gf = f.contact_dist[e].cpu().numpy(), f.contact_pos[e].cpu().numpy(), f.contact_frame[e].cpu().numpy()
@@ -336,13 +323,39 @@ def test_engine_matches_oracle_on_sphere_capsule_and_convex_pairs(load_model):
                 r, g = ref[n].ravel(), getattr(f, n)[e].cpu().numpy().ravel()
                 assert np.abs(r - g).max() <= 5e-4 * max(1e-6, np.abs(r).max()) + 1e-5, (n, e)
             assert np.abs(ref["qacc"] - f.qacc[e].cpu().numpy()).max() <= 1e-3 * max(1.0, np.abs(ref["qacc"]).max())
+    print(f"convex pairs in contact: {checked} checked, {ties} equal to the float32 oracle only (rounding-decided ties), {len(flips)} equal to neither", flips)
+    return seen, checked, ties, flips
+
+
+@pytest.mark.gpu
+def test_engine_matches_oracle_on_sphere_capsule_and_convex_pairs(load_model):
+    import torch
+
+    from ambersim_b200 import mjx
+
+    mj = load_model("blocks")
+    m = mjx.device_put(mj)
+    assert "generic kernels" in m.describe()
+    o = Oracle(mj)
+    rng = np.random.default_rng(5)
+    E = 96
+    qs = np.tile(mj.key_qpos("home"), (E, 1))
+    qs[:, 0] = rng.uniform(-0.2, 0.45, E)
+    qs[:, 1] = rng.uniform(-0.2, 0.2, E)
+    qs[:, 2] = rng.uniform(0.3, 0.42, E)
+    quat = np.array([1, 0, 0, 0]) + 0.2 * rng.normal(size=(E, 4))
+    qs[:, 3:7] = quat / np.linalg.norm(quat, axis=1, keepdims=True)
+    qs[:, 7:] += rng.uniform(-0.6, 0.6, (E, 3))
+    vs = 0.3 * rng.normal(size=(E, mj.nv))
+    cs = mj.key_ctrl("home") + 0.2 * rng.normal(size=(E, mj.nu))
+    seen, checked, ties, flips = _compare_contacts_with_the_oracles(mj, m, o, qs, vs, cs)
     assert all(v >= 5 for v in seen.values()), seen  # every new pair function is exercised in contact
     # what equals neither oracle are ties again (the device contracts multiply-adds, the float32 oracle on the CPU does not): a few per cent
     assert len(flips) <= 0.05 * checked, (len(flips), checked, flips)
-    print(f"convex pairs in contact: {checked} checked, {ties} equal to the float32 oracle only (rounding-decided ties), {len(flips)} equal to neither", flips)
     # teacher-forced steps: each device step from the oracle's own state, while the robot settles on the pedestal
     from ambersim_b200.trajopt.shooting import shoot
 
+    t = lambda a: torch.tensor(a, dtype=torch.float32, device="cuda")
     x = np.concatenate([mj.key_qpos("home"), np.zeros(mj.nv)])
     x[2] = 0.36
     for k in range(60):
@@ -350,6 +363,43 @@ def test_engine_matches_oracle_on_sphere_capsule_and_convex_pairs(load_model):
         nxt = o.rollout(x, u[None])[1]
         got = shoot(m, t(x), t(u[None])).cpu().numpy()[1]
         assert np.abs(got - nxt).max() < 1e-3 * max(1.0, np.abs(nxt).max()), k
+        x = nxt
+
+
+@pytest.mark.gpu
+def test_bh280_with_its_real_small_hulls_and_contacts_on(load_model):
+    """The reference's Barrett hand with contacts ON, on the tractable part of its real collision geometry (`tests/models/bh280_hulls.xml`:
+    the 7 collision hulls of at most 48 vertices, 19 hull - hull pairs, 76 contact slots, from the reference's OBJ files): finger tips
+    closing on each other. contact_dist / pos / frame and the resulting accelerations against the oracle, then steps."""
+    import torch
+
+    from ambersim_b200 import mjx
+    from ambersim_b200.trajopt.shooting import shoot
+
+    mj = load_model("bh280_hulls")
+    assert mj.npair == 19 and mj.n_unsupported_pairs == 0 and set(mj.pair_kind.tolist()) == {mjcf.PAIR_CONVEX_CONVEX}
+    m = mjx.device_put(mj)
+    m = m.replace(opt=m.opt.replace(timestep=0.002, iterations=2, ls_iterations=6))
+    o = Oracle(mj, m.opt)
+    assert (o.ncon, o.ne, o.nl, o.nefc) == (76, 4, 8, 316) and "generic kernels" in m.describe()
+    rng = np.random.default_rng(7)
+    E = 48
+    qs = np.zeros((E, 8))
+    qs[:, 0] = rng.uniform(2.2, 2.44, E); qs[:, 1] = rng.uniform(0.6, 0.84, E)      # finger 3 closed
+    qs[:, 2] = rng.uniform(1.1, 1.9, E); qs[:, 3] = rng.uniform(2.25, 2.43, E); qs[:, 4] = rng.uniform(0.6, 0.84, E)  # finger 1 swung in and closed
+    qs[:, 5] = qs[:, 2] + rng.uniform(-0.05, 0.05, E); qs[:, 6] = rng.uniform(1.0, 2.4, E); qs[:, 7] = rng.uniform(0.2, 0.8, E)
+    vs = 0.5 * rng.normal(size=(E, 8))
+    cs = rng.uniform(-1, 1, (E, mj.nu))
+    seen, checked, ties, flips = _compare_contacts_with_the_oracles(mj, m, o, qs, vs, cs)
+    assert seen[mjcf.PAIR_CONVEX_CONVEX] >= 8 and len(flips) <= max(1, 0.1 * checked), (seen, checked, flips)
+    # teacher-forced steps from a touching pose
+    t = lambda a: torch.tensor(a, dtype=torch.float32, device="cuda")
+    x = np.concatenate([[2.34, 0.7, 1.5, 2.35, 0.7, 1.5, 1.4, 0.5], np.zeros(8)])
+    for k in range(25):
+        u = rng.uniform(-1, 1, mj.nu)
+        nxt = o.rollout(x, u[None])[1]
+        got = shoot(m, t(x), t(u[None])).cpu().numpy()[1]
+        assert np.abs(got - nxt).max() < 2e-3 * max(1.0, np.abs(nxt).max()), k
         x = nxt
 
 

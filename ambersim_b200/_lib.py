@@ -73,6 +73,7 @@ def lib():
     L.abr_forward_dev.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, vp]
     L.abr_env_step_dev.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp]
     L.abr_env_set_randomization.argtypes = [vp, vp, C.c_int]
+    L.abr_env_set_randomization_ex.argtypes = [vp, vp, C.c_int, C.c_int]
     L.abr_forward_fields_dev.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, C.POINTER(S["AbrDataFields"]), vp]
     L.abr_env_step_fields_dev.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.POINTER(S["AbrDataFields"]), vp]
     L.abr_env_task_step_dev.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, C.c_float, C.c_int, vp, vp, vp, vp, vp, vp]

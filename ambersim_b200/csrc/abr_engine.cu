@@ -103,7 +103,7 @@ struct AbrModel {
   int max_smem = 0;
   cudaStream_t stream = nullptr;  // for the *_host entry points
   cudaStream_t copy_stream = nullptr;  // host->device slices of a pipelined abr_rollout_host
-  const float* dr = nullptr; int dr_E = 0;  // abr_env_set_randomization
+  const float* dr = nullptr; int dr_E = 0, dr_n = 2;  // abr_env_set_randomization(_ex)
   std::vector<cudaEvent_t> ev;
   Scratch s_costs, s_in, s_out, s_dbg, s_traj, s_carry;
   Scratch s_mpc;  // abr_mpc_dev's winner buffers: its own, so that a *_host call on the handle's stream never shares scratch with it
@@ -965,7 +965,7 @@ static int launch_env(const AbrModel* m, const Layout& L, const EnvArgs& a_in, c
   EnvArgs a = a_in;
   if (m->dr) {
     if (a.E != m->dr_E) return fail(ABR_EINVAL, "env call: batch size differs from the one given to abr_env_set_randomization");
-    a.dr = m->dr;
+    a.dr = m->dr; a.dr_n = m->dr_n;
   }
   if (use_hand(m, L, false) && !a.dbg && !a.fo_on && !a.t_steps && !a.dr) return launch_result(launch_hand_env_3(L, a, st));
   if (use_limb(m, L, false, a.dbg != nullptr || a.fo_on)) {
@@ -1522,11 +1522,12 @@ int abr_env_step_dev(AbrModel* m, float* qpos, float* qvel, float* qacc_warmstar
   return launch_env(m, m->lay, a, (cudaStream_t)stream);
 }
 
-int abr_env_set_randomization(AbrModel* m, const float* dr, int E) {
-  if (!m || E < 0 || (dr && E == 0)) return fail(ABR_EINVAL, "abr_env_set_randomization: bad argument");
-  m->dr = dr; m->dr_E = dr ? E : 0;
+int abr_env_set_randomization_ex(AbrModel* m, const float* dr, int E, int nparam) {
+  if (!m || E < 0 || (dr && E == 0) || (nparam != 2 && nparam != 4)) return fail(ABR_EINVAL, "abr_env_set_randomization: bad argument (nparam is 2 or 4)");
+  m->dr = dr; m->dr_E = dr ? E : 0; m->dr_n = nparam;
   return ABR_OK;
 }
+int abr_env_set_randomization(AbrModel* m, const float* dr, int E) { return abr_env_set_randomization_ex(m, dr, E, 2); }
 
 int abr_env_task_step_dev(AbrModel* m, float* qpos, float* qvel, float* qacc_warmstart, float* time, const float* ctrl, int E, int nsubsteps,
                           const float* first_qpos, const float* first_qvel, const float* first_qacc_warmstart, const AbrCost* reward,

@@ -193,7 +193,8 @@ struct EnvArgs {
   int* t_steps; float* t_obs; float* t_reward; unsigned char* t_done; unsigned char* t_trunc;
   const float* t_qd; const float* t_rd; const float* t_xg;
   float t_zmin; int t_max_steps;
-  const float* dr;  // nullable [E,2]: per-env contact friction scale, actuator strength scale (abr_env_set_randomization)
+  const float* dr;  // nullable [E,dr_n]: per-env scales of contact friction, actuator strength (, joint damping, joint armature)
+  int dr_n;
   AbrDataFields fo; int fo_on;  // derived mjx.Data fields written per world (abr_*_fields_dev; needs the un-aliased layout)
 };
 
@@ -208,7 +209,11 @@ __global__ void __launch_bounds__(ABR_TPB, ABR_MINB) k_env(const __grid_constant
   const int w = valid ? wraw : A.E - 1;
   Ctx c{L, smem, reinterpret_cast<const int*>(smem + L.n_mf), smem + L.n_mf + L.n_mi + grp * L.world_stride, (int)(threadIdx.x % G)};
   const int nq = L.nq, nv = L.nv, nu = L.nu;
-  if (A.dr) { c.frs = A.dr[2 * (size_t)w]; c.acs = A.dr[2 * (size_t)w + 1]; }
+  if (A.dr) {
+    const float* r = A.dr + (size_t)A.dr_n * w;
+    c.frs = r[0]; c.acs = r[1];
+    if (A.dr_n >= 4) { c.dps = r[2]; c.ars = r[3]; }
+  }
   init_world<G>(c);
   const bool reset = A.reset_mask && A.reset_mask[w];
   const bool was_done = A.t_steps && A.t_done[w];  // AutoResetWrapper zeroes the counter of an env that finished last step

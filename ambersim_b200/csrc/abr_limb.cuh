@@ -295,7 +295,7 @@ template <int LGC> struct LaneCfg {
   const float* T;  // table + lane-in-group
   ShareT<LGC> S;
   float dt, grav[3], mass, inv_mass, tol, ls_tol, meaninertia;
-  float frs, acs;  // per-world domain randomisation: contact friction scale, actuator strength scale (1 = the model's own)
+  float frs, acs, dps, ars;  // per-world domain randomisation: scales of contact friction, actuator strength, joint damping, joint armature (1 = the model's own)
   int iterations, ls_iterations, disableflags, nefc, nv;
 };
 
@@ -731,11 +731,11 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
         const float bias = cdof_dot(cdof, d, f);
         float t = 0.f;
         if (p == 0) {
-          if (passive_on) t = -LTF(mp.trunk() + d) * s.v[d];
+          if (passive_on) t = -C.dps * LTF(mp.trunk() + d) * s.v[d];
         } else {
           const int fl = jflags[p];
           const float q = s.qc[p - 1];
-          if (passive_on) t = -LTF(mp.jnt(p) + 8) * (q - LTF(mp.jnt(p) + 7)) - LTF(mp.jnt(p) + 9) * s.v[d];
+          if (passive_on) t = -LTF(mp.jnt(p) + 8) * (q - LTF(mp.jnt(p) + 7)) - C.dps * LTF(mp.jnt(p) + 9) * s.v[d];
           // actuator (transmission + fwd_actuation); prm: ctrlrange2 forcerange2 gainprm3 biasprm3 gear
           const float* prm = &LTF(mp.jnt(p) + 24);
           const int af = fl >> kJActShift;
@@ -783,7 +783,7 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
           for (int j = 0; j < N; j++) {
             if (j <= i) {
               float t = cdof_dot(cdof, j, buf);
-              if (i == j) t += (i < 6) ? LTF(mp.trunk() + 6 + i) : LTF(mp.jnt(PD(i)) + 10);
+              if (i == j) t += C.ars * ((i < 6) ? LTF(mp.trunk() + 6 + i) : LTF(mp.jnt(PD(i)) + 10));
               M[TR(i, j)] = t;
             }
           }
@@ -1089,7 +1089,7 @@ __device__ __forceinline__ void euler(Lane<NL, NC>& s, const LaneCfg<LGC>& C, fl
     float hD[N], rhs[N];
 #pragma unroll
     for (int i = 0; i < N; i++) {
-      const float damp = (i < 6) ? LTF(mp.trunk() + i) : LTF(mp.jnt(PD(i)) + 9);
+      const float damp = C.dps * ((i < 6) ? LTF(mp.trunk() + i) : LTF(mp.jnt(PD(i)) + 9));
       M[TR(i, i)] += damp * dt;
       rhs[i] = fs[i] + fc[i];
     }
@@ -1144,7 +1144,7 @@ template <int NL, int NC, int LGC, int SPEC = -1> __device__ __forceinline__ Lan
   C.T = T + g;
   C.S.own = LTI(mp.ish()); C.S.lvl = LTI(mp.ish() + 1); C.S.mx = L.l_mx; C.S.lg_ = L.lg2G;
   C.dt = L.timestep; C.grav[0] = L.gravity[0]; C.grav[1] = L.gravity[1]; C.grav[2] = L.gravity[2];
-  C.frs = 1.f; C.acs = 1.f;
+  C.frs = 1.f; C.acs = 1.f; C.dps = 1.f; C.ars = 1.f;
   C.mass = L.l_mass; C.inv_mass = 1.f / L.l_mass; C.tol = L.tolerance; C.ls_tol = L.ls_tolerance; C.meaninertia = L.meaninertia;
   C.iterations = Spec<SPEC>::gen ? L.iterations : 1; C.ls_iterations = L.ls_iterations; C.disableflags = Spec<SPEC>::flags(L.disableflags); C.nefc = L.nefc; C.nv = L.nv;
   return C;
@@ -1371,7 +1371,11 @@ __global__ void __launch_bounds__(kMaxTPB, ABR_LIMB_MINB) k_limb_env(const __gri
   const bool valid = wraw < A.E;
   const int w = valid ? wraw : A.E - 1;
   LaneCfg<LGC> C = make_cfg<NL, NC, LGC, SPEC>(L, smem, g);
-  if (A.dr) { C.frs = A.dr[2 * (size_t)w]; C.acs = A.dr[2 * (size_t)w + 1]; }
+  if (A.dr) {
+    const float* r = A.dr + (size_t)A.dr_n * w;
+    C.frs = r[0]; C.acs = r[1];
+    if (A.dr_n >= 4) { C.dps = r[2]; C.ars = r[3]; }
+  }
   const bool reset = A.reset_mask && A.reset_mask[w];
   const bool was_done = A.t_steps && A.t_done[w];  // AutoResetWrapper zeroes the counter of an env that finished last step
   const float* sq = (reset ? A.first_qpos : A.qpos) + (size_t)w * nq;

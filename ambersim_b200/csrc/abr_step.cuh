@@ -31,7 +31,9 @@ struct Ctx {
   float* W;         // this world's shared-memory region
   int lane;         // lane within the group
   float frs = 1.f;  // per-world domain randomisation: contact friction scale ...
-  float acs = 1.f;  // ... and actuator strength scale (abr_env_set_randomization)
+  float acs = 1.f;  // ... actuator strength scale,
+  float dps = 1.f;  // ... joint damping scale
+  float ars = 1.f;  // ... and joint armature scale (abr_env_set_randomization_ex)
 };
 
 // ------------------------------------------------------------------------------ small math
@@ -825,7 +827,7 @@ template <int G> __device__ void stage_crb(const Ctx& c) {
     const int i = ij >> 16, j = ij & 0xffff;
     const float* a = cdof + 6 * j; const float* b = buf + 6 * i;
     float s = a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5];
-    if (i == j) s += MF(dof_armature)[i];
+    if (i == j) s += c.ars * MF(dof_armature)[i];
     M[L.sparse ? k : tri(i) + j] = s;
   }
   __syncwarp();
@@ -1267,7 +1269,7 @@ template <int G> __device__ void stage_velocity(const Ctx& c) {
         const int a = MI(jnt_qposadr)[j];
         s = -MF(jnt_stiffness)[j] * (qpos[a] - MF(qpos_spring)[a]);
       }
-      s -= MF(dof_damping)[d] * qvel[d];
+      s -= c.dps * MF(dof_damping)[d] * qvel[d];
     }
     s -= bias;
     const int aa = MI(dof_actadr)[d], an = MI(dof_actnum)[d];
@@ -1618,7 +1620,7 @@ template <int G> __device__ bool post_forward(const Ctx& c, int stage) {
 #pragma unroll 1
       for (int k = c.lane; k < nent; k += G) {
         const int ij = tab[k];
-        H[k] = M[k] + (((ij >> 16) == (ij & 0xffff)) ? MF(dof_damping)[ij >> 16] * dt : 0.f);
+        H[k] = M[k] + (((ij >> 16) == (ij & 0xffff)) ? c.dps * MF(dof_damping)[ij >> 16] * dt : 0.f);
       }
       float* rhs = WF(grad);
       for (int d = c.lane; d < nv; d += G) rhs[d] = WF(fs)[d] + WF(fc)[d];

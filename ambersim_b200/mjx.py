@@ -200,6 +200,31 @@ class Data:
         return dataclasses.replace(self, **kw)
 
 
+def _register_dataclass_pytree(cls) -> None:
+    """Makes a dataclass a pytree node for `torch.utils._pytree` (tree_map / tree_flatten), the role flax.struct plays for
+    mjx.Data and brax's State in the reference (rl/base.py:14-32): wrappers written as `tree_map(where_done, first, state)` work."""
+    from torch.utils import _pytree
+
+    names = [f.name for f in dataclasses.fields(cls)]
+
+    def flatten(x):  # fields that are None (derived fields not requested) are structure, not leaves, as in JAX
+        present = tuple(n for n in names if getattr(x, n) is not None)
+        return [getattr(x, n) for n in present], present
+
+    def unflatten(values, present):
+        return cls(**dict(zip(present, values)))
+
+    try:
+        _pytree.register_pytree_node(cls, flatten, unflatten, serialized_type_name=f"{cls.__module__}.{cls.__name__}")
+    except (ValueError, TypeError):  # registered already (module reloaded) or an older torch without the keyword
+        try:
+            _pytree.register_pytree_node(cls, flatten, unflatten)
+        except ValueError:
+            pass
+
+
+_register_dataclass_pytree(Data)
+
 DERIVED_FIELDS = ("xpos", "xquat", "xipos", "xanchor", "xaxis", "cinert", "cdof", "cvel", "cdof_dot", "qfrc_smooth", "qacc_smooth",
                   "qfrc_constraint", "efc_force", "efc_D", "efc_aref", "contact_dist", "contact_pos", "contact_frame")
 
@@ -342,17 +367,19 @@ def step(m: Model, d: Data, nsubsteps: int = 1, fields=()) -> Data:
 
 def set_randomization(m: Model, dr: Optional[torch.Tensor]) -> None:
     """Per-env domain randomisation for the env entry points (forward / step with a leading batch of E envs):
-    dr (E, 2) = {contact friction scale, actuator strength scale} on the device, or None to switch it off.
-    The tensor is referenced, not copied: it is kept alive on the model until replaced."""
+    dr (E, 2) = {contact friction scale, actuator strength scale} or (E, 4) = those + {joint damping scale, joint armature scale}
+    on the device, or None to switch it off. Like `model.replace(dof_damping=..., dof_armature=...)` in MJX the scales leave the
+    compiled constants (invweight0, meaninertia) of the base model untouched. The tensor is referenced, not copied: it is kept
+    alive on the model until replaced."""
     if dr is None:
         for h in m._handles.values():
             _lib.check(_lib.lib().abr_env_set_randomization(h.ptr, None, 0))
         m._dr = None
         return
     dr = dr.to(torch.float32).contiguous()
-    assert dr.dim() == 2 and dr.shape[1] == 2 and dr.is_cuda
+    assert dr.dim() == 2 and dr.shape[1] in (2, 4) and dr.is_cuda
     h = m.handle(dr.device.index or 0)
-    _lib.check(_lib.lib().abr_env_set_randomization(h.ptr, _ptr(dr), dr.shape[0]))
+    _lib.check(_lib.lib().abr_env_set_randomization_ex(h.ptr, _ptr(dr), dr.shape[0], dr.shape[1]))
     m._dr = dr
 
 

@@ -34,6 +34,9 @@ class State:
         return dataclasses.replace(self, **kw)
 
 
+mjx._register_dataclass_pytree(State)
+
+
 class MjxEnv(ABC):
     """API for an engine-backed system for training and inference.
 

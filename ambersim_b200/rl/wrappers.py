@@ -49,6 +49,21 @@ class Wrapper:
         return self.env.step(state, action)
 
 
+class VmapWrapper(Wrapper):
+    """brax.envs.wrappers.training.VmapWrapper for API compatibility: the engine's envs are batched natively (a leading dimension on
+    every `State` / `mjx.Data` field replaces `jax.vmap`), so this only checks / records the batch size."""
+
+    def __init__(self, env, batch_size: Optional[int] = None):
+        super().__init__(env)
+        self.batch_size = batch_size
+
+    def reset(self, rng) -> State:
+        state = self.env.reset(rng)
+        if self.batch_size is not None and tuple(state.done.shape[:1]) != (self.batch_size,):
+            raise ValueError(f"VmapWrapper(batch_size={self.batch_size}) around an env that resets {tuple(state.done.shape)} worlds")
+        return state
+
+
 class EpisodeWrapper(Wrapper):
     """Episode length and action repeat: info['steps'] counts env steps, `done` is raised at
     `episode_length` and info['truncation'] marks episodes ended by the length alone."""
@@ -147,8 +162,9 @@ class FusedQuadraticTaskEnv:
     training hot loop, not a functional API. `step` never synchronises."""
 
     def __init__(self, env: QuadraticTaskEnv, episode_length: int, randomization: Optional[torch.Tensor] = None):
-        """randomization: optional (num_envs, 2) tensor of per-env {contact friction scale, actuator strength scale}
-        (abr_env_set_randomization): every env then steps its own variant of the model."""
+        """randomization: optional (num_envs, 2) tensor of per-env {contact friction scale, actuator strength scale} or (num_envs, 4)
+        with {joint damping scale, joint armature scale} as well (abr_env_set_randomization_ex): every env then steps its own
+        variant of the model."""
         self.randomization = randomization
         if not torch.equal(env.reward_fn.Q, torch.diag(torch.diagonal(env.reward_fn.Q))) or \
                 not torch.equal(env.reward_fn.R, torch.diag(torch.diagonal(env.reward_fn.R))):
@@ -163,7 +179,7 @@ class FusedQuadraticTaskEnv:
         E = self.env.num_envs
         if self.randomization is not None:  # installed before pipeline_init so the cached first state's warm start sees it too
             dev0 = mjx._dev(self.env._device)
-            self._dr = self.randomization.to(device=dev0, dtype=torch.float32).reshape(E, 2).contiguous()
+            self._dr = self.randomization.to(device=dev0, dtype=torch.float32).reshape(E, -1).contiguous()
             mjx.set_randomization(self.env.sys, self._dr)
         s = self.env.reset(rng)
         d = s.pipeline_state

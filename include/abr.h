@@ -336,6 +336,11 @@ int abr_env_step_fields_dev(AbrModel* m, float* qpos, float* qvel, float* qacc_w
  * not copied (caller-owned, must outlive the env calls); abr_forward_dev / abr_env_step_dev /
  * abr_env_task_step_dev then require the same E. */
 int abr_env_set_randomization(AbrModel* m, const float* dr, int E);
+/* The same with nparam = 2 or 4 scales per env: dr [E,nparam] = {contact friction, actuator strength, joint damping, joint armature}.
+ * The damping scale multiplies dof_damping (passive force and the implicit-damping Euler term), the armature scale dof_armature
+ * (the diagonal of the joint-space inertia); like `model.replace(dof_damping=..., dof_armature=...)` in MJX they leave the
+ * mj_setConst constants (invweight0, meaninertia) of the base model untouched. */
+int abr_env_set_randomization_ex(AbrModel* m, const float* dr, int E, int nparam);
 
 /* ---- one whole training-env step in ONE launch: MjxEnv.step of a quadratic
  * tracking task wrapped in brax's EpisodeWrapper + AutoResetWrapper, E envs in place, DEVICE pointers.

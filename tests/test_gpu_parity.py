@@ -722,6 +722,48 @@ def test_env_domain_randomization(load_model, name, lanes):
     assert np.abs(out.qvel[1].cpu().numpy() - out.qvel[2].cpu().numpy()).max() > 1e-3
 
 
+@pytest.mark.parametrize("name,lanes,disable", [("barkour", 0, 0), ("barkour", 0, 16384), ("barkour", 8, 0), ("biped", 0, 0), ("tripod", 0, 0)])
+def test_env_domain_randomization_four_parameters(load_model, name, lanes, disable):
+    """abr_env_set_randomization_ex with four scales per env: contact friction, actuator strength, joint damping (the passive force AND
+    the implicit-damping Euler term: both settings of eulerdamp) and joint armature. Each env is compared with an oracle whose host
+    model carries the scaled dof_damping / dof_armature with the base model's compiled constants, which is what
+    `model.replace(dof_damping=..., dof_armature=...)` gives an MJX user."""
+    import copy
+
+    mj, m, _ = model_with(load_model, name, disableflags=disable)
+    if lanes:
+        m.set_lanes(lanes)
+    rng = np.random.default_rng(19)
+    dr = np.array([[1.0, 1.0, 1.0, 1.0], [1.0, 1.0, 3.0, 1.0], [1.0, 1.0, 1.0, 4.0], [0.6, 1.2, 0.3, 2.5], [1.4, 0.7, 2.0, 0.5]])
+    E = len(dr)
+    q, v, c = sample_state(mj, name, rng)
+    v[:2] += 0.5
+    w = rng.normal(size=mj.nv)
+    tile = lambda a: t32(np.tile(a, (E, 1)))
+    d = mjx.Data(qpos=tile(q), qvel=tile(v), ctrl=tile(c), qacc=torch.zeros(E, mj.nv, device=DEV), qacc_warmstart=tile(w),
+                 time=torch.zeros(E, device=DEV))
+    plain = mjx.step(m, d)
+    mjx.set_randomization(m, t32(dr))
+    out = mjx.step(m, d)
+    mjx.set_randomization(m, None)
+    assert torch.equal(out.qpos[0], plain.qpos[0]) and torch.equal(out.qvel[0], plain.qvel[0])  # unit scales: the same numbers
+    assert not torch.equal(out.qvel[1], plain.qvel[1]) and not torch.equal(out.qvel[2], plain.qvel[2])
+    for e in range(E):
+        mj_e = copy.deepcopy(mj)
+        mj_e.pair_friction = np.array(mj.pair_friction, dtype=np.float64).copy()
+        mj_e.pair_friction[:, :2] *= dr[e, 0]
+        mj_e.actuator_gainprm = np.array(mj.actuator_gainprm, dtype=np.float64) * dr[e, 1]
+        mj_e.actuator_biasprm = np.array(mj.actuator_biasprm, dtype=np.float64) * dr[e, 1]
+        mj_e.dof_damping = np.array(mj.dof_damping, dtype=np.float64) * dr[e, 2]
+        mj_e.dof_armature = np.array(mj.dof_armature, dtype=np.float64) * dr[e, 3]
+        o = Oracle(mj_e, m.opt)
+        qr, vr, wr, _ = o.step(q, v, c, w)
+        q32, v32, _, _ = o.step(q, v, c, w, prec=1)
+        assert np.all(np.abs(out.qpos[e].cpu().numpy() - qr) <= 1e-5 + 1e-4 * np.abs(qr) + 3 * np.abs(q32 - qr)), f"env {e}"
+        assert np.abs(out.qvel[e].cpu().numpy() - vr).max() <= 1e-4 * max(1.0, np.abs(vr).max()) + 3 * np.abs(v32 - vr).max(), f"env {e}"
+    assert np.abs(out.qvel[1].cpu().numpy() - out.qvel[2].cpu().numpy()).max() > 1e-3
+
+
 @pytest.mark.parametrize("name", ["bh280", "barkour"])
 def test_finite_difference_shooting(load_model, name):
     """Gradient-based shooting on the engine: the central-difference gradient (2 N nu + 1 rollouts in one launch) equals the

@@ -245,3 +245,24 @@ def test_reference_bh280_file_with_its_collision_meshes():
     f_ref = o.forward(0.1 * np.ones(8), np.zeros(8))
     f_own = Oracle(own, own.opt.replace(disableflags=16, iterations=1, ls_iterations=4, timestep=0.002)).forward(0.1 * np.ones(8), np.zeros(8))
     assert np.allclose(f_ref["qacc"], f_own["qacc"], rtol=1e-9, atol=1e-9)
+
+
+def test_state_and_data_are_pytrees():
+    """`State` / `mjx.Data` flatten like the flax dataclasses they mirror (rl/base.py:14-32): brax-style wrappers written with
+    tree_map (`where(done, first, state)` over the whole state) work on them."""
+    import torch
+    from torch.utils import _pytree
+
+    from ambersim_b200.rl.base import State
+
+    E = 3
+    d = mjx.Data(qpos=torch.ones(E, 2), qvel=torch.zeros(E, 2), ctrl=torch.zeros(E, 1), qacc=torch.zeros(E, 2), qacc_warmstart=torch.zeros(E, 2),
+                 time=torch.zeros(E))
+    s = State(d, obs=torch.arange(E * 4.0).reshape(E, 4), reward=torch.zeros(E), done=torch.tensor([0.0, 1.0, 0.0]), metrics={"r": torch.ones(E)}, info={})
+    first = _pytree.tree_map(lambda x: x * 0 + 7, s)
+    assert isinstance(first, State) and isinstance(first.pipeline_state, mjx.Data) and first.pipeline_state.xpos is None
+    done = s.done.bool()
+    blend = _pytree.tree_map(lambda a, b: torch.where(done.reshape(done.shape + (1,) * (b.dim() - 1)), a, b), first, s)
+    assert blend.pipeline_state.qpos.tolist() == [[1, 1], [7, 7], [1, 1]] and blend.obs[1].tolist() == [7, 7, 7, 7] and blend.metrics["r"].tolist() == [1, 7, 1]
+    leaves, spec = _pytree.tree_flatten(s)
+    assert all(isinstance(x, torch.Tensor) for x in leaves) and _pytree.tree_unflatten(leaves, spec).obs is s.obs

@@ -395,6 +395,95 @@ def test_full_size_properties_barkour(load_model):
     assert np.abs(xs_sub[2, :21].cpu().numpy() - ref).max() < 2e-3
 
 
+def test_full_size_properties_biped(load_model):
+    """BASELINE config C3 shape (16384 worlds x 1000 steps of the biped / exoskeleton-class stand-in): determinism, finiteness,
+    batch independence, unit quaternions, and the first steps of one world against the oracle."""
+    mj, m, o = model_with(load_model, "biped")
+    W, N = 16384, 1000
+    g = torch.Generator(device=DEV).manual_seed(3)
+    c0, q0 = t32(mj.key_ctrl("stand")), mj.key_qpos("stand")
+    lim = t32(mj.actuator_ctrlrange)
+    us = torch.clamp(c0 + 0.05 * torch.randn((W, N, mj.nu), generator=g, device=DEV), lim[:, 0], lim[:, 1])
+    x0 = t32(np.concatenate([q0, np.zeros(mj.nv)])).repeat(W, 1)
+    x0[:, 7:mj.nq] += (torch.rand((W, mj.nq - 7), generator=g, device=DEV) - 0.5) * 0.04
+    nx = mj.nq + mj.nv
+    cf = StaticGoalQuadraticCost(np.eye(nx), 10 * np.eye(nx), 0.01 * np.eye(mj.nu), np.concatenate([q0, np.zeros(mj.nv)]))
+    c1 = shoot_cost(m, x0, us, cf)
+    assert torch.equal(c1, shoot_cost(m, x0, us, cf))  # bit-deterministic
+    assert torch.isfinite(c1).all()
+    sub = torch.tensor([0, 5, 8191, 16383], device=DEV)
+    xs_sub = shoot(m, x0[sub], us[sub])
+    c_sub, _ = cf.cost(xs_sub, us[sub], None)
+    assert torch.allclose(c_sub, c1[sub], rtol=1e-4)  # a world's result does not depend on its batch
+    assert torch.allclose(xs_sub[:, :, 3:7].norm(dim=-1), torch.ones_like(xs_sub[:, :, 3]), atol=1e-5)
+    ref = o.rollout(x0[8191].cpu().numpy().astype(np.float64), us[8191, :15].cpu().numpy().astype(np.float64))
+    assert np.abs(xs_sub[2, :16].cpu().numpy() - ref).max() < 2e-3
+
+
+def test_full_size_properties_sampler_sweep(load_model):
+    """BASELINE config C4 at its largest size (1 048 576 samples x horizon 32, one problem): the winner is the first minimum of the
+    returned costs (numpy, NaN as minimum), its controls are the guess plus its own Philox noise, its trajectory is the rollout of
+    those controls, and four shards by global sample id reproduce the costs and the winner bit for bit."""
+    mj, m, o = model_with(load_model, "barkour")
+    nx, nu, S, N, seed = mj.nq + mj.nv, mj.nu, 1 << 20, 32, 0xC4C4
+    x0 = np.concatenate([mj.key_qpos("home"), np.zeros(mj.nv)])
+    xg = x0.copy()
+    xg[0] += 0.2
+    cf = StaticGoalQuadraticCost(np.eye(nx), 10 * np.eye(nx), 0.01 * np.eye(nu), xg)
+    ug = t32(np.tile(mj.key_ctrl("home"), (N, 1)))
+    p = VanillaPredictiveSamplerParams(key=seed, x0=t32(x0), us_guess=ug)
+    ps = VanillaPredictiveSampler(model=m, cost_function=cf, nsamples=S, stdev=0.1)
+    xs, us, info = ps.optimize(p, return_info=True)
+    costs = info["costs"].reshape(-1).cpu().numpy()
+    assert costs.shape == (S,) and np.isfinite(costs).all()
+    k = int(info["best_idx"])
+    assert k == int(np.argmin(costs)) and float(info["best_cost"]) == costs[k]  # first minimum, bit-exact on the device's own costs
+    lim = mj.actuator_ctrlrange.astype(np.float32)
+    z = _philox.normals(seed, k, 0, np.arange(N * nu)).reshape(N, nu) if k > 0 else np.zeros((N, nu), np.float32)
+    assert np.allclose(us.cpu().numpy(), np.clip(ug.cpu().numpy() + z * np.float32(0.1), lim[:, 0], lim[:, 1]), atol=2e-6)
+    assert torch.equal(xs, shoot(m, t32(x0), us))  # the returned trajectory is the rollout of the returned controls
+    assert costs[0] == float(shoot_cost(m, t32(x0), ug[None], cf)[0])  # sample 0 is the un-noised guess
+    parts = []
+    for q in range(4):
+        psk = VanillaPredictiveSampler(model=m, cost_function=cf, nsamples=S // 4, stdev=0.1)
+        parts.append(psk.optimize(p, sample_offset=q * (S // 4), nsamples_total=S, return_info=True)[2])
+    assert torch.equal(torch.cat([q["costs"].reshape(-1) for q in parts]), info["costs"].reshape(-1))
+    best = torch.stack([q["best_cost"].reshape(()) for q in parts])
+    assert int(parts[int(best.argmin())]["best_idx"]) == k
+
+
+def test_full_size_properties_env_step(load_model):
+    """BASELINE config C5 shape (8192 auto-resetting envs): 300 fused env steps under random actions. Episode counters, done /
+    truncation flags and the reset blend stay consistent for every env, rewards are finite and negative, and every env that
+    finished holds its first state again."""
+    from ambersim_b200.rl.wrappers import FusedQuadraticTaskEnv, QuadraticTaskEnv
+
+    mj = load_model("barkour")
+    nx, E, T, L = mj.nq + mj.nv, 8192, 300, 120
+    q0 = mj.key_qpos("home")
+    rew = StaticGoalQuadraticCost(np.eye(nx), np.eye(nx), 0.01 * np.eye(mj.nu), np.concatenate([q0, np.zeros(mj.nv)]))
+    env = FusedQuadraticTaskEnv(QuadraticTaskEnv(mj, rew, q0, E, z_min=0.12, jitter=0.05), episode_length=L)
+    st = env.reset(5)
+    first_q = st.pipeline_state.qpos.clone()
+    g = torch.Generator(device=DEV).manual_seed(9)
+    lim = t32(mj.actuator_ctrlrange)
+    steps_prev = st.info["steps"].clone()
+    n_done = n_trunc = 0
+    for t in range(T):
+        a = torch.clamp(t32(mj.key_ctrl("home")) + 0.6 * torch.randn((E, mj.nu), generator=g, device=DEV), lim[:, 0], lim[:, 1])
+        st = env.step(st, a)
+        done, trunc, steps = st.done.bool(), st.info["truncation"].bool(), st.info["steps"]
+        assert torch.isfinite(st.reward).all() and (st.reward <= 0).all()
+        assert torch.equal(steps, steps_prev + 1) and (steps <= L).all()  # (the counter of a finished env restarts on its next step)
+        assert torch.equal(done & (steps == L) | trunc, done & (steps == L)) and not (trunc & ~done).any()
+        fin = done.nonzero().flatten()
+        assert torch.equal(st.pipeline_state.qpos[fin], first_q[fin])  # where(done, first_state, state)
+        assert torch.isfinite(st.pipeline_state.qpos).all() and torch.isfinite(st.obs).all()
+        n_done += int(done.sum()); n_trunc += int(trunc.sum())
+        steps_prev = torch.where(done, torch.zeros_like(steps), steps)
+    assert n_done > E and n_trunc > 0 and n_done > n_trunc  # both kinds of episode ends happened
+
+
 def test_ffma_peak_is_plausible():
     import ctypes as C
 

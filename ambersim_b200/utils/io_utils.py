@@ -4,9 +4,9 @@
     mj_to_mjx_model_and_data(mj_model) -> (mjx.Model, mjx.Data)
     load_mjx_model_and_data_from_file(filepath, force_float) -> (mjx.Model, mjx.Data)
 
-`mujoco` is not installable here, so MJCF files are compiled by ambersim_b200.utils.mjcf; a real
-`mujoco.MjModel` handed in by a caller who has the package is flattened by ambersim_b200.utils.mjmodel. URDF munging (reference
-io_utils.py:18-136) is MuJoCo-compiler work and out of scope.
+`mujoco` is not installable here, so MJCF files are compiled by ambersim_b200.utils.mjcf and URDF files by the same compiler behind
+ambersim_b200.utils.urdf (MuJoCo's URDF import conventions + the reference's actuators-from-transmissions and equalities-from-mimics,
+io_utils.py:18-121); a real `mujoco.MjModel` handed in by a caller who has the package is flattened by ambersim_b200.utils.mjmodel.
 """
 from __future__ import annotations
 
@@ -27,7 +27,7 @@ def load_mj_model_from_file(
     iterations: Optional[int] = None,
     ls_iterations: Optional[int] = None,
 ) -> mjcf.MjModel:
-    """Loads a model from an MJCF path (absolute, cwd-relative or package-root-relative).
+    """Loads a model from an MJCF or URDF path (absolute, cwd-relative or package-root-relative).
 
     solver: 'newton' (default, as the reference does for mujoco >= 3.0.1) or 'cg'.
     iterations / ls_iterations: override the <option> values when given.
@@ -43,11 +43,9 @@ def load_mj_model_from_file(
         assert solver_id in (1, 2)
     path = _check_filepath(filepath)
     ext = str(path).rsplit(".", 1)[-1]
-    if ext == "urdf":
-        raise NotImplementedError("URDF needs MuJoCo's compiler; convert to MJCF first (out of the engine's scope)")
-    if ext != "xml":
+    if ext not in ("urdf", "xml"):
         raise NotImplementedError
-    m = mjcf.compile_mjcf(path, force_float=force_float)
+    m = mjcf.compile_urdf(path, force_float=force_float) if ext == "urdf" else mjcf.compile_mjcf(path, force_float=force_float)
     kw = dict(solver=solver_id)
     if iterations is not None:
         kw["iterations"] = iterations

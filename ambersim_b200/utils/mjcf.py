@@ -1048,6 +1048,19 @@ class _Compiler:
                 )
 
 
+def compile_urdf(path, force_float: bool = False) -> MjModel:
+    """Compile a URDF file the way the reference loads one (MuJoCo's URDF import + ambersim's actuators-from-transmissions and
+    equalities-from-mimics, io_utils.py:18-121, 196-204): ambersim_b200.utils.urdf builds the equivalent MJCF tree."""
+    from ambersim_b200.utils.urdf import urdf_to_mjcf
+
+    root, base = urdf_to_mjcf(path)
+    comp = _Compiler(root, force_float=force_float)
+    comp.base_dir = base
+    m = comp.compile()
+    m.source = str(path)
+    return m
+
+
 def compile_mjcf(path, force_float: bool = False) -> MjModel:
     """Compile an MJCF file into a flat `MjModel` (stand-in for MjModel.from_xml_path)."""
     path = Path(path)

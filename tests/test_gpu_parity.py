@@ -484,6 +484,27 @@ def test_full_size_properties_env_step(load_model):
     assert n_done > E and n_trunc > 0 and n_done > n_trunc  # both kinds of episode ends happened
 
 
+def test_urdf_loaded_model_steps_like_the_oracle():
+    """A URDF goes through the loader's URDF front end (transmissions -> motors, mimic -> joint equality, welded tool link, slide joint,
+    box / capsule / sphere collision geoms) and then steps on the engine like any MJCF model."""
+    from ambersim_b200.utils.io_utils import load_mj_model_from_file
+
+    mj = load_mj_model_from_file("tests/models/arm.urdf")
+    m = mjx.device_put(mj)
+    m = m.replace(opt=m.opt.replace(timestep=0.002, iterations=3, ls_iterations=8))
+    o = Oracle(mj, m.opt)
+    assert o.ne == 1 and o.nl == 2 and o.ncon >= 1
+    rng = np.random.default_rng(31)
+    for k in range(6):
+        q = np.array([rng.uniform(-1.4, 1.9), rng.uniform(0.0, 0.25), 0.0])
+        q[2] = 0.1 + 0.5 * q[0] + rng.uniform(-0.05, 0.05)
+        v, c, w = rng.normal(size=3), rng.uniform(-2, 2, 2), rng.normal(size=3)
+        qr, vr, wr, _ = o.step(q, v, c, w)
+        d = mjx.step(m, mjx.Data(qpos=t32(q), qvel=t32(v), ctrl=t32(c), qacc=t32(v), qacc_warmstart=t32(w), time=torch.zeros((), device=DEV)))
+        assert np.abs(d.qpos.cpu().numpy() - qr).max() < 2e-5 + 2e-4 * np.abs(qr).max(), k
+        assert np.abs(d.qvel.cpu().numpy() - vr).max() < 2e-3 * max(1.0, np.abs(vr).max()), k
+
+
 def test_ffma_peak_is_plausible():
     import ctypes as C
 

@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 from ambersim_b200 import ROOT, mjx
+from ambersim_b200.utils import mjcf
 from ambersim_b200.utils._internal_utils import _check_filepath
 from ambersim_b200.utils.io_utils import load_mj_model_from_file, mj_to_mjx_model_and_data
 
@@ -99,9 +100,13 @@ def test_model_mirror_and_unsupported(tmp_path):
     assert bad.n_unsupported_pairs == 3  # the cylinder against the plane, the box and the sphere
     with pytest.raises(NotImplementedError):
         bad.handle(0)
+    other = tmp_path / "x.sdf"  # neither .urdf nor .xml: refused like the reference (io_utils.py:203-204)
+    other.write_text("<sdf/>")
+    with pytest.raises(NotImplementedError):
+        load_mj_model_from_file(other)
     urdf = tmp_path / "x.urdf"
     urdf.write_text("<robot name='x'/>")
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):  # a URDF without links has no root link
         load_mj_model_from_file(urdf)
 
 
@@ -266,3 +271,77 @@ def test_state_and_data_are_pytrees():
     assert blend.pipeline_state.qpos.tolist() == [[1, 1], [7, 7], [1, 1]] and blend.obs[1].tolist() == [7, 7, 7, 7] and blend.metrics["r"].tolist() == [1, 7, 1]
     leaves, spec = _pytree.tree_flatten(s)
     assert all(isinstance(x, torch.Tensor) for x in leaves) and _pytree.tree_unflatten(leaves, spec).obs is s.obs
+
+
+def _rpy(r, p, y):
+    cr, sr, cp, sp, cy, sy = np.cos(r), np.sin(r), np.cos(p), np.sin(p), np.cos(y), np.sin(y)
+    return (np.array([[cy, -sy, 0], [sy, cy, 0], [0, 0, 1]]) @ np.array([[cp, 0, sp], [0, 1, 0], [-sp, 0, cp]])
+            @ np.array([[1, 0, 0], [0, cr, -sr], [0, sr, cr]]))
+
+
+def test_urdf_front_end_on_an_authored_arm():
+    """load_mj_model_from_file on a URDF (reference io_utils.py:196-204): MuJoCo's import conventions + ambersim's
+    actuators-from-transmissions (io_utils.py:18-69) and equalities-from-mimics (io_utils.py:72-121), checked field by field against
+    values computed here from the URDF's numbers."""
+    from oracle.independent import _qmat
+    from oracle.oracle import Oracle
+
+    m = load_mj_model_from_file("tests/models/arm.urdf")
+    assert m.names["body"] == ["world", "base", "upper", "slider", "tool", "finger"]  # welded links stay bodies (fusestatic is not applied)
+    assert m.body_parentid.tolist() == [0, 0, 1, 2, 3, 4] and (m.nq, m.nv, m.nu, m.neq) == (3, 3, 2, 1)
+    assert m.names["joint"] == ["shoulder", "extend", "curl"] and m.jnt_type.tolist() == [mjcf.JNT_HINGE, mjcf.JNT_SLIDE, mjcf.JNT_HINGE]
+    assert m.jnt_bodyid.tolist() == [2, 3, 5]  # the tool is welded to the slider: no joint of its own
+    # joint origin -> child body frame (fixed-axis roll / pitch / yaw)
+    assert np.allclose(m.body_pos[2], [0, 0, 0.1]) and np.allclose(_qmat(m.body_quat[2]), _rpy(0.2, 0.4, -0.6), atol=1e-12)
+    assert np.allclose(m.body_pos[4], [0, 0, 0.2]) and np.allclose(_qmat(m.body_quat[4]), _rpy(0, 0, 1.0), atol=1e-12)
+    assert np.allclose(m.jnt_pos, 0) and np.allclose(m.jnt_axis, [[0, 0, 1], [1, 0, 0], [0, 1, 0]])
+    assert m.jnt_limited.tolist() == [1, 1, 0] and np.allclose(m.jnt_range[:2], [[-1.5, 2.0], [0, 0.25]])  # continuous: unlimited
+    assert np.allclose(m.dof_damping, [0.4, 2.0, 0.0])
+    # inertia: the tensor is given in the frame `origin rpy`; in the body frame it is R I R'
+    I = np.array([[0.004, 0.0006, -0.0003], [0.0006, 0.009, 0.0002], [-0.0003, 0.0002, 0.008]])
+    R = _rpy(0.3, -0.2, 0.5)
+    got = _qmat(m.body_iquat[2]) @ np.diag(m.body_inertia[2]) @ _qmat(m.body_iquat[2]).T
+    assert np.allclose(got, R @ I @ R.T, atol=1e-15) and np.allclose(m.body_ipos[2], [0.1, 0.02, 0]) and np.isclose(m.body_mass[2], 1.2)
+    # one motor per transmission: limited to +- effort where the joint has one
+    assert m.names["actuator"] == ["shoulder_actuator", "extend_actuator"] and m.actuator_trnid.tolist() == [0, 1]
+    assert m.actuator_ctrllimited.tolist() == [1, 0] and np.allclose(m.actuator_ctrlrange[0], [-12.5, 12.5])
+    # one joint equality per mimic: q_curl = 0.1 + 0.5 q_shoulder
+    assert m.names["equality"] == ["curl_shoulder_equality"] and (m.eq_obj1id[0], m.eq_obj2id[0]) == (2, 0)
+    assert np.allclose(m.eq_data[0, :5], [0.1, 0.5, 0, 0, 0])
+    # collision geoms only (MuJoCo's URDF default discards visuals); sizes are half extents / half lengths
+    assert m.names["geom"][:2] == ["base_col", "upper_col"] and m.ngeom == 3 and m.geom_type.tolist() == [mjcf.GEOM_BOX, mjcf.GEOM_CAPSULE, mjcf.GEOM_SPHERE]
+    assert np.allclose(m.geom_size[0], [0.1, 0.1, 0.05]) and np.allclose(m.geom_size[1, :2], [0.03, 0.15]) and np.allclose(m.geom_pos[1], [0.2, 0, 0])
+    assert np.allclose(_qmat(m.geom_quat[1]), _rpy(0, 1.5708, 0), atol=1e-12)
+    f = Oracle(m, m.opt.replace(disableflags=16)).forward([0.3, 0.1, 0.25], [0.2, -0.1, 0.1], [1.0, -0.5])
+    assert np.isfinite(f["qacc"]).all() and f["efc_J"].shape[0] >= 1
+
+
+REF_MODELS = "/root/reference/ambersim/models"
+
+
+@pytest.mark.skipif(not __import__("os").path.exists(REF_MODELS), reason="the reference tree is only present in the build container")
+def test_reference_urdfs_load_like_the_xml_mujoco_made_from_them():
+    """The reference ships each model as a URDF and as the MJCF that MuJoCo's compiler + ambersim's `_add_actuators` / `_add_mimics`
+    produced from it (`save_model_xml`, io_utils.py:196-204). Loading the URDF through this repo's front end must give the model that
+    loading that MJCF gives: the MJCF is real MuJoCo output, printed to 6 digits."""
+    from oracle.independent import _qmat
+
+    u = load_mj_model_from_file(REF_MODELS + "/barrett_hand/bh280.urdf")
+    x = load_mj_model_from_file(REF_MODELS + "/barrett_hand/bh280.xml")
+    assert (u.nq, u.nv, u.nu, u.nbody, u.ngeom, u.neq) == (x.nq, x.nv, x.nu, x.nbody, x.ngeom, x.neq) == (8, 8, 4, 10, 98, 4)
+    for k in ("body", "joint", "geom", "actuator", "equality"):
+        assert u.names[k] == x.names[k], k
+    for k in ("body_mass", "body_pos", "body_ipos", "jnt_axis", "jnt_range", "actuator_ctrlrange", "eq_data", "geom_pos", "geom_quat", "geom_size"):
+        assert np.allclose(getattr(u, k), getattr(x, k), rtol=0, atol=1e-12), k
+    assert np.allclose(u.body_quat, x.body_quat, atol=1e-6) and np.array_equal(u.geom_vertnum, x.geom_vertnum)
+    assert np.array_equal(u.geom_contype, x.geom_contype) and np.array_equal(u.pair_geom1, x.pair_geom1) and u.n_unsupported_pairs == x.n_unsupported_pairs
+    for b in range(1, u.nbody):  # the same inertia tensor in the body frame (the MJCF carries quat + diaginertia to 6 digits)
+        Tu = _qmat(u.body_iquat[b]) @ np.diag(u.body_inertia[b]) @ _qmat(u.body_iquat[b]).T
+        Tx = _qmat(x.body_iquat[b]) @ np.diag(x.body_inertia[b]) @ _qmat(x.body_iquat[b]).T
+        assert np.abs(Tu - Tx).max() < 5e-6 * np.abs(Tx).max(), b
+    assert np.allclose(u.dof_invweight0, x.dof_invweight0, rtol=1e-6) and np.isclose(u.stat.meaninertia, x.stat.meaninertia, rtol=1e-6)
+    p = load_mj_model_from_file(REF_MODELS + "/pendulum/pendulum.urdf")
+    q = load_mj_model_from_file(REF_MODELS + "/pendulum/pendulum.xml")
+    assert (p.nq, p.nu, p.nbody) == (q.nq, q.nu, q.nbody) == (1, 1, 3) and p.names["body"] == q.names["body"] and p.names["actuator"] == q.names["actuator"]
+    assert np.allclose(p.body_mass, q.body_mass) and np.allclose(p.body_inertia, q.body_inertia) and np.allclose(p.actuator_ctrlrange, q.actuator_ctrlrange)
+    assert np.allclose(p.dof_invweight0, q.dof_invweight0, rtol=1e-9) and np.allclose(p.jnt_range, [[-3.1416, 3.1416]])

@@ -345,3 +345,15 @@ def test_reference_urdfs_load_like_the_xml_mujoco_made_from_them():
     assert (p.nq, p.nu, p.nbody) == (q.nq, q.nu, q.nbody) == (1, 1, 3) and p.names["body"] == q.names["body"] and p.names["actuator"] == q.names["actuator"]
     assert np.allclose(p.body_mass, q.body_mass) and np.allclose(p.body_inertia, q.body_inertia) and np.allclose(p.actuator_ctrlrange, q.actuator_ctrlrange)
     assert np.allclose(p.dof_invweight0, q.dof_invweight0, rtol=1e-9) and np.allclose(p.jnt_range, [[-3.1416, 3.1416]])
+
+
+def test_introspection_helpers_and_urdf_actuators():
+    """The reference's loader test counts actuators against the URDF's transmissions and equalities against its mimic joints
+    (tests/test_model_io.py:66-100), through its introspection helpers."""
+    from ambersim_b200.utils.introspection_utils import get_actuator_names, get_equality_names, get_geom_names, get_joint_names
+
+    m = load_mj_model_from_file("tests/models/arm.urdf")
+    assert get_actuator_names(m) == ["shoulder_actuator", "extend_actuator"] and get_equality_names(m) == ["curl_shoulder_equality"]
+    assert get_joint_names(m) == ["shoulder", "extend", "curl"] and len(get_geom_names(m)) == m.ngeom
+    b = load_mj_model_from_file("models/barrett_hand/bh280.xml")
+    assert len(get_actuator_names(b)) == 4 and len(get_equality_names(b)) == 4 and len(get_joint_names(b)) == 8

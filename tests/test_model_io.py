@@ -357,3 +357,16 @@ def test_introspection_helpers_and_urdf_actuators():
     assert get_joint_names(m) == ["shoulder", "extend", "curl"] and len(get_geom_names(m)) == m.ngeom
     b = load_mj_model_from_file("models/barrett_hand/bh280.xml")
     assert len(get_actuator_names(b)) == 4 and len(get_equality_names(b)) == 4 and len(get_joint_names(b)) == 8
+
+
+def test_save_model_xml_round_trip(tmp_path):
+    """save_model_xml (reference conversion_utils.py:11-37, tests/test_model_io.py:57-63): the MJCF saved from a URDF loads to the same model."""
+    from ambersim_b200.utils.conversion_utils import save_model_xml
+
+    out = tmp_path / "arm.xml"
+    save_model_xml("tests/models/arm.urdf", out)
+    a, b = load_mj_model_from_file("tests/models/arm.urdf"), load_mj_model_from_file(out)
+    assert a.names == b.names and (a.nq, a.nv, a.nu, a.neq, a.ngeom) == (b.nq, b.nv, b.nu, b.neq, b.ngeom)
+    for k in ("body_pos", "body_quat", "body_mass", "body_inertia", "body_ipos", "jnt_axis", "jnt_range", "dof_damping", "eq_data", "actuator_ctrlrange",
+              "geom_size", "geom_pos", "dof_invweight0", "body_invweight0"):
+        assert np.allclose(getattr(a, k), getattr(b, k), rtol=1e-9, atol=1e-12), k

@@ -358,6 +358,24 @@ def read_obj_vertices(path) -> np.ndarray:
     return np.array(out)
 
 
+def read_stl_vertices(path) -> np.ndarray:
+    """Vertices of an STL file, binary or ASCII (every triangle corner; the hull reduction follows)."""
+    raw = Path(path).read_bytes()
+    if len(raw) >= 84:
+        ntri = int(np.frombuffer(raw[80:84], dtype="<u4")[0])
+        if len(raw) == 84 + 50 * ntri and ntri > 0:  # binary: 80-byte header, count, 50 bytes per triangle (normal, 3 corners, attribute)
+            rec = np.frombuffer(raw[84:], dtype=np.dtype([("n", "<f4", 3), ("v", "<f4", (3, 3)), ("a", "<u2")]))
+            return np.unique(rec["v"].reshape(-1, 3).astype(np.float64), axis=0)
+    out = []
+    for line in raw.decode("ascii", errors="ignore").splitlines():
+        t = line.split()
+        if len(t) == 4 and t[0] == "vertex":
+            out.append([float(t[1]), float(t[2]), float(t[3])])
+    if not out:
+        raise ValueError(f"{path}: not an STL file")
+    return np.unique(np.array(out), axis=0)
+
+
 def _expand_includes(root: ET.Element, base: Path) -> None:
     for parent in list(root.iter()):
         for i, child in enumerate(list(parent)):
@@ -624,9 +642,12 @@ class _Compiler:
                     v = _floats(attrs["vertex"]).reshape(-1, 3)
                 elif "file" in attrs:
                     f = self.base_dir / self.meshdir / attrs["file"]
-                    if f.suffix.lower() != ".obj":
-                        raise NotImplementedError(f"mesh file {f.name}: only Wavefront OBJ is read")
-                    v = read_obj_vertices(f)
+                    if f.suffix.lower() == ".obj":
+                        v = read_obj_vertices(f)
+                    elif f.suffix.lower() == ".stl":
+                        v = read_stl_vertices(f)
+                    else:
+                        raise NotImplementedError(f"mesh file {f.name}: Wavefront OBJ and STL are read")
                 else:
                     raise ValueError("<mesh> needs `vertex` or `file`")
                 scale = _floats(attrs.get("scale"), 3, [1, 1, 1])

@@ -370,3 +370,26 @@ def test_save_model_xml_round_trip(tmp_path):
     for k in ("body_pos", "body_quat", "body_mass", "body_inertia", "body_ipos", "jnt_axis", "jnt_range", "dof_damping", "eq_data", "actuator_ctrlrange",
               "geom_size", "geom_pos", "dof_invweight0", "body_invweight0"):
         assert np.allclose(getattr(a, k), getattr(b, k), rtol=1e-9, atol=1e-12), k
+
+
+def test_stl_meshes_binary_and_ascii(tmp_path):
+    """Mesh geoms from STL files (what URDFs usually reference): binary and ASCII give the hull of the same tetrahedron."""
+    import struct
+
+    pts = np.array([[0, 0, 0], [0.1, 0, 0], [0, 0.1, 0], [0, 0, 0.1]], dtype=np.float32)
+    tris = [(0, 2, 1), (0, 1, 3), (0, 3, 2), (1, 2, 3)]
+    with open(tmp_path / "tet.stl", "wb") as f:
+        f.write(b"binary tetrahedron".ljust(80, b" ") + struct.pack("<I", len(tris)))
+        for t in tris:
+            f.write(struct.pack("<3f", 0, 0, 0) + b"".join(struct.pack("<3f", *pts[i]) for i in t) + struct.pack("<H", 0))
+    lines = ["solid tet"] + [ln for t in tris for ln in (["facet normal 0 0 0", "outer loop"] + [f"vertex {pts[i][0]} {pts[i][1]} {pts[i][2]}" for i in t] + ["endloop", "endfacet"])] + ["endsolid tet"]
+    (tmp_path / "tet_ascii.stl").write_text("\n".join(lines))
+    xml = tmp_path / "m.xml"
+    xml.write_text("""<mujoco><asset><mesh name="a" file="tet.stl"/><mesh name="b" file="tet_ascii.stl" scale="2 2 2"/></asset><worldbody>
+      <geom type="plane" size="1 1 .1"/><body pos="0 0 1"><freejoint/><inertial pos="0 0 0" mass="1" diaginertia=".1 .1 .1"/>
+      <geom type="mesh" mesh="a"/><geom type="mesh" mesh="b" pos=".3 0 0"/></body></worldbody></mujoco>""")
+    m = load_mj_model_from_file(xml)
+    assert m.geom_vertnum.tolist() == [0, 4, 4] and m.geom_facenum.tolist() == [0, 4, 4] and m.geom_edgenum.tolist() == [0, 6, 6]
+    va, vb = m.vert[:4], m.vert[4:]
+    assert {tuple(np.round(v, 6)) for v in va} == {tuple(np.round(p, 6)) for p in pts.astype(np.float64)}
+    assert {tuple(np.round(v, 6)) for v in vb} == {tuple(np.round(2 * p, 6)) for p in pts.astype(np.float64)}

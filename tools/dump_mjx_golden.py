@@ -1,4 +1,4 @@
-"""Run on a machine that HAS mujoco + mujoco-mjx + jax (not this image): dumps, for each of the repo's five models,
+"""Run on a machine that HAS mujoco + mujoco-mjx + jax (not this image): dumps, for each of the repo's five models and three convex-collision fixtures,
 (1) a reference rollout through the reference's own `shoot`, (2) every per-stage `mjx.Data` field of one `mjx.forward`
 at a seeded state (controls and warm start included) and (3) the compiled `MjModel` field by field (mj_setConst
 constants, defaults, frames) into tests/golden/mjx_<model>.npz. tests/test_oracle_physics.py
@@ -24,12 +24,15 @@ except ImportError as e:  # pragma: no cover
 
 MODELS = {"pendulum": ("pendulum/scene.xml", None, {}), "bh280": ("barrett_hand/bh280.xml", None, dict(timestep=0.002, iterations=1, ls_iterations=4, disableflags=16)),
           "barkour": ("barkour_standin/barkour_vb_standin.xml", "home", {}), "biped": ("biped_standin/biped_exo_standin.xml", "stand", {}),
-          "exolegs": ("biped_standin/exo_legs_standin.xml", "stand", {})}
+          "exolegs": ("biped_standin/exo_legs_standin.xml", "stand", {}),
+          # convex collision fixtures (paths from the repo root): plane / sphere / capsule / convex - convex pairs of collision_convex.py
+          "boxbot": ("tests/models/boxbot.xml", "home", {}), "blocks": ("tests/models/blocks.xml", "home", {}),
+          "bh280_hulls": ("tests/models/bh280_hulls.xml", None, dict(timestep=0.002, iterations=2, ls_iterations=6))}
 STAGES = ("xpos xquat xmat xipos ximat xanchor xaxis geom_xpos geom_xmat subtree_com cinert cdof crb qM qLD actuator_length actuator_velocity "
           "actuator_force qfrc_actuator cvel cdof_dot qfrc_passive qfrc_bias qfrc_smooth qacc_smooth efc_J efc_D efc_aref efc_pos efc_force "
           "qfrc_constraint qacc qacc_warmstart").split()
 for name, (rel, key, kw) in MODELS.items():
-    mj_model = mujoco.MjModel.from_xml_path(str(ROOT / "ambersim_b200/models" / rel))
+    mj_model = mujoco.MjModel.from_xml_path(str(ROOT / rel if rel.startswith("tests/") else ROOT / "ambersim_b200/models" / rel))
     for k, v in kw.items():
         setattr(mj_model.opt, k, v)
     m = mjx.device_put(mj_model)
@@ -56,6 +59,13 @@ for name, (rel, key, kw) in MODELS.items():
     if key:
         sq[7:] += rng.uniform(-0.1, 0.1, mj_model.nq - 7)
         sq[2] -= 0.004  # feet pressed into the floor: contact rows active
+    if name == "boxbot":
+        sq[2] = 0.06  # the chassis box and the mesh foot on the tilted floor
+    if name == "blocks":
+        sq[2] = 0.31  # settled on the pedestal: capsule foot, sphere hand, mesh tail and (tilted) the chassis box
+        sq[3:7] = np.array([0.99, -0.13, -0.04, 0.0]) / np.linalg.norm([0.99, -0.13, -0.04, 0.0])
+    if name == "bh280_hulls":
+        sq = np.array([2.34, 0.7, 1.5, 2.35, 0.7, 1.5, 1.4, 0.5])  # finger tips closed on each other
     sv, sc, sw = 0.3 * rng.normal(size=mj_model.nv), us[0], rng.normal(size=mj_model.nv)
     d = mjx.make_data(m).replace(qpos=jnp.asarray(sq, jnp.float32), qvel=jnp.asarray(sv, jnp.float32), ctrl=jnp.asarray(sc, jnp.float32),
                                  qacc_warmstart=jnp.asarray(sw, jnp.float32))

@@ -1,6 +1,8 @@
 """Randomised models of the limb-kernel class (tests/_randmodel.py): host-side plan invariants on the CPU, and on the
 GPU the limb kernels and the generic kernels against the float64 oracle, teacher-forced, from settled contact states.
 Tolerances are the single-step bounds of tests/test_gpu_parity.py."""
+import os
+
 import numpy as np
 import pytest
 
@@ -71,7 +73,7 @@ def test_random_model_oracle_float32_tracks_float64(tmp_path, cfg):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("cfg", list(CONFIGS))
-@pytest.mark.parametrize("seed", range(10))
+@pytest.mark.parametrize("seed", range(int(os.environ.get("ABR_SOAK_SEEDS", "10"))))  # a soak run sets ABR_SOAK_SEEDS higher
 def test_random_model_step_parity(tmp_path, cfg, seed):
     import torch
 
@@ -107,4 +109,5 @@ def test_random_model_step_parity(tmp_path, cfg, seed):
         vmax = np.maximum(1.0, np.abs(v1).max(axis=1))
         assert np.all(np.abs(gv - v1).max(axis=1) <= 1e-4 * vmax + 3 * np.abs(v32 - v1).max(axis=1)), f"qvel, lanes {lanes}"
         ran.append(gq)
-    assert not np.array_equal(ran[0], ran[1])  # two different kernels really ran
+    if plan["eligible"]:  # limb vs generic kernels: different arithmetic, so different roundings (two group sizes of the generic kernels may well agree bit for bit)
+        assert not np.array_equal(ran[0], ran[1])

@@ -423,3 +423,29 @@ def test_c_abi_refuses_inconsistent_hull_tables(load_model):
         rc = _lib.lib().abr_model_create(C.byref(host), 0, C.byref(ptr))
         assert rc == _lib.ABR_EINVAL and what in _lib.lib().abr_last_error().decode(), (field, rc, _lib.lib().abr_last_error())
         assert not ptr.value
+
+
+def test_hull_topology_of_random_point_clouds():
+    """convex_topology on random hulls: closed polyhedra (Euler), outward unit normals, every polygon planar, convex and counter-clockwise,
+    every edge shared by exactly two faces."""
+    rng = np.random.default_rng(3)
+    for trial in range(12):
+        n = int(rng.integers(5, 40))
+        pts = rng.normal(size=(n, 3)) * rng.uniform(0.05, 0.3, 3)
+        if trial % 3 == 0:  # some coplanar groups: a prism-like cloud, so that triangles get merged into polygons
+            pts = np.concatenate([np.c_[rng.normal(size=(6, 2)) * 0.1, np.full(6, -0.1)], np.c_[rng.normal(size=(6, 2)) * 0.1, np.full(6, 0.1)]])
+        v = mjcf.convex_vertices(pts)
+        faces, normals, edges = mjcf.convex_topology(v)
+        assert len(v) - len(edges) + len(faces) == 2
+        c = v.mean(axis=0)
+        count = {}
+        for f, nn in zip(faces, normals):
+            assert 3 <= len(f) <= mjcf.MAX_FACE_VERTS and np.isclose(np.linalg.norm(nn), 1.0)
+            P = v[f]
+            assert np.abs((P - P[0]) @ nn).max() < 1e-9  # planar
+            assert np.dot(P.mean(axis=0) - c, nn) > 0  # outward
+            assert np.all((v - P[0]) @ nn < 1e-9)  # a supporting plane of the hull
+            for a, b, d in zip(f, f[1:] + f[:1], f[2:] + f[:2]):
+                assert np.dot(np.cross(v[b] - v[a], v[d] - v[b]), nn) > -1e-12  # convex, counter-clockwise seen from outside
+                count[(min(a, b), max(a, b))] = count.get((min(a, b), max(a, b)), 0) + 1
+        assert sorted(count) == [tuple(e) for e in edges.tolist()] and set(count.values()) == {2}

@@ -1338,8 +1338,8 @@ int abr_rollout_host(AbrModel* m, const float* x0, int x0_stride, const float* u
     rc = m->s_carry.ensure(sizeof(float) * (size_t)nworld * (m->lay.nq + 2 * m->lay.nv + 8));
     if (rc) return rc;
     // the copy stream must not overwrite d_us while an earlier call's kernels may still read it
-    CK(cudaEventRecord(m->ev[nslice], m->stream));
-    CK(cudaStreamWaitEvent(m->copy_stream, m->ev[nslice], 0));
+    CK(cudaEventRecord(m->ev[0], m->stream));
+    CK(cudaStreamWaitEvent(m->copy_stream, m->ev[0], 0));
     const int per = (N + nslice - 1) / nslice;
     RolloutArgs a;
     memset(&a, 0, sizeof(a));
@@ -1347,13 +1347,30 @@ int abr_rollout_host(AbrModel* m, const float* x0, int x0_stride, const float* u
     a.mode = 0; a.nworld = nworld; a.N = N; a.xs_out = xs_out ? d_xs : nullptr; a.costs_out = costs_out ? d_c : nullptr;
     a.cost = cost_view(costs_out ? cost : nullptr); a.carry = (float*)m->s_carry.p;
     const size_t pitch = sizeof(float) * (size_t)N * nu;
-    for (int k = 0; k < nslice; k++) {
-      const int tb = k * per, te = std::min(N, tb + per);
+    // slice boundaries: the first copy is exposed (nothing to overlap it with), so the schedule starts with a short slice and grows
+    // by 1.5x (the next slice's copy must fit under this slice's steps: host-to-device moves a step's controls about twice as fast as
+    // the kernel consumes them) until it reaches N / nslice; ABR_SLICES asks for uniform slices
+    std::vector<int> bounds{0};
+    if (getenv("ABR_SLICES")) {
+      for (int tb = per; tb < N; tb += per) bounds.push_back(tb);
+    } else {
+      for (double len = 8.0; bounds.back() < N;) {
+        const int step = std::max(1, std::min(2 * per, (int)len));  // up to N / 8 steps per slice once the ramp is over
+        bounds.push_back(std::min(N, bounds.back() + step));
+        len *= 1.5;
+      }
+      bounds.pop_back();
+    }
+    bounds.push_back(N);
+    const int nb = (int)bounds.size() - 1;
+    while ((int)m->ev.size() < nb + 2) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); m->ev.push_back(e); }
+    for (int k = 0; k < nb; k++) {
+      const int tb = bounds[k], te = bounds[k + 1];
       if (tb >= te) break;
       CK(cudaMemcpy2DAsync(d_us + (size_t)tb * nu, pitch, us + (size_t)tb * nu, pitch, sizeof(float) * (size_t)(te - tb) * nu, nworld,
                            cudaMemcpyHostToDevice, m->copy_stream));
-      CK(cudaEventRecord(m->ev[k], m->copy_stream));
-      CK(cudaStreamWaitEvent(m->stream, m->ev[k], 0));
+      CK(cudaEventRecord(m->ev[k + 1], m->copy_stream));
+      CK(cudaStreamWaitEvent(m->stream, m->ev[k + 1], 0));
       a.t_begin = tb; a.t_end = te;
       rc = launch_rollout(m, m->lay, a, m->stream);
       if (rc) return rc;

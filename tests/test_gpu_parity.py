@@ -614,15 +614,15 @@ def test_host_rollout_pipelined_slices_equal_one_launch(load_model, monkeypatch)
     us = np.clip(mj.key_ctrl("home") + 0.1 * rng.normal(size=(W, N, mj.nu)), mj.actuator_ctrlrange[:, 0], mj.actuator_ctrlrange[:, 1]).astype(np.float32)
     cf = StaticGoalQuadraticCost(np.eye(nx), 10 * np.eye(nx), 0.01 * np.eye(mj.nu), x0[0])
     res = {}
-    for mode, env in (("sliced", {"ABR_SLICES": "5"}), ("single", {"ABR_NO_PIPELINE": "1"})):
+    for mode, env in (("sliced", {"ABR_SLICES": "5"}), ("graded", {}), ("single", {"ABR_NO_PIPELINE": "1"})):
         for k in ("ABR_SLICES", "ABR_NO_PIPELINE"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         res[mode] = (shoot(m, x0, us), shoot_cost(m, x0, us, cf))
     assert isinstance(res["sliced"][0], np.ndarray)
-    assert np.array_equal(res["sliced"][0], res["single"][0])
-    assert np.array_equal(np.asarray(res["sliced"][1]), np.asarray(res["single"][1]))
+    assert np.array_equal(res["sliced"][0], res["single"][0]) and np.array_equal(res["graded"][0], res["single"][0])
+    assert np.array_equal(np.asarray(res["sliced"][1]), np.asarray(res["single"][1])) and np.array_equal(np.asarray(res["graded"][1]), np.asarray(res["single"][1]))
     assert np.isfinite(res["sliced"][0]).all()
 
 

@@ -262,6 +262,27 @@ def extra_configs(mj, m, cf, q0, torch, device, stream, L, peak_tf):
     ex["c3b_exo_legs_16384x1000"] = {"world_steps_per_s": rate, "costs_finite": fin, "flop_per_world_step": F_WS_EXO_LEGS,
                                      "frac_of_ffma_peak": F_WS_EXO_LEGS * rate / 1e12 / peak_tf, "kernels": em.describe(),
                                      "model": "exo_legs_standin (nq=19 nv=18 nu=12 nbody=14 ncon=8 nefc=44; Newton it=1 ls=6 Euler dt=.004)"}
+    # convex collision at scale (context, not a BASELINE config): the test fixture with box / capsule / sphere / mesh geoms against a static
+    # box and a static wedge (sphere -, capsule - and convex - convex pairs, 19 contact slots) on the generic kernels
+    try:
+        cj = load_mj_model_from_file("tests/models/blocks.xml")
+        cm = mjx.device_put(cj)
+        cq0 = np.concatenate([cj.key_qpos("home"), np.zeros(cj.nv)])
+        cq0[2] = 0.33
+        cnx = cj.nq + cj.nv
+        ccf = StaticGoalQuadraticCost(np.eye(cnx), 10.0 * np.eye(cnx), 0.01 * np.eye(cj.nu), cq0)
+        Wc, Nc = 2048, 100
+        cx0 = torch.tensor(cq0, **f).repeat(Wc, 1)
+        clim = torch.tensor(cj.actuator_ctrlrange, **f)
+        cus = torch.minimum(torch.maximum(torch.tensor(cj.key_ctrl("home"), **f) + 0.2 * torch.randn((Wc, Nc, cj.nu), generator=g, **f), clim[:, 0]), clim[:, 1])
+        ccosts = torch.empty(Wc, **f)
+        chh, cch = cm.handle(device.index or 0), ccf.device_cost(device.index or 0)
+        cms = _timed(torch, stream, lambda: _lib.check(L.abr_rollout_dev(chh.ptr, p(cx0), cnx, p(cus), Nc * cj.nu, Wc, Nc, None, cch.ptr, p(ccosts),
+                                                                         C.c_void_p(stream.cuda_stream))), 2)
+        ex["convex_blocks_2048x100"] = {"world_steps_per_s": Wc * Nc / (cms * 1e-3), "costs_finite": bool(torch.isfinite(ccosts).all()), "kernels": cm.describe(),
+                                        "model": "tests/models/blocks.xml (nv=9, 6 convex pairs, 19 contact slots, nefc=79)"}
+    except FileNotFoundError:
+        pass
     sweep = {}
     prm = VanillaPredictiveSamplerParams(key=3, x0=torch.tensor(q0, **f), us_guess=torch.tensor(mj.key_ctrl("home"), **f).repeat(32, 1))
     for S in (1024, 4096, 16384, 65536, 262144, 1048576):

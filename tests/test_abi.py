@@ -85,3 +85,34 @@ def test_exchange_refuses_without_a_device():
     handle = C.create_string_buffer(_lib.xchg_handle_bytes())
     x = C.c_void_p()
     assert L.abr_xchg_create(0, 2, 0, 16, C.byref(x), handle) == _lib.ABR_ENODEVICE
+
+
+def _build_c_client(tmp_path):
+    import subprocess
+
+    from ambersim_b200 import _abi
+
+    root = _abi.REPO_ROOT
+    exe = tmp_path / "abr_c_client"
+    subprocess.run(["gcc", "-std=c99", "-O1", "-Wall", "-Werror", f"-I{root / 'include'}", "-o", str(exe), str(root / "tests/c_client/abr_c_client.c"),
+                    f"-L{root / 'ambersim_b200'}", "-labr", "-lm", f"-Wl,-rpath,{root / 'ambersim_b200'}"], check=True, capture_output=True)
+    return subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+
+
+def test_plain_c_client_builds_and_fails_loudly_without_a_device(tmp_path):
+    """include/abr.h is plain C99 and libabr.so links into a C program with nothing else (no Python, torch or C++ runtime on the client
+    side). Without a CUDA device the program gets ABR_ENODEVICE from abr_model_create, never a fallback."""
+    import torch
+
+    r = _build_c_client(tmp_path)
+    assert r.returncode == 0, r.stdout + r.stderr
+    if not torch.cuda.is_available():
+        assert "ABR_ENODEVICE" in r.stdout
+
+
+@pytest.mark.gpu
+def test_plain_c_client_rolls_a_pendulum(tmp_path):
+    """The same C program on a GPU: a hand-filled AbrModelHost of a damped pendulum, 8 worlds x 200 steps through abr_rollout_host;
+    finite, never above the release angle, half a period where the physical pendulum's is, identical worlds bit-identical."""
+    r = _build_c_client(tmp_path)
+    assert r.returncode == 0 and "0 failed checks" in r.stdout, r.stdout + r.stderr

@@ -896,6 +896,9 @@ static int pick_lanes(const AbrModel* m, int nworld) {
   // every SM sub-partition a warp, they win (bh280, 4096 x 32 solve: 2.07 ms with 8 lanes, 3.55 ms with 32)
   if (m->lay.nv <= 10) {
     const long subparts = 4L * m->num_sms;
+    // many contact slots (convex pairs carry 2 - 4 each and every slot runs its pair's selection on its own lane): 16 lanes take them in
+    // fewer rounds (blocks.xml, 19 slots: 3.6e6 / 4.0e6 world-steps/s at 2048 / 16384 worlds with 16 lanes, 2.8e6 / 3.1e6 with 8, 3.1e6 with 32)
+    if (m->lay.ncon > 8 && (long)nworld * 16 / 32 >= subparts / 2) return 16;
     if ((long)nworld * 8 / 32 >= subparts / 2) return 8;
     if ((long)nworld * 16 / 32 >= subparts / 2) return 16;
     return 32;

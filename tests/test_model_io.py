@@ -393,3 +393,24 @@ def test_stl_meshes_binary_and_ascii(tmp_path):
     va, vb = m.vert[:4], m.vert[4:]
     assert {tuple(np.round(v, 6)) for v in va} == {tuple(np.round(p, 6)) for p in pts.astype(np.float64)}
     assert {tuple(np.round(v, 6)) for v in vb} == {tuple(np.round(2 * p, 6)) for p in pts.astype(np.float64)}
+
+
+def test_shipped_urdfs_load_like_the_shipped_mjcf(tmp_path, monkeypatch):
+    """The package ships its two reference models as URDF and as MJCF, like the reference (tests/test_model_io.py:24-47 loads
+    `models/pendulum/pendulum.urdf` by global, local and package-relative paths, str or Path): both forms give the same model."""
+    for u, x in (("models/pendulum/pendulum.urdf", "models/pendulum/pendulum.xml"), ("models/barrett_hand/bh280.urdf", "models/barrett_hand/bh280.xml")):
+        a, b = load_mj_model_from_file(u), load_mj_model_from_file(x)
+        assert (a.nq, a.nv, a.nu, a.nbody, a.neq) == (b.nq, b.nv, b.nu, b.nbody, b.neq) and a.names["actuator"] == b.names["actuator"]
+        assert np.allclose(a.body_mass, b.body_mass) and np.allclose(a.dof_invweight0, b.dof_invweight0, rtol=1e-6)
+        assert np.allclose(a.eq_data, b.eq_data) and np.allclose(a.actuator_ctrlrange, b.actuator_ctrlrange)
+        if "bh280" in u:  # (the reference's pendulum.xml was edited by hand after the conversion: its joint lost the URDF's limit)
+            assert np.allclose(a.jnt_range, b.jnt_range)
+        else:
+            assert a.jnt_limited.tolist() == [1] and np.allclose(a.jnt_range, [[-3.1416, 3.1416]])
+    glob = ROOT + "/models/pendulum/pendulum.urdf"
+    local = tmp_path / "pendulum.urdf"
+    local.write_text(Path(glob).read_text())
+    monkeypatch.chdir(tmp_path)
+    for p in (glob, Path(glob), "pendulum.urdf", Path("pendulum.urdf"), "models/pendulum/pendulum.urdf", Path("models/pendulum/pendulum.urdf")):
+        assert load_mj_model_from_file(p).nq == 1
+    assert load_mj_model_from_file("models/barrett_hand/bh280.urdf", force_float=True).nq == 15  # reference tests/test_model_io.py:146

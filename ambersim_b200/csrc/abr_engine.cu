@@ -1293,7 +1293,7 @@ int abr_rollout_dev(AbrModel* m, const float* x0, int x0_stride, const float* us
                     float* xs_out, const AbrCost* cost, float* costs_out, void* stream) {
   if (nworld < 0 || N < 0) return fail(ABR_EINVAL, "abr_rollout_dev: negative size");
   if (m && nworld == 0) return ABR_OK;  // an empty batch has no buffers to point at
-  if (!m || !x0 || (!us && N > 0)) return fail(ABR_EINVAL, "abr_rollout_dev: null argument");
+  if (!m || !x0 || (!us && N > 0 && m && m->lay.nu > 0)) return fail(ABR_EINVAL, "abr_rollout_dev: null argument");
   if (cost && (cost->nx != m->lay.nx || cost->nu != m->lay.nu)) return fail(ABR_EINVAL, "abr_rollout_dev: cost dimensions do not match the model");
   if (costs_out && !cost) return fail(ABR_EINVAL, "abr_rollout_dev: costs_out without a cost");
   ABR_ON_DEVICE(m->device);
@@ -1310,7 +1310,7 @@ int abr_rollout_host(AbrModel* m, const float* x0, int x0_stride, const float* u
                      float* xs_out, const AbrCost* cost, float* costs_out) {
   if (nworld < 0 || N < 0) return fail(ABR_EINVAL, "abr_rollout_host: negative size");
   if (m && nworld == 0) return ABR_OK;
-  if (!m || !x0 || (!us && N > 0)) return fail(ABR_EINVAL, "abr_rollout_host: null argument");
+  if (!m || !x0 || (!us && N > 0 && m && m->lay.nu > 0)) return fail(ABR_EINVAL, "abr_rollout_host: null argument");
   if (cost && (cost->nx != m->lay.nx || cost->nu != m->lay.nu)) return fail(ABR_EINVAL, "abr_rollout_host: cost dimensions do not match the model");
   if (costs_out && !cost) return fail(ABR_EINVAL, "abr_rollout_host: costs_out without a cost");
   ABR_ON_DEVICE(m->device);

@@ -311,7 +311,8 @@ def _stream(dev: torch.device):
 
 def _flat(t: torch.Tensor, n: int, dev: torch.device, batch: tuple) -> torch.Tensor:
     t = torch.as_tensor(t, dtype=torch.float32, device=dev)
-    return t.expand(*batch, n).reshape(-1, n).contiguous().clone()
+    rows = int(np.prod(batch)) if batch else 1  # explicit: reshape(-1, 0) is ambiguous for a model without actuators (nu = 0)
+    return t.expand(*batch, n).reshape(rows, n).contiguous().clone()
 
 
 def _batch_shape(m: Model, d: Data) -> tuple:

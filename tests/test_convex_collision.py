@@ -449,3 +449,28 @@ def test_hull_topology_of_random_point_clouds():
                 assert np.dot(np.cross(v[b] - v[a], v[d] - v[b]), nn) > -1e-12  # convex, counter-clockwise seen from outside
                 count[(min(a, b), max(a, b))] = count.get((min(a, b), max(a, b)), 0) + 1
         assert sorted(count) == [tuple(e) for e in edges.tolist()] and set(count.values()) == {2}
+
+
+@pytest.mark.gpu
+def test_model_without_actuators_steps_and_shoots(tmp_path):
+    """nu = 0 (a passive box dropped on a box): mjx.step and shoot take (.., 0)-shaped controls; the rollout matches the oracle."""
+    import torch
+
+    from ambersim_b200 import mjx
+    from ambersim_b200.trajopt.shooting import shoot
+
+    mj = _pair(tmp_path, '<geom type="box" size=".05 .08 .03" friction="0.9 0.01 0.001"/>')
+    assert mj.nu == 0
+    m = mjx.device_put(mj)
+    o = Oracle(mj)
+    q0 = np.array([0.03, -0.02, 0.2 + 0.03 + 0.004, np.cos(0.2), 0.02, 0.03, np.sin(0.2)])
+    q0[3:] /= np.linalg.norm(q0[3:])
+    x0 = np.concatenate([q0, np.zeros(6)])
+    t = lambda a: torch.tensor(a, dtype=torch.float32, device="cuda")
+    d = mjx.step(m, mjx.Data(qpos=t(np.tile(q0, (3, 1))), qvel=torch.zeros(3, 6, device="cuda"), ctrl=torch.zeros(3, 0, device="cuda"),
+                             qacc=torch.zeros(3, 6, device="cuda"), qacc_warmstart=torch.zeros(3, 6, device="cuda"), time=torch.zeros(3, device="cuda")))
+    ref = o.rollout(x0, np.zeros((1, 0)))[1]
+    assert d.ctrl.shape == (3, 0) and np.abs(d.qpos[1].cpu().numpy() - ref[:7]).max() < 1e-5
+    xs = shoot(m, t(x0), torch.zeros(20, 0, device="cuda")).cpu().numpy()
+    refx = o.rollout(x0, np.zeros((20, 0)))
+    assert xs.shape == (21, 13) and np.abs(xs[:8] - refx[:8]).max() < 5e-4

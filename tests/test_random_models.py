@@ -111,3 +111,62 @@ def test_random_model_step_parity(tmp_path, cfg, seed):
         ran.append(gq)
     if plan["eligible"]:  # limb vs generic kernels: different arithmetic, so different roundings (two group sizes of the generic kernels may well agree bit for bit)
         assert not np.array_equal(ran[0], ran[1])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", list(CONFIGS))
+@pytest.mark.parametrize("seed", range(max(2, int(os.environ.get("ABR_SOAK_SEEDS", "10")) // 5)))
+def test_random_model_sampler_and_env_parity(tmp_path, cfg, seed):
+    """The other two entry points on random models: a predictive-sampling solve (per-sample costs against oracle rollouts, first-minimum
+    argmin on the device's own costs, winner trajectory = rollout of the winner controls) and env steps with substeps and the
+    auto-reset blend against the oracle."""
+    import torch
+
+    from ambersim_b200.rl.base import VectorEnvStepper
+    from ambersim_b200.trajopt.cost import StaticGoalQuadraticCost
+    from ambersim_b200.trajopt.shooting import VanillaPredictiveSampler, VanillaPredictiveSamplerParams, shoot
+    from oracle.oracle import quad_cost
+
+    mj, q, c = _load(tmp_path, 1000 + seed, cfg, iterations=1)
+    if mj.nu == 0:
+        pytest.skip("a model without actuators has nothing to sample")
+    o = Oracle(mj)
+    m = mjx.device_put(mj)
+    lo, hi = mj.actuator_ctrlrange[:, 0], mj.actuator_ctrlrange[:, 1]
+    clip = lambda u: np.where(mj.actuator_ctrllimited > 0, np.clip(u, lo, hi), u)
+    settle = o.rollout(np.concatenate([q, np.zeros(mj.nv)])[None], np.tile(clip(c), (1, 150, 1)))[0, -1]
+    nx, S, N = mj.nq + mj.nv, 24, 6
+    t32 = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float32, device="cuda")
+    Q, Qf, R = np.eye(nx), 10 * np.eye(nx), 0.01 * np.eye(mj.nu)
+    ps = VanillaPredictiveSampler(model=m, cost_function=StaticGoalQuadraticCost(Q, Qf, R, settle), nsamples=S, stdev=0.1)
+    rng = np.random.default_rng(500 + seed)
+    noise = rng.normal(size=(S - 1, N, mj.nu)).astype(np.float32)
+    ug = np.tile(clip(c), (N, 1)).astype(np.float32)
+    x0 = settle.astype(np.float32)
+    xs, us, info = ps.optimize(VanillaPredictiveSamplerParams(key=0, x0=t32(x0), us_guess=t32(ug), noise=t32(noise)), return_info=True)
+    costs = info["costs"].reshape(-1).cpu().numpy()
+    us_all = np.concatenate([ug[None], ug[None] + np.float32(0.1) * noise]).astype(np.float64)
+    if (mj.actuator_ctrllimited > 0).all():
+        us_all = np.clip(us_all, lo, hi)
+        ref = quad_cost(o.rollout(x0.astype(np.float64), us_all), us_all, Q, Qf, R, settle)
+        assert np.allclose(costs, ref, rtol=1e-2, atol=1e-3), np.abs(costs / ref - 1).max()
+    k = int(info["best_idx"])
+    assert np.isfinite(costs).all() and k == int(np.argmin(costs))
+    # the winner's trajectory is the rollout of the winner's controls (another compile-time variant of the kernel ran it: equal up to rounding)
+    assert (xs - shoot(m, t32(x0), us)).abs().max() < 1e-4
+    # env steps: two substeps, half of the envs reset to their first state before stepping
+    E = 6
+    q0s = np.tile(settle[: mj.nq], (E, 1))
+    st = VectorEnvStepper(m, t32(q0s), torch.zeros(E, mj.nv, device="cuda"), nsubsteps=2)
+    ctrl = clip(c + 0.2 * rng.normal(size=(E, mj.nu)))
+    st.step(t32(ctrl))
+    mid_q, mid_v, mid_w = st.qpos.cpu().numpy().copy(), st.qvel.cpu().numpy().copy(), st.warm.cpu().numpy().copy()
+    done = torch.tensor([1, 0, 1, 0, 1, 0], device="cuda")
+    st.step(t32(ctrl), done)
+    fq, fv, fw = st.first_qpos.cpu().numpy(), st.first_qvel.cpu().numpy(), st.first_warm.cpu().numpy()
+    for e in range(E):
+        a = (fq[e], fv[e], fw[e]) if int(done[e]) else (mid_q[e], mid_v[e], mid_w[e])
+        qr, vr, _, _ = o.step(a[0], a[1], ctrl[e], a[2], nsteps=2)
+        q32, v32, _, _ = o.step(a[0], a[1], ctrl[e], a[2], nsteps=2, prec=1)
+        assert np.all(np.abs(st.qpos[e].cpu().numpy() - qr) <= 2e-5 + 2e-4 * np.abs(qr) + 3 * np.abs(q32 - qr)), e
+        assert np.abs(st.qvel[e].cpu().numpy() - vr).max() <= 2e-4 * max(1.0, np.abs(vr).max()) + 3 * np.abs(v32 - vr).max(), e

@@ -170,3 +170,45 @@ def test_random_model_sampler_and_env_parity(tmp_path, cfg, seed):
         q32, v32, _, _ = o.step(a[0], a[1], ctrl[e], a[2], nsteps=2, prec=1)
         assert np.all(np.abs(st.qpos[e].cpu().numpy() - qr) <= 2e-5 + 2e-4 * np.abs(qr) + 3 * np.abs(q32 - qr)), e
         assert np.abs(st.qvel[e].cpu().numpy() - vr).max() <= 2e-4 * max(1.0, np.abs(vr).max()) + 3 * np.abs(v32 - vr).max(), e
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", list(CONFIGS))
+@pytest.mark.parametrize("seed", range(max(2, int(os.environ.get("ABR_SOAK_SEEDS", "10")) // 5)))
+def test_random_model_derived_fields_and_host_calls(tmp_path, cfg, seed):
+    """Batched derived mjx.Data fields (xpos, xquat, cvel, qfrc_*, efc_*, contact_*) of one forward pass on random models against the
+    oracle's stage dump, and the host-pointer entry points (numpy in, numpy out) against the device-pointer ones."""
+    import torch
+
+    from ambersim_b200.trajopt.shooting import shoot
+
+    mj, q, c = _load(tmp_path, 2000 + seed, cfg, iterations=2)
+    o = Oracle(mj)
+    m = mjx.device_put(mj)
+    lo, hi = mj.actuator_ctrlrange[:, 0], mj.actuator_ctrlrange[:, 1]
+    clip = lambda u: np.where(mj.actuator_ctrllimited > 0, np.clip(u, lo, hi), u) if mj.nu else u
+    settle = o.rollout(np.concatenate([q, np.zeros(mj.nv)])[None], np.tile(clip(c), (1, 120, 1)))[0, -1]
+    rng = np.random.default_rng(700 + seed)
+    E = 3
+    qs = np.tile(settle[: mj.nq], (E, 1))
+    qs[:, 7:] += rng.uniform(-0.05, 0.05, (E, mj.nq - 7))
+    vs = 0.3 * rng.normal(size=(E, mj.nv))
+    cs = clip(c + 0.2 * rng.normal(size=(E, mj.nu)))
+    ws = rng.normal(size=(E, mj.nv))
+    t32 = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float32, device="cuda")
+    names = ("xpos", "xquat", "cvel", "qfrc_smooth", "qacc_smooth", "qfrc_constraint", "efc_force", "efc_D", "efc_aref", "contact_dist", "contact_pos")
+    d = mjx.forward(m, mjx.Data(qpos=t32(qs), qvel=t32(vs), ctrl=t32(cs), qacc=torch.zeros(E, mj.nv, device="cuda"), qacc_warmstart=t32(ws),
+                                time=torch.zeros(E, device="cuda")), fields=names)
+    for e in range(E):
+        ref = o.forward(d.qpos[e].cpu().numpy(), vs[e], cs[e], ws[e])
+        for n in names:
+            r, g = ref[n].ravel(), getattr(d, n)[e].cpu().numpy().ravel()
+            tol = 5e-3 if n in ("efc_force", "qfrc_constraint") else 5e-4  # two Newton iterations, not converged: the forces carry the solver's float32 path
+            assert np.abs(r - g).max() <= tol * max(1e-6, np.abs(r).max()) + 1e-5, (n, e, np.abs(r - g).max(), np.abs(r).max())
+    # host-pointer rollout = device-pointer rollout, bit for bit
+    N = 9
+    x0 = np.concatenate([qs[0], vs[0]]).astype(np.float32)
+    us = clip(c + 0.1 * rng.normal(size=(4, N, mj.nu))).astype(np.float32)
+    xs_h = shoot(m, x0, us)
+    xs_d = shoot(m, t32(x0), t32(us)).cpu().numpy()
+    assert isinstance(xs_h, np.ndarray) and np.array_equal(xs_h, xs_d)

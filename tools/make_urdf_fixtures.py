@@ -4,7 +4,7 @@ examples/load_from_file.py, tests/test_model_io.py:24-47).
 Reads the reference's ambersim/models/pendulum/pendulum.urdf and ambersim/models/barrett_hand/bh280.urdf (MIT, Caltech-AMBER/ambersim)
 and keeps what the dynamics need: links with their inertials, joints (origins, axes, limits, mimics), transmissions and the <mujoco>
 compiler block; the Barrett hand's 98 mesh geoms are dropped like in the shipped bh280.xml (4 MB of OBJ files stay in the reference), the
-pendulum keeps its primitive geoms. Run once in the build container:  python tools/make_urdf_fixtures.py /root/reference
+pendulum keeps its collision capsule (visual geoms carry no dynamics and are dropped). Run once in the build container:  python tools/make_urdf_fixtures.py /root/reference
 """
 import re
 import sys
@@ -18,7 +18,7 @@ for rel, drop_geoms in (("pendulum/pendulum.urdf", False), ("barrett_hand/bh280.
     root = ET.fromstring(text)
     for link in root.findall("link"):
         for el in list(link):
-            if el.tag not in ("inertial", "visual", "collision") or (drop_geoms and el.tag != "inertial"):
+            if el.tag not in ("inertial", "collision") or (drop_geoms and el.tag != "inertial"):  # visuals carry no dynamics
                 link.remove(el)
     comp = root.find("mujoco/compiler")
     if comp is not None and drop_geoms:

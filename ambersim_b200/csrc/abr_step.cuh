@@ -307,6 +307,12 @@ __device__ __forceinline__ void project_pt_onto_plane(const float* pt, const flo
   const float dist = v_dot(d, n);
   for (int i = 0; i < 3; i++) out[i] = pt[i] - dist * n[i];
 }
+// unit vector with one reciprocal square root (the separating-axis loops normalise three vectors per edge pair; a zero vector stays zero)
+__device__ __forceinline__ void v_unit3(float* x) {
+  const float ss = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
+  const float inv = (ss > 0.f) ? rsqrtf(ss) : 0.f;
+  x[0] *= inv; x[1] *= inv; x[2] *= inv;
+}
 // _clip_edge_to_planes against the side planes of the counter-clockwise polygon P (np corners, normal nrm): plane k passes through
 // corner k-1 with the outward normal (P[k] - P[k-1]) x nrm
 __device__ inline bool clip_edge_to_poly(const float* p0, const float* p1, const float* P, int np, const float* nrm, float* out0, float* out1) {
@@ -623,23 +629,28 @@ template <int G> __device__ void stage_collision(const Ctx& c) {
         to_world(p2, m2, VB + 3 * MI(edge_vert)[2 * (eb + j)], b0);
         to_world(p2, m2, VB + 3 * MI(edge_vert)[2 * (eb + j) + 1], b1);
         float db[3] = {b0[0] - b1[0], b0[1] - b1[1], b0[2] - b1[2]};
-        v_normalize(db, 3);
+        v_unit3(db);
 #pragma unroll 1
         for (int i = 0; i < nea; i++) {
-          float a0[3], a1[3];
-          to_world(p1, m1, VA + 3 * MI(edge_vert)[2 * (ea + i)], a0);
-          to_world(p1, m1, VA + 3 * MI(edge_vert)[2 * (ea + i) + 1], a1);
-          float da[3] = {a0[0] - a1[0], a0[1] - a1[1], a0[2] - a1[2]};
-          v_normalize(da, 3);
+          // the edge's direction needs the rotation only; its end points are placed in the world when the pair is a candidate
+          const float* la0 = VA + 3 * MI(edge_vert)[2 * (ea + i)]; const float* la1 = VA + 3 * MI(edge_vert)[2 * (ea + i) + 1];
+          const float dl[3] = {la0[0] - la1[0], la0[1] - la1[1], la0[2] - la1[2]};
+          float da[3];
+          rot_world(m1, dl, da);
+          v_unit3(da);
           float ax[3], sg;
           v_cross(da, db, ax);
           if (v_dot(ax, ax) < 1e-6f) continue;
-          v_normalize(ax, 3);
+          v_unit3(ax);
           const float d = axis_dist(ax, sg);
+          if (!(d < ebest + 1e-6f)) continue;
           // parallel edges tie on their common axis: the supporting pair (its own separation along the axis = the hulls') is taken
+          float a0[3], a1[3];
+          to_world(p1, m1, la0, a0);
+          to_world(p1, m1, la1, a1);
           const float ma[3] = {a0[0] + a1[0], a0[1] + a1[1], a0[2] + a1[2]}, mb[3] = {b0[0] + b1[0], b0[1] + b1[1], b0[2] + b1[2]};
           const float dpair = sg * 0.5f * (v_dot(ax, ma) - v_dot(ax, mb));
-          if (d < ebest - 1e-6f || (d < ebest + 1e-6f && dpair > epair)) {
+          if (d < ebest - 1e-6f || dpair > epair) {
             ebest = fminf(ebest, d); epair = dpair; esign = sg; ei = i; ej = j; eaxis[0] = ax[0]; eaxis[1] = ax[1]; eaxis[2] = ax[2];
           }
         }

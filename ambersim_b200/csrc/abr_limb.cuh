@@ -1128,11 +1128,29 @@ constexpr int kMaxTPB = ABR_LIMB_MAXTPB;  // largest CTA: 8 warps = every regist
 // cache, so every SM streams it from the GPC-level cache each step; the warps of one SM run in loose lockstep and share that
 // stream, while the SMs of a GPC compete for it. A small batch therefore runs faster on FEWER SMs with MORE warps each:
 // the per-GPC instruction traffic drops with the number of streaming SMs. ABR_LIMB_TPB overrides the policy (probes).
-inline int pick_tpb(long nwarps) {
+// The long-chain families (NL >= 6: the step spills and streams > 128 KB of code) run a wave of 7- / 6-warp CTAs in 0.955 / 0.94
+// of the time of a wave of 8-warp CTAs (one CTA per SM at 255 registers), so their launches take the CTA size that minimises
+// waves x time per wave. The model reproduces every point of profiles/r2_tpb_sweep3.txt to 2 % (C3: 2048 warps = 256 CTAs of 8
+// warps or 293 of 7, two waves either way: +4.4 %; 8192 warps: 7 waves of 8 beat 8 waves of 7). The Barkour class does not
+// follow it (its second, partial wave runs faster than a full one) and keeps 8 warps.
+constexpr int kNumSM = 148;  // B200
+inline int pick_tpb(long nwarps, int nl = 0) {
   const char* ev = getenv("ABR_LIMB_TPB");
   const int env = ev ? atoi(ev) : 0;
   if (env >= 32 && env <= kMaxTPB && env % 32 == 0) return env;
-  return nwarps <= 16 ? 128 : kMaxTPB;  // measured: profiles/r2_tpb_sweep*.txt (a handful of warps: one per sub-partition)
+  if (nwarps <= 16) return 128;  // measured: profiles/r2_tpb_sweep*.txt (a handful of warps: one per sub-partition)
+  if (nl >= 6 && kMaxTPB == 256) {
+    const int wpc[3] = {8, 7, 6};
+    const double per_wave[3] = {1.0, 0.955, 0.94};
+    int best = 8; double best_t = 1e30;
+    for (int i = 0; i < 3; i++) {
+      const long ctas = (nwarps + wpc[i] - 1) / wpc[i];
+      const double t = (double)((ctas + kNumSM - 1) / kNumSM) * per_wave[i];
+      if (t < best_t - 1e-9) { best_t = t; best = wpc[i]; }
+    }
+    return best * 32;
+  }
+  return kMaxTPB;
 }
 #ifndef ABR_LIMB_MINB
 #define ABR_LIMB_MINB 1  // resident CTAs per SM the register allocation must allow (1 = up to 255 registers)
@@ -1471,7 +1489,7 @@ __global__ void __launch_bounds__(kMaxTPB, ABR_LIMB_MINB) k_limb_env(const __gri
 template <int NL, int NC, class Args, class K> int launch_limb(K kern, const Layout& L, const Args& a, int nworld, int extra_floats, int extra_per_thread, cudaStream_t st) {
   constexpr Map mp{NL, NC};
   const long threads = (long)nworld << L.lg2G;
-  const int tpb = pick_tpb((threads + 31) / 32);
+  const int tpb = pick_tpb((threads + 31) / 32, NL);
   const size_t sm = sizeof(float) * ((size_t)mp.total() * kStride + extra_floats + (size_t)extra_per_thread * tpb);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * ((size_t)mp.total() * kStride + extra_floats + (size_t)extra_per_thread * kMaxTPB)));
   if (e != cudaSuccess) return (int)e;

@@ -329,6 +329,34 @@ def extra_configs(mj, m, cf, q0, torch, device, stream, L, peak_tf):
     return ex
 
 
+def _bind_near_gpu(index):
+    """Binds the calling thread to the CPU set NVML reports for GPU `index` (honouring CUDA_VISIBLE_DEVICES through the UUID);
+    returns the previous affinity mask, or None when NVML / sched_setaffinity is not available (then nothing changed)."""
+    try:
+        import pynvml
+        import torch
+
+        prev = os.sched_getaffinity(0)
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(index).uuid)
+        hnd = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        pynvml.nvmlDeviceSetCpuAffinity(hnd)
+        if not (os.sched_getaffinity(0) & prev):  # never leave the thread outside the mask the launcher gave it
+            os.sched_setaffinity(0, prev)
+            return None
+        return prev
+    except Exception:
+        return None
+
+
+def _unbind(prev):
+    if prev:
+        try:
+            os.sched_setaffinity(0, prev)
+        except Exception:
+            pass
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -450,8 +478,12 @@ def main():
 
     if not args.no_extra:
         # ---- e2e: host buffers through the C-ABI host entry point, copies inside the timed region
+        # the pinned pages are placed while this thread is bound to the CPUs next to its GPU (NVML's affinity mask), so that
+        # N ranks copying at once do not cross the socket interconnect; the binding is dropped again right after
+        near = _bind_near_gpu(device.index or 0)
         x0_h, us_h = x0.cpu().pin_memory(), us.cpu().pin_memory()
         costs_h = torch.empty(WORLDS, dtype=torch.float32).pin_memory()
+        _unbind(near)
         hp = lambda t: C.c_void_p(t.data_ptr())
 
         def e2e_step():
@@ -469,7 +501,8 @@ def main():
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         out["e2e"] = {"value": world * WORLDS * HORIZON * K / float(dt), "unit": "world-steps/s",
                       "h2d_bytes_per_step": int(us_h.numel() * 4 + x0_h.numel() * 4), "d2h_bytes_per_step": int(costs_h.numel() * 4),
-                      "api": "abr_rollout_host (pinned host buffers in, costs out)", "timer": "host wall clock around K calls"}
+                      "api": "abr_rollout_host (pinned host buffers in, costs out)", "timer": "host wall clock around K calls",
+                      "host_buffers": "pinned; allocated next to the GPU (NVML CPU affinity)" if near else "pinned"}
         out["e2e_matches_device"] = bool(torch.equal(costs_h.to(device), costs))
 
         sharded = None

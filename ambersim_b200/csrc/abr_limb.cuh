@@ -1494,6 +1494,16 @@ template <int NL, int NC, class Args, class K> int launch_limb(K kern, const Lay
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * ((size_t)mp.total() * kStride + extra_floats + (size_t)extra_per_thread * kMaxTPB)));
   if (e != cudaSuccess) return (int)e;
   const int grid = (int)((threads + tpb - 1) / tpb);
+  static const int cl = [] { const char* e = getenv("ABR_LIMB_CLUSTER"); return e ? atoi(e) : 0; }();  // probe: co-scheduled CTA groups
+  if (cl > 1 && cl <= 8) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((grid + cl - 1) / cl * cl)); cfg.blockDim = dim3((unsigned)tpb); cfg.dynamicSmemBytes = sm; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kern, L, a);
+    return e != cudaSuccess ? (int)e : (int)cudaGetLastError();
+  }
   kern<<<grid, tpb, sm, st>>>(L, a);
   return (int)cudaGetLastError();
 }

@@ -88,21 +88,35 @@ __device__ __forceinline__ float gall(float x, int lg) { return gs(x, lg, lg); }
 
 // 1/x as the bare MUFU.RCP (about 1 ulp): the operands here (clamped pivots, impedances in (0,1), regularisers >= mjMINVAL,
 // line-search curvatures) never reach the magnitudes whose scaling fix-ups make the compiler's `1.f / x` nine instructions long
+// ABR_PRECISE_MATH (`make precise`): correctly rounded reciprocal / square root and libdevice's sincosf instead, to measure what the
+// fast forms change and cost (tools/precise_vs_fast.py, profiles/r2_precise_math.txt)
 __device__ __forceinline__ float rcp_fast(float x) {
+#ifdef ABR_PRECISE_MATH
+  return __frcp_rn(x);
+#else
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
+#endif
 }
 __device__ __forceinline__ float sqrt_fast(float x) {
+#ifdef ABR_PRECISE_MATH
+  return __fsqrt_rn(x);
+#else
   float r;
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
+#endif
 }
 __device__ __forceinline__ float safe_div_fast(float a, float b) { return a * rcp_fast(b + ((b == 0.f) ? kMinVal : 0.f)); }
 
 // sin/cos with a three-constant Cody-Waite reduction and Cephes minimax polynomials (about 1 ulp for
 // |x| < 1e5): branch-free, so the straight-line step carries no Payne-Hanek slow path per call site.
 __device__ __forceinline__ void sincos_bf(float x, float& sn, float& cs) {
+#ifdef ABR_PRECISE_MATH
+  sincosf(x, &sn, &cs);
+  return;
+#endif
   const float j = rintf(x * 0.636619772367581343f);
   float r = fmaf(-j, 1.57079625129699707031f, x);
   r = fmaf(-j, 7.54978941586159635335e-08f, r);

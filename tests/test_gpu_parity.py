@@ -1272,7 +1272,7 @@ def test_limb_kernels_are_bit_identical_across_cta_sizes(load_model, monkeypatch
         mj, m, _ = model_with(load_model, name)
         nx = mj.nq + mj.nv
         rng = np.random.default_rng(9)
-        W, N = 100, 12
+        W, N = 300, 12  # 38 warps: the policy itself (tpb None) picks 6-warp CTAs for the biped class, 8-warp CTAs for Barkour
         x0 = np.tile(np.concatenate([mj.key_qpos(key), np.zeros(mj.nv)]), (W, 1))
         x0[:, 7:mj.nq] += rng.uniform(-0.05, 0.05, (W, mj.nq - 7))
         us = mj.key_ctrl(key) + 0.1 * rng.standard_normal((W, N, mj.nu))
@@ -1280,8 +1280,11 @@ def test_limb_kernels_are_bit_identical_across_cta_sizes(load_model, monkeypatch
         ps = VanillaPredictiveSampler(model=m, cost_function=cf, nsamples=300, stdev=0.1)
         prm = VanillaPredictiveSamplerParams(key=1, x0=t32(x0[0]), us_guess=t32(us[0]))
         out = []
-        for tpb in ("32", "96", "256"):
-            monkeypatch.setenv("ABR_LIMB_TPB", tpb)
+        for tpb in ("32", "96", "192", "224", "256", None):
+            if tpb is None:
+                monkeypatch.delenv("ABR_LIMB_TPB", raising=False)
+            else:
+                monkeypatch.setenv("ABR_LIMB_TPB", tpb)
             out.append((shoot(m, t32(x0), t32(us)), shoot_cost(m, t32(x0), t32(us), cf), *ps.optimize(prm)))
         for o in out[1:]:
             assert all(torch.equal(a, b) for a, b in zip(out[0], o))

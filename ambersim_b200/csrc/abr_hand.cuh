@@ -248,7 +248,7 @@ template <int NL> __device__ __forceinline__ void forward(Lane<NL>& s, const Cfg
     const float pos = gall(part, lg) - data[0];  // polycoef[0] once per row
     jvel = gall(jvel, lg);
     float D, aref;
-    row_kbi<false>(&HTF(mp.eq(r)), pos, jvel, HTF(mp.eq(r) + 7), valid, D, aref);
+    row_kbi<false, kStride>(&HTF(mp.eq(r)), pos, jvel, HTF(mp.eq(r) + 7), valid, D, aref);
     eD[r] = D; earef[r] = aref;
   }
   float lD[NL], laref[NL], lsg[NL];
@@ -261,7 +261,7 @@ template <int NL> __device__ __forceinline__ void forward(Lane<NL>& s, const Cfg
     const bool active = (pos < 0.f) && (jflags[d] & kJLimited);
     const float sg = (dmin < dmax) ? 1.f : -1.f;
     lsg[d] = active ? sg : 0.f;
-    row_kbi<false>(&HTF(mp.jnt(p) + 14), pos, sg * s.v[d], HTF(mp.jnt(p) + 14 + 7), active, lD[d], laref[d]);
+    row_kbi<false, kStride>(&HTF(mp.jnt(p) + 14), pos, sg * s.v[d], HTF(mp.jnt(p) + 14 + 7), active, lD[d], laref[d]);
   }
   // ---------------------------------------------------------------- solver.solve (Newton)
   // state of a point: x, M x (local), limit residuals (local), equality residuals (replicated)

@@ -31,10 +31,15 @@ namespace limb {
 
 // ---- per-lane model table: word (slot, lane) lives at T[slot * kStride + lane]
 constexpr int kStride = 8;  // max lanes per world
+// In shared memory the table is lane-major: word (slot, lane) at S[lane * tpad(total) + slot], every lane's column 16-byte aligned and
+// every block of Map a multiple of 4 words, so that neighbouring slots load as LDS.64 / LDS.128; tpad = 4 (mod 32) keeps the columns of up
+// to 8 lanes on disjoint banks.
+constexpr int kLS = 1;  // slot stride in shared memory
+__host__ __device__ constexpr int tpad(int total) { return ((total - 4 + 31) / 32) * 32 + 4; }
 constexpr int kBodyW = 24;  // anchor in the parent frame (body_pos + R(body_quat) jnt_pos)3 | body_quat4 | body_ipos3 | body_quat o (0, jnt_axis)4 |
                             // mass | inertia tensor in the body frame (xx yy zz xy xz yz)6 | joint axis in the parent frame3
-constexpr int kJntW = 35;   // jnt_pos3 jnt_axis3 qpos0 qpos_spring stiffness damping armature range2 margin | limit prm[10] | act prm[11]
-constexpr int kConW = 33;   // geom_pos3 radius | con prm[14] | plane normal3 point3 frame9
+constexpr int kJntW = 36;   // jnt_pos3 jnt_axis3 qpos0 qpos_spring stiffness damping armature range2 margin | limit prm[10] | act prm[11]
+constexpr int kConW = 36;   // geom_pos3 radius | con prm[14] | plane normal3 point3 frame9
 constexpr int kJntI = 4;    // flags, global dof, global qpos adr, global actuator
 constexpr int kConI = 2;    // local body position of the sphere (-1 = empty slot), condim
 struct Map {
@@ -313,31 +318,31 @@ template <int LGC> struct LaneCfg {
   int iterations, ls_iterations, disableflags, nefc, nv;
 };
 
-#define LTF(slot) (C.T[(slot) * kStride])
-#define LTI(slot) (__float_as_int(C.T[(slot) * kStride]))
+#define LTF(slot) (C.T[(slot) * kLS])
+#define LTI(slot) (__float_as_int(C.T[(slot) * kLS]))
 
 // kbi: impedance, D and aref of one active row (constraint._kbi / _row in SURVEY App. A.7), split so that the four pyramid
 // rows of a contact (same penetration, same solref / solimp) evaluate the impedance once
 struct Kbi { float b, kip, g; };  // damping b, stiffness * impedance * pos, (1 - imp) / imp
-template <bool POW2> __device__ __forceinline__ Kbi kbi_imp(const float* prm /* smem, stride kStride */, float pos) {
-  const float k = prm[0 * kStride], dmin = prm[2 * kStride], dmax = prm[3 * kStride];
-  const float iw = prm[4 * kStride], mid = prm[5 * kStride];
+template <bool POW2, int ST = kLS> __device__ __forceinline__ Kbi kbi_imp(const float* prm /* smem, slot stride ST (the hand tables: kStride) */, float pos) {
+  const float k = prm[0 * ST], dmin = prm[2 * ST], dmax = prm[3 * ST];
+  const float iw = prm[4 * ST], mid = prm[5 * ST];
   const float x = fabsf(pos) * iw;
   float ia, ib;
   if (POW2) {
     ia = x * x; const float t = 1.f - x; ib = t * t;
   } else {
-    const float power = prm[6 * kStride];
+    const float power = prm[6 * ST];
     if (power == 2.f) { ia = x * x; const float t = 1.f - x; ib = t * t; }
     else if (power == 1.f) { ia = x; ib = 1.f - x; }
     else { ia = pow_cold(x, power); ib = pow_cold(1.f - x, power); }
   }
-  const float y = (x < mid) ? prm[8 * kStride] * ia : 1.f - prm[9 * kStride] * ib;
+  const float y = (x < mid) ? prm[8 * ST] * ia : 1.f - prm[9 * ST] * ib;
   float imp = dmin + y * (dmax - dmin);
   imp = fminf(fmaxf(imp, dmin), dmax);
   if (x > 1.f) imp = dmax;
   Kbi o;
-  o.b = prm[1 * kStride]; o.kip = k * imp * pos; o.g = (1.f - imp) * rcp_fast(imp);
+  o.b = prm[1 * ST]; o.kip = k * imp * pos; o.g = (1.f - imp) * rcp_fast(imp);
   return o;
 }
 __device__ __forceinline__ void kbi_row(const Kbi& q, float jvel, float invw, bool active, float& D, float& aref) {
@@ -345,8 +350,8 @@ __device__ __forceinline__ void kbi_row(const Kbi& q, float jvel, float invw, bo
   D = active ? rcp_fast(R) : 0.f;
   aref = active ? -q.b * jvel - q.kip : 0.f;
 }
-template <bool POW2> __device__ __forceinline__ void row_kbi(const float* prm, float pos, float jvel, float invw, bool active, float& D, float& aref) {
-  kbi_row(kbi_imp<POW2>(prm, pos), jvel, invw, active, D, aref);
+template <bool POW2, int ST = kLS> __device__ __forceinline__ void row_kbi(const float* prm, float pos, float jvel, float invw, bool active, float& D, float& aref) {
+  kbi_row(kbi_imp<POW2, ST>(prm, pos), jvel, invw, active, D, aref);
 }
 
 struct LSP { float alpha, d0, d1, q1, q2; };  // the point's cost is alpha^2 q2 + alpha q1 + q0(alpha): q0 is only summed for the points whose cost is read
@@ -754,15 +759,15 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
           const float* prm = &LTF(mp.jnt(p) + 24);
           const int af = fl >> kJActShift;
           float ct = s.ctrl[p - 1];
-          if ((af & 1) && !(C.disableflags & ABR_DSBL_CLAMPCTRL)) ct = fminf(fmaxf(ct, prm[0]), prm[1 * kStride]);
-          const float gear = prm[10 * kStride];
+          if ((af & 1) && !(C.disableflags & ABR_DSBL_CLAMPCTRL)) ct = fminf(fmaxf(ct, prm[0]), prm[1 * kLS]);
+          const float gear = prm[10 * kLS];
           const float len = q * gear, vel = s.v[d] * gear;
-          float gain = prm[4 * kStride];
-          if (af & 4) gain += prm[5 * kStride] * len + prm[6 * kStride] * vel;
+          float gain = prm[4 * kLS];
+          if (af & 4) gain += prm[5 * kLS] * len + prm[6 * kLS] * vel;
           float bs = 0.f;
-          if (af & 8) bs = prm[7 * kStride] + prm[8 * kStride] * len + prm[9 * kStride] * vel;
+          if (af & 8) bs = prm[7 * kLS] + prm[8 * kLS] * len + prm[9 * kLS] * vel;
           float af_ = (gain * ct + bs) * C.acs;
-          if (af & 2) af_ = fminf(fmaxf(af_, prm[2 * kStride]), prm[3 * kStride]);
+          if (af & 2) af_ = fminf(fmaxf(af_, prm[2 * kLS]), prm[3 * kLS]);
           af_ *= gear;
           t += ((fl & kJAct) && act_on) ? af_ : 0.f;
         }
@@ -874,7 +879,7 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
 #pragma unroll
     for (int c = 0; c < NC; c++) {
       const float* prm = &LTF(mp.con(c) + 4);
-      const float pos = cdist[c] - prm[13 * kStride];
+      const float pos = cdist[c] - prm[13 * kLS];
       const bool act0 = (pos < 0.f) && (LTI(mp.icon(c)) >= 0);
       const bool pyr = LTI(mp.icon(c) + 1) == 3;
       const Kbi kq = kbi_imp<Spec<SPEC>::pow2>(prm, pos);
@@ -883,9 +888,9 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
         const int r = NL + 4 * c + sub;
         const float mu = (sub < 2) ? R.mu1[c] : R.mu2[c];
         const float jvel = bva[c][0] + ((sub & 1) ? -mu : mu) * bva[c][1 + (sub >> 1)];
-        float invw = (sub < 2 || !pyr) ? prm[7 * kStride] : prm[10 * kStride];
+        float invw = (sub < 2 || !pyr) ? prm[7 * kLS] : prm[10 * kLS];
         if (pyr && C.frs != 1.f) {  // the pyramid's invweight is t (1 + mu^2) 2 mu^2 / impratio: rescale it with the friction
-          const float mu0 = prm[(sub < 2 ? 11 : 12) * kStride];
+          const float mu0 = prm[(sub < 2 ? 11 : 12) * kLS];
           invw *= C.frs * C.frs * (1.f + mu * mu) / (1.f + mu0 * mu0);
         }
         kbi_row(kq, jvel, invw, act0 && (pyr || sub == 0), R.D[r], R.aref[r]);
@@ -1173,7 +1178,7 @@ inline int pick_tpb(long nwarps, int nl = 0) {
 template <int NL, int NC, int LGC, int SPEC = -1> __device__ __forceinline__ LaneCfg<LGC> make_cfg(const Layout& L, const float* T, int g) {
   constexpr Map mp{NL, NC};
   LaneCfg<LGC> C;
-  C.T = T + g;
+  C.T = (const float*)__builtin_assume_aligned(T + g * tpad(mp.total()), 16);
   C.S.own = LTI(mp.ish()); C.S.lvl = LTI(mp.ish() + 1); C.S.mx = L.l_mx; C.S.lg_ = L.lg2G;
   C.dt = L.timestep; C.grav[0] = L.gravity[0]; C.grav[1] = L.gravity[1]; C.grav[2] = L.gravity[2];
   C.frs = 1.f; C.acs = 1.f; C.dps = 1.f; C.ars = 1.f;
@@ -1244,8 +1249,9 @@ __global__ void __launch_bounds__(kMaxTPB, ABR_LIMB_MINB) k_limb_rollout(const _
   constexpr int N = 6 + NL, NTRI = N * (N + 1) / 2;
   const int ntab = mp.total() * kStride;
   const int nx = L.nx, nu = L.nu, nq = L.nq, Nh = A.N;
-  for (int i = threadIdx.x; i < ntab; i += blockDim.x) smem[i] = A.blob[L.f_ltab + i];
-  float* cqd = smem + ntab; float* cqf = cqd + nx; float* crd = cqf + nx; float* cxg = crd + nu;
+  constexpr int TOTP = tpad(mp.total());
+  for (int i = threadIdx.x; i < ntab; i += blockDim.x) smem[(i % kStride) * TOTP + i / kStride] = A.blob[L.f_ltab + i];
+  float* cqd = smem + TOTP * kStride; float* cqf = cqd + nx; float* crd = cqf + nx; float* cxg = crd + nu;
   if (A.cost.enabled) {
     for (int i = threadIdx.x; i < nx; i += blockDim.x) { cqd[i] = A.cost.qd[i]; cqf[i] = A.cost.qfd[i]; cxg[i] = A.cost.xg[i]; }
     for (int i = threadIdx.x; i < nu; i += blockDim.x) crd[i] = A.cost.rd[i];
@@ -1395,7 +1401,8 @@ __global__ void __launch_bounds__(kMaxTPB, ABR_LIMB_MINB) k_limb_env(const __gri
   constexpr int N = 6 + NL, NTRI = N * (N + 1) / 2;
   const int ntab = mp.total() * kStride;
   const int nu = L.nu, nq = L.nq, nv = L.nv;
-  for (int i = threadIdx.x; i < ntab; i += blockDim.x) smem[i] = A.blob[L.f_ltab + i];
+  constexpr int TOTP = tpad(mp.total());
+  for (int i = threadIdx.x; i < ntab; i += blockDim.x) smem[(i % kStride) * TOTP + i / kStride] = A.blob[L.f_ltab + i];
   __syncthreads();
   const int lg = (LGC >= 0) ? (LGC & 3) : L.lg2G;
   const int g = threadIdx.x & ((1 << lg) - 1);
@@ -1504,8 +1511,8 @@ template <int NL, int NC, class Args, class K> int launch_limb(K kern, const Lay
   constexpr Map mp{NL, NC};
   const long threads = (long)nworld << L.lg2G;
   const int tpb = pick_tpb((threads + 31) / 32, NL);
-  const size_t sm = sizeof(float) * ((size_t)mp.total() * kStride + extra_floats + (size_t)extra_per_thread * tpb);
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * ((size_t)mp.total() * kStride + extra_floats + (size_t)extra_per_thread * kMaxTPB)));
+  const size_t sm = sizeof(float) * ((size_t)tpad(mp.total()) * kStride + extra_floats + (size_t)extra_per_thread * tpb);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * ((size_t)tpad(mp.total()) * kStride + extra_floats + (size_t)extra_per_thread * kMaxTPB)));
   if (e != cudaSuccess) return (int)e;
   const int grid = (int)((threads + tpb - 1) / tpb);
   static const int cl = [] { const char* e = getenv("ABR_LIMB_CLUSTER"); return e ? atoi(e) : 0; }();  // probe: co-scheduled CTA groups

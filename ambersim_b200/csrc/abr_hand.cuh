@@ -397,7 +397,7 @@ template <int NL> __device__ __forceinline__ void forward(Lane<NL>& s, const Cfg
       la0[d] = 0.5f * ja * ja * Dr; la1[d] = w * ja * Dr; la2[d] = 0.5f * w * w * Dr;
     }
 #define HLS_EVAL(al) ls_eval<NL, 0>(Jl, jvl, la1, la2, (al), qg1, qg2, lg)
-    const LSP p0 = HLS_EVAL(0.f);
+    const LSP p0 = ls_eval<NL, 0, true>(Jl, jvl, la1, la2, 0.f, qg1, qg2, lg);
     const LSP l0 = HLS_EVAL(-safe_div_fast(p0.d0, p0.d1));
     const bool lesser = l0.d0 < p0.d0;
     LSP hi = lesser ? p0 : l0;
@@ -427,7 +427,7 @@ template <int NL> __device__ __forceinline__ void forward(Lane<NL>& s, const Cfg
       }
     }
 #undef HLS_EVAL
-    const float c_p0 = ls_cost<NL, 0>(Jl, jvl, la0, p0, qg0, lg), c_lo = ls_cost<NL, 0>(Jl, jvl, la0, lo, qg0, lg), c_hi = ls_cost<NL, 0>(Jl, jvl, la0, hi, qg0, lg);
+    const float c_p0 = ls_cost<NL, 0, true>(Jl, jvl, la0, p0, qg0, lg), c_lo = ls_cost<NL, 0>(Jl, jvl, la0, lo, qg0, lg), c_hi = ls_cost<NL, 0>(Jl, jvl, la0, hi, qg0, lg);
     const bool improved = (c_lo < c_p0) || (c_hi < c_p0);
     const float alpha = (improved && live) ? ((c_lo < c_hi) ? lo.alpha : hi.alpha) : 0.f;
 #pragma unroll

@@ -162,6 +162,13 @@ template <int N> __device__ __forceinline__ void cdof_axpy(const float (&cdof)[N
 #pragma unroll
   for (int i = 0; i < 6; i++) V[i] = fmaf(cdof[d][i], x, V[i]);
 }
+// inert_mul(I, [0 | v_lin]): the products with the exact zeros of the angular part dropped
+__device__ __forceinline__ void inert_mul_lin(const float* I, const float* v, float* r) {
+  r[0] = fmaf(-I[8], v[4], I[7] * v[5]);
+  r[1] = fmaf(-I[6], v[5], I[8] * v[3]);
+  r[2] = fmaf(-I[7], v[3], I[6] * v[4]);
+  r[3] = I[9] * v[3]; r[4] = I[9] * v[4]; r[5] = I[9] * v[5];
+}
 // inert_mul(I, e_{3+q}): the momentum of a unit translation along axis q
 __device__ __forceinline__ void inert_mul_unit(const float* I, int q, float* r) {
   // cross(I + 6, e_q) with the zero products dropped
@@ -266,6 +273,7 @@ template <int N, class SH> __device__ __forceinline__ void mul_m(const float (&M
     float u = 0.f;
 #pragma unroll
     for (int j = 0; j < N; j++) {
+      if (i < 3 && j < 3 && i != j) continue;  // the translational block of M is m * identity: exact zeros off its diagonal
       if (j <= i) lo = fmaf(M[TR(i, j)], x[j], lo);
       else if (PD(j) == PD(i)) lo = fmaf(M[TR(j, i)], x[j], lo);
       else u += S.o(PD(j)) ? M[TR(j, i)] * x[j] : 0.f;
@@ -435,27 +443,29 @@ template <int NL, int NC, bool CB, class SH, bool AT_AS = false> __device__ __fo
 // coefficients 0.5 D ja^2, D ja jv, 0.5 D jv^2 (a row counts while ja + alpha jv < 0).
 // Rows below R0 are skipped: the caller passes R0 = NL when no lane of the warp has an active joint-limit row (their
 // coefficients are exact zeros then, so the sums are the same numbers).
-template <int NR, int R0> __device__ __forceinline__ LSP ls_eval(const float (&Jaref)[NR], const float (&jv)[NR], const float (&a1)[NR],
+// Z: the point alpha = 0 (the products with that exact zero, which the compiler may not fold, are left out).
+template <int NR, int R0, bool Z = false> __device__ __forceinline__ LSP ls_eval(const float (&Jaref)[NR], const float (&jv)[NR], const float (&a1)[NR],
                                                          const float (&a2)[NR], float alpha, float qg1, float qg2, int lg) {
   float q1 = 0.f, q2 = 0.f;
 #pragma unroll
   for (int r = R0; r < NR; r++) {
-    if (fmaf(alpha, jv[r], Jaref[r]) < 0.f) { q1 += a1[r]; q2 += a2[r]; }  // predicated adds, no selects
+    if ((Z ? Jaref[r] : fmaf(alpha, jv[r], Jaref[r])) < 0.f) { q1 += a1[r]; q2 += a2[r]; }  // predicated adds, no selects
   }
   q1 = gall(q1, lg) + qg1; q2 = gall(q2, lg) + qg2;
   LSP pt;
-  pt.alpha = alpha; pt.q1 = q1; pt.q2 = q2;
-  pt.d0 = 2.f * alpha * q2 + q1;
+  pt.alpha = Z ? 0.f : alpha; pt.q1 = q1; pt.q2 = q2;
+  pt.d0 = Z ? q1 : 2.f * alpha * q2 + q1;
   pt.d1 = 2.f * q2 + ((q2 == 0.f) ? kMinVal : 0.f);
   return pt;
 }
 // the cost of a point (the loop's decisions only read d0 / d1, so q0 is summed for the three points whose cost is compared)
-template <int NR, int R0> __device__ __forceinline__ float ls_cost(const float (&Jaref)[NR], const float (&jv)[NR], const float (&a0)[NR], const LSP& pt, float qg0, int lg) {
+template <int NR, int R0, bool Z = false> __device__ __forceinline__ float ls_cost(const float (&Jaref)[NR], const float (&jv)[NR], const float (&a0)[NR], const LSP& pt, float qg0, int lg) {
   float q0 = 0.f;
 #pragma unroll
   for (int r = R0; r < NR; r++)
-    if (fmaf(pt.alpha, jv[r], Jaref[r]) < 0.f) q0 += a0[r];
+    if ((Z ? Jaref[r] : fmaf(pt.alpha, jv[r], Jaref[r])) < 0.f) q0 += a0[r];
   q0 = gall(q0, lg) + qg0;
+  if (Z) return q0;
   return pt.alpha * pt.alpha * pt.q2 + pt.alpha * pt.q1 + q0;
 }
 
@@ -470,7 +480,7 @@ template <int NR, int R0> __device__ __forceinline__ float line_search(const flo
     la0[r] = 0.5f * ja * ja * Dr; la1[r] = w * ja * Dr; la2[r] = 0.5f * w * w * Dr;
   }
 #define LS_EVAL(al) ls_eval<NR, R0>(Jaref, jv, la1, la2, (al), qg1, qg2, lg)
-  const LSP p0 = LS_EVAL(0.f);
+  const LSP p0 = ls_eval<NR, R0, true>(Jaref, jv, la1, la2, 0.f, qg1, qg2, lg);
   const LSP l0 = LS_EVAL(-safe_div_fast(p0.d0, p0.d1));
   const bool lesser = l0.d0 < p0.d0;
   LSP hi = lesser ? p0 : l0;
@@ -500,7 +510,7 @@ template <int NR, int R0> __device__ __forceinline__ float line_search(const flo
     }
   }
 #undef LS_EVAL
-  const float c_p0 = ls_cost<NR, R0>(Jaref, jv, la0, p0, qg0, lg), c_lo = ls_cost<NR, R0>(Jaref, jv, la0, lo, qg0, lg), c_hi = ls_cost<NR, R0>(Jaref, jv, la0, hi, qg0, lg);
+  const float c_p0 = ls_cost<NR, R0, true>(Jaref, jv, la0, p0, qg0, lg), c_lo = ls_cost<NR, R0>(Jaref, jv, la0, lo, qg0, lg), c_hi = ls_cost<NR, R0>(Jaref, jv, la0, hi, qg0, lg);
   const bool improved = (c_lo < c_p0) || (c_hi < c_p0);
   return (improved && live) ? ((c_lo < c_hi) ? lo.alpha : hi.alpha) : 0.f;
 }
@@ -703,8 +713,13 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
 #pragma unroll
       for (int i = 0; i < 6; i++) cdd[q][i] = 0.f;
     }
+    // cv is a pure translation here, so motion_cross(cv, cdof[q]) = [0 | v_lin x axis_q]: the products with cv's exact zeros
+    // (which the compiler may not fold) are dropped, as are the updates of ca's angular part by them
 #pragma unroll
-    for (int q = 3; q < 6; q++) motion_cross(cv, cdof[q], cdd[q]);
+    for (int q = 3; q < 6; q++) {
+      cdd[q][0] = 0.f; cdd[q][1] = 0.f; cdd[q][2] = 0.f;
+      v_cross(cv + 3, cdof[q], cdd[q] + 3);
+    }
 #pragma unroll
     for (int q = 3; q < 6; q++)
 #pragma unroll
@@ -712,7 +727,7 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
 #pragma unroll
     for (int q = 3; q < 6; q++)
 #pragma unroll
-      for (int i = 0; i < 6; i++) ca[i] = fmaf(cdd[q][i], s.v[q], ca[i]);
+      for (int i = 3; i < 6; i++) ca[i] = fmaf(cdd[q][i], s.v[q], ca[i]);
 #pragma unroll
     for (int p = 0; p < NP; p++) {
       if (p > 0) {
@@ -725,7 +740,7 @@ __device__ __forceinline__ void forward(Lane<NL, NC>& s, const LaneCfg<LGC>& C, 
 #pragma unroll
       for (int i = 0; i < 6; i++) cvel[p][i] = cv[i];
       float f1[6], f2[6], f3[6];
-      inert_mul(cinert[p], ca, f1);
+      if (p == 0) inert_mul_lin(cinert[p], ca, f1); else inert_mul(cinert[p], ca, f1);  // the trunk's ca has no angular part
       inert_mul(cinert[p], cv, f2);
       motion_cross_force(cv, f2, f3);
 #pragma unroll

@@ -1166,7 +1166,7 @@ constexpr int kMaxTPB = ABR_LIMB_MAXTPB;  // largest CTA: 8 warps = every regist
 // of the time of a wave of 8-warp CTAs (one CTA per SM at 255 registers), so their launches take the CTA size that minimises
 // waves x time per wave. The model reproduces every point of profiles/r2_tpb_sweep3.txt to 2 % (C3: 2048 warps = 256 CTAs of 8
 // warps or 293 of 7, two waves either way: +4.4 %; 8192 warps: 7 waves of 8 beat 8 waves of 7). The Barkour class does not
-// follow it (its second, partial wave runs faster than a full one) and keeps 8 warps.
+// follow it (its second, partial wave runs faster than a full one) and keeps 8 warps beyond 518 warps (7 below: see the end of pick_tpb).
 constexpr int kNumSM = 148;  // B200
 inline int pick_tpb(long nwarps, int nl = 0) {
   const char* ev = getenv("ABR_LIMB_TPB");
@@ -1184,6 +1184,9 @@ inline int pick_tpb(long nwarps, int nl = 0) {
     }
     return best * 32;
   }
+  // short-chain families, a single wave: 7-warp CTAs run 1 - 1.8 % faster than 8-warp ones (profiles/r2_tpb_sweep4.txt: 2048 / 3072 /
+  // 4096 worlds of the Barkour class; from 8192 worlds = 1024 warps on, 8 warps win again)
+  if (kMaxTPB == 256 && nwarps <= 7L * kNumSM / 2) return 224;
   return kMaxTPB;
 }
 #ifndef ABR_LIMB_MINB

@@ -40,7 +40,7 @@ NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
 # the kernels as shipped (round 2: `ncu ... -k regex:k_limb_rollout --launch-skip 3 -c 1 python bench.py --steps 2 --warmup 3 --no-extra`,
 # profiles/r2_c2_final_summary.txt): 197.44 MB read + 3.83 MB written vs 197.23 MB algorithmic (the controls). A profiler capture,
 # not a live counter of the run that prints it: `roofline.traffic_source` says so.
-NCU_DRAM_BYTES_C2 = 197_443_328 + 3_826_688
+NCU_DRAM_BYTES_C2 = 197_409_536 + 3_629_312  # dram__bytes_read.sum + dram__bytes_write.sum of the C2 launch (profiles/r2_c2_final2_summary.txt)
 
 
 def peaks():
@@ -446,7 +446,11 @@ def main():
         e1.record(stream)
         barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+    ms_by_rank = None
     if world > 1:
+        parts = [torch.zeros_like(ms) for _ in range(world)]  # every rank's own device time: shows which GPU sets the max
+        dist.all_gather(parts, ms)
+        ms_by_rank = [float(p) / K for p in parts]
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms)
     ms_per_step = ms_total / K
@@ -457,6 +461,8 @@ def main():
            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
            "data": "synthetic", "config": config, "clocks": clk.summary(), "gpu_launches": K, "costs_finite": finite}
     out["config"]["lanes_per_world"] = args.lanes or "auto"
+    if ms_by_rank is not None:
+        out["ms_per_step_by_rank"] = ms_by_rank
 
     # ---- roofline of the one dominant kernel (k_rollout): FP32 FMA pipe, not HBM and not tensor cores
     pk, pk_kind = peaks()
@@ -467,7 +473,7 @@ def main():
     alg_bytes = WORLDS * HORIZON * mj.nu * 4 + WORLDS * (mj.nq + mj.nv) * 4 + WORLDS * 4
     out["roofline"] = {"bound": "fp32", "achieved": achieved_tf, "peak": tf.value, "unit": "TFLOP/s", "frac": achieved_tf / tf.value,
                        "traffic": NCU_DRAM_BYTES_C2 if not args.lanes else None, "traffic_unit": "bytes per launch (ncu dram read+write)",
-                       "traffic_source": "profiles/r2_c2_final_summary.txt: ncu --set full capture of this launch (same command, kernels as shipped), not measured live",
+                       "traffic_source": "profiles/r2_c2_final2_summary.txt: ncu --set full capture of this launch (same command, kernels as shipped), not measured live",
                        "peak_kind": "FFMA microkernel timed in this run (abr_ffma_peak)",
                        "peak_nominal": NOMINAL_FP32_TFLOPS, "frac_of_nominal": achieved_tf / NOMINAL_FP32_TFLOPS,
                        "flop_per_world_step": F_WS,

@@ -1272,7 +1272,7 @@ def test_limb_kernels_are_bit_identical_across_cta_sizes(load_model, monkeypatch
         mj, m, _ = model_with(load_model, name)
         nx = mj.nq + mj.nv
         rng = np.random.default_rng(9)
-        W, N = 300, 12  # 38 warps: the policy itself (tpb None) picks 6-warp CTAs for the biped class, 8-warp CTAs for Barkour
+        W, N = 300, 12  # 38 warps: the policy itself (tpb None) picks 6-warp CTAs for the biped class, 7-warp CTAs for Barkour (single wave)
         x0 = np.tile(np.concatenate([mj.key_qpos(key), np.zeros(mj.nv)]), (W, 1))
         x0[:, 7:mj.nq] += rng.uniform(-0.05, 0.05, (W, mj.nq - 7))
         us = mj.key_ctrl(key) + 0.1 * rng.standard_normal((W, N, mj.nu))

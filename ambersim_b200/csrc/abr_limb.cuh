@@ -1275,6 +1275,9 @@ __global__ void __launch_bounds__(kMaxTPB, ABR_LIMB_MINB) k_limb_rollout(const _
     for (int i = threadIdx.x; i < nu; i += blockDim.x) crd[i] = A.cost.rd[i];
   }
   __syncthreads();
+#ifdef ABR_PROBE_SKEW  // probe: the second warp of each sub-partition starts ABR_PROBE_SKEW cycles late (one-off, no per-step cost)
+  if ((threadIdx.x >> 5) & 4) { const long long t0 = clock64(); while (clock64() - t0 < (long long)(ABR_PROBE_SKEW)) {} }
+#endif
   const int lg = (LGC >= 0) ? (LGC & 3) : L.lg2G;
   const int g = threadIdx.x & ((1 << lg) - 1);
   const int wraw = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> lg);

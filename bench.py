@@ -40,7 +40,7 @@ NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
 # the kernels as shipped (round 2: `ncu ... -k regex:k_limb_rollout --launch-skip 3 -c 1 python bench.py --steps 2 --warmup 3 --no-extra`,
 # profiles/r2_c2_final_summary.txt): 197.44 MB read + 3.83 MB written vs 197.23 MB algorithmic (the controls). A profiler capture,
 # not a live counter of the run that prints it: `roofline.traffic_source` says so.
-NCU_DRAM_BYTES_C2 = 197_477_632 + 3_521_792  # dram__bytes_read.sum + dram__bytes_write.sum of the C2 launch (profiles/r2_c2_final3_summary.txt)
+NCU_DRAM_BYTES_C2 = 197_432_320 + 4_168_448  # dram__bytes_read.sum + dram__bytes_write.sum of the C2 launch (profiles/r2_c2_final4_summary.txt)
 
 
 def peaks():
@@ -473,7 +473,7 @@ def main():
     alg_bytes = WORLDS * HORIZON * mj.nu * 4 + WORLDS * (mj.nq + mj.nv) * 4 + WORLDS * 4
     out["roofline"] = {"bound": "fp32", "achieved": achieved_tf, "peak": tf.value, "unit": "TFLOP/s", "frac": achieved_tf / tf.value,
                        "traffic": NCU_DRAM_BYTES_C2 if not args.lanes else None, "traffic_unit": "bytes per launch (ncu dram read+write)",
-                       "traffic_source": "profiles/r2_c2_final3_summary.txt: ncu --set full capture of this launch (same command, kernels as shipped), not measured live",
+                       "traffic_source": "profiles/r2_c2_final4_summary.txt: ncu --set full capture of this launch (same command, kernels as shipped), not measured live",
                        "peak_kind": "FFMA microkernel timed in this run (abr_ffma_peak)",
                        "peak_nominal": NOMINAL_FP32_TFLOPS, "frac_of_nominal": achieved_tf / NOMINAL_FP32_TFLOPS,
                        "flop_per_world_step": F_WS,
